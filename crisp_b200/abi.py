@@ -1,0 +1,334 @@
+"""ctypes mirror of include/crispgpu.h — the C ABI of the B200 statistics engine.
+
+Every structure here is field-for-field the one declared in include/crispgpu.h (which cites the
+reference interface each field replaces: `struct VARIANT`, parsebam/variant.h:50-95, and the option
+globals of optionparser.c:17-136).  `Batch` is the host-side struct-of-arrays container a front end
+fills where the reference calls newCRISPcaller (variantcalls.c:115).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+ABI_VERSION = 1
+MAXALLELES = 8
+NCOUNT = 24
+MAXSLOTS = 5
+
+SLOT_UNTESTED, SLOT_REJECT_AF, SLOT_REJECT_CT, SLOT_NOCALL, SLOT_CALLED = range(5)
+
+OK = 0
+ERR_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_TICKET = -1, -2, -3, -4, -5, -6
+
+ALTREAD_DTYPE = np.dtype(
+    [("pool", "<u2"), ("offset", "<u2"), ("aligned", "<u2"), ("strand", "u1"), ("pad", "u1")]
+)
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("n_pools", C.c_int32),
+        ("ploidy", C.POINTER(C.c_int32)),
+        ("varpoolsize", C.c_int32),
+        ("em_flag", C.c_int32),
+        ("max_iter", C.c_int32),
+        ("chisq_permutation", C.c_int32),
+        ("fast_filter", C.c_int32),
+        ("use_base_qvs", C.c_int32),
+        ("min_reads", C.c_int32),
+        ("qv_offset", C.c_int32),
+        ("min_q", C.c_int32),
+        ("pivot_sample", C.c_int32),
+        ("association", C.c_int32),
+        ("phenotypes", C.POINTER(C.c_int32)),
+        ("thresh1", C.c_double),
+        ("min_qpv", C.c_double),
+        ("thresh3", C.c_double),
+        ("ser", C.c_double),
+        ("relax", C.c_double),
+        ("qmin", C.c_double),
+        ("agilent_ref_bias", C.c_double),
+        ("theta", C.c_double),
+        ("rng_seed", C.c_uint64),
+        ("exact_mode", C.c_int32),
+        ("use_qv", C.c_int32),
+    ]
+
+
+class CBatch(C.Structure):
+    _fields_ = [
+        ("n_sites", C.c_int32),
+        ("reserved", C.c_int32),
+        ("tid", C.c_void_p),
+        ("pos", C.c_void_p),
+        ("refbase", C.c_void_p),
+        ("maxvec_al", C.c_void_p),
+        ("maxvec_ct", C.c_void_p),
+        ("counts", C.c_void_p),
+        ("indcounts", C.c_void_p),
+        ("indel_len", C.c_void_p),
+        ("hplen", C.c_void_p),
+        ("read_off", C.c_void_p),
+        ("reads", C.c_void_p),
+        ("alt_off", C.c_void_p),
+        ("alt_reads", C.c_void_p),
+        ("amb_idx", C.c_void_p),
+        ("amb_dec", C.c_void_p),
+        ("amb_ep", C.c_void_p),
+        ("n_amb", C.c_int32),
+        ("reserved2", C.c_int32),
+        ("qhigh", C.c_void_p),
+        ("stats", C.c_void_p),
+        ("tstats", C.c_void_p),
+    ]
+
+
+_RESULT_FIELDS = [
+    # name, numpy dtype, per-(site) width (5 = per slot, 1 = per site)
+    ("varalleles", np.int32, 1),
+    ("strandpass", np.int32, 1),
+    ("status", np.uint8, 5),
+    ("allele", np.uint8, 5),
+    ("call_rank", np.int8, 5),
+    ("call_row", np.int32, 5),
+    ("paf", np.float64, 5),
+    ("ctpval", np.float64, 5),
+    ("chi2pval", np.float64, 5),
+    ("af_ml", np.float64, 5),
+    ("delta", np.float64, 5),
+    ("deltaf", np.float64, 5),
+    ("hwe", np.float64, 5),
+    ("qvpf", np.float64, 5),
+    ("qvpr", np.float64, 5),
+    ("varpools", np.int32, 5),
+    ("allelecount", np.int32, 5),
+    ("variantpools", np.int32, 5),
+    ("em_iters", np.int32, 5),
+    ("perm_k", np.int32, 5),
+    ("perm_hits", np.int32, 5),
+]
+
+
+class CResults(C.Structure):
+    _fields_ = (
+        [("n_sites", C.c_int32), ("n_calls", C.c_int32)]
+        + [(name, C.c_void_p) for name, _, _ in _RESULT_FIELDS]
+        + [("ac", C.c_void_p), ("qv", C.c_void_p)]
+    )
+
+
+class Timing(C.Structure):
+    _fields_ = [
+        ("h2d_ms", C.c_float),
+        ("evaluate_ms", C.c_float),
+        ("permute_ms", C.c_float),
+        ("filter_ms", C.c_float),
+        ("em_ms", C.c_float),
+        ("legacy_ms", C.c_float),
+        ("d2h_ms", C.c_float),
+        ("total_ms", C.c_float),
+        ("n_tasks_em", C.c_int32),
+        ("n_tasks_perm", C.c_int32),
+        ("launches", C.c_int64),
+        ("h2d_bytes", C.c_int64),
+        ("d2h_bytes", C.c_int64),
+    ]
+
+
+def default_config_dict() -> dict:
+    """The reference's defaults (readmultiplebams.c:21-47, newcrispcaller.c:20-32, crispEM.c:14,26)."""
+    return dict(
+        varpoolsize=0, em_flag=1, max_iter=20000, chisq_permutation=0, fast_filter=1, use_base_qvs=1,
+        min_reads=4, qv_offset=33, min_q=13, pivot_sample=0, association=0, thresh1=-3.5, min_qpv=-5.0,
+        thresh3=-2.0, ser=-1.0, relax=0.75, qmin=23.0, agilent_ref_bias=0.5, theta=0.001, rng_seed=1,
+        exact_mode=0, use_qv=0,
+    )
+
+
+@dataclass
+class EngineConfig:
+    """Python-side configuration; `to_c()` snapshots it into the ABI struct."""
+
+    ploidy: np.ndarray
+    options: dict = field(default_factory=dict)
+    phenotypes: Optional[np.ndarray] = None
+
+    def __post_init__(self):
+        self.ploidy = np.ascontiguousarray(self.ploidy, dtype=np.int32)
+        opts = default_config_dict()
+        unknown = set(self.options) - set(opts)
+        if unknown:
+            raise KeyError(f"unknown engine options: {sorted(unknown)}")
+        opts.update(self.options)
+        if "varpoolsize" not in self.options:
+            # init_poolsizes (init_variant.c:143-151): 1 when adjacent pool sizes differ
+            opts["varpoolsize"] = int(np.any(self.ploidy[1:] != self.ploidy[:-1]))
+        self.options = opts
+        if self.phenotypes is not None:
+            self.phenotypes = np.ascontiguousarray(self.phenotypes, dtype=np.int32)
+
+    @property
+    def n_pools(self) -> int:
+        return int(self.ploidy.shape[0])
+
+    def to_c(self) -> Config:
+        cfg = Config()
+        cfg.abi_version = ABI_VERSION
+        cfg.n_pools = self.n_pools
+        cfg.ploidy = self.ploidy.ctypes.data_as(C.POINTER(C.c_int32))
+        cfg.phenotypes = (
+            self.phenotypes.ctypes.data_as(C.POINTER(C.c_int32)) if self.phenotypes is not None else None
+        )
+        for k, v in self.options.items():
+            setattr(cfg, k, v)
+        cfg._keep = (self.ploidy, self.phenotypes)
+        return cfg
+
+
+_BATCH_ARRAYS = [
+    # name, dtype, required
+    ("tid", np.int32, True),
+    ("pos", np.int32, True),
+    ("refbase", np.uint8, True),
+    ("maxvec_al", np.uint8, True),
+    ("maxvec_ct", np.int32, True),
+    ("counts", np.int32, True),
+    ("indcounts", np.int32, True),
+    ("indel_len", np.int16, False),
+    ("hplen", np.int16, False),
+    ("read_off", np.uint32, True),
+    ("reads", np.uint16, True),
+    ("alt_off", np.uint32, False),
+    ("alt_reads", ALTREAD_DTYPE, False),
+    ("amb_idx", np.int32, False),
+    ("amb_dec", np.int32, False),
+    ("amb_ep", np.float64, False),
+    ("qhigh", np.float64, False),
+    ("stats", np.float64, False),
+    ("tstats", np.float64, False),
+]
+
+
+class Batch:
+    """Struct-of-arrays batch of candidate sites (`crispgpu_batch`)."""
+
+    def __init__(self, n_pools: int, **arrays):
+        self.n_pools = int(n_pools)
+        for name, dt, req in _BATCH_ARRAYS:
+            a = arrays.pop(name, None)
+            if a is None:
+                if req:
+                    raise ValueError(f"batch array {name!r} is required")
+                setattr(self, name, None)
+                continue
+            setattr(self, name, np.ascontiguousarray(a, dtype=dt))
+        if arrays:
+            raise KeyError(f"unknown batch arrays: {sorted(arrays)}")
+        self.n_sites = int(self.tid.shape[0])
+        self.validate()
+
+    def validate(self) -> None:
+        n, P = self.n_sites, self.n_pools
+        def want(name, size):
+            a = getattr(self, name)
+            if a is not None and a.size != size:
+                raise ValueError(f"batch array {name!r}: {a.size} elements, expected {size}")
+        want("pos", n); want("refbase", n); want("maxvec_al", n * 8); want("maxvec_ct", n * 8)
+        want("counts", n * 24); want("indcounts", n * P * 24); want("indel_len", n * 8); want("hplen", n * 8)
+        want("read_off", n * P + 1); want("alt_off", n * 5 + 1); want("amb_idx", n * 5)
+        want("qhigh", n * P * 16); want("stats", n * P * 16); want("tstats", n * 16)
+        if n and int(self.read_off[-1]) != self.reads.size:
+            raise ValueError("read_off[-1] != len(reads)")
+        if self.alt_off is not None and (self.alt_reads is None or int(self.alt_off[-1]) != self.alt_reads.size):
+            raise ValueError("alt_off[-1] != len(alt_reads)")
+        self.n_amb = 0
+        if self.amb_idx is not None:
+            self.n_amb = int(self.amb_idx.max(initial=-1)) + 1
+            if self.n_amb:
+                want("amb_dec", self.n_amb * P * 4); want("amb_ep", self.n_amb * P * 2)
+
+    def nbytes(self) -> int:
+        return sum(getattr(self, name).nbytes for name, _, _ in _BATCH_ARRAYS if getattr(self, name) is not None)
+
+    def as_c(self) -> CBatch:
+        b = CBatch()
+        b.n_sites = self.n_sites
+        b.n_amb = self.n_amb
+        for name, _, _ in _BATCH_ARRAYS:
+            a = getattr(self, name)
+            setattr(b, name, a.ctypes.data if a is not None else None)
+        b._keep = self
+        return b
+
+    def select(self, idx) -> "Batch":
+        """Sub-batch of the given site indices (used by the region sharder and the tests)."""
+        idx = np.asarray(idx, dtype=np.int64)
+        P = self.n_pools
+        out = {}
+        for name in ("tid", "pos", "refbase"):
+            out[name] = getattr(self, name)[idx]
+        for name, w in (("maxvec_al", 8), ("maxvec_ct", 8), ("counts", 24), ("indcounts", P * 24),
+                        ("indel_len", 8), ("hplen", 8), ("qhigh", P * 16), ("stats", P * 16), ("tstats", 16)):
+            a = getattr(self, name)
+            if a is not None:
+                out[name] = a.reshape(self.n_sites, w)[idx].reshape(-1)
+        # ragged: reads
+        ro = self.read_off.astype(np.int64)
+        lo, hi = ro[idx * P], ro[idx * P + P]
+        seg = [self.reads[a:b] for a, b in zip(lo, hi)]
+        out["reads"] = np.concatenate(seg) if seg else np.zeros(0, np.uint16)
+        per = (ro.reshape(-1)[1:] - ro.reshape(-1)[:-1]).reshape(self.n_sites, P)[idx].reshape(-1)
+        out["read_off"] = np.concatenate([[0], np.cumsum(per)]).astype(np.uint32)
+        if self.alt_off is not None:
+            ao = self.alt_off.astype(np.int64)
+            seg = [self.alt_reads[ao[s * 5]:ao[s * 5 + 5]] for s in idx]
+            out["alt_reads"] = np.concatenate(seg) if seg else np.zeros(0, ALTREAD_DTYPE)
+            per = (ao[1:] - ao[:-1]).reshape(self.n_sites, 5)[idx].reshape(-1)
+            out["alt_off"] = np.concatenate([[0], np.cumsum(per)]).astype(np.uint32)
+        if self.amb_idx is not None:
+            ai = self.amb_idx.reshape(self.n_sites, 5)[idx].reshape(-1).copy()
+            used = np.unique(ai[ai >= 0])
+            remap = -np.ones(max(self.n_amb, 1), dtype=np.int32)
+            remap[used] = np.arange(used.size, dtype=np.int32)
+            ai[ai >= 0] = remap[ai[ai >= 0]]
+            out["amb_idx"] = ai
+            if used.size:
+                out["amb_dec"] = self.amb_dec.reshape(self.n_amb, P * 4)[used].reshape(-1)
+                if self.amb_ep is not None:
+                    out["amb_ep"] = self.amb_ep.reshape(self.n_amb, P * 2)[used].reshape(-1)
+        return Batch(P, **out)
+
+
+class Results:
+    """Owning numpy copy of a `crispgpu_results` block."""
+
+    def __init__(self, n_sites: int, n_pools: int, max_calls: Optional[int] = None):
+        self.n_sites, self.n_pools = n_sites, n_pools
+        self.n_calls = 0
+        self.max_calls = n_sites * 5 if max_calls is None else max_calls
+        for name, dt, w in _RESULT_FIELDS:
+            setattr(self, name, np.zeros((n_sites, w) if w > 1 else (n_sites,), dtype=dt))
+        self.ac = np.zeros((self.max_calls, n_pools), np.int32)
+        self.qv = np.zeros((self.max_calls, n_pools), np.float64)
+
+    @classmethod
+    def from_c(cls, cres: CResults, n_pools: int) -> "Results":
+        n = cres.n_sites
+        r = cls(n, n_pools, max_calls=max(cres.n_calls, 0))
+        r.n_calls = cres.n_calls
+        for name, dt, w in _RESULT_FIELDS:
+            ptr = getattr(cres, name)
+            dst = getattr(r, name)
+            if ptr and dst.size:
+                C.memmove(dst.ctypes.data, ptr, dst.nbytes)
+        if r.n_calls:
+            C.memmove(r.ac.ctypes.data, cres.ac, r.ac.nbytes)
+            C.memmove(r.qv.ctypes.data, cres.qv, r.qv.nbytes)
+        return r
+
+    def called_sites(self) -> np.ndarray:
+        return np.nonzero(self.varalleles >= 1)[0]

@@ -1,0 +1,238 @@
+/*
+ * crispgpu.h — C ABI of the B200 statistics engine for CRISP candidate sites.
+ *
+ * This is the drop-in boundary.  The reference (vibansal/crisp) has no plugin /
+ * FFI interface: its per-site statistics engine is entered by one direct call,
+ *     v = newCRISPcaller(reflist,current,position,bq,bamfiles_data,variant,maxvec,vfile)
+ *                                                   (variantcalls.c:115, prototype crisp/crispcaller.h:21)
+ * which reads `struct VARIANT` (parsebam/variant.h:50-95) plus the live read queue and
+ * writes its outputs back into `struct VARIANT` before print_pooledvariant()
+ * (crisp/newcrispprint.c:347) formats the VCF record.  The functions below replace that
+ * call for a *batch* of candidate sites: the host front end (parsebam/, unchanged C)
+ * packs the fields of `struct VARIANT` and the three read-queue snapshots the engine
+ * needs into the struct-of-arrays `crispgpu_batch`, the GPU computes everything
+ * newCRISPcaller would have computed, and `crispgpu_results` returns exactly the fields
+ * print_pooledvariant() consumes (newcrispprint.c:357-473, 248-298).
+ *
+ * Plain C, plain pointers and sizes; no C++ or torch types.  All functions return 0 on
+ * success or a negative crispgpu_status; no exceptions, nothing is written to stdout.
+ * There is no CPU fallback: if no CUDA device is usable crispgpu_create() fails.
+ */
+#ifndef CRISPGPU_H
+#define CRISPGPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRISPGPU_ABI_VERSION 1
+
+#define CRISPGPU_MAXALLELES 8  /* `maxalleles`, readmultiplebams.c:27: A,C,G,T + indel slots 4..6 */
+#define CRISPGPU_NCOUNT 24     /* 3 strand classes x 8 alleles: index = allele + s*8, s=0 fwd,1 rev,2 bidirectional
+                                  (parsebam/variant.c:301-312) */
+#define CRISPGPU_MAXSLOTS 5    /* alleles maxvec[1..5] are tested, newcrispcaller.c:205 */
+#define CRISPGPU_NCHISTAT 5
+
+typedef enum crispgpu_status {
+	CRISPGPU_OK = 0,
+	CRISPGPU_ERR_ARG = -1,       /* NULL pointer, bad size, inconsistent offsets */
+	CRISPGPU_ERR_NO_DEVICE = -2, /* no usable CUDA device (there is no CPU fallback) */
+	CRISPGPU_ERR_CUDA = -3,      /* CUDA runtime error; see crispgpu_last_error() */
+	CRISPGPU_ERR_NOMEM = -4,
+	CRISPGPU_ERR_UNSUPPORTED = -5, /* configuration needs an input array the batch does not carry */
+	CRISPGPU_ERR_TICKET = -6
+} crispgpu_status;
+
+/* Snapshot of the reference's global option variables that reach the engine
+ * (optionparser.c:17-136).  Field comments name the reference global. */
+typedef struct crispgpu_config {
+	int32_t abi_version;       /* must be CRISPGPU_ABI_VERSION */
+	int32_t n_pools;           /* variant->samples */
+	const int32_t* ploidy;     /* variant->ploidy[n_pools]  (--poolsize / PS=)  init_variant.c:135 */
+	int32_t varpoolsize;       /* variant->varpoolsize: 1 if pool sizes differ (HWE skipped, crispEM.c:187) */
+	int32_t em_flag;           /* EMflag (--EM), newcrispcaller.c:32 : 1 = EM caller, 0 = legacy caller */
+	int32_t max_iter;          /* MAXITER (--perms), newcrispcaller.c:21 */
+	int32_t chisq_permutation; /* CHISQ_PERMUTATION (--chisquare 0 sets 1), FET/contables.c:11 */
+	int32_t fast_filter;       /* FAST_FILTER, newcrispcaller.c:24 */
+	int32_t use_base_qvs;      /* USE_BASE_QVS (--usebq), newcrispcaller.c:20 */
+	int32_t min_reads;         /* MIN_READS (--minc), newcrispcaller.c:23 */
+	int32_t qv_offset;         /* QVoffset, readmultiplebams.c:25 */
+	int32_t min_q;             /* MINQ (--mbq), readmultiplebams.c:26 */
+	int32_t pivot_sample;      /* PIVOTSAMPLE (--pivotsample), readmultiplebams.c:46 */
+	int32_t association;       /* options->association (--phenotypes given), crispEM.c:383 */
+	const int32_t* phenotypes; /* options->phenotypes[n_pools] bit mask 1 control/2 case/4 early; may be NULL */
+	double thresh1;            /* --ctpval  (-3.5), newcrispcaller.c:22 */
+	double min_qpv;            /* MINQpv, --qvpval (-5) */
+	double thresh3;            /* thresh3 (-2) */
+	double ser;                /* SER (-e) (-1) */
+	double relax;              /* RELAX (0.75) */
+	double qmin;               /* Qmin (23) */
+	double agilent_ref_bias;   /* AGILENT_REF_BIAS (--refbias) 0.5, crispEM.c:26 */
+	double theta;              /* THETA 0.001, crispEM.c:14 */
+	/* engine-only switches (no reference counterpart) */
+	uint64_t rng_seed;         /* key of the counter-based RNG; results are a pure function of
+	                              (rng_seed, tid, pos, slot), independent of batching and GPU count */
+	int32_t exact_mode;        /* 1: small 2xk tables use exact enumeration (FET/contables_exact.c:62-117 gate) */
+	int32_t use_qv;            /* USE_QV (--weighted), readmultiplebams.c:24: how remove_ambiguous_bases adjusts Qhighcounts */
+} crispgpu_config;
+
+/* One packed read of the per-site pileup snapshot: what calculate_pooled_likelihoods_snp
+ * (crisp/crispEM.c:104-136) reads from `struct alignedread`.  Only reads with
+ * filter=='0' && type==0 are packed (others contribute nothing there).
+ *   bits 0-7   quality char  bcall->quality[l1+delta]   (post-OPE value, still +33, bamread.c:124)
+ *   bits 8-9   BTI[bcall->sequence[l1+delta]]  0..3
+ *   bit  10    bcall->strand != 0
+ *   bit  11    bcall->bidir == 1
+ * Reads are grouped by pool: reads of (site s, pool i) are read_off[s*P+i] .. read_off[s*P+i+1]. */
+typedef uint16_t crispgpu_read;
+#define CRISPGPU_READ(qualchar, base, rev, bidir) \
+	((uint16_t)(((qualchar) & 0xff) | (((base) & 3) << 8) | (((rev) ? 1 : 0) << 10) | (((bidir) ? 1 : 0) << 11)))
+
+/* One alternate-allele read as calculate_uniquereads (parsebam/allelecounts.c:50-77) sees it. */
+typedef struct crispgpu_altread {
+	uint16_t pool;    /* sample */
+	uint16_t offset;  /* bcall->l1 + bcall->delta */
+	uint16_t aligned; /* bcall->alignedbases */
+	uint8_t strand;   /* bcall->strand */
+	uint8_t pad;
+} crispgpu_altread;
+
+/* Struct-of-arrays batch of n_sites candidate sites (sites that passed variantcalls.c:76-92).
+ * P = config.n_pools.  All arrays are caller-owned host memory (pinned memory from
+ * crispgpu_host_alloc makes the copies asynchronous) and must stay valid until crispgpu_wait(). */
+typedef struct crispgpu_batch {
+	int32_t n_sites;
+	int32_t reserved;
+	const int32_t* tid;         /* [n]     reference id  (pass-through key, RNG key) */
+	const int32_t* pos;         /* [n]     variant->position (0-based) */
+	const uint8_t* refbase;     /* [n]     variant->refbase 0..3 */
+	const uint8_t* maxvec_al;   /* [n][8]  maxvec[k].al after sort_allelecounts (allelecounts.c:155) */
+	const int32_t* maxvec_ct;   /* [n][8]  maxvec[k].ct */
+	const int32_t* counts;      /* [n][24] variant->counts */
+	const int32_t* indcounts;   /* [n][P][24] variant->indcounts[i][0..3A) */
+	const int16_t* indel_len;   /* [n][8]  alleles>=4: +len for "+XX", -len for "-XX" (strlen(itb[a])-1), else 0; may be NULL if no indels */
+	const int16_t* hplen;       /* [n][8]  variant->HPlength[a] (calculate_indel_ambiguity); may be NULL */
+	const uint32_t* read_off;   /* [n*P+1] */
+	const crispgpu_read* reads; /* [read_off[n*P]] */
+	/* calculate_uniquereads inputs: for (site s, slot k=al-1): alt_off[s*5+k] .. alt_off[s*5+k+1],
+	 * entries sorted by pool, at most (alt read count of the pool) entries per pool. */
+	const uint32_t* alt_off;    /* [n*5+1] */
+	const crispgpu_altread* alt_reads;
+	/* what remove_ambiguous_bases(bq,variant,HPlength[allele2],+1) (process_indel_variant.c:20-66) subtracts
+	 * from the reference-base counts before an indel allele is evaluated: amb_idx[s*5+k] = -1 (none) or row r,
+	 * amb_dec[r][i][0..3] = number of removed reference reads of pool i that are {forward, reverse,
+	 * bidirectional with strand 0, bidirectional with strand 1} (:39-48: the first two come off
+	 * indcounts[i][refbase], [refbase+8], the last two off [refbase+16]; Qhighcounts/stats come off by strand, :57-60).
+	 * amb_ep[r][i][0..1] = sum of 10^(-q/10) over the removed reads of strand 0 / 1 (only read when
+	 * stats or weighted Qhighcounts are in use).  May be NULL. */
+	const int32_t* amb_idx;     /* [n][5] */
+	const int32_t* amb_dec;     /* [n_amb][P][4] */
+	const double* amb_ep;       /* [n_amb][P][2] or NULL */
+	int32_t n_amb;
+	int32_t reserved2;
+	/* optional real-valued pileup sums (NULL unless needed):
+	 *   qhigh  variant->Qhighcounts[i][0..2A)  read when chisq_permutation=1 (chi2pvalue, FET/chisquare.c:16);
+	 *          NULL means Qhighcounts[i][a+8s] = indcounts[i][a+8s], s=0,1 (exact when there are no
+	 *          bidirectional reads and --weighted is off, parsebam/variant.c:318-320)
+	 *   stats  variant->stats[i][0..2A), tstats variant->tstats[0..2A)  needed when em_flag=0 (chernoff_bound);
+	 *          NULL means zeros */
+	const double* qhigh;        /* [n][P][16] */
+	const double* stats;        /* [n][P][16] */
+	const double* tstats;       /* [n][16] */
+} crispgpu_batch;
+
+/* Per tested allele slot (al = slot+1 of maxvec), state of the reference's per-allele loop
+ * (newcrispcaller.c:205-246). */
+enum {
+	CRISPGPU_SLOT_UNTESTED = 0,  /* maxvec[al].ct < 3 */
+	CRISPGPU_SLOT_REJECT_AF = 1, /* evaluate_variant returned 0 at the p[0] filter (newcrispcaller.c:72) */
+	CRISPGPU_SLOT_REJECT_CT = 2, /* evaluate_variant returned 0 at the homopolymer / FAST_FILTER tests (:108-127) */
+	CRISPGPU_SLOT_NOCALL = 3,    /* reached the caller (EM or legacy) but was not called a variant */
+	CRISPGPU_SLOT_CALLED = 4     /* variant allele: occupies index `call_rank` of the site's varalleles list */
+};
+
+/* Results for the batch.  Arrays are owned by the context (pinned host memory) and stay valid
+ * until the next crispgpu_submit()/crispgpu_destroy() on that context. */
+typedef struct crispgpu_results {
+	int32_t n_sites;
+	int32_t n_calls;            /* total called alleles in the batch = rows of ac/qv */
+	const int32_t* varalleles;  /* [n]    variant->varalleles : >=1  <=> a VCF record is printed */
+	const int32_t* strandpass;  /* [n]    variant->strandpass (EM 0 only) */
+	/* per (site, slot) — [n][5] */
+	const uint8_t* status;      /* CRISPGPU_SLOT_* */
+	const uint8_t* allele;      /* allele2 = maxvec[al].al */
+	const int8_t* call_rank;    /* index into variant->alleles[]/crispvar[] or -1 */
+	const int32_t* call_row;    /* row of ac/qv or -1 */
+	const double* paf;          /* p[0] initial AF estimate of evaluate_variant (x ploidy sum) */
+	const double* ctpval;       /* variant->ctpval[]   (VCF CT=) */
+	const double* chi2pval;     /* variant->chi2pval[] */
+	const double* af_ml;        /* crispvar[].AF_ML   (VCF AF=) */
+	const double* delta;        /* crispvar[].delta   (VCF QUAL, EMstats) */
+	const double* deltaf;       /* crispvar[].deltaf  (EMstats, VF=) */
+	const double* hwe;          /* crispvar[].deltar = log10 HWE p (HWEstats) */
+	const double* qvpf;         /* variant->qvpvaluef[] (EM 0) */
+	const double* qvpr;         /* variant->qvpvaluer[] (EM 0) */
+	const int32_t* varpools;    /* variant->varpools[] = nvariants[] (VCF VP=) */
+	const int32_t* allelecount; /* crispvar[].allelecount (VCF AC=) */
+	const int32_t* variantpools;/* crispvar[].variantpools */
+	const int32_t* em_iters;    /* EM iterations executed (diagnostic) */
+	const int32_t* perm_k;      /* permutations executed (stop index) (diagnostic) */
+	const int32_t* perm_hits;   /* hits at stop (diagnostic) */
+	/* per called allele — [n_calls][P] */
+	const int32_t* ac;          /* crispvar[].AC[i]  (bit-exact) */
+	const double* qv;           /* crispvar[].QV[i] */
+} crispgpu_results;
+
+/* Device timings of the last completed batch, CUDA events on the engine's stream (ms). */
+typedef struct crispgpu_timing {
+	float h2d_ms;
+	float evaluate_ms;   /* evaluate_variant + contingency-table p-values (asymptotic) */
+	float permute_ms;    /* permutation / exact p-value kernel */
+	float filter_ms;     /* FAST_FILTER + task compaction */
+	float em_ms;         /* likelihood + EM + genotypes + pool statistics */
+	float legacy_ms;     /* --EM 0 caller */
+	float d2h_ms;
+	float total_ms;      /* first H2D byte to last D2H byte (kernels only for resident runs) */
+	int32_t n_tasks_em;  /* (site,slot) tasks that reached the EM kernel */
+	int32_t n_tasks_perm;
+	int64_t launches;    /* kernels launched for the batch */
+	int64_t h2d_bytes;
+	int64_t d2h_bytes;
+} crispgpu_timing;
+
+typedef struct crispgpu_ctx crispgpu_ctx;
+
+/* Fill *cfg with the reference's defaults (readmultiplebams.c:21-47, newcrispcaller.c:20-32). */
+void crispgpu_config_defaults(crispgpu_config* cfg);
+
+/* Create an engine bound to CUDA device `device_id`.  `stream` may be a cudaStream_t the caller
+ * owns (e.g. torch's current stream) or NULL for a private stream. */
+int crispgpu_create(const crispgpu_config* cfg, int device_id, void* stream, crispgpu_ctx** out);
+void crispgpu_destroy(crispgpu_ctx* ctx);
+
+/* Asynchronous: copy the batch to the device, run the engine, copy results back.  One batch
+ * may be in flight per context. */
+int crispgpu_submit(crispgpu_ctx* ctx, const crispgpu_batch* batch, int64_t* ticket);
+int crispgpu_wait(crispgpu_ctx* ctx, int64_t ticket, crispgpu_results* out);
+
+/* Device-resident path used to time the kernels alone: upload once, run many times. */
+int crispgpu_upload(crispgpu_ctx* ctx, const crispgpu_batch* batch);
+int crispgpu_run_resident(crispgpu_ctx* ctx, int fetch_results, crispgpu_results* out);
+
+int crispgpu_get_timing(crispgpu_ctx* ctx, crispgpu_timing* out);
+const char* crispgpu_last_error(crispgpu_ctx* ctx);
+
+/* Pinned host memory for batch arrays. */
+void* crispgpu_host_alloc(size_t bytes);
+void crispgpu_host_free(void* p);
+
+int crispgpu_abi_version(void);
+int crispgpu_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRISPGPU_H */

@@ -1,0 +1,153 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes loaders for the two CPU checkers.
+
+  RefEngine     oracle/_ref/libcrispref.so : the UNMODIFIED reference engine (built by oracle/Makefile from
+                /root/reference) driven by oracle/ref_harness.c
+  OracleEngine  oracle/liboracle.so        : oracle/crisp_oracle.c, the plain-C restatement
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this module;
+nothing under crisp_b200/ does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from crisp_b200.abi import _RESULT_FIELDS, Batch, CBatch, Config, EngineConfig, Results
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_LIB = os.path.join(HERE, "_ref", "libcrispref.so")
+ORACLE_LIB = os.path.join(HERE, "liboracle.so")
+
+MODE_SLOTS, MODE_CALLER = 0, 1
+RNG_DRAND48, RNG_PHILOX = 0, 1
+
+
+class HostResults(C.Structure):
+    _fields_ = (
+        [("n_sites", C.c_int32), ("n_calls", C.c_int32), ("max_calls", C.c_int32), ("reserved", C.c_int32)]
+        + [(name, C.c_void_p) for name, _, _ in _RESULT_FIELDS]
+        + [("ac", C.c_void_p), ("qv", C.c_void_p), ("genll", C.c_void_p), ("genll_stride", C.c_int32),
+           ("reserved2", C.c_int32)]
+    )
+
+
+def build(force: bool = False) -> None:
+    """Compile liboracle.so and, when /root/reference is present, oracle/_ref/libcrispref.so."""
+    args = ["make", "-s", "-C", HERE]
+    if force:
+        args.append("-B")
+    subprocess.run(args + ["all"], check=True)
+
+
+def _host_results(res: Results, genll: np.ndarray | None) -> HostResults:
+    h = HostResults()
+    h.n_sites = res.n_sites
+    h.max_calls = res.max_calls
+    for name, _, _ in _RESULT_FIELDS:
+        setattr(h, name, getattr(res, name).ctypes.data)
+    h.ac = res.ac.ctypes.data
+    h.qv = res.qv.ctypes.data
+    if genll is not None:
+        h.genll = genll.ctypes.data
+        h.genll_stride = genll.shape[-1]
+    return h
+
+
+class _CpuEngine:
+    lib_path = ""
+    prefix = ""
+
+    def __init__(self, cfg: EngineConfig):
+        if not os.path.exists(self.lib_path):
+            raise FileNotFoundError(f"{self.lib_path} not built (run `make -C oracle`)")
+        self.lib = C.CDLL(self.lib_path)
+        self.cfg = cfg
+        self._ccfg = cfg.to_c()
+        create = getattr(self.lib, self.prefix + "_create")
+        create.restype = C.c_void_p
+        create.argtypes = [C.POINTER(Config)]
+        self.h = create(C.byref(self._ccfg))
+        if not self.h:
+            raise RuntimeError("oracle create failed")
+        self._run = getattr(self.lib, self.prefix + "_run")
+        self._run.restype = C.c_int
+        self._run.argtypes = [C.c_void_p, C.POINTER(CBatch), C.POINTER(HostResults), C.c_int, C.c_long,
+                              C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        self._err = getattr(self.lib, self.prefix + "_last_error")
+        self._err.restype = C.c_char_p
+        self._err.argtypes = [C.c_void_p]
+
+    def run(self, batch: Batch, mode: int = MODE_SLOTS, seed: int = 1, want_vcf: bool = False,
+            want_genll: bool = False):
+        res = Results(batch.n_sites, batch.n_pools)
+        genll = None
+        if want_genll:
+            genll = np.zeros((batch.n_sites, 5, 4, batch.n_pools, int(self.cfg.ploidy.max()) + 1))
+        h = _host_results(res, genll)
+        cb = batch.as_c()
+        cap = (1 << 16) + batch.n_sites * (512 + 64 * batch.n_pools) if want_vcf else 0
+        buf = C.create_string_buffer(cap) if cap else None
+        ln = C.c_size_t(0)
+        rc = self._run(self.h, C.byref(cb), C.byref(h), mode, seed, buf, cap, C.byref(ln))
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}_run failed rc={rc}: {self._err(self.h).decode()}")
+        res.n_calls = h.n_calls
+        res.ac = res.ac[: res.n_calls]
+        res.qv = res.qv[: res.n_calls]
+        res.vcf = buf.value.decode() if buf is not None else None
+        res.genll = genll
+        return res
+
+
+class RefEngine(_CpuEngine):
+    lib_path = REF_LIB
+    prefix = "crisp_ref"
+
+    def replay_vcf(self, batch: Batch, res: Results) -> str:
+        fn = self.lib.crisp_ref_replay_vcf
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.POINTER(CBatch), C.POINTER(HostResults), C.c_char_p, C.c_size_t,
+                       C.POINTER(C.c_size_t)]
+        full = Results(res.n_sites, res.n_pools, max_calls=max(res.n_calls, 1))
+        for name, _, _ in _RESULT_FIELDS:
+            getattr(full, name)[...] = getattr(res, name)
+        full.ac[: res.n_calls] = res.ac[: res.n_calls]
+        full.qv[: res.n_calls] = res.qv[: res.n_calls]
+        h = _host_results(full, None)
+        h.n_calls = res.n_calls
+        cb = batch.as_c()
+        cap = (1 << 16) + batch.n_sites * (512 + 64 * batch.n_pools)
+        buf = C.create_string_buffer(cap)
+        ln = C.c_size_t(0)
+        rc = fn(self.h, C.byref(cb), C.byref(h), buf, cap, C.byref(ln))
+        if rc != 0:
+            raise RuntimeError("replay failed")
+        return buf.value.decode()
+
+    def scalar(self, name: str, restype, argtypes):
+        fn = getattr(self.lib, "crisp_ref_" + name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+        return fn
+
+
+class OracleEngine(_CpuEngine):
+    lib_path = ORACLE_LIB
+    prefix = "crisp_oracle"
+
+    def scalar(self, name: str, restype, argtypes):
+        fn = getattr(self.lib, "crisp_oracle_" + name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+        return fn
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_LIB)
+
+
+def have_oracle() -> bool:
+    return os.path.exists(ORACLE_LIB)

@@ -1,0 +1,716 @@
+/*
+ * ref_harness.c — TEST INFRASTRUCTURE ONLY (never linked into, loaded by or shipped with crisp_b200/).
+ *
+ * Drives the UNMODIFIED reference engine (vibansal/crisp, compiled where it lies under
+ * /root/reference by oracle/Makefile into oracle/_ref/) on a `crispgpu_batch`, so that the CUDA
+ * engine and the C restatement (oracle/crisp_oracle.c) can be checked against what CRISP itself
+ * computes on identical inputs.  No reference source is copied: the reference's translation units
+ *     crisp/newcrispcaller.c  parsebam/variant.c  parsebam/allelecounts.c  FET/chisquare.c  FET/contables.c
+ * are compiled as they are, and this file only (a) defines the host globals they expect from
+ * readmultiplebams.c:17-54, (b) rebuilds `struct VARIANT` (parsebam/variant.h:50-95) and the read queue
+ * (`struct alignedread`, parsebam/bamread.h:17-43) from the batch, and (c) calls the reference entry points.
+ *
+ * Two drive modes:
+ *   CRISP_REF_MODE_SLOTS   the per-allele loop of newCRISPcaller (crisp/newcrispcaller.c:205-246) is walked here,
+ *                          calling the reference's evaluate_variant / compute_GLL_pooled / calculate_pool_statistics /
+ *                          pooled_variantcaller / remove_ambiguous_bases, so that every (site, slot) state is visible
+ *                          and HPlength can be taken from the batch;
+ *   CRISP_REF_MODE_CALLER  newCRISPcaller itself is called (SNP-only sites; HPlength is recomputed by the reference from
+ *                          a synthetic flanking sequence) — used to cross-check the slot walk and to obtain VCF text.
+ * In both modes the VCF record is produced by the reference's own print_pooledvariant (crisp/newcrispprint.c:347).
+ */
+#define _GNU_SOURCE
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+#include <fcntl.h>
+#include <math.h>
+
+#include "bamread.h"
+#include "bamsreader.h"
+#include "variant.h"
+#include "allelecounts.h"
+#include "contables.h"
+#include "crispcaller.h"
+
+#include "oracle_abi.h"
+
+/* ---- globals the engine objects leave undefined (values: readmultiplebams.c:21-47, bamread.c:3) ---- */
+int SOLID = 0;
+int QVset = 0;
+int USE_QV = 0;
+int QVoffset = 33;
+int MIN_M = 20, MAX_MM = 4;
+int MINQ = 13;
+int maxalleles = 8;
+int READLENGTH = 100;
+int MINFLANK = 5;
+int OVERLAPPING_PE_READS = 1;
+int INDEL_REALIGNMENT = 0;
+int PIVOTSAMPLE = 0;
+int PFLAG = 0;
+char INT_CIGAROP[] = {'M', 'I', 'D', 'N', 'S', 'H', 'P', '=', 'X'};
+int realign_read(struct BAMFILE_data* bd, int sample, struct alignedread* bcall, REFLIST* reflist) { return 0; }
+
+/* ---- engine globals and functions defined inside the reference objects ---- */
+extern int EMflag, FAST_FILTER, USE_BASE_QVS, MAXITER, MIN_READS, CHISQ_PERMUTATION;
+extern double thresh1, MINQpv, thresh3, SER, RELAX, Qmin, AGILENT_REF_BIAS, THETA;
+int evaluate_variant(READQUEUE* bq, struct VARIANT* variant, int allele1, int allele2, int allele3, double paf[]);
+int compute_GLL_pooled(READQUEUE* bq, struct VARIANT* variant, int allele1, int allele2, int allele3, double p[]);
+int calculate_pool_statistics(READQUEUE* bq, struct BAMFILE_data* bd, struct VARIANT* variant, int allele1, int allele2);
+int remove_ambiguous_bases(READQUEUE* bq, struct VARIANT* variant, int HPlength, int delta);
+int print_pooledvariant(struct VARIANT* variant, FILE* vfile, REFLIST* reflist, int current, ALLELE* maxvec, int EMflag);
+void calculate_pooled_likelihoods_snp(READQUEUE* bq, struct VARIANT* variant, int a1, int a2, int a3, double E01[], double E10[]);
+double ncr(int n, int r);
+double fet(int c1, int r1, int c2, int r2);
+double minreads_pvalue(int R, int A, double e);
+double binomial_pvalue(int R, int A, double e);
+double kf_lgamma(double z);
+double kf_gammaq(double s, double z);
+void chernoff_bound(int* counts, double* stats, int refbase, int altbase, double SER, double* P0, double* P1, int maxalleles);
+int pvalue_contable_iter_stranded(int** ctable, double** ctable_weighted, int* strata, int size, int maxiter, int** newtable, double* permp, double* chisqp, double chi2stats[]);
+int pvalue_lowcoverage(int** ctable, int size, int iter, struct acounts* atable, double* permp);
+
+enum { CRISP_REF_MODE_SLOTS = 0, CRISP_REF_MODE_CALLER = 1 };
+
+#define QBUFLEN 1024
+#define FLANK 64
+
+typedef struct ref_ctx {
+	crispgpu_config cfg;
+	int P, maxploidy;
+	int* ploidy;
+	int* phenotypes;
+	struct OPTIONS options;
+	struct VARIANT variant;
+	struct BAMFILE_data* bd;
+	READQUEUE rq;
+	struct alignedread* reads;
+	int reads_cap;
+	int* cigars;
+	char* basebuf[4];
+	char* qualbuf[256];
+	REFLIST reflist;
+	char* refname;
+	unsigned char* refseq;
+	int reflen;
+	char err[256];
+} ref_ctx;
+
+static const char BASES[4] = {'A', 'C', 'G', 'T'};
+
+static void apply_config(const ref_ctx* c)
+{
+	const crispgpu_config* g = &c->cfg;
+	EMflag = g->em_flag;
+	MAXITER = g->max_iter;
+	CHISQ_PERMUTATION = g->chisq_permutation;
+	FAST_FILTER = g->fast_filter;
+	USE_BASE_QVS = g->use_base_qvs;
+	MIN_READS = g->min_reads;
+	QVoffset = g->qv_offset;
+	MINQ = g->min_q;
+	PIVOTSAMPLE = g->pivot_sample;
+	thresh1 = g->thresh1;
+	MINQpv = g->min_qpv;
+	thresh3 = g->thresh3;
+	SER = g->ser;
+	RELAX = g->relax;
+	Qmin = g->qmin;
+	AGILENT_REF_BIAS = g->agilent_ref_bias;
+	THETA = g->theta;
+	USE_QV = g->use_qv;
+	PFLAG = 0;
+}
+
+void* crisp_ref_create(const crispgpu_config* cfg)
+{
+	if (!cfg || cfg->n_pools <= 0 || !cfg->ploidy) return NULL;
+	ref_ctx* c = (ref_ctx*)calloc(1, sizeof(ref_ctx));
+	c->cfg = *cfg;
+	c->P = cfg->n_pools;
+	c->ploidy = (int*)malloc(sizeof(int) * c->P);
+	for (int i = 0; i < c->P; i++) {
+		c->ploidy[i] = cfg->ploidy[i];
+		if (cfg->ploidy[i] > c->maxploidy) c->maxploidy = cfg->ploidy[i];
+	}
+	c->cfg.ploidy = c->ploidy;
+	c->phenotypes = (int*)calloc(c->P, sizeof(int));
+	if (cfg->phenotypes) for (int i = 0; i < c->P; i++) c->phenotypes[i] = cfg->phenotypes[i];
+	c->cfg.phenotypes = c->phenotypes;
+	memset(&c->options, 0, sizeof(c->options));
+	c->options.bamfiles = c->P;
+	c->options.samples = c->P;
+	c->options.association = cfg->association;
+	c->options.phenotypes = c->phenotypes;
+	c->options.ploidy = c->ploidy;
+	/* as multisampleVC does (readmultiplebams.c:84-87): ploidy first, then init_variant */
+	memset(&c->variant, 0, sizeof(c->variant));
+	c->variant.ploidy = (int*)calloc(c->P, sizeof(int));
+	for (int i = 0; i < c->P; i++) c->variant.ploidy[i] = c->ploidy[i];
+	c->variant.varpoolsize = cfg->varpoolsize;
+	apply_config(c);
+	init_variant(&c->variant, c->P, c->P);
+	c->variant.options = &c->options;
+	c->bd = (struct BAMFILE_data*)calloc(c->P, sizeof(struct BAMFILE_data));
+	for (int b = 0; b < 4; b++) {
+		c->basebuf[b] = (char*)malloc(QBUFLEN);
+		memset(c->basebuf[b], BASES[b], QBUFLEN);
+	}
+	/* synthetic flanking sequence for print_flanking_sequence / calculate_indel_ambiguity */
+	c->reflen = 2 * FLANK + 1;
+	c->refseq = (unsigned char*)malloc(c->reflen + 1);
+	c->refname = (char*)malloc(64);
+	c->reflist.ns = 1;
+	c->reflist.names = &c->refname;
+	c->reflist.lengths = &c->reflen;
+	c->reflist.sequences = &c->refseq;
+	return c;
+}
+
+void crisp_ref_destroy(void* h)
+{
+	/* the reference never frees struct VARIANT; the harness leaks it the same way (test process only) */
+	ref_ctx* c = (ref_ctx*)h;
+	if (!c) return;
+	free(c->reads);
+	free(c->cigars);
+	free(c->bd);
+	free(c);
+}
+
+static char* qual_buffer(ref_ctx* c, int q)
+{
+	q &= 0xff;
+	if (!c->qualbuf[q]) {
+		c->qualbuf[q] = (char*)malloc(QBUFLEN);
+		memset(c->qualbuf[q], q, QBUFLEN);
+	}
+	return c->qualbuf[q];
+}
+
+/* deterministic flanking sequence: position-hashed bases, site base = refbase, base after the site differs from it
+ * (so that the CALLER mode never finds a homopolymer); previousbase etc. come from here in both modes. */
+static void make_flank(ref_ctx* c, int tid, int pos, int refbase)
+{
+	for (int k = 0; k < c->reflen; k++) {
+		unsigned x = (unsigned)(pos + k - FLANK) * 2654435761u + (unsigned)tid * 40503u;
+		x ^= x >> 15;
+		c->refseq[k] = BASES[(x >> 7) & 3];
+	}
+	c->refseq[c->reflen] = 0;
+	c->refseq[FLANK] = BASES[refbase & 3];
+	snprintf(c->refname, 64, "chr%d", tid);
+}
+
+static void fill_site(ref_ctx* c, const crispgpu_batch* b, int s)
+{
+	struct VARIANT* v = &c->variant;
+	const int P = c->P;
+	v->position = FLANK; /* position inside the synthetic flank; the VCF column is patched by the caller */
+	v->refbase = b->refbase[s];
+	v->refb = BASES[v->refbase & 3];
+	v->IUPAC = 0;
+	snprintf(v->chrom, 64, "chr%d", b->tid[s]);
+	for (int a = 0; a < 4; a++) {
+		v->itb[a][0] = BASES[a];
+		v->itb[a][1] = 0;
+	}
+	for (int a = 4; a < 8; a++) {
+		int len = b->indel_len ? b->indel_len[s * 8 + a] : 0;
+		int L = len < 0 ? -len : len;
+		if (L > 1000) L = 1000;
+		v->itb[a][0] = len < 0 ? '-' : '+';
+		for (int k = 0; k < L; k++) v->itb[a][1 + k] = BASES[(a + k) & 3];
+		v->itb[a][1 + L] = 0;
+		if (len == 0) {
+			v->itb[a][0] = 'N';
+			v->itb[a][1] = 0;
+		}
+	}
+	for (int k = 0; k < 10; k++) v->HPlength[k] = 0;
+	if (b->hplen) for (int a = 0; a < 8; a++) v->HPlength[a] = b->hplen[s * 8 + a];
+	v->varalleles = 0;
+	v->strandpass = 0;
+	for (int q = 0; q < 32; q++) v->counts[q] = q < 24 ? b->counts[s * 24 + q] : 0;
+	for (int q = 0; q < 16; q++) v->tstats[q] = b->tstats ? b->tstats[s * 16 + q] : 0.0;
+	int total = 0;
+	for (int i = 0; i < P; i++) {
+		const int32_t* ic = b->indcounts + ((size_t)s * P + i) * 24;
+		int depth = 0;
+		for (int q = 0; q < 32; q++) v->indcounts[i][q] = q < 24 ? ic[q] : 0;
+		for (int q = 0; q < 24; q++) depth += ic[q];
+		v->readdepths[i] = depth;
+		total += depth;
+		for (int q = 0; q < 48; q++) v->Qhighcounts[i][q] = 0.0;
+		for (int q = 0; q < 16; q++) {
+			v->Qhighcounts[i][q] = b->qhigh ? b->qhigh[((size_t)s * P + i) * 16 + q] : (double)ic[q];
+			v->stats[i][q] = b->stats ? b->stats[((size_t)s * P + i) * 16 + q] : 0.0;
+		}
+	}
+	for (int k = 0; k < 8; k++) v->filteredreads[k] = 0;
+	v->MQcounts[0] = v->MQcounts[1] = v->MQcounts[2] = 0;
+	v->MQcounts[3] = total;
+	make_flank(c, b->tid[s], b->pos[s], v->refbase);
+}
+
+/* Build the read queue of site s.  Returns 0, or -1 when the alt-read side list does not match the stream. */
+static int build_reads(ref_ctx* c, const crispgpu_batch* b, int s)
+{
+	struct VARIANT* v = &c->variant;
+	const int P = c->P;
+	const uint32_t r0 = b->read_off[(size_t)s * P], r1 = b->read_off[(size_t)(s + 1) * P];
+	uint32_t nalt = 0;
+	if (b->alt_off) nalt = b->alt_off[s * 5 + 5] - b->alt_off[s * 5];
+	int need = (int)(r1 - r0) + (int)nalt + 1;
+	if (need > c->reads_cap) {
+		c->reads_cap = need * 2;
+		c->reads = (struct alignedread*)realloc(c->reads, sizeof(struct alignedread) * c->reads_cap);
+		c->cigars = (int*)realloc(c->cigars, sizeof(int) * c->reads_cap);
+	}
+	int n = 0;
+	struct alignedread* prev = NULL;
+	c->rq.first = c->rq.last = NULL;
+	c->rq.reads = 0;
+	for (int i = 0; i < P; i++) c->bd[i].first = c->bd[i].last = NULL;
+	/* per (slot) cursors into the alt list, per pool */
+	for (int i = 0; i < P; i++) {
+		const uint32_t a0 = b->read_off[(size_t)s * P + i], a1 = b->read_off[(size_t)s * P + i + 1];
+		struct alignedread* pprev = NULL;
+		uint32_t cursor[5], cend[5];
+		int taken[5] = {0, 0, 0, 0, 0};
+		for (int k = 0; k < 5; k++) {
+			cursor[k] = cend[k] = 0;
+			if (!b->alt_off) continue;
+			uint32_t lo = b->alt_off[s * 5 + k], hi = b->alt_off[s * 5 + k + 1];
+			while (lo < hi && b->alt_reads[lo].pool < i) lo++;
+			uint32_t e = lo;
+			while (e < hi && b->alt_reads[e].pool == i) e++;
+			cursor[k] = lo;
+			cend[k] = e;
+		}
+		/* ambiguous reference reads: the m-th reference read of class cls gets remaining match length
+		 * rem = min HPlength[slot allele] over slots whose decrement row covers m (nested by construction) */
+		int refseen[4] = {0, 0, 0, 0};
+		for (uint32_t r = a0; r < a1; r++) {
+			crispgpu_read w = b->reads[r];
+			struct alignedread* rd = &c->reads[n];
+			memset(rd, 0, sizeof(*rd));
+			int q = w & 0xff, base = (w >> 8) & 3, rev = (w >> 10) & 1, bidir = (w >> 11) & 1;
+			rd->sampleid = i;
+			rd->strand = rev;
+			rd->bidir = bidir;
+			rd->position = v->position - 10;
+			rd->lastpos = v->position + 50;
+			rd->filter = '0';
+			rd->type = 0;
+			rd->sequence = c->basebuf[base];
+			rd->quality = qual_buffer(c, q);
+			rd->l1 = 50;
+			rd->delta = 0;
+			rd->alignedbases = 100;
+			rd->allele = base + (rev ? 8 : 0);
+			rd->mquality = 60;
+			int rem = 1000000;
+			if (base == v->refbase && b->amb_idx) {
+				int cls = bidir ? 2 + rev : rev;
+				int m = refseen[cls]++;
+				for (int k = 0; k < 5; k++) {
+					int row = b->amb_idx[s * 5 + k];
+					if (row < 0) continue;
+					int dec = b->amb_dec[((size_t)row * P + i) * 4 + cls];
+					int hp = v->HPlength[b->maxvec_al[s * 8 + k + 1]];
+					if (m < dec && hp < rem) rem = hp;
+				}
+			}
+			c->cigars[n] = (rem << 4) | BAM_CMATCH;
+			rd->fcigarlist = &c->cigars[n];
+			rd->fcigs = 1;
+			rd->cigoffset = 0;
+			/* alternate-allele reads that calculate_uniquereads (allelecounts.c:53-57) would collect */
+			if (q >= MINQ + QVoffset) {
+				for (int k = 0; k < 5; k++) {
+					int al = b->maxvec_al[s * 8 + k + 1];
+					if (al >= 4 || al != base) continue;
+					if (cursor[k] < cend[k]) {
+						const crispgpu_altread* e = &b->alt_reads[cursor[k]++];
+						if (e->strand != rev) {
+							snprintf(c->err, sizeof c->err, "site %d slot %d pool %d: alt-read strand mismatch", s, k, i);
+							return -1;
+						}
+						rd->l1 = e->offset;
+						rd->alignedbases = e->aligned;
+						taken[k]++;
+					}
+				}
+			}
+			if (prev) prev->next = rd; else c->rq.first = rd;
+			if (pprev) pprev->nextread = rd; else c->bd[i].first = rd;
+			prev = rd;
+			pprev = rd;
+			n++;
+		}
+		/* indel alleles: one synthetic indel-carrying read per alt-list entry */
+		for (int k = 0; k < 5; k++) {
+			int al = b->maxvec_al[s * 8 + k + 1];
+			if (al < 4) {
+				if (cursor[k] != cend[k]) {
+					snprintf(c->err, sizeof c->err, "site %d slot %d pool %d: %u alt-list entries without a matching read", s, k, i, cend[k] - cursor[k]);
+					return -1;
+				}
+				continue;
+			}
+			while (cursor[k] < cend[k]) {
+				const crispgpu_altread* e = &b->alt_reads[cursor[k]++];
+				struct alignedread* rd = &c->reads[n];
+				memset(rd, 0, sizeof(*rd));
+				rd->sampleid = i;
+				rd->strand = e->strand;
+				rd->position = v->position - 10;
+				rd->lastpos = v->position + 50;
+				rd->filter = '0';
+				rd->type = b->indel_len ? b->indel_len[s * 8 + al] : 1;
+				rd->sequence = c->basebuf[0];
+				rd->quality = qual_buffer(c, 30 + 33);
+				rd->l1 = e->offset;
+				rd->alignedbases = e->aligned;
+				rd->allele = -1;
+				rd->mquality = 60;
+				c->cigars[n] = (1000000 << 4) | BAM_CMATCH;
+				rd->fcigarlist = &c->cigars[n];
+				rd->fcigs = 1;
+				if (prev) prev->next = rd; else c->rq.first = rd;
+				if (pprev) pprev->nextread = rd; else c->bd[i].first = rd;
+				prev = rd;
+				pprev = rd;
+				n++;
+			}
+		}
+		c->bd[i].last = pprev;
+	}
+	c->rq.last = prev;
+	c->rq.reads = n;
+	return 0;
+}
+
+static int stdout_saved = -1;
+static void mute_stdout(void)
+{
+	fflush(stdout);
+	stdout_saved = dup(1);
+	int nul = open("/dev/null", O_WRONLY);
+	dup2(nul, 1);
+	close(nul);
+}
+static void unmute_stdout(void)
+{
+	fflush(stdout);
+	if (stdout_saved >= 0) {
+		dup2(stdout_saved, 1);
+		close(stdout_saved);
+		stdout_saved = -1;
+	}
+}
+
+static void dump_genll(ref_ctx* c, crisp_host_results* out, int s, int k)
+{
+	if (!out->genll) return;
+	const int P = c->P, st = out->genll_stride;
+	struct VARIANT* v = &c->variant;
+	double** src[4] = {v->GENLL, v->GENLLf, v->GENLLr, v->GENLLb};
+	for (int t = 0; t < 4; t++)
+		for (int i = 0; i < P; i++) {
+			double* dst = out->genll + ((((size_t)s * 5 + k) * 4 + t) * P + i) * st;
+			for (int j = 0; j <= c->ploidy[i] && j < st; j++) dst[j] = src[t][i][j];
+		}
+}
+
+const char* crisp_ref_last_error(void* h) { return ((ref_ctx*)h)->err; }
+
+/*
+ * Run the reference engine over the batch.  rng_seed: srand48(seed) once at the start (the reference seeds with
+ * time(NULL), readmultiplebams.c:252).  vcf: optional buffer receiving the VCF records of called sites,
+ * each line prefixed by "<site index>\t" so it can be matched to the batch.
+ */
+int crisp_ref_run(void* h, const crispgpu_batch* b, crisp_host_results* out, int mode, long rng_seed, char* vcf, size_t vcf_cap, size_t* vcf_len)
+{
+	ref_ctx* c = (ref_ctx*)h;
+	if (!c || !b || !out) return CRISPGPU_ERR_ARG;
+	struct VARIANT* v = &c->variant;
+	const int P = c->P, n = b->n_sites;
+	apply_config(c);
+	srand48(rng_seed);
+	char* mem = NULL;
+	size_t memlen = 0;
+	FILE* vf = open_memstream(&mem, &memlen);
+	char* tmem = NULL;
+	size_t tlen = 0;
+	FILE* tf = open_memstream(&tmem, &tlen);
+	ALLELE maxvec[8];
+	int rc = 0;
+	out->n_sites = n;
+	out->n_calls = 0;
+	mute_stdout();
+	for (int s = 0; s < n && rc == 0; s++) {
+		fill_site(c, b, s);
+		for (int k = 0; k < 8; k++) {
+			maxvec[k].al = b->maxvec_al[s * 8 + k];
+			maxvec[k].ct = b->maxvec_ct[s * 8 + k];
+			maxvec[k].vars = 0;
+		}
+		for (int k = 0; k < 5; k++) {
+			int o = s * 5 + k;
+			out->status[o] = CRISPGPU_SLOT_UNTESTED;
+			out->allele[o] = maxvec[k + 1].al;
+			out->call_rank[o] = -1;
+			out->call_row[o] = -1;
+			out->paf[o] = out->ctpval[o] = out->chi2pval[o] = out->af_ml[o] = out->delta[o] = out->deltaf[o] = out->hwe[o] = 0;
+			out->qvpf[o] = out->qvpr[o] = 0;
+			out->varpools[o] = out->allelecount[o] = out->variantpools[o] = 0;
+			if (out->em_iters) out->em_iters[o] = 0;
+			if (out->perm_k) out->perm_k[o] = 0;
+			if (out->perm_hits) out->perm_hits[o] = 0;
+		}
+		int reads_built = 0;
+		if (mode == CRISP_REF_MODE_CALLER) {
+			if (build_reads(c, b, s) != 0) { rc = CRISPGPU_ERR_ARG; break; }
+			rewind(tf);
+			int called = newCRISPcaller(&c->reflist, 0, v->position, &c->rq, c->bd, v, maxvec, tf);
+			fflush(tf);
+			if (called) {
+				fprintf(vf, "%d\t", s);
+				fwrite(tmem, 1, tlen, vf);
+			}
+			out->varalleles[s] = v->varalleles;
+			out->strandpass[s] = v->strandpass;
+			for (int r = 0; r < v->varalleles; r++) {
+				int k;
+				for (k = 0; k < 5; k++)
+					if (maxvec[k + 1].ct >= 3 && maxvec[k + 1].al == v->alleles[r]) break;
+				if (k == 5) continue;
+				int o = s * 5 + k;
+				out->status[o] = CRISPGPU_SLOT_CALLED;
+				out->call_rank[o] = r;
+				out->ctpval[o] = v->ctpval[r];
+				out->chi2pval[o] = v->chi2pval[r];
+				out->af_ml[o] = v->crispvar[r].AF_ML;
+				out->delta[o] = v->crispvar[r].delta;
+				out->deltaf[o] = v->crispvar[r].deltaf;
+				out->hwe[o] = v->crispvar[r].deltar;
+				out->qvpf[o] = v->qvpvaluef[r];
+				out->qvpr[o] = v->qvpvaluer[r];
+				out->varpools[o] = v->nvariants[r];
+				out->allelecount[o] = v->crispvar[r].allelecount;
+				out->variantpools[o] = v->crispvar[r].variantpools;
+				if (EMflag >= 1 && out->n_calls < out->max_calls) {
+					int row = out->n_calls++;
+					out->call_row[o] = row;
+					for (int i = 0; i < P; i++) {
+						out->ac[(size_t)row * P + i] = v->crispvar[r].AC[i];
+						out->qv[(size_t)row * P + i] = v->crispvar[r].QV[i];
+					}
+				}
+			}
+			continue;
+		}
+		/* ---- CRISP_REF_MODE_SLOTS: the loop of newcrispcaller.c:203-246, with reference callees ---- */
+		v->strandpass = 0;
+		v->varalleles = 0;
+		double paf[2] = {0.0, 0.0};
+		for (int al = 1; al <= 5 && rc == 0; al++) {
+			if (maxvec[al].ct < 3) continue;
+			int o = s * 5 + al - 1;
+			int allele1 = maxvec[0].al, allele2 = maxvec[al].al, allele3 = maxvec[al == 1 ? al + 1 : 1].al;
+			v->ctpval[v->varalleles] = 0;
+			int indelflag = 0, is_variant = 0;
+			if ((allele2 >= 4 && v->HPlength[allele2] > 0) || (allele3 >= 4 && v->HPlength[allele3] >= 100)) {
+				indelflag = v->HPlength[allele2];
+				if (!reads_built) {
+					if (build_reads(c, b, s) != 0) { rc = CRISPGPU_ERR_ARG; break; }
+					reads_built = 1;
+				}
+				remove_ambiguous_bases(&c->rq, v, indelflag, 1);
+			}
+			int potentialvar = evaluate_variant(&c->rq, v, allele1, allele2, allele3, paf);
+			out->ctpval[o] = v->ctpval[v->varalleles];
+			out->chi2pval[o] = v->chi2pval[v->varalleles];
+			if (potentialvar == 1) {
+				out->paf[o] = paf[0];
+				if (!reads_built) {
+					if (build_reads(c, b, s) != 0) { rc = CRISPGPU_ERR_ARG; break; }
+					reads_built = 1;
+				}
+				out->status[o] = CRISPGPU_SLOT_NOCALL;
+				int slotrank = v->varalleles;
+				if (EMflag >= 1) {
+					is_variant = compute_GLL_pooled(&c->rq, v, allele1, allele2, allele3, paf);
+					dump_genll(c, out, s, al - 1);
+					out->af_ml[o] = v->crispvar[slotrank].AF_ML;
+					out->delta[o] = v->crispvar[slotrank].delta;
+					out->deltaf[o] = v->crispvar[slotrank].deltaf;
+					out->hwe[o] = v->crispvar[slotrank].deltar;
+					if (is_variant == 1) {
+						int variantpools = calculate_pool_statistics(&c->rq, c->bd, v, allele1, allele2);
+						v->varpools[v->varalleles] = variantpools;
+						v->alleles[v->varalleles] = allele2;
+						v->nvariants[v->varalleles] = variantpools;
+						v->varalleles++;
+					}
+				} else {
+					is_variant = pooled_variantcaller(&c->rq, c->bd, v, allele1, allele2);
+					out->qvpf[o] = v->qvpvaluef[slotrank];
+					out->qvpr[o] = v->qvpvaluer[slotrank];
+				}
+				if (is_variant == 1) {
+					out->status[o] = CRISPGPU_SLOT_CALLED;
+					out->call_rank[o] = slotrank;
+					out->varpools[o] = v->nvariants[slotrank];
+					out->allelecount[o] = v->crispvar[slotrank].allelecount;
+					out->variantpools[o] = v->crispvar[slotrank].variantpools;
+					if (EMflag >= 1 && out->n_calls < out->max_calls) {
+						int row = out->n_calls++;
+						out->call_row[o] = row;
+						for (int i = 0; i < P; i++) {
+							out->ac[(size_t)row * P + i] = v->crispvar[slotrank].AC[i];
+							out->qv[(size_t)row * P + i] = v->crispvar[slotrank].QV[i];
+						}
+					}
+				}
+			} else {
+				/* distinguish the two reject points of evaluate_variant: the AF filter returns before any
+				 * contingency-table work (newcrispcaller.c:72), so ctpval is still the 0 written at :209 */
+				out->status[o] = CRISPGPU_SLOT_REJECT_CT;
+				{
+					/* recompute the AF filter decision exactly as :48-72 does */
+					double p0 = 0;
+					for (int i = 0; i < P; i++) {
+						double C1 = 0, C2 = 0, C3 = 0;
+						for (int t = 0; t < 3; t++) {
+							C1 += v->indcounts[i][allele1 + t * 8];
+							C2 += v->indcounts[i][allele2 + t * 8];
+							C3 += v->indcounts[i][allele3 + t * 8];
+						}
+						double p1 = C2 / (C1 + C2 + C3 + 0.001);
+						p1 *= v->ploidy[i];
+						if (p1 >= 0.2 && C2 >= 4) p0 += p1;
+						else if (p1 >= 0.4 && C2 >= 3) p0 += p1;
+						else if (v->ploidy[i] == 2 && p1 >= 0.25 && C2 >= 1) p0 += p1;
+					}
+					out->paf[o] = p0;
+					if (p0 < 0.25 || (v->ploidy[0] == 2 && p0 <= 0.4)) out->status[o] = CRISPGPU_SLOT_REJECT_AF;
+				}
+			}
+			if (indelflag > 0) remove_ambiguous_bases(&c->rq, v, indelflag, -1);
+		}
+		out->varalleles[s] = v->varalleles;
+		out->strandpass[s] = v->strandpass;
+		if (v->varalleles >= 1 && rc == 0) {
+			int indelflag = 0;
+			for (int i = 0; i < v->varalleles; i++)
+				if (v->alleles[i] >= 4 && v->HPlength[v->alleles[i]] > indelflag) indelflag = v->HPlength[v->alleles[i]];
+			if (indelflag > 0) remove_ambiguous_bases(&c->rq, v, indelflag, 1);
+			fprintf(vf, "%d\t", s);
+			print_pooledvariant(v, vf, &c->reflist, 0, maxvec, EMflag);
+		}
+	}
+	unmute_stdout();
+	fclose(vf);
+	fclose(tf);
+	free(tmem);
+	if (vcf && vcf_cap > 0) {
+		size_t m = memlen < vcf_cap - 1 ? memlen : vcf_cap - 1;
+		memcpy(vcf, mem, m);
+		vcf[m] = 0;
+	}
+	if (vcf_len) *vcf_len = memlen;
+	free(mem);
+	return rc;
+}
+
+/*
+ * Replay: fill struct VARIANT from a results block (as the host shim of INTEGRATION.md does) and let the
+ * reference's print_pooledvariant write the VCF record.  Used to prove "GPU results -> unchanged printer"
+ * gives the same text as the reference end to end.
+ */
+int crisp_ref_replay_vcf(void* h, const crispgpu_batch* b, const crisp_host_results* res, char* vcf, size_t vcf_cap, size_t* vcf_len)
+{
+	ref_ctx* c = (ref_ctx*)h;
+	struct VARIANT* v = &c->variant;
+	const int P = c->P;
+	apply_config(c);
+	char* mem = NULL;
+	size_t memlen = 0;
+	FILE* vf = open_memstream(&mem, &memlen);
+	ALLELE maxvec[8];
+	for (int s = 0; s < b->n_sites; s++) {
+		if (res->varalleles[s] < 1) continue;
+		fill_site(c, b, s);
+		for (int k = 0; k < 8; k++) {
+			maxvec[k].al = b->maxvec_al[s * 8 + k];
+			maxvec[k].ct = b->maxvec_ct[s * 8 + k];
+		}
+		v->varalleles = res->varalleles[s];
+		v->strandpass = res->strandpass[s];
+		int hpmax = 0, hpslot = -1;
+		for (int k = 0; k < 5; k++) {
+			int o = s * 5 + k, r = res->call_rank[o];
+			if (res->status[o] != CRISPGPU_SLOT_CALLED || r < 0) continue;
+			v->alleles[r] = res->allele[o];
+			v->ctpval[r] = res->ctpval[o];
+			v->chi2pval[r] = res->chi2pval[o];
+			v->qvpvaluef[r] = res->qvpf[o];
+			v->qvpvaluer[r] = res->qvpr[o];
+			v->varpools[r] = v->nvariants[r] = res->varpools[o];
+			v->crispvar[r].allele = res->allele[o];
+			v->crispvar[r].AF_ML = res->af_ml[o];
+			v->crispvar[r].delta = res->delta[o];
+			v->crispvar[r].deltaf = res->deltaf[o];
+			v->crispvar[r].deltar = res->hwe[o];
+			v->crispvar[r].allelecount = res->allelecount[o];
+			v->crispvar[r].variantpools = res->variantpools[o];
+			int row = res->call_row[o];
+			for (int i = 0; i < P; i++) {
+				v->crispvar[r].AC[i] = row >= 0 ? res->ac[(size_t)row * P + i] : 0;
+				v->crispvar[r].QV[i] = row >= 0 ? res->qv[(size_t)row * P + i] : 0;
+			}
+			if (res->allele[o] >= 4 && v->HPlength[res->allele[o]] > hpmax) {
+				hpmax = v->HPlength[res->allele[o]];
+				hpslot = k;
+			}
+		}
+		/* newcrispcaller.c:253-263: counts are reduced once more with the largest called-indel HPlength */
+		if (hpmax > 0 && hpslot >= 0 && b->amb_idx && b->amb_idx[s * 5 + hpslot] >= 0) {
+			int row = b->amb_idx[s * 5 + hpslot];
+			for (int i = 0; i < P; i++) {
+				const int32_t* d = b->amb_dec + ((size_t)row * P + i) * 4;
+				v->indcounts[i][v->refbase] -= d[0];
+				v->indcounts[i][v->refbase + 8] -= d[1];
+				v->indcounts[i][v->refbase + 16] -= d[2] + d[3];
+			}
+		}
+		fprintf(vf, "%d\t", s);
+		print_pooledvariant(v, vf, &c->reflist, 0, maxvec, EMflag);
+	}
+	fclose(vf);
+	if (vcf && vcf_cap > 0) {
+		size_t m = memlen < vcf_cap - 1 ? memlen : vcf_cap - 1;
+		memcpy(vcf, mem, m);
+		vcf[m] = 0;
+	}
+	if (vcf_len) *vcf_len = memlen;
+	free(mem);
+	return 0;
+}
+
+/* ---- scalar known-answer entry points (SURVEY.md §8c level 2) ---- */
+double crisp_ref_ncr(int n, int r) { return ncr(n, r); }
+double crisp_ref_fet(int c1, int r1, int c2, int r2) { return fet(c1, r1, c2, r2); }
+double crisp_ref_minreads_pvalue(int R, int A, double e) { return minreads_pvalue(R, A, e); }
+double crisp_ref_binomial_pvalue(int R, int A, double e) { return binomial_pvalue(R, A, e); }
+double crisp_ref_kf_lgamma(double z) { return kf_lgamma(z); }
+double crisp_ref_kf_gammaq(double s, double z) { return kf_gammaq(s, z); }
+void crisp_ref_chernoff(int* counts, double* stats, int refbase, int altbase, double ser, double* p0, double* p1)
+{
+	chernoff_bound(counts, stats, refbase, altbase, ser, p0, p1, 8);
+}
