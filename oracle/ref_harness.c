@@ -598,7 +598,10 @@ int crisp_ref_run(void* h, const crispgpu_batch* b, crisp_host_results* out, int
 						else if (v->ploidy[i] == 2 && p1 >= 0.25 && C2 >= 1) p0 += p1;
 					}
 					out->paf[o] = p0;
-					if (p0 < 0.25 || (v->ploidy[0] == 2 && p0 <= 0.4)) out->status[o] = CRISPGPU_SLOT_REJECT_AF;
+					if (p0 < 0.25 || (v->ploidy[0] == 2 && p0 <= 0.4)) {
+						out->status[o] = CRISPGPU_SLOT_REJECT_AF;
+						out->chi2pval[o] = 0; /* not written on this path: variant->chi2pval[] still holds a stale value */
+					}
 				}
 			}
 			if (indelflag > 0) remove_ambiguous_bases(&c->rq, v, indelflag, -1);
