@@ -303,6 +303,52 @@ class Batch:
         return Batch(P, **out)
 
 
+def concat_batches(parts: list) -> Batch:
+    """Concatenate batches of the same pool layout (site order preserved)."""
+    if not parts:
+        raise ValueError("no batches")
+    P = parts[0].n_pools
+    out = {}
+    for name in ("tid", "pos", "refbase", "maxvec_al", "maxvec_ct", "counts", "indcounts", "reads"):
+        out[name] = np.concatenate([getattr(b, name) for b in parts])
+    for name, w, fill in (("indel_len", 8, 0), ("hplen", 8, 0), ("qhigh", P * 16, None), ("stats", P * 16, None), ("tstats", 16, None)):
+        have = [getattr(b, name) is not None for b in parts]
+        if not any(have):
+            continue
+        if not all(have) and fill is None:
+            raise ValueError(f"cannot concatenate: {name} present in only some batches")
+        dt = next(getattr(b, name) for b in parts if getattr(b, name) is not None).dtype
+        out[name] = np.concatenate([getattr(b, name) if getattr(b, name) is not None else np.full(b.n_sites * w, fill, dt) for b in parts])
+    def cat_off(name):
+        offs, base = [np.zeros(1, np.int64)], 0
+        for b in parts:
+            o = getattr(b, name).astype(np.int64)
+            offs.append(o[1:] + base)
+            base += int(o[-1])
+        return np.concatenate(offs).astype(np.uint32)
+    out["read_off"] = cat_off("read_off")
+    if any(b.alt_off is not None for b in parts):
+        if not all(b.alt_off is not None for b in parts):
+            raise ValueError("cannot concatenate: alt_off present in only some batches")
+        out["alt_off"] = cat_off("alt_off")
+        out["alt_reads"] = np.concatenate([b.alt_reads for b in parts])
+    if any(b.amb_idx is not None for b in parts):
+        idx, dec, ep, base = [], [], [], 0
+        for b in parts:
+            ai = b.amb_idx.copy() if b.amb_idx is not None else -np.ones(b.n_sites * 5, np.int32)
+            ai[ai >= 0] += base
+            idx.append(ai)
+            if b.n_amb:
+                dec.append(b.amb_dec)
+                ep.append(b.amb_ep if b.amb_ep is not None else np.zeros(b.n_amb * P * 2))
+                base += b.n_amb
+        out["amb_idx"] = np.concatenate(idx)
+        if dec:
+            out["amb_dec"] = np.concatenate(dec)
+            out["amb_ep"] = np.concatenate(ep)
+    return Batch(P, **out)
+
+
 class Results:
     """Owning numpy copy of a `crispgpu_results` block."""
 

@@ -1,0 +1,675 @@
+// crispgpu.cu — C ABI (include/crispgpu.h) of the B200 statistics engine: context, batch transfer, kernel pipeline.
+//
+// Pipeline per batch, all on one stream:
+//   H2D  ->  k_evaluate  ->  [k_permute_* -> k_filter]  ->  k_em | k_legacy  ->  k_finalize  ->  D2H
+// The only host synchronisation is one event wait after the screening stage to learn how many (site, slot) tasks
+// reached the caller (sizes the per-pool allele-count rows).  There is no CPU compute path.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/crispgpu.h"
+#include "dmath.cuh"
+#include "engine_types.cuh"
+#include "k_em.cuh"
+#include "k_evaluate.cuh"
+#include "k_legacy.cuh"
+#include "k_permute.cuh"
+
+using namespace crisp;
+
+namespace {
+
+struct DevBuf {
+	void* p = nullptr;
+	size_t cap = 0;
+};
+
+enum { EV_START, EV_H2D, EV_EVAL, EV_PERM, EV_FILTER, EV_CALL, EV_D2H, EV_COUNT };
+
+}  // namespace
+
+struct crispgpu_ctx {
+	int device = 0;
+	int num_sms = 0;
+	size_t smem_optin = 0;
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	crispgpu_config cfg{};
+	std::vector<int32_t> ploidy, phenotypes, pclass, class_ploidy;
+	int P = 0, K = 0, nmax = 0;
+	// device configuration tables
+	DevBuf d_ploidy, d_pclass, d_class_ploidy, d_NC, d_T, d_ncr;
+	// device batch
+	DevBuf d_b[24];
+	DevBatch db{};
+	int n_sites = 0;
+	bool resident = false;
+	// device results + pinned mirrors
+	DevBuf d_o[24], d_ac, d_qv;
+	DevBuf h_o[24], h_ac, h_qv;
+	DevOut dout{};
+	// queues
+	DevBuf d_perm_tasks, d_call_tasks, d_counters, h_counters, d_gws;
+	size_t gws_stride = 0;
+	// launch geometry
+	int ev_warps = 8, ev_grid = 0;
+	size_t ev_smem = 0;
+	int em_threads = 256, em_grid = 0;
+	size_t em_smem = 0;
+	bool em_smem_g = true;
+	int pm_threads = 256, pm_grid = 0, pm_l10cap = 2048;
+	size_t pm_smem = 0;
+	int lg_grid = 0;
+	size_t lg_smem = 0;
+	// bookkeeping
+	cudaEvent_t ev[EV_COUNT]{};
+	cudaEvent_t ev_counts = nullptr;
+	int64_t ticket = 0;
+	bool inflight = false;
+	crispgpu_timing timing{};
+	crispgpu_results res{};
+	int n_call = 0, n_perm = 0;
+	char err[512] = {0};
+};
+
+namespace {
+
+#define CK(call)                                                                                             \
+	do {                                                                                                     \
+		cudaError_t e_ = (call);                                                                             \
+		if (e_ != cudaSuccess) {                                                                             \
+			snprintf(ctx->err, sizeof ctx->err, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+			return CRISPGPU_ERR_CUDA;                                                                        \
+		}                                                                                                    \
+	} while (0)
+
+int ensure_dev(crispgpu_ctx* ctx, DevBuf& b, size_t bytes)
+{
+	if (bytes <= b.cap) return 0;
+	if (b.p) CK(cudaFree(b.p));
+	b.p = nullptr;
+	b.cap = 0;
+	size_t cap = bytes + bytes / 4 + 256;
+	CK(cudaMalloc(&b.p, cap));
+	b.cap = cap;
+	return 0;
+}
+
+int ensure_host(crispgpu_ctx* ctx, DevBuf& b, size_t bytes)
+{
+	if (bytes <= b.cap) return 0;
+	if (b.p) CK(cudaFreeHost(b.p));
+	b.p = nullptr;
+	b.cap = 0;
+	size_t cap = bytes + bytes / 4 + 256;
+	CK(cudaMallocHost(&b.p, cap));
+	b.cap = cap;
+	return 0;
+}
+
+// result arrays in the order of DevOut / crispgpu_results; width = elements per site
+struct OutField { size_t elem; int width; };
+const OutField kOutFields[] = {
+	{4, 1}, {4, 1},                 // varalleles, strandpass
+	{1, 5}, {1, 5}, {1, 5}, {4, 5}, // status, allele, call_rank, call_row
+	{8, 5}, {8, 5}, {8, 5}, {8, 5}, {8, 5}, {8, 5}, {8, 5}, {8, 5}, {8, 5},  // paf ctpval chi2pval af_ml delta deltaf hwe qvpf qvpr
+	{4, 5}, {4, 5}, {4, 5}, {4, 5}, {4, 5}, {4, 5},  // varpools allelecount variantpools em_iters perm_k perm_hits
+};
+constexpr int kNumOut = sizeof(kOutFields) / sizeof(kOutFields[0]);
+
+void bind_out(crispgpu_ctx* ctx)
+{
+	void** d = reinterpret_cast<void**>(&ctx->dout);
+	for (int f = 0; f < kNumOut; f++) d[f] = ctx->d_o[f].p;
+	ctx->dout.ac = static_cast<int32_t*>(ctx->d_ac.p);
+	ctx->dout.qv = static_cast<double*>(ctx->d_qv.p);
+}
+
+size_t em_smem_fixed(int P, int J, int nwarps)
+{
+	size_t off = (sizeof(EmShared) + 15) & ~size_t(15);
+	off += sizeof(double) * P;
+	off += sizeof(double) * J * 2;
+	off += sizeof(int32_t) * 6 * P;
+	off = (off + 15) & ~size_t(15);
+	off += sizeof(uint32_t) * 6 * kNQ * nwarps;
+	off = (off + 15) & ~size_t(15);
+	return off;
+}
+
+int setup_geometry(crispgpu_ctx* ctx)
+{
+	const int P = ctx->P, J = ctx->nmax + 1;
+	const size_t budget = ctx->smem_optin;
+	// k_evaluate: warps per CTA limited by the staged count block
+	ctx->ev_warps = 8;
+	while (ctx->ev_warps > 1 && (size_t)ctx->ev_warps * P * kICPad * 4 > budget / 2) ctx->ev_warps >>= 1;
+	ctx->ev_smem = (size_t)ctx->ev_warps * P * kICPad * 4;
+	if (ctx->ev_smem > budget) return CRISPGPU_ERR_UNSUPPORTED;
+	// k_em
+	const int rounds = (P + 31) / 32;
+	if (rounds > kMaxRounds) return CRISPGPU_ERR_UNSUPPORTED;
+	int warps = rounds * 3;
+	if (warps > kEmMaxWarps) warps = kEmMaxWarps;
+	ctx->em_threads = warps * 32;
+	const size_t fixed = em_smem_fixed(P, J, warps);
+	const size_t gbytes = (size_t)3 * J * P * sizeof(double);
+	ctx->em_smem_g = fixed + gbytes <= budget;
+	ctx->em_smem = ctx->em_smem_g ? fixed + gbytes : fixed;
+	ctx->gws_stride = (size_t)3 * J * P;
+	// k_permute: threads per CTA limited by the per-permutation occupancy columns
+	ctx->pm_l10cap = P > 2048 ? P : 2048;
+	size_t pfixed = ((sizeof(PermShared) + 15) & ~size_t(15)) + sizeof(uint32_t) * 3 * (P + 1) + sizeof(int32_t) * 4 * P + 32 + sizeof(double) * (ctx->pm_l10cap > P ? ctx->pm_l10cap : P);
+	ctx->pm_threads = 256;
+	while (ctx->pm_threads > 32 && pfixed + (size_t)P * ctx->pm_threads * 4 > budget - 1024) ctx->pm_threads >>= 1;
+	ctx->pm_smem = pfixed + (size_t)P * ctx->pm_threads * 4;
+	if (ctx->pm_smem > budget) ctx->pm_smem = 0;  // permutation modes unsupported for this many pools
+	ctx->lg_smem = (size_t)4 * P * sizeof(double);
+	return 0;
+}
+
+template <typename K>
+int occupancy_grid(crispgpu_ctx* ctx, K kernel, int threads, size_t smem, int* grid)
+{
+	int per_sm = 0;
+	if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+	if (per_sm < 1) per_sm = 1;
+	*grid = per_sm * ctx->num_sms;
+	return 0;
+}
+
+int launch_evaluate(crispgpu_ctx* ctx, const EngineParams& prm)
+{
+	const int n = ctx->n_sites;
+	auto go = [&](auto kernel, int warps) -> int {
+		int grid = 0;
+		int rc = occupancy_grid(ctx, kernel, warps * 32, ctx->ev_smem, &grid);
+		if (rc) return rc;
+		int need = (n + warps - 1) / warps;
+		if (grid > need) grid = need;
+		if (grid < 1) grid = 1;
+		kernel<<<grid, warps * 32, ctx->ev_smem, ctx->stream>>>(prm);
+		return 0;
+	};
+	switch (ctx->ev_warps) {
+		case 8: return go(k_evaluate<8>, 8);
+		case 4: return go(k_evaluate<4>, 4);
+		case 2: return go(k_evaluate<2>, 2);
+		default: return go(k_evaluate<1>, 1);
+	}
+}
+
+struct BatchArray { const void* host; size_t bytes; };
+
+int collect_arrays(crispgpu_ctx* ctx, const crispgpu_batch* b, BatchArray* a)
+{
+	const size_t n = b->n_sites, P = ctx->P;
+	if (!b->tid || !b->pos || !b->refbase || !b->maxvec_al || !b->maxvec_ct || !b->counts || !b->indcounts || !b->read_off) return CRISPGPU_ERR_ARG;
+	const size_t nreads = n ? b->read_off[n * P] : 0;
+	const size_t nalt = (b->alt_off && n) ? b->alt_off[n * 5] : 0;
+	if (nreads && !b->reads) return CRISPGPU_ERR_ARG;
+	if (nalt && !b->alt_reads) return CRISPGPU_ERR_ARG;
+	if (b->amb_idx && b->n_amb > 0 && !b->amb_dec) return CRISPGPU_ERR_ARG;
+	int k = 0;
+	a[k++] = {b->tid, n * 4};
+	a[k++] = {b->pos, n * 4};
+	a[k++] = {b->refbase, n};
+	a[k++] = {b->maxvec_al, n * 8};
+	a[k++] = {b->maxvec_ct, n * 32};
+	a[k++] = {b->counts, n * 96};
+	a[k++] = {b->indcounts, n * P * 96};
+	a[k++] = {b->indel_len, b->indel_len ? n * 16 : 0};
+	a[k++] = {b->hplen, b->hplen ? n * 16 : 0};
+	a[k++] = {b->read_off, (n * P + 1) * 4};
+	a[k++] = {b->reads, nreads * 2};
+	a[k++] = {b->alt_off, b->alt_off ? (n * 5 + 1) * 4 : 0};
+	a[k++] = {b->alt_reads, nalt * sizeof(crispgpu_altread)};
+	a[k++] = {b->amb_idx, b->amb_idx ? n * 20 : 0};
+	a[k++] = {b->amb_dec, (b->amb_idx && b->amb_dec) ? (size_t)b->n_amb * P * 16 : 0};
+	a[k++] = {b->amb_ep, (b->amb_idx && b->amb_ep) ? (size_t)b->n_amb * P * 16 : 0};
+	a[k++] = {b->qhigh, b->qhigh ? n * P * 128 : 0};
+	a[k++] = {b->stats, b->stats ? n * P * 128 : 0};
+	a[k++] = {b->tstats, b->tstats ? n * 128 : 0};
+	return k;
+}
+
+int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b)
+{
+	BatchArray a[24];
+	const int k = collect_arrays(ctx, b, a);
+	if (k < 0) {
+		snprintf(ctx->err, sizeof ctx->err, "batch is missing a required array");
+		return k;
+	}
+	const void** dptr = reinterpret_cast<const void**>(&ctx->db.tid);
+	int64_t bytes = 0;
+	for (int i = 0; i < k; i++) {
+		if (a[i].bytes == 0 || a[i].host == nullptr) { dptr[i] = nullptr; continue; }
+		int rc = ensure_dev(ctx, ctx->d_b[i], a[i].bytes);
+		if (rc) return rc;
+		CK(cudaMemcpyAsync(ctx->d_b[i].p, a[i].host, a[i].bytes, cudaMemcpyHostToDevice, ctx->stream));
+		dptr[i] = ctx->d_b[i].p;
+		bytes += (int64_t)a[i].bytes;
+	}
+	ctx->db.n_sites = b->n_sites;
+	ctx->db.P = ctx->P;
+	ctx->n_sites = b->n_sites;
+	ctx->timing.h2d_bytes = bytes;
+	return 0;
+}
+
+int ensure_outputs(crispgpu_ctx* ctx, int n)
+{
+	for (int f = 0; f < kNumOut; f++) {
+		size_t bytes = (size_t)n * kOutFields[f].width * kOutFields[f].elem;
+		int rc = ensure_dev(ctx, ctx->d_o[f], bytes);
+		if (rc) return rc;
+		rc = ensure_host(ctx, ctx->h_o[f], bytes);
+		if (rc) return rc;
+	}
+	int rc = ensure_dev(ctx, ctx->d_perm_tasks, (size_t)n * 5 * 4);
+	if (rc) return rc;
+	rc = ensure_dev(ctx, ctx->d_call_tasks, (size_t)n * 5 * 4);
+	if (rc) return rc;
+	return 0;
+}
+
+EngineParams make_params(crispgpu_ctx* ctx)
+{
+	EngineParams prm{};
+	prm.b = ctx->db;
+	DevCfg& c = prm.c;
+	const crispgpu_config& g = ctx->cfg;
+	c.P = ctx->P; c.K = ctx->K; c.nmax = ctx->nmax; c.n_pclass = (int)ctx->class_ploidy.size(); c.ploidy0 = ctx->ploidy[0];
+	c.varpoolsize = g.varpoolsize;
+	c.em_flag = g.em_flag; c.max_iter = g.max_iter; c.chisq_permutation = g.chisq_permutation; c.fast_filter = g.fast_filter;
+	c.use_base_qvs = g.use_base_qvs; c.min_reads = g.min_reads; c.qv_offset = g.qv_offset; c.min_q = g.min_q; c.pivot_sample = g.pivot_sample;
+	c.use_qv = g.use_qv; c.exact_mode = g.exact_mode;
+	c.thresh1 = g.thresh1; c.min_qpv = g.min_qpv; c.thresh3 = g.thresh3; c.ser = g.ser; c.relax = g.relax; c.qmin = g.qmin;
+	c.ref_bias = g.agilent_ref_bias; c.theta = g.theta;
+	double alpha = 0.0;
+	for (int j = 1; j <= ctx->K; j++) alpha += 1.0 / j;  // crispEM.c:223-224
+	alpha *= g.theta;
+	c.alpha_prior = alpha;
+	c.rng_seed = g.rng_seed;
+	c.ploidy = static_cast<const int32_t*>(ctx->d_ploidy.p);
+	c.pclass = static_cast<const int32_t*>(ctx->d_pclass.p);
+	c.NC = static_cast<const double*>(ctx->d_NC.p);
+	c.T = static_cast<const double*>(ctx->d_T.p);
+	c.ncr_tab = static_cast<const double*>(ctx->d_ncr.p);
+	bind_out(ctx);
+	prm.o = ctx->dout;
+	prm.q.perm_tasks = static_cast<int32_t*>(ctx->d_perm_tasks.p);
+	prm.q.call_tasks = static_cast<int32_t*>(ctx->d_call_tasks.p);
+	prm.q.counters = static_cast<int32_t*>(ctx->d_counters.p);
+	prm.gws = static_cast<double*>(ctx->d_gws.p);
+	prm.gws_stride = ctx->gws_stride;
+	return prm;
+}
+
+// runs the kernel pipeline on data already on the device; fetch = copy results to the pinned mirrors
+int run_pipeline(crispgpu_ctx* ctx, bool fetch)
+{
+	const int n = ctx->n_sites;
+	const crispgpu_config& g = ctx->cfg;
+	int rc = ensure_outputs(ctx, n > 0 ? n : 1);
+	if (rc) return rc;
+	int64_t launches = 0;
+	CK(cudaMemsetAsync(ctx->d_counters.p, 0, 16 * sizeof(int32_t), ctx->stream));
+	EngineParams prm = make_params(ctx);
+	CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
+	if (n > 0) {
+		rc = launch_evaluate(ctx, prm);
+		if (rc) return rc;
+		launches++;
+	}
+	CK(cudaGetLastError());
+	CK(cudaEventRecord(ctx->ev[EV_EVAL], ctx->stream));
+	if (g.chisq_permutation == 1 && n > 0) {
+		if (ctx->pm_smem == 0) {
+			snprintf(ctx->err, sizeof ctx->err, "permutation test: %d pools exceed the shared-memory layout", ctx->P);
+			return CRISPGPU_ERR_UNSUPPORTED;
+		}
+		if (ctx->ploidy[0] > 2) {
+			if (!ctx->pm_grid) { rc = occupancy_grid(ctx, k_permute_stranded, ctx->pm_threads, ctx->pm_smem, &ctx->pm_grid); if (rc) return rc; }
+			k_permute_stranded<<<ctx->pm_grid, ctx->pm_threads, ctx->pm_smem, ctx->stream>>>(prm, ctx->pm_l10cap);
+		} else {
+			if (!ctx->pm_grid) { rc = occupancy_grid(ctx, k_permute_lowcov, ctx->pm_threads, ctx->pm_smem, &ctx->pm_grid); if (rc) return rc; }
+			k_permute_lowcov<<<ctx->pm_grid, ctx->pm_threads, ctx->pm_smem, ctx->stream>>>(prm);
+		}
+		launches++;
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(ctx->ev[EV_PERM], ctx->stream));
+		k_filter<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(prm);
+		launches++;
+		CK(cudaGetLastError());
+	} else {
+		CK(cudaEventRecord(ctx->ev[EV_PERM], ctx->stream));
+	}
+	CK(cudaEventRecord(ctx->ev[EV_FILTER], ctx->stream));
+	// how many tasks reached the caller: sizes the per-pool rows
+	CK(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaEventRecord(ctx->ev_counts, ctx->stream));
+	CK(cudaEventSynchronize(ctx->ev_counts));
+	const int32_t* hc = static_cast<const int32_t*>(ctx->h_counters.p);
+	ctx->n_perm = hc[0];
+	ctx->n_call = hc[1];
+	const int rows = g.em_flag >= 1 ? ctx->n_call : 0;
+	if (rows > 0) {
+		rc = ensure_dev(ctx, ctx->d_ac, (size_t)rows * ctx->P * 4); if (rc) return rc;
+		rc = ensure_dev(ctx, ctx->d_qv, (size_t)rows * ctx->P * 8); if (rc) return rc;
+		prm = make_params(ctx);
+	}
+	if (ctx->n_call > 0) {
+		if (g.em_flag >= 1) {
+			if (!ctx->em_grid) {
+				rc = ctx->em_smem_g ? occupancy_grid(ctx, k_em<true>, ctx->em_threads, ctx->em_smem, &ctx->em_grid)
+				                    : occupancy_grid(ctx, k_em<false>, ctx->em_threads, ctx->em_smem, &ctx->em_grid);
+				if (rc) return rc;
+			}
+			int grid = ctx->em_grid < ctx->n_call ? ctx->em_grid : ctx->n_call;
+			if (!ctx->em_smem_g) {
+				rc = ensure_dev(ctx, ctx->d_gws, (size_t)ctx->em_grid * ctx->gws_stride * sizeof(double));
+				if (rc) return rc;
+				prm = make_params(ctx);
+				k_em<false><<<grid, ctx->em_threads, ctx->em_smem, ctx->stream>>>(prm);
+			} else {
+				k_em<true><<<grid, ctx->em_threads, ctx->em_smem, ctx->stream>>>(prm);
+			}
+		} else {
+			if (!ctx->lg_grid) { rc = occupancy_grid(ctx, k_legacy<4>, 128, ctx->lg_smem, &ctx->lg_grid); if (rc) return rc; }
+			int need = (ctx->n_call + 3) / 4;
+			k_legacy<4><<<ctx->lg_grid < need ? ctx->lg_grid : need, 128, ctx->lg_smem, ctx->stream>>>(prm);
+		}
+		launches++;
+		CK(cudaGetLastError());
+	}
+	if (n > 0) {
+		k_finalize<<<(n + 255) / 256, 256, 0, ctx->stream>>>(prm);
+		launches++;
+		CK(cudaGetLastError());
+	}
+	CK(cudaEventRecord(ctx->ev[EV_CALL], ctx->stream));
+	int64_t d2h = 0;
+	if (fetch) {
+		for (int f = 0; f < kNumOut; f++) {
+			size_t bytes = (size_t)n * kOutFields[f].width * kOutFields[f].elem;
+			if (!bytes) continue;
+			CK(cudaMemcpyAsync(ctx->h_o[f].p, ctx->d_o[f].p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+			d2h += (int64_t)bytes;
+		}
+		if (rows > 0) {
+			rc = ensure_host(ctx, ctx->h_ac, (size_t)rows * ctx->P * 4); if (rc) return rc;
+			rc = ensure_host(ctx, ctx->h_qv, (size_t)rows * ctx->P * 8); if (rc) return rc;
+			CK(cudaMemcpyAsync(ctx->h_ac.p, ctx->d_ac.p, (size_t)rows * ctx->P * 4, cudaMemcpyDeviceToHost, ctx->stream));
+			CK(cudaMemcpyAsync(ctx->h_qv.p, ctx->d_qv.p, (size_t)rows * ctx->P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+			d2h += (int64_t)rows * ctx->P * 12;
+		}
+	}
+	CK(cudaEventRecord(ctx->ev[EV_D2H], ctx->stream));
+	ctx->timing.launches = launches;
+	ctx->timing.d2h_bytes = d2h;
+	ctx->timing.n_tasks_em = ctx->n_call;
+	ctx->timing.n_tasks_perm = ctx->n_perm;
+	return 0;
+}
+
+void fill_results(crispgpu_ctx* ctx, crispgpu_results* out)
+{
+	crispgpu_results& r = ctx->res;
+	r.n_sites = ctx->n_sites;
+	r.n_calls = ctx->cfg.em_flag >= 1 ? ctx->n_call : 0;
+	const void** hp = reinterpret_cast<const void**>(&r.varalleles);
+	for (int f = 0; f < kNumOut; f++) hp[f] = ctx->h_o[f].p;
+	r.ac = static_cast<const int32_t*>(ctx->h_ac.p);
+	r.qv = static_cast<const double*>(ctx->h_qv.p);
+	if (out) *out = r;
+}
+
+int finish_timing(crispgpu_ctx* ctx)
+{
+	crispgpu_timing& t = ctx->timing;
+	CK(cudaEventElapsedTime(&t.h2d_ms, ctx->ev[EV_START], ctx->ev[EV_H2D]));
+	CK(cudaEventElapsedTime(&t.evaluate_ms, ctx->ev[EV_H2D], ctx->ev[EV_EVAL]));
+	CK(cudaEventElapsedTime(&t.permute_ms, ctx->ev[EV_EVAL], ctx->ev[EV_PERM]));
+	CK(cudaEventElapsedTime(&t.filter_ms, ctx->ev[EV_PERM], ctx->ev[EV_FILTER]));
+	float call_ms = 0;
+	CK(cudaEventElapsedTime(&call_ms, ctx->ev[EV_FILTER], ctx->ev[EV_CALL]));
+	t.em_ms = ctx->cfg.em_flag >= 1 ? call_ms : 0.f;
+	t.legacy_ms = ctx->cfg.em_flag >= 1 ? 0.f : call_ms;
+	CK(cudaEventElapsedTime(&t.d2h_ms, ctx->ev[EV_CALL], ctx->ev[EV_D2H]));
+	CK(cudaEventElapsedTime(&t.total_ms, ctx->ev[EV_START], ctx->ev[EV_D2H]));
+	return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void crispgpu_config_defaults(crispgpu_config* cfg)
+{
+	if (!cfg) return;
+	memset(cfg, 0, sizeof(*cfg));
+	cfg->abi_version = CRISPGPU_ABI_VERSION;
+	cfg->em_flag = 1;
+	cfg->max_iter = 20000;
+	cfg->chisq_permutation = 0;
+	cfg->fast_filter = 1;
+	cfg->use_base_qvs = 1;
+	cfg->min_reads = 4;
+	cfg->qv_offset = 33;
+	cfg->min_q = 13;
+	cfg->thresh1 = -3.5;
+	cfg->min_qpv = -5;
+	cfg->thresh3 = -2;
+	cfg->ser = -1;
+	cfg->relax = 0.75;
+	cfg->qmin = 23;
+	cfg->agilent_ref_bias = 0.5;
+	cfg->theta = 0.001;
+	cfg->rng_seed = 1;
+}
+
+int crispgpu_abi_version(void) { return CRISPGPU_ABI_VERSION; }
+
+int crispgpu_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+	return n;
+}
+
+int crispgpu_create(const crispgpu_config* cfg, int device_id, void* stream, crispgpu_ctx** out)
+{
+	if (!cfg || !out || cfg->abi_version != CRISPGPU_ABI_VERSION || cfg->n_pools <= 0 || !cfg->ploidy) return CRISPGPU_ERR_ARG;
+	*out = nullptr;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device_id < 0 || device_id >= ndev) return CRISPGPU_ERR_NO_DEVICE;
+	crispgpu_ctx* ctx = new (std::nothrow) crispgpu_ctx();
+	if (!ctx) return CRISPGPU_ERR_NOMEM;
+	auto fail = [&](int rc) { crispgpu_destroy(ctx); return rc; };
+	ctx->device = device_id;
+	if (cudaSetDevice(device_id) != cudaSuccess) return fail(CRISPGPU_ERR_NO_DEVICE);
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) return fail(CRISPGPU_ERR_NO_DEVICE);
+	if (prop.major < 10) return fail(CRISPGPU_ERR_NO_DEVICE);  // built for sm_100a only
+	ctx->num_sms = prop.multiProcessorCount;
+	ctx->smem_optin = prop.sharedMemPerBlockOptin;
+	ctx->cfg = *cfg;
+	ctx->P = cfg->n_pools;
+	ctx->ploidy.assign(cfg->ploidy, cfg->ploidy + ctx->P);
+	ctx->cfg.ploidy = ctx->ploidy.data();
+	if (cfg->phenotypes) ctx->phenotypes.assign(cfg->phenotypes, cfg->phenotypes + ctx->P);
+	ctx->cfg.phenotypes = ctx->phenotypes.empty() ? nullptr : ctx->phenotypes.data();
+	ctx->pclass.resize(ctx->P);
+	for (int i = 0; i < ctx->P; i++) {
+		const int n = ctx->ploidy[i];
+		if (n < 1) return fail(CRISPGPU_ERR_ARG);
+		ctx->K += n;
+		if (n > ctx->nmax) ctx->nmax = n;
+		int pc = -1;
+		for (size_t k = 0; k < ctx->class_ploidy.size(); k++) if (ctx->class_ploidy[k] == n) pc = (int)k;
+		if (pc < 0) { pc = (int)ctx->class_ploidy.size(); ctx->class_ploidy.push_back(n); }
+		ctx->pclass[i] = pc;
+	}
+	if (ctx->class_ploidy.size() > 64) return fail(CRISPGPU_ERR_UNSUPPORTED);
+	if (setup_geometry(ctx) != 0) return fail(CRISPGPU_ERR_UNSUPPORTED);
+	if (stream) ctx->stream = static_cast<cudaStream_t>(stream);
+	else {
+		if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
+		ctx->own_stream = true;
+	}
+	for (int i = 0; i < EV_COUNT; i++) if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
+	if (cudaEventCreateWithFlags(&ctx->ev_counts, cudaEventDisableTiming) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
+	// configuration tables: NC on the host exactly as init_variant does (init_variant.c:19-25), T on the device
+	const int J = ctx->nmax + 1, ncl = (int)ctx->class_ploidy.size();
+	std::vector<double> NC((size_t)ncl * J, 0.0);
+	for (int k = 0; k < ncl; k++) {
+		const int n = ctx->class_ploidy[k];
+		double* row = NC.data() + (size_t)k * J;
+		for (int j = 1; j < n; j++) row[j] = row[j - 1] + log10((double)(n - j + 1)) - log10((double)j);
+	}
+	auto up = [&](DevBuf& b, const void* src, size_t bytes) -> int {
+		int rc = ensure_dev(ctx, b, bytes);
+		if (rc) return rc;
+		if (cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return CRISPGPU_ERR_CUDA;
+		return 0;
+	};
+	int rc = 0;
+	if ((rc = up(ctx->d_ploidy, ctx->ploidy.data(), (size_t)ctx->P * 4))) return fail(rc);
+	if ((rc = up(ctx->d_pclass, ctx->pclass.data(), (size_t)ctx->P * 4))) return fail(rc);
+	if ((rc = up(ctx->d_class_ploidy, ctx->class_ploidy.data(), (size_t)ncl * 4))) return fail(rc);
+	if ((rc = up(ctx->d_NC, NC.data(), NC.size() * 8))) return fail(rc);
+	if ((rc = ensure_dev(ctx, ctx->d_T, (size_t)ncl * 2 * kNQ * J * 8))) return fail(rc);
+	if (cfg->chisq_permutation == 1 && ctx->ploidy[0] == 2) {
+		// constant table log10 C(n,r) in the reference's own summation order, evaluated with the host libm
+		const int H = kNcrTabN / 2 + 1;
+		std::vector<double> tab((size_t)kNcrTabN * H, 0.0);
+		for (int n = 1; n < kNcrTabN; n++) {
+			double ll = 0.0;
+			for (int r = 1; r <= n / 2; r++) {
+				ll += log10((double)(n - (r - 1)) / (double)r);
+				tab[(size_t)n * H + r] = ll;
+			}
+		}
+		if ((rc = up(ctx->d_ncr, tab.data(), tab.size() * 8))) return fail(rc);
+	}
+	if ((rc = ensure_dev(ctx, ctx->d_counters, 16 * 4))) return fail(rc);
+	if ((rc = ensure_host(ctx, ctx->h_counters, 16 * 4))) return fail(rc);
+	k_build_T<<<ctx->num_sms, 256, 0, ctx->stream>>>(static_cast<double*>(ctx->d_T.p), static_cast<const int32_t*>(ctx->d_class_ploidy.p), ncl, J, cfg->qv_offset, cfg->agilent_ref_bias);
+	if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
+	*out = ctx;
+	return CRISPGPU_OK;
+}
+
+void crispgpu_destroy(crispgpu_ctx* ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+	auto fd = [](DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; };
+	auto fh = [](DevBuf& b) { if (b.p) cudaFreeHost(b.p); b.p = nullptr; };
+	fd(ctx->d_ploidy); fd(ctx->d_pclass); fd(ctx->d_class_ploidy); fd(ctx->d_NC); fd(ctx->d_T); fd(ctx->d_ncr);
+	for (auto& b : ctx->d_b) fd(b);
+	for (auto& b : ctx->d_o) fd(b);
+	for (auto& b : ctx->h_o) fh(b);
+	fd(ctx->d_ac); fd(ctx->d_qv); fh(ctx->h_ac); fh(ctx->h_qv);
+	fd(ctx->d_perm_tasks); fd(ctx->d_call_tasks); fd(ctx->d_counters); fh(ctx->h_counters); fd(ctx->d_gws);
+	for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+	if (ctx->ev_counts) cudaEventDestroy(ctx->ev_counts);
+	if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+int crispgpu_submit(crispgpu_ctx* ctx, const crispgpu_batch* batch, int64_t* ticket)
+{
+	if (!ctx || !batch || batch->n_sites < 0) return CRISPGPU_ERR_ARG;
+	if (ctx->inflight) {
+		snprintf(ctx->err, sizeof ctx->err, "a batch is already in flight; call crispgpu_wait first");
+		return CRISPGPU_ERR_TICKET;
+	}
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
+	int rc = copy_batch(ctx, batch);
+	if (rc) return rc;
+	ctx->resident = false;
+	rc = run_pipeline(ctx, true);
+	if (rc) return rc;
+	ctx->inflight = true;
+	ctx->ticket++;
+	if (ticket) *ticket = ctx->ticket;
+	return CRISPGPU_OK;
+}
+
+int crispgpu_wait(crispgpu_ctx* ctx, int64_t ticket, crispgpu_results* out)
+{
+	if (!ctx) return CRISPGPU_ERR_ARG;
+	if (!ctx->inflight || ticket != ctx->ticket) return CRISPGPU_ERR_TICKET;
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaEventSynchronize(ctx->ev[EV_D2H]));
+	ctx->inflight = false;
+	int rc = finish_timing(ctx);
+	if (rc) return rc;
+	fill_results(ctx, out);
+	return CRISPGPU_OK;
+}
+
+int crispgpu_upload(crispgpu_ctx* ctx, const crispgpu_batch* batch)
+{
+	if (!ctx || !batch || batch->n_sites < 0) return CRISPGPU_ERR_ARG;
+	if (ctx->inflight) return CRISPGPU_ERR_TICKET;
+	CK(cudaSetDevice(ctx->device));
+	int rc = copy_batch(ctx, batch);
+	if (rc) return rc;
+	CK(cudaStreamSynchronize(ctx->stream));
+	ctx->resident = true;
+	return CRISPGPU_OK;
+}
+
+int crispgpu_run_resident(crispgpu_ctx* ctx, int fetch_results, crispgpu_results* out)
+{
+	if (!ctx) return CRISPGPU_ERR_ARG;
+	if (!ctx->resident) {
+		snprintf(ctx->err, sizeof ctx->err, "no resident batch: call crispgpu_upload first");
+		return CRISPGPU_ERR_ARG;
+	}
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
+	int rc = run_pipeline(ctx, fetch_results != 0);
+	if (rc) return rc;
+	CK(cudaEventSynchronize(ctx->ev[EV_D2H]));
+	rc = finish_timing(ctx);
+	if (rc) return rc;
+	if (fetch_results) fill_results(ctx, out);
+	return CRISPGPU_OK;
+}
+
+int crispgpu_get_timing(crispgpu_ctx* ctx, crispgpu_timing* out)
+{
+	if (!ctx || !out) return CRISPGPU_ERR_ARG;
+	*out = ctx->timing;
+	return CRISPGPU_OK;
+}
+
+const char* crispgpu_last_error(crispgpu_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+void* crispgpu_host_alloc(size_t bytes)
+{
+	void* p = nullptr;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+	return p;
+}
+
+void crispgpu_host_free(void* p)
+{
+	if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

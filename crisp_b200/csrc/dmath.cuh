@@ -1,0 +1,208 @@
+// dmath.cuh — scalar device functions of the CRISP statistics engine (sm_100a, FP64 CUDA cores).
+//
+// Each function states the reference lines whose *results* it reproduces (vibansal/crisp).  They are written for
+// the device: no recursion, no libm state, branch structure chosen for warp execution.
+#pragma once
+#include <cstdint>
+
+namespace crisp {
+
+constexpr double kLn10 = 2.302585092994045684;
+constexpr double kCtEps = 1e-6;  // `epsilon`, FET/contables.h:9
+constexpr double kMinP = 1e-6;   // MINP, crisp/crispEM.c:6
+
+// log10 C(n,r), r-term sum of log10 ratios in the reference's order (FET/contables.c:80-87)
+__device__ __forceinline__ double d_ncr(int n, int r)
+{
+	if (r == 0 || n == r) return 0.0;
+	if (2 * r > n) r = n - r;
+	double ll = 0.0;
+	for (int i = 0; i < r; i++) ll += log10((double)(n - i) / (double)(i + 1));
+	return ll;
+}
+
+// ln Gamma(z), AS245 (FET/kfunc.c:9-22)
+__device__ __forceinline__ double d_lgamma(double z)
+{
+	double x = 0.0;
+	x += 0.1659470187408462e-06 / (z + 7);
+	x += 0.9934937113930748e-05 / (z + 6);
+	x -= 0.1385710331296526 / (z + 5);
+	x += 12.50734324009056 / (z + 4);
+	x -= 176.6150291498386 / (z + 3);
+	x += 771.3234287757674 / (z + 2);
+	x -= 1259.139216722289 / (z + 1);
+	x += 676.5203681218835 / z;
+	x += 0.9999999999995183;
+	return log(x) - 5.58106146679532777 - z + (z - 0.5) * log(z + 6.5);
+}
+
+// ln of the regularised upper incomplete gamma Q(s,z) with the reference's branch rule, series length and
+// continued-fraction tolerances (FET/kfunc.c:73-116).  Callers divide by ln 10.
+__device__ inline double d_gammaq(double s, double z)
+{
+	if (z <= 1. || z < s) {
+		double sum = 1., x = 1.;
+		for (int k = 1; k < 100; ++k) {
+			sum += (x *= z / (s + k));
+			if (x / sum < 1e-14) break;
+		}
+		double lp = s * log(z) - z - d_lgamma(s + 1.) + log(sum);
+		return log(1.0 - exp(lp));
+	}
+	double f = 1. + z - s, C = f, D = 0.;
+	for (int j = 1; j < 100; ++j) {
+		double a = j * (s - j), b = (j << 1) + 1 + z - s, d;
+		D = b + a * D;
+		if (D < 1e-290) D = 1e-290;
+		C = b + a / C;
+		if (C < 1e-290) C = 1e-290;
+		D = 1. / D;
+		d = C * D;
+		f *= d;
+		if (fabs(d - 1.) < 1e-14) break;
+	}
+	return s * log(z) - z - d_lgamma(s) - log(f);
+}
+
+// log10 p of a chi-square tail as the reference forms it: kf_gammaq(dof1/2, stat/2)/ln 10
+__device__ __forceinline__ double d_chi2_log10p(double dof1, double stat) { return d_gammaq(dof1 / 2, stat / 2) / log(10.0); }
+
+// lower binomial tail log10 P(X <= A) (FET/contables.c:197-209)
+__device__ inline double d_minreads_pvalue(int R, int A, double e)
+{
+	double e1 = log10(e), e2 = log10(1.0 - e);
+	double pvlog = R * e2, sum = pvlog;
+	for (int r = 1; r <= A; r++) {
+		pvlog += log10((double)(R - r + 1)) - log10((double)r) + e1 - e2;
+		if (pvlog < sum) sum += log10(1.0 + exp10(pvlog - sum));
+		else sum = pvlog + log10(1.0 + exp10(sum - pvlog));
+	}
+	return sum;
+}
+
+// upper binomial tail log10 P(X >= A) (FET/contables.c:232-242)
+__device__ inline double d_binomial_pvalue(int R, int A, double e)
+{
+	double e1 = log10(e), e2 = log10(1.0 - e);
+	double pvlog = d_ncr(R, A) + A * e1 + (R - A) * e2, sum = pvlog;
+	for (int r = A + 1; r < R + 1; r++) {
+		pvlog += log10((double)(R - r + 1)) - log10((double)r) + e1 - e2;
+		sum += log10(1.0 + exp10(pvlog - sum));
+	}
+	return sum;
+}
+
+// two-sided 2x2 Fisher exact test, log10 p (FET/contables.c:131-171; the one-sided sums there feed nothing)
+__device__ inline double d_fet(int c1, int r1, int c2, int r2)
+{
+	int minc = 0, maxc = c1 + c2;
+	if (r2 < c1 + c2) minc = c1 + c2 - r2;
+	if (r1 < c1 + c2) maxc = r1;
+	const double ptable = d_ncr(r1, c1) + d_ncr(r2, c2);
+	int c11 = minc, c21 = c1 + c2 - minc;
+	double p1 = d_ncr(r1, c11), p2 = d_ncr(r2, c21), pvalue = -10000000;
+	bool any = false;
+	while (c11 <= maxc) {
+		if (p1 + p2 <= ptable + kCtEps) {
+			if (p1 + p2 <= pvalue) pvalue += log10(1.0 + exp10(p1 + p2 - pvalue));
+			else pvalue = p1 + p2 + log10(1.0 + exp10(pvalue - p1 - p2));
+			any = true;
+		}
+		if (r1 - c11 > 0) p1 += log10((double)(r1 - c11)) - log10((double)(c11 + 1));
+		if (c21 > 0) p2 += log10((double)c21) - log10((double)(r2 - c21 + 1));
+		c11 += 1;
+		c21 -= 1;
+	}
+	if (!any) pvalue = ptable;
+	return pvalue - d_ncr(r1 + r2, c1 + c2);
+}
+
+// Chernoff-bound quality-value p-values for one strand pair (FET/contables.c:342-364)
+__device__ inline void d_chernoff(const int* counts, const double* stats, int refbase, int altbase, double ser, double* P0, double* P1)
+{
+	double p0, p1;
+	if (ser == -1) {
+		double mu0 = stats[altbase] + stats[refbase], mu1 = stats[altbase + 8] + stats[refbase + 8];
+		double d0 = (counts[altbase] == 0 || mu0 == 0) ? 1 : counts[altbase] / mu0 - 1;
+		double d1 = (counts[altbase + 8] == 0 || mu1 == 0) ? 1 : counts[altbase + 8] / mu1 - 1;
+		p0 = d0 <= 0 ? 0 : mu0 * (d0 * log10(2.718281) - (1 + d0) * log10(1 + d0));
+		p1 = d1 <= 0 ? 0 : mu1 * (d1 * log10(2.718281) - (1 + d1) * log10(1 + d1));
+	} else {
+		p0 = d_binomial_pvalue(counts[refbase] + counts[altbase], counts[altbase], ser);
+		p1 = d_binomial_pvalue(counts[refbase + 8] + counts[altbase + 8], counts[altbase + 8], ser);
+	}
+	*P0 = p0;
+	*P1 = p1;
+}
+
+// ---- Philox4x32-10 counter-based generator (one stream per (site, slot, permutation, stratum)) ----
+struct Philox {
+	uint32_t k0, k1;
+	uint32_t c0, c1, c2;
+	uint32_t out[4];
+	int have;
+	__device__ __forceinline__ void init(uint64_t seed, int tid, int pos, int slot, uint32_t perm, uint32_t stratum)
+	{
+		k0 = (uint32_t)seed ^ (uint32_t)pos;
+		k1 = (uint32_t)(seed >> 32) ^ ((uint32_t)tid * 8u + (uint32_t)slot);
+		c0 = perm;
+		c1 = 0;
+		c2 = stratum;
+		have = 0;
+	}
+	__device__ __forceinline__ void refill()
+	{
+		uint32_t a = c0, b = c1, c = c2, d = 0, x = k0, y = k1;
+#pragma unroll
+		for (int r = 0; r < 10; r++) {
+			uint32_t h0 = __umulhi(0xD2511F53u, a), l0 = 0xD2511F53u * a;
+			uint32_t h1 = __umulhi(0xCD9E8D57u, c), l1 = 0xCD9E8D57u * c;
+			a = h1 ^ b ^ x;
+			b = l1;
+			c = h0 ^ d ^ y;
+			d = l0;
+			x += 0x9E3779B9u;
+			y += 0xBB67AE85u;
+		}
+		out[0] = a; out[1] = b; out[2] = c; out[3] = d;
+		c1++;
+		have = 4;
+	}
+	__device__ __forceinline__ uint32_t next()
+	{
+		if (have == 0) refill();
+		uint32_t v = have == 4 ? out[0] : have == 3 ? out[1] : have == 2 ? out[2] : out[3];
+		have--;
+		return v;
+	}
+	// exact uniform integer in [0, M): multiply-shift with rejection
+	__device__ __forceinline__ uint32_t below(uint32_t M)
+	{
+		uint64_t m = (uint64_t)next() * M;
+		uint32_t l = (uint32_t)m;
+		if (l < M) {
+			uint32_t t = (0u - M) % M;
+			while (l < t) {
+				m = (uint64_t)next() * M;
+				l = (uint32_t)m;
+			}
+		}
+		return (uint32_t)(m >> 32);
+	}
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+__device__ __forceinline__ int warp_sum(int v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+}  // namespace crisp

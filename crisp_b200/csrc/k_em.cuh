@@ -1,0 +1,502 @@
+// k_em.cuh — fused likelihood + EM + genotype + pool-statistics kernel: one CTA per (site, allele slot) task that
+// survived k_evaluate, i.e. the work of compute_GLL_pooled (crisp/crispEM.c:356-391):
+//   calculate_pooled_likelihoods_snp   crispEM.c:91-138   (quality-value likelihood; histogram x table contraction)
+//   calculate_pooled_likelihoods_indel crispEM.c:54-87    (count-based likelihood, redone every EM iteration)
+//   EMmethod                           crispEM.c:207-351
+//   calculate_genotypes                crispEM.c:141-203
+//   calculate_pool_statistics          crisp/poolstats.c:5-60 + calculate_uniquereads parsebam/allelecounts.c:42-81
+//
+// Data layout: the three genotype-likelihood planes that feed outputs (all reads, forward, reverse) live in shared
+// memory as G[plane][j][pool] for the whole task, so the EM never touches HBM; the bidirectional plane is only needed
+// at j = 0.  EM work is organised as units (round of 32 pools) x (plane): one lane per pool walks j sequentially, so
+// the per-pool log-sum-exp needs no cross-lane traffic and terms more than 20 decades below the pool's maximum are
+// skipped warp-uniformly (they cannot change a double-precision sum).
+#pragma once
+#include "dmath.cuh"
+#include "engine_types.cuh"
+#include "k_evaluate.cuh"
+
+namespace crisp {
+
+constexpr int kEmMaxWarps = 8;
+constexpr int kMaxRounds = 64;  // pools <= 2048
+
+struct EmShared {
+	// iteration state (written by warp 0, read by all)
+	double lp[3][2];      // log10 p, log10(1-p) per plane
+	double p[3];
+	double LL[3];
+	double E01[3], E10[3];
+	double LLnull0;
+	double part_LL[3][kMaxRounds];
+	double part_pn[3][kMaxRounds];
+	double part_null[kMaxRounds];
+	double part_T[12][kMaxRounds];
+	int part_i[2][kMaxRounds];
+	int part_w[kEmMaxWarps];
+	int exitflag;
+	int iter;
+	int task;
+	double delta, deltaf, hwe;
+};
+
+__device__ __forceinline__ double em_term(const double* Gp, int P, int i, int j, int n, double nc, double l0, double l1)
+{
+	// GENLL + NC + log10(p)*j + log10(1-p)*(n-j)   (crispEM.c:249)
+	return Gp[(size_t)j * P + i] + nc + l0 * j + l1 * (n - j);
+}
+
+template <bool SMEM_G>
+__global__ void __launch_bounds__(kEmMaxWarps * 32) k_em(EngineParams prm)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const DevBatch& b = prm.b;
+	const DevCfg& c = prm.c;
+	const int P = c.P, nmax = c.nmax, J = nmax + 1;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+	const int rounds = (P + 31) >> 5;
+	const size_t plane = (size_t)J * P;
+
+	// ---- shared memory carve-up ----
+	EmShared* sh = reinterpret_cast<EmShared*>(smem_raw);
+	size_t off = (sizeof(EmShared) + 15) & ~size_t(15);
+	double* Gb0 = reinterpret_cast<double*>(smem_raw + off); off += sizeof(double) * P;
+	double* NCs = reinterpret_cast<double*>(smem_raw + off); off += sizeof(double) * J;           // single ploidy class only
+	double* gcnt = reinterpret_cast<double*>(smem_raw + off); off += sizeof(double) * J;          // genotype_counts / HWE terms
+	int32_t* cnt6 = reinterpret_cast<int32_t*>(smem_raw + off); off += sizeof(int32_t) * 6 * P;   // [6][P]: a1 f,r,b ; a2 f,r,b
+	off = (off + 15) & ~size_t(15);
+	uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + off); off += sizeof(uint32_t) * 6 * kNQ * nwarps;
+	off = (off + 15) & ~size_t(15);
+	double* G = SMEM_G ? reinterpret_cast<double*>(smem_raw + off) : prm.gws + (size_t)blockIdx.x * prm.gws_stride;
+	double* Gt = G;
+	double* Gf = G + plane;
+	double* Gr = G + 2 * plane;
+
+	const bool oneclass = c.n_pclass == 1;
+	if (oneclass) for (int j = tid; j < J; j += blockDim.x) NCs[j] = c.NC[j];
+
+	for (;;) {
+		__syncthreads();
+		if (tid == 0) sh->task = atomicAdd(prm.q.counters + 3, 1);
+		__syncthreads();
+		const int task = sh->task;
+		if (task >= prm.q.counters[1]) break;
+		const int o = prm.q.call_tasks[task], s = o / kSlots, slot = o - s * kSlots;
+		const uint8_t* mal = b.maxvec_al + s * 8;
+		int a1, a2, a3;
+		slot_alleles(mal, slot, a1, a2, a3);
+		const int refbase = b.refbase[s];
+		const int row = slot_amb_row(b, s, slot, a2, a3);
+		const bool countlik = (a2 >= 4 || c.use_base_qvs == 0);
+		int ilen = 0, is_ins = 0;
+		if (a2 >= 4 && b.indel_len) { ilen = abs((int)b.indel_len[s * 8 + a2]); is_ins = b.indel_len[s * 8 + a2] > 0; }
+		// indel_bias (crispEM.c:36-49)
+		double het_bias = 0;
+		if (is_ins && ilen >= 1) het_bias = (5.0 + ilen / 2) / (double)(100.0 - 5.0 - ilen / 2);
+		else if (ilen >= 1 && !is_ins) het_bias = 5.0 / (double)(100.0 - 5.0);
+
+		// ---- per-pool counts of the two alleles (ambiguity-adjusted) ----
+		for (int i = tid; i < P; i += blockDim.x) {
+			const int32_t* r = b.indcounts + ((size_t)s * P + i) * kNC;
+			int dd[3] = {0, 0, 0};
+			if (row >= 0) {
+				const int32_t* d = b.amb_dec + ((size_t)row * P + i) * 4;
+				dd[0] = d[0]; dd[1] = d[1]; dd[2] = d[2] + d[3];
+			}
+#pragma unroll
+			for (int k = 0; k < 3; k++) {
+				cnt6[k * P + i] = r[a1 + 8 * k] - (a1 == refbase ? dd[k] : 0);
+				cnt6[(3 + k) * P + i] = r[a2 + 8 * k] - (a2 == refbase ? dd[k] : 0);
+			}
+		}
+		// site totals for the initial indel error rates (crispEM.c:366-374)
+		if (tid == 0) {
+			double E[3];
+			for (int k = 0; k < 3; k++) {
+				int t1 = b.counts[s * kNC + a1 + 8 * k], t2 = b.counts[s * kNC + a2 + 8 * k];
+				if (row >= 0) {
+					// counts[] is reduced by the same reads as indcounts[] (process_indel_variant.c:42,46)
+					int dec = 0;
+					for (int i = 0; i < P; i++) {
+						const int32_t* d = b.amb_dec + ((size_t)row * P + i) * 4;
+						dec += k == 0 ? d[0] : k == 1 ? d[1] : d[2] + d[3];
+					}
+					if (a1 == refbase) t1 -= dec;
+					if (a2 == refbase) t2 -= dec;
+				}
+				E[k] = (double)(t2 + 1.0) / (t1 + t2 + 1.0);
+			}
+			if (E[0] >= 0.005 || E[1] >= 0.005) E[0] = E[1] = E[2] = 0.005;
+			for (int k = 0; k < 3; k++) { sh->E01[k] = E[k]; sh->E10[k] = E[k]; }
+			// starting allele frequency: p[0]/K with the clamp of crispEM.c:360
+			double p0 = prm.o.paf[o] / c.K;
+			if (1.0 - p0 < kMinP) p0 = 1.0 - kMinP;
+			sh->p[0] = sh->p[1] = sh->p[2] = p0;
+			sh->LL[0] = sh->LL[1] = sh->LL[2] = 0.0;
+			sh->exitflag = 0;
+			sh->iter = 0;
+		}
+		__syncthreads();
+
+		// =====================================================================================================
+		// likelihood planes
+		// =====================================================================================================
+		auto count_likelihood = [&]() {
+			// calculate_pooled_likelihoods_indel (crispEM.c:54-87) with the current E01/E10
+			double e01[3], e10[3];
+			for (int k = 0; k < 3; k++) {
+				e01[k] = sh->E01[k]; e10[k] = sh->E10[k];
+				if (e01[k] < kMinP) e01[k] = kMinP; else if (e01[k] > 1.0 - kMinP) e01[k] = 1.0 - kMinP;
+				if (e10[k] < kMinP) e10[k] = kMinP; else if (e10[k] > 1.0 - kMinP) e10[k] = 1.0 - kMinP;
+			}
+			e01[2] = e01[0] * e01[1];
+			e10[2] = e10[0] * e10[1];
+			for (int idx = tid; idx < J * P; idx += blockDim.x) {
+				const int j = idx / P, i = idx - j * P;
+				const int n = c.ploidy[i];
+				if (j > n) continue;
+				double f = (double)j / n;
+				f /= (1 + het_bias);
+				double ef = (1.0 - e01[0]) * (1.0 - f) + e10[0] * f, er = (1.0 - e01[1]) * (1.0 - f) + e10[1] * f, eb = (1.0 - e01[2]) * (1.0 - f) + e10[2] * f;
+				double gf = cnt6[0 * P + i] * log10(ef) + cnt6[3 * P + i] * log10(1.0 - ef);
+				double gr = cnt6[1 * P + i] * log10(er) + cnt6[4 * P + i] * log10(1.0 - er);
+				double gb = cnt6[2 * P + i] * log10(eb) + cnt6[5 * P + i] * log10(1.0 - eb);
+				Gf[idx] = gf;
+				Gr[idx] = gr;
+				Gt[idx] = gf + gr + gb;
+				if (j == 0) Gb0[i] = gb;
+			}
+			__syncthreads();
+			if (tid == 0) for (int k = 0; k < 3; k++) { sh->E01[k] = e01[k]; sh->E10[k] = e10[k]; }  // clamps are applied in place (:65-69)
+		};
+
+		if (countlik) {
+			count_likelihood();
+			// EMmethod starts from its own E01 = E10 = 0.001 (crispEM.c:211); the count-based values above only
+			// shape the first likelihood (crispEM.c:362-375)
+			if (tid == 0) for (int k = 0; k < 3; k++) { sh->E01[k] = 0.001; sh->E10[k] = 0.001; }
+		} else {
+			// calculate_pooled_likelihoods_snp: per pool, histogram the packed reads over (strand class, allele, quality)
+			// and contract with the table T[allele][quality][j]
+			uint32_t* h = hist + (size_t)warp * 6 * kNQ;
+			for (int i = warp; i < P; i += nwarps) {
+				for (int k = lane; k < 6 * kNQ; k += 32) h[k] = 0;
+				__syncwarp();
+				const uint32_t r0 = b.read_off[(size_t)s * P + i], r1 = b.read_off[(size_t)s * P + i + 1];
+				for (uint32_t rb = r0; rb < r1; rb += 32) {
+					const uint32_t r = rb + lane;
+					const bool in = r < r1;
+					uint32_t w = in ? (uint32_t)__ldg(b.reads + r) : 0u;
+					const int base = (w >> 8) & 3;
+					const int which = base == a1 ? 0 : (base == a2 ? 1 : -1);
+					const bool use = in && which >= 0;
+					const int cls = (w >> 11) & 1 ? 2 : ((w >> 10) & 1);
+					const int key = use ? (cls * 2 + which) * kNQ + (w & 0x7f) : -1 - lane;
+					const unsigned peers = __match_any_sync(0xffffffffu, key);
+					if (use && lane == __ffs(peers) - 1) h[key] += __popc(peers);
+				}
+				__syncwarp();
+				const int n = c.ploidy[i];
+				const double* Tp = c.T + (size_t)c.pclass[i] * 2 * kNQ * J;
+				for (int jc = 0; jc * 32 < n + 1; jc++) {
+					const int j = jc * 32 + lane;
+					const bool jv = j <= n;
+					double acc[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+					for (int cls = 0; cls < 3; cls++) {
+						for (int which = 0; which < 2; which++) {
+							const uint32_t* hh = h + (cls * 2 + which) * kNQ;
+							const double* Tw = Tp + (size_t)which * kNQ * J;
+							for (int qc = 0; qc < kNQ; qc += 32) {
+								const uint32_t hv = hh[qc + lane];
+								unsigned m = __ballot_sync(0xffffffffu, hv != 0);
+								while (m) {
+									const int bq = __ffs(m) - 1;
+									m &= m - 1;
+									const double cntv = (double)__shfl_sync(0xffffffffu, hv, bq);
+									if (jv) acc[cls] += cntv * __ldg(Tw + (size_t)(qc + bq) * J + j);
+								}
+							}
+						}
+					}
+					if (jv) {
+						const size_t idx = (size_t)j * P + i;
+						Gf[idx] = acc[0];
+						Gr[idx] = acc[1];
+						Gt[idx] = acc[0] + acc[1] + acc[2];
+						if (j == 0) Gb0[i] = acc[2];
+					}
+				}
+				__syncwarp();
+			}
+			__syncthreads();
+		}
+
+		// =====================================================================================================
+		// EM iterations (crispEM.c:233-314)
+		// =====================================================================================================
+		for (;;) {
+			if (tid < 3) {
+				sh->lp[tid][0] = log10(sh->p[tid]);
+				sh->lp[tid][1] = log10(1.0 - sh->p[tid]);
+			}
+			__syncthreads();
+			const int nunits = rounds * 3;
+			for (int u = warp; u < nunits; u += nwarps) {
+				const int pl = u / rounds, rd = u - pl * rounds;
+				const int i = rd * 32 + lane;
+				const bool act = i < P;
+				const int ii = act ? i : P - 1;
+				const int n = c.ploidy[ii];
+				const double* Gp = G + (size_t)pl * plane;
+				const double* ncp = oneclass ? NCs : c.NC + (size_t)c.pclass[ii] * J;
+				const double l0 = sh->lp[pl][0], l1 = sh->lp[pl][1];
+				double m = -1e300;
+				for (int j = 0; j <= nmax; j++) {
+					if (j <= n) m = fmax(m, em_term(Gp, P, ii, j, n, ncp[j], l0, l1));
+				}
+				double S = 0.0, Wj = 0.0;
+				double T00[3] = {0, 0, 0}, T01[3] = {0, 0, 0}, T10[3] = {0, 0, 0}, T11[3] = {0, 0, 0};
+				for (int j = 0; j <= nmax; j++) {
+					const double d = (j <= n) ? em_term(Gp, P, ii, j, n, ncp[j], l0, l1) - m : -1e300;
+					if (d > -kExpCut) {
+						const double e = exp10(d);
+						S += e;
+						Wj += (double)j * e;
+						if (countlik && pl == 0) {
+							const double f = (double)j / n;
+#pragma unroll
+							for (int k = 0; k < 3; k++) {
+								const double E01 = sh->E01[k], E10 = sh->E10[k];
+								const double den1 = (1.0 - f) * (1.0 - E01) + f * E10, den2 = (1.0 - f) * E01 + f * (1.0 - E10);
+								T00[k] += e * (1.0 - f) * (1.0 - E01) / den1;
+								T10[k] += e * f * E10 / den1;
+								T11[k] += e * f * (1.0 - E10) / den2;
+								T01[k] += e * (1.0 - f) * E01 / den2;
+							}
+						}
+					}
+				}
+				double L = m + log10(S);
+				double llc = 0.0, pn = 0.0, nul = 0.0;
+				if (act) {
+					llc = L;
+					pn = Wj / S;
+					if (pl == 0) nul = Gt[ii];
+					else if (pl == 1) llc += Gr[ii] + Gb0[ii];   // LLtotalf += GENLLr[i][0] + GENLLb[i][0]  (:262)
+					else llc += Gf[ii] + Gb0[ii];                // LLtotalr += GENLLf[i][0] + GENLLb[i][0]  (:261)
+				}
+				llc = warp_sum(llc);
+				pn = warp_sum(pn);
+				if (pl == 0) nul = warp_sum(nul);
+				if (countlik && pl == 0) {
+#pragma unroll
+					for (int k = 0; k < 3; k++) {
+						const double c1 = act ? (double)cnt6[k * P + ii] / S : 0.0, c2 = act ? (double)cnt6[(3 + k) * P + ii] / S : 0.0;
+						double t00 = warp_sum(c1 * T00[k]), t10 = warp_sum(c1 * T10[k]), t11 = warp_sum(c2 * T11[k]), t01 = warp_sum(c2 * T01[k]);
+						if (lane == 0) { sh->part_T[k][rd] = t00; sh->part_T[3 + k][rd] = t01; sh->part_T[6 + k][rd] = t10; sh->part_T[9 + k][rd] = t11; }
+					}
+				}
+				if (lane == 0) {
+					sh->part_LL[pl][rd] = llc;
+					sh->part_pn[pl][rd] = pn;
+					if (pl == 0) sh->part_null[rd] = nul;
+				}
+			}
+			__syncthreads();
+			// ---- finish the iteration: warp 0, lane pl handles plane pl ----
+			if (warp == 0) {
+				double LLn = 0.0, pn = 0.0, prev = 0.0;
+				if (lane < 3) {
+					for (int r = 0; r < rounds; r++) { LLn += sh->part_LL[lane][r]; pn += sh->part_pn[lane][r]; }
+					prev = sh->LL[lane];
+					pn /= c.K;
+					if (pn < kMinP) pn = kMinP;
+					if (1.0 - pn <= kMinP) pn = 1.0 - kMinP;
+				}
+				// convergence: fabsf() of the double differences against double thresholds (crispEM.c:304)
+				const double dl = (double)fabsf((float)(LLn - prev));
+				const double d0 = __shfl_sync(0xffffffffu, dl, 0), d1 = __shfl_sync(0xffffffffu, dl, 1), d2 = __shfl_sync(0xffffffffu, dl, 2);
+				if (lane < 3) { sh->LL[lane] = LLn; sh->p[lane] = pn; }
+				if (lane == 0) {
+					const int it = ++sh->iter;
+					double nul = 0.0;
+					for (int r = 0; r < rounds; r++) nul += sh->part_null[r];
+					sh->LLnull0 = nul;
+					if (countlik) {
+						for (int k = 0; k < 3; k++) {
+							double t00 = 0, t01 = 0, t10 = 0, t11 = 0;
+							for (int r = 0; r < rounds; r++) { t00 += sh->part_T[k][r]; t01 += sh->part_T[3 + k][r]; t10 += sh->part_T[6 + k][r]; t11 += sh->part_T[9 + k][r]; }
+							double e01 = (t01 + 1.5 - 1) / (t01 + t00 + 1.5 + 50 - 1), e10 = (t10 + 1.5 - 1) / (t10 + t11 + 50 + 1.5 - 1);
+							if (e10 > 0.05) e10 = 0.05;
+							sh->E01[k] = e01;
+							sh->E10[k] = e10;
+						}
+					}
+					if ((it >= 2 && d0 <= 0.0001 && d1 <= 0.01 && d2 <= 0.01) || it >= 1000) sh->exitflag = 1;
+				}
+			}
+			__syncthreads();
+			if (countlik) count_likelihood();  // crispEM.c:298, also on the exit iteration
+			if (sh->exitflag) break;
+		}
+
+		// =====================================================================================================
+		// statistics of the fit (crispEM.c:321-349)
+		// =====================================================================================================
+		if (tid == 0) {
+			const double LLt = sh->LL[0], LLf = sh->LL[1], LLr = sh->LL[2];
+			const double deltaf = (LLf > LLr) ? LLf - LLt - log10(2.0) : LLr - LLt - log10(2.0);
+			const double ALPHA = c.alpha_prior;
+			const double LLrefadd = sh->LLnull0 + log10(1.0 - ALPHA);
+			double LL = LLt + log10(ALPHA);
+			if (LLrefadd < LL) LL += log10(1.0 + exp10(LLrefadd - LL));
+			else LL = LLrefadd + log10(1.0 + exp10(LL - LLrefadd));
+			sh->delta = LL - LLrefadd;
+			sh->deltaf = deltaf;
+			sh->hwe = 0.0;
+		}
+		__syncthreads();
+		const double delta = sh->delta, pfin = sh->p[0];
+		const bool called = delta >= 2;
+		int varpools = 0;
+		if (called) {
+			// ---- calculate_genotypes: argmax / runner-up per pool, posterior genotype counts, HWE ----
+			const double l0 = log10(pfin), l1 = log10(1.0 - pfin);
+			double* post = Gf;  // forward plane is no longer needed: reuse as posterior[j][pool]
+			for (int rd = warp; rd < rounds; rd += nwarps) {
+				const int i = rd * 32 + lane;
+				const bool act = i < P;
+				const int ii = act ? i : P - 1;
+				const int n = c.ploidy[ii];
+				const double* ncp = oneclass ? NCs : c.NC + (size_t)c.pclass[ii] * J;
+				double best = -100000, second = -100000;
+				int bg = 0;
+				for (int j = 0; j <= n; j++) {
+					const double t = em_term(Gt, P, ii, j, n, ncp[j], l0, l1);
+					if (t > best) { second = best; bg = j; best = t; }
+					else if (t > second) second = t;
+				}
+				// the running log-sum-exp of :168-169 equals max + log10(sum 10^(t-max)) up to rounding
+				double S = 0.0;
+				for (int j = 0; j <= n; j++) {
+					const double d = em_term(Gt, P, ii, j, n, ncp[j], l0, l1) - best;
+					if (d > -kExpCut) S += exp10(d);
+				}
+				const double Lb = best + log10(S);
+				for (int j = 0; j <= nmax; j++) {
+					double v = 0.0;
+					if (act && j <= n) {
+						const double d = em_term(Gt, P, ii, j, n, ncp[j], l0, l1) - Lb;
+						if (d > -kExpCut - 3) v = exp10(d);
+					}
+					if (act) post[(size_t)j * P + ii] = v;
+				}
+				if (act) {
+					prm.o.ac[(size_t)task * P + i] = bg;
+					prm.o.qv[(size_t)task * P + i] = 10 * (best - second);
+				}
+				const int vp = warp_sum(act && bg > 0 ? 1 : 0), acs = warp_sum(act ? bg : 0);
+				if (lane == 0) { sh->part_i[0][rd] = vp; sh->part_i[1][rd] = acs; }
+			}
+			__syncthreads();
+			if (c.varpoolsize == 0) {
+				// HWE chi-square over genotype classes with expected count >= 2 (crispEM.c:187-199)
+				const int n0 = c.ploidy[0];
+				for (int j = tid; j <= n0; j += blockDim.x) {
+					double gc = 0.0;
+					for (int i = 0; i < P; i++) gc += post[(size_t)j * P + i];
+					const double ec = exp10(c.NC[j] + j * l0 + (n0 - j) * l1 + log10((double)P));
+					gcnt[j] = ec >= 2 ? (gc - ec) * (gc - ec) / ec : -1.0;
+				}
+				__syncthreads();
+				if (tid == 0) {
+					double stat = 0.0, dof = 0.0;
+					for (int j = 0; j <= n0; j++) if (gcnt[j] >= 0.0) { stat += gcnt[j]; dof += 1; }
+					sh->hwe = (stat > 0 && dof >= 2) ? d_gammaq((dof - 1) / 2, stat / 2) / log(10.0) : 0.0;
+				}
+			}
+			// ---- calculate_pool_statistics: read-evidence filter per pool ----
+			const uint32_t alo = b.alt_off ? b.alt_off[s * kSlots + slot] : 0, ahi = b.alt_off ? b.alt_off[s * kSlots + slot + 1] : 0;
+			const int MR = c.min_reads;
+			int vpl = 0;
+			for (int i = warp; i < P; i += nwarps) {
+				const int f = cnt6[3 * P + i], r = cnt6[4 * P + i], bd = cnt6[5 * P + i];
+				if (f + r + bd < 2) continue;
+				// entries of this pool (list is sorted by pool): lower bounds by binary search
+				uint32_t lo = alo, hi = ahi;
+				while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (b.alt_reads[mid].pool < i) lo = mid + 1; else hi = mid; }
+				uint32_t e0 = lo;
+				hi = ahi;
+				while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (b.alt_reads[mid].pool <= i) lo = mid + 1; else hi = mid; }
+				int m = (int)(lo - e0);
+				if (m > f + r + bd) m = f + r + bd;  // `i < reads` cap, allelecounts.c:53
+				int uq = 0, mid = 0;
+				for (int e = lane; e < m; e += 32) {
+					const crispgpu_altread x = b.alt_reads[e0 + e];
+					bool first = true;
+					for (int e2 = 0; e2 < e; e2++) {
+						const crispgpu_altread y = b.alt_reads[e0 + e2];
+						if (y.strand == x.strand && y.offset == x.offset) { first = false; break; }
+					}
+					uq += first ? 1 : 0;
+					if (x.offset >= 5 && (int)x.aligned - (int)x.offset >= 5) mid++;
+				}
+				uq = warp_sum(uq);
+				mid = warp_sum(mid);
+				if (m == 0) uq = 1;  // *unique starts at 1 (allelecounts.c:45)
+				int varpool = 0;
+				if (f + r + bd >= MR && mid > 0 && uq >= MR - 1) varpool = 1;
+				else if (f + r + bd >= MR - 1 && f + bd > 0 && r + bd > 0 && mid > 0 && uq >= MR - 1) varpool = 1;
+				vpl += varpool;
+			}
+			// combine per-warp pool counts
+			__syncthreads();
+			if (lane == 0) sh->part_w[warp] = vpl;
+			__syncthreads();
+			if (tid == 0) for (int w = 0; w < nwarps; w++) varpools += sh->part_w[w];
+		}
+		__syncthreads();
+		if (tid == 0) {
+			prm.o.af_ml[o] = pfin;
+			prm.o.delta[o] = delta;
+			prm.o.deltaf[o] = sh->deltaf;
+			prm.o.hwe[o] = sh->hwe;
+			prm.o.em_iters[o] = sh->iter;
+			prm.o.call_row[o] = called ? task : -1;
+			if (called) {
+				int vp = 0, acs = 0;
+				for (int r = 0; r < rounds; r++) { vp += sh->part_i[0][r]; acs += sh->part_i[1][r]; }
+				prm.o.variantpools[o] = vp;
+				prm.o.allelecount[o] = acs;
+				prm.o.varpools[o] = varpools;
+				prm.o.status[o] = CRISPGPU_SLOT_CALLED;
+			}
+		}
+	}
+}
+
+// likelihood table T[pclass][which][q][j] (crispEM.c:110,117-118): which=0 -> log10 e, which=1 -> log10(1-e)
+__global__ void k_build_T(double* T, const int32_t* class_ploidy, int n_pclass, int J, int qv_offset, double beta)
+{
+	const size_t total = (size_t)n_pclass * kNQ * J;
+	for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+		const int j = (int)(idx % J);
+		const int q = (int)((idx / J) % kNQ);
+		const int pc = (int)(idx / ((size_t)J * kNQ));
+		const int n = class_ploidy[pc];
+		double v0 = 0.0, v1 = 0.0;
+		if (j <= n) {
+			const double ep = pow(0.1, ((double)q - qv_offset) / 10);
+			double f = (double)j * (1.0 - beta);
+			f /= f + (double)(n - j) * beta;
+			const double e = (1.0 - ep) * (1.0 - f) + ep * f;
+			v0 = log10(e);
+			v1 = log10(1.0 - e);
+		}
+		T[((size_t)(pc * 2 + 0) * kNQ + q) * J + j] = v0;
+		T[((size_t)(pc * 2 + 1) * kNQ + q) * J + j] = v1;
+	}
+}
+
+}  // namespace crisp

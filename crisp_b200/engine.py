@@ -1,0 +1,178 @@
+"""Host-side mirror of the C ABI: `Engine` drives crisp_b200/csrc/libcrispgpu.so through ctypes.
+
+This is the replacement for the per-site call `newCRISPcaller(...)` (variantcalls.c:115): the front end packs
+candidate sites into a `Batch`, `Engine.run` returns the fields print_pooledvariant (crisp/newcrispprint.c:347)
+consumes.  There is no CPU fallback: a missing library or a missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .abi import Batch, CBatch, Config, CResults, EngineConfig, Results, Timing
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libcrispgpu.so")
+
+EXPORTS = [
+    "crispgpu_config_defaults", "crispgpu_create", "crispgpu_destroy", "crispgpu_submit", "crispgpu_wait",
+    "crispgpu_upload", "crispgpu_run_resident", "crispgpu_get_timing", "crispgpu_last_error",
+    "crispgpu_host_alloc", "crispgpu_host_free", "crispgpu_abi_version", "crispgpu_device_count",
+]
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def load_library() -> C.CDLL:
+    """Load libcrispgpu.so (built in-tree by `python -m crisp_b200.build`); raises if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(f"{LIB_PATH} is missing: build it with `python -m crisp_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.crispgpu_config_defaults.argtypes = [C.POINTER(Config)]
+    lib.crispgpu_config_defaults.restype = None
+    lib.crispgpu_create.argtypes = [C.POINTER(Config), C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.crispgpu_create.restype = C.c_int
+    lib.crispgpu_destroy.argtypes = [C.c_void_p]
+    lib.crispgpu_destroy.restype = None
+    lib.crispgpu_submit.argtypes = [C.c_void_p, C.POINTER(CBatch), C.POINTER(C.c_int64)]
+    lib.crispgpu_submit.restype = C.c_int
+    lib.crispgpu_wait.argtypes = [C.c_void_p, C.c_int64, C.POINTER(CResults)]
+    lib.crispgpu_wait.restype = C.c_int
+    lib.crispgpu_upload.argtypes = [C.c_void_p, C.POINTER(CBatch)]
+    lib.crispgpu_upload.restype = C.c_int
+    lib.crispgpu_run_resident.argtypes = [C.c_void_p, C.c_int, C.POINTER(CResults)]
+    lib.crispgpu_run_resident.restype = C.c_int
+    lib.crispgpu_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
+    lib.crispgpu_get_timing.restype = C.c_int
+    lib.crispgpu_last_error.argtypes = [C.c_void_p]
+    lib.crispgpu_last_error.restype = C.c_char_p
+    lib.crispgpu_host_alloc.argtypes = [C.c_size_t]
+    lib.crispgpu_host_alloc.restype = C.c_void_p
+    lib.crispgpu_host_free.argtypes = [C.c_void_p]
+    lib.crispgpu_host_free.restype = None
+    lib.crispgpu_abi_version.restype = C.c_int
+    lib.crispgpu_device_count.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def pinned_like(a: np.ndarray) -> np.ndarray:
+    """Copy of `a` in pinned host memory (crispgpu_host_alloc), so crispgpu_submit's copies are asynchronous."""
+    lib = load_library()
+    nbytes = max(a.nbytes, 1)
+    ptr = lib.crispgpu_host_alloc(nbytes)
+    if not ptr:
+        raise EngineError("crispgpu_host_alloc failed")
+    buf = (C.c_char * nbytes).from_address(ptr)
+    out = np.frombuffer(buf, dtype=a.dtype, count=a.size).reshape(a.shape)
+    out[...] = a
+    out_ref = _PinnedOwner(ptr, lib)
+    # keep the owner alive with the array
+    _pinned_owners[id(out)] = (out_ref, out)
+    return out
+
+
+_pinned_owners: dict = {}
+
+
+class _PinnedOwner:
+    def __init__(self, ptr, lib):
+        self.ptr, self.lib = ptr, lib
+
+    def __del__(self):
+        try:
+            self.lib.crispgpu_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pin_batch(batch: Batch) -> Batch:
+    """A copy of the batch whose arrays live in pinned memory."""
+    from .abi import _BATCH_ARRAYS
+
+    arrays = {}
+    for name, _, _ in _BATCH_ARRAYS:
+        a = getattr(batch, name)
+        if a is not None:
+            arrays[name] = pinned_like(a)
+    out = Batch.__new__(Batch)
+    out.n_pools = batch.n_pools
+    for name, _, _ in _BATCH_ARRAYS:
+        setattr(out, name, arrays.get(name))
+    out.n_sites = batch.n_sites
+    out.n_amb = batch.n_amb
+    return out
+
+
+class Engine:
+    """One engine context bound to one CUDA device (`crispgpu_ctx`)."""
+
+    def __init__(self, cfg: EngineConfig, device: int = 0, stream: int | None = None):
+        self.lib = load_library()
+        self.cfg = cfg
+        self._ccfg = cfg.to_c()
+        h = C.c_void_p()
+        rc = self.lib.crispgpu_create(C.byref(self._ccfg), device, C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != 0:
+            raise EngineError(f"crispgpu_create failed: status {rc} (no usable sm_100 device?)" if rc == -2 else f"crispgpu_create failed: status {rc}")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.crispgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise EngineError(f"{what} failed: status {rc}: {self.lib.crispgpu_last_error(self.h).decode()}")
+
+    # ---- the call a front end makes: host batch in, host results out ----
+    def submit(self, batch: Batch) -> int:
+        cb = batch.as_c()
+        t = C.c_int64(0)
+        self._check(self.lib.crispgpu_submit(self.h, C.byref(cb), C.byref(t)), "crispgpu_submit")
+        self._inflight = (cb, batch)
+        return t.value
+
+    def wait(self, ticket: int, copy: bool = True):
+        cres = CResults()
+        self._check(self.lib.crispgpu_wait(self.h, ticket, C.byref(cres)), "crispgpu_wait")
+        self._inflight = None
+        return Results.from_c(cres, self.cfg.n_pools) if copy else cres
+
+    def run(self, batch: Batch) -> Results:
+        return self.wait(self.submit(batch))
+
+    # ---- device-resident path (kernel timing) ----
+    def upload(self, batch: Batch) -> None:
+        cb = batch.as_c()
+        self._check(self.lib.crispgpu_upload(self.h, C.byref(cb)), "crispgpu_upload")
+
+    def run_resident(self, fetch: bool = False):
+        cres = CResults()
+        self._check(self.lib.crispgpu_run_resident(self.h, 1 if fetch else 0, C.byref(cres)), "crispgpu_run_resident")
+        return Results.from_c(cres, self.cfg.n_pools) if fetch else None
+
+    def timing(self) -> dict:
+        t = Timing()
+        self._check(self.lib.crispgpu_get_timing(self.h, C.byref(t)), "crispgpu_get_timing")
+        return {name: getattr(t, name) for name, _ in Timing._fields_}
+
+
+def device_count() -> int:
+    return load_library().crispgpu_device_count()

@@ -196,9 +196,18 @@ def synth_batch(
             dec = rng.binomial(avail, min(0.9, 0.01 * hp))
             row = np.zeros((P, 4), np.int32)
             row[:, :2] = dec
+            # sum of error probabilities of the removed reads = the first dec[i][st] reference reads of that strand
+            eps = np.zeros((P, 2))
+            for i in range(P):
+                lo, hi = read_off[s * P + i], read_off[s * P + i + 1]
+                for st in range(2):
+                    if dec[i, st] == 0:
+                        continue
+                    m = np.nonzero((base[lo:hi] == rb) & (strand[lo:hi] == st) & (bidir[lo:hi] == 0))[0][: dec[i, st]]
+                    eps[i, st] = (10.0 ** (-q[lo:hi][m] / 10.0)).sum()
             amb_idx[s, ksl] = len(amb_rows)
             amb_rows.append(row)
-            amb_eps.append(dec * 10.0 ** (-3.0))
+            amb_eps.append(eps)
 
     # drop non-candidate sites
     keep_sites = np.nonzero(cand)[0]

@@ -1,0 +1,97 @@
+"""Host-side logic: synthetic generator, allele sort, batch slicing, region sharding and the rank-0 merge
+(world_size-2 gloo run)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from crisp_b200.abi import EngineConfig, concat_batches
+from crisp_b200.shard import merge_results, partition_sites, shard_batch
+from crisp_b200.synth import sort_alleles, synth_batch
+from oracle.loader import RNG_PHILOX, OracleEngine
+from util import compare_results
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_synth_is_deterministic_and_candidate_only():
+    a = synth_batch(200, 8, 20, 60, seed=3, variant_frac=0.4, bidir_frac=0.1)
+    b = synth_batch(200, 8, 20, 60, seed=3, variant_frac=0.4, bidir_frac=0.1)
+    assert a.n_sites == b.n_sites and np.array_equal(a.reads, b.reads) and np.array_equal(a.indcounts, b.indcounts)
+    ic = a.indcounts.reshape(a.n_sites, 8, 3, 8).sum(axis=2)
+    for s in range(a.n_sites):
+        nonref = [x for x in range(8) if x != a.refbase[s]]
+        assert (ic[s][:, nonref] >= 3).any()  # variantcalls.c:85,92
+    # counts are consistent with the packed stream
+    ro = a.read_off.astype(np.int64)
+    for s in (0, a.n_sites - 1):
+        for i in range(8):
+            w = a.reads[ro[s * 8 + i]:ro[s * 8 + i + 1]].astype(np.int64)
+            cls = np.where((w >> 11) & 1, 2, (w >> 10) & 1)
+            key = ((w >> 8) & 3) + 8 * cls
+            assert np.array_equal(np.bincount(key, minlength=24), a.indcounts.reshape(a.n_sites, 8, 24)[s, i])
+
+
+def test_sort_alleles_matches_reference_rule():
+    # reference first, then exchange sort by count descending (allelecounts.c:155-187)
+    counts = np.array([[5, 50, 7, 7, 0, 0, 3, 0], [9, 1, 9, 30, 2, 0, 0, 0]])
+    al, ct = sort_alleles(counts, np.array([1, 3]))
+    assert al[0].tolist()[:5] == [1, 2, 3, 0, 6] and ct[0].tolist()[:5] == [50, 7, 7, 5, 3]
+    assert al[1].tolist()[:4] == [3, 0, 2, 4] or al[1].tolist()[:4] == [3, 2, 0, 4]
+    assert ct[1].tolist()[:5] == [30, 9, 9, 2, 1]
+
+
+def test_select_concat_roundtrip():
+    b = synth_batch(80, 6, 16, 50, seed=9, variant_frac=0.5, indel_frac=0.4)
+    idx = np.arange(b.n_sites)
+    parts = [b.select(idx[:30]), b.select(idx[30:])]
+    c = concat_batches(parts)
+    for name in ("tid", "pos", "refbase", "maxvec_al", "maxvec_ct", "counts", "indcounts", "read_off", "reads", "alt_off"):
+        assert np.array_equal(getattr(b, name), getattr(c, name)), name
+    assert np.array_equal(b.alt_reads, c.alt_reads)
+
+
+def test_partition_is_contiguous_and_balanced():
+    rng = np.random.default_rng(0)
+    tid = rng.integers(0, 3, 1000)
+    pos = rng.integers(0, 10**6, 1000)
+    parts = partition_sites(tid, pos, 8)
+    allidx = np.concatenate(parts)
+    assert sorted(allidx.tolist()) == list(range(1000))
+    keys = tid[allidx].astype(np.int64) * 10**7 + pos[allidx]
+    assert np.all(np.diff(keys) >= 0)
+    assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    w = rng.random(1000)
+    wp = partition_sites(tid, pos, 4, weight=w)
+    loads = [w[p].sum() for p in wp]
+    assert max(loads) - min(loads) < 0.05 * w.sum()
+
+
+def test_sharded_run_equals_single_run():
+    """Results do not depend on how sites are sharded (Philox streams are keyed by site, not by position in the batch)."""
+    cfg = EngineConfig(ploidy=np.full(8, 20), options=dict(chisq_permutation=1, max_iter=300))
+    b = synth_batch(90, 8, 20, 60, seed=4, variant_frac=0.5)
+    orc = OracleEngine(cfg)
+    whole = orc.run(b, mode=RNG_PHILOX)
+    parts, idxs = [], []
+    for r in range(3):
+        sub, idx = shard_batch(b, 3, r)
+        parts.append(orc.run(sub, mode=RNG_PHILOX))
+        idxs.append(idx)
+    merged = merge_results(parts, idxs, b.n_sites, 8)
+    compare_results(merged, whole, tol=0.0, label="sharded")
+    assert np.array_equal(merged.perm_k, whole.perm_k) and np.array_equal(merged.perm_hits, whole.perm_hits)
+
+
+def test_two_rank_gloo_gather():
+    """world_size-2 run of the N>1 host path on CPU (gloo): each rank processes its region with the checker standing
+    in for the device, rank 0 merges in coordinate order."""
+    script = os.path.join(ROOT, "tests", "_gloo_worker.py")
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.path.join(ROOT, "tests"))
+    res = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+         "--master-port", "29611", script], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "GLOO_MERGE_OK" in res.stdout

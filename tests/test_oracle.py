@@ -1,0 +1,144 @@
+"""CPU tests of the checkers themselves: the C restatement (oracle/crisp_oracle.c) against
+  (1) the committed golden vectors produced by the unmodified reference (tests/golden/, scripts/make_golden.py),
+  (2) the reference itself when oracle/_ref is present (built from /root/reference here; travels prebuilt to the GPU box),
+  (3) the known-answer values recorded in SURVEY.md §8c.
+The reference ships no tests of its own; these pin the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from crisp_b200.abi import EngineConfig
+from crisp_b200.synth import survey_demo_batch, synth_batch
+from golden_io import golden_names, load_golden
+from oracle.loader import MODE_CALLER, MODE_SLOTS, RNG_DRAND48, RNG_PHILOX, OracleEngine, RefEngine, have_ref
+from util import FP_FIELDS, INT_FIELDS, compare_results
+
+needs_ref = pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+
+# SURVEY.md §8c level 2: values printed by the reference's own functions
+KATS = [
+    ("ncr", (10, 3), 2.0791812460476247), ("ncr", (100, 50), 29.00385390977171), ("ncr", (200, 7), 12.358676364700507),
+    ("fet", (3, 50, 10, 60), -0.86482538043645185), ("fet", (0, 100, 8, 90), -2.6702592500383115),
+    ("minreads_pvalue", (100, 2, 0.05), -0.92715117745995934), ("minreads_pvalue", (57, 4, 0.05), -0.073356255354241187),
+    ("binomial_pvalue", (100, 7, 0.01), -4.1482302106869877), ("kf_lgamma", (4.5,), 2.4537365708424428),
+    ("kf_gammaq", (2.5, 10.0), -6.684827300476976), ("kf_gammaq", (2.5, 0.5), -0.038152879313638192),
+]
+SIGS = {
+    "ncr": [C.c_int, C.c_int], "fet": [C.c_int] * 4, "minreads_pvalue": [C.c_int, C.c_int, C.c_double],
+    "binomial_pvalue": [C.c_int, C.c_int, C.c_double], "kf_lgamma": [C.c_double], "kf_gammaq": [C.c_double, C.c_double],
+}
+
+
+def _cfg(P=6, n=20, **opts):
+    return EngineConfig(ploidy=np.full(P, n), options=opts)
+
+
+@pytest.mark.parametrize("fn,args,want", KATS)
+def test_scalar_known_answers(fn, args, want):
+    orc = OracleEngine(_cfg())
+    got = orc.scalar(fn, C.c_double, SIGS[fn])(*args)
+    assert got == pytest.approx(want, rel=1e-14, abs=1e-15)
+    if have_ref():
+        assert RefEngine(_cfg()).scalar(fn, C.c_double, SIGS[fn])(*args) == got
+
+
+def test_gammaq_chi2_tail_kat():
+    # kf_gammaq(4.5, 27.85)/ln 10 = -8.04787816035231
+    orc = OracleEngine(_cfg())
+    g = orc.scalar("kf_gammaq", C.c_double, SIGS["kf_gammaq"])(4.5, 27.85)
+    assert g / np.log(10) == pytest.approx(-8.04787816035231, rel=1e-13)
+
+
+def test_survey_demo_site():
+    """The six-pool site of SURVEY.md §8c level 3, values printed by the reference during the survey."""
+    r = OracleEngine(_cfg()).run(survey_demo_batch(), mode=RNG_DRAND48)
+    assert r.status[0, 0] == 4 and r.varalleles[0] == 1
+    assert r.paf[0, 0] == 1.3999860001399986
+    assert r.ctpval[0, 0] == -5.0082859818506558 and r.chi2pval[0, 0] == -5.0082859818506558
+    assert r.af_ml[0, 0] == 0.012768332219397762
+    assert r.delta[0, 0] == 5.3010728026494967
+    assert r.deltaf[0, 0] == -2.0304825902872743
+    assert r.hwe[0, 0] == 0
+    assert r.ac[0].tolist() == [1, 0, 0, 0, 0, 0]
+    np.testing.assert_allclose(r.qv[0], [10.9095566534, 28.0831570167, 28.0946013699, 28.0825585559, 28.1000096436, 0.865157209598], rtol=1e-11)
+
+
+def test_survey_demo_permutation_drand48():
+    # CHISQ_PERMUTATION=1, srand48(12345): 4 hits in all 20000 permutations -> log10(5/20001)
+    r = OracleEngine(_cfg(chisq_permutation=1)).run(survey_demo_batch(), mode=RNG_DRAND48, seed=12345)
+    assert r.ctpval[0, 0] == -3.6021034186048251
+    assert r.perm_k[0, 0] == 20001 and r.perm_hits[0, 0] == 4
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_reproduces_golden(name):
+    cfg, batch, want, seed = load_golden(name)
+    got = OracleEngine(cfg).run(batch, mode=RNG_DRAND48, seed=seed)
+    for f in INT_FIELDS:
+        assert np.array_equal(getattr(got, f), getattr(want, f)), f
+    for f in FP_FIELDS:
+        assert np.array_equal(getattr(got, f), getattr(want, f)), f  # bit-exact: same libm, same operation order
+    assert got.n_calls == want.n_calls
+    assert np.array_equal(got.ac, want.ac) and np.array_equal(got.qv, want.qv)
+
+
+SCENARIOS = [
+    ("default", 10, 20, 100, {}, dict(variant_frac=0.4, bidir_frac=0.1, second_alt_frac=0.3)),
+    ("perm", 10, 20, 100, dict(chisq_permutation=1, max_iter=1000), dict(variant_frac=0.4, with_qhigh=True)),
+    ("lowcov", 30, 2, 10, dict(chisq_permutation=1, max_iter=1000), dict(variant_frac=0.5, bidir_frac=0.1)),
+    ("indel", 10, 20, 100, {}, dict(variant_frac=0.3, indel_frac=0.5, bidir_frac=0.05)),
+    ("em0", 10, 20, 100, dict(em_flag=0), dict(variant_frac=0.4, indel_frac=0.2, with_stats=True, with_qhigh=True)),
+    ("varpool", 8, [10, 20, 30, 40, 10, 20, 30, 40], 120, {}, dict(variant_frac=0.4, bidir_frac=0.1)),
+    ("nobq", 10, 20, 100, dict(use_base_qvs=0), dict(variant_frac=0.4)),
+    ("weighted_amb", 10, 20, 100, dict(use_qv=1, chisq_permutation=1, max_iter=500), dict(variant_frac=0.3, indel_frac=0.5, with_qhigh=True)),
+]
+
+
+@needs_ref
+@pytest.mark.parametrize("name,P,ploidy,depth,opts,kw", SCENARIOS)
+def test_oracle_equals_reference(name, P, ploidy, depth, opts, kw):
+    cfg = EngineConfig(ploidy=np.broadcast_to(np.asarray(ploidy), (P,)).copy(), options=opts)
+    batch = synth_batch(120, P, cfg.ploidy, depth, seed=5, **kw)
+    ref = RefEngine(cfg)
+    want = ref.run(batch, seed=99, want_vcf=True, want_genll=True)
+    got = OracleEngine(cfg).run(batch, mode=RNG_DRAND48, seed=99, want_genll=True)
+    # bit-exact, except where the batch carries an aggregated real-valued decrement (sum of per-read error
+    # probabilities) that the reference subtracts read by read: same value up to summation order
+    compare_results(got, want, tol=1e-12 if opts.get("use_qv") else 0.0, label=name)
+    assert np.array_equal(got.genll, want.genll)
+    # the results block carries everything the unchanged printer needs: replayed VCF text is identical
+    assert ref.replay_vcf(batch, got) == want.vcf
+
+
+@needs_ref
+def test_slot_walk_equals_newCRISPcaller():
+    """The harness's slot walk (which exposes per-slot state) gives the same records as calling the reference's
+    newCRISPcaller itself (SNP-only sites)."""
+    cfg = _cfg(P=10)
+    batch = synth_batch(150, 10, cfg.ploidy, 100, seed=8, variant_frac=0.5, bidir_frac=0.1, second_alt_frac=0.3)
+    ref = RefEngine(cfg)
+    a = ref.run(batch, mode=MODE_SLOTS, want_vcf=True)
+    b = ref.run(batch, mode=MODE_CALLER, want_vcf=True)
+    assert a.vcf == b.vcf and len(a.vcf.splitlines()) > 20
+    assert np.array_equal(a.varalleles, b.varalleles)
+
+
+def test_philox_sampler_matches_drand48_distribution():
+    """The counter-based sampler draws from the same null law as the reference's drand48 shuffle: compare hit
+    frequencies over many sites (binomial tolerance), and the stop rule bookkeeping."""
+    cfg = _cfg(P=8, chisq_permutation=1, max_iter=400)
+    batch = synth_batch(300, 8, cfg.ploidy, 60, seed=21, variant_frac=0.5)
+    orc = OracleEngine(cfg)
+    a = orc.run(batch, mode=RNG_DRAND48, seed=7)
+    b = orc.run(batch, mode=RNG_PHILOX)
+    tested = a.perm_k > 0
+    assert np.array_equal(tested, b.perm_k > 0) and tested.sum() > 100
+    # per-slot Monte-Carlo p estimates agree within 5 binomial sigmas of the pooled permutation count
+    pa = (a.perm_hits[tested] + 1) / (a.perm_k[tested] + 1)
+    pb = (b.perm_hits[tested] + 1) / (b.perm_k[tested] + 1)
+    k = np.minimum(a.perm_k[tested], b.perm_k[tested])
+    p = 0.5 * (pa + pb)
+    sigma = np.sqrt(2 * p * (1 - p) / k) + 2.0 / k
+    assert np.all(np.abs(pa - pb) <= 6 * sigma)
+    assert abs(pa.mean() - pb.mean()) < 0.02
