@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — candidate sites/sec of the CRISP per-site statistics engine on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
+  python bench.py --impl reference --gpus N --steps K --warmup W   the reference's own CPU code on the host cores
+
+A "step" is one pass of the hot path (k_evaluate -> k_em -> k_finalize; + permutation kernels when the workload
+enables them) over one batch of synthetic candidate sites of the named shape.  At N GPUs the sites are sharded by
+genomic region, one shard per rank, no data-path collective: weak scaling, each rank owns a batch of
+`--sites` candidates.  `value` is device-timed with the inputs resident in HBM; `e2e` is the same metric through the
+C-ABI call a front end makes (crispgpu_submit/crispgpu_wait) with pinned host buffers, host<->device copies inside
+the timed region.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: 50 pools x poolsize 48, synthetic exome at 200x per pool (default flags: --EM 1,
+    # asymptotic contingency test).  variant_frac: planted variants every 500 bp vs ~1.3 % of positions being
+    # sequencing-error candidates at this depth -> ~15 % of candidates carry a variant.
+    "exome50x48": dict(P=50, ploidy=48, depth=200, options={}, synth=dict(variant_frac=0.15)),
+    "c1_10x20_perm": dict(P=10, ploidy=20, depth=100, options=dict(chisq_permutation=1, max_iter=20000), synth=dict(variant_frac=0.3)),
+    "c3_100x96": dict(P=100, ploidy=96, depth=60, options={}, synth=dict(variant_frac=0.15)),
+    "c4_perm_stress": dict(P=50, ploidy=48, depth=200, options=dict(chisq_permutation=1, max_iter=1000000), synth=dict(variant_frac=0.8, rare=True)),
+    "c5_500x10": dict(P=500, ploidy=10, depth=10, options={}, synth=dict(variant_frac=0.15)),
+}
+
+
+def make_batch(wl: dict, n_sites: int, seed: int, tid: int = 0):
+    """Seeded synthetic candidate sites of the workload's shape, generated in chunks to bound host memory."""
+    from crisp_b200.abi import concat_batches
+    from crisp_b200.synth import synth_batch
+
+    parts, have, chunk, k = [], 0, 1024, 0
+    while have < n_sites:
+        b = synth_batch(chunk, wl["P"], wl["ploidy"], wl["depth"], seed=seed * 1000 + k, tid=tid, pos_start=1000 + k * chunk * 75, **wl["synth"])
+        parts.append(b)
+        have += b.n_sites
+        k += 1
+    full = concat_batches(parts)
+    return full.select(np.arange(n_sites)) if full.n_sites > n_sites else full
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _ref_worker(args):
+    cfg_ploidy, options, arrays, P, seed = args
+    from crisp_b200.abi import Batch, EngineConfig
+    from oracle.loader import OracleEngine, RefEngine, have_ref
+    cfg = EngineConfig(ploidy=cfg_ploidy, options=options)
+    batch = Batch(P, **arrays)
+    t0 = time.perf_counter()
+    if have_ref():
+        RefEngine(cfg).run(batch, seed=seed)
+    else:
+        OracleEngine(cfg).run(batch, mode=0, seed=seed)
+    return time.perf_counter() - t0, batch.n_sites
+
+
+def run_reference_sample(wl: dict, batch, cores: int, sites_per_core: int):
+    """The reference's own CPU implementation (oracle/_ref; oracle port if it was never built) on `cores` processes,
+    each owning a contiguous region of the sample — the reference's --regions parallelism."""
+    import multiprocessing as mp
+    from crisp_b200.abi import _BATCH_ARRAYS
+    from oracle.loader import have_ref
+
+    n = min(batch.n_sites, cores * sites_per_core)
+    per = n // cores
+    jobs = []
+    ploidy = np.full(wl["P"], wl["ploidy"], np.int32)
+    for c in range(cores):
+        sub = batch.select(np.arange(c * per, (c + 1) * per))
+        arrays = {name: getattr(sub, name) for name, _, _ in _BATCH_ARRAYS if getattr(sub, name) is not None}
+        jobs.append((ploidy, wl["options"], arrays, wl["P"], 1 + c))
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        out = pool.map(_ref_worker, jobs)
+    wall = time.perf_counter() - t0
+    busy = max(o[0] for o in out)
+    sites = sum(o[1] for o in out)
+    return sites / busy, sites, busy, wall, ("reference" if have_ref() else "port")
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="exome50x48", choices=sorted(WORKLOADS))
+    ap.add_argument("--sites", type=int, default=8192, help="candidate sites per GPU per step")
+    ap.add_argument("--cpu-sites-per-core", type=int, default=96)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": f"{args.workload}: {wl['P']} pools x poolsize {wl['ploidy']}, {wl['depth']}x per pool, options {wl['options'] or 'defaults (--EM 1, asymptotic CT)'}",
+              "sites_per_gpu_per_step": args.sites, "sharding": "genomic region per rank, no collective",
+              "l2_policy": "inputs larger than L2 (batch > 126 MB)" if args.sites * (2 * wl['P'] * wl['depth'] + 96 * wl['P']) > 126e6 else "L2 flushed between steps",
+              "synthetic": wl["synth"]}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from oracle.loader import build
+        build()
+        cores = host_cores()
+        batch = make_batch(wl, cores * args.cpu_sites_per_core, seed=1)
+        for _ in range(max(0, min(args.warmup, 1))):
+            run_reference_sample(wl, batch, cores, max(1, args.cpu_sites_per_core // 8))
+        vals, t_total = [], 0.0
+        for _ in range(args.steps):
+            v, sites, busy, wall, kind = run_reference_sample(wl, batch, cores, args.cpu_sites_per_core)
+            vals.append(v)
+            t_total += busy
+        value = float(np.mean(vals))
+        line = {"impl": "reference", "metric": "candidate sites/sec", "value": value, "unit": "sites/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": "sites/s", "cores": cores, "kind": kind,
+                                 "sample": f"{cores} processes x {args.cpu_sites_per_core} sites of the workload, one contiguous region each (the reference's --regions parallelism); sites/s = sites / slowest process"},
+                "e2e": {"value": value, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from crisp_b200.abi import EngineConfig
+    from crisp_b200.engine import Engine, measure_fp64_tflops, pin_batch
+    from crisp_b200 import build as cbuild
+
+    cbuild.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = EngineConfig(ploidy=np.full(wl["P"], wl["ploidy"]), options=wl["options"])
+    # region shard of this rank: its own contiguous run of candidate sites (tid = rank)
+    batch = make_batch(wl, args.sites, seed=1 + rank, tid=rank)
+    pinned = pin_batch(batch)
+    stream = torch.cuda.Stream(device=local)
+    eng = Engine(cfg, device=local, stream=stream.cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}") if "flushed" in config["l2_policy"] else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput ----------------
+    eng.upload(batch)
+    for _ in range(args.warmup):
+        eng.run_resident(fetch=False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kt = {"evaluate_ms": 0.0, "em_ms": 0.0, "permute_ms": 0.0, "filter_ms": 0.0, "legacy_ms": 0.0}
+    launches = 0
+    with torch.cuda.stream(stream):
+        e0.record()
+        for _ in range(args.steps):
+            if flush is not None:
+                flush.fill_(1)
+            eng.run_resident(fetch=False)
+            t = eng.timing()
+            for k in kt:
+                kt[k] += t[k]
+            launches += t["launches"]
+        e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    t_last = eng.timing()
+    # ---------------- end to end through the C ABI from pinned host memory ----------------
+    for _ in range(max(1, args.warmup // 2)):
+        eng.run(pinned)
+    barrier()
+    w0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        for _ in range(args.steps):
+            res = eng.wait(eng.submit(pinned), copy=False)
+    barrier()
+    e2e_s = time.perf_counter() - w0
+    t_e2e = eng.timing()
+    clocks = sampler.stop() if rank == 0 else None
+    results = eng.run(batch)
+
+    times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = float(times[0]), float(times[1])
+    total_sites = batch.n_sites * world
+    value = total_sites * args.steps / (ms_max * 1e-3)
+    e2e_value = total_sites * args.steps / (e2e_ms_max * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        fp64_peak = measure_fp64_tflops(local)
+        P, J = wl["P"], wl["ploidy"] + 1
+        n_em = t_last["n_tasks_em"]
+        iters = results.em_iters[results.em_iters > 0]
+        # algorithmic work of the EM kernel: per iteration 3 planes x sum_i (n_i+1) genotype evaluations at
+        # 35 flop + 3 P logs at 30 flop; plus the likelihood contraction, 2 flop per (histogram bin, j, plane)
+        ge_flops = float(iters.sum()) * (35.0 * 3 * P * J + 30.0 * 3 * P)
+        em_ms = kt["em_ms"] / args.steps
+        ev_ms = kt["evaluate_ms"] / args.steps
+        ro = batch.read_off.astype(np.int64)
+        em_sites = np.unique(np.nonzero(results.em_iters > 0)[0])
+        em_bytes = float(sum(2 * (ro[(s + 1) * P] - ro[s * P]) for s in em_sites)) + n_em * (96.0 * P + 12.0 * P + 128.0)
+        ev_bytes = batch.n_sites * (96.0 * P + 40.0 + 5 * 110.0)
+        dominant = "k_em" if em_ms >= ev_ms else "k_evaluate"
+        roof_em = {"kernel": "k_em", "bound": "fp64", "achieved": ge_flops / (em_ms * 1e-3) / 1e12 if em_ms > 0 else None, "peak": fp64_peak,
+                   "unit": "TFLOP/s", "frac": (ge_flops / (em_ms * 1e-3) / 1e12 / fp64_peak) if em_ms > 0 and fp64_peak > 0 else None,
+                   "traffic": None, "peak_source": "DFMA loop measured live (crispgpu_measure_fp64_tflops)",
+                   "ms_per_launch": em_ms, "tasks_per_launch": n_em, "mean_em_iterations": float(iters.mean()) if iters.size else 0.0,
+                   "algorithmic_hbm_GBps": em_bytes / (em_ms * 1e-3) / 1e9 if em_ms > 0 else None}
+        roof_ev = {"kernel": "k_evaluate", "bound": "hbm", "achieved": ev_bytes / (ev_ms * 1e-3) / 1e9 if ev_ms > 0 else None, "peak": hbm_peak, "unit": "GB/s",
+                   "frac": (ev_bytes / (ev_ms * 1e-3) / 1e9 / hbm_peak) if ev_ms > 0 else None, "traffic": None, "peak_source": hbm_src,
+                   "ms_per_launch": ev_ms, "sites_per_launch": batch.n_sites}
+        line = {"metric": "candidate sites/sec", "value": value, "unit": "sites/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": int(t_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(t_e2e["d2h_bytes"]),
+                        "ms_per_step": e2e_ms_max / args.steps, "h2d_ms": t_e2e["h2d_ms"], "d2h_ms": t_e2e["d2h_ms"]},
+                "gpu_launches": int(launches),
+                "roofline": roof_em if dominant == "k_em" else roof_ev,
+                "roofline_secondary": roof_ev if dominant == "k_em" else roof_em,
+                "kernel_ms_per_step": {k: v / args.steps for k, v in kt.items()},
+                "tasks": {"sites": batch.n_sites, "em_tasks": n_em, "called_alleles": int((results.status == 4).sum()), "perm_tasks": t_last["n_tasks_perm"]}}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle.loader import build
+            build()
+            cores = host_cores()
+            v, sites, busy, wall, kind = run_reference_sample(wl, batch, cores, args.cpu_sites_per_core)
+            line["cpu_baseline"] = {"value": v, "unit": "sites/s", "cores": cores, "kind": kind,
+                                    "sample": f"{sites} sites of the same batch, {cores} processes x {args.cpu_sites_per_core} sites (contiguous regions), {busy:.1f} s busy"}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

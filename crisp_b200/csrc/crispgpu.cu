@@ -449,9 +449,49 @@ int finish_timing(crispgpu_ctx* ctx)
 	return 0;
 }
 
+__global__ void k_dfma_peak(double* out, int iters)
+{
+	double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+	const double m = 1.0000001, c = 1e-7;
+	for (int i = 0; i < iters; i++) {
+		a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+		a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+	}
+	if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) out[0] = a0;
+}
+
 }  // namespace
 
 extern "C" {
+
+int crispgpu_measure_fp64_tflops(int device_id, double* tflops)
+{
+	if (!tflops) return CRISPGPU_ERR_ARG;
+	cudaDeviceProp prop;
+	if (cudaSetDevice(device_id) != cudaSuccess || cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) return CRISPGPU_ERR_NO_DEVICE;
+	double* d = nullptr;
+	cudaEvent_t e0, e1;
+	if (cudaMalloc(&d, 8) != cudaSuccess) return CRISPGPU_ERR_CUDA;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+	double best = 0.0;
+	for (int rep = 0; rep < 4; rep++) {
+		cudaEventRecord(e0);
+		k_dfma_peak<<<blocks, threads>>>(d, iters);
+		cudaEventRecord(e1);
+		if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return CRISPGPU_ERR_CUDA; }
+		float ms = 0;
+		cudaEventElapsedTime(&ms, e0, e1);
+		double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+		if (rep > 0 && tf > best) best = tf;
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(d);
+	*tflops = best;
+	return CRISPGPU_OK;
+}
 
 void crispgpu_config_defaults(crispgpu_config* cfg)
 {

@@ -19,6 +19,7 @@ EXPORTS = [
     "crispgpu_config_defaults", "crispgpu_create", "crispgpu_destroy", "crispgpu_submit", "crispgpu_wait",
     "crispgpu_upload", "crispgpu_run_resident", "crispgpu_get_timing", "crispgpu_last_error",
     "crispgpu_host_alloc", "crispgpu_host_free", "crispgpu_abi_version", "crispgpu_device_count",
+    "crispgpu_measure_fp64_tflops",
 ]
 
 _lib = None
@@ -60,6 +61,8 @@ def load_library() -> C.CDLL:
     lib.crispgpu_host_free.restype = None
     lib.crispgpu_abi_version.restype = C.c_int
     lib.crispgpu_device_count.restype = C.c_int
+    lib.crispgpu_measure_fp64_tflops.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    lib.crispgpu_measure_fp64_tflops.restype = C.c_int
     _lib = lib
     return lib
 
@@ -172,6 +175,15 @@ class Engine:
         t = Timing()
         self._check(self.lib.crispgpu_get_timing(self.h, C.byref(t)), "crispgpu_get_timing")
         return {name: getattr(t, name) for name, _ in Timing._fields_}
+
+
+def measure_fp64_tflops(device: int = 0) -> float:
+    """FP64 FMA throughput of the device measured with a register-resident DFMA loop (TFLOP/s)."""
+    v = C.c_double(0.0)
+    rc = load_library().crispgpu_measure_fp64_tflops(device, C.byref(v))
+    if rc != 0:
+        raise EngineError(f"crispgpu_measure_fp64_tflops failed: status {rc}")
+    return v.value
 
 
 def device_count() -> int:

@@ -232,6 +232,10 @@ void crispgpu_host_free(void* p);
 int crispgpu_abi_version(void);
 int crispgpu_device_count(void);
 
+/* Measured FP64 FMA throughput of the device (TFLOP/s, 2 flop per DFMA) from a register-resident DFMA loop:
+ * the roofline denominator of the EM kernel (MEASURED_PEAKS.json carries no FP64 figure). */
+int crispgpu_measure_fp64_tflops(int device_id, double* tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,7 @@ def lib():
 
 def test_header_symbols_are_exported(lib):
     header = open(os.path.join(ROOT, "include", "crispgpu.h")).read()
-    declared = set(re.findall(r"\b(crispgpu_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(crispgpu_[a-z0-9_]+)\s*\(", header))
     assert declared == set(EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
