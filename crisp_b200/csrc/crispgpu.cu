@@ -135,11 +135,15 @@ size_t em_smem_fixed(int P, int J, int nwarps)
 {
 	size_t off = (sizeof(EmShared) + 15) & ~size_t(15);
 	off += sizeof(double) * P;
-	off += sizeof(double) * J * 2;
+	off += sizeof(double) * J;
 	off += sizeof(int32_t) * 6 * P;
 	off = (off + 15) & ~size_t(15);
-	off += sizeof(uint32_t) * 6 * kNQ * nwarps;
+	off += sizeof(uint16_t) * 6 * kNQ * nwarps;
 	off = (off + 15) & ~size_t(15);
+	const int rounds = (P + 31) / 32;
+	off += sizeof(double) * 19 * rounds + sizeof(int32_t) * 2 * rounds;
+	off = (off + 15) & ~size_t(15);
+	off += sizeof(double) * 3 * P;
 	return off;
 }
 
@@ -148,10 +152,8 @@ int setup_geometry(crispgpu_ctx* ctx)
 	const int P = ctx->P, J = ctx->nmax + 1;
 	const size_t budget = ctx->smem_optin;
 	// k_evaluate: warps per CTA limited by the staged count block
-	ctx->ev_warps = 8;
-	while (ctx->ev_warps > 1 && (size_t)ctx->ev_warps * P * kICPad * 4 > budget / 2) ctx->ev_warps >>= 1;
-	ctx->ev_smem = (size_t)ctx->ev_warps * P * kICPad * 4;
-	if (ctx->ev_smem > budget) return CRISPGPU_ERR_UNSUPPORTED;
+	ctx->ev_warps = 4;
+	ctx->ev_smem = 0;
 	// k_em
 	const int rounds = (P + 31) / 32;
 	if (rounds > kMaxRounds) return CRISPGPU_ERR_UNSUPPORTED;
@@ -179,6 +181,7 @@ int occupancy_grid(crispgpu_ctx* ctx, K kernel, int threads, size_t smem, int* g
 {
 	int per_sm = 0;
 	if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	if (smem > 0) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
 	if (per_sm < 1) per_sm = 1;
 	*grid = per_sm * ctx->num_sms;
@@ -192,6 +195,7 @@ int launch_evaluate(crispgpu_ctx* ctx, const EngineParams& prm)
 		int grid = 0;
 		int rc = occupancy_grid(ctx, kernel, warps * 32, ctx->ev_smem, &grid);
 		if (rc) return rc;
+		grid *= 4;  // several waves of short CTAs: sites differ in the number of tested slots
 		int need = (n + warps - 1) / warps;
 		if (grid > need) grid = need;
 		if (grid < 1) grid = 1;

@@ -19,6 +19,7 @@
 namespace crisp {
 
 constexpr int kEmMaxWarps = 8;
+constexpr double kExpCut2 = 24.0;  // cut-off used with an approximate log-sum-exp shift (leaves >= 20 decades of margin)
 constexpr int kMaxRounds = 64;  // pools <= 2048
 
 struct EmShared {
@@ -28,11 +29,6 @@ struct EmShared {
 	double LL[3];
 	double E01[3], E10[3];
 	double LLnull0;
-	double part_LL[3][kMaxRounds];
-	double part_pn[3][kMaxRounds];
-	double part_null[kMaxRounds];
-	double part_T[12][kMaxRounds];
-	int part_i[2][kMaxRounds];
 	int part_w[kEmMaxWarps];
 	int exitflag;
 	int iter;
@@ -40,14 +36,13 @@ struct EmShared {
 	double delta, deltaf, hwe;
 };
 
-__device__ __forceinline__ double em_term(const double* Gp, int P, int i, int j, int n, double nc, double l0, double l1)
-{
-	// GENLL + NC + log10(p)*j + log10(1-p)*(n-j)   (crispEM.c:249)
-	return Gp[(size_t)j * P + i] + nc + l0 * j + l1 * (n - j);
-}
+// The EM term GENLL + NC + log10(p)*j + log10(1-p)*(n-j) (crispEM.c:249) is evaluated as
+//   H[j] + j*(log10 p - log10(1-p)) + n*log10(1-p),   H[j] = GENLL[j] + NC[j]  (stored once per likelihood update),
+// so the inner loops cost one shared-memory load and one FMA per genotype; the pool-constant n*log10(1-p) is added
+// after the maximum is known.
 
 template <bool SMEM_G>
-__global__ void __launch_bounds__(kEmMaxWarps * 32) k_em(EngineParams prm)
+__global__ void __maxnreg__(96) k_em(EngineParams prm)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const DevBatch& b = prm.b;
@@ -61,19 +56,21 @@ __global__ void __launch_bounds__(kEmMaxWarps * 32) k_em(EngineParams prm)
 	EmShared* sh = reinterpret_cast<EmShared*>(smem_raw);
 	size_t off = (sizeof(EmShared) + 15) & ~size_t(15);
 	double* Gb0 = reinterpret_cast<double*>(smem_raw + off); off += sizeof(double) * P;
-	double* NCs = reinterpret_cast<double*>(smem_raw + off); off += sizeof(double) * J;           // single ploidy class only
 	double* gcnt = reinterpret_cast<double*>(smem_raw + off); off += sizeof(double) * J;          // genotype_counts / HWE terms
 	int32_t* cnt6 = reinterpret_cast<int32_t*>(smem_raw + off); off += sizeof(int32_t) * 6 * P;   // [6][P]: a1 f,r,b ; a2 f,r,b
 	off = (off + 15) & ~size_t(15);
-	uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + off); off += sizeof(uint32_t) * 6 * kNQ * nwarps;
+	uint16_t* hist = reinterpret_cast<uint16_t*>(smem_raw + off); off += sizeof(uint16_t) * 6 * kNQ * nwarps;
 	off = (off + 15) & ~size_t(15);
+	// per-round partial sums of one iteration: [0..2] LL per plane, [3..5] pnew per plane, [6] LLnull0, [7..18] T sums
+	double* part = reinterpret_cast<double*>(smem_raw + off); off += sizeof(double) * 19 * rounds;
+	int32_t* part_i = reinterpret_cast<int32_t*>(smem_raw + off); off += sizeof(int32_t) * 2 * rounds;
+	off = (off + 15) & ~size_t(15);
+	double* mprev = reinterpret_cast<double*>(smem_raw + off); off += sizeof(double) * 3 * P;  // log-sum-exp shift per (plane, pool)
 	double* G = SMEM_G ? reinterpret_cast<double*>(smem_raw + off) : prm.gws + (size_t)blockIdx.x * prm.gws_stride;
 	double* Gt = G;
 	double* Gf = G + plane;
 	double* Gr = G + 2 * plane;
 
-	const bool oneclass = c.n_pclass == 1;
-	if (oneclass) for (int j = tid; j < J; j += blockDim.x) NCs[j] = c.NC[j];
 
 	for (;;) {
 		__syncthreads();
@@ -88,6 +85,8 @@ __global__ void __launch_bounds__(kEmMaxWarps * 32) k_em(EngineParams prm)
 		const int refbase = b.refbase[s];
 		const int row = slot_amb_row(b, s, slot, a2, a3);
 		const bool countlik = (a2 >= 4 || c.use_base_qvs == 0);
+		// e(f) is linear in f and f linear in j unless a reference bias bends it: log-likelihood planes concave in j
+		const bool unimodal = countlik || c.ref_bias == 0.5;
 		int ilen = 0, is_ins = 0;
 		if (a2 >= 4 && b.indel_len) { ilen = abs((int)b.indel_len[s * 8 + a2]); is_ins = b.indel_len[s * 8 + a2] > 0; }
 		// indel_bias (crispEM.c:36-49)
@@ -161,9 +160,10 @@ __global__ void __launch_bounds__(kEmMaxWarps * 32) k_em(EngineParams prm)
 				double gf = cnt6[0 * P + i] * log10(ef) + cnt6[3 * P + i] * log10(1.0 - ef);
 				double gr = cnt6[1 * P + i] * log10(er) + cnt6[4 * P + i] * log10(1.0 - er);
 				double gb = cnt6[2 * P + i] * log10(eb) + cnt6[5 * P + i] * log10(1.0 - eb);
-				Gf[idx] = gf;
-				Gr[idx] = gr;
-				Gt[idx] = gf + gr + gb;
+				const double nc = __ldg(c.NC + (size_t)c.pclass[i] * J + j);
+				Gf[idx] = gf + nc;
+				Gr[idx] = gr + nc;
+				Gt[idx] = (gf + gr + gb) + nc;
 				if (j == 0) Gb0[i] = gb;
 			}
 			__syncthreads();
@@ -177,54 +177,113 @@ __global__ void __launch_bounds__(kEmMaxWarps * 32) k_em(EngineParams prm)
 			if (tid == 0) for (int k = 0; k < 3; k++) { sh->E01[k] = 0.001; sh->E10[k] = 0.001; }
 		} else {
 			// calculate_pooled_likelihoods_snp: per pool, histogram the packed reads over (strand class, allele, quality)
-			// and contract with the table T[allele][quality][j]
-			uint32_t* h = hist + (size_t)warp * 6 * kNQ;
+			// and contract with the table T[allele][quality][j].  One warp per pool; each lane owns genotypes j and j+32
+			// (and j+64, j+96 for pool sizes above 63).
+			uint16_t* h = hist + (size_t)warp * 6 * kNQ;
 			for (int i = warp; i < P; i += nwarps) {
-				for (int k = lane; k < 6 * kNQ; k += 32) h[k] = 0;
-				__syncwarp();
 				const uint32_t r0 = b.read_off[(size_t)s * P + i], r1 = b.read_off[(size_t)s * P + i + 1];
-				for (uint32_t rb = r0; rb < r1; rb += 32) {
-					const uint32_t r = rb + lane;
-					const bool in = r < r1;
-					uint32_t w = in ? (uint32_t)__ldg(b.reads + r) : 0u;
-					const int base = (w >> 8) & 3;
-					const int which = base == a1 ? 0 : (base == a2 ? 1 : -1);
-					const bool use = in && which >= 0;
-					const int cls = (w >> 11) & 1 ? 2 : ((w >> 10) & 1);
-					const int key = use ? (cls * 2 + which) * kNQ + (w & 0x7f) : -1 - lane;
-					const unsigned peers = __match_any_sync(0xffffffffu, key);
-					if (use && lane == __ffs(peers) - 1) h[key] += __popc(peers);
-				}
-				__syncwarp();
 				const int n = c.ploidy[i];
 				const double* Tp = c.T + (size_t)c.pclass[i] * 2 * kNQ * J;
-				for (int jc = 0; jc * 32 < n + 1; jc++) {
-					const int j = jc * 32 + lane;
-					const bool jv = j <= n;
-					double acc[3] = {0.0, 0.0, 0.0};
+				double acc[3][4];
+#pragma unroll
+				for (int cls = 0; cls < 3; cls++)
+#pragma unroll
+					for (int jc = 0; jc < 4; jc++) acc[cls][jc] = 0.0;
+				// 16-bit bins: a pool deeper than 65504 reads is folded block by block
+				for (uint32_t blk = r0; blk < r1 || blk == r0; blk += 65504u) {
+					const uint32_t bend = min(r1, blk + 65504u);
+					{
+						uint4* hz = reinterpret_cast<uint4*>(h);
+						for (int k = lane; k < 6 * kNQ * 2 / 16; k += 32) hz[k] = make_uint4(0u, 0u, 0u, 0u);
+					}
+					__syncwarp();
+					unsigned present = 0;  // which 32-wide quality chunks hold any read of interest
+					for (uint32_t cb = blk; cb < bend; cb += 256) {
+						// 8 independent coalesced loads per lane first (memory-level parallelism), then the warp-wide binning
+						uint32_t wv[8];
+#pragma unroll
+						for (int k = 0; k < 8; k++) {
+							const uint32_t r = cb + k * 32 + lane;
+							wv[k] = r < bend ? (uint32_t)__ldg(b.reads + r) : 0xffffffffu;
+						}
+#pragma unroll
+						for (int k = 0; k < 8; k++) {
+							if (cb + k * 32 >= bend) break;
+							const uint32_t w = wv[k];
+							const bool in = w != 0xffffffffu;
+							const int base = (w >> 8) & 3;
+							const int which = base == a1 ? 0 : (base == a2 ? 1 : -1);
+							const bool use = in && which >= 0;
+							const int cls = (w >> 11) & 1 ? 2 : ((w >> 10) & 1);
+							const int key = use ? (cls * 2 + which) * kNQ + (w & 0x7f) : -1 - lane;
+							const unsigned peers = __match_any_sync(0xffffffffu, key);
+							if (use && lane == __ffs(peers) - 1) h[key] += (uint16_t)__popc(peers);
+							if (use) present |= 1u << ((w & 0x7f) >> 5);
+						}
+					}
+					present |= __shfl_xor_sync(0xffffffffu, present, 16);
+					present |= __shfl_xor_sync(0xffffffffu, present, 8);
+					present |= __shfl_xor_sync(0xffffffffu, present, 4);
+					present |= __shfl_xor_sync(0xffffffffu, present, 2);
+					present |= __shfl_xor_sync(0xffffffffu, present, 1);
+					__syncwarp();
 #pragma unroll
 					for (int cls = 0; cls < 3; cls++) {
+#pragma unroll
 						for (int which = 0; which < 2; which++) {
-							const uint32_t* hh = h + (cls * 2 + which) * kNQ;
-							const double* Tw = Tp + (size_t)which * kNQ * J;
+							const uint16_t* hh = h + (cls * 2 + which) * kNQ;
+							const double* Tw = Tp + (size_t)which * kNQ * J + lane;
 							for (int qc = 0; qc < kNQ; qc += 32) {
+								if (!((present >> (qc >> 5)) & 1u)) continue;
 								const uint32_t hv = hh[qc + lane];
 								unsigned m = __ballot_sync(0xffffffffu, hv != 0);
 								while (m) {
 									const int bq = __ffs(m) - 1;
 									m &= m - 1;
 									const double cntv = (double)__shfl_sync(0xffffffffu, hv, bq);
-									if (jv) acc[cls] += cntv * __ldg(Tw + (size_t)(qc + bq) * J + j);
+									const double* Tr = Tw + (size_t)(qc + bq) * J;
+#pragma unroll
+									for (int jc = 0; jc < 4; jc++)
+										if (jc * 32 <= nmax && jc * 32 + lane <= n) acc[cls][jc] = fma(cntv, __ldg(Tr + jc * 32), acc[cls][jc]);
 								}
 							}
 						}
 					}
-					if (jv) {
+					// pool sizes above 127: remaining genotypes are accumulated in place, one chunk at a time
+					for (int jc = 4; jc * 32 <= n; jc++) {
+						const int j = jc * 32 + lane;
+						double a3[3] = {0.0, 0.0, 0.0};
+						for (int cw = 0; cw < 6; cw++) {
+							const uint16_t* hh = h + cw * kNQ;
+							const double* Tw = Tp + (size_t)(cw & 1) * kNQ * J;
+							for (int q = 0; q < kNQ; q++) {
+								const uint32_t hv = hh[q];
+								if (hv && j <= n) a3[cw >> 1] = fma((double)hv, __ldg(Tw + (size_t)q * J + j), a3[cw >> 1]);
+							}
+						}
+						if (j <= n) {
+							const size_t idx = (size_t)j * P + i;
+							const bool first = blk == r0;
+							const double nc = first ? __ldg(c.NC + (size_t)c.pclass[i] * J + j) : 0.0;
+							Gf[idx] = (first ? nc : Gf[idx]) + a3[0];
+							Gr[idx] = (first ? nc : Gr[idx]) + a3[1];
+							Gt[idx] = (first ? nc : Gt[idx]) + (a3[0] + a3[1] + a3[2]);
+						}
+					}
+					__syncwarp();
+					if (bend >= r1) break;
+				}
+				const double* ncp = c.NC + (size_t)c.pclass[i] * J;
+#pragma unroll
+				for (int jc = 0; jc < 4; jc++) {
+					const int j = jc * 32 + lane;
+					if (jc * 32 <= nmax && j <= n) {
 						const size_t idx = (size_t)j * P + i;
-						Gf[idx] = acc[0];
-						Gr[idx] = acc[1];
-						Gt[idx] = acc[0] + acc[1] + acc[2];
-						if (j == 0) Gb0[i] = acc[2];
+						const double nc = __ldg(ncp + j);
+						Gf[idx] = acc[0][jc] + nc;
+						Gr[idx] = acc[1][jc] + nc;
+						Gt[idx] = (acc[0][jc] + acc[1][jc] + acc[2][jc]) + nc;
+						if (j == 0) Gb0[i] = acc[2][jc];
 					}
 				}
 				__syncwarp();
@@ -248,35 +307,65 @@ __global__ void __launch_bounds__(kEmMaxWarps * 32) k_em(EngineParams prm)
 				const bool act = i < P;
 				const int ii = act ? i : P - 1;
 				const int n = c.ploidy[ii];
-				const double* Gp = G + (size_t)pl * plane;
-				const double* ncp = oneclass ? NCs : c.NC + (size_t)c.pclass[ii] * J;
+				const double* Hp = G + (size_t)pl * plane + ii;
 				const double l0 = sh->lp[pl][0], l1 = sh->lp[pl][1];
-				double m = -1e300;
-				for (int j = 0; j <= nmax; j++) {
-					if (j <= n) m = fmax(m, em_term(Gp, P, ii, j, n, ncp[j], l0, l1));
-				}
-				double S = 0.0, Wj = 0.0;
+				const double dl = l0 - l1, base = (double)n * l1;
+				// Shift of the log-sum-exp: the exact maximum on the first iteration, afterwards the maximum seen in the
+				// previous iteration (any shift within a few decades of the maximum gives the same sum; the fallback below
+				// repeats the unit when the assumed shift turns out more than 3 decades too high).
+				double m;
+				if (sh->iter == 0 || countlik) {  // count-based planes are rebuilt every iteration: always take the exact maximum
+					m = -1e300;
+					const double* hp = Hp;
+					double jd = 0.0, vprev = -1e300;
+					for (int j = 0; j <= nmax; j++, hp += P, jd += 1.0) {
+						const bool in = j <= n;
+						const double v = in ? fma(jd, dl, *hp) : -1e300;
+						m = fmax(m, v);
+						// H[j] + j*dl is concave in j (unimodal): past the mode nothing larger follows
+						if (unimodal && __all_sync(0xffffffffu, !in || v < vprev)) break;
+						vprev = v;
+					}
+				} else m = mprev[pl * P + ii];
+				double S = 0.0, Wj = 0.0, newmax = -1e300;
 				double T00[3] = {0, 0, 0}, T01[3] = {0, 0, 0}, T10[3] = {0, 0, 0}, T11[3] = {0, 0, 0};
-				for (int j = 0; j <= nmax; j++) {
-					const double d = (j <= n) ? em_term(Gp, P, ii, j, n, ncp[j], l0, l1) - m : -1e300;
-					if (d > -kExpCut) {
-						const double e = exp10(d);
-						S += e;
-						Wj += (double)j * e;
-						if (countlik && pl == 0) {
-							const double f = (double)j / n;
+				for (int attempt = 0; attempt < 2; attempt++) {
+					const double* hp = Hp;
+					double jd = 0.0, vprev = -1e300;
+					for (int j = 0; j <= nmax; j++, hp += P, jd += 1.0) {
+						const bool in = j <= n;
+						const double v = in ? fma(jd, dl, *hp) : -1e300;
+						const double d = v - m;
+						newmax = fmax(newmax, v);
+						if (d > -kExpCut2) {
+							const double e = exp10(d);
+							S += e;
+							Wj = fma(jd, e, Wj);
+							if (countlik && pl == 0) {
+								const double f = jd / n;
 #pragma unroll
-							for (int k = 0; k < 3; k++) {
-								const double E01 = sh->E01[k], E10 = sh->E10[k];
-								const double den1 = (1.0 - f) * (1.0 - E01) + f * E10, den2 = (1.0 - f) * E01 + f * (1.0 - E10);
-								T00[k] += e * (1.0 - f) * (1.0 - E01) / den1;
-								T10[k] += e * f * E10 / den1;
-								T11[k] += e * f * (1.0 - E10) / den2;
-								T01[k] += e * (1.0 - f) * E01 / den2;
+								for (int k = 0; k < 3; k++) {
+									const double E01 = sh->E01[k], E10 = sh->E10[k];
+									const double den1 = (1.0 - f) * (1.0 - E01) + f * E10, den2 = (1.0 - f) * E01 + f * (1.0 - E10);
+									T00[k] += e * (1.0 - f) * (1.0 - E01) / den1;
+									T10[k] += e * f * E10 / den1;
+									T11[k] += e * f * (1.0 - E10) / den2;
+									T01[k] += e * (1.0 - f) * E01 / den2;
+								}
 							}
 						}
+						// descending and below the cut-off for every lane: the remaining terms are smaller still
+						if (unimodal && __all_sync(0xffffffffu, !in || (v < vprev && d <= -kExpCut2))) break;
+						vprev = v;
 					}
+					if (__all_sync(0xffffffffu, fabs(m - newmax) <= 3.0)) break;
+					// the stored shift was off by more than 3 decades for some pool: redo the unit with the maxima just found
+					m = newmax; S = 0.0; Wj = 0.0;
+#pragma unroll
+					for (int k = 0; k < 3; k++) { T00[k] = T01[k] = T10[k] = T11[k] = 0.0; }
 				}
+				if (act) mprev[pl * P + ii] = newmax;
+				m += base;
 				double L = m + log10(S);
 				double llc = 0.0, pn = 0.0, nul = 0.0;
 				if (act) {
@@ -294,13 +383,13 @@ __global__ void __launch_bounds__(kEmMaxWarps * 32) k_em(EngineParams prm)
 					for (int k = 0; k < 3; k++) {
 						const double c1 = act ? (double)cnt6[k * P + ii] / S : 0.0, c2 = act ? (double)cnt6[(3 + k) * P + ii] / S : 0.0;
 						double t00 = warp_sum(c1 * T00[k]), t10 = warp_sum(c1 * T10[k]), t11 = warp_sum(c2 * T11[k]), t01 = warp_sum(c2 * T01[k]);
-						if (lane == 0) { sh->part_T[k][rd] = t00; sh->part_T[3 + k][rd] = t01; sh->part_T[6 + k][rd] = t10; sh->part_T[9 + k][rd] = t11; }
+						if (lane == 0) { part[(7 + k) * rounds + rd] = t00; part[(10 + k) * rounds + rd] = t01; part[(13 + k) * rounds + rd] = t10; part[(16 + k) * rounds + rd] = t11; }
 					}
 				}
 				if (lane == 0) {
-					sh->part_LL[pl][rd] = llc;
-					sh->part_pn[pl][rd] = pn;
-					if (pl == 0) sh->part_null[rd] = nul;
+					part[pl * rounds + rd] = llc;
+					part[(3 + pl) * rounds + rd] = pn;
+					if (pl == 0) part[6 * rounds + rd] = nul;
 				}
 			}
 			__syncthreads();
@@ -308,7 +397,7 @@ __global__ void __launch_bounds__(kEmMaxWarps * 32) k_em(EngineParams prm)
 			if (warp == 0) {
 				double LLn = 0.0, pn = 0.0, prev = 0.0;
 				if (lane < 3) {
-					for (int r = 0; r < rounds; r++) { LLn += sh->part_LL[lane][r]; pn += sh->part_pn[lane][r]; }
+					for (int r = 0; r < rounds; r++) { LLn += part[lane * rounds + r]; pn += part[(3 + lane) * rounds + r]; }
 					prev = sh->LL[lane];
 					pn /= c.K;
 					if (pn < kMinP) pn = kMinP;
@@ -321,12 +410,12 @@ __global__ void __launch_bounds__(kEmMaxWarps * 32) k_em(EngineParams prm)
 				if (lane == 0) {
 					const int it = ++sh->iter;
 					double nul = 0.0;
-					for (int r = 0; r < rounds; r++) nul += sh->part_null[r];
+					for (int r = 0; r < rounds; r++) nul += part[6 * rounds + r];
 					sh->LLnull0 = nul;
 					if (countlik) {
 						for (int k = 0; k < 3; k++) {
 							double t00 = 0, t01 = 0, t10 = 0, t11 = 0;
-							for (int r = 0; r < rounds; r++) { t00 += sh->part_T[k][r]; t01 += sh->part_T[3 + k][r]; t10 += sh->part_T[6 + k][r]; t11 += sh->part_T[9 + k][r]; }
+							for (int r = 0; r < rounds; r++) { t00 += part[(7 + k) * rounds + r]; t01 += part[(10 + k) * rounds + r]; t10 += part[(13 + k) * rounds + r]; t11 += part[(16 + k) * rounds + r]; }
 							double e01 = (t01 + 1.5 - 1) / (t01 + t00 + 1.5 + 50 - 1), e10 = (t10 + 1.5 - 1) / (t10 + t11 + 50 + 1.5 - 1);
 							if (e10 > 0.05) e10 = 0.05;
 							sh->E01[k] = e01;
@@ -369,35 +458,48 @@ __global__ void __launch_bounds__(kEmMaxWarps * 32) k_em(EngineParams prm)
 				const bool act = i < P;
 				const int ii = act ? i : P - 1;
 				const int n = c.ploidy[ii];
-				const double* ncp = oneclass ? NCs : c.NC + (size_t)c.pclass[ii] * J;
+				const double* Hp = Gt + ii;
+				const double dl = l0 - l1, base = (double)n * l1;
 				double best = -100000, second = -100000;
 				int bg = 0;
-				for (int j = 0; j <= n; j++) {
-					const double t = em_term(Gt, P, ii, j, n, ncp[j], l0, l1);
-					if (t > best) { second = best; bg = j; best = t; }
-					else if (t > second) second = t;
+				{
+					const double* hp = Hp;
+					double jd = 0.0;
+					for (int j = 0; j <= n; j++, hp += P, jd += 1.0) {
+						const double t = fma(jd, dl, *hp) + base;
+						if (t > best) { second = best; bg = j; best = t; }
+						else if (t > second) second = t;
+					}
 				}
 				// the running log-sum-exp of :168-169 equals max + log10(sum 10^(t-max)) up to rounding
 				double S = 0.0;
-				for (int j = 0; j <= n; j++) {
-					const double d = em_term(Gt, P, ii, j, n, ncp[j], l0, l1) - best;
-					if (d > -kExpCut) S += exp10(d);
+				{
+					const double* hp = Hp;
+					double jd = 0.0;
+					for (int j = 0; j <= n; j++, hp += P, jd += 1.0) {
+						const double d = fma(jd, dl, *hp) + base - best;
+						if (d > -kExpCut) S += exp10(d);
+					}
 				}
 				const double Lb = best + log10(S);
-				for (int j = 0; j <= nmax; j++) {
-					double v = 0.0;
-					if (act && j <= n) {
-						const double d = em_term(Gt, P, ii, j, n, ncp[j], l0, l1) - Lb;
-						if (d > -kExpCut - 3) v = exp10(d);
+				{
+					const double* hp = Hp;
+					double jd = 0.0;
+					for (int j = 0; j <= nmax; j++, hp += P, jd += 1.0) {
+						double v = 0.0;
+						if (act && j <= n) {
+							const double d = fma(jd, dl, *hp) + base - Lb;
+							if (d > -kExpCut - 3) v = exp10(d);
+						}
+						if (act) post[(size_t)j * P + ii] = v;
 					}
-					if (act) post[(size_t)j * P + ii] = v;
 				}
 				if (act) {
 					prm.o.ac[(size_t)task * P + i] = bg;
 					prm.o.qv[(size_t)task * P + i] = 10 * (best - second);
 				}
 				const int vp = warp_sum(act && bg > 0 ? 1 : 0), acs = warp_sum(act ? bg : 0);
-				if (lane == 0) { sh->part_i[0][rd] = vp; sh->part_i[1][rd] = acs; }
+				if (lane == 0) { part_i[rd] = vp; part_i[rounds + rd] = acs; }
 			}
 			__syncthreads();
 			if (c.varpoolsize == 0) {
@@ -466,7 +568,7 @@ __global__ void __launch_bounds__(kEmMaxWarps * 32) k_em(EngineParams prm)
 			prm.o.call_row[o] = called ? task : -1;
 			if (called) {
 				int vp = 0, acs = 0;
-				for (int r = 0; r < rounds; r++) { vp += sh->part_i[0][r]; acs += sh->part_i[1][r]; }
+				for (int r = 0; r < rounds; r++) { vp += part_i[r]; acs += part_i[rounds + r]; }
 				prm.o.variantpools[o] = vp;
 				prm.o.allelecount[o] = acs;
 				prm.o.varpools[o] = varpools;

@@ -3,8 +3,7 @@
 // (parsebam/allelecounts.c:208-261), the asymptotic contingency-table p-values chi2pvalue_stratified
 // (FET/chisquare-stratified.c:12-203) / chi2pvalue (FET/chisquare.c:16-136) and the FAST_FILTER rejects.
 //
-// HBM-bound: one warp streams one site's [P][24] count block (96 B per pool) into shared memory with 16-byte loads,
-// then lanes run over pools.  Slots that survive are appended to the caller queue (or, with --chisquare 0, to the
+// One warp per site, lanes over pools; the [P][24] count block (96 B per pool) is read straight from global memory.  Slots that survive are appended to the caller queue (or, with --chisquare 0, to the
 // permutation queue; k_filter applies the rejects once the Monte-Carlo p-value is known).
 #pragma once
 #include "dmath.cuh"
@@ -55,6 +54,8 @@ __device__ __forceinline__ bool pass_fast_filter(const DevCfg& c, const DevBatch
 	return true;
 }
 
+__device__ __forceinline__ size_t cell_row(int row, int P, size_t cell) { return (size_t)row * P + cell % P; }
+
 __device__ __forceinline__ void queue_push(int32_t* list, int32_t* counter, int32_t v)
 {
 	int idx = atomicAdd(counter, 1);
@@ -79,33 +80,46 @@ __device__ inline double chi2_from_groups(int P, int pivot, double sj0, double s
 	return pv2;
 }
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_evaluate(EngineParams prm)
+// counts of one allele in the three strand classes for pool row r, ambiguity-adjusted
+__device__ __forceinline__ void load3(const int32_t* __restrict__ r, int a, bool isref, const int* dd, int* x)
 {
-	extern __shared__ __align__(16) unsigned char smem_raw[];
+	x[0] = __ldg(r + a); x[1] = __ldg(r + a + 8); x[2] = __ldg(r + a + 16);
+	if (isref) { x[0] -= dd[0]; x[1] -= dd[1]; x[2] -= dd[2]; }
+}
+
+// Qhighcounts-style strand totals (forward, reverse) of one allele for the weighted table
+__device__ __forceinline__ void loadq(const DevBatch& b, const DevCfg& c, const int32_t* __restrict__ r, size_t cell, int a, bool isref, int row, double* q)
+{
+#pragma unroll
+	for (int k = 0; k < 2; k++) {
+		q[k] = b.qhigh ? __ldg(b.qhigh + cell * 16 + 8 * k + a) : (double)__ldg(r + a + 8 * k);
+		if (isref && row >= 0) {
+			const int32_t* d = b.amb_dec + cell_row(row, c.P, cell) * 4;
+			double dec = d[k] + d[2 + k];
+			if (c.use_qv == 1 && b.amb_ep) dec -= b.amb_ep[cell_row(row, c.P, cell) * 2 + k];
+			q[k] -= dec;
+		}
+	}
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_evaluate(EngineParams prm)
+{
 	const DevBatch& b = prm.b;
 	const DevCfg& c = prm.c;
 	const int P = c.P;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	int32_t* ic = reinterpret_cast<int32_t*>(smem_raw) + (size_t)warp * P * kICPad;
 	const int pivot = c.pivot_sample;
 	const bool permmode = c.chisq_permutation == 1;
 
 	for (int s = blockIdx.x * WARPS + warp; s < b.n_sites; s += gridDim.x * WARPS) {
-		// ---- stage the site's counts: P*24 ints = P*6 int4, coalesced ----
-		const int4* src = reinterpret_cast<const int4*>(b.indcounts + (size_t)s * P * kNC);
-		for (int v = lane; v < P * 6; v += 32) {
-			int4 x = __ldg(src + v);
-			int i = v / 6, q = (v - i * 6) * 4;
-			int32_t* d = ic + i * kICPad + q;
-			d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
-		}
-		__syncwarp();
+		// lanes run over pools and read their 96-byte count rows straight from global memory (each row is touched
+		// by nine scalar loads per tested slot; the three 32-byte sectors of a row stay in L1 between them)
+		const int32_t* __restrict__ ic = b.indcounts + (size_t)s * P * kNC;
 		const uint8_t* mal = b.maxvec_al + s * 8;
 		const int32_t* mct = b.maxvec_ct + s * 8;
 		const int refbase = b.refbase[s];
-		// results of the slot owned by this lane (lanes 0..4)
-		double my_p0 = 0, my_sj0 = 0, my_sj1 = 0, my_tot = 0, my_wj0 = 0, my_wj1 = 0, my_wtot = 0;
+		double my_p0 = 0, my_sj0 = 0, my_sj1 = 0;
 		int my_tested = 0;
 		for (int slot = 0; slot < kSlots; slot++) {
 			if (mct[slot + 1] < 3) continue;
@@ -113,68 +127,53 @@ __global__ void __launch_bounds__(WARPS * 32) k_evaluate(EngineParams prm)
 			slot_alleles(mal, slot, a1, a2, a3);
 			const int row = slot_amb_row(b, s, slot, a2, a3);
 			const int alt = (a1 == refbase || a2 != refbase) ? a2 : a1;
-			// ---- pass 1: allele-frequency guess and group totals ----
+			// ---- pass 1: allele-frequency guess (newcrispcaller.c:48-68) and per-group strand totals ----
 			double p0 = 0;
 			int g0[6] = {0, 0, 0, 0, 0, 0}, g1[6] = {0, 0, 0, 0, 0, 0};
 			double w0[4] = {0, 0, 0, 0}, w1[4] = {0, 0, 0, 0};
 			for (int i = lane; i < P; i += 32) {
-				const int32_t* r = ic + i * kICPad;
+				const int32_t* r = ic + i * kNC;
+				int dd[3] = {0, 0, 0};
+				if (row >= 0) { const int32_t* d = b.amb_dec + ((size_t)row * P + i) * 4; dd[0] = d[0]; dd[1] = d[1]; dd[2] = d[2] + d[3]; }
 				int x1[3], x2[3], x3[3];
-#pragma unroll
-				for (int k = 0; k < 3; k++) { x1[k] = r[a1 + 8 * k]; x2[k] = r[a2 + 8 * k]; x3[k] = r[a3 + 8 * k]; }
-				if (row >= 0) {
-					const int32_t* d = b.amb_dec + ((size_t)row * P + i) * 4;
-					int dd[3] = {d[0], d[1], d[2] + d[3]};
-#pragma unroll
-					for (int k = 0; k < 3; k++) {
-						if (a1 == refbase) x1[k] -= dd[k];
-						if (a2 == refbase) x2[k] -= dd[k];
-						if (a3 == refbase) x3[k] -= dd[k];
-					}
-				}
+				load3(r, a1, a1 == refbase, dd, x1);
+				load3(r, a2, a2 == refbase, dd, x2);
+				load3(r, a3, a3 == refbase, dd, x3);
 				const int n = c.ploidy[i];
-				double C1 = x1[0] + x1[1] + x1[2], C2 = x2[0] + x2[1] + x2[2], C3 = x3[0] + x3[1] + x3[2];
+				const double C1 = x1[0] + x1[1] + x1[2], C2 = x2[0] + x2[1] + x2[2], C3 = x3[0] + x3[1] + x3[2];
 				double p1 = C2 / (C1 + C2 + C3 + 0.001);
 				p1 *= n;
 				if (p1 >= 0.2 && C2 >= 4) p0 += p1;
 				else if (p1 >= 0.4 && C2 >= 3) p0 += p1;
 				else if (n == 2 && p1 >= 0.25 && C2 >= 1) p0 += p1;
-				int* g = (pivot > 0 && i >= pivot) ? g1 : g0;
+				if (!permmode) {
+					int* g = (pivot > 0 && i >= pivot) ? g1 : g0;
 #pragma unroll
-				for (int k = 0; k < 3; k++) { g[2 * k] += x1[k] + x2[k] + x3[k]; g[2 * k + 1] += x2[k]; }
-				if (permmode) {
+					for (int k = 0; k < 3; k++) { g[2 * k] += x1[k] + x2[k] + x3[k]; g[2 * k + 1] += x2[k]; }
+				} else {
 					// ctable_weighted columns (allelecounts.c:231-236): Qhighcounts by strand
 					double* w = (i < pivot) ? w0 : w1;
 					double q1[2], q2[2], q3[2], qa[2];
-#pragma unroll
-					for (int k = 0; k < 2; k++) {
-						if (b.qhigh) {
-							const double* q = b.qhigh + ((size_t)s * P + i) * 16 + 8 * k;
-							q1[k] = q[a1]; q2[k] = q[a2]; q3[k] = q[a3]; qa[k] = q[alt];
-						} else {
-							q1[k] = r[a1 + 8 * k]; q2[k] = r[a2 + 8 * k]; q3[k] = r[a3 + 8 * k]; qa[k] = r[alt + 8 * k];
-						}
-						if (row >= 0) {
-							const int32_t* d = b.amb_dec + ((size_t)row * P + i) * 4;
-							double dec = d[k] + d[2 + k];
-							if (c.use_qv == 1 && b.amb_ep) dec -= b.amb_ep[((size_t)row * P + i) * 2 + k];
-							if (a1 == refbase) q1[k] -= dec;
-							if (a2 == refbase) q2[k] -= dec;
-							if (a3 == refbase) q3[k] -= dec;
-							if (alt == refbase) qa[k] -= dec;
-						}
-					}
+					const size_t cell = (size_t)s * P + i;
+					loadq(b, c, r, cell, a1, a1 == refbase, row, q1);
+					loadq(b, c, r, cell, a2, a2 == refbase, row, q2);
+					loadq(b, c, r, cell, a3, a3 == refbase, row, q3);
+					loadq(b, c, r, cell, alt, alt == refbase, row, qa);
 					w[0] += q1[0] + q2[0] + q3[0]; w[1] += qa[0]; w[2] += q1[1] + q2[1] + q3[1]; w[3] += qa[1];
 				}
 			}
 			p0 = warp_sum(p0);
-#pragma unroll
-			for (int k = 0; k < 6; k++) { g0[k] = warp_sum(g0[k]); g1[k] = warp_sum(g1[k]); }
 			const bool af_ok = !(p0 < 0.25 || (c.ploidy0 == 2 && p0 <= 0.4));
-			double sj0 = 0, sj1 = 0, tot = 0, wj0 = 0, wj1 = 0, wtot = 0;
+			double sj0 = 0, sj1 = 0;
 			if (af_ok && !permmode) {
-				// ---- pass 2: chi2pvalue_stratified joint statistic ----
-				double Ef[2], Er[2], Eb[2];
+				// ---- pass 2: chi2pvalue_stratified joint statistic (chisquare-stratified.c:44-61) ----
+#pragma unroll
+				for (int k = 0; k < 6; k++) g0[k] = warp_sum(g0[k]);
+				if (pivot > 0) {
+#pragma unroll
+					for (int k = 0; k < 6; k++) g1[k] = warp_sum(g1[k]);
+				}
+				double Ef[2], Er[2], Eb[2], rvf[2], rvr[2], rvb[2];
 				{
 					const int* g = g0;
 					for (int t = 0; t < 2; t++, g = g1) {
@@ -182,90 +181,70 @@ __global__ void __launch_bounds__(WARPS * 32) k_evaluate(EngineParams prm)
 						if (Ef[t] >= 0.999) Ef[t] = 0.999;
 						if (Er[t] >= 0.999) Er[t] = 0.999;
 						if (Eb[t] >= 0.999) Eb[t] = 0.999;
+						// per-group reciprocal standard deviations per read; the bidirectional term pairs (1-Eb) with Er (:57)
+						rvf[t] = rsqrt((1.0 - Ef[t]) * Ef[t]); rvr[t] = rsqrt((1.0 - Er[t]) * Er[t]); rvb[t] = rsqrt((1.0 - Eb[t]) * Er[t]);
+						if (pivot == 0) break;
 					}
 				}
-				tot = (double)g0[0] + g0[2] + g1[0] + g1[2] + g0[4] + g1[4];
+				const double tot = (double)g0[0] + g0[2] + g1[0] + g1[2] + g0[4] + g1[4];
 				if (tot >= 25) {
 					for (int i = lane; i < P; i += 32) {
-						const int32_t* r = ic + i * kICPad;
-						int x2[3], tt[3];
-#pragma unroll
-						for (int k = 0; k < 3; k++) { x2[k] = r[a2 + 8 * k]; tt[k] = r[a1 + 8 * k] + r[a2 + 8 * k] + r[a3 + 8 * k]; }
-						if (row >= 0) {
-							const int32_t* d = b.amb_dec + ((size_t)row * P + i) * 4;
-							int dd[3] = {d[0], d[1], d[2] + d[3]};
-#pragma unroll
-							for (int k = 0; k < 3; k++) {
-								int nref = (a1 == refbase) + (a2 == refbase) + (a3 == refbase);
-								tt[k] -= nref * dd[k];
-								if (a2 == refbase) x2[k] -= dd[k];
-							}
-						}
+						const int32_t* r = ic + i * kNC;
+						int dd[3] = {0, 0, 0};
+						if (row >= 0) { const int32_t* d = b.amb_dec + ((size_t)row * P + i) * 4; dd[0] = d[0]; dd[1] = d[1]; dd[2] = d[2] + d[3]; }
+						int x1[3], x2[3], x3[3];
+						load3(r, a1, a1 == refbase, dd, x1);
+						load3(r, a2, a2 == refbase, dd, x2);
+						load3(r, a3, a3 == refbase, dd, x3);
 						const int t = (pivot > 0 && i >= pivot) ? 1 : 0;
-						const int a = tt[0], bb = tt[1], cc = tt[2];
+						const int a = x1[0] + x2[0] + x3[0], bb = x1[1] + x2[1] + x3[1], cc = x1[2] + x2[2] + x3[2];
 						if (a + bb + cc < 1) continue;
-						double df = 0, dr = 0, db = 0, nf = sqrt((double)(a * a + bb * bb + cc * cc));
-						double w1 = a / nf, w2 = bb / nf, w3 = cc / nf;
-						if (a > 0) df = (x2[0] - Ef[t] * a) / sqrt((1.0 - Ef[t]) * Ef[t] * a);
-						if (bb > 0) dr = (x2[1] - Er[t] * bb) / sqrt((1.0 - Er[t]) * Er[t] * bb);
-						if (cc > 0) db = (x2[2] - Eb[t] * cc) / sqrt((1.0 - Eb[t]) * Er[t] * cc);  // Er: chisquare-stratified.c:57
-						double z = w1 * df + w2 * dr + w3 * db;
+						// z = (a df + b dr + c db)/|(a,b,c)| with d* = (alt - E n)/sqrt(var n): n d* = sqrt(n) (alt - E n) / sqrt(var)
+						double acc = 0.0;
+						if (a > 0) acc += sqrt((double)a) * (x2[0] - Ef[t] * a) * rvf[t];
+						if (bb > 0) acc += sqrt((double)bb) * (x2[1] - Er[t] * bb) * rvr[t];
+						if (cc > 0) acc += sqrt((double)cc) * (x2[2] - Eb[t] * cc) * rvb[t];
+						const double z = acc * rsqrt((double)(a * a + bb * bb + cc * cc));
 						if (t == 0) sj0 += z * z; else sj1 += z * z;
 					}
 					sj0 = warp_sum(sj0);
-					sj1 = warp_sum(sj1);
+					if (pivot > 0) sj1 = warp_sum(sj1);
 				}
-			} else if (af_ok && permmode) {
-				// ---- chi2pvalue on the weighted two-strand table (reported as chi2pval) ----
+			} else if (af_ok && permmode && c.ploidy0 > 2) {
+				// ---- chi2pvalue on the weighted two-strand table (reported as chi2pval; FET/chisquare.c:62-94) ----
 #pragma unroll
 				for (int k = 0; k < 4; k++) { w0[k] = warp_sum(w0[k]); w1[k] = warp_sum(w1[k]); }
 				double Ef[2], Er[2];
 				Ef[0] = (w0[1] + 0.25) / (w0[0] + 0.25); Er[0] = (w0[3] + 0.25) / (w0[2] + 0.25);
 				Ef[1] = (w1[1] + 0.25) / (w1[0] + 0.25); Er[1] = (w1[3] + 0.25) / (w1[2] + 0.25);
 				for (int t = 0; t < 2; t++) { if (Ef[t] >= 0.999) Ef[t] = 0.999; if (Er[t] >= 0.999) Er[t] = 0.999; }
-				wtot = w0[0] + w0[2] + w1[0] + w1[2];
+				const double wtot = w0[0] + w0[2] + w1[0] + w1[2];
 				if (wtot >= 25) {
 					for (int i = lane; i < P; i += 32) {
-						const int32_t* r = ic + i * kICPad;
-						double t0, t1, t2, t3;
-						{
-							double q1[2], q2[2], q3[2], qa[2];
-#pragma unroll
-							for (int k = 0; k < 2; k++) {
-								if (b.qhigh) {
-									const double* q = b.qhigh + ((size_t)s * P + i) * 16 + 8 * k;
-									q1[k] = q[a1]; q2[k] = q[a2]; q3[k] = q[a3]; qa[k] = q[alt];
-								} else {
-									q1[k] = r[a1 + 8 * k]; q2[k] = r[a2 + 8 * k]; q3[k] = r[a3 + 8 * k]; qa[k] = r[alt + 8 * k];
-								}
-								if (row >= 0) {
-									const int32_t* d = b.amb_dec + ((size_t)row * P + i) * 4;
-									double dec = d[k] + d[2 + k];
-									if (c.use_qv == 1 && b.amb_ep) dec -= b.amb_ep[((size_t)row * P + i) * 2 + k];
-									if (a1 == refbase) q1[k] -= dec;
-									if (a2 == refbase) q2[k] -= dec;
-									if (a3 == refbase) q3[k] -= dec;
-									if (alt == refbase) qa[k] -= dec;
-								}
-							}
-							t0 = q1[0] + q2[0] + q3[0]; t1 = qa[0]; t2 = q1[1] + q2[1] + q3[1]; t3 = qa[1];
-						}
+						const int32_t* r = ic + i * kNC;
+						double q1[2], q2[2], q3[2], qa[2];
+						const size_t cell = (size_t)s * P + i;
+						loadq(b, c, r, cell, a1, a1 == refbase, row, q1);
+						loadq(b, c, r, cell, a2, a2 == refbase, row, q2);
+						loadq(b, c, r, cell, a3, a3 == refbase, row, q3);
+						loadq(b, c, r, cell, alt, alt == refbase, row, qa);
+						const double t0 = q1[0] + q2[0] + q3[0], t1 = qa[0], t2 = q1[1] + q2[1] + q3[1], t3 = qa[1];
 						if (!(t0 + t2 >= 1)) continue;
 						const int t = i < pivot ? 0 : 1;
 						double df = 0, dr = 0;
-						double w1 = t0 / sqrt(t0 * t0 + t2 * t2);
-						double w2 = sqrt(1.0 - w1 * w1);
+						const double ww1 = t0 / sqrt(t0 * t0 + t2 * t2);
+						const double ww2 = sqrt(1.0 - ww1 * ww1);
 						if (t0 > 0) df = (t1 - Ef[t] * t0) / sqrt((1.0 - Ef[t]) * Ef[t] * t0);
 						if (t2 > 0) dr = (t3 - Er[t] * t2) / sqrt((1.0 - Er[t]) * Er[t] * t2);
-						double z = w1 * df + w2 * dr;
-						if (t == 0) wj0 += z * z; else wj1 += z * z;
+						const double z = ww1 * df + ww2 * dr;
+						if (t == 0) sj0 += z * z; else sj1 += z * z;
 					}
-					wj0 = warp_sum(wj0);
-					wj1 = warp_sum(wj1);
+					sj0 = warp_sum(sj0);
+					sj1 = warp_sum(sj1);
 				}
 			}
 			if (lane == slot) {
-				my_p0 = p0; my_sj0 = sj0; my_sj1 = sj1; my_tot = tot; my_wj0 = wj0; my_wj1 = wj1; my_wtot = wtot;
+				my_p0 = p0; my_sj0 = sj0; my_sj1 = sj1;
 				my_tested = af_ok ? 2 : 1;
 			}
 		}
@@ -283,7 +262,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_evaluate(EngineParams prm)
 					status = pass_fast_filter(c, b, s, a2, my_p0, ctp, ctp, 0.0) ? CRISPGPU_SLOT_NOCALL : CRISPGPU_SLOT_REJECT_CT;
 					if (status == CRISPGPU_SLOT_NOCALL) queue_push(prm.q.call_tasks, prm.q.counters + 1, o);
 				} else {
-					if (c.ploidy0 > 2) chi = chi2_from_groups(P, pivot, my_wj0, my_wj1, false);
+					if (c.ploidy0 > 2) chi = chi2_from_groups(P, pivot, my_sj0, my_sj1, false);
 					status = CRISPGPU_SLOT_REJECT_CT;  // provisional: k_filter decides once the permutation p-value exists
 					queue_push(prm.q.perm_tasks, prm.q.counters + 0, o);
 				}
@@ -300,7 +279,6 @@ __global__ void __launch_bounds__(WARPS * 32) k_evaluate(EngineParams prm)
 			prm.o.em_iters[o] = 0; prm.o.perm_k[o] = 0; prm.o.perm_hits[o] = 0;
 		}
 		if (lane == 0) { prm.o.varalleles[s] = 0; prm.o.strandpass[s] = 0; }
-		__syncwarp();
 	}
 }
 
