@@ -75,6 +75,8 @@ struct crispgpu_ctx {
 	crispgpu_timing timing{};
 	crispgpu_results res{};
 	int n_call = 0, n_perm = 0;
+	int64_t stage1_launches = 0;
+	bool fetch_pending = false;
 	char err[512] = {0};
 };
 
@@ -318,8 +320,11 @@ EngineParams make_params(crispgpu_ctx* ctx)
 	return prm;
 }
 
-// runs the kernel pipeline on data already on the device; fetch = copy results to the pinned mirrors
-int run_pipeline(crispgpu_ctx* ctx, bool fetch)
+// Stage 1 (enqueued by submit): screening kernels up to the copy of the task counters.
+// Stage 2 (enqueued by wait, after the counters arrived): caller kernels, finalisation, D2H.
+// Splitting at the only host synchronisation keeps crispgpu_submit non-blocking, so a front end can keep a second
+// context busy with the next batch's H2D while this one computes.
+int run_stage1(crispgpu_ctx* ctx)
 {
 	const int n = ctx->n_sites;
 	const crispgpu_config& g = ctx->cfg;
@@ -361,6 +366,17 @@ int run_pipeline(crispgpu_ctx* ctx, bool fetch)
 	// how many tasks reached the caller: sizes the per-pool rows
 	CK(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaEventRecord(ctx->ev_counts, ctx->stream));
+	ctx->stage1_launches = launches;
+	return 0;
+}
+
+int run_stage2(crispgpu_ctx* ctx, bool fetch)
+{
+	const int n = ctx->n_sites;
+	const crispgpu_config& g = ctx->cfg;
+	int rc = 0;
+	int64_t launches = ctx->stage1_launches;
+	EngineParams prm = make_params(ctx);
 	CK(cudaEventSynchronize(ctx->ev_counts));
 	const int32_t* hc = static_cast<const int32_t*>(ctx->h_counters.p);
 	ctx->n_perm = hc[0];
@@ -644,7 +660,7 @@ int crispgpu_submit(crispgpu_ctx* ctx, const crispgpu_batch* batch, int64_t* tic
 	int rc = copy_batch(ctx, batch);
 	if (rc) return rc;
 	ctx->resident = false;
-	rc = run_pipeline(ctx, true);
+	rc = run_stage1(ctx);
 	if (rc) return rc;
 	ctx->inflight = true;
 	ctx->ticket++;
@@ -657,9 +673,11 @@ int crispgpu_wait(crispgpu_ctx* ctx, int64_t ticket, crispgpu_results* out)
 	if (!ctx) return CRISPGPU_ERR_ARG;
 	if (!ctx->inflight || ticket != ctx->ticket) return CRISPGPU_ERR_TICKET;
 	CK(cudaSetDevice(ctx->device));
-	CK(cudaEventSynchronize(ctx->ev[EV_D2H]));
 	ctx->inflight = false;
-	int rc = finish_timing(ctx);
+	int rc = run_stage2(ctx, true);
+	if (rc) return rc;
+	CK(cudaEventSynchronize(ctx->ev[EV_D2H]));
+	rc = finish_timing(ctx);
 	if (rc) return rc;
 	fill_results(ctx, out);
 	return CRISPGPU_OK;
@@ -686,7 +704,9 @@ int crispgpu_run_resident(crispgpu_ctx* ctx, int fetch_results, crispgpu_results
 	}
 	CK(cudaSetDevice(ctx->device));
 	CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
-	int rc = run_pipeline(ctx, fetch_results != 0);
+	int rc = run_stage1(ctx);
+	if (rc) return rc;
+	rc = run_stage2(ctx, fetch_results != 0);
 	if (rc) return rc;
 	CK(cudaEventSynchronize(ctx->ev[EV_D2H]));
 	rc = finish_timing(ctx);
