@@ -49,6 +49,7 @@ struct crispgpu_ctx {
 	DevBuf d_b[24];
 	DevBatch db{};
 	int n_sites = 0;
+	size_t n_reads = 0;
 	bool resident = false;
 	// device results + pinned mirrors
 	DevBuf d_o[24], d_ac, d_qv;
@@ -60,7 +61,9 @@ struct crispgpu_ctx {
 	// launch geometry
 	int ev_warps = 8, ev_grid = 0;
 	size_t ev_smem = 0;
-	int em_threads = 256, em_grid = 0;
+	int em_threads = 256, em_grid = 0, em_warps = 8, em_key = -1;
+	int nq = 0, dense_lik = 0;
+	uint8_t qlist[16] = {0};
 	size_t em_smem = 0;
 	bool em_smem_g = true;
 	int pm_threads = 256, pm_grid = 0, pm_l10cap = 2048;
@@ -133,14 +136,16 @@ void bind_out(crispgpu_ctx* ctx)
 	ctx->dout.qv = static_cast<double*>(ctx->d_qv.p);
 }
 
-size_t em_smem_fixed(int P, int J, int nwarps)
+size_t em_smem_fixed(int P, int J, int nwarps, bool dense, int nq)
 {
 	size_t off = (sizeof(EmShared) + 15) & ~size_t(15);
 	off += sizeof(double) * P;
 	off += sizeof(double) * J;
 	off += sizeof(int32_t) * 6 * P;
 	off = (off + 15) & ~size_t(15);
-	off += sizeof(uint16_t) * 6 * kNQ * nwarps;
+	off += dense ? sizeof(uint32_t) * 2 * nq * 3 * P : sizeof(uint16_t) * 6 * kNQ * nwarps;
+	off = (off + 15) & ~size_t(15);
+	off += dense ? sizeof(double) * 2 * nq * J + kNQ : 0;
 	off = (off + 15) & ~size_t(15);
 	const int rounds = (P + 31) / 32;
 	off += sizeof(double) * 19 * rounds + sizeof(int32_t) * 2 * rounds;
@@ -162,7 +167,8 @@ int setup_geometry(crispgpu_ctx* ctx)
 	int warps = rounds * 3;
 	if (warps > kEmMaxWarps) warps = kEmMaxWarps;
 	ctx->em_threads = warps * 32;
-	const size_t fixed = em_smem_fixed(P, J, warps);
+	ctx->em_warps = warps;
+	const size_t fixed = em_smem_fixed(P, J, warps, false, 0);
 	const size_t gbytes = (size_t)3 * J * P * sizeof(double);
 	ctx->em_smem_g = fixed + gbytes <= budget;
 	ctx->em_smem = ctx->em_smem_g ? fixed + gbytes : fixed;
@@ -267,6 +273,7 @@ int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b)
 	ctx->db.n_sites = b->n_sites;
 	ctx->db.P = ctx->P;
 	ctx->n_sites = b->n_sites;
+	ctx->n_reads = b->n_sites ? b->read_off[(size_t)b->n_sites * ctx->P] : 0;
 	ctx->timing.h2d_bytes = bytes;
 	return 0;
 }
@@ -310,6 +317,9 @@ EngineParams make_params(crispgpu_ctx* ctx)
 	c.NC = static_cast<const double*>(ctx->d_NC.p);
 	c.T = static_cast<const double*>(ctx->d_T.p);
 	c.ncr_tab = static_cast<const double*>(ctx->d_ncr.p);
+	c.nq = ctx->nq;
+	c.dense_lik = ctx->dense_lik;
+	memcpy(c.qlist, ctx->qlist, sizeof c.qlist);
 	bind_out(ctx);
 	prm.o = ctx->dout;
 	prm.q.perm_tasks = static_cast<int32_t*>(ctx->d_perm_tasks.p);
@@ -340,6 +350,11 @@ int run_stage1(crispgpu_ctx* ctx)
 		launches++;
 	}
 	CK(cudaGetLastError());
+	if (n > 0 && g.em_flag >= 1 && g.use_base_qvs == 1 && ctx->n_reads > 0) {
+		k_qualmap<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->db.reads, ctx->n_reads, static_cast<int32_t*>(ctx->d_counters.p));
+		launches++;
+		CK(cudaGetLastError());
+	}
 	CK(cudaEventRecord(ctx->ev[EV_EVAL], ctx->stream));
 	if (g.chisq_permutation == 1 && n > 0) {
 		if (ctx->pm_smem == 0) {
@@ -364,7 +379,7 @@ int run_stage1(crispgpu_ctx* ctx)
 	}
 	CK(cudaEventRecord(ctx->ev[EV_FILTER], ctx->stream));
 	// how many tasks reached the caller: sizes the per-pool rows
-	CK(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaEventRecord(ctx->ev_counts, ctx->stream));
 	ctx->stage1_launches = launches;
 	return 0;
@@ -381,6 +396,26 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 	const int32_t* hc = static_cast<const int32_t*>(ctx->h_counters.p);
 	ctx->n_perm = hc[0];
 	ctx->n_call = hc[1];
+	{
+		// distinct quality characters of the batch -> dense likelihood path when few enough and one pool size
+		int nq = 0;
+		uint8_t ql[16] = {0};
+		for (int q = 0; q < kNQ; q++)
+			if ((static_cast<const uint32_t*>(ctx->h_counters.p)[4 + (q >> 5)] >> (q & 31)) & 1u) { if (nq < 16) ql[nq] = (uint8_t)q; nq++; }
+		const bool dense = g.em_flag >= 1 && g.use_base_qvs == 1 && ctx->class_ploidy.size() == 1 && nq >= 1 && nq <= kDenseNQ && ctx->em_smem_g &&
+		                   em_smem_fixed(ctx->P, ctx->nmax + 1, ctx->em_warps, true, nq) + (size_t)3 * (ctx->nmax + 1) * ctx->P * 8 <= ctx->smem_optin;
+		ctx->nq = dense ? nq : 0;
+		ctx->dense_lik = dense ? 1 : 0;
+		memcpy(ctx->qlist, ql, sizeof ql);
+		const int key = dense ? nq : 0;
+		if (key != ctx->em_key) {
+			ctx->em_key = key;
+			ctx->em_grid = 0;
+			const size_t fixed = em_smem_fixed(ctx->P, ctx->nmax + 1, ctx->em_warps, dense, nq);
+			ctx->em_smem = ctx->em_smem_g ? fixed + (size_t)3 * (ctx->nmax + 1) * ctx->P * 8 : fixed;
+		}
+		prm = make_params(ctx);
+	}
 	const int rows = g.em_flag >= 1 ? ctx->n_call : 0;
 	if (rows > 0) {
 		rc = ensure_dev(ctx, ctx->d_ac, (size_t)rows * ctx->P * 4); if (rc) return rc;

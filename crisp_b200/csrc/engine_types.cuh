@@ -11,6 +11,7 @@ constexpr int kNC = 24;         // 3 strand classes x 8 alleles
 constexpr int kSlots = 5;
 constexpr int kICPad = 25;      // padded row of the staged per-pool counts (bank-conflict-free with lanes over pools)
 constexpr int kNQ = 128;        // quality characters 0..127 index the likelihood table
+constexpr int kDenseNQ = 16;     // most distinct qualities the dense likelihood path handles
 constexpr int kNcrTabN = 256;   // rows of the host-computed log10 C(n,r) table
 constexpr double kExpCut = 20.0;  // terms below 10^-20 of the running maximum cannot change a double sum
 
@@ -48,6 +49,10 @@ struct DevCfg {
 	const int32_t* pclass;   // [P] index of the pool's ploidy among the distinct ploidies
 	const double* NC;        // [n_pclass][nmax+1]  log10 C(n,j)  (parsebam/init_variant.c:19-25, computed on the host)
 	const double* T;         // [n_pclass][2][kNQ][nmax+1] log10 e / log10(1-e) per (quality, allele count)
+	// distinct quality characters of the batch (k_qualmap): when there are at most kDenseNQ of them and the pools share one
+	// size, k_em uses the dense likelihood path with the table rows staged in shared memory
+	int nq, dense_lik;
+	uint8_t qlist[16];
 	const double* ncr_tab;   // [kNcrTabN][kNcrTabN/2+1] log10 C(n,r), r <= n/2, host-computed in the reference's summation
 	                         // order (FET/contables.c:80-87) so that the epsilon-free comparisons of lowcovFET.c:132-133
 	                         // see bit-identical terms; NULL unless the low-coverage permutation test is enabled
@@ -83,7 +88,7 @@ struct DevOut {
 struct DevQueues {
 	int32_t* perm_tasks;   // site*5+slot
 	int32_t* call_tasks;   // site*5+slot that reached the caller (EM or legacy)
-	int32_t* counters;     // [0]=n_perm [1]=n_call [2]=perm head [3]=call head
+	int32_t* counters;     // [0]=n_perm [1]=n_call [2]=perm head [3]=call head [4..7]=quality-presence bitmap (128 bits)
 };
 
 struct EngineParams {

@@ -59,7 +59,15 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm)
 	double* gcnt = reinterpret_cast<double*>(smem_raw + off); off += sizeof(double) * J;          // genotype_counts / HWE terms
 	int32_t* cnt6 = reinterpret_cast<int32_t*>(smem_raw + off); off += sizeof(int32_t) * 6 * P;   // [6][P]: a1 f,r,b ; a2 f,r,b
 	off = (off + 15) & ~size_t(15);
-	uint16_t* hist = reinterpret_cast<uint16_t*>(smem_raw + off); off += sizeof(uint16_t) * 6 * kNQ * nwarps;
+	const int nq = c.nq;
+	const bool dense = c.dense_lik != 0;
+	// sparse path: one 16-bit histogram [6][128] per warp; dense path: one 32-bit histogram [allele][quality][class][pool]
+	uint16_t* hist = reinterpret_cast<uint16_t*>(smem_raw + off);
+	uint32_t* dh = reinterpret_cast<uint32_t*>(smem_raw + off);
+	off += dense ? sizeof(uint32_t) * 2 * nq * 3 * P : sizeof(uint16_t) * 6 * kNQ * nwarps;
+	off = (off + 15) & ~size_t(15);
+	double* Ts = reinterpret_cast<double*>(smem_raw + off); off += dense ? sizeof(double) * 2 * nq * J : 0;  // staged table rows
+	uint8_t* qd = reinterpret_cast<uint8_t*>(smem_raw + off); off += dense ? kNQ : 0;                         // quality -> dense index
 	off = (off + 15) & ~size_t(15);
 	// per-round partial sums of one iteration: [0..2] LL per plane, [3..5] pnew per plane, [6] LLnull0, [7..18] T sums
 	double* part = reinterpret_cast<double*>(smem_raw + off); off += sizeof(double) * 19 * rounds;
@@ -71,6 +79,18 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm)
 	double* Gf = G + plane;
 	double* Gr = G + 2 * plane;
 
+	if (dense) {
+		// batch-constant: dense index of each quality character and the table rows of the present qualities
+		for (int q = tid; q < kNQ; q += blockDim.x) {
+			int d = 0;
+			for (int k = 0; k < nq; k++) if (c.qlist[k] < q) d++;
+			qd[q] = (uint8_t)d;
+		}
+		for (int idx = tid; idx < 2 * nq * J; idx += blockDim.x) {
+			const int j = idx % J, wd = idx / J, w = wd / nq, d = wd - w * nq;
+			Ts[idx] = c.T[((size_t)w * kNQ + c.qlist[d]) * J + j];
+		}
+	}
 
 	for (;;) {
 		__syncthreads();
@@ -175,10 +195,81 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm)
 			// EMmethod starts from its own E01 = E10 = 0.001 (crispEM.c:211); the count-based values above only
 			// shape the first likelihood (crispEM.c:362-375)
 			if (tid == 0) for (int k = 0; k < 3; k++) { sh->E01[k] = 0.001; sh->E10[k] = 0.001; }
+		} else if (dense) {
+			// calculate_pooled_likelihoods_snp, dense form (few distinct qualities, one pool size).
+			// (1) per pool (one warp) bin the packed reads into dh[allele][quality][class][pool];
+			// (2) contract with the staged table rows, LANES OVER POOLS: for a tile of 8 genotypes every (allele, quality)
+			//     bin costs three conflict-free count loads and, per genotype, one broadcast table load + three DFMAs.
+			for (int k = tid; k < 2 * nq * 3 * P; k += blockDim.x) dh[k] = 0;
+			__syncthreads();
+			for (int i = warp; i < P; i += nwarps) {
+				const uint32_t r0 = b.read_off[(size_t)s * P + i], r1 = b.read_off[(size_t)s * P + i + 1];
+				for (uint32_t cb = r0; cb < r1; cb += 256) {
+					uint32_t wv[8];
+#pragma unroll
+					for (int k = 0; k < 8; k++) {
+						const uint32_t r = cb + k * 32 + lane;
+						wv[k] = r < r1 ? (uint32_t)__ldg(b.reads + r) : 0xffffffffu;
+					}
+#pragma unroll
+					for (int k = 0; k < 8; k++) {
+						if (cb + k * 32 >= r1) break;
+						const uint32_t w = wv[k];
+						const int base = (w >> 8) & 3;
+						const int which = base == a1 ? 0 : (base == a2 ? 1 : -1);
+						const bool use = w != 0xffffffffu && which >= 0;
+						const int cls = (w >> 11) & 1 ? 2 : ((w >> 10) & 1);
+						const int key = use ? (which * nq + qd[w & 0x7f]) * 3 + cls : -1 - lane;
+						const unsigned peers = __match_any_sync(0xffffffffu, key);
+						if (use && lane == __ffs(peers) - 1) dh[key * P + i] += __popc(peers);
+					}
+				}
+			}
+			__syncthreads();
+			const int ntile = (J + 7) >> 3;
+			for (int item = warp; item < rounds * ntile; item += nwarps) {
+				const int rd = item / ntile, j0 = (item - rd * ntile) * 8;
+				const int i = rd * 32 + lane;
+				const bool act = i < P;
+				const int ii = act ? i : P - 1;
+				double acc[3][8];
+#pragma unroll
+				for (int cls = 0; cls < 3; cls++)
+#pragma unroll
+					for (int jj = 0; jj < 8; jj++) acc[cls][jj] = 0.0;
+				for (int wd = 0; wd < 2 * nq; wd++) {
+					const uint32_t cf = dh[(wd * 3 + 0) * P + ii], cr = dh[(wd * 3 + 1) * P + ii], cbd = dh[(wd * 3 + 2) * P + ii];
+					if (!__any_sync(0xffffffffu, (cf | cr | cbd) != 0)) continue;
+					const double xf = (double)cf, xr = (double)cr, xb = (double)cbd;
+					const double* tr = Ts + wd * J + j0;
+#pragma unroll
+					for (int jj = 0; jj < 8; jj++) {
+						const double t = (j0 + jj < J) ? tr[jj] : 0.0;
+						acc[0][jj] = fma(xf, t, acc[0][jj]);
+						acc[1][jj] = fma(xr, t, acc[1][jj]);
+						acc[2][jj] = fma(xb, t, acc[2][jj]);
+					}
+				}
+				if (act) {
+#pragma unroll
+					for (int jj = 0; jj < 8; jj++) {
+						const int j = j0 + jj;
+						if (j < J) {
+							const double nc = c.NC[j];
+							const size_t idx = (size_t)j * P + i;
+							Gf[idx] = acc[0][jj] + nc;
+							Gr[idx] = acc[1][jj] + nc;
+							Gt[idx] = (acc[0][jj] + acc[1][jj] + acc[2][jj]) + nc;
+							if (j == 0) Gb0[i] = acc[2][jj];
+						}
+					}
+				}
+			}
+			__syncthreads();
 		} else {
-			// calculate_pooled_likelihoods_snp: per pool, histogram the packed reads over (strand class, allele, quality)
-			// and contract with the table T[allele][quality][j].  One warp per pool; each lane owns genotypes j and j+32
-			// (and j+64, j+96 for pool sizes above 63).
+			// calculate_pooled_likelihoods_snp, sparse form (any number of qualities / pool sizes): per pool, histogram
+			// the packed reads over (strand class, allele, quality) and contract with the table T[allele][quality][j].
+			// One warp per pool; each lane owns genotypes j and j+32 (and j+64, j+96 for pool sizes above 63).
 			uint16_t* h = hist + (size_t)warp * 6 * kNQ;
 			for (int i = warp; i < P; i += nwarps) {
 				const uint32_t r0 = b.read_off[(size_t)s * P + i], r1 = b.read_off[(size_t)s * P + i + 1];

@@ -282,6 +282,38 @@ __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_evaluate(Eng
 	}
 }
 
+// Which quality characters occur in the batch's packed read stream: a 128-bit presence bitmap (counters[4..7]).
+// HBM-streaming pass (2 B per read, 16-byte loads); lets k_em pick the dense likelihood path.
+__global__ void k_qualmap(const uint16_t* __restrict__ reads, size_t n_reads, int32_t* counters)
+{
+	unsigned long long lo = 0ull, hi = 0ull;
+	const size_t nvec = n_reads / 8;
+	const uint4* v = reinterpret_cast<const uint4*>(reads);
+	for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nvec; k += (size_t)gridDim.x * blockDim.x) {
+		const uint4 x = __ldg(v + k);
+		const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+		for (int t = 0; t < 4; t++) {
+			const uint32_t q0 = w[t] & 0x7f, q1 = (w[t] >> 16) & 0x7f;
+			if (q0 < 64) lo |= 1ull << q0; else hi |= 1ull << (q0 - 64);
+			if (q1 < 64) lo |= 1ull << q1; else hi |= 1ull << (q1 - 64);
+		}
+	}
+	if (blockIdx.x == 0 && threadIdx.x < (int)(n_reads - nvec * 8)) {
+		const uint32_t q = reads[nvec * 8 + threadIdx.x] & 0x7f;
+		if (q < 64) lo |= 1ull << q; else hi |= 1ull << (q - 64);
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) { lo |= __shfl_xor_sync(0xffffffffu, lo, o); hi |= __shfl_xor_sync(0xffffffffu, hi, o); }
+	if ((threadIdx.x & 31) == 0) {
+		unsigned int* c = reinterpret_cast<unsigned int*>(counters) + 4;
+		if ((uint32_t)lo) atomicOr(c + 0, (uint32_t)lo);
+		if (lo >> 32) atomicOr(c + 1, (uint32_t)(lo >> 32));
+		if ((uint32_t)hi) atomicOr(c + 2, (uint32_t)hi);
+		if (hi >> 32) atomicOr(c + 3, (uint32_t)(hi >> 32));
+	}
+}
+
 // After the permutation kernel: apply the FAST_FILTER rejects with the Monte-Carlo p-value and queue the survivors.
 __global__ void k_filter(EngineParams prm)
 {

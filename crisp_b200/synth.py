@@ -65,6 +65,7 @@ def synth_batch(
     fixed_depth: bool = False,
     with_qhigh: bool = False,
     with_stats: bool = False,
+    quals=None,
 ) -> Batch:
     rng = np.random.default_rng(seed)
     P = int(n_pools)
@@ -96,7 +97,10 @@ def synth_batch(
     R = int(cell.sum())
     cell_of_read = np.repeat(np.arange(n * P, dtype=np.int64), cell)
     site_of_read = cell_of_read // P
-    q = QUALS[rng.choice(5, size=R, p=QUAL_P)]
+    if quals is None:
+        q = QUALS[rng.choice(5, size=R, p=QUAL_P)]
+    else:  # e.g. range(14, 42): the many-valued quality spectrum of older instruments
+        q = np.asarray(list(quals), dtype=np.int64)[rng.integers(0, len(quals), R)]
     strand = (rng.random(R) < 0.5).astype(np.int64)
     bidir = (rng.random(R) < bidir_frac).astype(np.int64) if bidir_frac > 0 else np.zeros(R, np.int64)
     u = rng.random(R)

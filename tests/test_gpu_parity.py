@@ -27,6 +27,9 @@ SCENARIOS = [
     ("chr20_c3", 48, 100, 96, 60, {}, dict(variant_frac=0.5)),
     ("lowcov_c5", 48, 500, 10, 10, {}, dict(variant_frac=0.5)),
     ("varpool", 300, 8, [10, 20, 30, 40, 10, 20, 30, 40], 120, {}, dict(variant_frac=0.4, bidir_frac=0.1)),
+    ("manyquals", 200, 10, 20, 100, {}, dict(variant_frac=0.4, bidir_frac=0.1, quals=range(14, 42))),
+    ("twelvequals_c2", 100, 50, 48, 200, {}, dict(variant_frac=0.3, quals=range(20, 42, 2))),
+    ("deep_pool", 40, 4, 40, 3000, {}, dict(variant_frac=0.5)),
     ("pivot", 300, 12, 16, 80, dict(pivot_sample=5), dict(variant_frac=0.4)),
     ("indel", 300, 10, 20, 100, {}, dict(variant_frac=0.3, indel_frac=0.5, bidir_frac=0.05)),
     ("nobq", 200, 10, 20, 100, dict(use_base_qvs=0), dict(variant_frac=0.4)),
