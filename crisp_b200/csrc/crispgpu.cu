@@ -39,6 +39,8 @@ struct crispgpu_ctx {
 	int num_sms = 0;
 	size_t smem_optin = 0;
 	cudaStream_t stream = nullptr;
+	cudaStream_t side = nullptr;  // side stream: the quality-presence scan overlaps the screening kernel
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 	bool own_stream = false;
 	crispgpu_config cfg{};
 	std::vector<int32_t> ploidy, phenotypes, pclass, class_ploidy;
@@ -148,7 +150,7 @@ size_t em_smem_fixed(int P, int J, int nwarps, bool dense, int nq)
 	off += dense ? sizeof(double) * 2 * nq * J + kNQ : 0;
 	off = (off + 15) & ~size_t(15);
 	const int rounds = (P + 31) / 32;
-	off += sizeof(double) * 19 * rounds + sizeof(int32_t) * 2 * rounds;
+	off += sizeof(double) * 2 * 19 * rounds + sizeof(int32_t) * 2 * rounds;
 	off = (off + 15) & ~size_t(15);
 	off += sizeof(double) * 3 * P;
 	return off;
@@ -344,17 +346,23 @@ int run_stage1(crispgpu_ctx* ctx)
 	CK(cudaMemsetAsync(ctx->d_counters.p, 0, 16 * sizeof(int32_t), ctx->stream));
 	EngineParams prm = make_params(ctx);
 	CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
+	const bool scan = n > 0 && g.em_flag >= 1 && g.use_base_qvs == 1 && ctx->n_reads > 0;
+	if (scan) {
+		// fork: the read-stream scan is independent of the count-based screening
+		CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+		CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+		k_qualmap<<<ctx->num_sms * 2, 256, 0, ctx->side>>>(ctx->db.reads, ctx->n_reads, static_cast<int32_t*>(ctx->d_counters.p));
+		launches++;
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(ctx->ev_join, ctx->side));
+	}
 	if (n > 0) {
 		rc = launch_evaluate(ctx, prm);
 		if (rc) return rc;
 		launches++;
 	}
 	CK(cudaGetLastError());
-	if (n > 0 && g.em_flag >= 1 && g.use_base_qvs == 1 && ctx->n_reads > 0) {
-		k_qualmap<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->db.reads, ctx->n_reads, static_cast<int32_t*>(ctx->d_counters.p));
-		launches++;
-		CK(cudaGetLastError());
-	}
+	if (scan) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
 	CK(cudaEventRecord(ctx->ev[EV_EVAL], ctx->stream));
 	if (g.chisq_permutation == 1 && n > 0) {
 		if (ctx->pm_smem == 0) {
@@ -623,6 +631,9 @@ int crispgpu_create(const crispgpu_config* cfg, int device_id, void* stream, cri
 	}
 	for (int i = 0; i < EV_COUNT; i++) if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
 	if (cudaEventCreateWithFlags(&ctx->ev_counts, cudaEventDisableTiming) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
+	if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
+	if (cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
+	if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
 	// configuration tables: NC on the host exactly as init_variant does (init_variant.c:19-25), T on the device
 	const int J = ctx->nmax + 1, ncl = (int)ctx->class_ploidy.size();
 	std::vector<double> NC((size_t)ncl * J, 0.0);
@@ -679,6 +690,9 @@ void crispgpu_destroy(crispgpu_ctx* ctx)
 	fd(ctx->d_perm_tasks); fd(ctx->d_call_tasks); fd(ctx->d_counters); fh(ctx->h_counters); fd(ctx->d_gws);
 	for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
 	if (ctx->ev_counts) cudaEventDestroy(ctx->ev_counts);
+	if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+	if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+	if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
 	if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }

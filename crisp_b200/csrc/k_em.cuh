@@ -70,7 +70,7 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm)
 	uint8_t* qd = reinterpret_cast<uint8_t*>(smem_raw + off); off += dense ? kNQ : 0;                         // quality -> dense index
 	off = (off + 15) & ~size_t(15);
 	// per-round partial sums of one iteration: [0..2] LL per plane, [3..5] pnew per plane, [6] LLnull0, [7..18] T sums
-	double* part = reinterpret_cast<double*>(smem_raw + off); off += sizeof(double) * 19 * rounds;
+	double* part_base = reinterpret_cast<double*>(smem_raw + off); off += sizeof(double) * 2 * 19 * rounds;  // double-buffered
 	int32_t* part_i = reinterpret_cast<int32_t*>(smem_raw + off); off += sizeof(int32_t) * 2 * rounds;
 	off = (off + 15) & ~size_t(15);
 	double* mprev = reinterpret_cast<double*>(smem_raw + off); off += sizeof(double) * 3 * P;  // log-sum-exp shift per (plane, pool)
@@ -160,11 +160,15 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm)
 		// =====================================================================================================
 		// likelihood planes
 		// =====================================================================================================
+		// error rates of the count-based likelihood, identical in every thread (registers)
+		double E01[3], E10[3];
+		for (int k = 0; k < 3; k++) { E01[k] = sh->E01[k]; E10[k] = sh->E10[k]; }
 		auto count_likelihood = [&]() {
-			// calculate_pooled_likelihoods_indel (crispEM.c:54-87) with the current E01/E10
-			double e01[3], e10[3];
+			// calculate_pooled_likelihoods_indel (crispEM.c:54-87) with the current E01/E10; the clamps and the
+			// product rule for the bidirectional class are applied in place (:65-69)
+			double* e01 = E01;
+			double* e10 = E10;
 			for (int k = 0; k < 3; k++) {
-				e01[k] = sh->E01[k]; e10[k] = sh->E10[k];
 				if (e01[k] < kMinP) e01[k] = kMinP; else if (e01[k] > 1.0 - kMinP) e01[k] = 1.0 - kMinP;
 				if (e10[k] < kMinP) e10[k] = kMinP; else if (e10[k] > 1.0 - kMinP) e10[k] = 1.0 - kMinP;
 			}
@@ -187,14 +191,13 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm)
 				if (j == 0) Gb0[i] = gb;
 			}
 			__syncthreads();
-			if (tid == 0) for (int k = 0; k < 3; k++) { sh->E01[k] = e01[k]; sh->E10[k] = e10[k]; }  // clamps are applied in place (:65-69)
 		};
 
 		if (countlik) {
 			count_likelihood();
 			// EMmethod starts from its own E01 = E10 = 0.001 (crispEM.c:211); the count-based values above only
 			// shape the first likelihood (crispEM.c:362-375)
-			if (tid == 0) for (int k = 0; k < 3; k++) { sh->E01[k] = 0.001; sh->E10[k] = 0.001; }
+			for (int k = 0; k < 3; k++) { E01[k] = 0.001; E10[k] = 0.001; }
 		} else if (dense) {
 			// calculate_pooled_likelihoods_snp, dense form (few distinct qualities, one pool size).
 			// (1) per pool (one warp) bin the packed reads into dh[allele][quality][class][pool];
@@ -221,7 +224,7 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm)
 						const int cls = (w >> 11) & 1 ? 2 : ((w >> 10) & 1);
 						const int key = use ? (which * nq + qd[w & 0x7f]) * 3 + cls : -1 - lane;
 						const unsigned peers = __match_any_sync(0xffffffffu, key);
-						if (use && lane == __ffs(peers) - 1) dh[key * P + i] += __popc(peers);
+						if (use && lane == __ffs(peers) - 1) atomicAdd(dh + key * P + i, (uint32_t)__popc(peers));  // fire-and-forget; one warp per column
 					}
 				}
 			}
@@ -385,12 +388,13 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm)
 		// =====================================================================================================
 		// EM iterations (crispEM.c:233-314)
 		// =====================================================================================================
+		// Iteration state lives in registers, replicated in every warp (lane pl holds plane pl): one barrier per
+		// iteration, after which every warp reduces the per-round partial sums in the same fixed order.
+		double my_p = sh->p[0], my_LL = 0.0, LLnull0 = 0.0;
+		int it = 0;
 		for (;;) {
-			if (tid < 3) {
-				sh->lp[tid][0] = log10(sh->p[tid]);
-				sh->lp[tid][1] = log10(1.0 - sh->p[tid]);
-			}
-			__syncthreads();
+			const double my_l0 = log10(my_p), my_l1 = log10(1.0 - my_p);
+			double* part = part_base + (it & 1) * 19 * rounds;
 			const int nunits = rounds * 3;
 			for (int u = warp; u < nunits; u += nwarps) {
 				const int pl = u / rounds, rd = u - pl * rounds;
@@ -399,13 +403,13 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm)
 				const int ii = act ? i : P - 1;
 				const int n = c.ploidy[ii];
 				const double* Hp = G + (size_t)pl * plane + ii;
-				const double l0 = sh->lp[pl][0], l1 = sh->lp[pl][1];
+				const double l0 = __shfl_sync(0xffffffffu, my_l0, pl), l1 = __shfl_sync(0xffffffffu, my_l1, pl);
 				const double dl = l0 - l1, base = (double)n * l1;
 				// Shift of the log-sum-exp: the exact maximum on the first iteration, afterwards the maximum seen in the
 				// previous iteration (any shift within a few decades of the maximum gives the same sum; the fallback below
 				// repeats the unit when the assumed shift turns out more than 3 decades too high).
 				double m;
-				if (sh->iter == 0 || countlik) {  // count-based planes are rebuilt every iteration: always take the exact maximum
+				if (it == 0 || countlik) {  // count-based planes are rebuilt every iteration: always take the exact maximum
 					m = -1e300;
 					const double* hp = Hp;
 					double jd = 0.0, vprev = -1e300;
@@ -429,19 +433,18 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm)
 						const double d = v - m;
 						newmax = fmax(newmax, v);
 						if (d > -kExpCut2) {
-							const double e = exp10(d);
+							const double e = exp10_lse(d);
 							S += e;
 							Wj = fma(jd, e, Wj);
 							if (countlik && pl == 0) {
 								const double f = jd / n;
 #pragma unroll
 								for (int k = 0; k < 3; k++) {
-									const double E01 = sh->E01[k], E10 = sh->E10[k];
-									const double den1 = (1.0 - f) * (1.0 - E01) + f * E10, den2 = (1.0 - f) * E01 + f * (1.0 - E10);
-									T00[k] += e * (1.0 - f) * (1.0 - E01) / den1;
-									T10[k] += e * f * E10 / den1;
-									T11[k] += e * f * (1.0 - E10) / den2;
-									T01[k] += e * (1.0 - f) * E01 / den2;
+									const double den1 = (1.0 - f) * (1.0 - E01[k]) + f * E10[k], den2 = (1.0 - f) * E01[k] + f * (1.0 - E10[k]);
+									T00[k] += e * (1.0 - f) * (1.0 - E01[k]) / den1;
+									T10[k] += e * f * E10[k] / den1;
+									T11[k] += e * f * (1.0 - E10[k]) / den2;
+									T01[k] += e * (1.0 - f) * E01[k] / den2;
 								}
 							}
 						}
@@ -484,42 +487,40 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm)
 				}
 			}
 			__syncthreads();
-			// ---- finish the iteration: warp 0, lane pl handles plane pl ----
-			if (warp == 0) {
-				double LLn = 0.0, pn = 0.0, prev = 0.0;
-				if (lane < 3) {
-					for (int r = 0; r < rounds; r++) { LLn += part[lane * rounds + r]; pn += part[(3 + lane) * rounds + r]; }
-					prev = sh->LL[lane];
-					pn /= c.K;
-					if (pn < kMinP) pn = kMinP;
-					if (1.0 - pn <= kMinP) pn = 1.0 - kMinP;
-				}
-				// convergence: fabsf() of the double differences against double thresholds (crispEM.c:304)
-				const double dl = (double)fabsf((float)(LLn - prev));
-				const double d0 = __shfl_sync(0xffffffffu, dl, 0), d1 = __shfl_sync(0xffffffffu, dl, 1), d2 = __shfl_sync(0xffffffffu, dl, 2);
-				if (lane < 3) { sh->LL[lane] = LLn; sh->p[lane] = pn; }
-				if (lane == 0) {
-					const int it = ++sh->iter;
-					double nul = 0.0;
-					for (int r = 0; r < rounds; r++) nul += part[6 * rounds + r];
-					sh->LLnull0 = nul;
-					if (countlik) {
-						for (int k = 0; k < 3; k++) {
-							double t00 = 0, t01 = 0, t10 = 0, t11 = 0;
-							for (int r = 0; r < rounds; r++) { t00 += part[(7 + k) * rounds + r]; t01 += part[(10 + k) * rounds + r]; t10 += part[(13 + k) * rounds + r]; t11 += part[(16 + k) * rounds + r]; }
-							double e01 = (t01 + 1.5 - 1) / (t01 + t00 + 1.5 + 50 - 1), e10 = (t10 + 1.5 - 1) / (t10 + t11 + 50 + 1.5 - 1);
-							if (e10 > 0.05) e10 = 0.05;
-							sh->E01[k] = e01;
-							sh->E10[k] = e10;
-						}
-					}
-					if ((it >= 2 && d0 <= 0.0001 && d1 <= 0.01 && d2 <= 0.01) || it >= 1000) sh->exitflag = 1;
-				}
+			// ---- finish the iteration (every warp, identically): lane pl handles plane pl ----
+			double LLn = 0.0, pn = 0.0;
+			if (lane < 3) {
+				for (int r = 0; r < rounds; r++) { LLn += part[lane * rounds + r]; pn += part[(3 + lane) * rounds + r]; }
+				pn /= c.K;
+				if (pn < kMinP) pn = kMinP;
+				if (1.0 - pn <= kMinP) pn = 1.0 - kMinP;
 			}
-			__syncthreads();
-			if (countlik) count_likelihood();  // crispEM.c:298, also on the exit iteration
-			if (sh->exitflag) break;
+			// convergence: fabsf() of the double differences against double thresholds (crispEM.c:304)
+			const double dconv = (double)fabsf((float)(LLn - my_LL));
+			const double d0 = __shfl_sync(0xffffffffu, dconv, 0), d1 = __shfl_sync(0xffffffffu, dconv, 1), d2 = __shfl_sync(0xffffffffu, dconv, 2);
+			my_LL = LLn;
+			my_p = lane < 3 ? pn : 0.5;
+			it++;
+			LLnull0 = 0.0;
+			for (int r = 0; r < rounds; r++) LLnull0 += part[6 * rounds + r];
+			if (countlik) {
+				for (int k = 0; k < 3; k++) {
+					double t00 = 0, t01 = 0, t10 = 0, t11 = 0;
+					for (int r = 0; r < rounds; r++) { t00 += part[(7 + k) * rounds + r]; t01 += part[(10 + k) * rounds + r]; t10 += part[(13 + k) * rounds + r]; t11 += part[(16 + k) * rounds + r]; }
+					double e01 = (t01 + 1.5 - 1) / (t01 + t00 + 1.5 + 50 - 1), e10 = (t10 + 1.5 - 1) / (t10 + t11 + 50 + 1.5 - 1);
+					if (e10 > 0.05) e10 = 0.05;
+					E01[k] = e01;
+					E10[k] = e10;
+				}
+				count_likelihood();  // crispEM.c:298, also on the exit iteration
+			}
+			if ((it >= 2 && d0 <= 0.0001 && d1 <= 0.01 && d2 <= 0.01) || it >= 1000) break;
 		}
+		if (warp == 0) {
+			if (lane < 3) { sh->LL[lane] = my_LL; sh->p[lane] = my_p; }
+			if (lane == 0) { sh->LLnull0 = LLnull0; sh->iter = it; }
+		}
+		__syncthreads();
 
 		// =====================================================================================================
 		// statistics of the fit (crispEM.c:321-349)
@@ -569,7 +570,7 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm)
 					double jd = 0.0;
 					for (int j = 0; j <= n; j++, hp += P, jd += 1.0) {
 						const double d = fma(jd, dl, *hp) + base - best;
-						if (d > -kExpCut) S += exp10(d);
+						if (d > -kExpCut) S += exp10_lse(d);
 					}
 				}
 				const double Lb = best + log10(S);
@@ -580,7 +581,7 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm)
 						double v = 0.0;
 						if (act && j <= n) {
 							const double d = fma(jd, dl, *hp) + base - Lb;
-							if (d > -kExpCut - 3) v = exp10(d);
+							if (d > -kExpCut - 3) v = exp10_lse(d);
 						}
 						if (act) post[(size_t)j * P + ii] = v;
 					}
