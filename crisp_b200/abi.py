@@ -110,6 +110,12 @@ _RESULT_FIELDS = [
     ("em_iters", np.int32, 5),
     ("perm_k", np.int32, 5),
     ("perm_hits", np.int32, 5),
+    ("assoc_p", np.float64, 5),
+    ("assoc_llr", np.float64, 5),
+    ("assoc_or", np.float64, 5),
+    ("assoc_p1", np.float64, 5),
+    ("assoc_llr1", np.float64, 5),
+    ("assoc_or1", np.float64, 5),
 ]
 
 

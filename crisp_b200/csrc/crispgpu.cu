@@ -46,7 +46,7 @@ struct crispgpu_ctx {
 	std::vector<int32_t> ploidy, phenotypes, pclass, class_ploidy;
 	int P = 0, K = 0, nmax = 0;
 	// device configuration tables
-	DevBuf d_ploidy, d_pclass, d_class_ploidy, d_NC, d_T, d_ncr;
+	DevBuf d_ploidy, d_pclass, d_class_ploidy, d_NC, d_T, d_ncr, d_pheno;
 	// device batch
 	DevBuf d_b[24];
 	DevBatch db{};
@@ -54,8 +54,8 @@ struct crispgpu_ctx {
 	size_t n_reads = 0;
 	bool resident = false;
 	// device results + pinned mirrors
-	DevBuf d_o[24], d_ac, d_qv;
-	DevBuf h_o[24], h_ac, h_qv;
+	DevBuf d_o[32], d_ac, d_qv;
+	DevBuf h_o[32], h_ac, h_qv;
 	DevOut dout{};
 	// queues
 	DevBuf d_perm_tasks, d_call_tasks, d_counters, h_counters, d_gws;
@@ -127,6 +127,7 @@ const OutField kOutFields[] = {
 	{1, 5}, {1, 5}, {1, 5}, {4, 5}, // status, allele, call_rank, call_row
 	{8, 5}, {8, 5}, {8, 5}, {8, 5}, {8, 5}, {8, 5}, {8, 5}, {8, 5}, {8, 5},  // paf ctpval chi2pval af_ml delta deltaf hwe qvpf qvpr
 	{4, 5}, {4, 5}, {4, 5}, {4, 5}, {4, 5}, {4, 5},  // varpools allelecount variantpools em_iters perm_k perm_hits
+	{8, 5}, {8, 5}, {8, 5}, {8, 5}, {8, 5}, {8, 5},  // assoc_p assoc_llr assoc_or assoc_p1 assoc_llr1 assoc_or1
 };
 constexpr int kNumOut = sizeof(kOutFields) / sizeof(kOutFields[0]);
 
@@ -307,6 +308,8 @@ EngineParams make_params(crispgpu_ctx* ctx)
 	c.em_flag = g.em_flag; c.max_iter = g.max_iter; c.chisq_permutation = g.chisq_permutation; c.fast_filter = g.fast_filter;
 	c.use_base_qvs = g.use_base_qvs; c.min_reads = g.min_reads; c.qv_offset = g.qv_offset; c.min_q = g.min_q; c.pivot_sample = g.pivot_sample;
 	c.use_qv = g.use_qv; c.exact_mode = g.exact_mode;
+	c.association = (g.association == 1 && ctx->d_pheno.p) ? 1 : 0;
+	c.phenotypes = static_cast<const int32_t*>(ctx->d_pheno.p);
 	c.thresh1 = g.thresh1; c.min_qpv = g.min_qpv; c.thresh3 = g.thresh3; c.ser = g.ser; c.relax = g.relax; c.qmin = g.qmin;
 	c.ref_bias = g.agilent_ref_bias; c.theta = g.theta;
 	double alpha = 0.0;
@@ -653,6 +656,7 @@ int crispgpu_create(const crispgpu_config* cfg, int device_id, void* stream, cri
 	if ((rc = up(ctx->d_pclass, ctx->pclass.data(), (size_t)ctx->P * 4))) return fail(rc);
 	if ((rc = up(ctx->d_class_ploidy, ctx->class_ploidy.data(), (size_t)ncl * 4))) return fail(rc);
 	if ((rc = up(ctx->d_NC, NC.data(), NC.size() * 8))) return fail(rc);
+	if (!ctx->phenotypes.empty() && (rc = up(ctx->d_pheno, ctx->phenotypes.data(), (size_t)ctx->P * 4))) return fail(rc);
 	if ((rc = ensure_dev(ctx, ctx->d_T, (size_t)ncl * 2 * kNQ * J * 8))) return fail(rc);
 	if (cfg->chisq_permutation == 1 && ctx->ploidy[0] == 2) {
 		// constant table log10 C(n,r) in the reference's own summation order, evaluated with the host libm
@@ -682,7 +686,7 @@ void crispgpu_destroy(crispgpu_ctx* ctx)
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	auto fd = [](DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; };
 	auto fh = [](DevBuf& b) { if (b.p) cudaFreeHost(b.p); b.p = nullptr; };
-	fd(ctx->d_ploidy); fd(ctx->d_pclass); fd(ctx->d_class_ploidy); fd(ctx->d_NC); fd(ctx->d_T); fd(ctx->d_ncr);
+	fd(ctx->d_ploidy); fd(ctx->d_pclass); fd(ctx->d_class_ploidy); fd(ctx->d_NC); fd(ctx->d_T); fd(ctx->d_ncr); fd(ctx->d_pheno);
 	for (auto& b : ctx->d_b) fd(b);
 	for (auto& b : ctx->d_o) fd(b);
 	for (auto& b : ctx->h_o) fh(b);

@@ -42,11 +42,12 @@ struct DevBatch {
 struct DevCfg {
 	int P, K, nmax, n_pclass, ploidy0, varpoolsize;
 	int em_flag, max_iter, chisq_permutation, fast_filter, use_base_qvs, min_reads, qv_offset, min_q, pivot_sample;
-	int use_qv, exact_mode;
+	int use_qv, exact_mode, association;
 	double thresh1, min_qpv, thresh3, ser, relax, qmin, ref_bias, theta, alpha_prior;  // alpha_prior = theta * H_K
 	uint64_t rng_seed;
 	const int32_t* ploidy;   // [P]
 	const int32_t* pclass;   // [P] index of the pool's ploidy among the distinct ploidies
+	const int32_t* phenotypes;  // [P] bit mask 1 control / 2 case / 4 early onset (options->phenotypes), NULL without --phenotypes
 	const double* NC;        // [n_pclass][nmax+1]  log10 C(n,j)  (parsebam/init_variant.c:19-25, computed on the host)
 	const double* T;         // [n_pclass][2][kNQ][nmax+1] log10 e / log10(1-e) per (quality, allele count)
 	// distinct quality characters of the batch (k_qualmap): when there are at most kDenseNQ of them and the pools share one
@@ -80,6 +81,12 @@ struct DevOut {
 	int32_t* em_iters;
 	int32_t* perm_k;
 	int32_t* perm_hits;
+	double* assoc_p;
+	double* assoc_llr;
+	double* assoc_or;
+	double* assoc_p1;
+	double* assoc_llr1;
+	double* assoc_or1;
 	int32_t* ac;   // [rows][P]
 	double* qv;    // [rows][P]
 };

@@ -161,7 +161,7 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm)
 		// likelihood planes
 		// =====================================================================================================
 		// error rates of the count-based likelihood, identical in every thread (registers)
-		double E01[3], E10[3];
+		double E01[3], E10[3], EL01[3] = {0.001, 0.001, 0.001}, EL10[3] = {0.001, 0.001, 0.001};
 		for (int k = 0; k < 3; k++) { E01[k] = sh->E01[k]; E10[k] = sh->E10[k]; }
 		auto count_likelihood = [&]() {
 			// calculate_pooled_likelihoods_indel (crispEM.c:54-87) with the current E01/E10; the clamps and the
@@ -196,8 +196,8 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm)
 		if (countlik) {
 			count_likelihood();
 			// EMmethod starts from its own E01 = E10 = 0.001 (crispEM.c:211); the count-based values above only
-			// shape the first likelihood (crispEM.c:362-375)
-			for (int k = 0; k < 3; k++) { E01[k] = 0.001; E10[k] = 0.001; }
+			// shape the first likelihood (crispEM.c:362-375) and, later, the association statistic (:385)
+			for (int k = 0; k < 3; k++) { EL01[k] = E01[k]; EL10[k] = E10[k]; E01[k] = 0.001; E10[k] = 0.001; }
 		} else if (dense) {
 			// calculate_pooled_likelihoods_snp, dense form (few distinct qualities, one pool size).
 			// (1) per pool (one warp) bin the packed reads into dh[allele][quality][class][pool];
@@ -609,6 +609,71 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm)
 					for (int j = 0; j <= n0; j++) if (gcnt[j] >= 0.0) { stat += gcnt[j]; dof += 1; }
 					sh->hwe = (stat > 0 && dof >= 2) ? d_gammaq((dof - 1) / 2, stat / 2) / log(10.0) : 0.0;
 				}
+			}
+			// ---- calculate_LRstatistic (crisp/LRstatistic.c:48-69), --phenotypes only: five EMs restricted to pool subsets ----
+			if (c.association && pfin >= 0.0001 && delta >= 3) {
+				__syncthreads();  // HWE above still reads the posterior plane
+				for (int k = 0; k < 3; k++) { E01[k] = EL01[k]; E10[k] = EL10[k]; }
+				const int flags[5] = {7, 1, 6, 4, 5};
+				double pout[5], llout[5];
+				for (int q = 0; q < 5; q++) {
+					const int flag = flags[q];
+					int Ksub = 0;
+					for (int i = 0; i < P; i++) if (c.phenotypes[i] & flag) Ksub += c.ploidy[i];
+					double p = pfin, LLprev = 0.0, LL = 0.0;
+					for (int it2 = 1; it2 <= 1000; it2++) {
+						double* pb = part_base + (it2 & 1) * 19 * rounds;
+						const double l0 = log10(p), l1 = log10(1.0 - p), dl = l0 - l1;
+						for (int rd = warp; rd < rounds; rd += nwarps) {
+							const int i = rd * 32 + lane;
+							const bool act = i < P && (c.phenotypes[i < P ? i : 0] & flag) != 0;
+							const int ii = i < P ? i : P - 1;
+							const int n = c.ploidy[ii];
+							const double* hp0 = Gt + ii;
+							double m = -1e300, S = 0.0, Wj = 0.0;
+							{
+								const double* hp = hp0; double jd = 0.0;
+								for (int j = 0; j <= n; j++, hp += P, jd += 1.0) m = fmax(m, fma(jd, dl, *hp));
+							}
+							{
+								const double* hp = hp0; double jd = 0.0;
+								for (int j = 0; j <= n; j++, hp += P, jd += 1.0) {
+									const double d = fma(jd, dl, *hp) - m;
+									if (d > -kExpCut) { const double e = exp10_lse(d); S += e; Wj = fma(jd, e, Wj); }
+								}
+							}
+							const double L = m + (double)n * l1 + log10(S);
+							const double lls = warp_sum(act ? L : 0.0), pns = warp_sum(act ? Wj / S : 0.0);
+							if (lane == 0) { pb[rd] = lls; pb[rounds + rd] = pns; }
+						}
+						__syncthreads();
+						LL = 0.0;
+						double pn = 0.0;
+						for (int r = 0; r < rounds; r++) { LL += pb[r]; pn += pb[rounds + r]; }
+						pn /= Ksub;
+						if (countlik) count_likelihood();  // LRstatistic.c:40 (with compute_GLL_pooled's error rates)
+						if (pn < kMinP) pn = kMinP;
+						if (1.0 - pn <= kMinP) pn = 1.0 - kMinP;
+						const bool done = it2 >= 2 && (double)fabsf((float)(LL - LLprev)) <= 0.01;
+						p = pn;
+						LLprev = LL;
+						if (done) break;
+					}
+					pout[q] = p;
+					llout[q] = LL;
+					__syncthreads();  // the next subset reuses the partial-sum buffers
+				}
+				if (tid == 0) {
+					const double pctl = pout[1], pcase = pout[2], pcase1 = pout[3];
+					const double LLR = llout[2] + llout[1] - llout[0], LLR1 = llout[3] + llout[1] - llout[4];
+					prm.o.assoc_llr[o] = LLR;
+					prm.o.assoc_or[o] = pcase * (1.0 - pctl) / ((1.0 - pcase) * pctl);
+					prm.o.assoc_p[o] = d_gammaq(0.5, LLR * log(10.0)) / log(10.0);
+					prm.o.assoc_llr1[o] = LLR1;
+					prm.o.assoc_or1[o] = pcase1 * (1.0 - pctl) / ((1.0 - pcase1) * pctl);
+					prm.o.assoc_p1[o] = d_gammaq(0.5, LLR1 * log(10.0)) / log(10.0);
+				}
+				__syncthreads();
 			}
 			// ---- calculate_pool_statistics: read-evidence filter per pool ----
 			const uint32_t alo = b.alt_off ? b.alt_off[s * kSlots + slot] : 0, ahi = b.alt_off ? b.alt_off[s * kSlots + slot + 1] : 0;

@@ -277,6 +277,7 @@ __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_evaluate(Eng
 			prm.o.af_ml[o] = 0; prm.o.delta[o] = 0; prm.o.deltaf[o] = 0; prm.o.hwe[o] = 0; prm.o.qvpf[o] = 0; prm.o.qvpr[o] = 0;
 			prm.o.varpools[o] = 0; prm.o.allelecount[o] = 0; prm.o.variantpools[o] = 0;
 			prm.o.em_iters[o] = 0; prm.o.perm_k[o] = 0; prm.o.perm_hits[o] = 0;
+			prm.o.assoc_p[o] = 0; prm.o.assoc_llr[o] = 0; prm.o.assoc_or[o] = 0; prm.o.assoc_p1[o] = 0; prm.o.assoc_llr1[o] = 0; prm.o.assoc_or1[o] = 0;
 		}
 		if (lane == 0) { prm.o.varalleles[s] = 0; prm.o.strandpass[s] = 0; }
 	}

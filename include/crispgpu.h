@@ -181,6 +181,15 @@ typedef struct crispgpu_results {
 	const int32_t* em_iters;    /* EM iterations executed (diagnostic) */
 	const int32_t* perm_k;      /* permutations executed (stop index) (diagnostic) */
 	const int32_t* perm_hits;   /* hits at stop (diagnostic) */
+	/* case/control likelihood-ratio association statistic (crisp/LRstatistic.c:48-69; the reference prints these on its
+	 * `ASSOC` stdout line only).  Filled when config.association = 1 and the slot satisfies crispEM.c:383
+	 * (AF_ML >= 1e-4 and delta >= 3); 0 otherwise.  *1 = the early-onset variant (phenotype masks 4 / 5). */
+	const double* assoc_p;      /* log10 p = kf_gammaq(0.5, LLR ln 10)/ln 10 */
+	const double* assoc_llr;    /* LL(cases) + LL(controls) - LL(all) */
+	const double* assoc_or;     /* odds ratio of the two allele-frequency estimates */
+	const double* assoc_p1;
+	const double* assoc_llr1;
+	const double* assoc_or1;
 	/* per called allele — [n_calls][P] */
 	const int32_t* ac;          /* crispvar[].AC[i]  (bit-exact) */
 	const double* qv;           /* crispvar[].QV[i] */

@@ -658,6 +658,7 @@ static double o_perm_lowcov(oracle_ctx* c, int iter, int tid, int pos, int slot,
 typedef struct slot_out {
 	int status; double paf, ctpval, chi2pval; int perm_k, perm_hits;
 	double af_ml, delta, deltaf, hwe, qvpf, qvpr; int varpools, allelecount, variantpools, em_iters;
+	double assoc[6]; /* p, LLR, OR, p1, LLR1, OR1 */
 } slot_out;
 
 static int o_evaluate(oracle_ctx* c, const crispgpu_batch* b, int s, int slot, int a1, int a2, int a3, double paf[2], slot_out* o)
@@ -915,6 +916,61 @@ static double o_em(oracle_ctx* c, int a1, int a2, int ilen, int is_ins, double p
 	return p;
 }
 
+/* calculate_likelihood_EM — crisp/LRstatistic.c:6-45: the EM restricted to the pools whose phenotype matches `flag` */
+static double o_subset_em(oracle_ctx* c, int a1, int a2, int ilen, int is_ins, double p, double* dataLL, double E01[3], double E10[3], int flag)
+{
+	const int P = c->P;
+	int K = 0, iter = 0, exitloop = 0;
+	double LL = 0, LLprev = 0;
+	for (int i = 0; i < P; i++) if (c->phenotypes[i] & flag) K += c->ploidy[i];
+	while (iter++ < 1000 && exitloop == 0) {
+		double pnew = 0;
+		LL = 0;
+		const double lp0 = log10(p), lp1 = log10(1.0 - p);
+		for (int i = 0; i < P; i++) {
+			if ((c->phenotypes[i] & flag) == 0) continue;
+			const int n = c->ploidy[i];
+			double Lj = 0;
+			for (int j = 0; j <= n; j++) {
+				double t = GX(c, c->G, i, j) + c->NC[i][j] + lp0 * j + lp1 * (n - j);
+				LSE_STEP(Lj, t, j);
+			}
+			LL += Lj;
+			for (int j = 0; j <= n; j++) {
+				double t = GX(c, c->G, i, j) + c->NC[i][j] + lp0 * j + lp1 * (n - j);
+				pnew += (double)j * pow(10, t - Lj);
+			}
+		}
+		pnew /= K;
+		if (a2 >= 4 || c->cfg.use_base_qvs == 0) o_likelihood_indel(c, a1, a2, ilen, is_ins, E01, E10);
+		if (pnew < MINP) pnew = MINP;
+		if (1.0 - pnew <= MINP) pnew = 1.0 - MINP;
+		if (iter >= 2 && fabsf(LL - LLprev) <= 0.01) exitloop = 1;
+		p = pnew;
+		LLprev = LL;
+	}
+	*dataLL = LL;
+	return p;
+}
+
+/* calculate_LRstatistic — crisp/LRstatistic.c:48-69; phenotype bits: 1 control, 2 case, 4 early onset */
+static void o_lr_statistic(oracle_ctx* c, int a1, int a2, int ilen, int is_ins, double p, double E01[3], double E10[3], double out[6])
+{
+	double LLall, LLctl, LLcase, LLearly, LL1;
+	o_subset_em(c, a1, a2, ilen, is_ins, p, &LLall, E01, E10, 7);
+	double pcontrols = o_subset_em(c, a1, a2, ilen, is_ins, p, &LLctl, E01, E10, 1);
+	double pcases = o_subset_em(c, a1, a2, ilen, is_ins, p, &LLcase, E01, E10, 6);
+	double OR = pcases * (1.0 - pcontrols) / ((1.0 - pcases) * pcontrols);
+	double LLR = LLcase + LLctl - LLall;
+	double pvalue = o_gammaq(0.5, LLR * log(10)) / log(10);
+	double pcases1 = o_subset_em(c, a1, a2, ilen, is_ins, p, &LLearly, E01, E10, 4);
+	o_subset_em(c, a1, a2, ilen, is_ins, p, &LL1, E01, E10, 5);
+	double OR1 = pcases1 * (1.0 - pcontrols) / ((1.0 - pcases1) * pcontrols);
+	double LLR1 = LLearly + LLctl - LL1;
+	double pvalue1 = o_gammaq(0.5, LLR1 * log(10)) / log(10);
+	out[0] = pvalue; out[1] = LLR; out[2] = OR; out[3] = pvalue1; out[4] = LLR1; out[5] = OR1;
+}
+
 /* compute_GLL_pooled — crisp/crispEM.c:356-391 */
 static int o_compute_gll(oracle_ctx* c, const crispgpu_batch* b, int s, int a1, int a2, double paf[2], slot_out* o, int* AC, double* QV)
 {
@@ -924,15 +980,16 @@ static int o_compute_gll(oracle_ctx* c, const crispgpu_batch* b, int s, int a1, 
 	paf[1] /= K;
 	if (1.0 - paf[1] < MINP) paf[1] = 1.0 - MINP;
 	int ilen = 0, is_ins = 0;
+	double E01[3] = {0.001, 0.001, 0.001}, E10[3] = {0.001, 0.001, 0.001};
 	if (a2 >= 4 || c->cfg.use_base_qvs == 0) {
 		if (a2 >= 4 && b->indel_len) { ilen = abs(b->indel_len[s * 8 + a2]); is_ins = b->indel_len[s * 8 + a2] > 0; }
-		double E01[3], E10[3];
 		for (int k = 0; k < 3; k++) E01[k] = (double)(c->counts[a2 + k * NA] + 1.0) / (c->counts[a1 + k * NA] + c->counts[a2 + k * NA] + 1.0);
 		if (E01[0] >= 0.005 || E01[1] >= 0.005) E01[0] = E01[1] = E01[2] = 0.005;
 		for (int k = 0; k < 3; k++) E10[k] = E01[k];
 		o_likelihood_indel(c, a1, a2, ilen, is_ins, E01, E10);
 	} else o_likelihood_snp(c, b, s, a1, a2);
 	double pem = o_em(c, a1, a2, ilen, is_ins, paf[0], o, AC, QV);
+	if (c->cfg.association == 1 && pem >= 0.0001 && o->delta >= 3) o_lr_statistic(c, a1, a2, ilen, is_ins, pem, E01, E10, o->assoc);  /* crispEM.c:383 */
 	paf[0] = pem;
 	return o->delta >= 2 ? 1 : 0;
 }
@@ -1165,6 +1222,7 @@ int crisp_oracle_run(void* h, const crispgpu_batch* b, crisp_host_results* out, 
 			if (out->em_iters) out->em_iters[oix] = o.em_iters;
 			if (out->perm_k) out->perm_k[oix] = o.perm_k;
 			if (out->perm_hits) out->perm_hits[oix] = o.perm_hits;
+			if (out->assoc_p) { out->assoc_p[oix] = o.assoc[0]; out->assoc_llr[oix] = o.assoc[1]; out->assoc_or[oix] = o.assoc[2]; out->assoc_p1[oix] = o.assoc[3]; out->assoc_llr1[oix] = o.assoc[4]; out->assoc_or1[oix] = o.assoc[5]; }
 			if (called) {
 				varalleles++;
 				if (c->cfg.em_flag >= 1 && out->n_calls < out->max_calls) {

@@ -38,6 +38,12 @@ typedef struct crisp_host_results {
 	int32_t* em_iters;
 	int32_t* perm_k;
 	int32_t* perm_hits;
+	double* assoc_p;
+	double* assoc_llr;
+	double* assoc_or;
+	double* assoc_p1;
+	double* assoc_llr1;
+	double* assoc_or1;
 	int32_t* ac;          /* [max_calls][P] */
 	double* qv;           /* [max_calls][P] */
 	/* optional per-(site,slot) dumps for kernel-level parity (may be NULL):

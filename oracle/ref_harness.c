@@ -395,13 +395,19 @@ static int build_reads(ref_ctx* c, const crispgpu_batch* b, int s)
 }
 
 static int stdout_saved = -1;
+static FILE* stdout_capture = NULL;
+/* the engine logs to stdout (and the association statistic exists nowhere else: LRstatistic.c:62-64): capture it */
 static void mute_stdout(void)
 {
 	fflush(stdout);
 	stdout_saved = dup(1);
-	int nul = open("/dev/null", O_WRONLY);
-	dup2(nul, 1);
-	close(nul);
+	stdout_capture = tmpfile();
+	if (stdout_capture) dup2(fileno(stdout_capture), 1);
+	else {
+		int nul = open("/dev/null", O_WRONLY);
+		dup2(nul, 1);
+		close(nul);
+	}
 }
 static void unmute_stdout(void)
 {
@@ -424,6 +430,34 @@ static void dump_genll(ref_ctx* c, crisp_host_results* out, int s, int k)
 			double* dst = out->genll + ((((size_t)s * 5 + k) * 4 + t) * P + i) * st;
 			for (int j = 0; j <= c->ploidy[i] && j < st; j++) dst[j] = src[t][i][j];
 		}
+}
+
+/* Parse the captured `ASSOC` lines (one per slot that met crispEM.c:383, in call order) into the result arrays.
+ * Printed precision only: %0.2f / %0.3f. */
+static void collect_assoc(crisp_host_results* out, const int* slots, int nslots)
+{
+	if (!stdout_capture) return;
+	char* line = NULL;
+	size_t cap = 0;
+	int k = 0;
+	rewind(stdout_capture);
+	while (getline(&line, &cap, stdout_capture) > 0) {
+		char* a = strstr(line, "ASSOC ");
+		if (!a) continue;
+		char* bar = strchr(a, '|');
+		if (!bar || k >= nslots) continue;
+		double pc, pctl, pca, pca1, l0, l1, l2, llr, orr, pv, m0, m1, m2, llr1, or1, pv1;
+		int got = sscanf(bar + 1, " %lf %lf %lf %lf LL %lf %lf %lf LLR %lf:%lf:%lf LL %lf %lf %lf LLR %lf:%lf:%lf", &pc, &pctl, &pca, &pca1, &l0, &l1, &l2, &llr, &orr, &pv, &m0, &m1, &m2, &llr1, &or1, &pv1);
+		if (got == 16 && out->assoc_p) {
+			int o = slots[k];
+			out->assoc_p[o] = pv; out->assoc_llr[o] = llr; out->assoc_or[o] = orr;
+			out->assoc_p1[o] = pv1; out->assoc_llr1[o] = llr1; out->assoc_or1[o] = or1;
+		}
+		k++;
+	}
+	free(line);
+	fclose(stdout_capture);
+	stdout_capture = NULL;
 }
 
 const char* crisp_ref_last_error(void* h) { return ((ref_ctx*)h)->err; }
@@ -451,6 +485,8 @@ int crisp_ref_run(void* h, const crispgpu_batch* b, crisp_host_results* out, int
 	int rc = 0;
 	out->n_sites = n;
 	out->n_calls = 0;
+	int* assoc_slots = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1) * 5);
+	int n_assoc = 0;
 	mute_stdout();
 	for (int s = 0; s < n && rc == 0; s++) {
 		fill_site(c, b, s);
@@ -467,6 +503,7 @@ int crisp_ref_run(void* h, const crispgpu_batch* b, crisp_host_results* out, int
 			out->call_row[o] = -1;
 			out->paf[o] = out->ctpval[o] = out->chi2pval[o] = out->af_ml[o] = out->delta[o] = out->deltaf[o] = out->hwe[o] = 0;
 			out->qvpf[o] = out->qvpr[o] = 0;
+			if (out->assoc_p) out->assoc_p[o] = out->assoc_llr[o] = out->assoc_or[o] = out->assoc_p1[o] = out->assoc_llr1[o] = out->assoc_or1[o] = 0;
 			out->varpools[o] = out->allelecount[o] = out->variantpools[o] = 0;
 			if (out->em_iters) out->em_iters[o] = 0;
 			if (out->perm_k) out->perm_k[o] = 0;
@@ -550,6 +587,7 @@ int crisp_ref_run(void* h, const crispgpu_batch* b, crisp_host_results* out, int
 					out->delta[o] = v->crispvar[slotrank].delta;
 					out->deltaf[o] = v->crispvar[slotrank].deltaf;
 					out->hwe[o] = v->crispvar[slotrank].deltar;
+					if (c->options.association == 1 && paf[0] >= 0.0001 && v->crispvar[slotrank].delta >= 3) assoc_slots[n_assoc++] = o;  /* crispEM.c:383 */
 					if (is_variant == 1) {
 						int variantpools = calculate_pool_statistics(&c->rq, c->bd, v, allele1, allele2);
 						v->varpools[v->varalleles] = variantpools;
@@ -618,6 +656,8 @@ int crisp_ref_run(void* h, const crispgpu_batch* b, crisp_host_results* out, int
 		}
 	}
 	unmute_stdout();
+	collect_assoc(out, assoc_slots, mode == CRISP_REF_MODE_SLOTS ? n_assoc : 0);
+	free(assoc_slots);
 	fclose(vf);
 	fclose(tf);
 	free(tmem);

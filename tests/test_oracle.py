@@ -142,3 +142,26 @@ def test_philox_sampler_matches_drand48_distribution():
     sigma = np.sqrt(2 * p * (1 - p) / k) + 2.0 / k
     assert np.all(np.abs(pa - pb) <= 6 * sigma)
     assert abs(pa.mean() - pb.mean()) < 0.02
+
+
+@needs_ref
+@pytest.mark.parametrize("kw", [dict(variant_frac=0.6), dict(variant_frac=0.3, indel_frac=0.6)], ids=["snp", "indel"])
+def test_association_statistic_matches_reference_log_line(kw):
+    """calculate_LRstatistic (crisp/LRstatistic.c:48-69) writes only an `ASSOC` line to stdout; the harness parses it.
+    The oracle must agree to the printed precision (%0.2f for p and LLR, %0.3f for the odds ratio)."""
+    P = 12
+    ph = np.array([1, 1, 1, 1, 2, 2, 2, 2, 6, 6, 1, 2], np.int32)
+    cfg = EngineConfig(ploidy=np.full(P, 20), options=dict(association=1), phenotypes=ph)
+    batch = synth_batch(150, P, 20, 100, seed=3, **kw)
+    want = RefEngine(cfg).run(batch)
+    got = OracleEngine(cfg).run(batch, mode=RNG_DRAND48)
+    m = want.assoc_llr != 0
+    assert m.sum() > 40
+    for f, tol in (("assoc_p", 0.00501), ("assoc_llr", 0.00501), ("assoc_or", 0.000501), ("assoc_p1", 0.00501), ("assoc_llr1", 0.00501), ("assoc_or1", 0.000501)):
+        a, b = getattr(want, f)[m], getattr(got, f)[m]
+        fin = np.isfinite(a) & np.isfinite(b)
+        assert np.array_equal(np.isnan(a), np.isnan(b)), f
+        big = np.abs(a) > 1e4  # %0.3f of a huge odds ratio carries fewer significant digits than a double compare needs
+        assert np.all(np.abs(a - b)[fin & ~big] <= tol), f
+    # everything else is unaffected by the association pass
+    compare_results(got, want, tol=0.0, label="assoc", fp_skip=("assoc_p", "assoc_llr", "assoc_or", "assoc_p1", "assoc_llr1", "assoc_or1"))
