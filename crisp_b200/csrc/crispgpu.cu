@@ -59,6 +59,7 @@ struct crispgpu_ctx {
 	DevOut dout{};
 	// queues
 	DevBuf d_perm_tasks, d_call_tasks, d_counters, h_counters, d_gws;
+	DevBuf d_tail_task, d_tail_head, d_tail_total, d_tail_rec, d_tail_counters;  // long permutation tasks (k_permute_stranded_tail)
 	size_t gws_stride = 0;
 	// launch geometry
 	int ev_warps = 8, ev_grid = 0;
@@ -373,8 +374,45 @@ int run_stage1(crispgpu_ctx* ctx)
 			return CRISPGPU_ERR_UNSUPPORTED;
 		}
 		if (ctx->ploidy[0] > 2) {
-			if (!ctx->pm_grid) { rc = occupancy_grid(ctx, k_permute_stranded, ctx->pm_threads, ctx->pm_smem, &ctx->pm_grid); if (rc) return rc; }
-			k_permute_stranded<<<ctx->pm_grid, ctx->pm_threads, ctx->pm_smem, ctx->stream>>>(prm, ctx->pm_l10cap);
+			if (!ctx->pm_grid) {
+				rc = occupancy_grid(ctx, k_permute_stranded, ctx->pm_threads, ctx->pm_smem, &ctx->pm_grid); if (rc) return rc;
+				int g2 = 0;
+				rc = occupancy_grid(ctx, k_permute_stranded_tail, ctx->pm_threads, ctx->pm_smem, &g2); if (rc) return rc;
+				if (g2 < ctx->pm_grid) ctx->pm_grid = g2;
+			}
+			// head: first 1024 permutations of every task; tasks still undecided go to the chunked tail
+			PermTail tail{};
+			rc = ensure_dev(ctx, ctx->d_tail_task, (size_t)n * 5 * 4); if (rc) return rc;
+			rc = ensure_dev(ctx, ctx->d_tail_head, (size_t)n * 5 * 4); if (rc) return rc;
+			rc = ensure_dev(ctx, ctx->d_tail_total, (size_t)n * 5 * 4); if (rc) return rc;
+			rc = ensure_dev(ctx, ctx->d_tail_counters, 4 * 4); if (rc) return rc;
+			CK(cudaMemsetAsync(ctx->d_tail_counters.p, 0, 4 * 4, ctx->stream));
+			tail.task = static_cast<int32_t*>(ctx->d_tail_task.p);
+			tail.hits_head = static_cast<int32_t*>(ctx->d_tail_head.p);
+			tail.total = static_cast<int32_t*>(ctx->d_tail_total.p);
+			tail.counters = static_cast<int32_t*>(ctx->d_tail_counters.p);
+			k_permute_stranded<<<ctx->pm_grid, ctx->pm_threads, ctx->pm_smem, ctx->stream>>>(prm, ctx->pm_l10cap, tail);
+			CK(cudaGetLastError());
+			if (g.max_iter > kPermHead) {
+				// the number of tail tasks sizes the chunk records (the one extra host wait of the permutation mode)
+				int32_t* hc2 = static_cast<int32_t*>(ctx->h_counters.p) + 8;
+				CK(cudaMemcpyAsync(hc2, ctx->d_tail_counters.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+				CK(cudaStreamSynchronize(ctx->stream));
+				const int n_tail = hc2[0];
+				if (n_tail > 0) {
+					const int T = ctx->pm_threads, rem = g.max_iter - kPermHead;
+					int chunk = ((rem + 255) / 256 + T - 1) / T * T;
+					if (chunk < 4 * T) chunk = 4 * T;
+					tail.chunk = chunk;
+					tail.nchunks = (rem + chunk - 1) / chunk;
+					rc = ensure_dev(ctx, ctx->d_tail_rec, (size_t)n_tail * tail.nchunks * kPermRec * 4); if (rc) return rc;
+					tail.rec = static_cast<int32_t*>(ctx->d_tail_rec.p);
+					k_permute_stranded_tail<<<ctx->pm_grid, ctx->pm_threads, ctx->pm_smem, ctx->stream>>>(prm, ctx->pm_l10cap, tail);
+					CK(cudaGetLastError());
+					k_permute_stranded_resolve<<<(n_tail + 127) / 128, 128, 0, ctx->stream>>>(prm, tail);
+					launches += 2;
+				}
+			}
 		} else {
 			if (!ctx->pm_grid) { rc = occupancy_grid(ctx, k_permute_lowcov, ctx->pm_threads, ctx->pm_smem, &ctx->pm_grid); if (rc) return rc; }
 			k_permute_lowcov<<<ctx->pm_grid, ctx->pm_threads, ctx->pm_smem, ctx->stream>>>(prm);
@@ -691,6 +729,7 @@ void crispgpu_destroy(crispgpu_ctx* ctx)
 	for (auto& b : ctx->d_o) fd(b);
 	for (auto& b : ctx->h_o) fh(b);
 	fd(ctx->d_ac); fd(ctx->d_qv); fh(ctx->h_ac); fh(ctx->h_qv);
+	fd(ctx->d_tail_task); fd(ctx->d_tail_head); fd(ctx->d_tail_total); fd(ctx->d_tail_rec); fd(ctx->d_tail_counters);
 	fd(ctx->d_perm_tasks); fd(ctx->d_call_tasks); fd(ctx->d_counters); fh(ctx->h_counters); fd(ctx->d_gws);
 	for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
 	if (ctx->ev_counts) cudaEventDestroy(ctx->ev_counts);

@@ -50,35 +50,165 @@ __device__ __forceinline__ int block_prefix(int flag, int* warp_tot, int& total)
 template <typename Occ, typename Bump>
 __device__ __forceinline__ void place_balls(Philox& rng, const uint32_t* cum, int P, uint32_t M, int ones, Occ occ, Bump bump)
 {
+	// pool of slot u = largest i with cum[i] <= u.  Pools of one experiment hold similar numbers of reads, so the
+	// proportional guess u*P/M is usually right or off by one; a short walk fixes it (exact for any marginals).
+	const float scale = M ? (float)P / (float)M : 0.f;
 	for (int d = 0; d < ones; d++) {
 		for (;;) {
 			const uint32_t u = rng.below(M);
-			int lo = 0, hi = P;
-			while (hi - lo > 1) {
-				const int mid = (lo + hi) >> 1;
-				if (cum[mid] <= u) lo = mid; else hi = mid;
-			}
+			int lo = min(P - 1, (int)((float)u * scale));
+			while (cum[lo] > u) lo--;
+			while (cum[lo + 1] <= u) lo++;
 			if (u - cum[lo] >= (uint32_t)occ(lo)) { bump(lo); break; }
 		}
 	}
 }
 
-__global__ void k_permute_stranded(EngineParams prm, int l10cap)
+// ---- stranded test: shared-memory view of one task -----------------------------------------------------------
+struct StrandedView {
+	PermShared* sh;
+	uint32_t* cumf;
+	uint32_t* cumr;
+	int32_t* Ntot;
+	int32_t* alt;
+	double* L10;
+	uint32_t* occ;  // [P][T]: low 16 bits forward balls, high 16 reverse balls
+	int l10cap;
+};
+
+__device__ __forceinline__ StrandedView stranded_view(unsigned char* smem_raw, int P, int l10cap)
+{
+	StrandedView v;
+	v.sh = reinterpret_cast<PermShared*>(smem_raw);
+	size_t off = (sizeof(PermShared) + 15) & ~size_t(15);
+	v.cumf = reinterpret_cast<uint32_t*>(smem_raw + off); off += sizeof(uint32_t) * (P + 1);
+	v.cumr = reinterpret_cast<uint32_t*>(smem_raw + off); off += sizeof(uint32_t) * (P + 1);
+	v.Ntot = reinterpret_cast<int32_t*>(smem_raw + off); off += sizeof(int32_t) * P;
+	v.alt = reinterpret_cast<int32_t*>(smem_raw + off); off += sizeof(int32_t) * 2 * P;
+	off = (off + 15) & ~size_t(15);
+	v.L10 = reinterpret_cast<double*>(smem_raw + off); off += sizeof(double) * l10cap;
+	v.occ = reinterpret_cast<uint32_t*>(smem_raw + off);
+	v.l10cap = l10cap;
+	return v;
+}
+
+// Block-wide: marginals (ctable_stranded columns 0..3, allelecounts.c:221-227), cumulative slot counts, the observed
+// statistic clra = sum_i log10 C(Nf+Nr, af+ar) (contables.c:296-298) and the log10 table.  Ends with a barrier.
+__device__ inline void stranded_setup(const EngineParams& prm, const StrandedView& v, int o)
+{
+	const DevBatch& b = prm.b;
+	const int P = prm.c.P, T = blockDim.x, tid = threadIdx.x;
+	const int s = o / kSlots, slot = o - s * kSlots;
+	int a1, a2, a3;
+	slot_alleles(b.maxvec_al + s * 8, slot, a1, a2, a3);
+	const int refbase = b.refbase[s];
+	const int row = slot_amb_row(b, s, slot, a2, a3);
+	const int altal = (a1 == refbase || a2 != refbase) ? a2 : a1;
+	for (int i = tid; i < P; i += T) {
+		const int32_t* r = b.indcounts + ((size_t)s * P + i) * kNC;
+		int dd[2] = {0, 0};
+		if (row >= 0) { const int32_t* d = b.amb_dec + ((size_t)row * P + i) * 4; dd[0] = d[0]; dd[1] = d[1]; }
+		const int nref = (a1 == refbase) + (a2 == refbase) + (a3 == refbase);
+		const int nf = r[a1] + r[a2] + r[a3] - nref * dd[0], nr = r[a1 + 8] + r[a2 + 8] + r[a3 + 8] - nref * dd[1];
+		v.cumf[i + 1] = nf;
+		v.cumr[i + 1] = nr;
+		v.Ntot[i] = nf + nr;
+		v.alt[i] = r[altal] - (altal == refbase ? dd[0] : 0);
+		v.alt[P + i] = r[altal + 8] - (altal == refbase ? dd[1] : 0);
+	}
+	__syncthreads();
+	double* terms = v.L10;  // borrowed before the log table is built
+	for (int i = tid; i < P; i += T) terms[i] = d_ncr(v.Ntot[i], v.alt[i] + v.alt[P + i]);
+	__syncthreads();
+	if (tid == 0) {
+		uint32_t cf = 0, cr = 0;
+		int of = 0, orr = 0, mx = 0;
+		double clra = 0.0;
+		v.cumf[0] = v.cumr[0] = 0;
+		for (int i = 0; i < P; i++) {
+			cf += v.cumf[i + 1]; v.cumf[i + 1] = cf;
+			cr += v.cumr[i + 1]; v.cumr[i + 1] = cr;
+			of += v.alt[i]; orr += v.alt[P + i];
+			if (v.Ntot[i] > mx) mx = v.Ntot[i];
+			clra += terms[i];  // pool order, as the reference
+		}
+		v.sh->tot[0] = (int)cf; v.sh->tot[1] = (int)cr;
+		v.sh->ones[0] = of; v.sh->ones[1] = orr;
+		v.sh->maxN = mx;
+		v.sh->clra = clra;
+	}
+	__syncthreads();
+	const int maxN = v.sh->maxN;
+	if (maxN + 2 <= v.l10cap) for (int x = tid; x <= maxN + 1; x += T) v.L10[x] = x > 0 ? log10((double)x) : 0.0;
+	__syncthreads();
+}
+
+// One permutation (thread-local): place the forward and reverse balls, accumulate the statistic incrementally
+// (contables.c:312-323) and compare with the observed one.
+__device__ __forceinline__ int stranded_hit(const EngineParams& prm, const StrandedView& v, int s, int slot, uint32_t k)
+{
+	const int P = prm.c.P, T = blockDim.x;
+	uint32_t* myocc = v.occ + threadIdx.x;
+	const bool l10_smem = v.sh->maxN + 2 <= v.l10cap;
+	const double* L10 = v.L10;
+	const int32_t* Ntot = v.Ntot;
+	for (int i = 0; i < P; i++) myocc[(size_t)i * T] = 0;
+	double stat = 0.0;
+	Philox rng;
+	rng.init(prm.c.rng_seed, prm.b.tid[s], prm.b.pos[s], slot, k, 0);
+	place_balls(rng, v.cumf, P, (uint32_t)v.sh->tot[0], v.sh->ones[0],
+		[&](int i) { return myocc[(size_t)i * T] & 0xffffu; },
+		[&](int i) {
+			const uint32_t w = myocc[(size_t)i * T];
+			const int cb = (int)(w & 0xffffu) + (int)(w >> 16);
+			const int N = Ntot[i];
+			stat += l10_smem ? L10[N - cb] - L10[cb + 1] : log10((double)(N - cb)) - log10((double)(cb + 1));
+			myocc[(size_t)i * T] = w + 1u;
+		});
+	rng.init(prm.c.rng_seed, prm.b.tid[s], prm.b.pos[s], slot, k, 1);
+	place_balls(rng, v.cumr, P, (uint32_t)v.sh->tot[1], v.sh->ones[1],
+		[&](int i) { return myocc[(size_t)i * T] >> 16; },
+		[&](int i) {
+			const uint32_t w = myocc[(size_t)i * T];
+			const int cb = (int)(w & 0xffffu) + (int)(w >> 16);
+			const int N = Ntot[i];
+			stat += l10_smem ? L10[N - cb] - L10[cb + 1] : log10((double)(N - cb)) - log10((double)(cb + 1));
+			myocc[(size_t)i * T] = w + 0x10000u;
+		});
+	return stat <= v.sh->clra + kCtEps ? 1 : 0;
+}
+
+__device__ __forceinline__ void stranded_store(const EngineParams& prm, int o, int kk, int hh)
+{
+	prm.o.ctpval[o] = log10((double)(hh + 1)) - log10((double)(kk + 1));  // contables.c:336
+	prm.o.perm_k[o] = kk;
+	prm.o.perm_hits[o] = hh;
+}
+
+constexpr int kPermHead = 1024;   // permutations run by the head kernel (covers the k <= 1000 clause of the stop rule)
+constexpr int kPermRec = 12;      // ints per chunk record: [0] hits in the chunk, [1] skipped flag, [2..11] first ten hit indices
+
+// long-running tasks handed from the head kernel to the chunked tail kernel
+struct PermTail {
+	int32_t* task;       // [n] site*5+slot
+	int32_t* hits_head;  // [n] hits after the head permutations
+	int32_t* total;      // [n] hits found so far (head + finished chunks), drives the skip of later chunks
+	int32_t* rec;        // [n][nchunks][kPermRec]
+	int32_t* counters;   // [0] number of tail tasks, [1] work-item head
+	int chunk;           // permutations per chunk (multiple of the block size)
+	int nchunks;
+};
+
+// Head: one CTA per task, the first kPermHead permutations with the reference's sequential stop rule
+// (contables.c:327-328) evaluated on prefix sums in permutation order.  Tasks that neither stopped nor exhausted
+// their permutations go to the tail queue.
+__global__ void k_permute_stranded(EngineParams prm, int l10cap, PermTail tail)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const DevBatch& b = prm.b;
 	const DevCfg& c = prm.c;
-	const int P = c.P, T = blockDim.x, tid = threadIdx.x;
-	PermShared* sh = reinterpret_cast<PermShared*>(smem_raw);
-	size_t off = (sizeof(PermShared) + 15) & ~size_t(15);
-	uint32_t* cumf = reinterpret_cast<uint32_t*>(smem_raw + off); off += sizeof(uint32_t) * (P + 1);
-	uint32_t* cumr = reinterpret_cast<uint32_t*>(smem_raw + off); off += sizeof(uint32_t) * (P + 1);
-	int32_t* Ntot = reinterpret_cast<int32_t*>(smem_raw + off); off += sizeof(int32_t) * P;
-	int32_t* alt = reinterpret_cast<int32_t*>(smem_raw + off); off += sizeof(int32_t) * 2 * P;
-	off = (off + 15) & ~size_t(15);
-	double* L10 = reinterpret_cast<double*>(smem_raw + off); off += sizeof(double) * l10cap;
-	uint32_t* occ = reinterpret_cast<uint32_t*>(smem_raw + off);  // [P][T]: low 16 bits forward balls, high 16 reverse balls
-
+	const int T = blockDim.x, tid = threadIdx.x;
+	const StrandedView v = stranded_view(smem_raw, c.P, l10cap);
+	PermShared* sh = v.sh;
 	for (;;) {
 		__syncthreads();
 		if (tid == 0) sh->task = atomicAdd(prm.q.counters + 2, 1);
@@ -86,98 +216,16 @@ __global__ void k_permute_stranded(EngineParams prm, int l10cap)
 		const int task = sh->task;
 		if (task >= prm.q.counters[0]) break;
 		const int o = prm.q.perm_tasks[task], s = o / kSlots, slot = o - s * kSlots;
-		int a1, a2, a3;
-		slot_alleles(b.maxvec_al + s * 8, slot, a1, a2, a3);
-		const int refbase = b.refbase[s];
-		const int row = slot_amb_row(b, s, slot, a2, a3);
-		const int altal = (a1 == refbase || a2 != refbase) ? a2 : a1;
-		// ---- marginals: ctable_stranded columns 0..3 (allelecounts.c:221-227) ----
-		for (int i = tid; i < P; i += T) {
-			const int32_t* r = b.indcounts + ((size_t)s * P + i) * kNC;
-			int dd[2] = {0, 0};
-			if (row >= 0) { const int32_t* d = b.amb_dec + ((size_t)row * P + i) * 4; dd[0] = d[0]; dd[1] = d[1]; }
-			const int nref = (a1 == refbase) + (a2 == refbase) + (a3 == refbase);
-			const int nf = r[a1] + r[a2] + r[a3] - nref * dd[0], nr = r[a1 + 8] + r[a2 + 8] + r[a3 + 8] - nref * dd[1];
-			cumf[i + 1] = nf;
-			cumr[i + 1] = nr;
-			Ntot[i] = nf + nr;
-			alt[i] = r[altal] - (altal == refbase ? dd[0] : 0);
-			alt[P + i] = r[altal + 8] - (altal == refbase ? dd[1] : 0);
-		}
-		__syncthreads();
-		if (tid == 0) {
-			// serial prefix sums and the observed statistic clra = sum_i log10 C(Nf+Nr, af+ar)  (contables.c:296-298)
-			uint32_t cf = 0, cr = 0;
-			int of = 0, orr = 0, mx = 0;
-			double clra = 0.0;
-			cumf[0] = cumr[0] = 0;
-			for (int i = 0; i < P; i++) {
-				cf += cumf[i + 1]; cumf[i + 1] = cf;
-				cr += cumr[i + 1]; cumr[i + 1] = cr;
-				of += alt[i]; orr += alt[P + i];
-				if (Ntot[i] > mx) mx = Ntot[i];
-			}
-			sh->tot[0] = (int)cf; sh->tot[1] = (int)cr;
-			sh->ones[0] = of; sh->ones[1] = orr;
-			sh->maxN = mx;
-			sh->hits_before = 0;
-			sh->stop_k = 0;
-			sh->stop_hits = 0;
-			sh->clra = clra;
-		}
-		__syncthreads();
-		{
-			// clra summed in pool order by one thread after a parallel evaluation of the terms
-			double* terms = L10;  // borrowed before the log table is built
-			for (int i = tid; i < P; i += T) terms[i] = d_ncr(Ntot[i], alt[i] + alt[P + i]);
-			__syncthreads();
-			if (tid == 0) { double v = 0.0; for (int i = 0; i < P; i++) v += terms[i]; sh->clra = v; }
-			__syncthreads();
-		}
-		const int maxN = sh->maxN;
-		const bool l10_smem = maxN + 2 <= l10cap;
-		if (l10_smem) for (int x = tid; x <= maxN + 1; x += T) L10[x] = x > 0 ? log10((double)x) : 0.0;
-		__syncthreads();
-		const int onesf = sh->ones[0], onesr = sh->ones[1];
-		const uint32_t Mf = (uint32_t)sh->tot[0], Mr = (uint32_t)sh->tot[1];
-		const double thresh = sh->clra + kCtEps;
+		stranded_setup(prm, v, o);
 		const int maxiter = c.max_iter;
-		uint32_t* myocc = occ + tid;
-
+		const int head = maxiter < kPermHead ? maxiter : kPermHead;
 		int stop_k = 0, stop_hits = 0, hits_before = 0;
-		for (int base = 0; base < maxiter; base += T) {
+		for (int base = 0; base < head; base += T) {
 			const int k = base + tid + 1;
-			int hit = 0;
-			if (k <= maxiter) {
-				for (int i = 0; i < P; i++) myocc[(size_t)i * T] = 0;
-				double stat = 0.0;
-				Philox rng;
-				rng.init(c.rng_seed, b.tid[s], b.pos[s], slot, (uint32_t)k, 0);
-				place_balls(rng, cumf, P, Mf, onesf,
-					[&](int i) { return myocc[(size_t)i * T] & 0xffffu; },
-					[&](int i) {
-						const uint32_t v = myocc[(size_t)i * T];
-						const int cb = (int)(v & 0xffffu) + (int)(v >> 16);
-						const int N = Ntot[i];
-						stat += l10_smem ? L10[N - cb] - L10[cb + 1] : log10((double)(N - cb)) - log10((double)(cb + 1));
-						myocc[(size_t)i * T] = v + 1u;
-					});
-				rng.init(c.rng_seed, b.tid[s], b.pos[s], slot, (uint32_t)k, 1);
-				place_balls(rng, cumr, P, Mr, onesr,
-					[&](int i) { return myocc[(size_t)i * T] >> 16; },
-					[&](int i) {
-						const uint32_t v = myocc[(size_t)i * T];
-						const int cb = (int)(v & 0xffffu) + (int)(v >> 16);
-						const int N = Ntot[i];
-						stat += l10_smem ? L10[N - cb] - L10[cb + 1] : log10((double)(N - cb)) - log10((double)(cb + 1));
-						myocc[(size_t)i * T] = v + 0x10000u;
-					});
-				hit = stat <= thresh ? 1 : 0;
-			}
+			const int hit = k <= head ? stranded_hit(prm, v, s, slot, (uint32_t)k) : 0;
 			int total;
 			const int H = hits_before + block_prefix(hit, sh->warp_hits, total);
-			// first permutation (in order) at which the reference loop would break (contables.c:327-328)
-			const bool stop = k <= maxiter && (H >= 10 || (k <= 1000 && H >= 5));
+			const bool stop = k <= head && (H >= 10 || (k <= 1000 && H >= 5));
 			const unsigned sb = __ballot_sync(0xffffffffu, stop);
 			if ((tid & 31) == 0) sh->warp_first[tid >> 5] = sb ? (__ffs(sb) - 1) : -1;
 			__syncthreads();
@@ -194,12 +242,82 @@ __global__ void k_permute_stranded(EngineParams prm, int l10cap)
 			__syncthreads();
 		}
 		if (tid == 0) {
-			int kk = stop_k, hh = stop_hits;
-			if (kk == 0) { kk = maxiter + 1; hh = hits_before; }  // loop ran out: k = maxiter+1 (contables.c:308,336)
-			prm.o.ctpval[o] = log10((double)(hh + 1)) - log10((double)(kk + 1));
-			prm.o.perm_k[o] = kk;
-			prm.o.perm_hits[o] = hh;
+			if (stop_k > 0) stranded_store(prm, o, stop_k, stop_hits);
+			else if (maxiter <= head) stranded_store(prm, o, maxiter + 1, hits_before);  // loop ran out: k = maxiter+1
+			else {
+				const int h = atomicAdd(tail.counters + 0, 1);
+				tail.task[h] = o;
+				tail.hits_head[h] = hits_before;
+				tail.total[h] = hits_before;
+			}
 		}
+	}
+}
+
+// Tail: work items = (chunk, task), chunk-major so that every earlier chunk of a task has started before a later one.
+// A chunk records its hit count and the indices of its first ten hits; it is skipped when ten hits are already known
+// (they all lie in earlier chunks, so the reference's loop would have broken before this chunk).
+__global__ void k_permute_stranded_tail(EngineParams prm, int l10cap, PermTail tail)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const DevCfg& c = prm.c;
+	const int T = blockDim.x, tid = threadIdx.x;
+	const StrandedView v = stranded_view(smem_raw, c.P, l10cap);
+	PermShared* sh = v.sh;
+	const int ntask = tail.counters[0];
+	const long long nitems = (long long)ntask * tail.nchunks;
+	__shared__ int firsts[10];
+	for (;;) {
+		__syncthreads();
+		if (tid == 0) sh->task = atomicAdd(tail.counters + 1, 1);
+		__syncthreads();
+		const int item = sh->task;
+		if (item >= nitems) break;
+		const int chunk = item / ntask, h = item - chunk * ntask;
+		int32_t* rec = tail.rec + ((size_t)h * tail.nchunks + chunk) * kPermRec;
+		const int kbeg = kPermHead + chunk * tail.chunk, kend = min(c.max_iter, kbeg + tail.chunk);  // permutations (kbeg, kend]
+		if (kbeg >= c.max_iter || *((volatile int32_t*)(tail.total + h)) >= 10) {
+			if (tid == 0) { rec[0] = 0; rec[1] = 1; }
+			continue;
+		}
+		const int o = tail.task[h], s = o / kSlots, slot = o - s * kSlots;
+		stranded_setup(prm, v, o);
+		int found = 0;
+		for (int base = kbeg; base < kend; base += T) {
+			const int k = base + tid + 1;
+			const int hit = k <= kend ? stranded_hit(prm, v, s, slot, (uint32_t)k) : 0;
+			int total;
+			const int idx = found + block_prefix(hit, sh->warp_hits, total);  // 1-based rank of this hit within the chunk
+			if (hit && idx <= 10) firsts[idx - 1] = k;
+			found += total;
+			__syncthreads();
+		}
+		if (tid == 0) {
+			rec[0] = found;
+			rec[1] = 0;
+			for (int q = 0; q < 10 && q < found; q++) rec[2 + q] = firsts[q];
+			atomicAdd(tail.total + h, found);
+		}
+	}
+}
+
+// Resolve: walk each tail task's chunk records in permutation order to the tenth hit (the break of contables.c:327).
+__global__ void k_permute_stranded_resolve(EngineParams prm, PermTail tail)
+{
+	const int ntask = tail.counters[0];
+	for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < ntask; h += gridDim.x * blockDim.x) {
+		int cum = tail.hits_head[h], stop_k = 0;
+		for (int ch = 0; ch < tail.nchunks && stop_k == 0; ch++) {
+			const int32_t* rec = tail.rec + ((size_t)h * tail.nchunks + ch) * kPermRec;
+			if (rec[1]) break;  // skipped: ten hits were already known
+			const int cnt = rec[0];
+			for (int q = 0; q < cnt && q < 10; q++) {
+				if (++cum >= 10) { stop_k = rec[2 + q]; break; }
+			}
+			if (stop_k == 0 && cnt > 10) cum += cnt - 10;  // cannot happen (ten recorded hits already stop the walk)
+		}
+		if (stop_k > 0) stranded_store(prm, tail.task[h], stop_k, 10);
+		else stranded_store(prm, tail.task[h], prm.c.max_iter + 1, cum);
 	}
 }
 
