@@ -1,0 +1,220 @@
+/*
+ * crisp_shim.c — see crisp_shim.h.  Walks the reference's read lists the way the engine's three read-queue consumers
+ * do (crisp/crispEM.c:104-136, parsebam/allelecounts.c:50-67, parsebam/process_indel_variant.c:25-62) and snapshots
+ * what they would have read into the flat batch.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <ctype.h>
+
+#include "bamread.h"
+#include "bamsreader.h"
+#include "variant.h"
+#define CRISP_SHIM_WITH_REFERENCE_TYPES
+#include "crisp_shim.h"
+
+extern int maxalleles, MINQ, QVoffset, USE_QV;
+extern unsigned int BTI[];
+int calculate_indel_ambiguity(struct VARIANT* variant, REFLIST* reflist, int current, int allele);
+
+#define GROW(ptr, cap, need, type)                                    \
+	do {                                                              \
+		if ((size_t)(need) > (size_t)(cap)) {                         \
+			(cap) = (size_t)(need) * 2 + 64;                          \
+			(ptr) = (type*)realloc((ptr), (size_t)(cap) * sizeof(type)); \
+		}                                                             \
+	} while (0)
+
+crisp_shim_batch* crisp_shim_batch_new(int n_pools, int want_qhigh, int want_stats)
+{
+	crisp_shim_batch* sb = (crisp_shim_batch*)calloc(1, sizeof(*sb));
+	sb->n_pools = n_pools;
+	sb->want_qhigh = want_qhigh;
+	sb->want_stats = want_stats;
+	sb->read_off = (uint32_t*)calloc(1, sizeof(uint32_t));
+	sb->alt_off = (uint32_t*)calloc(1, sizeof(uint32_t));
+	return sb;
+}
+
+void crisp_shim_batch_clear(crisp_shim_batch* sb)
+{
+	sb->n_sites = 0;
+	sb->n_reads = sb->n_alt = 0;
+	sb->n_amb = 0;
+	sb->read_off[0] = 0;
+	sb->alt_off[0] = 0;
+}
+
+void crisp_shim_batch_free(crisp_shim_batch* sb)
+{
+	if (!sb) return;
+	free(sb->tid); free(sb->pos); free(sb->maxvec_ct); free(sb->counts); free(sb->indcounts); free(sb->amb_idx); free(sb->amb_dec);
+	free(sb->refbase); free(sb->maxvec_al); free(sb->indel_len); free(sb->hplen); free(sb->read_off); free(sb->alt_off);
+	free(sb->reads); free(sb->alt_reads); free(sb->amb_ep); free(sb->qhigh); free(sb->stats); free(sb->tstats);
+	free(sb);
+}
+
+void crisp_shim_batch_view(const crisp_shim_batch* sb, crispgpu_batch* b)
+{
+	memset(b, 0, sizeof(*b));
+	b->n_sites = sb->n_sites;
+	b->tid = sb->tid; b->pos = sb->pos; b->refbase = sb->refbase; b->maxvec_al = sb->maxvec_al; b->maxvec_ct = sb->maxvec_ct;
+	b->counts = sb->counts; b->indcounts = sb->indcounts; b->indel_len = sb->indel_len; b->hplen = sb->hplen;
+	b->read_off = sb->read_off; b->reads = sb->reads; b->alt_off = sb->alt_off; b->alt_reads = sb->alt_reads;
+	b->amb_idx = sb->amb_idx; b->amb_dec = sb->amb_dec; b->amb_ep = sb->amb_ep; b->n_amb = sb->n_amb;
+	b->qhigh = sb->want_qhigh ? sb->qhigh : NULL;
+	b->stats = sb->want_stats ? sb->stats : NULL;
+	b->tstats = sb->want_stats ? sb->tstats : NULL;
+}
+
+static void reserve_site(crisp_shim_batch* sb)
+{
+	const size_t n = (size_t)sb->n_sites + 1, P = sb->n_pools;
+	if ((int)n > sb->cap_sites) {
+		const size_t c = n * 2 + 64;
+		sb->tid = (int32_t*)realloc(sb->tid, c * 4); sb->pos = (int32_t*)realloc(sb->pos, c * 4);
+		sb->refbase = (uint8_t*)realloc(sb->refbase, c); sb->maxvec_al = (uint8_t*)realloc(sb->maxvec_al, c * 8);
+		sb->maxvec_ct = (int32_t*)realloc(sb->maxvec_ct, c * 32); sb->counts = (int32_t*)realloc(sb->counts, c * 96);
+		sb->indcounts = (int32_t*)realloc(sb->indcounts, c * P * 96);
+		sb->indel_len = (int16_t*)realloc(sb->indel_len, c * 16); sb->hplen = (int16_t*)realloc(sb->hplen, c * 16);
+		sb->read_off = (uint32_t*)realloc(sb->read_off, (c * P + 1) * 4); sb->alt_off = (uint32_t*)realloc(sb->alt_off, (c * 5 + 1) * 4);
+		sb->amb_idx = (int32_t*)realloc(sb->amb_idx, c * 20);
+		sb->qhigh = (double*)realloc(sb->qhigh, c * P * 128); sb->stats = (double*)realloc(sb->stats, c * P * 128);
+		sb->tstats = (double*)realloc(sb->tstats, c * 128);
+		sb->cap_sites = (int)c;
+	}
+}
+
+int crisp_shim_append_site(crisp_shim_batch* sb, REFLIST* reflist, int current, READQUEUE* bq, struct BAMFILE_data* bd,
+                           struct VARIANT* variant, ALLELE* maxvec, int tid)
+{
+	const int P = sb->n_pools, s = sb->n_sites;
+	reserve_site(sb);
+	sb->tid[s] = tid;
+	sb->pos[s] = variant->position;
+	sb->refbase[s] = (uint8_t)variant->refbase;
+	for (int k = 0; k < 8; k++) { sb->maxvec_al[s * 8 + k] = (uint8_t)maxvec[k].al; sb->maxvec_ct[s * 8 + k] = maxvec[k].ct; }
+	memcpy(sb->counts + (size_t)s * 24, variant->counts, 24 * sizeof(int));
+	for (int i = 0; i < P; i++) memcpy(sb->indcounts + ((size_t)s * P + i) * 24, variant->indcounts[i], 24 * sizeof(int));
+	for (int i = 0; i < P; i++)
+		for (int q = 0; q < 16; q++) {
+			sb->qhigh[((size_t)s * P + i) * 16 + q] = variant->Qhighcounts[i][q];
+			sb->stats[((size_t)s * P + i) * 16 + q] = variant->stats[i][q];
+		}
+	for (int q = 0; q < 16; q++) sb->tstats[(size_t)s * 16 + q] = variant->tstats[q];
+	/* homopolymer ambiguity of the tested indel alleles, newcrispcaller.c:191-198 */
+	for (int al = 1; al <= 5; al++) {
+		if (maxvec[al].ct < 3) continue;
+		const int a = maxvec[al].al;
+		if (current >= 0) {
+			variant->HPlength[a] = 0;
+			if (a >= 4 && (variant->itb[a][0] == '+' || variant->itb[a][0] == '-')) calculate_indel_ambiguity(variant, reflist, current, a);
+		}
+	}
+	for (int a = 0; a < 8; a++) {
+		int len = 0;
+		if (a >= 4 && (variant->itb[a][0] == '+' || variant->itb[a][0] == '-')) len = (int)strlen(variant->itb[a]) - 1;
+		sb->indel_len[s * 8 + a] = (int16_t)(a >= 4 && variant->itb[a][0] == '-' ? -len : len);
+		sb->hplen[s * 8 + a] = (int16_t)variant->HPlength[a];
+	}
+	/* 1. likelihood stream: what calculate_pooled_likelihoods_snp reads (crispEM.c:104-110) */
+	for (int i = 0; i < P; i++) {
+		for (struct alignedread* r = bd[i].first; r != NULL && r->position <= variant->position; r = r->nextread) {
+			if (r->lastpos < variant->position) continue;
+			if (r->filter != '0' || r->type != 0) continue;
+			GROW(sb->reads, sb->cap_reads, sb->n_reads + 1, crispgpu_read);
+			const int o = r->l1 + r->delta;
+			sb->reads[sb->n_reads++] = CRISPGPU_READ((unsigned char)r->quality[o], BTI[(unsigned char)r->sequence[o]], r->strand, r->bidir == 1);
+		}
+		sb->read_off[(size_t)s * P + i + 1] = (uint32_t)sb->n_reads;
+	}
+	/* 2. alt-read side list: what calculate_uniquereads collects (allelecounts.c:47-67), per tested slot and pool */
+	for (int k = 0; k < 5; k++) {
+		const int a2 = maxvec[k + 1].al;
+		if (maxvec[k + 1].ct >= 3) {
+			for (int i = 0; i < P; i++) {
+				const int cap = variant->indcounts[i][a2] + variant->indcounts[i][a2 + maxalleles] + variant->indcounts[i][a2 + 2 * maxalleles];
+				int taken = 0;
+				for (struct alignedread* r = bd[i].first; r != NULL && r->position <= variant->position; r = r->nextread) {
+					if (r->lastpos <= variant->position || r->filter == '1') continue;
+					int hit = 0;
+					if (r->quality[r->l1 + r->delta] >= MINQ + QVoffset && r->type == 0 && a2 < 4 && taken < cap) {
+						hit = toupper(r->sequence[r->l1 + r->delta]) == variant->itb[a2][0];
+					} else if (r->type > 0 && a2 >= 4 && taken < cap) {
+						hit = variant->itb[a2][0] == '+' && (int)strlen(variant->itb[a2]) - 1 == r->type;
+					} else if (r->type < 0 && a2 >= 4 && taken < cap) {
+						hit = variant->itb[a2][0] == '-' && (int)strlen(variant->itb[a2]) - 1 == -1 * r->type;
+					}
+					if (!hit) continue;
+					GROW(sb->alt_reads, sb->cap_alt, sb->n_alt + 1, crispgpu_altread);
+					crispgpu_altread* e = &sb->alt_reads[sb->n_alt++];
+					e->pool = (uint16_t)i; e->offset = (uint16_t)(r->l1 + r->delta); e->aligned = (uint16_t)r->alignedbases; e->strand = r->strand; e->pad = 0;
+					taken++;
+				}
+			}
+		}
+		sb->alt_off[s * 5 + k + 1] = (uint32_t)sb->n_alt;
+	}
+	/* 3. ambiguity rows: what remove_ambiguous_bases(+1) would subtract (process_indel_variant.c:25-62) */
+	for (int k = 0; k < 5; k++) {
+		sb->amb_idx[s * 5 + k] = -1;
+		if (maxvec[k + 1].ct < 3) continue;
+		const int a2 = maxvec[k + 1].al, a3 = maxvec[k == 0 ? 2 : 1].al;
+		if (!((a2 >= 4 && variant->HPlength[a2] > 0) || (a3 >= 4 && variant->HPlength[a3] >= 100))) continue;
+		const int hp = variant->HPlength[a2];
+		if (sb->n_amb + 1 > sb->cap_amb) {
+			sb->cap_amb = (sb->n_amb + 1) * 2 + 16;
+			sb->amb_dec = (int32_t*)realloc(sb->amb_dec, (size_t)sb->cap_amb * P * 16);
+			sb->amb_ep = (double*)realloc(sb->amb_ep, (size_t)sb->cap_amb * P * 16);
+		}
+		int32_t* dec = sb->amb_dec + (size_t)sb->n_amb * P * 4;
+		double* ep = sb->amb_ep + (size_t)sb->n_amb * P * 2;
+		memset(dec, 0, (size_t)P * 16);
+		memset(ep, 0, (size_t)P * 16);
+		for (struct alignedread* r = bq->first; r != NULL && r->position <= variant->position; r = r->next) {
+			if (r->lastpos <= variant->position) continue;
+			const int offset = r->strand == 1 ? maxalleles : 0;
+			if (!(r->filter == '0' && r->allele - offset == variant->refbase)) continue;
+			const int op = r->fcigarlist[r->cigoffset] & 0xf, ol = r->fcigarlist[r->cigoffset] >> 4;
+			if (op != BAM_CMATCH || (ol - r->delta <= hp)) {
+				const int st = r->strand == 1 ? 1 : 0;
+				dec[r->sampleid * 4 + (r->bidir == 1 ? 2 + st : st)]++;
+				ep[r->sampleid * 2 + st] += pow(0.1, ((double)r->quality[r->l1 + r->delta] - QVoffset) / 10);
+			}
+		}
+		sb->amb_idx[s * 5 + k] = sb->n_amb++;
+	}
+	sb->n_sites++;
+	return 0;
+}
+
+void crisp_shim_fill_variant(const crispgpu_results* r, int s, struct VARIANT* variant)
+{
+	const int P = variant->samples;
+	variant->varalleles = r->varalleles[s];
+	variant->strandpass = r->strandpass[s];
+	for (int k = 0; k < 5; k++) {
+		const int o = s * 5 + k, j = r->call_rank[o];
+		if (r->status[o] != CRISPGPU_SLOT_CALLED || j < 0) continue;
+		variant->alleles[j] = r->allele[o];
+		variant->ctpval[j] = r->ctpval[o];
+		variant->chi2pval[j] = r->chi2pval[o];
+		variant->qvpvaluef[j] = r->qvpf[o];
+		variant->qvpvaluer[j] = r->qvpr[o];
+		variant->varpools[j] = variant->nvariants[j] = r->varpools[o];
+		struct CRISPVAR* cv = &variant->crispvar[j];
+		cv->allele = r->allele[o];
+		cv->AF_ML = r->af_ml[o];
+		cv->delta = r->delta[o];
+		cv->deltaf = r->deltaf[o];
+		cv->deltar = r->hwe[o];
+		cv->allelecount = r->allelecount[o];
+		cv->variantpools = r->variantpools[o];
+		const int row = r->call_row[o];
+		for (int i = 0; i < P; i++) {
+			cv->AC[i] = row >= 0 ? r->ac[(size_t)row * P + i] : 0;
+			cv->QV[i] = row >= 0 ? r->qv[(size_t)row * P + i] : 0;
+		}
+	}
+}

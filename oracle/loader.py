@@ -127,6 +127,17 @@ class RefEngine(_CpuEngine):
             raise RuntimeError("replay failed")
         return buf.value.decode()
 
+    def shim_roundtrip(self, batch: Batch) -> tuple[int, str]:
+        """Pack every site again with the production host shim (host/crisp_shim.c) from the rebuilt reference
+        structures and compare with `batch`; returns (number of differing arrays, first difference)."""
+        fn = self.lib.crisp_ref_shim_roundtrip
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.POINTER(CBatch), C.c_char_p, C.c_size_t]
+        cb = batch.as_c()
+        msg = C.create_string_buffer(256)
+        rc = fn(self.h, C.byref(cb), msg, 256)
+        return rc, msg.value.decode()
+
     def scalar(self, name: str, restype, argtypes):
         fn = getattr(self.lib, "crisp_ref_" + name)
         fn.restype = restype

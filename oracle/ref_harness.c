@@ -35,6 +35,8 @@
 #include "crispcaller.h"
 
 #include "oracle_abi.h"
+#define CRISP_SHIM_WITH_REFERENCE_TYPES
+#include "../host/crisp_shim.h"
 
 /* ---- globals the engine objects leave undefined (values: readmultiplebams.c:21-47, bamread.c:3) ---- */
 int SOLID = 0;
@@ -686,6 +688,13 @@ int crisp_ref_replay_vcf(void* h, const crispgpu_batch* b, const crisp_host_resu
 	size_t memlen = 0;
 	FILE* vf = open_memstream(&mem, &memlen);
 	ALLELE maxvec[8];
+	crispgpu_results view;
+	memset(&view, 0, sizeof view);
+	view.n_sites = res->n_sites; view.n_calls = res->n_calls;
+	view.varalleles = res->varalleles; view.strandpass = res->strandpass; view.status = res->status; view.allele = res->allele;
+	view.call_rank = res->call_rank; view.call_row = res->call_row; view.ctpval = res->ctpval; view.chi2pval = res->chi2pval;
+	view.af_ml = res->af_ml; view.delta = res->delta; view.deltaf = res->deltaf; view.hwe = res->hwe; view.qvpf = res->qvpf; view.qvpr = res->qvpr;
+	view.varpools = res->varpools; view.allelecount = res->allelecount; view.variantpools = res->variantpools; view.ac = res->ac; view.qv = res->qv;
 	for (int s = 0; s < b->n_sites; s++) {
 		if (res->varalleles[s] < 1) continue;
 		fill_site(c, b, s);
@@ -693,30 +702,11 @@ int crisp_ref_replay_vcf(void* h, const crispgpu_batch* b, const crisp_host_resu
 			maxvec[k].al = b->maxvec_al[s * 8 + k];
 			maxvec[k].ct = b->maxvec_ct[s * 8 + k];
 		}
-		v->varalleles = res->varalleles[s];
-		v->strandpass = res->strandpass[s];
+		crisp_shim_fill_variant(&view, s, v);  /* the production copy-back (host/crisp_shim.c) */
 		int hpmax = 0, hpslot = -1;
 		for (int k = 0; k < 5; k++) {
-			int o = s * 5 + k, r = res->call_rank[o];
-			if (res->status[o] != CRISPGPU_SLOT_CALLED || r < 0) continue;
-			v->alleles[r] = res->allele[o];
-			v->ctpval[r] = res->ctpval[o];
-			v->chi2pval[r] = res->chi2pval[o];
-			v->qvpvaluef[r] = res->qvpf[o];
-			v->qvpvaluer[r] = res->qvpr[o];
-			v->varpools[r] = v->nvariants[r] = res->varpools[o];
-			v->crispvar[r].allele = res->allele[o];
-			v->crispvar[r].AF_ML = res->af_ml[o];
-			v->crispvar[r].delta = res->delta[o];
-			v->crispvar[r].deltaf = res->deltaf[o];
-			v->crispvar[r].deltar = res->hwe[o];
-			v->crispvar[r].allelecount = res->allelecount[o];
-			v->crispvar[r].variantpools = res->variantpools[o];
-			int row = res->call_row[o];
-			for (int i = 0; i < P; i++) {
-				v->crispvar[r].AC[i] = row >= 0 ? res->ac[(size_t)row * P + i] : 0;
-				v->crispvar[r].QV[i] = row >= 0 ? res->qv[(size_t)row * P + i] : 0;
-			}
+			int o = s * 5 + k;
+			if (res->status[o] != CRISPGPU_SLOT_CALLED || res->call_rank[o] < 0) continue;
 			if (res->allele[o] >= 4 && v->HPlength[res->allele[o]] > hpmax) {
 				hpmax = v->HPlength[res->allele[o]];
 				hpslot = k;
@@ -756,4 +746,62 @@ double crisp_ref_kf_gammaq(double s, double z) { return kf_gammaq(s, z); }
 void crisp_ref_chernoff(int* counts, double* stats, int refbase, int altbase, double ser, double* p0, double* p1)
 {
 	chernoff_bound(counts, stats, refbase, altbase, ser, p0, p1, 8);
+}
+
+
+/*
+ * Round trip of the production packer (host/crisp_shim.c): rebuild struct VARIANT and the read lists of every site of
+ * batch `b`, let crisp_shim_append_site pack them again, and compare the two batches.  Returns the number of arrays
+ * that differ (0 = identical) and describes the first difference in msg.
+ */
+int crisp_ref_shim_roundtrip(void* h, const crispgpu_batch* b, char* msg, size_t msgcap)
+{
+	ref_ctx* c = (ref_ctx*)h;
+	struct VARIANT* v = &c->variant;
+	const int P = c->P, n = b->n_sites;
+	apply_config(c);
+	crisp_shim_batch* sb = crisp_shim_batch_new(P, b->qhigh != NULL, b->stats != NULL);
+	ALLELE maxvec[8];
+	int bad = 0;
+	if (msg && msgcap) msg[0] = 0;
+	for (int s = 0; s < n; s++) {
+		fill_site(c, b, s);
+		v->position = b->pos[s];  /* the packer records the real coordinate */
+		if (build_reads(c, b, s) != 0) { crisp_shim_batch_free(sb); return -1; }
+		for (int k = 0; k < 8; k++) { maxvec[k].al = b->maxvec_al[s * 8 + k]; maxvec[k].ct = b->maxvec_ct[s * 8 + k]; }
+		crisp_shim_append_site(sb, &c->reflist, -1, &c->rq, c->bd, v, maxvec, b->tid[s]);
+	}
+	crispgpu_batch g;
+	crisp_shim_batch_view(sb, &g);
+#define CMP(name, bytes)                                                                                         \
+	do {                                                                                                         \
+		if ((bytes) && (b->name) && memcmp(g.name, b->name, (bytes)) != 0) {                                     \
+			if (!bad && msg) snprintf(msg, msgcap, "array %s differs", #name);                                   \
+			bad++;                                                                                               \
+		}                                                                                                        \
+	} while (0)
+	if (g.n_sites != n) { bad++; if (msg) snprintf(msg, msgcap, "site count %d vs %d", g.n_sites, n); }
+	CMP(tid, (size_t)n * 4); CMP(pos, (size_t)n * 4); CMP(refbase, (size_t)n); CMP(maxvec_al, (size_t)n * 8); CMP(maxvec_ct, (size_t)n * 32);
+	CMP(counts, (size_t)n * 96); CMP(indcounts, (size_t)n * P * 96); CMP(indel_len, (size_t)n * 16); CMP(hplen, (size_t)n * 16);
+	CMP(read_off, ((size_t)n * P + 1) * 4);
+	if (n) CMP(reads, (size_t)b->read_off[(size_t)n * P] * 2);
+	if (b->alt_off) {
+		CMP(alt_off, ((size_t)n * 5 + 1) * 4);
+		if (n && g.alt_off[n * 5] == b->alt_off[n * 5]) CMP(alt_reads, (size_t)b->alt_off[n * 5] * sizeof(crispgpu_altread));
+	}
+	if (b->amb_idx) {
+		for (int k = 0; k < n * 5 && bad == 0; k++) {
+			const int ra = b->amb_idx[k], rb = g.amb_idx[k];
+			if ((ra < 0) != (rb < 0)) { bad++; if (msg) snprintf(msg, msgcap, "amb_idx[%d]: %d vs %d", k, rb, ra); break; }
+			if (ra < 0) continue;
+			if (memcmp(b->amb_dec + (size_t)ra * P * 4, g.amb_dec + (size_t)rb * P * 4, (size_t)P * 16) != 0) { bad++; if (msg) snprintf(msg, msgcap, "amb_dec row of slot %d differs", k); break; }
+			if (b->amb_ep)
+				for (int q = 0; q < P * 2; q++)
+					if (fabs(b->amb_ep[(size_t)ra * P * 2 + q] - g.amb_ep[(size_t)rb * P * 2 + q]) > 1e-12) { bad++; if (msg) snprintf(msg, msgcap, "amb_ep row of slot %d differs", k); break; }
+		}
+	}
+	CMP(qhigh, (size_t)n * P * 128); CMP(stats, (size_t)n * P * 128); CMP(tstats, (size_t)n * 128);
+#undef CMP
+	crisp_shim_batch_free(sb);
+	return bad;
 }

@@ -165,3 +165,18 @@ def test_association_statistic_matches_reference_log_line(kw):
         assert np.all(np.abs(a - b)[fin & ~big] <= tol), f
     # everything else is unaffected by the association pass
     compare_results(got, want, tol=0.0, label="assoc", fp_skip=("assoc_p", "assoc_llr", "assoc_or", "assoc_p1", "assoc_llr1", "assoc_or1"))
+
+
+@needs_ref
+@pytest.mark.parametrize("kw", [
+    dict(variant_frac=0.5, bidir_frac=0.1, second_alt_frac=0.3),
+    dict(variant_frac=0.3, indel_frac=0.6, bidir_frac=0.05, with_qhigh=True, with_stats=True),
+], ids=["snp", "indel"])
+def test_host_shim_round_trip(kw):
+    """host/crisp_shim.c is the packer a CRISP maintainer links in at variantcalls.c:115.  Rebuild the reference's
+    struct VARIANT + read lists from a batch, pack them with the shim, and get the same batch back; the copy-back half
+    of the shim (crisp_shim_fill_variant) is what test_oracle_equals_reference's VCF replay goes through."""
+    cfg = _cfg(P=8)
+    batch = synth_batch(120, 8, cfg.ploidy, 80, seed=41, **kw)
+    bad, msg = RefEngine(cfg).shim_roundtrip(batch)
+    assert bad == 0, msg
