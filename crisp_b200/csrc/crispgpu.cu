@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -131,6 +132,11 @@ const OutField kOutFields[] = {
 	{8, 5}, {8, 5}, {8, 5}, {8, 5}, {8, 5}, {8, 5},  // assoc_p assoc_llr assoc_or assoc_p1 assoc_llr1 assoc_or1
 };
 constexpr int kNumOut = sizeof(kOutFields) / sizeof(kOutFields[0]);
+// DevOut, crispgpu_results and DevBatch are walked as arrays of pointers in the order of kOutFields / collect_arrays
+static_assert(sizeof(DevOut) == (kNumOut + 2) * sizeof(void*), "DevOut must be kNumOut result pointers followed by ac, qv");
+static_assert(sizeof(crispgpu_results) == 8 + (kNumOut + 2) * sizeof(void*), "crispgpu_results layout");
+static_assert(offsetof(crispgpu_results, varalleles) == 8 && offsetof(crispgpu_results, ac) == 8 + kNumOut * sizeof(void*), "crispgpu_results layout");
+static_assert(offsetof(DevBatch, tid) == 8 && sizeof(DevBatch) == 8 + 19 * sizeof(void*), "DevBatch must be 19 array pointers after two ints");
 
 void bind_out(crispgpu_ctx* ctx)
 {

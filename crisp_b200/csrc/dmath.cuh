@@ -7,7 +7,6 @@
 
 namespace crisp {
 
-constexpr double kLn10 = 2.302585092994045684;
 constexpr double kCtEps = 1e-6;  // `epsilon`, FET/contables.h:9
 constexpr double kMinP = 1e-6;   // MINP, crisp/crispEM.c:6
 

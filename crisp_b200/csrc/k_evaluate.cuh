@@ -11,14 +11,6 @@
 
 namespace crisp {
 
-struct SlotStat {
-	double p0;       // p[0] of evaluate_variant
-	double sj0, sj1; // joint statistic per pivot group
-	double tot;      // total reads used for the MINREADS test
-	double wj0, wj1, wtot; // weighted-table statistic (permutation mode)
-	int tested;
-};
-
 __device__ __forceinline__ int slot_alleles(const uint8_t* mal, int slot, int& a1, int& a2, int& a3)
 {
 	a1 = mal[0];

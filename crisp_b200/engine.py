@@ -67,28 +67,15 @@ def load_library() -> C.CDLL:
     return lib
 
 
-def pinned_like(a: np.ndarray) -> np.ndarray:
-    """Copy of `a` in pinned host memory (crispgpu_host_alloc), so crispgpu_submit's copies are asynchronous."""
-    lib = load_library()
-    nbytes = max(a.nbytes, 1)
-    ptr = lib.crispgpu_host_alloc(nbytes)
-    if not ptr:
-        raise EngineError("crispgpu_host_alloc failed")
-    buf = (C.c_char * nbytes).from_address(ptr)
-    out = np.frombuffer(buf, dtype=a.dtype, count=a.size).reshape(a.shape)
-    out[...] = a
-    out_ref = _PinnedOwner(ptr, lib)
-    # keep the owner alive with the array
-    _pinned_owners[id(out)] = (out_ref, out)
-    return out
+class _PinnedBlock:
+    """One crispgpu_host_alloc allocation; freed when the last array viewing it is collected."""
 
-
-_pinned_owners: dict = {}
-
-
-class _PinnedOwner:
-    def __init__(self, ptr, lib):
-        self.ptr, self.lib = ptr, lib
+    def __init__(self, nbytes: int):
+        self.lib = load_library()
+        self.ptr = self.lib.crispgpu_host_alloc(max(nbytes, 1))
+        if not self.ptr:
+            raise EngineError("crispgpu_host_alloc failed")
+        self.buf = (C.c_char * max(nbytes, 1)).from_address(self.ptr)
 
     def __del__(self):
         try:
@@ -97,19 +84,29 @@ class _PinnedOwner:
             pass
 
 
+def pinned_like(a: np.ndarray):
+    """(copy of `a` in pinned host memory, owner object that must outlive it)."""
+    block = _PinnedBlock(a.nbytes)
+    out = np.frombuffer(block.buf, dtype=a.dtype, count=a.size).reshape(a.shape)
+    out[...] = a
+    return out, block
+
+
 def pin_batch(batch: Batch) -> Batch:
-    """A copy of the batch whose arrays live in pinned memory."""
+    """A copy of the batch whose arrays live in pinned memory, so crispgpu_submit's copies are asynchronous."""
     from .abi import _BATCH_ARRAYS
 
-    arrays = {}
-    for name, _, _ in _BATCH_ARRAYS:
-        a = getattr(batch, name)
-        if a is not None:
-            arrays[name] = pinned_like(a)
     out = Batch.__new__(Batch)
     out.n_pools = batch.n_pools
+    out._pinned_blocks = []
     for name, _, _ in _BATCH_ARRAYS:
-        setattr(out, name, arrays.get(name))
+        a = getattr(batch, name)
+        if a is None:
+            setattr(out, name, None)
+            continue
+        arr, block = pinned_like(a)
+        out._pinned_blocks.append(block)
+        setattr(out, name, arr)
     out.n_sites = batch.n_sites
     out.n_amb = batch.n_amb
     return out

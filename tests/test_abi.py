@@ -63,12 +63,14 @@ def test_no_cpu_fallback_without_gpu(lib):
 
 
 def test_product_does_not_reference_the_oracle():
-    """Nothing under crisp_b200/ may import, link or execute oracle/."""
-    for dirpath, _, files in os.walk(os.path.join(ROOT, "crisp_b200")):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
-                text = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in text.replace("no CPU fallback", "").lower() or f == "__init__.py" and "oracle" not in text, (dirpath, f)
+    """Nothing under crisp_b200/, host/ or include/ may import, link or execute oracle/."""
+    for top in ("crisp_b200", "host", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".c")):
+                    text = open(os.path.join(dirpath, f)).read()
+                    for needle in ("oracle.loader", "from oracle", "import oracle", "liboracle", "libcrispref", "oracle_abi.h", "crisp_oracle"):
+                        assert needle not in text, (dirpath, f, needle)
 
 
 def test_batch_validation():
