@@ -59,7 +59,7 @@ struct crispgpu_ctx {
 	DevBuf h_o[32], h_ac, h_qv;
 	DevOut dout{};
 	// queues
-	DevBuf d_perm_tasks, d_call_tasks, d_counters, h_counters, d_gws;
+	DevBuf d_perm_tasks, d_call_tasks, d_call_tasks2, d_counters, h_counters, d_gws;
 	DevBuf d_tail_task, d_tail_head, d_tail_total, d_tail_rec, d_tail_counters;  // long permutation tasks (k_permute_stranded_tail)
 	size_t gws_stride = 0;
 	// launch geometry
@@ -81,7 +81,7 @@ struct crispgpu_ctx {
 	bool inflight = false;
 	crispgpu_timing timing{};
 	crispgpu_results res{};
-	int n_call = 0, n_perm = 0;
+	int n_call = 0, n_call1 = 0, n_call2 = 0, n_perm = 0;
 	int64_t stage1_launches = 0;
 	bool fetch_pending = false;
 	char err[512] = {0};
@@ -301,6 +301,8 @@ int ensure_outputs(crispgpu_ctx* ctx, int n)
 	if (rc) return rc;
 	rc = ensure_dev(ctx, ctx->d_call_tasks, (size_t)n * 5 * 4);
 	if (rc) return rc;
+	rc = ensure_dev(ctx, ctx->d_call_tasks2, (size_t)n * 5 * 4);
+	if (rc) return rc;
 	return 0;
 }
 
@@ -336,6 +338,7 @@ EngineParams make_params(crispgpu_ctx* ctx)
 	prm.o = ctx->dout;
 	prm.q.perm_tasks = static_cast<int32_t*>(ctx->d_perm_tasks.p);
 	prm.q.call_tasks = static_cast<int32_t*>(ctx->d_call_tasks.p);
+	prm.q.call_tasks2 = static_cast<int32_t*>(ctx->d_call_tasks2.p);
 	prm.q.counters = static_cast<int32_t*>(ctx->d_counters.p);
 	prm.gws = static_cast<double*>(ctx->d_gws.p);
 	prm.gws_stride = ctx->gws_stride;
@@ -401,7 +404,7 @@ int run_stage1(crispgpu_ctx* ctx)
 			CK(cudaGetLastError());
 			if (g.max_iter > kPermHead) {
 				// the number of tail tasks sizes the chunk records (the one extra host wait of the permutation mode)
-				int32_t* hc2 = static_cast<int32_t*>(ctx->h_counters.p) + 8;
+				int32_t* hc2 = static_cast<int32_t*>(ctx->h_counters.p) + 12;
 				CK(cudaMemcpyAsync(hc2, ctx->d_tail_counters.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
 				CK(cudaStreamSynchronize(ctx->stream));
 				const int n_tail = hc2[0];
@@ -434,7 +437,7 @@ int run_stage1(crispgpu_ctx* ctx)
 	}
 	CK(cudaEventRecord(ctx->ev[EV_FILTER], ctx->stream));
 	// how many tasks reached the caller: sizes the per-pool rows
-	CK(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 10 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaEventRecord(ctx->ev_counts, ctx->stream));
 	ctx->stage1_launches = launches;
 	return 0;
@@ -450,7 +453,9 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 	CK(cudaEventSynchronize(ctx->ev_counts));
 	const int32_t* hc = static_cast<const int32_t*>(ctx->h_counters.p);
 	ctx->n_perm = hc[0];
-	ctx->n_call = hc[1];
+	ctx->n_call1 = hc[1];
+	ctx->n_call2 = hc[8];
+	ctx->n_call = hc[1] + hc[8];
 	{
 		// distinct quality characters of the batch -> dense likelihood path when few enough and one pool size
 		int nq = 0;
@@ -479,20 +484,39 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 	}
 	if (ctx->n_call > 0) {
 		if (g.em_flag >= 1) {
-			if (!ctx->em_grid) {
-				rc = ctx->em_smem_g ? occupancy_grid(ctx, k_em<true>, ctx->em_threads, ctx->em_smem, &ctx->em_grid)
-				                    : occupancy_grid(ctx, k_em<false>, ctx->em_threads, ctx->em_smem, &ctx->em_grid);
-				if (rc) return rc;
-			}
-			int grid = ctx->em_grid < ctx->n_call ? ctx->em_grid : ctx->n_call;
-			if (!ctx->em_smem_g) {
-				rc = ensure_dev(ctx, ctx->d_gws, (size_t)ctx->em_grid * ctx->gws_stride * sizeof(double));
-				if (rc) return rc;
-				prm = make_params(ctx);
-				k_em<false><<<grid, ctx->em_threads, ctx->em_smem, ctx->stream>>>(prm);
+			const bool assoc = g.association == 1 && ctx->d_pheno.p != nullptr;
+			int32_t* cnt = static_cast<int32_t*>(ctx->d_counters.p);
+			auto launch_em = [&](auto kernel, const int32_t* list, int ntasks, int32_t* head, int row0) -> int {
+				if (ntasks <= 0) return 0;
+				if (!ctx->em_grid) {
+					int r2 = occupancy_grid(ctx, kernel, ctx->em_threads, ctx->em_smem, &ctx->em_grid);
+					if (r2) return r2;
+				} else if (ctx->em_smem > 48 * 1024) {
+					CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->em_smem));
+					CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+				}
+				int grid = ctx->em_grid < ntasks ? ctx->em_grid : ntasks;
+				if (!ctx->em_smem_g) {
+					int r2 = ensure_dev(ctx, ctx->d_gws, (size_t)ctx->em_grid * ctx->gws_stride * sizeof(double));
+					if (r2) return r2;
+					prm = make_params(ctx);
+				}
+				kernel<<<grid, ctx->em_threads, ctx->em_smem, ctx->stream>>>(prm, list, ntasks, head, row0);
+				launches++;
+				return 0;
+			};
+			const int32_t* l1 = prm.q.call_tasks;
+			const int32_t* l2 = prm.q.call_tasks2;
+			// quality-value likelihood tasks, then count-based likelihood tasks (rows follow the first list's)
+			if (ctx->em_smem_g) {
+				rc = assoc ? launch_em(k_em<true, true, false>, l1, ctx->n_call1, cnt + 3, 0) : launch_em(k_em<true, false, false>, l1, ctx->n_call1, cnt + 3, 0);
+				if (!rc) rc = assoc ? launch_em(k_em<true, true, true>, l2, ctx->n_call2, cnt + 9, ctx->n_call1) : launch_em(k_em<true, false, true>, l2, ctx->n_call2, cnt + 9, ctx->n_call1);
 			} else {
-				k_em<true><<<grid, ctx->em_threads, ctx->em_smem, ctx->stream>>>(prm);
+				rc = assoc ? launch_em(k_em<false, true, false>, l1, ctx->n_call1, cnt + 3, 0) : launch_em(k_em<false, false, false>, l1, ctx->n_call1, cnt + 3, 0);
+				if (!rc) rc = assoc ? launch_em(k_em<false, true, true>, l2, ctx->n_call2, cnt + 9, ctx->n_call1) : launch_em(k_em<false, false, true>, l2, ctx->n_call2, cnt + 9, ctx->n_call1);
 			}
+			if (rc) return rc;
+			launches--;  // the common increment below counts one
 		} else {
 			if (!ctx->lg_grid) { rc = occupancy_grid(ctx, k_legacy<4>, 128, ctx->lg_smem, &ctx->lg_grid); if (rc) return rc; }
 			int need = (ctx->n_call + 3) / 4;
@@ -736,7 +760,7 @@ void crispgpu_destroy(crispgpu_ctx* ctx)
 	for (auto& b : ctx->h_o) fh(b);
 	fd(ctx->d_ac); fd(ctx->d_qv); fh(ctx->h_ac); fh(ctx->h_qv);
 	fd(ctx->d_tail_task); fd(ctx->d_tail_head); fd(ctx->d_tail_total); fd(ctx->d_tail_rec); fd(ctx->d_tail_counters);
-	fd(ctx->d_perm_tasks); fd(ctx->d_call_tasks); fd(ctx->d_counters); fh(ctx->h_counters); fd(ctx->d_gws);
+	fd(ctx->d_perm_tasks); fd(ctx->d_call_tasks); fd(ctx->d_call_tasks2); fd(ctx->d_counters); fh(ctx->h_counters); fd(ctx->d_gws);
 	for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
 	if (ctx->ev_counts) cudaEventDestroy(ctx->ev_counts);
 	if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);

@@ -41,8 +41,9 @@ struct EmShared {
 // so the inner loops cost one shared-memory load and one FMA per genotype; the pool-constant n*log10(1-p) is added
 // after the maximum is known.
 
-template <bool SMEM_G>
-__global__ void __maxnreg__(96) k_em(EngineParams prm)
+// tasks[0..n_tasks): the (site, slot) list of this launch; head: its work counter; row0: first AC/QV row of the list
+template <bool SMEM_G, bool ASSOC, bool COUNTLIK>
+__global__ void __maxnreg__(96) k_em(EngineParams prm, const int32_t* __restrict__ tasks, int n_tasks, int32_t* head, int row0)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const DevBatch& b = prm.b;
@@ -94,17 +95,17 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm)
 
 	for (;;) {
 		__syncthreads();
-		if (tid == 0) sh->task = atomicAdd(prm.q.counters + 3, 1);
+		if (tid == 0) sh->task = atomicAdd(head, 1);
 		__syncthreads();
-		const int task = sh->task;
-		if (task >= prm.q.counters[1]) break;
-		const int o = prm.q.call_tasks[task], s = o / kSlots, slot = o - s * kSlots;
+		if (sh->task >= n_tasks) break;
+		const int o = tasks[sh->task], s = o / kSlots, slot = o - s * kSlots;
+		const int task = row0 + sh->task;  // AC/QV row
 		const uint8_t* mal = b.maxvec_al + s * 8;
 		int a1, a2, a3;
 		slot_alleles(mal, slot, a1, a2, a3);
 		const int refbase = b.refbase[s];
 		const int row = slot_amb_row(b, s, slot, a2, a3);
-		const bool countlik = (a2 >= 4 || c.use_base_qvs == 0);
+		constexpr bool countlik = COUNTLIK;  // (a2 >= 4 || --usebq 0), decided when the task was queued
 		// e(f) is linear in f and f linear in j unless a reference bias bends it: log-likelihood planes concave in j
 		const bool unimodal = countlik || c.ref_bias == 0.5;
 		int ilen = 0, is_ins = 0;
@@ -611,7 +612,7 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm)
 				}
 			}
 			// ---- calculate_LRstatistic (crisp/LRstatistic.c:48-69), --phenotypes only: five EMs restricted to pool subsets ----
-			if (c.association && pfin >= 0.0001 && delta >= 3) {
+			if (ASSOC && c.association && pfin >= 0.0001 && delta >= 3) {
 				__syncthreads();  // HWE above still reads the posterior plane
 				for (int k = 0; k < 3; k++) { E01[k] = EL01[k]; E10[k] = EL10[k]; }
 				const int flags[5] = {7, 1, 6, 4, 5};

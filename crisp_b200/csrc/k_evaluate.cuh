@@ -54,6 +54,13 @@ __device__ __forceinline__ void queue_push(int32_t* list, int32_t* counter, int3
 	list[idx] = v;
 }
 
+// a slot that reached the caller: EM tasks are split by likelihood kind so that each gets a specialised kernel
+__device__ __forceinline__ void push_call_task(const EngineParams& prm, int o, int a2)
+{
+	if (prm.c.em_flag >= 1 && (a2 >= 4 || prm.c.use_base_qvs == 0)) queue_push(prm.q.call_tasks2, prm.q.counters + 8, o);
+	else queue_push(prm.q.call_tasks, prm.q.counters + 1, o);
+}
+
 // p-value of the asymptotic test from the per-group joint statistics
 __device__ inline double chi2_from_groups(int P, int pivot, double sj0, double sj1, bool stratified)
 {
@@ -252,7 +259,7 @@ __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_evaluate(Eng
 				if (!permmode) {
 					ctp = chi = chi2_from_groups(P, pivot, my_sj0, my_sj1, true);
 					status = pass_fast_filter(c, b, s, a2, my_p0, ctp, ctp, 0.0) ? CRISPGPU_SLOT_NOCALL : CRISPGPU_SLOT_REJECT_CT;
-					if (status == CRISPGPU_SLOT_NOCALL) queue_push(prm.q.call_tasks, prm.q.counters + 1, o);
+					if (status == CRISPGPU_SLOT_NOCALL) push_call_task(prm, o, a2);
 				} else {
 					if (c.ploidy0 > 2) chi = chi2_from_groups(P, pivot, my_sj0, my_sj1, false);
 					status = CRISPGPU_SLOT_REJECT_CT;  // provisional: k_filter decides once the permutation p-value exists
@@ -279,32 +286,22 @@ __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_evaluate(Eng
 // HBM-streaming pass (2 B per read, 16-byte loads); lets k_em pick the dense likelihood path.
 __global__ void k_qualmap(const uint16_t* __restrict__ reads, size_t n_reads, int32_t* counters)
 {
-	unsigned long long lo = 0ull, hi = 0ull;
+	__shared__ unsigned char seen[kNQ];  // one flag per quality character; racing stores all write 1
+	for (int q = threadIdx.x; q < kNQ; q += blockDim.x) seen[q] = 0;
+	__syncthreads();
 	const size_t nvec = n_reads / 8;
 	const uint4* v = reinterpret_cast<const uint4*>(reads);
 	for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nvec; k += (size_t)gridDim.x * blockDim.x) {
 		const uint4 x = __ldg(v + k);
-		const uint32_t w[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-		for (int t = 0; t < 4; t++) {
-			const uint32_t q0 = w[t] & 0x7f, q1 = (w[t] >> 16) & 0x7f;
-			if (q0 < 64) lo |= 1ull << q0; else hi |= 1ull << (q0 - 64);
-			if (q1 < 64) lo |= 1ull << q1; else hi |= 1ull << (q1 - 64);
-		}
+		seen[x.x & 0x7f] = 1; seen[(x.x >> 16) & 0x7f] = 1;
+		seen[x.y & 0x7f] = 1; seen[(x.y >> 16) & 0x7f] = 1;
+		seen[x.z & 0x7f] = 1; seen[(x.z >> 16) & 0x7f] = 1;
+		seen[x.w & 0x7f] = 1; seen[(x.w >> 16) & 0x7f] = 1;
 	}
-	if (blockIdx.x == 0 && threadIdx.x < (int)(n_reads - nvec * 8)) {
-		const uint32_t q = reads[nvec * 8 + threadIdx.x] & 0x7f;
-		if (q < 64) lo |= 1ull << q; else hi |= 1ull << (q - 64);
-	}
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) { lo |= __shfl_xor_sync(0xffffffffu, lo, o); hi |= __shfl_xor_sync(0xffffffffu, hi, o); }
-	if ((threadIdx.x & 31) == 0) {
-		unsigned int* c = reinterpret_cast<unsigned int*>(counters) + 4;
-		if ((uint32_t)lo) atomicOr(c + 0, (uint32_t)lo);
-		if (lo >> 32) atomicOr(c + 1, (uint32_t)(lo >> 32));
-		if ((uint32_t)hi) atomicOr(c + 2, (uint32_t)hi);
-		if (hi >> 32) atomicOr(c + 3, (uint32_t)(hi >> 32));
-	}
+	if (blockIdx.x == 0 && threadIdx.x < (int)(n_reads - nvec * 8)) seen[reads[nvec * 8 + threadIdx.x] & 0x7f] = 1;
+	__syncthreads();
+	for (int q = threadIdx.x; q < kNQ; q += blockDim.x)
+		if (seen[q]) atomicOr(reinterpret_cast<unsigned int*>(counters) + 4 + (q >> 5), 1u << (q & 31));
 }
 
 // After the permutation kernel: apply the FAST_FILTER rejects with the Monte-Carlo p-value and queue the survivors.
@@ -319,7 +316,7 @@ __global__ void k_filter(EngineParams prm)
 		bool keep = pass_fast_filter(prm.c, prm.b, s, a2, prm.o.paf[o], ctp, ctp, prm.c.ploidy0 > 2 ? prm.o.chi2pval[o] : 0.0);
 		if (keep) {
 			prm.o.status[o] = CRISPGPU_SLOT_NOCALL;
-			queue_push(prm.q.call_tasks, prm.q.counters + 1, o);
+			push_call_task(prm, o, a2);
 		}
 	}
 }

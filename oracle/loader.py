@@ -12,6 +12,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -39,7 +40,8 @@ def build(force: bool = False) -> None:
     args = ["make", "-s", "-C", HERE]
     if force:
         args.append("-B")
-    subprocess.run(args + ["all"], check=True)
+    # make's own messages must not reach stdout: bench.py prints exactly one JSON line there
+    subprocess.run(args + ["all"], check=True, stdout=sys.stderr)
 
 
 def _host_results(res: Results, genll: np.ndarray | None) -> HostResults:
