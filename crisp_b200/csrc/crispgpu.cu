@@ -462,8 +462,9 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 		uint8_t ql[16] = {0};
 		for (int q = 0; q < kNQ; q++)
 			if ((static_cast<const uint32_t*>(ctx->h_counters.p)[4 + (q >> 5)] >> (q & 31)) & 1u) { if (nq < 16) ql[nq] = (uint8_t)q; nq++; }
-		const bool dense = g.em_flag >= 1 && g.use_base_qvs == 1 && ctx->class_ploidy.size() == 1 && nq >= 1 && nq <= kDenseNQ && ctx->em_smem_g &&
-		                   em_smem_fixed(ctx->P, ctx->nmax + 1, ctx->em_warps, true, nq) + (size_t)3 * (ctx->nmax + 1) * ctx->P * 8 <= ctx->smem_optin;
+		const size_t planes = ctx->em_smem_g ? (size_t)3 * (ctx->nmax + 1) * ctx->P * 8 : 0;  // planes in shared memory or in the global workspace
+		const bool dense = g.em_flag >= 1 && g.use_base_qvs == 1 && ctx->class_ploidy.size() == 1 && nq >= 1 && nq <= kDenseNQ &&
+		                   em_smem_fixed(ctx->P, ctx->nmax + 1, ctx->em_warps, true, nq) + planes <= ctx->smem_optin;
 		ctx->nq = dense ? nq : 0;
 		ctx->dense_lik = dense ? 1 : 0;
 		memcpy(ctx->qlist, ql, sizeof ql);

@@ -203,7 +203,10 @@ __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_evaluate(Eng
 						if (a > 0) acc += sqrt((double)a) * (x2[0] - Ef[t] * a) * rvf[t];
 						if (bb > 0) acc += sqrt((double)bb) * (x2[1] - Er[t] * bb) * rvr[t];
 						if (cc > 0) acc += sqrt((double)cc) * (x2[2] - Eb[t] * cc) * rvb[t];
-						const double z = acc * rsqrt((double)(a * a + bb * bb + cc * cc));
+						// the reference forms a*a+b*b+c*c in 32-bit int (chisquare-stratified.c:53): beyond ~33 000 reads per strand it
+						// wraps, the square root turns NaN and the test reports p = 0 — reproduced with defined unsigned wrap-around
+						const int ss = (int)((unsigned)a * (unsigned)a + (unsigned)bb * (unsigned)bb + (unsigned)cc * (unsigned)cc);
+						const double z = acc * rsqrt((double)ss);
 						if (t == 0) sj0 += z * z; else sj1 += z * z;
 					}
 					sj0 = warp_sum(sj0);

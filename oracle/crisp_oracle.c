@@ -296,7 +296,8 @@ static void o_chi2_stratified(oracle_ctx* c, int a1, int a2, int a3, double* pva
 		int b = IC(c, i, a1 + NA) + IC(c, i, a2 + NA) + IC(c, i, a3 + NA);
 		int cc = IC(c, i, a1 + 2 * NA) + IC(c, i, a2 + 2 * NA) + IC(c, i, a3 + 2 * NA);
 		if (a + b + cc < 1 || total < 25) continue;
-		double df = 0, dr = 0, db = 0, nf = sqrt(a * a + b * b + cc * cc);
+		/* :53 sums the squares in int; made explicit (two's-complement wrap, as the compiled reference behaves) */
+		double df = 0, dr = 0, db = 0, nf = sqrt((double)(int)((unsigned)a * (unsigned)a + (unsigned)b * (unsigned)b + (unsigned)cc * (unsigned)cc));
 		double w1 = a / nf, w2 = b / nf, w3 = cc / nf;
 		if (a > 0) df = (IC(c, i, a2) - Ef[g] * a) / sqrt((1.0 - Ef[g]) * Ef[g] * a);
 		if (b > 0) dr = (IC(c, i, a2 + NA) - Er[g] * b) / sqrt((1.0 - Er[g]) * Er[g] * b);

@@ -30,6 +30,10 @@ SCENARIOS = [
     ("manyquals", 200, 10, 20, 100, {}, dict(variant_frac=0.4, bidir_frac=0.1, quals=range(14, 42))),
     ("twelvequals_c2", 100, 50, 48, 200, {}, dict(variant_frac=0.3, quals=range(20, 42, 2))),
     ("deep_pool", 40, 4, 40, 3000, {}, dict(variant_frac=0.5)),
+    ("big_poolsize_sparse", 60, 6, [150, 150, 150, 140, 140, 140], 400, {}, dict(variant_frac=0.6)),   # genotypes beyond j = 127
+    ("big_poolsize_dense", 60, 6, 200, 400, {}, dict(variant_frac=0.6)),
+    ("very_deep_sparse", 6, 2, [20, 24], 70000, {}, dict(variant_frac=1.0)),                            # > 65504 reads per pool: 16-bit bins fold
+    ("very_deep_dense", 6, 2, 20, 70000, {}, dict(variant_frac=1.0)),
     ("pivot", 300, 12, 16, 80, dict(pivot_sample=5), dict(variant_frac=0.4)),
     ("indel", 300, 10, 20, 100, {}, dict(variant_frac=0.3, indel_frac=0.5, bidir_frac=0.05)),
     ("nobq", 200, 10, 20, 100, dict(use_base_qvs=0), dict(variant_frac=0.4)),
