@@ -66,7 +66,10 @@ struct crispgpu_ctx {
 	int ev_warps = 8, ev_grid = 0;
 	size_t ev_smem = 0;
 	int em_threads = 256, em_grid = 0, em_warps = 8, em_key = -1;
-	int nq = 0, dense_lik = 0;
+	int nq = 0, dense_lik = 0, nobidir = 0;
+	size_t em_smem2 = 0;       // shared memory of the two-plane (no bidirectional reads) instantiation
+	bool em_smem_g2 = false;   // its planes fit in shared memory
+	int em_grid2 = 0;
 	uint8_t qlist[16] = {0};
 	size_t em_smem = 0;
 	bool em_smem_g = true;
@@ -146,7 +149,7 @@ void bind_out(crispgpu_ctx* ctx)
 	ctx->dout.qv = static_cast<double*>(ctx->d_qv.p);
 }
 
-size_t em_smem_fixed(int P, int J, int nwarps, bool dense, int nq)
+size_t em_smem_fixed(int P, int J, int nwarps, bool dense, int nq, bool nobidir = false)
 {
 	size_t off = (sizeof(EmShared) + 15) & ~size_t(15);
 	off += sizeof(double) * P;
@@ -161,6 +164,8 @@ size_t em_smem_fixed(int P, int J, int nwarps, bool dense, int nq)
 	off += sizeof(double) * 2 * 19 * rounds + sizeof(int32_t) * 2 * rounds;
 	off = (off + 15) & ~size_t(15);
 	off += sizeof(double) * 3 * P;
+	off += nobidir ? sizeof(double) * J : 0;
+	off = (off + 15) & ~size_t(15);
 	return off;
 }
 
@@ -180,7 +185,7 @@ int setup_geometry(crispgpu_ctx* ctx)
 	ctx->em_warps = warps;
 	const size_t fixed = em_smem_fixed(P, J, warps, false, 0);
 	const size_t gbytes = (size_t)3 * J * P * sizeof(double);
-	ctx->em_smem_g = fixed + gbytes <= budget;
+	ctx->em_smem_g = 2 * (fixed + gbytes + 1024) <= budget;  // at least two CTAs per SM, else planes go to the global workspace
 	ctx->em_smem = ctx->em_smem_g ? fixed + gbytes : fixed;
 	ctx->gws_stride = (size_t)3 * J * P;
 	// k_permute: threads per CTA limited by the per-permutation occupancy columns
@@ -437,7 +442,7 @@ int run_stage1(crispgpu_ctx* ctx)
 	}
 	CK(cudaEventRecord(ctx->ev[EV_FILTER], ctx->stream));
 	// how many tasks reached the caller: sizes the per-pool rows
-	CK(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 10 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 11 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaEventRecord(ctx->ev_counts, ctx->stream));
 	ctx->stage1_launches = launches;
 	return 0;
@@ -468,12 +473,23 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 		ctx->nq = dense ? nq : 0;
 		ctx->dense_lik = dense ? 1 : 0;
 		memcpy(ctx->qlist, ql, sizeof ql);
-		const int key = dense ? nq : 0;
+		// two-plane variant: no bidirectional read in the batch, one pool size, no association pass
+		const bool scanned = g.em_flag >= 1 && g.use_base_qvs == 1 && ctx->n_reads > 0;
+		const bool nobidir = scanned && hc[10] == 0 && ctx->class_ploidy.size() == 1 && !(g.association == 1 && ctx->d_pheno.p);
+		ctx->nobidir = nobidir ? 1 : 0;
+		const int key = (dense ? nq : 0) + (nobidir ? 64 : 0);
 		if (key != ctx->em_key) {
 			ctx->em_key = key;
 			ctx->em_grid = 0;
-			const size_t fixed = em_smem_fixed(ctx->P, ctx->nmax + 1, ctx->em_warps, dense, nq);
-			ctx->em_smem = ctx->em_smem_g ? fixed + (size_t)3 * (ctx->nmax + 1) * ctx->P * 8 : fixed;
+			ctx->em_grid2 = 0;
+			const int J = ctx->nmax + 1;
+			const size_t fixed = em_smem_fixed(ctx->P, J, ctx->em_warps, dense, nq);
+			ctx->em_smem = ctx->em_smem_g ? fixed + (size_t)3 * J * ctx->P * 8 : fixed;
+			const size_t fixed2 = em_smem_fixed(ctx->P, J, ctx->em_warps, dense, nq, true);
+			// planes in shared memory only when at least two CTAs still fit per SM; a single resident CTA hides less latency
+			// than several CTAs working out of the L2-resident workspace (measured on config 3: 1.11 ms vs 0.98 ms)
+			ctx->em_smem_g2 = 2 * (fixed2 + (size_t)2 * J * ctx->P * 8 + 1024) <= ctx->smem_optin;
+			ctx->em_smem2 = ctx->em_smem_g2 ? fixed2 + (size_t)2 * J * ctx->P * 8 : fixed2;
 		}
 		prm = make_params(ctx);
 	}
@@ -487,34 +503,46 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 		if (g.em_flag >= 1) {
 			const bool assoc = g.association == 1 && ctx->d_pheno.p != nullptr;
 			int32_t* cnt = static_cast<int32_t*>(ctx->d_counters.p);
-			auto launch_em = [&](auto kernel, const int32_t* list, int ntasks, int32_t* head, int row0) -> int {
+			auto launch_em = [&](auto kernel, const int32_t* list, int ntasks, int32_t* head, int row0, size_t smem, bool smem_g, int* grid_cache) -> int {
 				if (ntasks <= 0) return 0;
-				if (!ctx->em_grid) {
-					int r2 = occupancy_grid(ctx, kernel, ctx->em_threads, ctx->em_smem, &ctx->em_grid);
+				if (!*grid_cache) {
+					int r2 = occupancy_grid(ctx, kernel, ctx->em_threads, smem, grid_cache);
 					if (r2) return r2;
-				} else if (ctx->em_smem > 48 * 1024) {
-					CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->em_smem));
+				} else if (smem > 48 * 1024) {
+					CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 					CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 				}
-				int grid = ctx->em_grid < ntasks ? ctx->em_grid : ntasks;
-				if (!ctx->em_smem_g) {
-					int r2 = ensure_dev(ctx, ctx->d_gws, (size_t)ctx->em_grid * ctx->gws_stride * sizeof(double));
+				int grid = *grid_cache < ntasks ? *grid_cache : ntasks;
+				if (!smem_g) {
+					int r2 = ensure_dev(ctx, ctx->d_gws, (size_t)*grid_cache * ctx->gws_stride * sizeof(double));
 					if (r2) return r2;
 					prm = make_params(ctx);
 				}
-				kernel<<<grid, ctx->em_threads, ctx->em_smem, ctx->stream>>>(prm, list, ntasks, head, row0);
+				kernel<<<grid, ctx->em_threads, smem, ctx->stream>>>(prm, list, ntasks, head, row0);
 				launches++;
 				return 0;
 			};
 			const int32_t* l1 = prm.q.call_tasks;
 			const int32_t* l2 = prm.q.call_tasks2;
-			// quality-value likelihood tasks, then count-based likelihood tasks (rows follow the first list's)
-			if (ctx->em_smem_g) {
-				rc = assoc ? launch_em(k_em<true, true, false>, l1, ctx->n_call1, cnt + 3, 0) : launch_em(k_em<true, false, false>, l1, ctx->n_call1, cnt + 3, 0);
-				if (!rc) rc = assoc ? launch_em(k_em<true, true, true>, l2, ctx->n_call2, cnt + 9, ctx->n_call1) : launch_em(k_em<true, false, true>, l2, ctx->n_call2, cnt + 9, ctx->n_call1);
+			const size_t sm3 = ctx->em_smem, sm2 = ctx->em_smem2;
+			const bool g3 = ctx->em_smem_g, g2 = ctx->em_smem_g2;
+			// quality-value likelihood tasks (two-plane kernel when the batch allows it) ...
+			if (ctx->nobidir) {
+				rc = g2 ? launch_em(k_em<true, false, false, true>, l1, ctx->n_call1, cnt + 3, 0, sm2, true, &ctx->em_grid2)
+				        : launch_em(k_em<false, false, false, true>, l1, ctx->n_call1, cnt + 3, 0, sm2, false, &ctx->em_grid2);
+			} else if (g3) {
+				rc = assoc ? launch_em(k_em<true, true, false, false>, l1, ctx->n_call1, cnt + 3, 0, sm3, true, &ctx->em_grid)
+				           : launch_em(k_em<true, false, false, false>, l1, ctx->n_call1, cnt + 3, 0, sm3, true, &ctx->em_grid);
 			} else {
-				rc = assoc ? launch_em(k_em<false, true, false>, l1, ctx->n_call1, cnt + 3, 0) : launch_em(k_em<false, false, false>, l1, ctx->n_call1, cnt + 3, 0);
-				if (!rc) rc = assoc ? launch_em(k_em<false, true, true>, l2, ctx->n_call2, cnt + 9, ctx->n_call1) : launch_em(k_em<false, false, true>, l2, ctx->n_call2, cnt + 9, ctx->n_call1);
+				rc = assoc ? launch_em(k_em<false, true, false, false>, l1, ctx->n_call1, cnt + 3, 0, sm3, false, &ctx->em_grid)
+				           : launch_em(k_em<false, false, false, false>, l1, ctx->n_call1, cnt + 3, 0, sm3, false, &ctx->em_grid);
+			}
+			// ... then count-based likelihood tasks (always three planes; their AC/QV rows follow the first list's)
+			if (!rc) {
+				if (g3) rc = assoc ? launch_em(k_em<true, true, true, false>, l2, ctx->n_call2, cnt + 9, ctx->n_call1, sm3, true, &ctx->em_grid)
+				                   : launch_em(k_em<true, false, true, false>, l2, ctx->n_call2, cnt + 9, ctx->n_call1, sm3, true, &ctx->em_grid);
+				else rc = assoc ? launch_em(k_em<false, true, true, false>, l2, ctx->n_call2, cnt + 9, ctx->n_call1, sm3, false, &ctx->em_grid)
+				                : launch_em(k_em<false, false, true, false>, l2, ctx->n_call2, cnt + 9, ctx->n_call1, sm3, false, &ctx->em_grid);
 			}
 			if (rc) return rc;
 			launches--;  // the common increment below counts one

@@ -42,8 +42,10 @@ struct EmShared {
 // after the maximum is known.
 
 // tasks[0..n_tasks): the (site, slot) list of this launch; head: its work counter; row0: first AC/QV row of the list
-template <bool SMEM_G, bool ASSOC, bool COUNTLIK>
-__global__ void __maxnreg__(96) k_em(EngineParams prm, const int32_t* __restrict__ tasks, int n_tasks, int32_t* head, int row0)
+// NOBIDIR: the batch has no bidirectional (overlapping-mate) reads and one pool size: the all-reads plane is not stored
+// (it equals forward + reverse - NC), two planes instead of three -> one more CTA per SM (or planes that fit at all)
+template <bool SMEM_G, bool ASSOC, bool COUNTLIK, bool NOBIDIR>
+__global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int32_t* __restrict__ tasks, int n_tasks, int32_t* head, int row0)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const DevBatch& b = prm.b;
@@ -75,11 +77,14 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm, const int32_t* __restrict
 	int32_t* part_i = reinterpret_cast<int32_t*>(smem_raw + off); off += sizeof(int32_t) * 2 * rounds;
 	off = (off + 15) & ~size_t(15);
 	double* mprev = reinterpret_cast<double*>(smem_raw + off); off += sizeof(double) * 3 * P;  // log-sum-exp shift per (plane, pool)
+	double* NCs = reinterpret_cast<double*>(smem_raw + off); off += NOBIDIR ? sizeof(double) * J : 0;  // log10 C(n,j), one pool size
+	off = (off + 15) & ~size_t(15);
 	double* G = SMEM_G ? reinterpret_cast<double*>(smem_raw + off) : prm.gws + (size_t)blockIdx.x * prm.gws_stride;
-	double* Gt = G;
-	double* Gf = G + plane;
-	double* Gr = G + 2 * plane;
+	double* Gt = NOBIDIR ? nullptr : G;
+	double* Gf = NOBIDIR ? G : G + plane;
+	double* Gr = NOBIDIR ? G + plane : G + 2 * plane;
 
+	if (NOBIDIR) for (int j = tid; j < J; j += blockDim.x) NCs[j] = c.NC[j];
 	if (dense) {
 		// batch-constant: dense index of each quality character and the table rows of the present qualities
 		for (int q = tid; q < kNQ; q += blockDim.x) {
@@ -188,7 +193,7 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm, const int32_t* __restrict
 				const double nc = __ldg(c.NC + (size_t)c.pclass[i] * J + j);
 				Gf[idx] = gf + nc;
 				Gr[idx] = gr + nc;
-				Gt[idx] = (gf + gr + gb) + nc;
+				if (!NOBIDIR) Gt[idx] = (gf + gr + gb) + nc;
 				if (j == 0) Gb0[i] = gb;
 			}
 			__syncthreads();
@@ -263,7 +268,7 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm, const int32_t* __restrict
 							const size_t idx = (size_t)j * P + i;
 							Gf[idx] = acc[0][jj] + nc;
 							Gr[idx] = acc[1][jj] + nc;
-							Gt[idx] = (acc[0][jj] + acc[1][jj] + acc[2][jj]) + nc;
+							if (!NOBIDIR) Gt[idx] = (acc[0][jj] + acc[1][jj] + acc[2][jj]) + nc;
 							if (j == 0) Gb0[i] = acc[2][jj];
 						}
 					}
@@ -362,7 +367,7 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm, const int32_t* __restrict
 							const double nc = first ? __ldg(c.NC + (size_t)c.pclass[i] * J + j) : 0.0;
 							Gf[idx] = (first ? nc : Gf[idx]) + a3[0];
 							Gr[idx] = (first ? nc : Gr[idx]) + a3[1];
-							Gt[idx] = (first ? nc : Gt[idx]) + (a3[0] + a3[1] + a3[2]);
+							if (!NOBIDIR) Gt[idx] = (first ? nc : Gt[idx]) + (a3[0] + a3[1] + a3[2]);
 						}
 					}
 					__syncwarp();
@@ -377,7 +382,7 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm, const int32_t* __restrict
 						const double nc = __ldg(ncp + j);
 						Gf[idx] = acc[0][jc] + nc;
 						Gr[idx] = acc[1][jc] + nc;
-						Gt[idx] = (acc[0][jc] + acc[1][jc] + acc[2][jc]) + nc;
+						if (!NOBIDIR) Gt[idx] = (acc[0][jc] + acc[1][jc] + acc[2][jc]) + nc;
 						if (j == 0) Gb0[i] = acc[2][jc];
 					}
 				}
@@ -403,7 +408,10 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm, const int32_t* __restrict
 				const bool act = i < P;
 				const int ii = act ? i : P - 1;
 				const int n = c.ploidy[ii];
-				const double* Hp = G + (size_t)pl * plane + ii;
+				// plane pl as a column of H; with NOBIDIR plane 0 is formed as forward + reverse - NC on the fly
+				const bool sum2 = NOBIDIR && pl == 0;
+				const double* Hp = (NOBIDIR ? (pl == 2 ? Gr : Gf) : G + (size_t)pl * plane) + ii;
+				const double* Hq = Gr + ii;
 				const double l0 = __shfl_sync(0xffffffffu, my_l0, pl), l1 = __shfl_sync(0xffffffffu, my_l1, pl);
 				const double dl = l0 - l1, base = (double)n * l1;
 				// Shift of the log-sum-exp: the exact maximum on the first iteration, afterwards the maximum seen in the
@@ -413,10 +421,11 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm, const int32_t* __restrict
 				if (it == 0 || countlik) {  // count-based planes are rebuilt every iteration: always take the exact maximum
 					m = -1e300;
 					const double* hp = Hp;
+					const double* hq = Hq;
 					double jd = 0.0, vprev = -1e300;
-					for (int j = 0; j <= nmax; j++, hp += P, jd += 1.0) {
+					for (int j = 0; j <= nmax; j++, hp += P, hq += P, jd += 1.0) {
 						const bool in = j <= n;
-						const double v = in ? fma(jd, dl, *hp) : -1e300;
+						const double v = in ? fma(jd, dl, sum2 ? (*hp + *hq) - NCs[j] : *hp) : -1e300;
 						m = fmax(m, v);
 						// H[j] + j*dl is concave in j (unimodal): past the mode nothing larger follows
 						if (unimodal && __all_sync(0xffffffffu, !in || v < vprev)) break;
@@ -427,10 +436,11 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm, const int32_t* __restrict
 				double T00[3] = {0, 0, 0}, T01[3] = {0, 0, 0}, T10[3] = {0, 0, 0}, T11[3] = {0, 0, 0};
 				for (int attempt = 0; attempt < 2; attempt++) {
 					const double* hp = Hp;
+					const double* hq = Hq;
 					double jd = 0.0, vprev = -1e300;
-					for (int j = 0; j <= nmax; j++, hp += P, jd += 1.0) {
+					for (int j = 0; j <= nmax; j++, hp += P, hq += P, jd += 1.0) {
 						const bool in = j <= n;
-						const double v = in ? fma(jd, dl, *hp) : -1e300;
+						const double v = in ? fma(jd, dl, sum2 ? (*hp + *hq) - NCs[j] : *hp) : -1e300;
 						const double d = v - m;
 						newmax = fmax(newmax, v);
 						if (d > -kExpCut2) {
@@ -466,7 +476,7 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm, const int32_t* __restrict
 				if (act) {
 					llc = L;
 					pn = Wj / S;
-					if (pl == 0) nul = Gt[ii];
+					if (pl == 0) nul = NOBIDIR ? Gf[ii] + Gr[ii] : Gt[ii];  // GENLL[i][0] (NC[0] = 0)
 					else if (pl == 1) llc += Gr[ii] + Gb0[ii];   // LLtotalf += GENLLr[i][0] + GENLLb[i][0]  (:262)
 					else llc += Gf[ii] + Gb0[ii];                // LLtotalr += GENLLf[i][0] + GENLLb[i][0]  (:261)
 				}
@@ -551,15 +561,17 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm, const int32_t* __restrict
 				const bool act = i < P;
 				const int ii = act ? i : P - 1;
 				const int n = c.ploidy[ii];
-				const double* Hp = Gt + ii;
+				const double* Hp = (NOBIDIR ? Gf : Gt) + ii;
+				const double* Hq = Gr + ii;
 				const double dl = l0 - l1, base = (double)n * l1;
 				double best = -100000, second = -100000;
 				int bg = 0;
 				{
 					const double* hp = Hp;
+					const double* hq = Hq;
 					double jd = 0.0;
-					for (int j = 0; j <= n; j++, hp += P, jd += 1.0) {
-						const double t = fma(jd, dl, *hp) + base;
+					for (int j = 0; j <= n; j++, hp += P, hq += P, jd += 1.0) {
+						const double t = fma(jd, dl, NOBIDIR ? (*hp + *hq) - NCs[j] : *hp) + base;
 						if (t > best) { second = best; bg = j; best = t; }
 						else if (t > second) second = t;
 					}
@@ -568,20 +580,23 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm, const int32_t* __restrict
 				double S = 0.0;
 				{
 					const double* hp = Hp;
+					const double* hq = Hq;
 					double jd = 0.0;
-					for (int j = 0; j <= n; j++, hp += P, jd += 1.0) {
-						const double d = fma(jd, dl, *hp) + base - best;
+					for (int j = 0; j <= n; j++, hp += P, hq += P, jd += 1.0) {
+						const double d = fma(jd, dl, NOBIDIR ? (*hp + *hq) - NCs[j] : *hp) + base - best;
 						if (d > -kExpCut) S += exp10_lse(d);
 					}
 				}
 				const double Lb = best + log10(S);
 				{
 					const double* hp = Hp;
+					const double* hq = Hq;
 					double jd = 0.0;
-					for (int j = 0; j <= nmax; j++, hp += P, jd += 1.0) {
+					for (int j = 0; j <= nmax; j++, hp += P, hq += P, jd += 1.0) {
 						double v = 0.0;
 						if (act && j <= n) {
-							const double d = fma(jd, dl, *hp) + base - Lb;
+							// (NOBIDIR: the forward value is read here before this lane overwrites it with the posterior)
+							const double d = fma(jd, dl, NOBIDIR ? (*hp + *hq) - NCs[j] : *hp) + base - Lb;
 							if (d > -kExpCut - 3) v = exp10_lse(d);
 						}
 						if (act) post[(size_t)j * P + ii] = v;
@@ -612,7 +627,7 @@ __global__ void __maxnreg__(96) k_em(EngineParams prm, const int32_t* __restrict
 				}
 			}
 			// ---- calculate_LRstatistic (crisp/LRstatistic.c:48-69), --phenotypes only: five EMs restricted to pool subsets ----
-			if (ASSOC && c.association && pfin >= 0.0001 && delta >= 3) {
+			if (ASSOC && !NOBIDIR && c.association && pfin >= 0.0001 && delta >= 3) {
 				__syncthreads();  // HWE above still reads the posterior plane
 				for (int k = 0; k < 3; k++) { E01[k] = EL01[k]; E10[k] = EL10[k]; }
 				const int flags[5] = {7, 1, 6, 4, 5};

@@ -290,18 +290,25 @@ __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_evaluate(Eng
 __global__ void k_qualmap(const uint16_t* __restrict__ reads, size_t n_reads, int32_t* counters)
 {
 	__shared__ unsigned char seen[kNQ];  // one flag per quality character; racing stores all write 1
+	int bidir = 0;
 	for (int q = threadIdx.x; q < kNQ; q += blockDim.x) seen[q] = 0;
 	__syncthreads();
 	const size_t nvec = n_reads / 8;
 	const uint4* v = reinterpret_cast<const uint4*>(reads);
 	for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nvec; k += (size_t)gridDim.x * blockDim.x) {
 		const uint4 x = __ldg(v + k);
+		if ((x.x | x.y | x.z | x.w) & 0x08000800u) bidir = 1;  // bit 11 of either half: a bidirectional read
 		seen[x.x & 0x7f] = 1; seen[(x.x >> 16) & 0x7f] = 1;
 		seen[x.y & 0x7f] = 1; seen[(x.y >> 16) & 0x7f] = 1;
 		seen[x.z & 0x7f] = 1; seen[(x.z >> 16) & 0x7f] = 1;
 		seen[x.w & 0x7f] = 1; seen[(x.w >> 16) & 0x7f] = 1;
 	}
-	if (blockIdx.x == 0 && threadIdx.x < (int)(n_reads - nvec * 8)) seen[reads[nvec * 8 + threadIdx.x] & 0x7f] = 1;
+	if (blockIdx.x == 0 && threadIdx.x < (int)(n_reads - nvec * 8)) {
+		const uint32_t w = reads[nvec * 8 + threadIdx.x];
+		seen[w & 0x7f] = 1;
+		if (w & 0x800u) bidir = 1;
+	}
+	if (__any_sync(0xffffffffu, bidir) && (threadIdx.x & 31) == 0) atomicOr(reinterpret_cast<unsigned int*>(counters) + 10, 1u);
 	__syncthreads();
 	for (int q = threadIdx.x; q < kNQ; q += blockDim.x)
 		if (seen[q]) atomicOr(reinterpret_cast<unsigned int*>(counters) + 4 + (q >> 5), 1u << (q & 31));
