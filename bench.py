@@ -139,7 +139,20 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
+def emit(line: dict) -> None:
+    """Write the one JSON line to the real stdout (everything else — NCCL banners, make, warnings — goes to stderr)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    # keep stdout clean for the single JSON line: libraries that print to fd 1 are routed to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -180,7 +193,7 @@ def main():
                 "cpu_baseline": {"value": value, "unit": "sites/s", "cores": cores, "kind": kind,
                                  "sample": f"{cores} processes x {args.cpu_sites_per_core} sites of the workload, one contiguous region each (the reference's --regions parallelism); sites/s = sites / slowest process"},
                 "e2e": {"value": value, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -326,7 +339,7 @@ def main():
             v, sites, busy, wall, kind = run_reference_sample(wl, batch, cores, args.cpu_sites_per_core)
             line["cpu_baseline"] = {"value": v, "unit": "sites/s", "cores": cores, "kind": kind,
                                     "sample": f"{sites} sites of the same batch, {cores} processes x {args.cpu_sites_per_core} sites (contiguous regions), {busy:.1f} s busy"}
-        print(json.dumps(line))
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
