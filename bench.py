@@ -35,6 +35,9 @@ WORKLOADS = {
     "c3_100x96": dict(P=100, ploidy=96, depth=60, options={}, synth=dict(variant_frac=0.15)),
     "c4_perm_stress": dict(P=50, ploidy=48, depth=200, options=dict(chisq_permutation=1, max_iter=1000000), synth=dict(variant_frac=0.8, rare=True)),
     "c5_500x10": dict(P=500, ploidy=10, depth=10, options={}, synth=dict(variant_frac=0.15)),
+    # config 5 with the permutation test on: pool size 10 dispatches to the stranded test, pool size 2 to lowcovFET
+    "c5_500x10_perm": dict(P=500, ploidy=10, depth=10, options=dict(chisq_permutation=1, max_iter=20000), synth=dict(variant_frac=0.3)),
+    "c5p_500x2_lowcov": dict(P=500, ploidy=2, depth=10, options=dict(chisq_permutation=1, max_iter=20000), synth=dict(variant_frac=0.5)),
 }
 
 

@@ -397,8 +397,8 @@ int run_stage1(crispgpu_ctx* ctx)
 			// head: first 1024 permutations of every task; tasks still undecided go to the chunked tail
 			PermTail tail{};
 			rc = ensure_dev(ctx, ctx->d_tail_task, (size_t)n * 5 * 4); if (rc) return rc;
-			rc = ensure_dev(ctx, ctx->d_tail_head, (size_t)n * 5 * 4); if (rc) return rc;
-			rc = ensure_dev(ctx, ctx->d_tail_total, (size_t)n * 5 * 4); if (rc) return rc;
+			rc = ensure_dev(ctx, ctx->d_tail_head, (size_t)n * 5 * 8); if (rc) return rc;
+			rc = ensure_dev(ctx, ctx->d_tail_total, (size_t)n * 5 * 8); if (rc) return rc;
 			rc = ensure_dev(ctx, ctx->d_tail_counters, 4 * 4); if (rc) return rc;
 			CK(cudaMemsetAsync(ctx->d_tail_counters.p, 0, 4 * 4, ctx->stream));
 			tail.task = static_cast<int32_t*>(ctx->d_tail_task.p);
@@ -428,8 +428,48 @@ int run_stage1(crispgpu_ctx* ctx)
 				}
 			}
 		} else {
-			if (!ctx->pm_grid) { rc = occupancy_grid(ctx, k_permute_lowcov, ctx->pm_threads, ctx->pm_smem, &ctx->pm_grid); if (rc) return rc; }
-			k_permute_lowcov<<<ctx->pm_grid, ctx->pm_threads, ctx->pm_smem, ctx->stream>>>(prm);
+			const size_t low_smem = ctx->pm_smem + (size_t)((ctx->P + 31) / 32) * ctx->pm_threads * 4;  // + the touched-pool bitmaps
+			if (low_smem > ctx->smem_optin) {
+				snprintf(ctx->err, sizeof ctx->err, "low-coverage permutation test: %d pools exceed the shared-memory layout", ctx->P);
+				return CRISPGPU_ERR_UNSUPPORTED;
+			}
+			if (!ctx->pm_grid) {
+				rc = occupancy_grid(ctx, k_permute_lowcov, ctx->pm_threads, low_smem, &ctx->pm_grid); if (rc) return rc;
+				int g2 = 0;
+				rc = occupancy_grid(ctx, k_permute_lowcov_tail, ctx->pm_threads, low_smem, &g2); if (rc) return rc;
+				if (g2 < ctx->pm_grid) ctx->pm_grid = g2;
+			}
+			PermTail tail{};
+			rc = ensure_dev(ctx, ctx->d_tail_task, (size_t)n * 5 * 4); if (rc) return rc;
+			rc = ensure_dev(ctx, ctx->d_tail_head, (size_t)n * 5 * 8); if (rc) return rc;
+			rc = ensure_dev(ctx, ctx->d_tail_total, (size_t)n * 5 * 8); if (rc) return rc;
+			rc = ensure_dev(ctx, ctx->d_tail_counters, 4 * 4); if (rc) return rc;
+			CK(cudaMemsetAsync(ctx->d_tail_counters.p, 0, 4 * 4, ctx->stream));
+			tail.task = static_cast<int32_t*>(ctx->d_tail_task.p);
+			tail.hits_head = static_cast<int32_t*>(ctx->d_tail_head.p);
+			tail.total = static_cast<int32_t*>(ctx->d_tail_total.p);
+			tail.counters = static_cast<int32_t*>(ctx->d_tail_counters.p);
+			k_permute_lowcov<<<ctx->pm_grid, ctx->pm_threads, low_smem, ctx->stream>>>(prm, tail);
+			CK(cudaGetLastError());
+			if (g.max_iter > kPermHead) {
+				int32_t* hc2 = static_cast<int32_t*>(ctx->h_counters.p) + 12;
+				CK(cudaMemcpyAsync(hc2, ctx->d_tail_counters.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+				CK(cudaStreamSynchronize(ctx->stream));
+				const int n_tail = hc2[0];
+				if (n_tail > 0) {
+					const int T = ctx->pm_threads, rem = g.max_iter - kPermHead;
+					int chunk = ((rem + 255) / 256 + T - 1) / T * T;
+					if (chunk < 4 * T) chunk = 4 * T;
+					tail.chunk = chunk;
+					tail.nchunks = (rem + chunk - 1) / chunk;
+					rc = ensure_dev(ctx, ctx->d_tail_rec, (size_t)n_tail * tail.nchunks * kLowRec * 4); if (rc) return rc;
+					tail.rec = static_cast<int32_t*>(ctx->d_tail_rec.p);
+					k_permute_lowcov_tail<<<ctx->pm_grid, ctx->pm_threads, low_smem, ctx->stream>>>(prm, tail);
+					CK(cudaGetLastError());
+					k_permute_lowcov_resolve<<<(n_tail + 127) / 128, 128, 0, ctx->stream>>>(prm, tail);
+					launches += 2;
+				}
+			}
 		}
 		launches++;
 		CK(cudaGetLastError());

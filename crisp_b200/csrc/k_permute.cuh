@@ -330,23 +330,137 @@ __device__ __forceinline__ double ncr_lookup(const double* tab, int n, int r)
 	return d_ncr(n, r);
 }
 
-// pvalue_lowcoverage: three strata (forward, reverse, bidirectional), statistic = sum over pools with balls of
-// log10 C(N_i, r_i) summed in pool order, two-sided counters without epsilon, stop rule of lowcovFET.c:135.
-__global__ void k_permute_lowcov(EngineParams prm)
+// ---- low-coverage test (pvalue_lowcoverage, FET/lowcovFET.c:23-149) -----------------------------------------------
+// Three strata (forward, reverse, bidirectional); statistic = sum over pools that received balls of log10 C(N_i, r_i),
+// summed in pool order; two-sided counters without epsilon (:132-133); stop rule of :135.
+struct LowcovView {
+	PermShared* sh;
+	uint32_t* cum;    // [3][P+1]
+	int32_t* Ntot;    // [P]
+	int32_t* alt;     // [3][P]
+	double* terms;    // [P]
+	uint32_t* touched;  // [ceil(P/32)][T] bitmap of pools holding balls in the current permutation
+	uint32_t* occ;      // [P][T]: 3 x 10-bit ball counts (f, r, b); all zero between permutations
+	int words;
+};
+
+__device__ __forceinline__ LowcovView lowcov_view(unsigned char* smem_raw, int P, int T)
 {
-	extern __shared__ __align__(16) unsigned char smem_raw[];
+	LowcovView v;
+	v.sh = reinterpret_cast<PermShared*>(smem_raw);
+	size_t off = (sizeof(PermShared) + 15) & ~size_t(15);
+	v.cum = reinterpret_cast<uint32_t*>(smem_raw + off); off += sizeof(uint32_t) * 3 * (P + 1);
+	v.Ntot = reinterpret_cast<int32_t*>(smem_raw + off); off += sizeof(int32_t) * P;
+	v.alt = reinterpret_cast<int32_t*>(smem_raw + off); off += sizeof(int32_t) * 3 * P;
+	off = (off + 15) & ~size_t(15);
+	v.terms = reinterpret_cast<double*>(smem_raw + off); off += sizeof(double) * P;
+	v.words = (P + 31) >> 5;
+	v.touched = reinterpret_cast<uint32_t*>(smem_raw + off); off += sizeof(uint32_t) * v.words * T;
+	v.occ = reinterpret_cast<uint32_t*>(smem_raw + off);
+	return v;
+}
+
+// Block-wide set-up; returns false (after writing the result) when the table has fewer than two alt reads (:42).
+__device__ inline bool lowcov_setup(const EngineParams& prm, const LowcovView& v, int o)
+{
 	const DevBatch& b = prm.b;
 	const DevCfg& c = prm.c;
 	const int P = c.P, T = blockDim.x, tid = threadIdx.x;
-	PermShared* sh = reinterpret_cast<PermShared*>(smem_raw);
-	size_t off = (sizeof(PermShared) + 15) & ~size_t(15);
-	uint32_t* cum = reinterpret_cast<uint32_t*>(smem_raw + off); off += sizeof(uint32_t) * 3 * (P + 1);
-	int32_t* Ntot = reinterpret_cast<int32_t*>(smem_raw + off); off += sizeof(int32_t) * P;
-	int32_t* alt = reinterpret_cast<int32_t*>(smem_raw + off); off += sizeof(int32_t) * 3 * P;
-	off = (off + 15) & ~size_t(15);
-	double* terms = reinterpret_cast<double*>(smem_raw + off); off += sizeof(double) * P;
-	uint32_t* occ = reinterpret_cast<uint32_t*>(smem_raw + off);  // [P][T]: 3 x 10-bit ball counts (f, r, b)
+	const int s = o / kSlots, slot = o - s * kSlots;
+	int a1, a2, a3;
+	slot_alleles(b.maxvec_al + s * 8, slot, a1, a2, a3);
+	const int refbase = b.refbase[s];
+	const int row = slot_amb_row(b, s, slot, a2, a3);
+	const int altal = (a1 == refbase || a2 != refbase) ? a2 : a1;
+	for (int i = tid; i < P; i += T) {
+		const int32_t* r = b.indcounts + ((size_t)s * P + i) * kNC;
+		int dd[3] = {0, 0, 0};
+		if (row >= 0) { const int32_t* d = b.amb_dec + ((size_t)row * P + i) * 4; dd[0] = d[0]; dd[1] = d[1]; dd[2] = d[2] + d[3]; }
+		const int nref3 = (a1 == refbase) + (a2 == refbase) + (a3 == refbase), nref2 = (a1 == refbase) + (a2 == refbase);
+		const int n0 = r[a1] + r[a2] + r[a3] - nref3 * dd[0], n1 = r[a1 + 8] + r[a2 + 8] + r[a3 + 8] - nref3 * dd[1];
+		const int n2 = r[a1 + 16] + r[a2 + 16] - nref2 * dd[2];  // bidirectional column excludes allele3 (allelecounts.c:228)
+		v.cum[0 * (P + 1) + i + 1] = n0; v.cum[1 * (P + 1) + i + 1] = n1; v.cum[2 * (P + 1) + i + 1] = n2;
+		v.Ntot[i] = n0 + n1 + n2;
+		for (int k = 0; k < 3; k++) v.alt[k * P + i] = r[altal + 8 * k] - (altal == refbase ? dd[k] : 0);
+		const int R = v.alt[i] + v.alt[P + i] + v.alt[2 * P + i];
+		v.terms[i] = R > 0 ? ncr_lookup(c.ncr_tab, n0 + n1 + n2, R) : 0.0;
+	}
+	for (int k = tid; k < P * T; k += T) v.occ[k] = 0;
+	for (int k = tid; k < v.words * T; k += T) v.touched[k] = 0;
+	__syncthreads();
+	if (tid == 0) {
+		double clra = 0.0;
+		for (int k = 0; k < 3; k++) {
+			uint32_t cc = 0; int on = 0;
+			v.cum[k * (P + 1)] = 0;
+			for (int i = 0; i < P; i++) { cc += v.cum[k * (P + 1) + i + 1]; v.cum[k * (P + 1) + i + 1] = cc; on += v.alt[k * P + i]; }
+			v.sh->tot[k] = (int)cc; v.sh->ones[k] = on;
+		}
+		for (int i = 0; i < P; i++) if (v.alt[i] + v.alt[P + i] + v.alt[2 * P + i] > 0) clra += v.terms[i];
+		v.sh->clra = clra;
+	}
+	__syncthreads();
+	if (v.sh->ones[0] + v.sh->ones[1] + v.sh->ones[2] < 2) {
+		if (tid == 0) { prm.o.ctpval[o] = 0.0; prm.o.perm_k[o] = 0; prm.o.perm_hits[o] = 0; }
+		return false;
+	}
+	return true;
+}
 
+// One permutation: bit 0 = statistic <= observed, bit 1 = statistic >= observed.  Work is proportional to the number of
+// balls: pools that received balls are tracked in a bitmap, walked in ascending pool order and cleared on the way.
+__device__ __forceinline__ int lowcov_hit(const EngineParams& prm, const LowcovView& v, int s, int slot, uint32_t k)
+{
+	const int P = prm.c.P, T = blockDim.x;
+	uint32_t* myocc = v.occ + threadIdx.x;
+	uint32_t* mybits = v.touched + threadIdx.x;
+	for (int st = 0; st < 3; st++) {
+		Philox rng;
+		rng.init(prm.c.rng_seed, prm.b.tid[s], prm.b.pos[s], slot, k, (uint32_t)st);
+		const int sft = 10 * st;
+		place_balls(rng, v.cum + st * (P + 1), P, (uint32_t)v.sh->tot[st], v.sh->ones[st],
+			[&](int i) { return (myocc[(size_t)i * T] >> sft) & 0x3ffu; },
+			[&](int i) {
+				myocc[(size_t)i * T] += 1u << sft;
+				mybits[(size_t)(i >> 5) * T] |= 1u << (i & 31);
+			});
+	}
+	double stat = 0.0;
+	for (int w = 0; w < v.words; w++) {
+		uint32_t bits = mybits[(size_t)w * T];
+		if (!bits) continue;
+		mybits[(size_t)w * T] = 0;
+		while (bits) {
+			const int i = (w << 5) + __ffs(bits) - 1;
+			bits &= bits - 1;
+			const uint32_t x = myocc[(size_t)i * T];
+			myocc[(size_t)i * T] = 0;
+			const int r = (int)(x & 0x3ffu) + (int)((x >> 10) & 0x3ffu) + (int)((x >> 20) & 0x3ffu);
+			stat += ncr_lookup(prm.c.ncr_tab, v.Ntot[i], r);
+		}
+	}
+	const double clra = v.sh->clra;
+	return (stat <= clra ? 1 : 0) | (stat >= clra ? 2 : 0);
+}
+
+__device__ __forceinline__ void lowcov_store(const EngineParams& prm, int o, int kk, int lo, int hi)
+{
+	const int use = hi < lo ? hi : lo;  // lowcovFET.c:139-144
+	prm.o.ctpval[o] = log10((double)use + 1) - log10((double)(kk + 1));
+	prm.o.perm_k[o] = kk;
+	prm.o.perm_hits[o] = use;
+}
+
+constexpr int kLowRec = 24;  // ints per chunk record: [0] lo hits, [1] hi hits, [2] skipped, [3] pad, [4..13] first ten lo indices, [14..23] hi
+
+// Head: the first kPermHead permutations of every task with the sequential stop rule (covers its k <= 100 clause).
+__global__ void k_permute_lowcov(EngineParams prm, PermTail tail)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const DevCfg& c = prm.c;
+	const int T = blockDim.x, tid = threadIdx.x;
+	const LowcovView v = lowcov_view(smem_raw, c.P, T);
+	PermShared* sh = v.sh;
 	for (;;) {
 		__syncthreads();
 		if (tid == 0) sh->task = atomicAdd(prm.q.counters + 2, 1);
@@ -354,73 +468,17 @@ __global__ void k_permute_lowcov(EngineParams prm)
 		const int task = sh->task;
 		if (task >= prm.q.counters[0]) break;
 		const int o = prm.q.perm_tasks[task], s = o / kSlots, slot = o - s * kSlots;
-		int a1, a2, a3;
-		slot_alleles(b.maxvec_al + s * 8, slot, a1, a2, a3);
-		const int refbase = b.refbase[s];
-		const int row = slot_amb_row(b, s, slot, a2, a3);
-		const int altal = (a1 == refbase || a2 != refbase) ? a2 : a1;
-		for (int i = tid; i < P; i += T) {
-			const int32_t* r = b.indcounts + ((size_t)s * P + i) * kNC;
-			int dd[3] = {0, 0, 0};
-			if (row >= 0) { const int32_t* d = b.amb_dec + ((size_t)row * P + i) * 4; dd[0] = d[0]; dd[1] = d[1]; dd[2] = d[2] + d[3]; }
-			const int nref3 = (a1 == refbase) + (a2 == refbase) + (a3 == refbase), nref2 = (a1 == refbase) + (a2 == refbase);
-			const int n0 = r[a1] + r[a2] + r[a3] - nref3 * dd[0], n1 = r[a1 + 8] + r[a2 + 8] + r[a3 + 8] - nref3 * dd[1];
-			const int n2 = r[a1 + 16] + r[a2 + 16] - nref2 * dd[2];  // bidirectional column excludes allele3 (allelecounts.c:228)
-			cum[0 * (P + 1) + i + 1] = n0; cum[1 * (P + 1) + i + 1] = n1; cum[2 * (P + 1) + i + 1] = n2;
-			Ntot[i] = n0 + n1 + n2;
-			for (int k = 0; k < 3; k++) alt[k * P + i] = r[altal + 8 * k] - (altal == refbase ? dd[k] : 0);
-			const int R = alt[i] + alt[P + i] + alt[2 * P + i];
-			terms[i] = R > 0 ? ncr_lookup(c.ncr_tab, n0 + n1 + n2, R) : 0.0;
-		}
-		__syncthreads();
-		if (tid == 0) {
-			double clra = 0.0;
-			for (int k = 0; k < 3; k++) {
-				uint32_t cc = 0; int on = 0;
-				cum[k * (P + 1)] = 0;
-				for (int i = 0; i < P; i++) { cc += cum[k * (P + 1) + i + 1]; cum[k * (P + 1) + i + 1] = cc; on += alt[k * P + i]; }
-				sh->tot[k] = (int)cc; sh->ones[k] = on;
-			}
-			for (int i = 0; i < P; i++) if (alt[i] + alt[P + i] + alt[2 * P + i] > 0) clra += terms[i];
-			sh->clra = clra;
-			sh->stop_k = 0;
-		}
-		__syncthreads();
-		const int tot_ones = sh->ones[0] + sh->ones[1] + sh->ones[2];
-		if (tot_ones < 2) {  // lowcovFET.c:42
-			if (tid == 0) { prm.o.ctpval[o] = 0.0; prm.o.perm_k[o] = 0; prm.o.perm_hits[o] = 0; }
-			continue;
-		}
-		const double clra = sh->clra;
+		if (!lowcov_setup(prm, v, o)) continue;
 		const int maxiter = c.max_iter;
-		uint32_t* myocc = occ + tid;
+		const int head = maxiter < kPermHead ? maxiter : kPermHead;
 		int lo_before = 0, hi_before = 0, stop_k = 0, stop_lo = 0, stop_hi = 0;
-		for (int base = 0; base < maxiter; base += T) {
+		for (int base = 0; base < head; base += T) {
 			const int k = base + tid + 1;
-			int flo = 0, fhi = 0;
-			if (k <= maxiter) {
-				for (int i = 0; i < P; i++) myocc[(size_t)i * T] = 0;
-				for (int st = 0; st < 3; st++) {
-					Philox rng;
-					rng.init(c.rng_seed, b.tid[s], b.pos[s], slot, (uint32_t)k, (uint32_t)st);
-					const int sft = 10 * st;
-					place_balls(rng, cum + st * (P + 1), P, (uint32_t)sh->tot[st], sh->ones[st],
-						[&](int i) { return (myocc[(size_t)i * T] >> sft) & 0x3ffu; },
-						[&](int i) { myocc[(size_t)i * T] += 1u << sft; });
-				}
-				double stat = 0.0;
-				for (int i = 0; i < P; i++) {
-					const uint32_t v = myocc[(size_t)i * T];
-					const int r = (int)(v & 0x3ffu) + (int)((v >> 10) & 0x3ffu) + (int)((v >> 20) & 0x3ffu);
-					if (r > 0) stat += ncr_lookup(c.ncr_tab, Ntot[i], r);
-				}
-				flo = stat <= clra ? 1 : 0;
-				fhi = stat >= clra ? 1 : 0;
-			}
+			const int f = k <= head ? lowcov_hit(prm, v, s, slot, (uint32_t)k) : 0;
 			int tl, th;
-			const int Hlo = lo_before + block_prefix(flo, sh->warp_hits, tl);
-			const int Hhi = hi_before + block_prefix(fhi, sh->warp_hits2, th);
-			const bool stop = k <= maxiter && ((Hlo >= 10 && Hhi >= 10) || (k <= 100 && Hlo >= 5 && Hhi >= 5));
+			const int Hlo = lo_before + block_prefix(f & 1, sh->warp_hits, tl);
+			const int Hhi = hi_before + block_prefix((f >> 1) & 1, sh->warp_hits2, th);
+			const bool stop = k <= head && ((Hlo >= 10 && Hhi >= 10) || (k <= 100 && Hlo >= 5 && Hhi >= 5));
 			const unsigned sb = __ballot_sync(0xffffffffu, stop);
 			if ((tid & 31) == 0) sh->warp_first[tid >> 5] = sb ? (__ffs(sb) - 1) : -1;
 			__syncthreads();
@@ -437,12 +495,96 @@ __global__ void k_permute_lowcov(EngineParams prm)
 			__syncthreads();
 		}
 		if (tid == 0) {
-			int kk = stop_k, l = stop_lo, h = stop_hi;
-			if (kk == 0) { kk = maxiter + 1; l = lo_before; h = hi_before; }
-			const int use = h < l ? h : l;  // lowcovFET.c:139-144
-			prm.o.ctpval[o] = log10((double)use + 1) - log10((double)(kk + 1));
-			prm.o.perm_k[o] = kk;
-			prm.o.perm_hits[o] = use;
+			if (stop_k > 0) lowcov_store(prm, o, stop_k, stop_lo, stop_hi);
+			else if (maxiter <= head) lowcov_store(prm, o, maxiter + 1, lo_before, hi_before);
+			else {
+				const int h = atomicAdd(tail.counters + 0, 1);
+				tail.task[h] = o;
+				tail.hits_head[2 * h] = lo_before;
+				tail.hits_head[2 * h + 1] = hi_before;
+				tail.total[2 * h] = lo_before;
+				tail.total[2 * h + 1] = hi_before;
+			}
+		}
+	}
+}
+
+// Tail: (chunk, task) items chunk-major; a chunk is skipped once both counters are known to have reached ten.
+__global__ void k_permute_lowcov_tail(EngineParams prm, PermTail tail)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const DevCfg& c = prm.c;
+	const int T = blockDim.x, tid = threadIdx.x;
+	const LowcovView v = lowcov_view(smem_raw, c.P, T);
+	PermShared* sh = v.sh;
+	const int ntask = tail.counters[0];
+	const long long nitems = (long long)ntask * tail.nchunks;
+	__shared__ int firsts[20];
+	for (;;) {
+		__syncthreads();
+		if (tid == 0) sh->task = atomicAdd(tail.counters + 1, 1);
+		__syncthreads();
+		const int item = sh->task;
+		if (item >= nitems) break;
+		const int chunk = item / ntask, h = item - chunk * ntask;
+		int32_t* rec = tail.rec + ((size_t)h * tail.nchunks + chunk) * kLowRec;
+		const int kbeg = kPermHead + chunk * tail.chunk, kend = min(c.max_iter, kbeg + tail.chunk);
+		const volatile int32_t* tot = tail.total + 2 * h;
+		if (kbeg >= c.max_iter || (tot[0] >= 10 && tot[1] >= 10)) {
+			if (tid == 0) { rec[0] = 0; rec[1] = 0; rec[2] = 1; }
+			continue;
+		}
+		const int o = tail.task[h], s = o / kSlots, slot = o - s * kSlots;
+		lowcov_setup(prm, v, o);  // cannot fail: the head already accepted the table
+		int flo = 0, fhi = 0;
+		for (int base = kbeg; base < kend; base += T) {
+			const int k = base + tid + 1;
+			const int f = k <= kend ? lowcov_hit(prm, v, s, slot, (uint32_t)k) : 0;
+			int tl, th;
+			const int ilo = flo + block_prefix(f & 1, sh->warp_hits, tl);
+			const int ihi = fhi + block_prefix((f >> 1) & 1, sh->warp_hits2, th);
+			if ((f & 1) && ilo <= 10) firsts[ilo - 1] = k;
+			if ((f & 2) && ihi <= 10) firsts[10 + ihi - 1] = k;
+			flo += tl;
+			fhi += th;
+			__syncthreads();
+		}
+		if (tid == 0) {
+			rec[0] = flo; rec[1] = fhi; rec[2] = 0;
+			for (int q = 0; q < 10 && q < flo; q++) rec[4 + q] = firsts[q];
+			for (int q = 0; q < 10 && q < fhi; q++) rec[14 + q] = firsts[10 + q];
+			atomicAdd(tail.total + 2 * h, flo);
+			atomicAdd(tail.total + 2 * h + 1, fhi);
+		}
+	}
+}
+
+// Resolve: the loop of lowcovFET.c:73-137 breaks at the first k where both counters have reached ten, i.e. at the later of
+// the two tenth hits; the smaller counter is then exactly ten (:139-144).
+__global__ void k_permute_lowcov_resolve(EngineParams prm, PermTail tail)
+{
+	const int ntask = tail.counters[0];
+	for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < ntask; h += gridDim.x * blockDim.x) {
+		int lo = tail.hits_head[2 * h], hi = tail.hits_head[2 * h + 1], klo = lo >= 10 ? kPermHead : 0, khi = hi >= 10 ? kPermHead : 0;
+		for (int ch = 0; ch < tail.nchunks && !(klo && khi); ch++) {
+			const int32_t* rec = tail.rec + ((size_t)h * tail.nchunks + ch) * kLowRec;
+			if (rec[2]) break;
+			for (int q = 0; q < rec[0] && q < 10 && !klo; q++) if (++lo >= 10) klo = rec[4 + q];
+			if (!klo && rec[0] > 10) lo += rec[0] - 10;
+			for (int q = 0; q < rec[1] && q < 10 && !khi; q++) if (++hi >= 10) khi = rec[14 + q];
+			if (!khi && rec[1] > 10) hi += rec[1] - 10;
+		}
+		if (klo && khi) lowcov_store(prm, tail.task[h], klo > khi ? klo : khi, 10, 10);
+		else {
+			// ran out of permutations: totals over all chunks
+			int tlo = tail.hits_head[2 * h], thi = tail.hits_head[2 * h + 1];
+			for (int ch = 0; ch < tail.nchunks; ch++) {
+				const int32_t* rec = tail.rec + ((size_t)h * tail.nchunks + ch) * kLowRec;
+				if (rec[2]) break;
+				tlo += rec[0];
+				thi += rec[1];
+			}
+			lowcov_store(prm, tail.task[h], prm.c.max_iter + 1, tlo, thi);
 		}
 	}
 }

@@ -266,3 +266,31 @@ def test_benchmark_shape_properties():
     assert int(again.status.astype(np.int64).sum() * 31 + again.allelecount.sum()) == int(base.status.astype(np.int64).sum() * 31 + base.allelecount.sum())
     assert np.array_equal(again.delta, base.delta)
     eng.close()
+
+
+def test_abi_error_paths():
+    """Misuse of the C ABI is reported through status codes and crispgpu_last_error, never by crashing."""
+    import ctypes as C
+    from crisp_b200.abi import CResults
+    from crisp_b200.engine import EngineError
+    cfg = _cfg(6, 20, {})
+    eng = Engine(cfg)
+    batch = synth_batch(40, 6, 20, 60, seed=5, variant_frac=0.5)
+    with pytest.raises(EngineError):
+        eng.run_resident()              # nothing uploaded
+    t = eng.submit(batch)
+    with pytest.raises(EngineError):
+        eng.submit(batch)               # one batch in flight per context
+    with pytest.raises(EngineError):
+        eng.wait(t + 7)                 # unknown ticket
+    res = eng.wait(t)
+    assert res.n_sites == batch.n_sites
+    with pytest.raises(EngineError):
+        eng.wait(t)                     # already consumed
+    cres = CResults()
+    assert eng.lib.crispgpu_wait(None, 0, C.byref(cres)) == -1
+    assert b"" == eng.lib.crispgpu_last_error(eng.h)[:0]
+    # the context is still usable after the errors
+    again = eng.run(batch)
+    compare_results(again, res, tol=0.0, label="after-errors")
+    eng.close()
