@@ -1,7 +1,7 @@
-// k_permute.cuh — Monte-Carlo contingency-table p-values: one CTA per (site, slot) task, one thread per permutation.
+// k_permute.cuh — Monte-Carlo contingency-table p-values, one thread per permutation.
 //
-//   k_permute_stranded   pvalue_contable_iter_stranded  FET/contables.c:261-339  (pool size > 2)
-//   k_permute_lowcov     pvalue_lowcoverage             FET/lowcovFET.c:23-149   (pool size == 2)
+//   k_permute_stranded (+ _tail, _resolve)   pvalue_contable_iter_stranded  FET/contables.c:261-339  (pool size > 2)
+//   k_permute_lowcov   (+ _tail, _resolve)   pvalue_lowcoverage             FET/lowcovFET.c:23-149   (pool size == 2)
 //
 // Null law: the alt reads of each strand are placed without replacement among that strand's read slots
 // (multivariate hypergeometric per strand, strands independent).  The reference shuffles a slot->pool index with
@@ -9,8 +9,14 @@
 // (k, block, stratum), so the result does not depend on batching, grid size or GPU count.  A ball is placed by
 // drawing a uniform slot, finding its pool in the shared-memory cumulative marginals, and rejecting the draw when it
 // lands on one of the pool's already-occupied slots (slots of a pool are exchangeable).  The reference's sequential
-// stopping rule (hits >= 10, or >= 5 within the first 1000 permutations) is evaluated on the prefix sums of the
-// hit flags in permutation order, so the reported (hits, k) is exactly what a serial run of the same streams gives.
+// stopping rule is evaluated on the prefix sums of the hit flags in permutation order, so the reported (hits, k) is
+// exactly what a serial run of the same streams gives.
+//
+// Head kernel: one CTA per task, the first 1024 permutations (decides every non-significant table and covers the
+// early clauses of the stop rules).  Tail kernel: undecided tasks are cut into <= 256 chunks processed as
+// (chunk, task) work items, chunk-major, each recording its hit counts and first ten hit indices; a chunk is skipped
+// once the break condition is known to have been met in earlier chunks.  Resolve kernel: walks the records in
+// permutation order to the break index.
 #pragma once
 #include "dmath.cuh"
 #include "engine_types.cuh"

@@ -23,17 +23,20 @@ SCEN = [
     ("lowcov", 300, 40, 2, 10, dict(chisq_permutation=1, max_iter=2000), dict(variant_frac=0.5, bidir_frac=0.1)),
     ("diploid", 300, 40, 2, 10, {}, dict(variant_frac=0.5)),
     ("em0", 300, 10, 20, 100, dict(em_flag=0), dict(variant_frac=0.4, indel_frac=0.2, with_stats=True, with_qhigh=True)),
+    ("manyquals", 200, 10, 20, 100, {}, dict(variant_frac=0.4, bidir_frac=0.1, quals=range(14, 42))),
+    ("bidir_dense", 200, 10, 20, 100, {}, dict(variant_frac=0.4, bidir_frac=0.2)),
     ("c3small", 60, 100, 96, 60, {}, dict(variant_frac=0.5)),
     ("c5small", 60, 500, 10, 10, {}, dict(variant_frac=0.5)),
 ]
 only = sys.argv[1:]
+SCALE = float(os.environ.get("GPU_CHECK_SCALE", "1"))  # shrink the scenarios, e.g. under compute-sanitizer
 fails = 0
 for name, n, P, ploidy, depth, opts, kw in SCEN:
     if only and name not in only:
         continue
     try:
         cfg = EngineConfig(ploidy=np.broadcast_to(np.asarray(ploidy), (P,)).copy(), options=opts)
-        b = survey_demo_batch() if n is None else synth_batch(n, P, cfg.ploidy, depth, seed=11, **kw)
+        b = survey_demo_batch() if n is None else synth_batch(max(8, int(n * SCALE)), P, cfg.ploidy, depth, seed=11, **kw)
         t = time.time(); want = OracleEngine(cfg).run(b, mode=RNG_PHILOX); to = time.time() - t
         eng = Engine(cfg)
         t = time.time(); got = eng.run(b); tg = time.time() - t

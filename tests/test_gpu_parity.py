@@ -261,7 +261,12 @@ def test_benchmark_shape_properties():
     assert np.array_equal(sr.status, base.status) and np.array_equal(sr.allelecount, base.allelecount)
     for f in ("paf", "ctpval", "af_ml", "delta", "deltaf", "hwe"):
         assert rel_err(getattr(sr, f), getattr(base, f)).max() <= REL_TOL, f
-    # --- reproducibility checksum ---
+    # --- reproducibility checksum (a shared-memory race would show up as run-to-run differences) ---
+    for _ in range(3):
+        again = eng.run(batch)
+        for f in ("paf", "ctpval", "af_ml", "delta", "deltaf", "hwe"):
+            assert np.array_equal(getattr(again, f), getattr(base, f)), f
+        assert np.array_equal(again.allelecount, base.allelecount) and np.array_equal(again.varpools, base.varpools)
     again = eng.run(batch)
     assert int(again.status.astype(np.int64).sum() * 31 + again.allelecount.sum()) == int(base.status.astype(np.int64).sum() * 31 + base.allelecount.sum())
     assert np.array_equal(again.delta, base.delta)
