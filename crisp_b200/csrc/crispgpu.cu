@@ -48,6 +48,7 @@ struct crispgpu_ctx {
 	int P = 0, K = 0, nmax = 0;
 	// device configuration tables
 	DevBuf d_ploidy, d_pclass, d_class_ploidy, d_NC, d_T, d_ncr, d_pheno;
+	DevBuf d_exact_row, d_exact_cl, d_exact_done;  // exact_mode: term tables of the exact 2 x k test, per-task decided flags
 	// device batch
 	DevBuf d_b[24];
 	DevBatch db{};
@@ -405,7 +406,16 @@ int run_stage1(crispgpu_ctx* ctx)
 			tail.hits_head = static_cast<int32_t*>(ctx->d_tail_head.p);
 			tail.total = static_cast<int32_t*>(ctx->d_tail_total.p);
 			tail.counters = static_cast<int32_t*>(ctx->d_tail_counters.p);
-			k_permute_stranded<<<ctx->pm_grid, ctx->pm_threads, ctx->pm_smem, ctx->stream>>>(prm, ctx->pm_l10cap, tail);
+			const int32_t* exact_done = nullptr;
+			if (ctx->d_exact_row.p) {
+				// small tables are decided exactly; the Monte-Carlo kernels skip what this pass marks done
+				rc = ensure_dev(ctx, ctx->d_exact_done, (size_t)n * 5 * 4); if (rc) return rc;
+				k_exact_2xk<<<ctx->num_sms * 4, 128, 0, ctx->stream>>>(prm, static_cast<const double*>(ctx->d_exact_row.p), static_cast<const double*>(ctx->d_exact_cl.p), static_cast<int32_t*>(ctx->d_exact_done.p));
+				CK(cudaGetLastError());
+				launches++;
+				exact_done = static_cast<const int32_t*>(ctx->d_exact_done.p);
+			}
+			k_permute_stranded<<<ctx->pm_grid, ctx->pm_threads, ctx->pm_smem, ctx->stream>>>(prm, ctx->pm_l10cap, tail, exact_done);
 			CK(cudaGetLastError());
 			if (g.max_iter > kPermHead) {
 				// the number of tail tasks sizes the chunk records (the one extra host wait of the permutation mode)
@@ -808,6 +818,28 @@ int crispgpu_create(const crispgpu_config* cfg, int device_id, void* stream, cri
 		}
 		if ((rc = up(ctx->d_ncr, tab.data(), tab.size() * 8))) return fail(rc);
 	}
+	if (cfg->chisq_permutation == 1 && cfg->exact_mode == 1 && ctx->ploidy[0] > 2 && ctx->P >= 2 && ctx->P < 8) {
+		// term tables of the exact test, host libm, the reference's two formulas: the running sums of
+		// compute_NCRtable (contables.c:244-257) for the enumerated tables, ncr() (contables.c:80-87) for the observed one
+		std::vector<double> rowt((size_t)kExactMaxN * kExactOnes, 0.0), clt((size_t)kExactMaxN * kExactOnes, 0.0);
+		for (int n = 1; n < kExactMaxN; n++) {
+			double value = 0.0;
+			for (int j = 1; j < kExactOnes; j++) {
+				if (j < n) { value += log10((double)(n - j + 1)) - log10((double)j); rowt[(size_t)n * kExactOnes + j] = value; }
+				if (j <= n) {
+					int r = j;
+					double ll = 0.0;
+					if (n != r) {
+						if (2 * r > n) r = n - r;
+						for (int i = 0; i < r; i++) ll += log10((double)(n - i) / (double)(i + 1));
+					}
+					clt[(size_t)n * kExactOnes + j] = ll;
+				}
+			}
+		}
+		if ((rc = up(ctx->d_exact_row, rowt.data(), rowt.size() * 8))) return fail(rc);
+		if ((rc = up(ctx->d_exact_cl, clt.data(), clt.size() * 8))) return fail(rc);
+	}
 	if ((rc = ensure_dev(ctx, ctx->d_counters, 16 * 4))) return fail(rc);
 	if ((rc = ensure_host(ctx, ctx->h_counters, 16 * 4))) return fail(rc);
 	k_build_T<<<ctx->num_sms, 256, 0, ctx->stream>>>(static_cast<double*>(ctx->d_T.p), static_cast<const int32_t*>(ctx->d_class_ploidy.p), ncl, J, cfg->qv_offset, cfg->agilent_ref_bias);
@@ -824,6 +856,7 @@ void crispgpu_destroy(crispgpu_ctx* ctx)
 	auto fd = [](DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; };
 	auto fh = [](DevBuf& b) { if (b.p) cudaFreeHost(b.p); b.p = nullptr; };
 	fd(ctx->d_ploidy); fd(ctx->d_pclass); fd(ctx->d_class_ploidy); fd(ctx->d_NC); fd(ctx->d_T); fd(ctx->d_ncr); fd(ctx->d_pheno);
+	fd(ctx->d_exact_row); fd(ctx->d_exact_cl); fd(ctx->d_exact_done);
 	for (auto& b : ctx->d_b) fd(b);
 	for (auto& b : ctx->d_o) fd(b);
 	for (auto& b : ctx->h_o) fh(b);

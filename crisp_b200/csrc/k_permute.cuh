@@ -208,7 +208,7 @@ struct PermTail {
 // Head: one CTA per task, the first kPermHead permutations with the reference's sequential stop rule
 // (contables.c:327-328) evaluated on prefix sums in permutation order.  Tasks that neither stopped nor exhausted
 // their permutations go to the tail queue.
-__global__ void k_permute_stranded(EngineParams prm, int l10cap, PermTail tail)
+__global__ void k_permute_stranded(EngineParams prm, int l10cap, PermTail tail, const int32_t* __restrict__ exact_done)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const DevCfg& c = prm.c;
@@ -221,6 +221,7 @@ __global__ void k_permute_stranded(EngineParams prm, int l10cap, PermTail tail)
 		__syncthreads();
 		const int task = sh->task;
 		if (task >= prm.q.counters[0]) break;
+		if (exact_done && exact_done[task]) continue;  // small table: the exact test already wrote the p-value
 		const int o = prm.q.perm_tasks[task], s = o / kSlots, slot = o - s * kSlots;
 		stranded_setup(prm, v, o);
 		const int maxiter = c.max_iter;
@@ -591,6 +592,119 @@ __global__ void k_permute_lowcov_resolve(EngineParams prm, PermTail tail)
 				thi += rec[1];
 			}
 			lowcov_store(prm, tail.task[h], prm.c.max_iter + 1, tlo, thi);
+		}
+	}
+}
+
+// ---- exact 2 x k test for small tables (exact_mode) ------------------------------------------------------------------
+// Specification: compute_pvalue_exact / pvalue_contable_iter, FET/contables_exact.c:62-117 (not part of CRISP.binary).
+// p = sum over all tables (a_1..a_k), sum a_i = A, a_i <= N_i, whose log10 probability sum_i log10 C(N_i, a_i) does not
+// exceed the observed one, of prod_i C(N_i, a_i) / C(N, A), on the unstranded table (N_i, alt_i).  Gate: fewer than 70 alt
+// reads, columns below 2001 reads, 2 <= pools < 8.  The acceptance test is evaluated with the reference's own
+// operands in its own order: the budget is reduced column by column (prob - cp) and the last column is accepted when
+// its term does not exceed what is left; both term tables come from the host's libm (exact ties with the observed
+// table decide whether its own probability is counted).  One CTA per task; threads split the values of the first two
+// columns and walk the remaining columns depth-first.
+constexpr int kExactMaxN = 2001;  // MAXN, FET/contables.c:10
+constexpr int kExactOnes = 70;
+
+__global__ void k_exact_2xk(EngineParams prm, const double* __restrict__ ncrT, const double* __restrict__ clT, int32_t* __restrict__ done)
+{
+	const DevBatch& b = prm.b;
+	const DevCfg& c = prm.c;
+	const int P = c.P, T = blockDim.x, tid = threadIdx.x;
+	__shared__ int N[8], A[8], Rsuf[9], s_ok, s_ones;
+	__shared__ double s_cl, s_part[32];
+	for (int task = blockIdx.x; task < prm.q.counters[0]; task += gridDim.x) {
+		__syncthreads();
+		const int o = prm.q.perm_tasks[task], s = o / kSlots, slot = o - s * kSlots;
+		if (tid < P) {
+			int a1, a2, a3;
+			slot_alleles(b.maxvec_al + s * 8, slot, a1, a2, a3);
+			const int refbase = b.refbase[s];
+			const int row = slot_amb_row(b, s, slot, a2, a3);
+			const int altal = (a1 == refbase || a2 != refbase) ? a2 : a1;
+			const int32_t* r = b.indcounts + ((size_t)s * P + tid) * kNC;
+			int dd = 0;
+			if (row >= 0) { const int32_t* d = b.amb_dec + ((size_t)row * P + tid) * 4; dd = d[0] + d[1] + d[2] + d[3]; }
+			// variant->ctable[i][0..1] (allelecounts.c:214-220): N = c0 + c1, alt = c1 (or c0 when the reference allele is second)
+			const int c0 = r[a1] + r[a1 + 8] + r[a1 + 16] + r[a3] + r[a3 + 8] + r[a3 + 16] - ((a1 == refbase) + (a3 == refbase)) * dd;
+			const int c1 = r[a2] + r[a2 + 8] + r[a2 + 16] - (a2 == refbase ? dd : 0);
+			N[tid] = c0 + c1;
+			A[tid] = altal == a2 ? c1 : c0;
+		}
+		__syncthreads();
+		if (tid == 0) {
+			int ones = 0, maxcol = 0, run = 0;
+			for (int i = 0; i < P; i++) { ones += A[i]; if (N[i] > maxcol) maxcol = N[i]; }
+			Rsuf[P] = 0;
+			for (int i = P - 1; i >= 0; i--) { run += N[i]; Rsuf[i] = run; }
+			const int ok = ones < kExactOnes && maxcol < kExactMaxN && P >= 2 && P < 8 && ones >= 0;
+			double cl = 0.0;
+			if (ok) for (int i = 0; i < P; i++) cl += clT[(size_t)N[i] * kExactOnes + A[i]];  // ncr(N_i, A_i), pool order
+			s_ok = ok; s_ones = ones; s_cl = cl;
+		}
+		__syncthreads();
+		if (!s_ok) { if (tid == 0) done[task] = 0; continue; }
+		const int ones = s_ones;
+		const double cl = s_cl;
+		double S = 0.0;
+		if (ones <= Rsuf[0]) {
+			const int m0 = min(N[0], ones) + 1, m1 = P > 2 ? min(N[1], ones) + 1 : 1;
+			for (int idx = tid; idx < m0 * m1; idx += T) {
+				const int t0 = idx / m1, t1 = idx - t0 * m1;
+				int lvl = 1, start = 1;
+				int tt[8], Ar[8];
+				double pr[8];
+				const double cp0 = N[0] > 0 ? ncrT[(size_t)N[0] * kExactOnes + t0] : 0.0;
+				Ar[1] = ones - t0;
+				pr[1] = cl - cp0;
+				if (P > 2) {
+					if (Ar[1] > Rsuf[1] || t1 > Ar[1]) continue;
+					const double cp1 = N[1] > 0 ? ncrT[(size_t)N[1] * kExactOnes + t1] : 0.0;
+					Ar[2] = Ar[1] - t1;
+					pr[2] = pr[1] - cp1;
+					lvl = start = 2;
+				}
+				tt[lvl] = 0;
+				for (;;) {
+					if (lvl == P - 1) {  // last column takes what is left
+						const int a = Ar[lvl];
+						if (a <= N[lvl]) {
+							const double cp = N[lvl] > 0 ? ncrT[(size_t)N[lvl] * kExactOnes + a] : 0.0;
+							const double x = cp - pr[lvl];
+							if (!(cp > pr[lvl]) && x > -290.0) S += exp10_lse(x);
+						}
+						lvl--;
+						if (lvl < start) break;
+						tt[lvl]++;
+						continue;
+					}
+					if (Ar[lvl] > Rsuf[lvl] || tt[lvl] > N[lvl] || tt[lvl] > Ar[lvl]) {
+						lvl--;
+						if (lvl < start) break;
+						tt[lvl]++;
+						continue;
+					}
+					const double cp = N[lvl] > 0 ? ncrT[(size_t)N[lvl] * kExactOnes + tt[lvl]] : 0.0;
+					Ar[lvl + 1] = Ar[lvl] - tt[lvl];
+					pr[lvl + 1] = pr[lvl] - cp;
+					tt[lvl + 1] = 0;
+					lvl++;
+				}
+			}
+		}
+		S = warp_sum(S);
+		if ((tid & 31) == 0) s_part[tid >> 5] = S;
+		__syncthreads();
+		if (tid == 0) {
+			double tot = 0.0;
+			for (int w = 0; w < (T >> 5); w++) tot += s_part[w];
+			const double p = tot > 0 ? log10(tot) + cl : -1.0;  // compute_pvalue_exact returns -1 when no table qualifies
+			prm.o.ctpval[o] = p - d_ncr(Rsuf[0], ones);
+			prm.o.perm_k[o] = 0;
+			prm.o.perm_hits[o] = -1;
+			done[task] = 1;
 		}
 	}
 }

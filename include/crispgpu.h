@@ -75,7 +75,9 @@ typedef struct crispgpu_config {
 	/* engine-only switches (no reference counterpart) */
 	uint64_t rng_seed;         /* key of the counter-based RNG; results are a pure function of
 	                              (rng_seed, tid, pos, slot), independent of batching and GPU count */
-	int32_t exact_mode;        /* 1: small 2xk tables use exact enumeration (FET/contables_exact.c:62-117 gate) */
+	int32_t exact_mode;        /* 1 (with chisq_permutation=1, pooled): tables with 2 <= pools < 8, < 70 alt reads and
+	                              columns < 2001 reads get compute_pvalue_exact (FET/contables_exact.c:62-117) on the
+	                              unstranded table instead of the Monte-Carlo estimate; reported with perm_k = 0, perm_hits = -1 */
 	int32_t use_qv;            /* USE_QV (--weighted), readmultiplebams.c:24: how remove_ambiguous_bases adjusts Qhighcounts */
 } crispgpu_config;
 

@@ -654,6 +654,63 @@ static double o_perm_lowcov(oracle_ctx* c, int iter, int tid, int pos, int slot,
 }
 
 /* ------------------------------------------------------------------------------------------------------------
+ * exact 2 x k test for small tables — FET/contables_exact.c:62-117 (not compiled into CRISP.binary; the specification
+ * of the engine's exact_mode)
+ * ---------------------------------------------------------------------------------------------------------- */
+#define EXACT_MAXN 2001 /* MAXN, FET/contables.c:10 */
+
+/* NCRtable[n][j], j < n: running sum of log10(n-j+1) - log10(j) (compute_NCRtable, contables.c:244-257); 0 for j >= n */
+static void o_ncr_row(int n, int upto, double* row)
+{
+	double value = 0;
+	row[0] = 0;
+	for (int j = 1; j <= upto; j++) {
+		if (j < n) { value += log10(n - j + 1) - log10(j); row[j] = value; }
+		else row[j] = 0;
+	}
+}
+
+static double o_exact_rec(const int* N, double* const* rows, int size, int offset, int R, int A, double prob)
+{
+	if (A > R) return -1;
+	if (size == 1) {
+		double cp = N[offset] > 0 ? rows[offset][A] : 0;
+		return cp > prob ? -1 : cp;
+	}
+	double sum = 0;
+	for (int i = 0; i <= N[offset] && i <= A; i++) {
+		double cp = N[offset] > 0 ? rows[offset][i] : 0;
+		double a = o_exact_rec(N, rows, size - 1, offset + 1, R - N[offset], A - i, prob - cp);
+		if (a > -1) sum += pow(10, a + cp - prob);
+	}
+	if (sum > 0) return log10(sum) + prob;
+	return -1;
+}
+
+/* gate of pvalue_contable_iter (contables_exact.c:104); returns 1 and the log10 p-value when the table qualifies */
+static int o_exact_2xk(const int* N, const int* A, int size, double* log10p)
+{
+	int ones = 0, reads = 0, maxcol = 0;
+	double cl = 0;
+	for (int i = 0; i < size; i++) {
+		cl += o_ncr(N[i], A[i]);
+		ones += A[i];
+		reads += N[i];
+		if (N[i] > maxcol) maxcol = N[i];
+	}
+	if (!(ones < 70 && maxcol < EXACT_MAXN && size >= 2 && size < 8)) return 0;
+	double* rows[8];
+	for (int i = 0; i < size; i++) {
+		rows[i] = (double*)calloc(ones + 2, sizeof(double));
+		o_ncr_row(N[i], ones, rows[i]);
+	}
+	double p = o_exact_rec(N, rows, size, 0, reads, ones, cl);
+	for (int i = 0; i < size; i++) free(rows[i]);
+	*log10p = p - o_ncr(reads, ones);
+	return 1;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
  * evaluate_variant — crisp/newcrispcaller.c:34-132
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct slot_out {
@@ -690,7 +747,15 @@ static int o_evaluate(oracle_ctx* c, const crispgpu_batch* b, int s, int slot, i
 	o_populate_contable(c, a1, a2, b->refbase[s], a3);
 	if (c->ploidy[0] > 2 && g->chisq_permutation == 1) {
 		o_chi2_weighted(c, &pv2, chistat);
-		pv1 = o_perm_stranded(c, g->max_iter, b->tid[s], b->pos[s], slot, &o->perm_k, &o->perm_hits);
+		int exact = 0;
+		if (g->exact_mode == 1 && P < 8) {
+			/* engine extension: small tables get the exact test on the unstranded table (N, alt) instead of the Monte-Carlo estimate */
+			int Nn[8], Aa[8];
+			for (int i = 0; i < P; i++) { Nn[i] = c->ctab2[i * 2]; Aa[i] = c->ctab2[i * 2 + 1]; }
+			exact = o_exact_2xk(Nn, Aa, P, &pv1);
+			if (exact) { o->perm_k = 0; o->perm_hits = -1; }
+		}
+		if (!exact) pv1 = o_perm_stranded(c, g->max_iter, b->tid[s], b->pos[s], slot, &o->perm_k, &o->perm_hits);
 		o->ctpval = pv1;
 		o->chi2pval = pv2;
 	} else if (c->ploidy[0] == 2 && g->chisq_permutation == 1) {
@@ -1252,5 +1317,11 @@ double crisp_oracle_kf_gammaq(double s, double z) { return o_gammaq(s, z); }
 void crisp_oracle_chernoff(int* counts, double* stats, int refbase, int altbase, double ser, double* p0, double* p1)
 {
 	o_chernoff(counts, stats, refbase, altbase, ser, p0, p1);
+}
+double crisp_oracle_exact_2xk(const int* N, const int* A, int size)
+{
+	double p = 1.0;
+	o_exact_2xk(N, A, size, &p);
+	return p;
 }
 void crisp_oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { philox4x32_10(ctr, key, out); }

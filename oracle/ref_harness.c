@@ -805,3 +805,42 @@ int crisp_ref_shim_roundtrip(void* h, const crispgpu_batch* b, char* msg, size_t
 	crisp_shim_batch_free(sb);
 	return bad;
 }
+
+
+/* ---- exact small-table mode: FET/contables_exact.c (dead in CRISP.binary, the specification of the GPU exact mode) ---- */
+double compute_pvalue_exact(int** ctable, int size, int offset, int R, int A, double prob, double** NCRtable, int st);
+void compute_NCRtable(double** NCRtable);
+extern int MAXN;
+static double** g_ncrtable = NULL;
+
+/* log10 p of the exact 2 x k test exactly as pvalue_contable_iter forms it (contables_exact.c:96-109), or 1.0 when the
+ * table fails its gate (ones < 70, max column < MAXN, 2 <= size < 8) */
+double crisp_ref_exact_2xk(const int* N, const int* A, int size)
+{
+	if (!g_ncrtable) {
+		g_ncrtable = (double**)calloc(MAXN, sizeof(double*));
+		for (int i = 0; i < MAXN; i++) g_ncrtable[i] = (double*)calloc(MAXN, sizeof(double));
+		compute_NCRtable(g_ncrtable);
+	}
+	int* rows = (int*)calloc((size_t)size * 2, sizeof(int));
+	int** ctable = (int**)calloc(size, sizeof(int*));
+	int ones = 0, reads = 0, maxcol = 0;
+	double cl = 0;
+	for (int i = 0; i < size; i++) {
+		ctable[i] = rows + 2 * i;
+		ctable[i][0] = N[i];
+		ctable[i][1] = A[i];
+		cl += ncr(N[i], A[i]);
+		ones += A[i];
+		reads += N[i];
+		if (N[i] > maxcol) maxcol = N[i];
+	}
+	double out = 1.0;
+	if (ones < 70 && maxcol < MAXN && size >= 2 && size < 8) {
+		double p = compute_pvalue_exact(ctable, size, 0, reads, ones, cl, g_ncrtable, 0);
+		out = p - ncr(reads, ones);
+	}
+	free(ctable);
+	free(rows);
+	return out;
+}

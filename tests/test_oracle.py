@@ -180,3 +180,96 @@ def test_host_shim_round_trip(kw):
     batch = synth_batch(120, 8, cfg.ploidy, 80, seed=41, **kw)
     bad, msg = RefEngine(cfg).shim_roundtrip(batch)
     assert bad == 0, msg
+
+
+# ---- exact 2 x k test (exact_mode; specification FET/contables_exact.c:62-117) ------------------------------------------
+def _exact_tables(seed, count):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(count):
+        size = int(rng.integers(2, 8))
+        N = rng.integers(0, 60, size).astype(np.int32)
+        if rng.random() < 0.2:
+            N[int(rng.integers(0, size))] = int(rng.integers(500, 2000))
+        A = np.minimum(N, rng.binomial(N, rng.choice([0.01, 0.05, 0.2]))).astype(np.int32)
+        while A.sum() >= 40:
+            A = A // 2
+        out.append((N, A))
+    return out
+
+
+def _exact_call(engine, N, A):
+    fn = engine.scalar("exact_2xk", C.c_double, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int])
+    return fn(N.ctypes.data_as(C.POINTER(C.c_int)), A.ctypes.data_as(C.POINTER(C.c_int)), len(N))
+
+
+def _exact_brute(N, A):
+    """(strict, with ties): log10 of the summed hypergeometric probabilities of all tables with the observed margins that
+    are less likely / no more likely than the observed one, in exact integer arithmetic.  The reference compares
+    rounded log10 sums without an epsilon (contables_exact.c:70), so tables tied with the observed one — including the
+    observed one itself — are counted or not depending on rounding; its answer lies between the two."""
+    from itertools import product
+    from math import comb, log10
+    ones, reads = int(A.sum()), int(N.sum())
+    obs = 1
+    for n, a in zip(N, A):
+        obs *= comb(int(n), int(a))
+    strict = ties = 0
+    for t in product(*[range(min(int(n), ones) + 1) for n in N[:-1]]):
+        last = ones - sum(t)
+        if last < 0 or last > N[-1]:
+            continue
+        w = comb(int(N[-1]), last)
+        for n, a in zip(N, t):
+            w *= comb(int(n), a)
+        if w < obs:
+            strict += w
+        if w <= obs:
+            ties += w
+    den = log10(comb(reads, ones))
+    return (log10(strict) - den if strict else -np.inf), log10(ties) - den
+
+
+def test_exact_2xk_against_brute_force():
+    orc = OracleEngine(_cfg())
+    rng = np.random.default_rng(5)
+    equal_hi = 0
+    for _ in range(60):
+        size = int(rng.integers(2, 5))
+        N = rng.integers(1, 14, size).astype(np.int32)
+        A = rng.binomial(N, 0.25).astype(np.int32)
+        lo, hi = _exact_brute(N, A)
+        got = _exact_call(orc, N, A)
+        if got < -1 - 1e-9 and lo == -np.inf and got < hi - 1e-9:
+            continue  # nothing qualified after rounding: the reference's "-1" sentinel minus the normaliser
+        assert lo - 1e-10 <= got <= hi + 1e-10, (N, A, lo, got, hi)
+        equal_hi += abs(got - hi) < 1e-10
+    assert equal_hi > 20
+
+
+@needs_ref
+def test_exact_2xk_equals_reference():
+    """compute_pvalue_exact of the unmodified FET/contables_exact.c (linked into oracle/_ref) on random small tables:
+    the restatement uses the same term tables and acceptance order, so the doubles are identical."""
+    orc, ref = OracleEngine(_cfg()), RefEngine(_cfg())
+    for N, A in _exact_tables(3, 300):
+        assert _exact_call(orc, N, A) == _exact_call(ref, N, A), (N, A)
+    # outside the gate (>= 70 alt reads, >= 8 columns) both report "not applicable" as 1.0
+    big = (np.full(4, 100, np.int32), np.full(4, 20, np.int32))
+    assert _exact_call(orc, *big) == 1.0 and _exact_call(ref, *big) == 1.0
+
+
+def test_exact_mode_replaces_monte_carlo_for_small_tables():
+    cfg_mc = _cfg(P=5, chisq_permutation=1, max_iter=2000)
+    cfg_ex = _cfg(P=5, chisq_permutation=1, max_iter=2000, exact_mode=1)
+    batch = synth_batch(120, 5, cfg_mc.ploidy, 50, seed=31, variant_frac=0.5)
+    mc = OracleEngine(cfg_mc).run(batch, mode=RNG_PHILOX)
+    ex = OracleEngine(cfg_ex).run(batch, mode=RNG_PHILOX)
+    exact = ex.perm_hits == -1
+    assert exact.sum() > 50 and np.all(ex.perm_k[exact] == 0)
+    other = ~exact
+    assert np.array_equal(ex.perm_k[other], mc.perm_k[other]) and np.array_equal(ex.perm_hits[other], mc.perm_hits[other])
+    # the Monte-Carlo test is on the stranded table, the exact one on the unstranded table: related, not equal
+    m = exact & (mc.perm_hits >= 5)
+    assert m.sum() > 50
+    assert np.corrcoef(ex.ctpval[m], mc.ctpval[m])[0, 1] > 0.5
