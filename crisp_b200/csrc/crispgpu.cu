@@ -48,6 +48,9 @@ struct crispgpu_ctx {
 	int P = 0, K = 0, nmax = 0;
 	// device configuration tables
 	DevBuf d_ploidy, d_pclass, d_class_ploidy, d_NC, d_T, d_ncr, d_pheno;
+	DevBuf d_need_reads;           // per-site flags of the on-demand read fetch
+	const uint16_t* lazy_reads = nullptr;  // device-visible address of the caller's pinned read array (on-demand fetch), or null
+	int64_t copied_bytes = 0;
 	DevBuf d_exact_row, d_exact_cl, d_exact_done;  // exact_mode: term tables of the exact 2 x k test, per-task decided flags
 	// device batch
 	DevBuf d_b[24];
@@ -101,6 +104,15 @@ namespace {
 			return CRISPGPU_ERR_CUDA;                                                                        \
 		}                                                                                                    \
 	} while (0)
+
+// after every launch; CRISPGPU_SYNC_CHECK=1 also waits for the device so that a faulting kernel is reported at its own line
+cudaError_t launch_check()
+{
+	static const bool sync = getenv("CRISPGPU_SYNC_CHECK") != nullptr;
+	cudaError_t e = cudaGetLastError();
+	if (e == cudaSuccess && sync) e = cudaDeviceSynchronize();
+	return e;
+}
 
 int ensure_dev(crispgpu_ctx* ctx, DevBuf& b, size_t bytes)
 {
@@ -268,7 +280,9 @@ int collect_arrays(crispgpu_ctx* ctx, const crispgpu_batch* b, BatchArray* a)
 	return k;
 }
 
-int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b)
+// lazy: the caller's arrays outlive the call (submit/wait), so the packed reads — 80 % of a batch, needed only by the
+// sites that reach the quality-value likelihood — may stay in pinned host memory and be fetched on demand.
+int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b, bool lazy)
 {
 	BatchArray a[24];
 	const int k = collect_arrays(ctx, b, a);
@@ -278,10 +292,25 @@ int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b)
 	}
 	const void** dptr = reinterpret_cast<const void**>(&ctx->db.tid);
 	int64_t bytes = 0;
+	constexpr int kReadsArray = 10;
+	constexpr size_t kLazyMinBytes = 1 << 20;
+	const bool reads_used = ctx->cfg.em_flag >= 1 && ctx->cfg.use_base_qvs == 1;
+	ctx->lazy_reads = nullptr;
 	for (int i = 0; i < k; i++) {
 		if (a[i].bytes == 0 || a[i].host == nullptr) { dptr[i] = nullptr; continue; }
 		int rc = ensure_dev(ctx, ctx->d_b[i], a[i].bytes);
 		if (rc) return rc;
+		if (i == kReadsArray && !reads_used) { dptr[i] = ctx->d_b[i].p; continue; }  // --EM 0 / --usebq 0: no kernel touches the reads
+		if (i == kReadsArray && lazy) {
+			cudaPointerAttributes at{};
+			if (cudaPointerGetAttributes(&at, a[i].host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer &&
+			    (reinterpret_cast<uintptr_t>(at.devicePointer) & 15) == 0 && a[i].bytes >= kLazyMinBytes) {
+				ctx->lazy_reads = static_cast<const uint16_t*>(at.devicePointer);
+				dptr[i] = ctx->d_b[i].p;
+				continue;
+			}
+			(void)cudaGetLastError();  // pageable memory: cudaPointerGetAttributes may flag an error on older drivers
+		}
 		CK(cudaMemcpyAsync(ctx->d_b[i].p, a[i].host, a[i].bytes, cudaMemcpyHostToDevice, ctx->stream));
 		dptr[i] = ctx->d_b[i].p;
 		bytes += (int64_t)a[i].bytes;
@@ -291,6 +320,7 @@ int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b)
 	ctx->n_sites = b->n_sites;
 	ctx->n_reads = b->n_sites ? b->read_off[(size_t)b->n_sites * ctx->P] : 0;
 	ctx->timing.h2d_bytes = bytes;
+	ctx->copied_bytes = bytes;
 	return 0;
 }
 
@@ -346,6 +376,7 @@ EngineParams make_params(crispgpu_ctx* ctx)
 	prm.q.call_tasks = static_cast<int32_t*>(ctx->d_call_tasks.p);
 	prm.q.call_tasks2 = static_cast<int32_t*>(ctx->d_call_tasks2.p);
 	prm.q.counters = static_cast<int32_t*>(ctx->d_counters.p);
+	prm.q.need_reads = ctx->lazy_reads ? static_cast<uint8_t*>(ctx->d_need_reads.p) : nullptr;
 	prm.gws = static_cast<double*>(ctx->d_gws.p);
 	prm.gws_stride = ctx->gws_stride;
 	return prm;
@@ -363,16 +394,21 @@ int run_stage1(crispgpu_ctx* ctx)
 	if (rc) return rc;
 	int64_t launches = 0;
 	CK(cudaMemsetAsync(ctx->d_counters.p, 0, 16 * sizeof(int32_t), ctx->stream));
+	const bool lazy = ctx->lazy_reads != nullptr && n > 0;
+	if (lazy) {
+		rc = ensure_dev(ctx, ctx->d_need_reads, (size_t)n); if (rc) return rc;
+		CK(cudaMemsetAsync(ctx->d_need_reads.p, 0, (size_t)n, ctx->stream));
+	} else ctx->lazy_reads = nullptr;
 	EngineParams prm = make_params(ctx);
 	CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
-	const bool scan = n > 0 && g.em_flag >= 1 && g.use_base_qvs == 1 && ctx->n_reads > 0;
+	const bool scan = n > 0 && g.em_flag >= 1 && g.use_base_qvs == 1 && ctx->n_reads > 0 && !lazy;
 	if (scan) {
 		// fork: the read-stream scan is independent of the count-based screening
 		CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
 		CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
 		k_qualmap<<<ctx->num_sms * 2, 256, 0, ctx->side>>>(ctx->db.reads, ctx->n_reads, static_cast<int32_t*>(ctx->d_counters.p));
 		launches++;
-		CK(cudaGetLastError());
+		CK(launch_check());
 		CK(cudaEventRecord(ctx->ev_join, ctx->side));
 	}
 	if (n > 0) {
@@ -380,7 +416,7 @@ int run_stage1(crispgpu_ctx* ctx)
 		if (rc) return rc;
 		launches++;
 	}
-	CK(cudaGetLastError());
+	CK(launch_check());
 	if (scan) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
 	CK(cudaEventRecord(ctx->ev[EV_EVAL], ctx->stream));
 	if (g.chisq_permutation == 1 && n > 0) {
@@ -411,12 +447,12 @@ int run_stage1(crispgpu_ctx* ctx)
 				// small tables are decided exactly; the Monte-Carlo kernels skip what this pass marks done
 				rc = ensure_dev(ctx, ctx->d_exact_done, (size_t)n * 5 * 4); if (rc) return rc;
 				k_exact_2xk<<<ctx->num_sms * 4, 128, 0, ctx->stream>>>(prm, static_cast<const double*>(ctx->d_exact_row.p), static_cast<const double*>(ctx->d_exact_cl.p), static_cast<int32_t*>(ctx->d_exact_done.p));
-				CK(cudaGetLastError());
+				CK(launch_check());
 				launches++;
 				exact_done = static_cast<const int32_t*>(ctx->d_exact_done.p);
 			}
 			k_permute_stranded<<<ctx->pm_grid, ctx->pm_threads, ctx->pm_smem, ctx->stream>>>(prm, ctx->pm_l10cap, tail, exact_done);
-			CK(cudaGetLastError());
+			CK(launch_check());
 			if (g.max_iter > kPermHead) {
 				// the number of tail tasks sizes the chunk records (the one extra host wait of the permutation mode)
 				int32_t* hc2 = static_cast<int32_t*>(ctx->h_counters.p) + 12;
@@ -432,7 +468,7 @@ int run_stage1(crispgpu_ctx* ctx)
 					rc = ensure_dev(ctx, ctx->d_tail_rec, (size_t)n_tail * tail.nchunks * kPermRec * 4); if (rc) return rc;
 					tail.rec = static_cast<int32_t*>(ctx->d_tail_rec.p);
 					k_permute_stranded_tail<<<ctx->pm_grid, ctx->pm_threads, ctx->pm_smem, ctx->stream>>>(prm, ctx->pm_l10cap, tail);
-					CK(cudaGetLastError());
+					CK(launch_check());
 					k_permute_stranded_resolve<<<(n_tail + 127) / 128, 128, 0, ctx->stream>>>(prm, tail);
 					launches += 2;
 				}
@@ -460,7 +496,7 @@ int run_stage1(crispgpu_ctx* ctx)
 			tail.total = static_cast<int32_t*>(ctx->d_tail_total.p);
 			tail.counters = static_cast<int32_t*>(ctx->d_tail_counters.p);
 			k_permute_lowcov<<<ctx->pm_grid, ctx->pm_threads, low_smem, ctx->stream>>>(prm, tail);
-			CK(cudaGetLastError());
+			CK(launch_check());
 			if (g.max_iter > kPermHead) {
 				int32_t* hc2 = static_cast<int32_t*>(ctx->h_counters.p) + 12;
 				CK(cudaMemcpyAsync(hc2, ctx->d_tail_counters.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -475,24 +511,31 @@ int run_stage1(crispgpu_ctx* ctx)
 					rc = ensure_dev(ctx, ctx->d_tail_rec, (size_t)n_tail * tail.nchunks * kLowRec * 4); if (rc) return rc;
 					tail.rec = static_cast<int32_t*>(ctx->d_tail_rec.p);
 					k_permute_lowcov_tail<<<ctx->pm_grid, ctx->pm_threads, low_smem, ctx->stream>>>(prm, tail);
-					CK(cudaGetLastError());
+					CK(launch_check());
 					k_permute_lowcov_resolve<<<(n_tail + 127) / 128, 128, 0, ctx->stream>>>(prm, tail);
 					launches += 2;
 				}
 			}
 		}
 		launches++;
-		CK(cudaGetLastError());
+		CK(launch_check());
 		CK(cudaEventRecord(ctx->ev[EV_PERM], ctx->stream));
 		k_filter<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(prm);
 		launches++;
-		CK(cudaGetLastError());
+		CK(launch_check());
 	} else {
 		CK(cudaEventRecord(ctx->ev[EV_PERM], ctx->stream));
 	}
+	if (lazy) {
+		// pull the reads of the sites that reached the quality-value likelihood straight from the caller's pinned array
+		k_fetch_reads<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->lazy_reads, static_cast<uint16_t*>(ctx->d_b[10].p), ctx->db.read_off,
+		                                                        static_cast<const uint8_t*>(ctx->d_need_reads.p), n, ctx->P, ctx->n_reads, static_cast<int32_t*>(ctx->d_counters.p));
+		launches++;
+		CK(launch_check());
+	}
 	CK(cudaEventRecord(ctx->ev[EV_FILTER], ctx->stream));
 	// how many tasks reached the caller: sizes the per-pool rows
-	CK(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 11 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaEventRecord(ctx->ev_counts, ctx->stream));
 	ctx->stage1_launches = launches;
 	return 0;
@@ -511,6 +554,7 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 	ctx->n_call1 = hc[1];
 	ctx->n_call2 = hc[8];
 	ctx->n_call = hc[1] + hc[8];
+	if (ctx->lazy_reads) ctx->timing.h2d_bytes = ctx->copied_bytes + 2 * (int64_t)(static_cast<uint32_t>(hc[14]) | (static_cast<uint64_t>(static_cast<uint32_t>(hc[15])) << 32));
 	{
 		// distinct quality characters of the batch -> dense likelihood path when few enough and one pool size
 		int nq = 0;
@@ -602,12 +646,12 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 			k_legacy<4><<<ctx->lg_grid < need ? ctx->lg_grid : need, 128, ctx->lg_smem, ctx->stream>>>(prm);
 		}
 		launches++;
-		CK(cudaGetLastError());
+		CK(launch_check());
 	}
 	if (n > 0) {
 		k_finalize<<<(n + 255) / 256, 256, 0, ctx->stream>>>(prm);
 		launches++;
-		CK(cudaGetLastError());
+		CK(launch_check());
 	}
 	CK(cudaEventRecord(ctx->ev[EV_CALL], ctx->stream));
 	int64_t d2h = 0;
@@ -856,7 +900,7 @@ void crispgpu_destroy(crispgpu_ctx* ctx)
 	auto fd = [](DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; };
 	auto fh = [](DevBuf& b) { if (b.p) cudaFreeHost(b.p); b.p = nullptr; };
 	fd(ctx->d_ploidy); fd(ctx->d_pclass); fd(ctx->d_class_ploidy); fd(ctx->d_NC); fd(ctx->d_T); fd(ctx->d_ncr); fd(ctx->d_pheno);
-	fd(ctx->d_exact_row); fd(ctx->d_exact_cl); fd(ctx->d_exact_done);
+	fd(ctx->d_exact_row); fd(ctx->d_exact_cl); fd(ctx->d_exact_done); fd(ctx->d_need_reads);
 	for (auto& b : ctx->d_b) fd(b);
 	for (auto& b : ctx->d_o) fd(b);
 	for (auto& b : ctx->h_o) fh(b);
@@ -881,7 +925,7 @@ int crispgpu_submit(crispgpu_ctx* ctx, const crispgpu_batch* batch, int64_t* tic
 	}
 	CK(cudaSetDevice(ctx->device));
 	CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
-	int rc = copy_batch(ctx, batch);
+	int rc = copy_batch(ctx, batch, true);
 	if (rc) return rc;
 	ctx->resident = false;
 	rc = run_stage1(ctx);
@@ -912,7 +956,7 @@ int crispgpu_upload(crispgpu_ctx* ctx, const crispgpu_batch* batch)
 	if (!ctx || !batch || batch->n_sites < 0) return CRISPGPU_ERR_ARG;
 	if (ctx->inflight) return CRISPGPU_ERR_TICKET;
 	CK(cudaSetDevice(ctx->device));
-	int rc = copy_batch(ctx, batch);
+	int rc = copy_batch(ctx, batch, false);
 	if (rc) return rc;
 	CK(cudaStreamSynchronize(ctx->stream));
 	ctx->resident = true;
@@ -951,7 +995,8 @@ const char* crispgpu_last_error(crispgpu_ctx* ctx) { return ctx ? ctx->err : "nu
 void* crispgpu_host_alloc(size_t bytes)
 {
 	void* p = nullptr;
-	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+	// mapped + portable: device-addressable from every GPU, so the packed reads can be fetched on demand (k_fetch_reads)
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
 	return p;
 }
 

@@ -96,7 +96,8 @@ struct DevQueues {
 	int32_t* perm_tasks;   // site*5+slot
 	int32_t* call_tasks;   // site*5+slot that reached the caller: quality-value (SNP) likelihood tasks, or every task with --EM 0
 	int32_t* call_tasks2;  // EM tasks whose likelihood is count-based (indel alleles, --usebq 0)
-	int32_t* counters;     // [0]=n_perm [1]=n_call [2]=perm head [3]=call head [4..7]=quality-presence bitmap (128 bits) [8]=n_call2 [9]=call2 head [10]=some read is bidirectional
+	uint8_t* need_reads;   // [n_sites] or null: site has a quality-value likelihood task (its reads are fetched from host memory on demand)
+	int32_t* counters;     // [14..15]=read elements fetched on demand (64-bit); [0]=n_perm [1]=n_call [2]=perm head [3]=call head [4..7]=quality-presence bitmap (128 bits) [8]=n_call2 [9]=call2 head [10]=some read is bidirectional
 };
 
 struct EngineParams {

@@ -58,7 +58,10 @@ __device__ __forceinline__ void queue_push(int32_t* list, int32_t* counter, int3
 __device__ __forceinline__ void push_call_task(const EngineParams& prm, int o, int a2)
 {
 	if (prm.c.em_flag >= 1 && (a2 >= 4 || prm.c.use_base_qvs == 0)) queue_push(prm.q.call_tasks2, prm.q.counters + 8, o);
-	else queue_push(prm.q.call_tasks, prm.q.counters + 1, o);
+	else {
+		queue_push(prm.q.call_tasks, prm.q.counters + 1, o);
+		if (prm.q.need_reads) prm.q.need_reads[o / kSlots] = 1;
+	}
 }
 
 // p-value of the asymptotic test from the per-group joint statistics
@@ -308,6 +311,63 @@ __global__ void k_qualmap(const uint16_t* __restrict__ reads, size_t n_reads, in
 		seen[w & 0x7f] = 1;
 		if (w & 0x800u) bidir = 1;
 	}
+	if (__any_sync(0xffffffffu, bidir) && (threadIdx.x & 31) == 0) atomicOr(reinterpret_cast<unsigned int*>(counters) + 10, 1u);
+	__syncthreads();
+	for (int q = threadIdx.x; q < kNQ; q += blockDim.x)
+		if (seen[q]) atomicOr(reinterpret_cast<unsigned int*>(counters) + 4 + (q >> 5), 1u << (q & 31));
+}
+
+// On-demand read fetch: the packed reads stay in pinned host memory and only the sites that reached the
+// quality-value likelihood are pulled over PCIe (zero-copy loads, 16 B per thread, four in flight) into the device
+// buffer at their own offsets, so read_off needs no remapping.  Ranges are widened to 16-byte boundaries — the extra
+// elements are the neighbouring sites' own reads, written with their own values.  The quality-presence bitmap and the
+// bidirectional flag (k_qualmap's outputs) are taken from the fetched reads on the way.
+__global__ void k_fetch_reads(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, const uint32_t* __restrict__ read_off,
+                              const uint8_t* __restrict__ need, int n_sites, int P, size_t n_reads, int32_t* counters)
+{
+	__shared__ unsigned char seen[kNQ];
+	int bidir = 0;
+	unsigned long long moved = 0;
+	for (int q = threadIdx.x; q < kNQ; q += blockDim.x) seen[q] = 0;
+	__syncthreads();
+	const uint4* s4 = reinterpret_cast<const uint4*>(src);
+	uint4* d4 = reinterpret_cast<uint4*>(dst);
+	const size_t nvec = n_reads / 8;
+	const int T = blockDim.x, tid = threadIdx.x;
+	for (int s = blockIdx.x; s < n_sites; s += gridDim.x) {
+		if (!need[s]) continue;
+		const size_t r0 = read_off[(size_t)s * P], r1 = read_off[(size_t)(s + 1) * P];
+		if (r1 <= r0) continue;
+		const size_t v0 = r0 / 8;
+		size_t v1 = (r1 + 7) / 8;
+		if (v1 > nvec) {  // the array ends inside the last vector: scalar tail
+			v1 = nvec;
+			for (size_t r = nvec * 8 + tid; r < r1; r += T) {
+				const uint16_t w = src[r];
+				dst[r] = w;
+				seen[w & 0x7f] = 1;
+				if (w & 0x800u) bidir = 1;
+			}
+		}
+		for (size_t k = v0 + tid; k < v1; k += 4 * (size_t)T) {
+			uint4 x[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++)
+				if (k + (size_t)u * T < v1) x[u] = __ldcs(s4 + k + (size_t)u * T);
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				if (k + (size_t)u * T >= v1) break;
+				d4[k + (size_t)u * T] = x[u];
+				if ((x[u].x | x[u].y | x[u].z | x[u].w) & 0x08000800u) bidir = 1;
+				seen[x[u].x & 0x7f] = 1; seen[(x[u].x >> 16) & 0x7f] = 1;
+				seen[x[u].y & 0x7f] = 1; seen[(x[u].y >> 16) & 0x7f] = 1;
+				seen[x[u].z & 0x7f] = 1; seen[(x[u].z >> 16) & 0x7f] = 1;
+				seen[x[u].w & 0x7f] = 1; seen[(x[u].w >> 16) & 0x7f] = 1;
+			}
+		}
+		if (tid == 0) moved += r1 - r0;
+	}
+	if (moved) atomicAdd(reinterpret_cast<unsigned long long*>(counters + 14), moved);
 	if (__any_sync(0xffffffffu, bidir) && (threadIdx.x & 31) == 0) atomicOr(reinterpret_cast<unsigned int*>(counters) + 10, 1u);
 	__syncthreads();
 	for (int q = threadIdx.x; q < kNQ; q += blockDim.x)

@@ -276,14 +276,23 @@ __global__ void k_permute_stranded_tail(EngineParams prm, int l10cap, PermTail t
 	__shared__ int firsts[10];
 	for (;;) {
 		__syncthreads();
-		if (tid == 0) sh->task = atomicAdd(tail.counters + 1, 1);
+		if (tid == 0) {
+			// one thread decides whether the chunk is skipped: the running total changes under concurrent chunks, and the
+			// whole block must take the same branch around the barriers below
+			const int it = atomicAdd(tail.counters + 1, 1);
+			sh->task = it;
+			if (it < nitems) {
+				const int ch = it / ntask, hh = it - ch * ntask;
+				sh->stop_k = (kPermHead + ch * tail.chunk >= c.max_iter || *((volatile int32_t*)(tail.total + hh)) >= 10) ? 1 : 0;
+			}
+		}
 		__syncthreads();
 		const int item = sh->task;
 		if (item >= nitems) break;
 		const int chunk = item / ntask, h = item - chunk * ntask;
 		int32_t* rec = tail.rec + ((size_t)h * tail.nchunks + chunk) * kPermRec;
 		const int kbeg = kPermHead + chunk * tail.chunk, kend = min(c.max_iter, kbeg + tail.chunk);  // permutations (kbeg, kend]
-		if (kbeg >= c.max_iter || *((volatile int32_t*)(tail.total + h)) >= 10) {
+		if (sh->stop_k) {
 			if (tid == 0) { rec[0] = 0; rec[1] = 1; }
 			continue;
 		}
@@ -529,15 +538,23 @@ __global__ void k_permute_lowcov_tail(EngineParams prm, PermTail tail)
 	__shared__ int firsts[20];
 	for (;;) {
 		__syncthreads();
-		if (tid == 0) sh->task = atomicAdd(tail.counters + 1, 1);
+		if (tid == 0) {
+			// one thread decides the skip for the whole block (the totals change under concurrent chunks)
+			const int it = atomicAdd(tail.counters + 1, 1);
+			sh->task = it;
+			if (it < nitems) {
+				const int ch = it / ntask, hh = it - ch * ntask;
+				const volatile int32_t* tot = tail.total + 2 * hh;
+				sh->stop_k = (kPermHead + ch * tail.chunk >= c.max_iter || (tot[0] >= 10 && tot[1] >= 10)) ? 1 : 0;
+			}
+		}
 		__syncthreads();
 		const int item = sh->task;
 		if (item >= nitems) break;
 		const int chunk = item / ntask, h = item - chunk * ntask;
 		int32_t* rec = tail.rec + ((size_t)h * tail.nchunks + chunk) * kLowRec;
 		const int kbeg = kPermHead + chunk * tail.chunk, kend = min(c.max_iter, kbeg + tail.chunk);
-		const volatile int32_t* tot = tail.total + 2 * h;
-		if (kbeg >= c.max_iter || (tot[0] >= 10 && tot[1] >= 10)) {
+		if (sh->stop_k) {
 			if (tid == 0) { rec[0] = 0; rec[1] = 0; rec[2] = 1; }
 			continue;
 		}

@@ -223,6 +223,46 @@ def test_submit_wait_equals_resident_path():
     eng.close()
 
 
+@pytest.mark.parametrize("opts,kw", [
+    ({}, dict(variant_frac=0.2, bidir_frac=0.05)),
+    ({}, dict(variant_frac=0.3, indel_frac=0.5, quals=range(14, 42))),
+    (dict(chisq_permutation=1, max_iter=2000), dict(variant_frac=0.3)),
+    (dict(use_base_qvs=0), dict(variant_frac=0.3)),
+    (dict(em_flag=0), dict(variant_frac=0.3, with_stats=True, with_qhigh=True)),
+], ids=["snp", "indel_manyquals", "perm", "nobq", "em0"])
+def test_on_demand_read_fetch_equals_full_copy(opts, kw):
+    """Pinned batches leave the packed reads in host memory and fetch only the sites that reach the quality-value
+    likelihood (k_fetch_reads); pageable batches copy everything.  Same results; fewer bytes over PCIe."""
+    cfg = _cfg(10, 20, opts)
+    batch = synth_batch(1500, 10, cfg.ploidy, 100, seed=77, **kw)
+    assert batch.reads.nbytes > (1 << 20)
+    eng = Engine(cfg)
+    full = eng.run(batch)
+    t_full = eng.timing()
+    lazy = eng.run(pin_batch(batch))
+    t_lazy = eng.timing()
+    again = eng.run(batch)   # the device read buffer now holds a mix of stale and fresh sites: results must not care
+    eng.close()
+    assert (full.status == 4).sum() > 30
+    want = OracleEngine(cfg).run(batch, mode=RNG_PHILOX)
+    compare_results(lazy, want, label="lazy-vs-oracle")
+    # the likelihood path (dense/sparse) is picked from the qualities seen, which may differ between the two scans
+    compare_results(lazy, full, label="lazy-vs-full")
+    compare_results(again, full, tol=0.0, label="full-repeat")
+    if opts.get("em_flag", 1) >= 1 and opts.get("use_base_qvs", 1) == 1:
+        assert t_lazy["h2d_bytes"] < t_full["h2d_bytes"]
+        fetched = t_lazy["h2d_bytes"] - (t_full["h2d_bytes"] - batch.reads.nbytes)
+        ro = batch.read_off.astype(np.int64)
+        assert 0 < fetched <= batch.reads.nbytes
+        per_site = 2 * (ro[10::10] - ro[:-1:10])
+        assert fetched <= per_site[(lazy.status >= 3).any(axis=1)].sum()  # only sites with a slot that reached the caller
+    else:
+        # --usebq 0 / --EM 0: no kernel reads the packed reads, neither path moves them
+        from crisp_b200.abi import _BATCH_ARRAYS
+        total = sum(getattr(batch, name).nbytes for name, _, _ in _BATCH_ARRAYS if getattr(batch, name) is not None)
+        assert t_lazy["h2d_bytes"] == t_full["h2d_bytes"] == total - batch.reads.nbytes
+
+
 def test_benchmark_shape_properties():
     """BASELINE config 2 shape (50 pools x 48, 200x): properties that hold at any size.
       * pool relabelling: permuting the pools permutes AC/QV and leaves the site statistics unchanged (1e-9);
