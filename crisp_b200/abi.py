@@ -84,6 +84,8 @@ class CBatch(C.Structure):
         ("qhigh", C.c_void_p),
         ("stats", C.c_void_p),
         ("tstats", C.c_void_p),
+        ("bin_off", C.c_void_p),
+        ("bins", C.c_void_p),
     ]
 
 
@@ -142,6 +144,7 @@ class Timing(C.Structure):
         ("launches", C.c_int64),
         ("h2d_bytes", C.c_int64),
         ("d2h_bytes", C.c_int64),
+        ("fetched_bytes", C.c_int64),
     ]
 
 
@@ -216,7 +219,33 @@ _BATCH_ARRAYS = [
     ("qhigh", np.float64, False),
     ("stats", np.float64, False),
     ("tstats", np.float64, False),
+    ("bin_off", np.uint32, False),
+    ("bins", np.uint32, False),
 ]
+
+
+def bins_from_reads(read_off: np.ndarray, reads: np.ndarray):
+    """(bin_off, bins) of the compact read format (`crispgpu_bin`): per (site, pool) cell the distinct read values with
+    their multiplicities, ascending by value; counts above 65535 are split over several bins."""
+    ro = read_off.astype(np.int64)
+    ncell = ro.size - 1
+    cell = np.repeat(np.arange(ncell, dtype=np.int64), ro[1:] - ro[:-1])
+    key, cnt = np.unique((cell << 16) | reads.astype(np.int64), return_counts=True)
+    rep = (cnt + 65534) // 65535
+    if (rep > 1).any():
+        key = np.repeat(key, rep)
+        first = np.cumsum(rep) - rep
+        part = np.arange(key.size) - np.repeat(first, rep)
+        cnt = np.minimum(np.repeat(cnt, rep) - part * 65535, 65535)
+    bins = ((cnt.astype(np.uint64) << 16) | (key & 0xFFFF).astype(np.uint64)).astype(np.uint32)
+    per = np.bincount(key >> 16, minlength=ncell)
+    bin_off = np.concatenate([[0], np.cumsum(per)]).astype(np.uint32)
+    return bin_off, bins
+
+
+def reads_from_bins(bin_off: np.ndarray, bins: np.ndarray) -> np.ndarray:
+    """The read multiset a binned batch stands for (cell by cell, bins in order)."""
+    return np.repeat((bins & 0xFFFF).astype(np.uint16), (bins >> 16).astype(np.int64))
 
 
 class Batch:
@@ -247,8 +276,12 @@ class Batch:
         want("counts", n * 24); want("indcounts", n * P * 24); want("indel_len", n * 8); want("hplen", n * 8)
         want("read_off", n * P + 1); want("alt_off", n * 5 + 1); want("amb_idx", n * 5)
         want("qhigh", n * P * 16); want("stats", n * P * 16); want("tstats", n * 16)
-        if n and int(self.read_off[-1]) != self.reads.size:
+        if n and self.reads is not None and int(self.read_off[-1]) != self.reads.size:
             raise ValueError("read_off[-1] != len(reads)")
+        if self.bins is not None:
+            want("bin_off", n * P + 1)
+            if n and (int(self.bin_off[-1]) != self.bins.size or int((self.bins >> 16).sum(dtype=np.int64)) != int(self.read_off[-1])):
+                raise ValueError("bins do not match bin_off / read_off")
         if self.alt_off is not None and (self.alt_reads is None or int(self.alt_off[-1]) != self.alt_reads.size):
             raise ValueError("alt_off[-1] != len(alt_reads)")
         self.n_amb = 0
@@ -259,6 +292,17 @@ class Batch:
 
     def nbytes(self) -> int:
         return sum(getattr(self, name).nbytes for name, _, _ in _BATCH_ARRAYS if getattr(self, name) is not None)
+
+    def binned(self) -> "Batch":
+        """The same batch in the compact read format: `bins`/`bin_off` instead of `reads` (what a front end ships when
+        PCIe is the bound; the engine rebuilds the reads on the device)."""
+        if self.bins is not None:
+            return self
+        out = Batch.__new__(Batch)
+        out.__dict__.update(self.__dict__)
+        out.bin_off, out.bins = bins_from_reads(self.read_off, self.reads)
+        out.reads = None
+        return out
 
     def as_c(self) -> CBatch:
         b = CBatch()

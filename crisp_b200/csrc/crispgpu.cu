@@ -51,6 +51,7 @@ struct crispgpu_ctx {
 	DevBuf d_need_reads;           // per-site flags of the on-demand read fetch
 	const uint16_t* lazy_reads = nullptr;  // device-visible address of the caller's pinned read array (on-demand fetch), or null
 	int64_t copied_bytes = 0;
+	bool binned = false;           // the batch came in the compact (value, count) read format
 	DevBuf d_exact_row, d_exact_cl, d_exact_done;  // exact_mode: term tables of the exact 2 x k test, per-task decided flags
 	// device batch
 	DevBuf d_b[24];
@@ -152,7 +153,7 @@ constexpr int kNumOut = sizeof(kOutFields) / sizeof(kOutFields[0]);
 static_assert(sizeof(DevOut) == (kNumOut + 2) * sizeof(void*), "DevOut must be kNumOut result pointers followed by ac, qv");
 static_assert(sizeof(crispgpu_results) == 8 + (kNumOut + 2) * sizeof(void*), "crispgpu_results layout");
 static_assert(offsetof(crispgpu_results, varalleles) == 8 && offsetof(crispgpu_results, ac) == 8 + kNumOut * sizeof(void*), "crispgpu_results layout");
-static_assert(offsetof(DevBatch, tid) == 8 && sizeof(DevBatch) == 8 + 19 * sizeof(void*), "DevBatch must be 19 array pointers after two ints");
+static_assert(offsetof(DevBatch, tid) == 8 && sizeof(DevBatch) == 8 + 21 * sizeof(void*), "DevBatch must be 21 array pointers after two ints");
 
 void bind_out(crispgpu_ctx* ctx)
 {
@@ -254,7 +255,9 @@ int collect_arrays(crispgpu_ctx* ctx, const crispgpu_batch* b, BatchArray* a)
 	if (!b->tid || !b->pos || !b->refbase || !b->maxvec_al || !b->maxvec_ct || !b->counts || !b->indcounts || !b->read_off) return CRISPGPU_ERR_ARG;
 	const size_t nreads = n ? b->read_off[n * P] : 0;
 	const size_t nalt = (b->alt_off && n) ? b->alt_off[n * 5] : 0;
-	if (nreads && !b->reads) return CRISPGPU_ERR_ARG;
+	const bool binned = b->bins != nullptr || (b->bin_off != nullptr && n && b->bin_off[n * P] == 0);
+	if (nreads && !b->reads && !binned) return CRISPGPU_ERR_ARG;
+	if (binned && !b->bin_off) return CRISPGPU_ERR_ARG;
 	if (nalt && !b->alt_reads) return CRISPGPU_ERR_ARG;
 	if (b->amb_idx && b->n_amb > 0 && !b->amb_dec) return CRISPGPU_ERR_ARG;
 	int k = 0;
@@ -277,6 +280,9 @@ int collect_arrays(crispgpu_ctx* ctx, const crispgpu_batch* b, BatchArray* a)
 	a[k++] = {b->qhigh, b->qhigh ? n * P * 128 : 0};
 	a[k++] = {b->stats, b->stats ? n * P * 128 : 0};
 	a[k++] = {b->tstats, b->tstats ? n * 128 : 0};
+	a[k++] = {binned ? b->bin_off : nullptr, binned ? (n * P + 1) * 4 : 0};
+	a[k++] = {binned ? b->bins : nullptr, binned && n ? (size_t)b->bin_off[n * P] * 4 : 0};
+	if (binned) a[10].host = nullptr;  // the read array is rebuilt on the device
 	return k;
 }
 
@@ -296,12 +302,20 @@ int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b, bool lazy)
 	constexpr size_t kLazyMinBytes = 1 << 20;
 	const bool reads_used = ctx->cfg.em_flag >= 1 && ctx->cfg.use_base_qvs == 1;
 	ctx->lazy_reads = nullptr;
+	ctx->binned = a[19].host != nullptr;
 	for (int i = 0; i < k; i++) {
+		if (i == kReadsArray && ctx->binned && a[i].bytes) {
+			int rc = ensure_dev(ctx, ctx->d_b[i], a[i].bytes);
+			if (rc) return rc;
+			dptr[i] = ctx->d_b[i].p;
+			continue;
+		}
 		if (a[i].bytes == 0 || a[i].host == nullptr) { dptr[i] = nullptr; continue; }
 		int rc = ensure_dev(ctx, ctx->d_b[i], a[i].bytes);
 		if (rc) return rc;
 		if (i == kReadsArray && !reads_used) { dptr[i] = ctx->d_b[i].p; continue; }  // --EM 0 / --usebq 0: no kernel touches the reads
-		if (i == kReadsArray && lazy) {
+		static const bool no_fetch = getenv("CRISPGPU_NO_FETCH") != nullptr;  // measurement switch: copy the whole read array instead
+		if (i == kReadsArray && lazy && !no_fetch) {
 			cudaPointerAttributes at{};
 			if (cudaPointerGetAttributes(&at, a[i].host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer &&
 			    (reinterpret_cast<uintptr_t>(at.devicePointer) & 15) == 0 && a[i].bytes >= kLazyMinBytes) {
@@ -376,7 +390,7 @@ EngineParams make_params(crispgpu_ctx* ctx)
 	prm.q.call_tasks = static_cast<int32_t*>(ctx->d_call_tasks.p);
 	prm.q.call_tasks2 = static_cast<int32_t*>(ctx->d_call_tasks2.p);
 	prm.q.counters = static_cast<int32_t*>(ctx->d_counters.p);
-	prm.q.need_reads = ctx->lazy_reads ? static_cast<uint8_t*>(ctx->d_need_reads.p) : nullptr;
+	prm.q.need_reads = (ctx->lazy_reads || ctx->binned) ? static_cast<uint8_t*>(ctx->d_need_reads.p) : nullptr;
 	prm.gws = static_cast<double*>(ctx->d_gws.p);
 	prm.gws_stride = ctx->gws_stride;
 	return prm;
@@ -395,13 +409,15 @@ int run_stage1(crispgpu_ctx* ctx)
 	int64_t launches = 0;
 	CK(cudaMemsetAsync(ctx->d_counters.p, 0, 16 * sizeof(int32_t), ctx->stream));
 	const bool lazy = ctx->lazy_reads != nullptr && n > 0;
-	if (lazy) {
+	const bool expand = ctx->binned && n > 0 && ctx->n_reads > 0 && g.em_flag >= 1 && g.use_base_qvs == 1;
+	if (!expand) ctx->binned = false;
+	if (lazy || expand) {
 		rc = ensure_dev(ctx, ctx->d_need_reads, (size_t)n); if (rc) return rc;
 		CK(cudaMemsetAsync(ctx->d_need_reads.p, 0, (size_t)n, ctx->stream));
 	} else ctx->lazy_reads = nullptr;
 	EngineParams prm = make_params(ctx);
 	CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
-	const bool scan = n > 0 && g.em_flag >= 1 && g.use_base_qvs == 1 && ctx->n_reads > 0 && !lazy;
+	const bool scan = n > 0 && g.em_flag >= 1 && g.use_base_qvs == 1 && ctx->n_reads > 0 && !lazy && !expand;
 	if (scan) {
 		// fork: the read-stream scan is independent of the count-based screening
 		CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
@@ -533,6 +549,12 @@ int run_stage1(crispgpu_ctx* ctx)
 		launches++;
 		CK(launch_check());
 	}
+	if (expand) {
+		k_expand_bins<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->db.bin_off, ctx->db.bins, ctx->db.read_off, static_cast<uint16_t*>(ctx->d_b[10].p),
+		                                                        static_cast<const uint8_t*>(ctx->d_need_reads.p), n, ctx->P, static_cast<int32_t*>(ctx->d_counters.p));
+		launches++;
+		CK(launch_check());
+	}
 	CK(cudaEventRecord(ctx->ev[EV_FILTER], ctx->stream));
 	// how many tasks reached the caller: sizes the per-pool rows
 	CK(cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -554,7 +576,12 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 	ctx->n_call1 = hc[1];
 	ctx->n_call2 = hc[8];
 	ctx->n_call = hc[1] + hc[8];
-	if (ctx->lazy_reads) ctx->timing.h2d_bytes = ctx->copied_bytes + 2 * (int64_t)(static_cast<uint32_t>(hc[14]) | (static_cast<uint64_t>(static_cast<uint32_t>(hc[15])) << 32));
+	if (hc[12]) {
+		snprintf(ctx->err, sizeof ctx->err, "compact reads: a cell's bin counts do not add up to its read_off span");
+		return CRISPGPU_ERR_ARG;
+	}
+	ctx->timing.fetched_bytes = ctx->lazy_reads ? 2 * (int64_t)(static_cast<uint32_t>(hc[14]) | (static_cast<uint64_t>(static_cast<uint32_t>(hc[15])) << 32)) : 0;
+	ctx->timing.h2d_bytes = ctx->copied_bytes + ctx->timing.fetched_bytes;
 	{
 		// distinct quality characters of the batch -> dense likelihood path when few enough and one pool size
 		int nq = 0;

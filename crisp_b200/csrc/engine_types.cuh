@@ -37,6 +37,8 @@ struct DevBatch {
 	const double* qhigh;
 	const double* stats;
 	const double* tstats;
+	const uint32_t* bin_off;
+	const uint32_t* bins;
 };
 
 struct DevCfg {

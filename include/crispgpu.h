@@ -93,6 +93,11 @@ typedef uint16_t crispgpu_read;
 #define CRISPGPU_READ(qualchar, base, rev, bidir) \
 	((uint16_t)(((qualchar) & 0xff) | (((base) & 3) << 8) | (((rev) ? 1 : 0) << 10) | (((bidir) ? 1 : 0) << 11)))
 
+/* (value, count) pair of the compact read format: low 16 bits = a crispgpu_read value, high 16 bits = how many reads
+ * of the cell carry exactly that value (1..65535; a value may appear in several bins when it occurs more often). */
+typedef uint32_t crispgpu_bin;
+#define CRISPGPU_BIN(read_value, count) ((crispgpu_bin)(((uint32_t)(count) << 16) | (uint32_t)(uint16_t)(read_value)))
+
 /* One alternate-allele read as calculate_uniquereads (parsebam/allelecounts.c:50-77) sees it. */
 typedef struct crispgpu_altread {
 	uint16_t pool;    /* sample */
@@ -144,6 +149,14 @@ typedef struct crispgpu_batch {
 	const double* qhigh;        /* [n][P][16] */
 	const double* stats;        /* [n][P][16] */
 	const double* tstats;       /* [n][16] */
+	/* Compact alternative to `reads` (the likelihood depends on a pool's reads only through how many carry each
+	 * (quality, base, strand, bidirectional) value): cell c = s*P+i owns bins[bin_off[c] .. bin_off[c+1]), any order.
+	 * When `bins` is non-NULL `reads` is ignored and may be NULL; `read_off` is still required and
+	 * read_off[c+1]-read_off[c] must equal the sum of the cell's bin counts (checked on the device for every site that
+	 * reaches the quality-value likelihood; crispgpu_wait fails with CRISPGPU_ERR_ARG otherwise).  The engine rebuilds
+	 * the read multiset in device memory (k_expand_bins), so results are those of the equivalent `reads` batch. */
+	const uint32_t* bin_off;    /* [n*P+1] or NULL */
+	const crispgpu_bin* bins;   /* [bin_off[n*P]] or NULL */
 } crispgpu_batch;
 
 /* Per tested allele slot (al = slot+1 of maxvec), state of the reference's per-allele loop
@@ -210,8 +223,9 @@ typedef struct crispgpu_timing {
 	int32_t n_tasks_em;  /* (site,slot) tasks that reached the EM kernel */
 	int32_t n_tasks_perm;
 	int64_t launches;    /* kernels launched for the batch */
-	int64_t h2d_bytes;
+	int64_t h2d_bytes;   /* bytes moved host -> device for the batch, on-demand fetches included */
 	int64_t d2h_bytes;
+	int64_t fetched_bytes; /* the part of h2d_bytes pulled on demand from pinned host memory (k_fetch_reads; inside filter_ms) */
 } crispgpu_timing;
 
 typedef struct crispgpu_ctx crispgpu_ctx;

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from crisp_b200.abi import EngineConfig, concat_batches
-from crisp_b200.engine import Engine, pin_batch
+from crisp_b200.engine import Engine, EngineError, pin_batch
 from crisp_b200.shard import merge_results, shard_batch
 from crisp_b200.synth import survey_demo_batch, synth_batch
 from golden_io import golden_names, load_golden
@@ -261,6 +261,50 @@ def test_on_demand_read_fetch_equals_full_copy(opts, kw):
         from crisp_b200.abi import _BATCH_ARRAYS
         total = sum(getattr(batch, name).nbytes for name, _, _ in _BATCH_ARRAYS if getattr(batch, name) is not None)
         assert t_lazy["h2d_bytes"] == t_full["h2d_bytes"] == total - batch.reads.nbytes
+
+
+BINNED = ["default_c1", "exome_c2", "varpool", "manyquals", "very_deep_sparse", "very_deep_dense", "big_poolsize_sparse", "indel", "nobq",
+          "perm_c1", "em0", "association"]
+
+
+@pytest.mark.parametrize("name,n,P,ploidy,depth,opts,kw", [s for s in SCENARIOS if s[0] in BINNED], ids=BINNED)
+def test_compact_read_format_matches_oracle(name, n, P, ploidy, depth, opts, kw):
+    """The same scenarios shipped as (value, count) bins instead of one element per read (k_expand_bins)."""
+    cfg = _cfg(P, ploidy, opts)
+    batch = synth_batch(n, P, cfg.ploidy, depth, seed=11, **kw)
+    want = OracleEngine(cfg).run(batch, mode=RNG_PHILOX)
+    compact = batch.binned()
+    assert compact.reads is None
+    if name != "manyquals":   # 28 quality values at 100x: more distinct values than reads to share them
+        assert compact.bins.nbytes < batch.reads.nbytes
+    eng = Engine(cfg)
+    got = eng.run(compact)
+    pinned = eng.run(pin_batch(compact))
+    eng.upload(compact)
+    resident = eng.run_resident(fetch=True)
+    eng.close()
+    skip = ("assoc_p", "assoc_p1") if opts.get("association") else ()
+    compare_results(got, want, label=name, fp_skip=skip)
+    compare_results(pinned, got, tol=0.0, label=name + "-pinned")
+    compare_results(resident, got, tol=0.0, label=name + "-resident")
+
+
+def test_compact_read_format_splits_large_counts_and_rejects_bad_counts():
+    from crisp_b200.abi import bins_from_reads, reads_from_bins
+    cfg = _cfg(2, 20, {})
+    batch = synth_batch(4, 2, cfg.ploidy, 140000, seed=3, variant_frac=1.0, quals=[30])
+    bo, bins = bins_from_reads(batch.read_off, batch.reads)
+    assert (bins >> 16).max() == 65535 and np.array_equal(np.sort(reads_from_bins(bo, bins)[: batch.read_off[1]]), np.sort(batch.reads[: batch.read_off[1]]))
+    want = OracleEngine(cfg).run(batch, mode=RNG_PHILOX)
+    eng = Engine(cfg)
+    compare_results(eng.run(batch.binned()), want, label="split")
+    bad = batch.binned()
+    bad.bins = bad.bins.copy()
+    bad.bins[0] -= 1 << 16   # one read short of read_off
+    with pytest.raises(EngineError, match="bin counts"):
+        eng.run(bad)
+    compare_results(eng.run(batch.binned()), want, label="after-error")   # the context stays usable
+    eng.close()
 
 
 def test_benchmark_shape_properties():
