@@ -86,6 +86,8 @@ class CBatch(C.Structure):
         ("tstats", C.c_void_p),
         ("bin_off", C.c_void_p),
         ("bins", C.c_void_p),
+        ("ic_off", C.c_void_p),
+        ("ic_sparse", C.c_void_p),
     ]
 
 
@@ -221,7 +223,21 @@ _BATCH_ARRAYS = [
     ("tstats", np.float64, False),
     ("bin_off", np.uint32, False),
     ("bins", np.uint32, False),
+    ("ic_off", np.uint32, False),
+    ("ic_sparse", np.uint32, False),
 ]
+
+
+def sparse_counts_from_dense(indcounts: np.ndarray):
+    """(ic_off, ic_sparse): the non-zero entries of every pool's 24-entry indcounts row as `crispgpu_count` words."""
+    rows = indcounts.reshape(-1, 24)
+    cell, idx = np.nonzero(rows)
+    val = rows[cell, idx].astype(np.int64)
+    if val.size and (val.min() < 0 or val.max() >= (1 << 27)):
+        raise ValueError("allele counts outside the 27-bit range of the sparse format")
+    ic = ((idx.astype(np.uint64) << 27) | val.astype(np.uint64)).astype(np.uint32)
+    off = np.concatenate([[0], np.cumsum(np.bincount(cell, minlength=rows.shape[0]))]).astype(np.uint32)
+    return off, ic
 
 
 def bins_from_reads(read_off: np.ndarray, reads: np.ndarray):
@@ -278,6 +294,12 @@ class Batch:
         want("qhigh", n * P * 16); want("stats", n * P * 16); want("tstats", n * 16)
         if n and self.reads is not None and int(self.read_off[-1]) != self.reads.size:
             raise ValueError("read_off[-1] != len(reads)")
+        if self.ic_off is not None:
+            want("ic_off", n * P + 1)
+            if n and int(self.ic_off[-1]) != (0 if self.ic_sparse is None else self.ic_sparse.size):
+                raise ValueError("ic_off[-1] != len(ic_sparse)")
+        elif self.indcounts is None:
+            raise ValueError("batch needs indcounts or ic_off/ic_sparse")
         if self.bins is not None:
             want("bin_off", n * P + 1)
             if n and (int(self.bin_off[-1]) != self.bins.size or int((self.bins >> 16).sum(dtype=np.int64)) != int(self.read_off[-1])):
@@ -302,6 +324,18 @@ class Batch:
         out.__dict__.update(self.__dict__)
         out.bin_off, out.bins = bins_from_reads(self.read_off, self.reads)
         out.reads = None
+        return out
+
+    def compact(self) -> "Batch":
+        """Transfer-optimised form: reads as (value, count) bins and the per-pool allele counts as their non-zero entries
+        (both rebuilt in device memory by the engine); about a fifth of the bytes on binned-quality data."""
+        out = self.binned()
+        if out is self:
+            out = Batch.__new__(Batch)
+            out.__dict__.update(self.__dict__)
+        if out.ic_off is None:
+            out.ic_off, out.ic_sparse = sparse_counts_from_dense(self.indcounts)
+            out.indcounts = None
         return out
 
     def as_c(self) -> CBatch:

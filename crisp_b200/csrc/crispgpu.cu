@@ -51,6 +51,7 @@ struct crispgpu_ctx {
 	DevBuf d_need_reads;           // per-site flags of the on-demand read fetch
 	const uint16_t* lazy_reads = nullptr;  // device-visible address of the caller's pinned read array (on-demand fetch), or null
 	int64_t copied_bytes = 0;
+	bool sparse_ic = false;        // the batch came with sparse per-pool allele counts
 	bool binned = false;           // the batch came in the compact (value, count) read format
 	DevBuf d_exact_row, d_exact_cl, d_exact_done;  // exact_mode: term tables of the exact 2 x k test, per-task decided flags
 	// device batch
@@ -153,7 +154,7 @@ constexpr int kNumOut = sizeof(kOutFields) / sizeof(kOutFields[0]);
 static_assert(sizeof(DevOut) == (kNumOut + 2) * sizeof(void*), "DevOut must be kNumOut result pointers followed by ac, qv");
 static_assert(sizeof(crispgpu_results) == 8 + (kNumOut + 2) * sizeof(void*), "crispgpu_results layout");
 static_assert(offsetof(crispgpu_results, varalleles) == 8 && offsetof(crispgpu_results, ac) == 8 + kNumOut * sizeof(void*), "crispgpu_results layout");
-static_assert(offsetof(DevBatch, tid) == 8 && sizeof(DevBatch) == 8 + 21 * sizeof(void*), "DevBatch must be 21 array pointers after two ints");
+static_assert(offsetof(DevBatch, tid) == 8 && sizeof(DevBatch) == 8 + 23 * sizeof(void*), "DevBatch must be 23 array pointers after two ints");
 
 void bind_out(crispgpu_ctx* ctx)
 {
@@ -252,7 +253,8 @@ struct BatchArray { const void* host; size_t bytes; };
 int collect_arrays(crispgpu_ctx* ctx, const crispgpu_batch* b, BatchArray* a)
 {
 	const size_t n = b->n_sites, P = ctx->P;
-	if (!b->tid || !b->pos || !b->refbase || !b->maxvec_al || !b->maxvec_ct || !b->counts || !b->indcounts || !b->read_off) return CRISPGPU_ERR_ARG;
+	const bool sparse_ic = b->ic_off != nullptr && (b->ic_sparse != nullptr || (n && b->ic_off[n * P] == 0));
+	if (!b->tid || !b->pos || !b->refbase || !b->maxvec_al || !b->maxvec_ct || !b->counts || (!b->indcounts && !sparse_ic) || !b->read_off) return CRISPGPU_ERR_ARG;
 	const size_t nreads = n ? b->read_off[n * P] : 0;
 	const size_t nalt = (b->alt_off && n) ? b->alt_off[n * 5] : 0;
 	const bool binned = b->bins != nullptr || (b->bin_off != nullptr && n && b->bin_off[n * P] == 0);
@@ -283,6 +285,9 @@ int collect_arrays(crispgpu_ctx* ctx, const crispgpu_batch* b, BatchArray* a)
 	a[k++] = {binned ? b->bin_off : nullptr, binned ? (n * P + 1) * 4 : 0};
 	a[k++] = {binned ? b->bins : nullptr, binned && n ? (size_t)b->bin_off[n * P] * 4 : 0};
 	if (binned) a[10].host = nullptr;  // the read array is rebuilt on the device
+	a[k++] = {sparse_ic ? b->ic_off : nullptr, sparse_ic ? (n * P + 1) * 4 : 0};
+	a[k++] = {sparse_ic ? b->ic_sparse : nullptr, sparse_ic && n ? (size_t)b->ic_off[n * P] * 4 : 0};
+	if (sparse_ic) a[6].host = nullptr;  // the dense table is rebuilt on the device
 	return k;
 }
 
@@ -303,7 +308,14 @@ int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b, bool lazy)
 	const bool reads_used = ctx->cfg.em_flag >= 1 && ctx->cfg.use_base_qvs == 1;
 	ctx->lazy_reads = nullptr;
 	ctx->binned = a[19].host != nullptr;
+	ctx->sparse_ic = a[21].host != nullptr;
 	for (int i = 0; i < k; i++) {
+		if (i == 6 && ctx->sparse_ic) {
+			int rc = ensure_dev(ctx, ctx->d_b[i], a[i].bytes ? a[i].bytes : 1);
+			if (rc) return rc;
+			dptr[i] = ctx->d_b[i].p;
+			continue;
+		}
 		if (i == kReadsArray && ctx->binned && a[i].bytes) {
 			int rc = ensure_dev(ctx, ctx->d_b[i], a[i].bytes);
 			if (rc) return rc;
@@ -313,6 +325,7 @@ int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b, bool lazy)
 		if (a[i].bytes == 0 || a[i].host == nullptr) { dptr[i] = nullptr; continue; }
 		int rc = ensure_dev(ctx, ctx->d_b[i], a[i].bytes);
 		if (rc) return rc;
+		if ((i == 19 || i == 20) && !reads_used) { dptr[i] = nullptr; continue; }
 		if (i == kReadsArray && !reads_used) { dptr[i] = ctx->d_b[i].p; continue; }  // --EM 0 / --usebq 0: no kernel touches the reads
 		static const bool no_fetch = getenv("CRISPGPU_NO_FETCH") != nullptr;  // measurement switch: copy the whole read array instead
 		if (i == kReadsArray && lazy && !no_fetch) {
@@ -416,6 +429,13 @@ int run_stage1(crispgpu_ctx* ctx)
 		CK(cudaMemsetAsync(ctx->d_need_reads.p, 0, (size_t)n, ctx->stream));
 	} else ctx->lazy_reads = nullptr;
 	EngineParams prm = make_params(ctx);
+	if (ctx->sparse_ic && n > 0) {
+		const size_t cells = (size_t)n * ctx->P;
+		CK(cudaMemsetAsync(ctx->d_b[6].p, 0, cells * kNC * sizeof(int32_t), ctx->stream));
+		k_expand_counts<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->db.ic_off, ctx->db.ic_sparse, static_cast<int32_t*>(ctx->d_b[6].p), cells);
+		launches++;
+		CK(launch_check());
+	}
 	CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
 	const bool scan = n > 0 && g.em_flag >= 1 && g.use_base_qvs == 1 && ctx->n_reads > 0 && !lazy && !expand;
 	if (scan) {

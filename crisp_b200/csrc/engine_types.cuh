@@ -39,6 +39,8 @@ struct DevBatch {
 	const double* tstats;
 	const uint32_t* bin_off;
 	const uint32_t* bins;
+	const uint32_t* ic_off;
+	const uint32_t* ic_sparse;
 };
 
 struct DevCfg {

@@ -374,6 +374,20 @@ __global__ void k_fetch_reads(const uint16_t* __restrict__ src, uint16_t* __rest
 		if (seen[q]) atomicOr(reinterpret_cast<unsigned int*>(counters) + 4 + (q >> 5), 1u << (q & 31));
 }
 
+// Sparse per-pool allele counts -> the dense [n][P][24] table the kernels index (zeroed beforehand): one thread per entry.
+__global__ void k_expand_counts(const uint32_t* __restrict__ ic_off, const uint32_t* __restrict__ ic_sparse, int32_t* __restrict__ indcounts, size_t n_cells)
+{
+	for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < n_cells; c += (size_t)gridDim.x * blockDim.x) {
+		const uint32_t e0 = ic_off[c], e1 = ic_off[c + 1];
+		int32_t* row = indcounts + c * kNC;
+		for (uint32_t e = e0; e < e1; e++) {
+			const uint32_t x = __ldg(ic_sparse + e);
+			const uint32_t idx = x >> 27;
+			if (idx < (uint32_t)kNC) row[idx] = (int32_t)(x & 0x7ffffffu);
+		}
+	}
+}
+
 // Compact read format -> packed reads: a (site, pool) cell arrives as (value, count) bins and is rebuilt in the device
 // read buffer at read_off (the order inside a cell is immaterial to the likelihood).  One warp per cell: lanes load
 // up to 32 bins, each bin is broadcast and written by the whole warp.  Only sites flagged by the screening kernels are

@@ -34,8 +34,14 @@ crisp_shim_batch* crisp_shim_batch_new(int n_pools, int want_qhigh, int want_sta
 	sb->want_stats = want_stats;
 	sb->read_off = (uint32_t*)calloc(1, sizeof(uint32_t));
 	sb->alt_off = (uint32_t*)calloc(1, sizeof(uint32_t));
+	sb->bin_off = (uint32_t*)calloc(1, sizeof(uint32_t));
+	sb->ic_off = (uint32_t*)calloc(1, sizeof(uint32_t));
+	sb->bin_count = (uint32_t*)calloc(4096, sizeof(uint32_t));
+	sb->bin_touched = (uint16_t*)calloc(4096, sizeof(uint16_t));
 	return sb;
 }
+
+void crisp_shim_batch_set_compact(crisp_shim_batch* sb, int compact) { sb->compact = compact != 0; }
 
 void crisp_shim_batch_clear(crisp_shim_batch* sb)
 {
@@ -44,6 +50,10 @@ void crisp_shim_batch_clear(crisp_shim_batch* sb)
 	sb->n_amb = 0;
 	sb->read_off[0] = 0;
 	sb->alt_off[0] = 0;
+	sb->n_bins = 0;
+	sb->bin_off[0] = 0;
+	sb->n_ic = 0;
+	sb->ic_off[0] = 0;
 }
 
 void crisp_shim_batch_free(crisp_shim_batch* sb)
@@ -52,6 +62,7 @@ void crisp_shim_batch_free(crisp_shim_batch* sb)
 	free(sb->tid); free(sb->pos); free(sb->maxvec_ct); free(sb->counts); free(sb->indcounts); free(sb->amb_idx); free(sb->amb_dec);
 	free(sb->refbase); free(sb->maxvec_al); free(sb->indel_len); free(sb->hplen); free(sb->read_off); free(sb->alt_off);
 	free(sb->reads); free(sb->alt_reads); free(sb->amb_ep); free(sb->qhigh); free(sb->stats); free(sb->tstats);
+	free(sb->bin_off); free(sb->bins); free(sb->bin_count); free(sb->bin_touched); free(sb->ic_off); free(sb->ic_sparse);
 	free(sb);
 }
 
@@ -61,7 +72,9 @@ void crisp_shim_batch_view(const crisp_shim_batch* sb, crispgpu_batch* b)
 	b->n_sites = sb->n_sites;
 	b->tid = sb->tid; b->pos = sb->pos; b->refbase = sb->refbase; b->maxvec_al = sb->maxvec_al; b->maxvec_ct = sb->maxvec_ct;
 	b->counts = sb->counts; b->indcounts = sb->indcounts; b->indel_len = sb->indel_len; b->hplen = sb->hplen;
-	b->read_off = sb->read_off; b->reads = sb->reads; b->alt_off = sb->alt_off; b->alt_reads = sb->alt_reads;
+	b->read_off = sb->read_off; b->reads = sb->compact ? NULL : sb->reads;
+	if (sb->compact) { b->bin_off = sb->bin_off; b->bins = sb->bins; b->ic_off = sb->ic_off; b->ic_sparse = sb->ic_sparse; b->indcounts = NULL; }
+	b->alt_off = sb->alt_off; b->alt_reads = sb->alt_reads;
 	b->amb_idx = sb->amb_idx; b->amb_dec = sb->amb_dec; b->amb_ep = sb->amb_ep; b->n_amb = sb->n_amb;
 	b->qhigh = sb->want_qhigh ? sb->qhigh : NULL;
 	b->stats = sb->want_stats ? sb->stats : NULL;
@@ -78,6 +91,8 @@ static void reserve_site(crisp_shim_batch* sb)
 		sb->maxvec_ct = (int32_t*)realloc(sb->maxvec_ct, c * 32); sb->counts = (int32_t*)realloc(sb->counts, c * 96);
 		sb->indcounts = (int32_t*)realloc(sb->indcounts, c * P * 96);
 		sb->indel_len = (int16_t*)realloc(sb->indel_len, c * 16); sb->hplen = (int16_t*)realloc(sb->hplen, c * 16);
+		sb->bin_off = (uint32_t*)realloc(sb->bin_off, (c * P + 1) * 4);
+		sb->ic_off = (uint32_t*)realloc(sb->ic_off, (c * P + 1) * 4);
 		sb->read_off = (uint32_t*)realloc(sb->read_off, (c * P + 1) * 4); sb->alt_off = (uint32_t*)realloc(sb->alt_off, (c * 5 + 1) * 4);
 		sb->amb_idx = (int32_t*)realloc(sb->amb_idx, c * 20);
 		sb->qhigh = (double*)realloc(sb->qhigh, c * P * 128); sb->stats = (double*)realloc(sb->stats, c * P * 128);
@@ -97,6 +112,15 @@ int crisp_shim_append_site(crisp_shim_batch* sb, REFLIST* reflist, int current, 
 	for (int k = 0; k < 8; k++) { sb->maxvec_al[s * 8 + k] = (uint8_t)maxvec[k].al; sb->maxvec_ct[s * 8 + k] = maxvec[k].ct; }
 	memcpy(sb->counts + (size_t)s * 24, variant->counts, 24 * sizeof(int));
 	for (int i = 0; i < P; i++) memcpy(sb->indcounts + ((size_t)s * P + i) * 24, variant->indcounts[i], 24 * sizeof(int));
+	if (sb->compact)
+		for (int i = 0; i < P; i++) {
+			for (int q = 0; q < 24; q++) {
+				if (variant->indcounts[i][q] == 0) continue;
+				GROW(sb->ic_sparse, sb->cap_ic, sb->n_ic + 1, crispgpu_count);
+				sb->ic_sparse[sb->n_ic++] = CRISPGPU_COUNT(q, variant->indcounts[i][q]);
+			}
+			sb->ic_off[(size_t)s * P + i + 1] = (uint32_t)sb->n_ic;
+		}
 	for (int i = 0; i < P; i++)
 		for (int q = 0; q < 16; q++) {
 			sb->qhigh[((size_t)s * P + i) * 16 + q] = variant->Qhighcounts[i][q];
@@ -119,15 +143,44 @@ int crisp_shim_append_site(crisp_shim_batch* sb, REFLIST* reflist, int current, 
 		sb->hplen[s * 8 + a] = (int16_t)variant->HPlength[a];
 	}
 	/* 1. likelihood stream: what calculate_pooled_likelihoods_snp reads (crispEM.c:104-110) */
+	int ntouched = 0;
 	for (int i = 0; i < P; i++) {
 		for (struct alignedread* r = bd[i].first; r != NULL && r->position <= variant->position; r = r->nextread) {
 			if (r->lastpos < variant->position) continue;
 			if (r->filter != '0' || r->type != 0) continue;
-			GROW(sb->reads, sb->cap_reads, sb->n_reads + 1, crispgpu_read);
 			const int o = r->l1 + r->delta;
-			sb->reads[sb->n_reads++] = CRISPGPU_READ((unsigned char)r->quality[o], BTI[(unsigned char)r->sequence[o]], r->strand, r->bidir == 1);
+			const crispgpu_read w = CRISPGPU_READ((unsigned char)r->quality[o], BTI[(unsigned char)r->sequence[o]], r->strand, r->bidir == 1);
+			if (sb->compact) {
+				if (sb->bin_count[w & 4095]++ == 0) sb->bin_touched[ntouched++] = (uint16_t)(w & 4095);
+				sb->n_reads++;
+				continue;
+			}
+			GROW(sb->reads, sb->cap_reads, sb->n_reads + 1, crispgpu_read);
+			sb->reads[sb->n_reads++] = w;
 		}
 		sb->read_off[(size_t)s * P + i + 1] = (uint32_t)sb->n_reads;
+		if (sb->compact) {
+			/* emit the cell's bins in ascending value order; a multiplicity above 65535 takes several bins */
+			for (int x = 1; x < ntouched; x++) {
+				const uint16_t t = sb->bin_touched[x];
+				int y = x - 1;
+				for (; y >= 0 && sb->bin_touched[y] > t; y--) sb->bin_touched[y + 1] = sb->bin_touched[y];
+				sb->bin_touched[y + 1] = t;
+			}
+			for (int x = 0; x < ntouched; x++) {
+				const uint16_t v = sb->bin_touched[x];
+				uint32_t left = sb->bin_count[v];
+				sb->bin_count[v] = 0;
+				while (left > 0) {
+					const uint32_t take = left > 65535 ? 65535 : left;
+					GROW(sb->bins, sb->cap_bins, sb->n_bins + 1, crispgpu_bin);
+					sb->bins[sb->n_bins++] = CRISPGPU_BIN(v, take);
+					left -= take;
+				}
+			}
+			ntouched = 0;
+			sb->bin_off[(size_t)s * P + i + 1] = (uint32_t)sb->n_bins;
+		}
 	}
 	/* 2. alt-read side list: what calculate_uniquereads collects (allelecounts.c:47-67), per tested slot and pool */
 	for (int k = 0; k < 5; k++) {

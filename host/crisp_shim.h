@@ -26,9 +26,23 @@ typedef struct crisp_shim_batch {
 	crispgpu_read* reads;
 	crispgpu_altread* alt_reads;
 	double *amb_ep, *qhigh, *stats, *tstats;
+	/* compact read format (crispgpu_bin): per (site, pool) the distinct read values with their multiplicities */
+	int compact;
+	size_t n_bins, cap_bins;
+	uint32_t* bin_off;
+	crispgpu_bin* bins;
+	size_t n_ic, cap_ic;
+	uint32_t* ic_off;
+	crispgpu_count* ic_sparse; /* compact mode: non-zero entries of every pool's indcounts row */
+	uint32_t* bin_count;    /* [4096] scratch: multiplicity of each 12-bit read value in the current cell */
+	uint16_t* bin_touched;  /* [4096] scratch: values seen in the current cell */
 } crisp_shim_batch;
 
 crisp_shim_batch* crisp_shim_batch_new(int n_pools, int want_qhigh, int want_stats);
+/* compact = 1: emit `bins`/`bin_off` instead of one element per read and `ic_sparse`/`ic_off` instead of the dense
+ * indcounts table (about a fifth of the bytes on binned-quality data; the engine rebuilds both on the device).
+ * Choose before the first append of a batch. */
+void crisp_shim_batch_set_compact(crisp_shim_batch* sb, int compact);
 void crisp_shim_batch_clear(crisp_shim_batch* sb);
 void crisp_shim_batch_free(crisp_shim_batch* sb);
 /* view of the accumulated sites as the ABI batch (pointers into sb; valid until the next append/clear) */

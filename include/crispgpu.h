@@ -98,6 +98,10 @@ typedef uint16_t crispgpu_read;
 typedef uint32_t crispgpu_bin;
 #define CRISPGPU_BIN(read_value, count) ((crispgpu_bin)(((uint32_t)(count) << 16) | (uint32_t)(uint16_t)(read_value)))
 
+/* One non-zero entry of a pool's indcounts row: bits 27..31 = index (allele + 8*strand class, 0..23), bits 0..26 = count. */
+typedef uint32_t crispgpu_count;
+#define CRISPGPU_COUNT(index, count) ((crispgpu_count)(((uint32_t)(index) << 27) | ((uint32_t)(count) & 0x7ffffffu)))
+
 /* One alternate-allele read as calculate_uniquereads (parsebam/allelecounts.c:50-77) sees it. */
 typedef struct crispgpu_altread {
 	uint16_t pool;    /* sample */
@@ -157,6 +161,12 @@ typedef struct crispgpu_batch {
 	 * the read multiset in device memory (k_expand_bins), so results are those of the equivalent `reads` batch. */
 	const uint32_t* bin_off;    /* [n*P+1] or NULL */
 	const crispgpu_bin* bins;   /* [bin_off[n*P]] or NULL */
+	/* Compact alternative to `indcounts` (a pool's 24-entry row is mostly zeros): cell c owns
+	 * ic_sparse[ic_off[c] .. ic_off[c+1]), the non-zero entries of variant->indcounts[i] in any order.  When
+	 * `ic_sparse` (or an all-empty `ic_off`) is given `indcounts` is ignored and may be NULL; the engine scatters the
+	 * entries into a zeroed dense table on the device (k_expand_counts). */
+	const uint32_t* ic_off;          /* [n*P+1] or NULL */
+	const crispgpu_count* ic_sparse; /* [ic_off[n*P]] or NULL */
 } crispgpu_batch;
 
 /* Per tested allele slot (al = slot+1 of maxvec), state of the reference's per-allele loop

@@ -761,6 +761,9 @@ int crisp_ref_shim_roundtrip(void* h, const crispgpu_batch* b, char* msg, size_t
 	const int P = c->P, n = b->n_sites;
 	apply_config(c);
 	crisp_shim_batch* sb = crisp_shim_batch_new(P, b->qhigh != NULL, b->stats != NULL);
+	/* a batch that also carries bins asks for the compact packer: its bins must come back, the reads are not emitted */
+	const int compact = b->bins != NULL && b->bin_off != NULL;
+	crisp_shim_batch_set_compact(sb, compact);
 	ALLELE maxvec[8];
 	int bad = 0;
 	if (msg && msgcap) msg[0] = 0;
@@ -782,9 +785,20 @@ int crisp_ref_shim_roundtrip(void* h, const crispgpu_batch* b, char* msg, size_t
 	} while (0)
 	if (g.n_sites != n) { bad++; if (msg) snprintf(msg, msgcap, "site count %d vs %d", g.n_sites, n); }
 	CMP(tid, (size_t)n * 4); CMP(pos, (size_t)n * 4); CMP(refbase, (size_t)n); CMP(maxvec_al, (size_t)n * 8); CMP(maxvec_ct, (size_t)n * 32);
-	CMP(counts, (size_t)n * 96); CMP(indcounts, (size_t)n * P * 96); CMP(indel_len, (size_t)n * 16); CMP(hplen, (size_t)n * 16);
+	CMP(counts, (size_t)n * 96);
+	if (!compact) CMP(indcounts, (size_t)n * P * 96);
+	else if (b->ic_off) {
+		if (g.indcounts != NULL) { bad++; if (msg) snprintf(msg, msgcap, "compact view still exposes indcounts"); }
+		CMP(ic_off, ((size_t)n * P + 1) * 4);
+		if (n && g.ic_off[(size_t)n * P] == b->ic_off[(size_t)n * P]) CMP(ic_sparse, (size_t)b->ic_off[(size_t)n * P] * 4);
+	} CMP(indel_len, (size_t)n * 16); CMP(hplen, (size_t)n * 16);
 	CMP(read_off, ((size_t)n * P + 1) * 4);
-	if (n) CMP(reads, (size_t)b->read_off[(size_t)n * P] * 2);
+	if (n && !compact) CMP(reads, (size_t)b->read_off[(size_t)n * P] * 2);
+	if (compact) {
+		if (g.reads != NULL) { bad++; if (msg) snprintf(msg, msgcap, "compact view still exposes reads"); }
+		CMP(bin_off, ((size_t)n * P + 1) * 4);
+		if (n && g.bin_off[(size_t)n * P] == b->bin_off[(size_t)n * P]) CMP(bins, (size_t)b->bin_off[(size_t)n * P] * 4);
+	}
 	if (b->alt_off) {
 		CMP(alt_off, ((size_t)n * 5 + 1) * 4);
 		if (n && g.alt_off[n * 5] == b->alt_off[n * 5]) CMP(alt_reads, (size_t)b->alt_off[n * 5] * sizeof(crispgpu_altread));

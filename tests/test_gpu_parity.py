@@ -282,11 +282,19 @@ def test_compact_read_format_matches_oracle(name, n, P, ploidy, depth, opts, kw)
     pinned = eng.run(pin_batch(compact))
     eng.upload(compact)
     resident = eng.run_resident(fetch=True)
+    # ... and with the per-pool allele counts as their non-zero entries only (k_expand_counts)
+    full = batch.compact()
+    assert full.indcounts is None and full.ic_sparse.nbytes <= batch.indcounts.nbytes // 3   # at most 8 of 24 entries in use without indels
+    sparse = eng.run(pin_batch(full))
+    t = eng.timing()
     eng.close()
     skip = ("assoc_p", "assoc_p1") if opts.get("association") else ()
     compare_results(got, want, label=name, fp_skip=skip)
     compare_results(pinned, got, tol=0.0, label=name + "-pinned")
     compare_results(resident, got, tol=0.0, label=name + "-resident")
+    compare_results(sparse, got, tol=0.0, label=name + "-sparse-counts")
+    used = full.nbytes() - (0 if opts.get("em_flag", 1) >= 1 and opts.get("use_base_qvs", 1) == 1 else full.bins.nbytes + full.bin_off.nbytes)
+    assert t["h2d_bytes"] == used
 
 
 def test_compact_read_format_splits_large_counts_and_rejects_bad_counts():

@@ -110,3 +110,29 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "sites/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
+
+
+def test_compact_formats_round_trip():
+    """bins_from_reads / sparse_counts_from_dense are exact re-encodings (what k_expand_bins / k_expand_counts undo)."""
+    from crisp_b200.abi import bins_from_reads, reads_from_bins, sparse_counts_from_dense
+    batch = synth_batch(60, 6, np.full(6, 20), 80, seed=5, variant_frac=0.4, bidir_frac=0.1, indel_frac=0.3)
+    bo, bins = bins_from_reads(batch.read_off, batch.reads)
+    back = reads_from_bins(bo, bins)
+    ro = batch.read_off.astype(np.int64)
+    assert back.size == batch.reads.size
+    for c in range(ro.size - 1):
+        assert np.array_equal(np.sort(batch.reads[ro[c]:ro[c + 1]]), back[ro[c]:ro[c + 1]])
+        cell = bins[bo[c]:bo[c + 1]] & 0xFFFF
+        assert np.all(cell[1:] > cell[:-1])            # ascending, distinct values
+    off, ic = sparse_counts_from_dense(batch.indcounts)
+    dense = np.zeros_like(batch.indcounts).reshape(-1, 24)
+    cell = np.repeat(np.arange(off.size - 1), np.diff(off.astype(np.int64)))
+    dense[cell, ic >> 27] = ic & 0x7FFFFFF
+    assert np.array_equal(dense.reshape(-1), batch.indcounts)
+    c = batch.compact()
+    c.validate()
+    assert c.reads is None and c.indcounts is None and c.nbytes() < batch.nbytes()
+    # a multiplicity above 65535 is split over consecutive bins of the same value
+    ro1 = np.array([0, 140000], np.uint32)
+    bo1, b1 = bins_from_reads(ro1, np.full(140000, 0x1A1E, np.uint16))
+    assert b1.tolist() == [(65535 << 16) | 0x1A1E, (65535 << 16) | 0x1A1E, (8930 << 16) | 0x1A1E] and bo1.tolist() == [0, 3]

@@ -178,8 +178,16 @@ def test_host_shim_round_trip(kw):
     of the shim (crisp_shim_fill_variant) is what test_oracle_equals_reference's VCF replay goes through."""
     cfg = _cfg(P=8)
     batch = synth_batch(120, 8, cfg.ploidy, 80, seed=41, **kw)
-    bad, msg = RefEngine(cfg).shim_roundtrip(batch)
+    ref = RefEngine(cfg)
+    bad, msg = ref.shim_roundtrip(batch)
     assert bad == 0, msg
+    # compact mode of the packer: the same read lists come back as the (value, count) bins bins_from_reads derives
+    from crisp_b200.abi import bins_from_reads
+    both = batch.compact()
+    both.reads, both.indcounts = batch.reads, batch.indcounts   # the harness rebuilds the reference's structures from these
+    bad, msg = ref.shim_roundtrip(both)
+    assert bad == 0, msg
+    assert np.array_equal(bins_from_reads(batch.read_off, batch.reads)[1], both.bins)
 
 
 # ---- exact 2 x k test (exact_mode; specification FET/contables_exact.c:62-117) ------------------------------------------
