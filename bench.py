@@ -165,8 +165,8 @@ def main():
     ap.add_argument("--sites", type=int, default=8192, help="candidate sites per GPU per step")
     ap.add_argument("--cpu-sites-per-core", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-format", default="bins", choices=["bins", "reads"],
-                    help="host-side read format of the end-to-end leg: compact (read bins + sparse allele counts), or dense arrays with one element per read")
+    ap.add_argument("--format", "--e2e-format", dest="e2e_format", default="bins", choices=["bins", "reads"],
+                    help="batch format of both legs: compact (read bins + sparse allele counts), or dense arrays with one element per read")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -227,7 +227,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput ----------------
-    eng.upload(batch)
+    eng.upload(batch.compact() if args.e2e_format == "bins" else batch)
     for _ in range(args.warmup):
         eng.run_resident(fetch=False)
     sampler = ClockSampler(local)

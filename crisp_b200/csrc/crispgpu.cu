@@ -51,6 +51,7 @@ struct crispgpu_ctx {
 	DevBuf d_need_reads;           // per-site flags of the on-demand read fetch
 	const uint16_t* lazy_reads = nullptr;  // device-visible address of the caller's pinned read array (on-demand fetch), or null
 	int64_t copied_bytes = 0;
+	bool bins_direct = false;      // k_em reads the bins themselves (dense likelihood path)
 	bool sparse_ic = false;        // the batch came with sparse per-pool allele counts
 	bool binned = false;           // the batch came in the compact (value, count) read format
 	DevBuf d_exact_row, d_exact_cl, d_exact_done;  // exact_mode: term tables of the exact 2 x k test, per-task decided flags
@@ -403,6 +404,7 @@ EngineParams make_params(crispgpu_ctx* ctx)
 	prm.q.call_tasks = static_cast<int32_t*>(ctx->d_call_tasks.p);
 	prm.q.call_tasks2 = static_cast<int32_t*>(ctx->d_call_tasks2.p);
 	prm.q.counters = static_cast<int32_t*>(ctx->d_counters.p);
+	if (!ctx->bins_direct) { prm.b.bins = nullptr; prm.b.bin_off = nullptr; }
 	prm.q.need_reads = (ctx->lazy_reads || ctx->binned) ? static_cast<uint8_t*>(ctx->d_need_reads.p) : nullptr;
 	prm.gws = static_cast<double*>(ctx->d_gws.p);
 	prm.gws_stride = ctx->gws_stride;
@@ -570,8 +572,10 @@ int run_stage1(crispgpu_ctx* ctx)
 		CK(launch_check());
 	}
 	if (expand) {
-		k_expand_bins<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->db.bin_off, ctx->db.bins, ctx->db.read_off, static_cast<uint16_t*>(ctx->d_b[10].p),
-		                                                        static_cast<const uint8_t*>(ctx->d_need_reads.p), n, ctx->P, static_cast<int32_t*>(ctx->d_counters.p));
+		// the bins double as the likelihood histogram (dense path of k_em); here only which qualities occur.  The reads are
+		// rebuilt (k_expand_bins, stage 2) only when the batch needs the sparse likelihood path.
+		k_scan_bins<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->db.bin_off, ctx->db.bins, static_cast<const uint8_t*>(ctx->d_need_reads.p), n, ctx->P,
+		                                                      static_cast<int32_t*>(ctx->d_counters.p));
 		launches++;
 		CK(launch_check());
 	}
@@ -596,10 +600,6 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 	ctx->n_call1 = hc[1];
 	ctx->n_call2 = hc[8];
 	ctx->n_call = hc[1] + hc[8];
-	if (hc[12]) {
-		snprintf(ctx->err, sizeof ctx->err, "compact reads: a cell's bin counts do not add up to its read_off span");
-		return CRISPGPU_ERR_ARG;
-	}
 	ctx->timing.fetched_bytes = ctx->lazy_reads ? 2 * (int64_t)(static_cast<uint32_t>(hc[14]) | (static_cast<uint64_t>(static_cast<uint32_t>(hc[15])) << 32)) : 0;
 	ctx->timing.h2d_bytes = ctx->copied_bytes + ctx->timing.fetched_bytes;
 	{
@@ -613,6 +613,13 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 		                   em_smem_fixed(ctx->P, ctx->nmax + 1, ctx->em_warps, true, nq) + planes <= ctx->smem_optin;
 		ctx->nq = dense ? nq : 0;
 		ctx->dense_lik = dense ? 1 : 0;
+		ctx->bins_direct = ctx->binned && dense;
+		if (ctx->binned && !dense && ctx->n_call1 > 0) {
+			k_expand_bins<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->db.bin_off, ctx->db.bins, ctx->db.read_off, static_cast<uint16_t*>(ctx->d_b[10].p),
+			                                                        static_cast<const uint8_t*>(ctx->d_need_reads.p), n, ctx->P, static_cast<int32_t*>(ctx->d_counters.p));
+			launches++;
+			CK(launch_check());
+		}
 		memcpy(ctx->qlist, ql, sizeof ql);
 		// two-plane variant: no bidirectional read in the batch, one pool size, no association pass
 		const bool scanned = g.em_flag >= 1 && g.use_base_qvs == 1 && ctx->n_reads > 0;
@@ -701,6 +708,7 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 		CK(launch_check());
 	}
 	CK(cudaEventRecord(ctx->ev[EV_CALL], ctx->stream));
+	if (ctx->binned) CK(cudaMemcpyAsync(static_cast<int32_t*>(ctx->h_counters.p) + 12, static_cast<int32_t*>(ctx->d_counters.p) + 12, 4, cudaMemcpyDeviceToHost, ctx->stream));
 	int64_t d2h = 0;
 	if (fetch) {
 		for (int f = 0; f < kNumOut; f++) {
@@ -992,6 +1000,10 @@ int crispgpu_wait(crispgpu_ctx* ctx, int64_t ticket, crispgpu_results* out)
 	int rc = run_stage2(ctx, true);
 	if (rc) return rc;
 	CK(cudaEventSynchronize(ctx->ev[EV_D2H]));
+	if (ctx->binned && static_cast<const int32_t*>(ctx->h_counters.p)[12]) {
+		snprintf(ctx->err, sizeof ctx->err, "compact reads: a cell's bin counts do not add up to its read_off span");
+		return CRISPGPU_ERR_ARG;
+	}
 	rc = finish_timing(ctx);
 	if (rc) return rc;
 	fill_results(ctx, out);
@@ -1024,6 +1036,10 @@ int crispgpu_run_resident(crispgpu_ctx* ctx, int fetch_results, crispgpu_results
 	rc = run_stage2(ctx, fetch_results != 0);
 	if (rc) return rc;
 	CK(cudaEventSynchronize(ctx->ev[EV_D2H]));
+	if (ctx->binned && static_cast<const int32_t*>(ctx->h_counters.p)[12]) {
+		snprintf(ctx->err, sizeof ctx->err, "compact reads: a cell's bin counts do not add up to its read_off span");
+		return CRISPGPU_ERR_ARG;
+	}
 	rc = finish_timing(ctx);
 	if (rc) return rc;
 	if (fetch_results) fill_results(ctx, out);

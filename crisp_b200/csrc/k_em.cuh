@@ -199,7 +199,7 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 			__syncthreads();
 		};
 
-		if (countlik) {
+		if constexpr (COUNTLIK) {
 			count_likelihood();
 			// EMmethod starts from its own E01 = E10 = 0.001 (crispEM.c:211); the count-based values above only
 			// shape the first likelihood (crispEM.c:362-375) and, later, the association statistic (:385)
@@ -211,6 +211,20 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 			//     bin costs three conflict-free count loads and, per genotype, one broadcast table load + three DFMAs.
 			for (int k = tid; k < 2 * nq * 3 * P; k += blockDim.x) dh[k] = 0;
 			__syncthreads();
+			if (b.bins) {
+				// compact input: the cell's (value, count) bins are the histogram already — one shared-memory add per bin
+				for (int i = warp; i < P; i += nwarps) {
+					const uint32_t b0 = b.bin_off[(size_t)s * P + i], b1 = b.bin_off[(size_t)s * P + i + 1];
+					for (uint32_t bb = b0 + lane; bb < b1; bb += 32) {
+						const uint32_t e = __ldg(b.bins + bb);
+						const int base = (e >> 8) & 3;
+						const int which = base == a1 ? 0 : (base == a2 ? 1 : -1);
+						if (which < 0) continue;
+						const int cls = (e >> 11) & 1 ? 2 : ((e >> 10) & 1);
+						atomicAdd(dh + ((which * nq + qd[e & 0x7f]) * 3 + cls) * P + i, e >> 16);
+					}
+				}
+			} else
 			for (int i = warp; i < P; i += nwarps) {
 				const uint32_t r0 = b.read_off[(size_t)s * P + i], r1 = b.read_off[(size_t)s * P + i + 1];
 				for (uint32_t cb = r0; cb < r1; cb += 256) {

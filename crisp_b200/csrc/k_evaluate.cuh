@@ -388,6 +388,29 @@ __global__ void k_expand_counts(const uint32_t* __restrict__ ic_off, const uint3
 	}
 }
 
+// Which qualities occur (and whether any read is bidirectional) among the bins of the flagged sites: k_qualmap's outputs
+// for a compact batch, read from the bins themselves (a tenth of the read stream).
+__global__ void k_scan_bins(const uint32_t* __restrict__ bin_off, const uint32_t* __restrict__ bins, const uint8_t* __restrict__ need, int n_sites, int P, int32_t* counters)
+{
+	__shared__ unsigned char seen[kNQ];
+	int bidir = 0;
+	for (int q = threadIdx.x; q < kNQ; q += blockDim.x) seen[q] = 0;
+	__syncthreads();
+	for (int s = blockIdx.x; s < n_sites; s += gridDim.x) {
+		if (need && !need[s]) continue;
+		const uint32_t b0 = bin_off[(size_t)s * P], b1 = bin_off[(size_t)(s + 1) * P];
+		for (uint32_t k = b0 + threadIdx.x; k < b1; k += blockDim.x) {
+			const uint32_t e = __ldg(bins + k);
+			seen[e & 0x7f] = 1;
+			if (e & 0x800u) bidir = 1;
+		}
+	}
+	if (__any_sync(0xffffffffu, bidir) && (threadIdx.x & 31) == 0) atomicOr(reinterpret_cast<unsigned int*>(counters) + 10, 1u);
+	__syncthreads();
+	for (int q = threadIdx.x; q < kNQ; q += blockDim.x)
+		if (seen[q]) atomicOr(reinterpret_cast<unsigned int*>(counters) + 4 + (q >> 5), 1u << (q & 31));
+}
+
 // Compact read format -> packed reads: a (site, pool) cell arrives as (value, count) bins and is rebuilt in the device
 // read buffer at read_off (the order inside a cell is immaterial to the likelihood).  One warp per cell: lanes load
 // up to 32 bins, each bin is broadcast and written by the whole warp.  Only sites flagged by the screening kernels are
