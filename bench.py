@@ -165,6 +165,7 @@ def main():
     ap.add_argument("--sites", type=int, default=8192, help="candidate sites per GPU per step")
     ap.add_argument("--cpu-sites-per-core", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--contexts", type=int, default=6, help="engine contexts per GPU in the end-to-end leg, one host thread each (batches in flight)")
     ap.add_argument("--format", "--e2e-format", dest="e2e_format", default="bins", choices=["bins", "reads"],
                     help="batch format of both legs: compact (read bins + sparse allele counts), or dense arrays with one element per read")
     args = ap.parse_args()
@@ -255,28 +256,44 @@ def main():
     # The call sequence a front end makes: crispgpu_submit (asynchronous: H2D + screening kernels) on one context while
     # the previous batch finishes on the other (crispgpu_wait: caller kernels + D2H).  Every step copies its inputs
     # from pinned host memory and reads its results back to the host.
-    stream2 = torch.cuda.Stream(device=local)
-    eng2 = Engine(cfg, device=local, stream=stream2.cuda_stream)
-    engs = [eng, eng2]
+    # One host thread per engine context, each looping crispgpu_submit / crispgpu_wait on its own stream; ctypes drops the
+    # GIL inside the calls, so the copies and kernels of the batches in flight overlap the way a multi-threaded front end
+    # would drive them.  The K timed steps (batches) are dealt round-robin to the threads.
+    import threading
+    nctx = max(1, min(args.contexts, args.steps))
+    extra_streams = [torch.cuda.Stream(device=local) for _ in range(nctx - 1)]
+    engs = [eng] + [Engine(cfg, device=local, stream=st.cuda_stream) for st in extra_streams]
     for e in engs:
         for _ in range(max(1, args.warmup // 2)):
             e.run(pinned)
+    share = [args.steps // nctx + (1 if k < args.steps % nctx else 0) for k in range(nctx)]
+    gate = threading.Barrier(nctx + 1)
+    errors = []
+
+    def front_end(e, nbatches):
+        try:
+            torch.cuda.set_device(local)
+            gate.wait()
+            for _ in range(nbatches):
+                e.wait(e.submit(pinned), copy=False)
+        except Exception as exc:  # noqa: BLE001
+            errors.append(exc)
+
+    workers = [threading.Thread(target=front_end, args=(e, nb)) for e, nb in zip(engs, share)]
+    for w in workers:
+        w.start()
     barrier()
+    gate.wait()
     w0 = time.perf_counter()
-    tickets = [None, None]
-    h2d_bytes = d2h_bytes = 0
-    for step in range(args.steps):
-        k = step & 1
-        if tickets[k] is not None:
-            engs[k].wait(tickets[k], copy=False)
-        tickets[k] = engs[k].submit(pinned)
-    for k in range(2):
-        if tickets[k] is not None:
-            engs[k].wait(tickets[k], copy=False)
+    for w in workers:
+        w.join()
     barrier()
     e2e_s = time.perf_counter() - w0
+    if errors:
+        raise errors[0]
     t_e2e = eng.timing()
-    eng2.close()
+    for e in engs[1:]:
+        e.close()
     clocks = sampler.stop() if rank == 0 else None
     results = eng.run(batch)
 
@@ -335,7 +352,7 @@ def main():
                         "input_format": ("compact: reads as (value,count) bins per site x pool, per-pool allele counts as non-zero entries; both expanded on the device (k_expand_bins, k_expand_counts)" if args.e2e_format == "bins"
                                          else "one 16-bit element per read; sites that reach the likelihood fetched on demand (k_fetch_reads)"),
                         "stage_ms_last_batch": {k: round(float(t_e2e[k]), 4) for k in ("h2d_ms", "evaluate_ms", "permute_ms", "filter_ms", "em_ms", "d2h_ms", "total_ms")},
-                        "mode": "two contexts per GPU in ping-pong: crispgpu_submit of batch k+1 overlaps crispgpu_wait of batch k"},
+                        "mode": f"{nctx} engine contexts per GPU, one host thread each looping crispgpu_submit/crispgpu_wait on pinned buffers; steps dealt round-robin"},
                 "gpu_launches": int(launches),
                 "roofline": roof_em if dominant == "k_em" else roof_ev,
                 "roofline_secondary": roof_ev if dominant == "k_em" else roof_em,

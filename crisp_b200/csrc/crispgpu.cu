@@ -87,8 +87,10 @@ struct crispgpu_ctx {
 	// bookkeeping
 	cudaEvent_t ev[EV_COUNT]{};
 	cudaEvent_t ev_counts = nullptr;
+	cudaEvent_t ev_epoch = nullptr;  // recorded at creation (crispgpu_debug_timeline)
 	int64_t ticket = 0;
 	bool inflight = false;
+	bool advanced = false;         // stage 2 of the batch in flight has been enqueued (crispgpu_advance)
 	crispgpu_timing timing{};
 	crispgpu_results res{};
 	int n_call = 0, n_call1 = 0, n_call2 = 0, n_perm = 0;
@@ -880,6 +882,7 @@ int crispgpu_create(const crispgpu_config* cfg, int device_id, void* stream, cri
 	}
 	for (int i = 0; i < EV_COUNT; i++) if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
 	if (cudaEventCreateWithFlags(&ctx->ev_counts, cudaEventDisableTiming) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
+	if (cudaEventCreate(&ctx->ev_epoch) != cudaSuccess || cudaEventRecord(ctx->ev_epoch, ctx->stream) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
 	if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
 	if (cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
 	if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
@@ -964,6 +967,7 @@ void crispgpu_destroy(crispgpu_ctx* ctx)
 	fd(ctx->d_perm_tasks); fd(ctx->d_call_tasks); fd(ctx->d_call_tasks2); fd(ctx->d_counters); fh(ctx->h_counters); fd(ctx->d_gws);
 	for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
 	if (ctx->ev_counts) cudaEventDestroy(ctx->ev_counts);
+	if (ctx->ev_epoch) cudaEventDestroy(ctx->ev_epoch);
 	if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
 	if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
 	if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
@@ -986,8 +990,21 @@ int crispgpu_submit(crispgpu_ctx* ctx, const crispgpu_batch* batch, int64_t* tic
 	rc = run_stage1(ctx);
 	if (rc) return rc;
 	ctx->inflight = true;
+	ctx->advanced = false;
 	ctx->ticket++;
 	if (ticket) *ticket = ctx->ticket;
+	return CRISPGPU_OK;
+}
+
+int crispgpu_advance(crispgpu_ctx* ctx, int64_t ticket)
+{
+	if (!ctx) return CRISPGPU_ERR_ARG;
+	if (!ctx->inflight || ticket != ctx->ticket) return CRISPGPU_ERR_TICKET;
+	if (ctx->advanced) return CRISPGPU_OK;
+	CK(cudaSetDevice(ctx->device));
+	int rc = run_stage2(ctx, true);
+	if (rc) { ctx->inflight = false; return rc; }
+	ctx->advanced = true;
 	return CRISPGPU_OK;
 }
 
@@ -997,7 +1014,8 @@ int crispgpu_wait(crispgpu_ctx* ctx, int64_t ticket, crispgpu_results* out)
 	if (!ctx->inflight || ticket != ctx->ticket) return CRISPGPU_ERR_TICKET;
 	CK(cudaSetDevice(ctx->device));
 	ctx->inflight = false;
-	int rc = run_stage2(ctx, true);
+	int rc = ctx->advanced ? 0 : run_stage2(ctx, true);
+	ctx->advanced = false;
 	if (rc) return rc;
 	CK(cudaEventSynchronize(ctx->ev[EV_D2H]));
 	if (ctx->binned && static_cast<const int32_t*>(ctx->h_counters.p)[12]) {
@@ -1043,6 +1061,16 @@ int crispgpu_run_resident(crispgpu_ctx* ctx, int fetch_results, crispgpu_results
 	rc = finish_timing(ctx);
 	if (rc) return rc;
 	if (fetch_results) fill_results(ctx, out);
+	return CRISPGPU_OK;
+}
+
+// Debugging aid (not part of the documented ABI): when each stage boundary of ctx's last completed batch happened,
+// in ms relative to `epoch` (a context's creation).  out[0..6] = START, H2D, EVAL, PERM, FILTER, CALL, D2H.
+extern "C" int crispgpu_debug_timeline(crispgpu_ctx* ctx, crispgpu_ctx* epoch, float* out)
+{
+	if (!ctx || !epoch || !out) return CRISPGPU_ERR_ARG;
+	for (int k = 0; k < EV_COUNT && k < 7; k++)
+		if (cudaEventElapsedTime(out + k, epoch->ev_epoch, ctx->ev[k]) != cudaSuccess) return CRISPGPU_ERR_CUDA;
 	return CRISPGPU_OK;
 }
 

@@ -16,7 +16,7 @@ from .abi import Batch, CBatch, Config, CResults, EngineConfig, Results, Timing
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libcrispgpu.so")
 
 EXPORTS = [
-    "crispgpu_config_defaults", "crispgpu_create", "crispgpu_destroy", "crispgpu_submit", "crispgpu_wait",
+    "crispgpu_config_defaults", "crispgpu_create", "crispgpu_destroy", "crispgpu_submit", "crispgpu_wait", "crispgpu_advance",
     "crispgpu_upload", "crispgpu_run_resident", "crispgpu_get_timing", "crispgpu_last_error",
     "crispgpu_host_alloc", "crispgpu_host_free", "crispgpu_abi_version", "crispgpu_device_count",
     "crispgpu_measure_fp64_tflops",
@@ -148,6 +148,10 @@ class Engine:
         self._check(self.lib.crispgpu_submit(self.h, C.byref(cb), C.byref(t)), "crispgpu_submit")
         self._inflight = (cb, batch)
         return t.value
+
+    def advance(self, ticket: int) -> None:
+        """Enqueue the batch's caller kernels and result copies without waiting for them (crispgpu_advance)."""
+        self._check(self.lib.crispgpu_advance(self.h, C.c_int64(ticket)), "crispgpu_advance")
 
     def wait(self, ticket: int, copy: bool = True):
         cres = CResults()

@@ -257,6 +257,10 @@ void crispgpu_destroy(crispgpu_ctx* ctx);
  * CRISPGPU_ERR_TICKET; so does a wait with a stale or unknown ticket. */
 int crispgpu_submit(crispgpu_ctx* ctx, const crispgpu_batch* batch, int64_t* ticket);
 int crispgpu_wait(crispgpu_ctx* ctx, int64_t ticket, crispgpu_results* out);
+/* Optional, between submit and wait: waits only for the screening counters of the batch and enqueues its caller
+ * kernels and device-to-host copies without waiting for them.  A front end juggling two contexts calls it on the other
+ * context before blocking in crispgpu_wait, so that this batch's EM runs while that batch's results travel back. */
+int crispgpu_advance(crispgpu_ctx* ctx, int64_t ticket);
 
 /* Device-resident path used to time the kernels alone: upload once, run many times. */
 int crispgpu_upload(crispgpu_ctx* ctx, const crispgpu_batch* batch);

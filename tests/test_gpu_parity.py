@@ -209,6 +209,25 @@ def test_results_independent_of_batching_and_sharding():
     eng.close()
 
 
+def test_advance_between_submit_and_wait():
+    """crispgpu_advance queues stage 2 early; results and error behaviour are those of a plain submit/wait."""
+    cfg = _cfg(10, 20, {})
+    batch = pin_batch(synth_batch(300, 10, cfg.ploidy, 100, seed=19, variant_frac=0.4).compact())
+    e0, e1 = Engine(cfg), Engine(cfg)
+    plain = e0.run(batch)
+    t0, t1 = e0.submit(batch), e1.submit(batch)
+    e1.advance(t1)
+    e1.advance(t1)            # idempotent
+    e0.advance(t0)
+    a, b = e0.wait(t0), e1.wait(t1)
+    compare_results(a, plain, tol=0.0, label="advance-0")
+    compare_results(b, plain, tol=0.0, label="advance-1")
+    with pytest.raises(EngineError):
+        e0.advance(t0)        # nothing in flight any more
+    e0.close()
+    e1.close()
+
+
 def test_submit_wait_equals_resident_path():
     cfg = _cfg(10, 20, {})
     batch = synth_batch(300, 10, cfg.ploidy, 100, seed=19, variant_frac=0.4)
