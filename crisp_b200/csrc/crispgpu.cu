@@ -441,12 +441,13 @@ int run_stage1(crispgpu_ctx* ctx)
 		CK(launch_check());
 	}
 	CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
-	const bool scan = n > 0 && g.em_flag >= 1 && g.use_base_qvs == 1 && ctx->n_reads > 0 && !lazy && !expand;
+	const bool scan = n > 0 && g.em_flag >= 1 && g.use_base_qvs == 1 && ctx->n_reads > 0 && !lazy;
 	if (scan) {
-		// fork: the read-stream scan is independent of the count-based screening
+		// fork: the scan of the read stream (or of its compact bins) is independent of the count-based screening
 		CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
 		CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-		k_qualmap<<<ctx->num_sms * 2, 256, 0, ctx->side>>>(ctx->db.reads, ctx->n_reads, static_cast<int32_t*>(ctx->d_counters.p));
+		if (expand) k_scan_bins<<<ctx->num_sms * 2, 256, 0, ctx->side>>>(ctx->db.bin_off, ctx->db.bins, nullptr, n, ctx->P, static_cast<int32_t*>(ctx->d_counters.p));
+		else k_qualmap<<<ctx->num_sms * 2, 256, 0, ctx->side>>>(ctx->db.reads, ctx->n_reads, static_cast<int32_t*>(ctx->d_counters.p));
 		launches++;
 		CK(launch_check());
 		CK(cudaEventRecord(ctx->ev_join, ctx->side));
@@ -570,14 +571,6 @@ int run_stage1(crispgpu_ctx* ctx)
 		// pull the reads of the sites that reached the quality-value likelihood straight from the caller's pinned array
 		k_fetch_reads<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->lazy_reads, static_cast<uint16_t*>(ctx->d_b[10].p), ctx->db.read_off,
 		                                                        static_cast<const uint8_t*>(ctx->d_need_reads.p), n, ctx->P, ctx->n_reads, static_cast<int32_t*>(ctx->d_counters.p));
-		launches++;
-		CK(launch_check());
-	}
-	if (expand) {
-		// the bins double as the likelihood histogram (dense path of k_em); here only which qualities occur.  The reads are
-		// rebuilt (k_expand_bins, stage 2) only when the batch needs the sparse likelihood path.
-		k_scan_bins<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->db.bin_off, ctx->db.bins, static_cast<const uint8_t*>(ctx->d_need_reads.p), n, ctx->P,
-		                                                      static_cast<int32_t*>(ctx->d_counters.p));
 		launches++;
 		CK(launch_check());
 	}
