@@ -175,7 +175,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": f"{args.workload}: {wl['P']} pools x poolsize {wl['ploidy']}, {wl['depth']}x per pool, options {wl['options'] or 'defaults (--EM 1, asymptotic CT)'}",
               "sites_per_gpu_per_step": args.sites, "sharding": "genomic region per rank, no collective",
-              "l2_policy": "inputs larger than L2 (batch > 126 MB)" if args.sites * (2 * wl['P'] * wl['depth'] + 96 * wl['P']) > 126e6 else "L2 flushed between steps",
+              "l2_policy": ("inputs larger than L2 (batch > 126 MB)" if args.e2e_format == "reads" and args.sites * (2 * wl['P'] * wl['depth'] + 96 * wl['P']) > 126e6
+                            else "L2 flushed between steps (256 MB fill, outside the per-step CUDA events)"),
               "synthetic": wl["synth"]}
 
     if args.impl == "reference":
@@ -235,22 +236,23 @@ def main():
     if rank == 0:
         sampler.start()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kt = {"evaluate_ms": 0.0, "em_ms": 0.0, "permute_ms": 0.0, "filter_ms": 0.0, "legacy_ms": 0.0}
     launches = 0
     with torch.cuda.stream(stream):
-        e0.record()
-        for _ in range(args.steps):
+        for e0, e1 in evs:
             if flush is not None:
                 flush.fill_(1)
+            e0.record()
             eng.run_resident(fetch=False)
+            e1.record()
             t = eng.timing()
             for k in kt:
                 kt[k] += t[k]
             launches += t["launches"]
-        e1.record()
     barrier()
-    ms = e0.elapsed_time(e1)
+    # the K steps, device time: sum of the per-step event pairs (equals one bracket around all of them when nothing sits between steps)
+    ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
     t_last = eng.timing()
     # ---------------- end to end through the C ABI from pinned host memory ----------------
     # The call sequence a front end makes: crispgpu_submit (asynchronous: H2D + screening kernels) on one context while
@@ -324,13 +326,17 @@ def main():
         ev_ms = kt["evaluate_ms"] / args.steps
         ro = batch.read_off.astype(np.int64)
         em_sites = np.unique(np.nonzero(results.em_iters > 0)[0])
-        em_bytes = float(sum(2 * (ro[(s + 1) * P] - ro[s * P]) for s in em_sites)) + n_em * (96.0 * P + 12.0 * P + 128.0)
+        if args.e2e_format == "bins":   # the likelihood reads the sites' (value,count) bins, 4 B each, instead of 2 B per read
+            bo = pinned.bin_off.astype(np.int64)
+            em_bytes = float(sum(4 * (bo[(s + 1) * P] - bo[s * P]) for s in em_sites)) + n_em * (96.0 * P + 12.0 * P + 128.0)
+        else:
+            em_bytes = float(sum(2 * (ro[(s + 1) * P] - ro[s * P]) for s in em_sites)) + n_em * (96.0 * P + 12.0 * P + 128.0)
         ev_bytes = batch.n_sites * (96.0 * P + 40.0 + 5 * 110.0)
         dominant = "k_em" if em_ms >= ev_ms else "k_evaluate"
         # DRAM traffic per launch from the committed ncu --set full capture of this very configuration (null otherwise)
         traffic = {}
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1", "traffic.json"))).get(args.workload, {})
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1", "traffic.json"))).get(args.workload + (":bins" if args.e2e_format == "bins" else ""), {})
             if tj.get("sites") == batch.n_sites:
                 traffic = {k: v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in tj.items() if isinstance(v, dict)}
         except Exception:
