@@ -243,12 +243,9 @@ int launch_evaluate(crispgpu_ctx* ctx, const EngineParams& prm)
 		kernel<<<grid, warps * 32, ctx->ev_smem, ctx->stream>>>(prm);
 		return 0;
 	};
-	switch (ctx->ev_warps) {
-		case 8: return go(k_evaluate<8>, 8);
-		case 4: return go(k_evaluate<4>, 4);
-		case 2: return go(k_evaluate<2>, 2);
-		default: return go(k_evaluate<1>, 1);
-	}
+	const bool perm = ctx->cfg.chisq_permutation == 1, pivot = ctx->cfg.pivot_sample > 0;
+	if (perm) return pivot ? go(k_evaluate<4, true, true>, 4) : go(k_evaluate<4, true, false>, 4);
+	return pivot ? go(k_evaluate<4, false, true>, 4) : go(k_evaluate<4, false, false>, 4);
 }
 
 struct BatchArray { const void* host; size_t bytes; };

@@ -222,11 +222,6 @@ __device__ __forceinline__ double warp_sum(double v)
 	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 	return v;
 }
-__device__ __forceinline__ int warp_sum(int v)
-{
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-	return v;
-}
+__device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }  // redux.sync: one instruction
 
 }  // namespace crisp

@@ -11,6 +11,9 @@
 
 namespace crisp {
 
+// resident threads per SM k_evaluate is compiled for: 1024 (64 registers) without a pivot sample, 512 (128 registers) with one
+constexpr int kEvalThreadsPerSM = 1024;
+
 __device__ __forceinline__ int slot_alleles(const uint8_t* mal, int slot, int& a1, int& a2, int& a3)
 {
 	a1 = mal[0];
@@ -104,15 +107,17 @@ __device__ __forceinline__ void loadq(const DevBatch& b, const DevCfg& c, const 
 	}
 }
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) k_evaluate(EngineParams prm)
+// PERM: --chisquare 0 (the weighted table and the permutation queue instead of the stratified statistic); PIVOT: a pivot
+// sample splits the pools into two groups.  Compile-time so that the common instantiation carries neither's registers.
+template <int WARPS, bool PERM, bool PIVOT>
+__global__ void __launch_bounds__(WARPS * 32, (PIVOT ? 512 : kEvalThreadsPerSM) / (WARPS * 32)) k_evaluate(EngineParams prm)
 {
 	const DevBatch& b = prm.b;
 	const DevCfg& c = prm.c;
 	const int P = c.P;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int pivot = c.pivot_sample;
-	const bool permmode = c.chisq_permutation == 1;
+	const int pivot = PIVOT ? c.pivot_sample : 0;
+	constexpr bool permmode = PERM;
 
 	for (int s = blockIdx.x * WARPS + warp; s < b.n_sites; s += gridDim.x * WARPS) {
 		// lanes run over pools and read their 96-byte count rows straight from global memory (each row is touched
