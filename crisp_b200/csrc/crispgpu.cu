@@ -90,6 +90,7 @@ struct crispgpu_ctx {
 	cudaEvent_t ev_epoch = nullptr;  // recorded at creation (crispgpu_debug_timeline)
 	int64_t ticket = 0;
 	bool inflight = false;
+	std::vector<const void*> prepared;  // kernels whose shared-memory attributes this context has set
 	bool advanced = false;         // stage 2 of the batch in flight has been enqueued (crispgpu_advance)
 	crispgpu_timing timing{};
 	crispgpu_results res{};
@@ -217,12 +218,27 @@ int setup_geometry(crispgpu_ctx* ctx)
 	return 0;
 }
 
+// Function attributes are process-wide: the dynamic shared-memory limit is always raised to everything the device allows
+// (never a per-context size), so contexts with different pool counts on other threads cannot lower it under a launch.
+template <typename K>
+int prepare_kernel(crispgpu_ctx* ctx, K kernel, size_t smem)
+{
+	if (smem == 0) return 0;
+	const void* key = reinterpret_cast<const void*>(kernel);
+	for (const void* p : ctx->prepared) if (p == key) return 0;
+	cudaFuncAttributes fa{};
+	CK(cudaFuncGetAttributes(&fa, kernel));
+	CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - fa.sharedSizeBytes)));
+	CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+	ctx->prepared.push_back(key);
+	return 0;
+}
+
 template <typename K>
 int occupancy_grid(crispgpu_ctx* ctx, K kernel, int threads, size_t smem, int* grid)
 {
 	int per_sm = 0;
-	if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	if (smem > 0) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+	{ int r0 = prepare_kernel(ctx, kernel, smem); if (r0) return r0; }
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
 	if (per_sm < 1) per_sm = 1;
 	*grid = per_sm * ctx->num_sms;
@@ -648,9 +664,9 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 				if (!*grid_cache) {
 					int r2 = occupancy_grid(ctx, kernel, ctx->em_threads, smem, grid_cache);
 					if (r2) return r2;
-				} else if (smem > 48 * 1024) {
-					CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-					CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+				} else {
+					int r2 = prepare_kernel(ctx, kernel, smem);  // another instantiation may have filled the shared grid cache
+					if (r2) return r2;
 				}
 				int grid = *grid_cache < ntasks ? *grid_cache : ntasks;
 				if (!smem_g) {

@@ -209,6 +209,71 @@ def test_results_independent_of_batching_and_sharding():
     eng.close()
 
 
+def test_context_reuse_across_different_batches():
+    """A context carries device buffers, flags and the k_em instantiation from batch to batch; whatever came before
+    (other qualities, bidirectional reads, far fewer or far more tasks, the other batch format), the results are those of
+    a fresh context, bit for bit."""
+    cfg = _cfg(10, 20, {})
+
+    def fresh(batch):
+        e = Engine(cfg)
+        r = e.run(batch)
+        e.close()
+        return r
+
+    a = synth_batch(600, 10, cfg.ploidy, 100, seed=3, variant_frac=0.3, indel_frac=0.2)
+    b = synth_batch(600, 10, cfg.ploidy, 100, seed=4, variant_frac=0.3, indel_frac=0.2)      # same shape, other sites
+    other_quals = synth_batch(600, 10, cfg.ploidy, 100, seed=5, variant_frac=0.3, quals=[22, 33])
+    with_bidir = synth_batch(600, 10, cfg.ploidy, 100, seed=6, variant_frac=0.3, bidir_frac=0.1)
+    few = a.select(np.arange(40))                                                              # sizes the rows for 40 sites ...
+    many = synth_batch(3000, 10, cfg.ploidy, 100, seed=7, variant_frac=0.6)                   # ... then far more tasks arrive
+    fa, fb = fresh(a), fresh(b)
+    compare_results(fa, OracleEngine(cfg).run(a, mode=RNG_PHILOX), label="oracle")
+    eng = Engine(cfg)
+    seq = [("a", a, fa), ("a-again", a, fa), ("b", b, fb), ("quals", other_quals, fresh(other_quals)), ("quals-again", other_quals, None),
+           ("bidir", with_bidir, fresh(with_bidir)), ("a-back", a, fa), ("few", few, fresh(few)), ("many", many, fresh(many)), ("many-again", many, None)]
+    last = None
+    for name, batch, want in seq:
+        for form in (batch, pin_batch(batch.compact())):
+            got = eng.run(form)
+            compare_results(got, want if want is not None else last, tol=0.0, label=name)
+        last = got if want is None else want
+    eng.upload(b)
+    compare_results(eng.run_resident(fetch=True), fb, tol=0.0, label="resident-first")
+    compare_results(eng.run_resident(fetch=True), fb, tol=0.0, label="resident-again")
+    eng.close()
+
+
+def test_contexts_of_different_shapes_share_the_process():
+    """Kernel attributes (dynamic shared-memory limits) are process-wide; contexts with small and large pool counts
+    must be able to alternate, also from different threads."""
+    import threading
+    small, large = _cfg(10, 20, {}), _cfg(100, 96, {})
+    bs = synth_batch(200, 10, small.ploidy, 100, seed=5, variant_frac=0.4)
+    bl = synth_batch(24, 100, large.ploidy, 60, seed=6, variant_frac=0.5)
+    ws, wl = OracleEngine(small).run(bs, mode=RNG_PHILOX), OracleEngine(large).run(bl, mode=RNG_PHILOX)
+    es, el = Engine(small), Engine(large)
+    for _ in range(2):
+        compare_results(es.run(bs), ws, label="small")
+        compare_results(el.run(bl), wl, label="large")
+    out = {}
+
+    def loop(name, eng, batch):
+        out[name] = [eng.run(batch) for _ in range(6)]
+
+    th = [threading.Thread(target=loop, args=("s", es, bs)), threading.Thread(target=loop, args=("l", el, bl))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for r in out["s"]:
+        compare_results(r, ws, label="small-threaded")
+    for r in out["l"]:
+        compare_results(r, wl, label="large-threaded")
+    es.close()
+    el.close()
+
+
 def test_advance_between_submit_and_wait():
     """crispgpu_advance queues stage 2 early; results and error behaviour are those of a plain submit/wait."""
     cfg = _cfg(10, 20, {})
