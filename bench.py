@@ -165,7 +165,8 @@ def main():
     ap.add_argument("--sites", type=int, default=8192, help="candidate sites per GPU per step")
     ap.add_argument("--cpu-sites-per-core", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--contexts", type=int, default=6, help="engine contexts per GPU in the end-to-end leg, one host thread each (batches in flight)")
+    ap.add_argument("--contexts", type=int, default=0,
+                    help="engine contexts per GPU in the end-to-end leg, one host thread each (batches in flight); 0 = 6, fewer when the ranks of a box would oversubscribe its cores")
     ap.add_argument("--format", "--e2e-format", dest="e2e_format", default="bins", choices=["bins", "reads"],
                     help="batch format of both legs: compact (read bins + sparse allele counts), or dense arrays with one element per read")
     args = ap.parse_args()
@@ -262,7 +263,8 @@ def main():
     # GIL inside the calls, so the copies and kernels of the batches in flight overlap the way a multi-threaded front end
     # would drive them.  The K timed steps (batches) are dealt round-robin to the threads.
     import threading
-    nctx = max(1, min(args.contexts, args.steps))
+    want_ctx = args.contexts if args.contexts > 0 else max(2, min(6, (os.cpu_count() or 8) // max(1, world)))
+    nctx = max(1, min(want_ctx, args.steps))
     extra_streams = [torch.cuda.Stream(device=local) for _ in range(nctx - 1)]
     engs = [eng] + [Engine(cfg, device=local, stream=st.cuda_stream) for st in extra_streams]
     for e in engs:
