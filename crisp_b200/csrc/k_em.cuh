@@ -207,8 +207,7 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 		} else if (dense) {
 			// calculate_pooled_likelihoods_snp, dense form (few distinct qualities, one pool size).
 			// (1) per pool (one warp) bin the packed reads into dh[allele][quality][class][pool];
-			// (2) contract with the staged table rows, LANES OVER POOLS: for a tile of 8 genotypes every (allele, quality)
-			//     bin costs three conflict-free count loads and, per genotype, one broadcast table load + three DFMAs.
+			// (2) contract with the staged table rows on the FP64 tensor cores (see below).
 			for (int k = tid; k < 2 * nq * 3 * P; k += blockDim.x) dh[k] = 0;
 			__syncthreads();
 			if (b.bins) {
@@ -249,41 +248,40 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 				}
 			}
 			__syncthreads();
-			const int ntile = (J + 7) >> 3;
-			for (int item = warp; item < rounds * ntile; item += nwarps) {
-				const int rd = item / ntile, j0 = (item - rd * ntile) * 8;
-				const int i = rd * 32 + lane;
-				const bool act = i < P;
-				const int ii = act ? i : P - 1;
-				double acc[3][8];
+			// (2) on the FP64 tensor cores: G[class][pool][j] = sum_bin dh[bin][class][pool] * Ts[bin][j] is a small GEMM
+			// (M = pools, N = genotypes, K = 2 nq bins).  One DMMA.8x8x4 does the work of eight DFMA warp instructions in one
+			// issue slot — the FP64 rate is the same, but this kernel is bound by issue slots, not by the FP64 pipe.
+			// Fragments (mma.sync.m8n8k4.row.col.f64): A[row = lane/4][k = lane%4], B[k = lane%4][col = lane/4],
+			// D[row = lane/4][col = 2 (lane%4) + {0,1}].
+			const int ptiles = (P + 7) >> 3, jtiles = (J + 7) >> 3, ksteps = (2 * nq + 3) >> 2;
+			constexpr int NCLS = NOBIDIR ? 2 : 3;  // no bidirectional reads: that class is empty
+			for (int item = warp; item < ptiles * jtiles; item += nwarps) {
+				const int pt = item / jtiles, jt = item - pt * jtiles;
+				const int prow = pt * 8 + (lane >> 2), jcol = jt * 8 + (lane >> 2), kk = lane & 3;
+				double acc[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+				for (int ks = 0; ks < ksteps; ks++) {
+					const int wd = ks * 4 + kk;
+					const bool kin = wd < 2 * nq;
+					const double bf = (kin && jcol < J) ? Ts[wd * J + jcol] : 0.0;
 #pragma unroll
-				for (int cls = 0; cls < 3; cls++)
-#pragma unroll
-					for (int jj = 0; jj < 8; jj++) acc[cls][jj] = 0.0;
-				for (int wd = 0; wd < 2 * nq; wd++) {
-					const uint32_t cf = dh[(wd * 3 + 0) * P + ii], cr = dh[(wd * 3 + 1) * P + ii], cbd = dh[(wd * 3 + 2) * P + ii];
-					if (!__any_sync(0xffffffffu, (cf | cr | cbd) != 0)) continue;
-					const double xf = (double)cf, xr = (double)cr, xb = (double)cbd;
-					const double* tr = Ts + wd * J + j0;
-#pragma unroll
-					for (int jj = 0; jj < 8; jj++) {
-						const double t = (j0 + jj < J) ? tr[jj] : 0.0;
-						acc[0][jj] = fma(xf, t, acc[0][jj]);
-						acc[1][jj] = fma(xr, t, acc[1][jj]);
-						acc[2][jj] = fma(xb, t, acc[2][jj]);
+					for (int cls = 0; cls < NCLS; cls++) {
+						const double af = (kin && prow < P) ? (double)dh[(wd * 3 + cls) * P + prow] : 0.0;
+						asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+						             : "+d"(acc[cls][0]), "+d"(acc[cls][1]) : "d"(af), "d"(bf));
 					}
 				}
-				if (act) {
+				const int i = prow;
+				if (i < P) {
 #pragma unroll
-					for (int jj = 0; jj < 8; jj++) {
-						const int j = j0 + jj;
+					for (int t = 0; t < 2; t++) {
+						const int j = jt * 8 + kk * 2 + t;
 						if (j < J) {
 							const double nc = c.NC[j];
 							const size_t idx = (size_t)j * P + i;
-							Gf[idx] = acc[0][jj] + nc;
-							Gr[idx] = acc[1][jj] + nc;
-							if (!NOBIDIR) Gt[idx] = (acc[0][jj] + acc[1][jj] + acc[2][jj]) + nc;
-							if (j == 0) Gb0[i] = acc[2][jj];
+							Gf[idx] = acc[0][t] + nc;
+							Gr[idx] = acc[1][t] + nc;
+							if (!NOBIDIR) Gt[idx] = (acc[0][t] + acc[1][t] + acc[2][t]) + nc;
+							if (j == 0) Gb0[i] = acc[2][t];
 						}
 					}
 				}
