@@ -60,6 +60,7 @@ struct crispgpu_ctx {
 	DevBatch db{};
 	int n_sites = 0;
 	size_t n_reads = 0;
+	size_t n_bins = 0;
 	bool resident = false;
 	// device results + pinned mirrors
 	DevBuf d_o[32], d_ac, d_qv;
@@ -362,6 +363,7 @@ int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b, bool lazy)
 	ctx->db.P = ctx->P;
 	ctx->n_sites = b->n_sites;
 	ctx->n_reads = b->n_sites ? b->read_off[(size_t)b->n_sites * ctx->P] : 0;
+	ctx->n_bins = (ctx->binned && b->n_sites) ? b->bin_off[(size_t)b->n_sites * ctx->P] : 0;
 	ctx->timing.h2d_bytes = bytes;
 	ctx->copied_bytes = bytes;
 	return 0;
@@ -459,7 +461,7 @@ int run_stage1(crispgpu_ctx* ctx)
 		// fork: the scan of the read stream (or of its compact bins) is independent of the count-based screening
 		CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
 		CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-		if (expand) k_scan_bins<<<ctx->num_sms * 2, 256, 0, ctx->side>>>(ctx->db.bin_off, ctx->db.bins, nullptr, n, ctx->P, static_cast<int32_t*>(ctx->d_counters.p));
+		if (expand) k_scan_bins<<<ctx->num_sms * 2, 256, 0, ctx->side>>>(ctx->db.bins, ctx->n_bins, static_cast<int32_t*>(ctx->d_counters.p));
 		else k_qualmap<<<ctx->num_sms * 2, 256, 0, ctx->side>>>(ctx->db.reads, ctx->n_reads, static_cast<int32_t*>(ctx->d_counters.p));
 		launches++;
 		CK(launch_check());

@@ -393,22 +393,25 @@ __global__ void k_expand_counts(const uint32_t* __restrict__ ic_off, const uint3
 	}
 }
 
-// Which qualities occur (and whether any read is bidirectional) among the bins of the flagged sites: k_qualmap's outputs
-// for a compact batch, read from the bins themselves (a tenth of the read stream).
-__global__ void k_scan_bins(const uint32_t* __restrict__ bin_off, const uint32_t* __restrict__ bins, const uint8_t* __restrict__ need, int n_sites, int P, int32_t* counters)
+// Which qualities occur (and whether any read is bidirectional) in a compact batch: k_qualmap's outputs read from the bins
+// themselves (a tenth of the read stream), flat 16-byte loads over the whole bin array.
+__global__ void k_scan_bins(const uint32_t* __restrict__ bins, size_t n_bins, int32_t* counters)
 {
 	__shared__ unsigned char seen[kNQ];
 	int bidir = 0;
 	for (int q = threadIdx.x; q < kNQ; q += blockDim.x) seen[q] = 0;
 	__syncthreads();
-	for (int s = blockIdx.x; s < n_sites; s += gridDim.x) {
-		if (need && !need[s]) continue;
-		const uint32_t b0 = bin_off[(size_t)s * P], b1 = bin_off[(size_t)(s + 1) * P];
-		for (uint32_t k = b0 + threadIdx.x; k < b1; k += blockDim.x) {
-			const uint32_t e = __ldg(bins + k);
-			seen[e & 0x7f] = 1;
-			if (e & 0x800u) bidir = 1;
-		}
+	const size_t nvec = n_bins / 4;
+	const uint4* v = reinterpret_cast<const uint4*>(bins);
+	for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nvec; k += (size_t)gridDim.x * blockDim.x) {
+		const uint4 x = __ldg(v + k);
+		if ((x.x | x.y | x.z | x.w) & 0x800u) bidir = 1;
+		seen[x.x & 0x7f] = 1; seen[x.y & 0x7f] = 1; seen[x.z & 0x7f] = 1; seen[x.w & 0x7f] = 1;
+	}
+	if (blockIdx.x == 0 && threadIdx.x < (int)(n_bins - nvec * 4)) {
+		const uint32_t e = bins[nvec * 4 + threadIdx.x];
+		seen[e & 0x7f] = 1;
+		if (e & 0x800u) bidir = 1;
 	}
 	if (__any_sync(0xffffffffu, bidir) && (threadIdx.x & 31) == 0) atomicOr(reinterpret_cast<unsigned int*>(counters) + 10, 1u);
 	__syncthreads();
