@@ -13,7 +13,7 @@ from typing import Optional
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAXALLELES = 8
 NCOUNT = 24
 MAXSLOTS = 5

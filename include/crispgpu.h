@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CRISPGPU_ABI_VERSION 1
+#define CRISPGPU_ABI_VERSION 2  /* 2: compact batch arrays (bins, sparse counts), crispgpu_advance, fetched_bytes */
 
 #define CRISPGPU_MAXALLELES 8  /* `maxalleles`, readmultiplebams.c:27: A,C,G,T + indel slots 4..6 */
 #define CRISPGPU_NCOUNT 24     /* 3 strand classes x 8 alleles: index = allele + s*8, s=0 fwd,1 rev,2 bidirectional

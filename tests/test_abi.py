@@ -29,7 +29,7 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_abi_version_and_defaults(lib):
-    assert lib.crispgpu_abi_version() == 1
+    assert lib.crispgpu_abi_version() == 2
     cfg = Config()
     lib.crispgpu_config_defaults(C.byref(cfg))
     # reference defaults: newcrispcaller.c:20-32, readmultiplebams.c:25-26, crispEM.c:14,26
