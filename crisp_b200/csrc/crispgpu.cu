@@ -51,7 +51,7 @@ struct crispgpu_ctx {
 	DevBuf d_need_reads;           // per-site flags of the on-demand read fetch
 	const uint16_t* lazy_reads = nullptr;  // device-visible address of the caller's pinned read array (on-demand fetch), or null
 	int64_t copied_bytes = 0;
-	bool bins_direct = false;      // k_em reads the bins themselves (dense likelihood path)
+	bool bins_direct = false;      // k_em reads the bins themselves
 	bool sparse_ic = false;        // the batch came with sparse per-pool allele counts
 	bool binned = false;           // the batch came in the compact (value, count) read format
 	DevBuf d_exact_row, d_exact_cl, d_exact_done;  // exact_mode: term tables of the exact 2 x k test, per-task decided flags
@@ -333,12 +333,7 @@ int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b, bool lazy)
 			dptr[i] = ctx->d_b[i].p;
 			continue;
 		}
-		if (i == kReadsArray && ctx->binned && a[i].bytes) {
-			int rc = ensure_dev(ctx, ctx->d_b[i], a[i].bytes);
-			if (rc) return rc;
-			dptr[i] = ctx->d_b[i].p;
-			continue;
-		}
+		if (i == kReadsArray && ctx->binned) { dptr[i] = nullptr; continue; }  // k_em consumes the bins; no read stream on the device
 		if (a[i].bytes == 0 || a[i].host == nullptr) { dptr[i] = nullptr; continue; }
 		int rc = ensure_dev(ctx, ctx->d_b[i], a[i].bytes);
 		if (rc) return rc;
@@ -422,7 +417,7 @@ EngineParams make_params(crispgpu_ctx* ctx)
 	prm.q.call_tasks2 = static_cast<int32_t*>(ctx->d_call_tasks2.p);
 	prm.q.counters = static_cast<int32_t*>(ctx->d_counters.p);
 	if (!ctx->bins_direct) { prm.b.bins = nullptr; prm.b.bin_off = nullptr; }
-	prm.q.need_reads = (ctx->lazy_reads || ctx->binned) ? static_cast<uint8_t*>(ctx->d_need_reads.p) : nullptr;
+	prm.q.need_reads = ctx->lazy_reads ? static_cast<uint8_t*>(ctx->d_need_reads.p) : nullptr;
 	prm.gws = static_cast<double*>(ctx->d_gws.p);
 	prm.gws_stride = ctx->gws_stride;
 	return prm;
@@ -441,9 +436,9 @@ int run_stage1(crispgpu_ctx* ctx)
 	int64_t launches = 0;
 	CK(cudaMemsetAsync(ctx->d_counters.p, 0, 16 * sizeof(int32_t), ctx->stream));
 	const bool lazy = ctx->lazy_reads != nullptr && n > 0;
-	const bool expand = ctx->binned && n > 0 && ctx->n_reads > 0 && g.em_flag >= 1 && g.use_base_qvs == 1;
-	if (!expand) ctx->binned = false;
-	if (lazy || expand) {
+	const bool use_bins = ctx->binned && n > 0 && ctx->n_bins > 0 && g.em_flag >= 1 && g.use_base_qvs == 1;
+	if (!use_bins) ctx->binned = false;
+	if (lazy) {
 		rc = ensure_dev(ctx, ctx->d_need_reads, (size_t)n); if (rc) return rc;
 		CK(cudaMemsetAsync(ctx->d_need_reads.p, 0, (size_t)n, ctx->stream));
 	} else ctx->lazy_reads = nullptr;
@@ -456,12 +451,12 @@ int run_stage1(crispgpu_ctx* ctx)
 		CK(launch_check());
 	}
 	CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
-	const bool scan = n > 0 && g.em_flag >= 1 && g.use_base_qvs == 1 && ctx->n_reads > 0 && !lazy;
+	const bool scan = n > 0 && g.em_flag >= 1 && g.use_base_qvs == 1 && !lazy && (use_bins || (ctx->n_reads > 0 && ctx->db.reads != nullptr));
 	if (scan) {
 		// fork: the scan of the read stream (or of its compact bins) is independent of the count-based screening
 		CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
 		CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-		if (expand) k_scan_bins<<<ctx->num_sms * 2, 256, 0, ctx->side>>>(ctx->db.bins, ctx->n_bins, static_cast<int32_t*>(ctx->d_counters.p));
+		if (use_bins) k_scan_bins<<<ctx->num_sms * 2, 256, 0, ctx->side>>>(ctx->db.bins, ctx->n_bins, static_cast<int32_t*>(ctx->d_counters.p));
 		else k_qualmap<<<ctx->num_sms * 2, 256, 0, ctx->side>>>(ctx->db.reads, ctx->n_reads, static_cast<int32_t*>(ctx->d_counters.p));
 		launches++;
 		CK(launch_check());
@@ -623,13 +618,7 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 		                   em_smem_fixed(ctx->P, ctx->nmax + 1, ctx->em_warps, true, nq) + planes <= ctx->smem_optin;
 		ctx->nq = dense ? nq : 0;
 		ctx->dense_lik = dense ? 1 : 0;
-		ctx->bins_direct = ctx->binned && dense;
-		if (ctx->binned && !dense && ctx->n_call1 > 0) {
-			k_expand_bins<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->db.bin_off, ctx->db.bins, ctx->db.read_off, static_cast<uint16_t*>(ctx->d_b[10].p),
-			                                                        static_cast<const uint8_t*>(ctx->d_need_reads.p), n, ctx->P, static_cast<int32_t*>(ctx->d_counters.p));
-			launches++;
-			CK(launch_check());
-		}
+		ctx->bins_direct = ctx->binned;  // both likelihood paths of k_em take the (value, count) bins as they are
 		memcpy(ctx->qlist, ql, sizeof ql);
 		// two-plane variant: no bidirectional read in the batch, one pool size, no association pass
 		const bool scanned = g.em_flag >= 1 && g.use_base_qvs == 1 && ctx->n_reads > 0;
@@ -718,7 +707,6 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 		CK(launch_check());
 	}
 	CK(cudaEventRecord(ctx->ev[EV_CALL], ctx->stream));
-	if (ctx->binned) CK(cudaMemcpyAsync(static_cast<int32_t*>(ctx->h_counters.p) + 12, static_cast<int32_t*>(ctx->d_counters.p) + 12, 4, cudaMemcpyDeviceToHost, ctx->stream));
 	int64_t d2h = 0;
 	if (fetch) {
 		for (int f = 0; f < kNumOut; f++) {
@@ -1026,10 +1014,6 @@ int crispgpu_wait(crispgpu_ctx* ctx, int64_t ticket, crispgpu_results* out)
 	ctx->advanced = false;
 	if (rc) return rc;
 	CK(cudaEventSynchronize(ctx->ev[EV_D2H]));
-	if (ctx->binned && static_cast<const int32_t*>(ctx->h_counters.p)[12]) {
-		snprintf(ctx->err, sizeof ctx->err, "compact reads: a cell's bin counts do not add up to its read_off span");
-		return CRISPGPU_ERR_ARG;
-	}
 	rc = finish_timing(ctx);
 	if (rc) return rc;
 	fill_results(ctx, out);
@@ -1062,10 +1046,6 @@ int crispgpu_run_resident(crispgpu_ctx* ctx, int fetch_results, crispgpu_results
 	rc = run_stage2(ctx, fetch_results != 0);
 	if (rc) return rc;
 	CK(cudaEventSynchronize(ctx->ev[EV_D2H]));
-	if (ctx->binned && static_cast<const int32_t*>(ctx->h_counters.p)[12]) {
-		snprintf(ctx->err, sizeof ctx->err, "compact reads: a cell's bin counts do not add up to its read_off span");
-		return CRISPGPU_ERR_ARG;
-	}
 	rc = finish_timing(ctx);
 	if (rc) return rc;
 	if (fetch_results) fill_results(ctx, out);

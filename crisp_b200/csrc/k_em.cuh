@@ -301,6 +301,64 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 				for (int cls = 0; cls < 3; cls++)
 #pragma unroll
 					for (int jc = 0; jc < 4; jc++) acc[cls][jc] = 0.0;
+				if (b.bins) {
+					// compact input: every (value, count) bin of the cell is one term count * T[allele][quality][j] — no histogram,
+					// no folding; the bin is broadcast and each lane updates its genotypes
+					const uint32_t b0 = b.bin_off[(size_t)s * P + i], b1 = b.bin_off[(size_t)s * P + i + 1];
+					for (uint32_t bb = b0; bb < b1; bb += 32) {
+						const uint32_t mine = bb + lane < b1 ? __ldg(b.bins + bb + lane) : 0u;
+						const int m = (int)min(32u, b1 - bb);
+						for (int k = 0; k < m; k++) {
+							const uint32_t e = __shfl_sync(0xffffffffu, mine, k);
+							const int base = (e >> 8) & 3;
+							const int which = base == a1 ? 0 : (base == a2 ? 1 : -1);
+							if (which < 0) continue;
+							const int cls = (e >> 11) & 1 ? 2 : ((e >> 10) & 1);
+							const double cntv = (double)(e >> 16);
+							const double* Tr = Tp + ((size_t)which * kNQ + (e & 0x7f)) * J + lane;
+							double t[4];
+#pragma unroll
+							for (int jc = 0; jc < 4; jc++) t[jc] = (jc * 32 <= nmax && jc * 32 + lane <= n) ? __ldg(Tr + jc * 32) : 0.0;
+							if (cls == 0) {
+#pragma unroll
+								for (int jc = 0; jc < 4; jc++) acc[0][jc] = fma(cntv, t[jc], acc[0][jc]);
+							} else if (cls == 1) {
+#pragma unroll
+								for (int jc = 0; jc < 4; jc++) acc[1][jc] = fma(cntv, t[jc], acc[1][jc]);
+							} else {
+#pragma unroll
+								for (int jc = 0; jc < 4; jc++) acc[2][jc] = fma(cntv, t[jc], acc[2][jc]);
+							}
+						}
+					}
+					// pool sizes above 127: the remaining genotypes, one chunk of 32 at a time over the same bins
+					for (int jc = 4; jc * 32 <= n; jc++) {
+						const int j = jc * 32 + lane;
+						double a3[3] = {0.0, 0.0, 0.0};
+						for (uint32_t bb = b0; bb < b1; bb += 32) {
+							const uint32_t mine = bb + lane < b1 ? __ldg(b.bins + bb + lane) : 0u;
+							const int m = (int)min(32u, b1 - bb);
+							for (int k = 0; k < m; k++) {
+								const uint32_t e = __shfl_sync(0xffffffffu, mine, k);
+								const int base = (e >> 8) & 3;
+								const int which = base == a1 ? 0 : (base == a2 ? 1 : -1);
+								if (which < 0 || j > n) continue;
+								const int cls = (e >> 11) & 1 ? 2 : ((e >> 10) & 1);
+								const double t = (double)(e >> 16) * __ldg(Tp + ((size_t)which * kNQ + (e & 0x7f)) * J + j);
+								a3[0] += cls == 0 ? t : 0.0;
+								a3[1] += cls == 1 ? t : 0.0;
+								a3[2] += cls == 2 ? t : 0.0;
+							}
+						}
+						if (j <= n) {
+							const size_t idx = (size_t)j * P + i;
+							const double nc = __ldg(c.NC + (size_t)c.pclass[i] * J + j);
+							Gf[idx] = nc + a3[0];
+							Gr[idx] = nc + a3[1];
+							if (!NOBIDIR) Gt[idx] = nc + (a3[0] + a3[1] + a3[2]);
+						}
+					}
+				} else
 				// 16-bit bins: a pool deeper than 65504 reads is folded block by block
 				for (uint32_t blk = r0; blk < r1 || blk == r0; blk += 65504u) {
 					const uint32_t bend = min(r1, blk + 65504u);

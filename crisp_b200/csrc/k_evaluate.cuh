@@ -419,49 +419,6 @@ __global__ void k_scan_bins(const uint32_t* __restrict__ bins, size_t n_bins, in
 		if (seen[q]) atomicOr(reinterpret_cast<unsigned int*>(counters) + 4 + (q >> 5), 1u << (q & 31));
 }
 
-// Compact read format -> packed reads: a (site, pool) cell arrives as (value, count) bins and is rebuilt in the device
-// read buffer at read_off (the order inside a cell is immaterial to the likelihood).  One warp per cell: lanes load
-// up to 32 bins, each bin is broadcast and written by the whole warp.  Only sites flagged by the screening kernels are
-// expanded.  Also produces k_qualmap's outputs, and flags (counters[12]) a cell whose counts disagree with read_off.
-__global__ void k_expand_bins(const uint32_t* __restrict__ bin_off, const uint32_t* __restrict__ bins, const uint32_t* __restrict__ read_off,
-                              uint16_t* __restrict__ reads, const uint8_t* __restrict__ need, int n_sites, int P, int32_t* counters)
-{
-	__shared__ unsigned char seen[kNQ];
-	int bidir = 0, bad = 0;
-	for (int q = threadIdx.x; q < kNQ; q += blockDim.x) seen[q] = 0;
-	__syncthreads();
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-	for (int s = blockIdx.x; s < n_sites; s += gridDim.x) {
-		if (need && !need[s]) continue;
-		for (int i = warp; i < P; i += W) {
-			const size_t c = (size_t)s * P + i;
-			const uint32_t b0 = bin_off[c], b1 = bin_off[c + 1], wend = read_off[c + 1];
-			uint32_t w = read_off[c];
-			for (uint32_t bb = b0; bb < b1; bb += 32) {
-				const uint32_t mine = bb + lane < b1 ? __ldg(bins + bb + lane) : 0u;
-				const int m = (int)min(32u, b1 - bb);
-				if (mine) {
-					seen[mine & 0x7f] = 1;
-					if (mine & 0x800u) bidir = 1;
-				}
-				for (int k = 0; k < m; k++) {
-					const uint32_t e = __shfl_sync(0xffffffffu, mine, k);
-					const uint32_t cnt = e >> 16;
-					const uint16_t val = (uint16_t)(e & 0xffffu);
-					for (uint32_t x = lane; x < cnt && w + x < wend; x += 32) reads[w + x] = val;
-					w += cnt;
-				}
-			}
-			if (w != wend) bad = 1;
-		}
-	}
-	if (bad) atomicOr(reinterpret_cast<unsigned int*>(counters) + 12, 1u);
-	if (__any_sync(0xffffffffu, bidir) && (threadIdx.x & 31) == 0) atomicOr(reinterpret_cast<unsigned int*>(counters) + 10, 1u);
-	__syncthreads();
-	for (int q = threadIdx.x; q < kNQ; q += blockDim.x)
-		if (seen[q]) atomicOr(reinterpret_cast<unsigned int*>(counters) + 4 + (q >> 5), 1u << (q & 31));
-}
-
 // After the permutation kernel: apply the FAST_FILTER rejects with the Monte-Carlo p-value and queue the survivors.
 __global__ void k_filter(EngineParams prm)
 {

@@ -155,11 +155,10 @@ typedef struct crispgpu_batch {
 	const double* tstats;       /* [n][16] */
 	/* Compact alternative to `reads` (the likelihood depends on a pool's reads only through how many carry each
 	 * (quality, base, strand, bidirectional) value): cell c = s*P+i owns bins[bin_off[c] .. bin_off[c+1]), any order.
-	 * When `bins` is non-NULL `reads` is ignored and may be NULL; `read_off` is still required and
-	 * read_off[c+1]-read_off[c] must equal the sum of the cell's bin counts.  The bins are the likelihood's histogram:
-	 * with one pool size and at most 16 distinct qualities k_em adds them up directly; otherwise the engine rebuilds the
-	 * read multiset in device memory (k_expand_bins; there a cell whose counts disagree with read_off makes
-	 * crispgpu_wait fail with CRISPGPU_ERR_ARG).  Results are those of the equivalent `reads` batch. */
+	 * When `bins` is non-NULL `reads` is ignored and may be NULL; `read_off` is still required (per-pool read totals,
+	 * the running sum of the bin counts).  The bins are the likelihood's sufficient statistic: k_em adds them into its
+	 * histogram (dense path) or multiplies them with the table rows directly (sparse path); no read stream is rebuilt.
+	 * Results are those of the equivalent `reads` batch. */
 	const uint32_t* bin_off;    /* [n*P+1] or NULL */
 	const crispgpu_bin* bins;   /* [bin_off[n*P]] or NULL */
 	/* Compact alternative to `indcounts` (a pool's 24-entry row is mostly zeros): cell c owns

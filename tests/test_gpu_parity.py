@@ -382,10 +382,9 @@ def test_compact_read_format_matches_oracle(name, n, P, ploidy, depth, opts, kw)
 
 
 @pytest.mark.parametrize("ploidy", [20, [20, 24]], ids=["dense", "sparse"])
-def test_compact_read_format_splits_large_counts_and_rejects_bad_counts(ploidy):
-    """Multiplicities above 65535 take several bins.  With one pool size k_em adds the bins straight into its histogram;
-    with several it needs the read stream, which k_expand_bins rebuilds — and there a cell whose counts disagree with
-    read_off is an error."""
+def test_compact_read_format_splits_large_counts(ploidy):
+    """Multiplicities above 65535 take several bins; both likelihood paths of k_em (one pool size: histogram + tensor-core
+    contraction; several: bin-by-bin) add them up."""
     from crisp_b200.abi import bins_from_reads, reads_from_bins
     cfg = _cfg(2, ploidy, {})
     batch = synth_batch(4, 2, cfg.ploidy, 140000, seed=3, variant_frac=1.0, quals=[30])
@@ -395,13 +394,6 @@ def test_compact_read_format_splits_large_counts_and_rejects_bad_counts(ploidy):
     assert (want.status == 4).sum() >= 2
     eng = Engine(cfg)
     compare_results(eng.run(batch.binned()), want, label="split")
-    if ploidy != 20:
-        bad = batch.binned()
-        bad.bins = bad.bins.copy()
-        bad.bins[0] -= 1 << 16   # one read short of read_off
-        with pytest.raises(EngineError, match="bin counts"):
-            eng.run(bad)
-        compare_results(eng.run(batch.binned()), want, label="after-error")   # the context stays usable
     eng.close()
 
 
