@@ -303,7 +303,11 @@ def main():
     results = eng.run(batch)
 
     times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local}")
+    per_rank = [[float(times[0]) / args.steps, float(times[1]) / args.steps]]
     if world > 1:
+        gathered = [torch.zeros_like(times) for _ in range(world)]
+        dist.all_gather(gathered, times)
+        per_rank = [[float(g[0]) / args.steps, float(g[1]) / args.steps] for g in gathered]
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms_max, e2e_ms_max = float(times[0]), float(times[1])
     total_sites = batch.n_sites * world
@@ -363,6 +367,7 @@ def main():
                         "stage_ms_last_batch": {k: round(float(t_e2e[k]), 4) for k in ("h2d_ms", "evaluate_ms", "permute_ms", "filter_ms", "em_ms", "d2h_ms", "total_ms")},
                         "mode": f"{nctx} engine contexts per GPU, one host thread each looping crispgpu_submit/crispgpu_wait on pinned buffers; steps dealt round-robin"},
                 "gpu_launches": int(launches),
+                "per_rank_ms_per_step": {"resident": [round(x[0], 4) for x in per_rank], "e2e": [round(x[1], 4) for x in per_rank]},
                 "roofline": roof_em if dominant == "k_em" else roof_ev,
                 "roofline_secondary": roof_ev if dominant == "k_em" else roof_em,
                 "kernel_ms_per_step": {k: v / args.steps for k, v in kt.items()},
