@@ -445,7 +445,6 @@ int run_stage1(crispgpu_ctx* ctx)
 	EngineParams prm = make_params(ctx);
 	if (ctx->sparse_ic && n > 0) {
 		const size_t cells = (size_t)n * ctx->P;
-		CK(cudaMemsetAsync(ctx->d_b[6].p, 0, cells * kNC * sizeof(int32_t), ctx->stream));
 		k_expand_counts<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->db.ic_off, ctx->db.ic_sparse, static_cast<int32_t*>(ctx->d_b[6].p), cells);
 		launches++;
 		CK(launch_check());

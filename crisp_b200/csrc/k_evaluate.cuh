@@ -379,12 +379,16 @@ __global__ void k_fetch_reads(const uint16_t* __restrict__ src, uint16_t* __rest
 		if (seen[q]) atomicOr(reinterpret_cast<unsigned int*>(counters) + 4 + (q >> 5), 1u << (q & 31));
 }
 
-// Sparse per-pool allele counts -> the dense [n][P][24] table the kernels index (zeroed beforehand): one thread per entry.
+// Sparse per-pool allele counts -> the dense [n][P][24] table the kernels index: one thread per cell zeroes its 96-byte
+// row (six 16-byte stores) and then drops the cell's non-zero entries into it.
 __global__ void k_expand_counts(const uint32_t* __restrict__ ic_off, const uint32_t* __restrict__ ic_sparse, int32_t* __restrict__ indcounts, size_t n_cells)
 {
 	for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < n_cells; c += (size_t)gridDim.x * blockDim.x) {
 		const uint32_t e0 = ic_off[c], e1 = ic_off[c + 1];
 		int32_t* row = indcounts + c * kNC;
+		int4* row4 = reinterpret_cast<int4*>(row);
+#pragma unroll
+		for (int k = 0; k < kNC / 4; k++) row4[k] = make_int4(0, 0, 0, 0);
 		for (uint32_t e = e0; e < e1; e++) {
 			const uint32_t x = __ldg(ic_sparse + e);
 			const uint32_t idx = x >> 27;
