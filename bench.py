@@ -341,21 +341,23 @@ def main():
         ev_bytes = batch.n_sites * (96.0 * P + 40.0 + 5 * 110.0)
         dominant = "k_em" if em_ms >= ev_ms else "k_evaluate"
         # DRAM traffic per launch from the committed ncu --set full capture of this very configuration (null otherwise)
-        traffic = {}
+        traffic, ncu_static = {}, {}
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r1", "traffic.json"))).get(args.workload + (":bins" if args.e2e_format == "bins" else ""), {})
             if tj.get("sites") == batch.n_sites:
                 traffic = {k: v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in tj.items() if isinstance(v, dict)}
+                ncu_static = {k: {m: v[m] for m in ("issue_active_pct", "fp64_pipe_pct", "warp_instructions", "registers") if m in v} for k, v in tj.items() if isinstance(v, dict)}
         except Exception:
             pass
         roof_em = {"kernel": "k_em", "bound": "fp64", "achieved": ge_flops / (em_ms * 1e-3) / 1e12 if em_ms > 0 else None, "peak": fp64_peak,
                    "unit": "TFLOP/s", "frac": (ge_flops / (em_ms * 1e-3) / 1e12 / fp64_peak) if em_ms > 0 and fp64_peak > 0 else None,
                    "traffic": traffic.get("k_em"), "algorithmic_bytes": em_bytes, "peak_source": "DFMA loop measured live (crispgpu_measure_fp64_tflops)",
                    "ms_per_launch": em_ms, "tasks_per_launch": n_em, "mean_em_iterations": float(iters.mean()) if iters.size else 0.0,
-                   "algorithmic_hbm_GBps": em_bytes / (em_ms * 1e-3) / 1e9 if em_ms > 0 else None}
+                   "algorithmic_hbm_GBps": em_bytes / (em_ms * 1e-3) / 1e9 if em_ms > 0 else None,
+                   "ncu_committed_capture": ncu_static.get("k_em") or None}
         roof_ev = {"kernel": "k_evaluate", "bound": "hbm", "achieved": ev_bytes / (ev_ms * 1e-3) / 1e9 if ev_ms > 0 else None, "peak": hbm_peak, "unit": "GB/s",
                    "frac": (ev_bytes / (ev_ms * 1e-3) / 1e9 / hbm_peak) if ev_ms > 0 else None, "traffic": traffic.get("k_evaluate"), "algorithmic_bytes": ev_bytes, "peak_source": hbm_src,
-                   "ms_per_launch": ev_ms, "sites_per_launch": batch.n_sites}
+                   "ms_per_launch": ev_ms, "sites_per_launch": batch.n_sites, "ncu_committed_capture": ncu_static.get("k_evaluate") or None}
         line = {"metric": "candidate sites/sec", "value": value, "unit": "sites/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config, "clocks": clocks,
