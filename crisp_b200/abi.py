@@ -302,7 +302,7 @@ class Batch:
             raise ValueError("batch needs indcounts or ic_off/ic_sparse")
         if self.bins is not None:
             want("bin_off", n * P + 1)
-            if n and (int(self.bin_off[-1]) != self.bins.size or int((self.bins >> 16).sum(dtype=np.int64)) != int(self.read_off[-1])):
+            if n and (int(self.bin_off[-1]) != self.bins.size or (self.read_off is not None and int((self.bins >> 16).sum(dtype=np.int64)) != int(self.read_off[-1]))):
                 raise ValueError("bins do not match bin_off / read_off")
         if self.alt_off is not None and (self.alt_reads is None or int(self.alt_off[-1]) != self.alt_reads.size):
             raise ValueError("alt_off[-1] != len(alt_reads)")
@@ -324,6 +324,7 @@ class Batch:
         out.__dict__.update(self.__dict__)
         out.bin_off, out.bins = bins_from_reads(self.read_off, self.reads)
         out.reads = None
+        out.read_off = None   # indexes the read stream only
         return out
 
     def compact(self) -> "Batch":

@@ -271,11 +271,11 @@ int collect_arrays(crispgpu_ctx* ctx, const crispgpu_batch* b, BatchArray* a)
 {
 	const size_t n = b->n_sites, P = ctx->P;
 	const bool sparse_ic = b->ic_off != nullptr && (b->ic_sparse != nullptr || (n && b->ic_off[n * P] == 0));
-	if (!b->tid || !b->pos || !b->refbase || !b->maxvec_al || !b->maxvec_ct || !b->counts || (!b->indcounts && !sparse_ic) || !b->read_off) return CRISPGPU_ERR_ARG;
-	const size_t nreads = n ? b->read_off[n * P] : 0;
-	const size_t nalt = (b->alt_off && n) ? b->alt_off[n * 5] : 0;
 	const bool binned = b->bins != nullptr || (b->bin_off != nullptr && n && b->bin_off[n * P] == 0);
-	if (nreads && !b->reads && !binned) return CRISPGPU_ERR_ARG;
+	if (!b->tid || !b->pos || !b->refbase || !b->maxvec_al || !b->maxvec_ct || !b->counts || (!b->indcounts && !sparse_ic) || (!b->read_off && !binned)) return CRISPGPU_ERR_ARG;
+	const size_t nreads = (n && !binned) ? b->read_off[n * P] : 0;
+	const size_t nalt = (b->alt_off && n) ? b->alt_off[n * 5] : 0;
+	if (nreads && !b->reads) return CRISPGPU_ERR_ARG;
 	if (binned && !b->bin_off) return CRISPGPU_ERR_ARG;
 	if (nalt && !b->alt_reads) return CRISPGPU_ERR_ARG;
 	if (b->amb_idx && b->n_amb > 0 && !b->amb_dec) return CRISPGPU_ERR_ARG;
@@ -289,7 +289,7 @@ int collect_arrays(crispgpu_ctx* ctx, const crispgpu_batch* b, BatchArray* a)
 	a[k++] = {b->indcounts, n * P * 96};
 	a[k++] = {b->indel_len, b->indel_len ? n * 16 : 0};
 	a[k++] = {b->hplen, b->hplen ? n * 16 : 0};
-	a[k++] = {b->read_off, (n * P + 1) * 4};
+	a[k++] = {binned ? nullptr : b->read_off, (n * P + 1) * 4};  // a compact batch has no read stream to index
 	a[k++] = {b->reads, nreads * 2};
 	a[k++] = {b->alt_off, b->alt_off ? (n * 5 + 1) * 4 : 0};
 	a[k++] = {b->alt_reads, nalt * sizeof(crispgpu_altread)};
@@ -357,7 +357,7 @@ int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b, bool lazy)
 	ctx->db.n_sites = b->n_sites;
 	ctx->db.P = ctx->P;
 	ctx->n_sites = b->n_sites;
-	ctx->n_reads = b->n_sites ? b->read_off[(size_t)b->n_sites * ctx->P] : 0;
+	ctx->n_reads = (b->n_sites && !ctx->binned) ? b->read_off[(size_t)b->n_sites * ctx->P] : 0;
 	ctx->n_bins = (ctx->binned && b->n_sites) ? b->bin_off[(size_t)b->n_sites * ctx->P] : 0;
 	ctx->timing.h2d_bytes = bytes;
 	ctx->copied_bytes = bytes;
@@ -620,7 +620,7 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 		ctx->bins_direct = ctx->binned;  // both likelihood paths of k_em take the (value, count) bins as they are
 		memcpy(ctx->qlist, ql, sizeof ql);
 		// two-plane variant: no bidirectional read in the batch, one pool size, no association pass
-		const bool scanned = g.em_flag >= 1 && g.use_base_qvs == 1 && ctx->n_reads > 0;
+		const bool scanned = g.em_flag >= 1 && g.use_base_qvs == 1 && (ctx->n_reads > 0 || (ctx->binned && ctx->n_bins > 0));
 		const bool nobidir = scanned && hc[10] == 0 && ctx->class_ploidy.size() == 1 && !(g.association == 1 && ctx->d_pheno.p);
 		ctx->nobidir = nobidir ? 1 : 0;
 		const int key = (dense ? nq : 0) + (nobidir ? 64 : 0);

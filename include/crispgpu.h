@@ -155,8 +155,7 @@ typedef struct crispgpu_batch {
 	const double* tstats;       /* [n][16] */
 	/* Compact alternative to `reads` (the likelihood depends on a pool's reads only through how many carry each
 	 * (quality, base, strand, bidirectional) value): cell c = s*P+i owns bins[bin_off[c] .. bin_off[c+1]), any order.
-	 * When `bins` is non-NULL `reads` is ignored and may be NULL; `read_off` is still required (per-pool read totals,
-	 * the running sum of the bin counts).  The bins are the likelihood's sufficient statistic: k_em adds them into its
+	 * When `bins` is non-NULL `reads` and `read_off` are ignored and may be NULL.  The bins are the likelihood's sufficient statistic: k_em adds them into its
 	 * histogram (dense path) or multiplies them with the table rows directly (sparse path); no read stream is rebuilt.
 	 * Results are those of the equivalent `reads` batch. */
 	const uint32_t* bin_off;    /* [n*P+1] or NULL */

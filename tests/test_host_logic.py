@@ -131,7 +131,7 @@ def test_compact_formats_round_trip():
     assert np.array_equal(dense.reshape(-1), batch.indcounts)
     c = batch.compact()
     c.validate()
-    assert c.reads is None and c.indcounts is None and c.nbytes() < batch.nbytes()
+    assert c.reads is None and c.read_off is None and c.indcounts is None and c.nbytes() < batch.nbytes()
     # a multiplicity above 65535 is split over consecutive bins of the same value
     ro1 = np.array([0, 140000], np.uint32)
     bo1, b1 = bins_from_reads(ro1, np.full(140000, 0x1A1E, np.uint16))

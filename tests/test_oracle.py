@@ -184,7 +184,7 @@ def test_host_shim_round_trip(kw):
     # compact mode of the packer: the same read lists come back as the (value, count) bins bins_from_reads derives
     from crisp_b200.abi import bins_from_reads
     both = batch.compact()
-    both.reads, both.indcounts = batch.reads, batch.indcounts   # the harness rebuilds the reference's structures from these
+    both.reads, both.read_off, both.indcounts = batch.reads, batch.read_off, batch.indcounts   # the harness rebuilds the reference's structures from these
     bad, msg = ref.shim_roundtrip(both)
     assert bad == 0, msg
     assert np.array_equal(bins_from_reads(batch.read_off, batch.reads)[1], both.bins)
