@@ -205,7 +205,7 @@ _BATCH_ARRAYS = [
     ("tid", np.int32, True),
     ("pos", np.int32, True),
     ("refbase", np.uint8, True),
-    ("maxvec_al", np.uint8, True),
+    ("maxvec_al", np.uint8, True),   # required by the constructor; without_maxvec() drops them (sorted on the device)
     ("maxvec_ct", np.int32, True),
     ("counts", np.int32, True),
     ("indcounts", np.int32, True),
@@ -337,6 +337,13 @@ class Batch:
         if out.ic_off is None:
             out.ic_off, out.ic_sparse = sparse_counts_from_dense(self.indcounts)
             out.indcounts = None
+        return out
+
+    def without_maxvec(self) -> "Batch":
+        """The batch without maxvec_al/maxvec_ct: the engine sorts the alleles itself (k_candidates)."""
+        out = Batch.__new__(Batch)
+        out.__dict__.update(self.__dict__)
+        out.maxvec_al = out.maxvec_ct = None
         return out
 
     def as_c(self) -> CBatch:

@@ -48,10 +48,12 @@ struct crispgpu_ctx {
 	int P = 0, K = 0, nmax = 0;
 	// device configuration tables
 	DevBuf d_ploidy, d_pclass, d_class_ploidy, d_NC, d_T, d_ncr, d_pheno;
+	DevBuf d_scr[8];               // crispgpu_screen_positions: inputs and outputs of the candidate screen
 	DevBuf d_need_reads;           // per-site flags of the on-demand read fetch
 	const uint16_t* lazy_reads = nullptr;  // device-visible address of the caller's pinned read array (on-demand fetch), or null
 	int64_t copied_bytes = 0;
 	bool bins_direct = false;      // k_em reads the bins themselves
+	bool device_sort = false;      // maxvec_al/maxvec_ct are produced on the device (k_candidates)
 	bool sparse_ic = false;        // the batch came with sparse per-pool allele counts
 	bool binned = false;           // the batch came in the compact (value, count) read format
 	DevBuf d_exact_row, d_exact_cl, d_exact_done;  // exact_mode: term tables of the exact 2 x k test, per-task decided flags
@@ -272,7 +274,7 @@ int collect_arrays(crispgpu_ctx* ctx, const crispgpu_batch* b, BatchArray* a)
 	const size_t n = b->n_sites, P = ctx->P;
 	const bool sparse_ic = b->ic_off != nullptr && (b->ic_sparse != nullptr || (n && b->ic_off[n * P] == 0));
 	const bool binned = b->bins != nullptr || (b->bin_off != nullptr && n && b->bin_off[n * P] == 0);
-	if (!b->tid || !b->pos || !b->refbase || !b->maxvec_al || !b->maxvec_ct || !b->counts || (!b->indcounts && !sparse_ic) || (!b->read_off && !binned)) return CRISPGPU_ERR_ARG;
+	if (!b->tid || !b->pos || !b->refbase || (!b->maxvec_al != !b->maxvec_ct) || !b->counts || (!b->indcounts && !sparse_ic) || (!b->read_off && !binned)) return CRISPGPU_ERR_ARG;
 	const size_t nreads = (n && !binned) ? b->read_off[n * P] : 0;
 	const size_t nalt = (b->alt_off && n) ? b->alt_off[n * 5] : 0;
 	if (nreads && !b->reads) return CRISPGPU_ERR_ARG;
@@ -325,8 +327,16 @@ int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b, bool lazy)
 	const bool reads_used = ctx->cfg.em_flag >= 1 && ctx->cfg.use_base_qvs == 1;
 	ctx->lazy_reads = nullptr;
 	ctx->binned = a[19].host != nullptr;
+	ctx->device_sort = false;
 	ctx->sparse_ic = a[21].host != nullptr;
 	for (int i = 0; i < k; i++) {
+		if ((i == 3 || i == 4) && a[i].host == nullptr && a[i].bytes) {  // no maxvec from the host: k_candidates sorts the alleles
+			int rc = ensure_dev(ctx, ctx->d_b[i], a[i].bytes);
+			if (rc) return rc;
+			dptr[i] = ctx->d_b[i].p;
+			ctx->device_sort = true;
+			continue;
+		}
 		if (i == 6 && ctx->sparse_ic) {
 			int rc = ensure_dev(ctx, ctx->d_b[i], a[i].bytes ? a[i].bytes : 1);
 			if (rc) return rc;
@@ -446,6 +456,12 @@ int run_stage1(crispgpu_ctx* ctx)
 	if (ctx->sparse_ic && n > 0) {
 		const size_t cells = (size_t)n * ctx->P;
 		k_expand_counts<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->db.ic_off, ctx->db.ic_sparse, static_cast<int32_t*>(ctx->d_b[6].p), cells);
+		launches++;
+		CK(launch_check());
+	}
+	if (ctx->device_sort && n > 0) {
+		k_candidates<<<(n + 7) / 8, 256, 0, ctx->stream>>>(ctx->db.refbase, ctx->db.counts, ctx->db.indcounts, static_cast<const int32_t*>(ctx->d_ploidy.p), n, ctx->P,
+		                                                   static_cast<uint8_t*>(ctx->d_b[3].p), static_cast<int32_t*>(ctx->d_b[4].p), nullptr);
 		launches++;
 		CK(launch_check());
 	}
@@ -954,6 +970,7 @@ void crispgpu_destroy(crispgpu_ctx* ctx)
 	auto fh = [](DevBuf& b) { if (b.p) cudaFreeHost(b.p); b.p = nullptr; };
 	fd(ctx->d_ploidy); fd(ctx->d_pclass); fd(ctx->d_class_ploidy); fd(ctx->d_NC); fd(ctx->d_T); fd(ctx->d_ncr); fd(ctx->d_pheno);
 	fd(ctx->d_exact_row); fd(ctx->d_exact_cl); fd(ctx->d_exact_done); fd(ctx->d_need_reads);
+	for (auto& b : ctx->d_scr) fd(b);
 	for (auto& b : ctx->d_b) fd(b);
 	for (auto& b : ctx->d_o) fd(b);
 	for (auto& b : ctx->h_o) fh(b);
@@ -1016,6 +1033,40 @@ int crispgpu_wait(crispgpu_ctx* ctx, int64_t ticket, crispgpu_results* out)
 	rc = finish_timing(ctx);
 	if (rc) return rc;
 	fill_results(ctx, out);
+	return CRISPGPU_OK;
+}
+
+int crispgpu_screen_positions(crispgpu_ctx* ctx, int32_t n, const uint8_t* refbase, const int32_t* counts, const int32_t* indcounts,
+                              const uint32_t* ic_off, const crispgpu_count* ic_sparse, uint8_t* maxvec_al, int32_t* maxvec_ct, int32_t* potential)
+{
+	if (!ctx || n < 0 || !refbase || !counts || (!indcounts && !ic_off) || !maxvec_al || !maxvec_ct || !potential) return CRISPGPU_ERR_ARG;
+	if (ctx->inflight) return CRISPGPU_ERR_TICKET;
+	if (n == 0) return CRISPGPU_OK;
+	CK(cudaSetDevice(ctx->device));
+	const size_t cells = (size_t)n * ctx->P;
+	DevBuf &d_ref = ctx->d_scr[0], &d_cnt = ctx->d_scr[1], &d_ic = ctx->d_scr[2], &d_off = ctx->d_scr[3], &d_sp = ctx->d_scr[4], &d_al = ctx->d_scr[5], &d_ct = ctx->d_scr[6], &d_pot = ctx->d_scr[7];
+	int rc;
+	if ((rc = ensure_dev(ctx, d_ref, n)) || (rc = ensure_dev(ctx, d_cnt, (size_t)n * kNC * 4)) || (rc = ensure_dev(ctx, d_ic, cells * kNC * 4)) ||
+	    (rc = ensure_dev(ctx, d_al, (size_t)n * 8)) || (rc = ensure_dev(ctx, d_ct, (size_t)n * 32)) || (rc = ensure_dev(ctx, d_pot, (size_t)n * 4))) return rc;
+	CK(cudaMemcpyAsync(d_ref.p, refbase, n, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(d_cnt.p, counts, (size_t)n * kNC * 4, cudaMemcpyHostToDevice, ctx->stream));
+	if (indcounts) CK(cudaMemcpyAsync(d_ic.p, indcounts, cells * kNC * 4, cudaMemcpyHostToDevice, ctx->stream));
+	else {
+		const size_t nsp = ic_off[cells];
+		if (nsp && !ic_sparse) return CRISPGPU_ERR_ARG;
+		if ((rc = ensure_dev(ctx, d_off, (cells + 1) * 4)) || (rc = ensure_dev(ctx, d_sp, (nsp ? nsp : 1) * 4))) return rc;
+		CK(cudaMemcpyAsync(d_off.p, ic_off, (cells + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+		if (nsp) CK(cudaMemcpyAsync(d_sp.p, ic_sparse, nsp * 4, cudaMemcpyHostToDevice, ctx->stream));
+		k_expand_counts<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(static_cast<const uint32_t*>(d_off.p), static_cast<const uint32_t*>(d_sp.p), static_cast<int32_t*>(d_ic.p), cells);
+		CK(launch_check());
+	}
+	k_candidates<<<(n + 7) / 8, 256, 0, ctx->stream>>>(static_cast<const uint8_t*>(d_ref.p), static_cast<const int32_t*>(d_cnt.p), static_cast<const int32_t*>(d_ic.p),
+	                                                   static_cast<const int32_t*>(ctx->d_ploidy.p), n, ctx->P, static_cast<uint8_t*>(d_al.p), static_cast<int32_t*>(d_ct.p), static_cast<int32_t*>(d_pot.p));
+	CK(launch_check());
+	CK(cudaMemcpyAsync(maxvec_al, d_al.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaMemcpyAsync(maxvec_ct, d_ct.p, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaMemcpyAsync(potential, d_pot.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
 	return CRISPGPU_OK;
 }
 

@@ -397,6 +397,54 @@ __global__ void k_expand_counts(const uint32_t* __restrict__ ic_off, const uint3
 	}
 }
 
+// Candidate screen (variantcalls.c:62-92): one warp per position.  Lanes sum the pools' contributions to the
+// potential-variant score; lane 0 builds maxvec exactly as sort_allelecounts does (allelecounts.c:134-183, IUPAC off):
+// read counts per allele, reference allele swapped to the front, then the exchange sort `if (ct[i] < ct[j]) swap` over
+// i = 1..6, j = i+1..7 — the same comparisons in the same order, so ties fall the same way.
+__global__ void k_candidates(const uint8_t* __restrict__ refbase, const int32_t* __restrict__ counts, const int32_t* __restrict__ indcounts,
+                             const int32_t* __restrict__ ploidy, int n_sites, int P, uint8_t* __restrict__ maxvec_al, int32_t* __restrict__ maxvec_ct,
+                             int32_t* __restrict__ potential)
+{
+	const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+	for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < n_sites; s += gridDim.x * wpb) {
+		const int ref = refbase[s];
+		if (potential) {
+			int pot = 0;
+			for (int i = lane; i < P; i += 32) {
+				const int32_t* r = indcounts + ((size_t)s * P + i) * kNC;
+				const bool diploid = ploidy[i] == 2;
+#pragma unroll
+				for (int a = 0; a < 8; a++) {
+					if (a == ref) continue;
+					const int t = r[a] + r[a + 8] + r[a + 16];
+					if (t >= 3) pot += 2;
+					else if (t >= 1 && diploid) pot += t;
+				}
+			}
+			pot = warp_sum(pot);
+			if (lane == 0) potential[s] = pot;
+		}
+		if (lane == 0) {
+			int ct[8], al[8];
+#pragma unroll
+			for (int a = 0; a < 8; a++) { ct[a] = counts[s * kNC + a] + counts[s * kNC + a + 8] + counts[s * kNC + a + 16]; al[a] = a; }
+			if (ref >= 1 && ref < 8) {
+				// swap entry 0 with the reference allele's entry (static indices only: the arrays live in registers)
+#pragma unroll
+				for (int a = 1; a < 8; a++)
+					if (a == ref) { const int tc = ct[0]; ct[0] = ct[a]; ct[a] = tc; const int ta = al[0]; al[0] = al[a]; al[a] = ta; }
+			}
+#pragma unroll
+			for (int i = 1; i < 7; i++)
+#pragma unroll
+				for (int j = i + 1; j < 8; j++)
+					if (ct[i] < ct[j]) { const int tc = ct[i]; ct[i] = ct[j]; ct[j] = tc; const int ta = al[i]; al[i] = al[j]; al[j] = ta; }
+#pragma unroll
+			for (int a = 0; a < 8; a++) { maxvec_al[s * 8 + a] = (uint8_t)al[a]; maxvec_ct[s * 8 + a] = ct[a]; }
+		}
+	}
+}
+
 // Which qualities occur (and whether any read is bidirectional) in a compact batch: k_qualmap's outputs read from the bins
 // themselves (a tenth of the read stream), flat 16-byte loads over the whole bin array.
 __global__ void k_scan_bins(const uint32_t* __restrict__ bins, size_t n_bins, int32_t* counters)

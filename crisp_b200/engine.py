@@ -16,7 +16,7 @@ from .abi import Batch, CBatch, Config, CResults, EngineConfig, Results, Timing
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libcrispgpu.so")
 
 EXPORTS = [
-    "crispgpu_config_defaults", "crispgpu_create", "crispgpu_destroy", "crispgpu_submit", "crispgpu_wait", "crispgpu_advance",
+    "crispgpu_config_defaults", "crispgpu_create", "crispgpu_destroy", "crispgpu_submit", "crispgpu_wait", "crispgpu_advance", "crispgpu_screen_positions",
     "crispgpu_upload", "crispgpu_run_resident", "crispgpu_get_timing", "crispgpu_last_error",
     "crispgpu_host_alloc", "crispgpu_host_free", "crispgpu_abi_version", "crispgpu_device_count",
     "crispgpu_measure_fp64_tflops",
@@ -158,6 +158,18 @@ class Engine:
         self._check(self.lib.crispgpu_wait(self.h, ticket, C.byref(cres)), "crispgpu_wait")
         self._inflight = None
         return Results.from_c(cres, self.cfg.n_pools) if copy else cres
+
+    def screen_positions(self, batch: Batch):
+        """(maxvec_al [n,8], maxvec_ct [n,8], potential [n]) of the candidate screen (crispgpu_screen_positions) for the
+        positions of `batch` (its counts, refbase and dense or sparse per-pool counts)."""
+        n = batch.n_sites
+        al, ct, pot = np.zeros((n, 8), np.uint8), np.zeros((n, 8), np.int32), np.zeros(n, np.int32)
+        ptr = lambda a: a.ctypes.data if a is not None else None  # noqa: E731
+        fn = self.lib.crispgpu_screen_positions
+        fn.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 8
+        self._check(fn(self.h, n, ptr(batch.refbase), ptr(batch.counts), ptr(batch.indcounts), ptr(batch.ic_off), ptr(batch.ic_sparse),
+                       ptr(al), ptr(ct), ptr(pot)), "crispgpu_screen_positions")
+        return al, ct, pot
 
     def run(self, batch: Batch) -> Results:
         return self.wait(self.submit(batch))

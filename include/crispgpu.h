@@ -120,7 +120,7 @@ typedef struct crispgpu_batch {
 	const int32_t* tid;         /* [n]     reference id  (pass-through key, RNG key) */
 	const int32_t* pos;         /* [n]     variant->position (0-based) */
 	const uint8_t* refbase;     /* [n]     variant->refbase 0..3 */
-	const uint8_t* maxvec_al;   /* [n][8]  maxvec[k].al after sort_allelecounts (allelecounts.c:155) */
+	const uint8_t* maxvec_al;   /* [n][8]  maxvec[k].al after sort_allelecounts (allelecounts.c:155); NULL (with maxvec_ct): sorted on the device */
 	const int32_t* maxvec_ct;   /* [n][8]  maxvec[k].ct */
 	const int32_t* counts;      /* [n][24] variant->counts */
 	const int32_t* indcounts;   /* [n][P][24] variant->indcounts[i][0..3A) */
@@ -255,6 +255,18 @@ void crispgpu_destroy(crispgpu_ctx* ctx);
  * CRISPGPU_ERR_TICKET; so does a wait with a stale or unknown ticket. */
 int crispgpu_submit(crispgpu_ctx* ctx, const crispgpu_batch* batch, int64_t* ticket);
 int crispgpu_wait(crispgpu_ctx* ctx, int64_t ticket, crispgpu_results* out);
+/* Candidate screen for n positions — what jointvariantcaller does between calculate_allelecounts and the call into the
+ * engine (variantcalls.c:62-92): sort_allelecounts (parsebam/allelecounts.c:134-183, the
+ * PICALL==3 ordering: reference allele first, then the exchange sort by read count) and the potential-variant score
+ * (variantcalls.c:76-92: +2 per (allele, pool) with >= 3 reads of a non-reference allele, + the read count for diploid
+ * pools with >= 1).  Inputs are the batch arrays `counts`, `refbase`, and `indcounts` or `ic_off`/`ic_sparse`; outputs
+ * into caller memory: maxvec_al [n][8], maxvec_ct [n][8], potential [n].  A position is a candidate when
+ * potential >= 2 (and its reference base is not N, which the front end knows).  Synchronous.
+ * crispgpu_submit runs the same kernel for a batch whose maxvec_al/maxvec_ct are NULL. */
+int crispgpu_screen_positions(crispgpu_ctx* ctx, int32_t n_sites, const uint8_t* refbase, const int32_t* counts,
+                              const int32_t* indcounts, const uint32_t* ic_off, const crispgpu_count* ic_sparse,
+                              uint8_t* maxvec_al, int32_t* maxvec_ct, int32_t* potential);
+
 /* Optional, between submit and wait: waits only for the screening counters of the batch and enqueues its caller
  * kernels and device-to-host copies without waiting for them.  A front end juggling two contexts calls it on the other
  * context before blocking in crispgpu_wait, so that this batch's EM runs while that batch's results travel back. */

@@ -1325,3 +1325,50 @@ double crisp_oracle_exact_2xk(const int* N, const int* A, int size)
 	return p;
 }
 void crisp_oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { philox4x32_10(ctr, key, out); }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * candidate screen — variantcalls.c:62-92
+ * ---------------------------------------------------------------------------------------------------------- */
+/* sort_allelecounts, parsebam/allelecounts.c:134-183 with IUPAC off: read count per allele, the reference allele's entry
+ * swapped to the front, then `if (ct[i] < ct[j]) swap` for i = 1..6, j = i+1..7 */
+static void o_sort_allelecounts(const int32_t* counts, int refbase, uint8_t* al_out, int32_t* ct_out)
+{
+	int ct[8], al[8];
+	for (int i = 0; i < 8; i++) { ct[i] = counts[i] + counts[i + 8] + counts[i + 16]; al[i] = i; }
+	if (refbase >= 1 && refbase < 8) {
+		int t = ct[0]; ct[0] = ct[refbase]; ct[refbase] = t;
+		t = al[0]; al[0] = al[refbase]; al[refbase] = t;
+	}
+	for (int i = 1; i < 7; i++)
+		for (int j = i + 1; j < 8; j++)
+			if (ct[i] < ct[j]) {
+				int t = ct[i]; ct[i] = ct[j]; ct[j] = t;
+				t = al[i]; al[i] = al[j]; al[j] = t;
+			}
+	for (int i = 0; i < 8; i++) { al_out[i] = (uint8_t)al[i]; ct_out[i] = ct[i]; }
+}
+
+/* potentialvariant of jointvariantcaller (variantcalls.c:76-92) for PICALL == 3 */
+static int o_potential_variant(const int32_t* indcounts, const int32_t* ploidy, int P, int refbase)
+{
+	int pot = 0;
+	for (int i = 0; i < 8; i++) {
+		if (i == refbase) continue;
+		for (int j = 0; j < P; j++) {
+			const int32_t* r = indcounts + (size_t)j * 24;
+			const int t = r[i] + r[i + 8] + r[i + 16];
+			if (t >= 3) pot += 2;
+			else if (t >= 1 && ploidy[j] == 2) pot += t;
+		}
+	}
+	return pot;
+}
+
+void crisp_oracle_screen(void* h, int n, const uint8_t* refbase, const int32_t* counts, const int32_t* indcounts, uint8_t* maxvec_al, int32_t* maxvec_ct, int32_t* potential)
+{
+	oracle_ctx* c = (oracle_ctx*)h;
+	for (int s = 0; s < n; s++) {
+		o_sort_allelecounts(counts + (size_t)s * 24, refbase[s], maxvec_al + (size_t)s * 8, maxvec_ct + (size_t)s * 8);
+		potential[s] = o_potential_variant(indcounts + (size_t)s * c->P * 24, c->ploidy, c->P, refbase[s]);
+	}
+}

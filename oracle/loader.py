@@ -140,6 +140,17 @@ class RefEngine(_CpuEngine):
         rc = fn(self.h, C.byref(cb), msg, 256)
         return rc, msg.value.decode()
 
+    def sort_allelecounts(self, batch: Batch):
+        """The reference's own sort_allelecounts (parsebam/allelecounts.c:134-183) on every site of the batch."""
+        n = batch.n_sites
+        al, ct = np.zeros((n, 8), np.uint8), np.zeros((n, 8), np.int32)
+        fn = self.lib.crisp_ref_sort_allelecounts
+        fn.restype = None
+        fn.argtypes = [C.c_void_p, C.POINTER(CBatch), C.c_void_p, C.c_void_p]
+        cb = batch.as_c()
+        fn(self.h, C.byref(cb), al.ctypes.data, ct.ctypes.data)
+        return al, ct
+
     def scalar(self, name: str, restype, argtypes):
         fn = getattr(self.lib, "crisp_ref_" + name)
         fn.restype = restype
@@ -150,6 +161,16 @@ class RefEngine(_CpuEngine):
 class OracleEngine(_CpuEngine):
     lib_path = ORACLE_LIB
     prefix = "crisp_oracle"
+
+    def screen(self, batch: Batch):
+        """Candidate screen restatement (variantcalls.c:62-92): (maxvec_al, maxvec_ct, potential)."""
+        n = batch.n_sites
+        al, ct, pot = np.zeros((n, 8), np.uint8), np.zeros((n, 8), np.int32), np.zeros(n, np.int32)
+        fn = self.lib.crisp_oracle_screen
+        fn.restype = None
+        fn.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6
+        fn(self.h, n, batch.refbase.ctypes.data, batch.counts.ctypes.data, batch.indcounts.ctypes.data, al.ctypes.data, ct.ctypes.data, pot.ctypes.data)
+        return al, ct, pot
 
     def scalar(self, name: str, restype, argtypes):
         fn = getattr(self.lib, "crisp_oracle_" + name)

@@ -858,3 +858,21 @@ double crisp_ref_exact_2xk(const int* N, const int* A, int size)
 	free(rows);
 	return out;
 }
+
+
+/* ---- candidate screen: the reference's own sort_allelecounts (parsebam/allelecounts.c:134-183) on a batch's counts ---- */
+int sort_allelecounts(struct VARIANT* variant, ALLELE* maxvec, int refbase);
+
+void crisp_ref_sort_allelecounts(void* h, const crispgpu_batch* b, uint8_t* maxvec_al, int32_t* maxvec_ct)
+{
+	ref_ctx* c = (ref_ctx*)h;
+	struct VARIANT* v = &c->variant;
+	apply_config(c);
+	ALLELE maxvec[8];
+	for (int s = 0; s < b->n_sites; s++) {
+		fill_site(c, b, s);
+		for (int k = 0; k < 8; k++) { maxvec[k].ct = 0; maxvec[k].al = k; }  /* variantcalls.c:60 */
+		sort_allelecounts(v, maxvec, v->refbase);
+		for (int k = 0; k < 8; k++) { maxvec_al[(size_t)s * 8 + k] = (uint8_t)maxvec[k].al; maxvec_ct[(size_t)s * 8 + k] = maxvec[k].ct; }
+	}
+}

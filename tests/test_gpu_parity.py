@@ -209,6 +209,28 @@ def test_results_independent_of_batching_and_sharding():
     eng.close()
 
 
+@pytest.mark.parametrize("ploidy", [20, [2, 20, 2, 20, 2, 20, 2, 20]], ids=["pooled", "mixed-diploid"])
+def test_candidate_screen_matches_oracle(ploidy):
+    """crispgpu_screen_positions (k_candidates): sort_allelecounts and the potential-variant score, dense and sparse
+    per-pool counts; and a batch submitted without maxvec gives the results of the batch with it."""
+    from test_oracle import _screen_batch
+    cfg, batch = _screen_batch(9, ploidy=ploidy, n=700)
+    want = OracleEngine(cfg).screen(batch)
+    eng = Engine(cfg)
+    for form in (batch, batch.compact()):
+        got = eng.screen_positions(form)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w)
+    # the synthetic generator sorted with the unscrambled counts; re-sort for this batch, then drop maxvec
+    batch.maxvec_al, batch.maxvec_ct = want[0].reshape(-1).copy(), want[1].reshape(-1).copy()
+    with_maxvec = eng.run(batch)
+    compare_results(eng.run(batch.without_maxvec()), with_maxvec, tol=0.0, label="device-sorted")
+    # several pool sizes take the bin-by-bin likelihood path: same terms as the per-read histogram, other summation order
+    compare_results(eng.run(pin_batch(batch.compact().without_maxvec())), with_maxvec, tol=0.0 if np.ndim(ploidy) == 0 else 1e-12, label="device-sorted-compact")
+    compare_results(with_maxvec, OracleEngine(cfg).run(batch, mode=RNG_PHILOX), label="oracle")
+    eng.close()
+
+
 def test_context_reuse_across_different_batches():
     """A context carries device buffers, flags and the k_em instantiation from batch to batch; whatever came before
     (other qualities, bidirectional reads, far fewer or far more tasks, the other batch format), the results are those of

@@ -281,3 +281,42 @@ def test_exact_mode_replaces_monte_carlo_for_small_tables():
     m = exact & (mc.perm_hits >= 5)
     assert m.sum() > 50
     assert np.corrcoef(ex.ctpval[m], mc.ctpval[m])[0, 1] > 0.5
+
+
+# ---- candidate screen (variantcalls.c:62-92) ------------------------------------------------
+def _screen_batch(seed, P=8, ploidy=20, n=400, **kw):
+    cfg = EngineConfig(ploidy=np.broadcast_to(np.asarray(ploidy), (P,)).copy(), options={})
+    batch = synth_batch(n, P, cfg.ploidy, 60, seed=seed, variant_frac=0.5, indel_frac=0.3, second_alt_frac=0.4, bidir_frac=0.1, **kw)
+    # sort ties and reference alleles other than the most frequent one: scramble some sites
+    rng = np.random.default_rng(seed)
+    n = batch.n_sites
+    batch.counts = batch.counts.copy()
+    c = batch.counts.reshape(-1, 24)
+    tie = rng.random(n) < 0.3
+    c[tie, 1] = c[tie, 2]; c[tie, 9] = c[tie, 10]; c[tie, 17] = c[tie, 18]
+    batch.refbase = rng.integers(0, 4, n).astype(np.uint8)
+    return cfg, batch
+
+
+@needs_ref
+def test_sort_allelecounts_equals_reference():
+    """o_sort_allelecounts against the reference's own sort_allelecounts (linked into oracle/_ref), ties included."""
+    for seed in (1, 2):
+        cfg, batch = _screen_batch(seed)
+        al, ct, _ = OracleEngine(cfg).screen(batch)
+        ral, rct = RefEngine(cfg).sort_allelecounts(batch)
+        assert np.array_equal(al, ral) and np.array_equal(ct, rct)
+        assert (ct[:, 1:-1] >= ct[:, 2:]).all() and np.array_equal(al[:, 0], batch.refbase)
+
+
+def test_potential_variant_score():
+    """variantcalls.c:76-92 (PICALL 3): +2 per (non-reference allele, pool) with >= 3 reads; diploid pools with 1-2 reads
+    add the read count.  Checked against a direct numpy evaluation."""
+    for ploidy in (20, 2, [2, 20, 2, 20, 2, 20, 2, 20]):
+        cfg, batch = _screen_batch(5, ploidy=ploidy)
+        _, _, pot = OracleEngine(cfg).screen(batch)
+        ic = batch.indcounts.reshape(batch.n_sites, 8, 3, 8).sum(axis=2)            # [site][pool][allele]
+        dip = (cfg.ploidy == 2)[None, :, None]
+        score = np.where(ic >= 3, 2, np.where((ic >= 1) & dip, ic, 0))
+        nonref = np.arange(8)[None, None, :] != batch.refbase[:, None, None]
+        assert np.array_equal(pot, (score * nonref).sum(axis=(1, 2)))
