@@ -208,7 +208,7 @@ struct PermTail {
 // Head: one CTA per task, the first kPermHead permutations with the reference's sequential stop rule
 // (contables.c:327-328) evaluated on prefix sums in permutation order.  Tasks that neither stopped nor exhausted
 // their permutations go to the tail queue.
-__global__ void k_permute_stranded(EngineParams prm, int l10cap, PermTail tail, const int32_t* __restrict__ exact_done)
+__global__ void __launch_bounds__(256, 4) k_permute_stranded(EngineParams prm, int l10cap, PermTail tail, const int32_t* __restrict__ exact_done)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const DevCfg& c = prm.c;
@@ -264,7 +264,7 @@ __global__ void k_permute_stranded(EngineParams prm, int l10cap, PermTail tail, 
 // Tail: work items = (chunk, task), chunk-major so that every earlier chunk of a task has started before a later one.
 // A chunk records its hit count and the indices of its first ten hits; it is skipped when ten hits are already known
 // (they all lie in earlier chunks, so the reference's loop would have broken before this chunk).
-__global__ void k_permute_stranded_tail(EngineParams prm, int l10cap, PermTail tail)
+__global__ void __launch_bounds__(256, 4) k_permute_stranded_tail(EngineParams prm, int l10cap, PermTail tail)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const DevCfg& c = prm.c;
