@@ -216,7 +216,11 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    want_ctx = args.contexts if args.contexts > 0 else max(2, min(6, (os.cpu_count() or 8) // max(1, world)))
+    # spinning waits are faster, but only while every waiting thread has a core of its own
+    oversubscribed = world * (want_ctx + 1) > (os.cpu_count() or 8) // 2
     cfg = EngineConfig(ploidy=np.full(wl["P"], wl["ploidy"]), options=wl["options"])
+    cfg_e2e = EngineConfig(ploidy=np.full(wl["P"], wl["ploidy"]), options=dict(wl["options"], blocking_wait=1 if oversubscribed else 0))
     # region shard of this rank: its own contiguous run of candidate sites (tid = rank)
     batch = make_batch(wl, args.sites, seed=1 + rank, tid=rank)
     shipped = batch.compact() if args.e2e_format == "bins" else batch   # the form both legs consume
@@ -264,10 +268,9 @@ def main():
     # GIL inside the calls, so the copies and kernels of the batches in flight overlap the way a multi-threaded front end
     # would drive them.  The K timed steps (batches) are dealt round-robin to the threads.
     import threading
-    want_ctx = args.contexts if args.contexts > 0 else max(2, min(6, (os.cpu_count() or 8) // max(1, world)))
     nctx = max(1, min(want_ctx, args.steps))
-    extra_streams = [torch.cuda.Stream(device=local) for _ in range(nctx - 1)]
-    engs = [eng] + [Engine(cfg, device=local, stream=st.cuda_stream) for st in extra_streams]
+    e2e_streams = [torch.cuda.Stream(device=local) for _ in range(nctx)]
+    engs = [Engine(cfg_e2e, device=local, stream=st.cuda_stream) for st in e2e_streams]
     for e in engs:
         for _ in range(max(1, args.warmup // 2)):
             e.run(pinned)
@@ -296,8 +299,8 @@ def main():
     e2e_s = time.perf_counter() - w0
     if errors:
         raise errors[0]
-    t_e2e = eng.timing()
-    for e in engs[1:]:
+    t_e2e = engs[0].timing()
+    for e in engs:
         e.close()
     clocks = sampler.stop() if rank == 0 else None
     results = eng.run(batch)
@@ -367,7 +370,7 @@ def main():
                         "input_format": ("compact: reads as (value,count) bins per site x pool (consumed as they are by k_em), per-pool allele counts as non-zero entries (k_expand_counts)" if args.e2e_format == "bins"
                                          else "one 16-bit element per read; sites that reach the likelihood fetched on demand (k_fetch_reads)"),
                         "stage_ms_last_batch": {k: round(float(t_e2e[k]), 4) for k in ("h2d_ms", "evaluate_ms", "permute_ms", "filter_ms", "em_ms", "d2h_ms", "total_ms")},
-                        "mode": f"{nctx} engine contexts per GPU, one host thread each looping crispgpu_submit/crispgpu_wait on pinned buffers; steps dealt round-robin"},
+                        "mode": f"{nctx} engine contexts per GPU, one host thread each looping crispgpu_submit/crispgpu_wait on pinned buffers; steps dealt round-robin; " + ("blocking waits (more waiting threads than spare cores)" if oversubscribed else "spinning waits")},
                 "gpu_launches": int(launches),
                 "per_rank_ms_per_step": {"resident": [round(x[0], 4) for x in per_rank], "e2e": [round(x[1], 4) for x in per_rank]},
                 "roofline": roof_em if dominant == "k_em" else roof_ev,

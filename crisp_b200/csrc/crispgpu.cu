@@ -90,6 +90,7 @@ struct crispgpu_ctx {
 	// bookkeeping
 	cudaEvent_t ev[EV_COUNT]{};
 	cudaEvent_t ev_counts = nullptr;
+	cudaEvent_t ev_done = nullptr;   // blocking-sync twin of EV_D2H (config.blocking_wait): crispgpu_wait sleeps on it
 	cudaEvent_t ev_epoch = nullptr;  // recorded at creation (crispgpu_debug_timeline)
 	int64_t ticket = 0;
 	bool inflight = false;
@@ -739,6 +740,7 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 		}
 	}
 	CK(cudaEventRecord(ctx->ev[EV_D2H], ctx->stream));
+	if (ctx->ev_done) CK(cudaEventRecord(ctx->ev_done, ctx->stream));
 	ctx->timing.launches = launches;
 	ctx->timing.d2h_bytes = d2h;
 	ctx->timing.n_tasks_em = ctx->n_call;
@@ -892,7 +894,8 @@ int crispgpu_create(const crispgpu_config* cfg, int device_id, void* stream, cri
 		ctx->own_stream = true;
 	}
 	for (int i = 0; i < EV_COUNT; i++) if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
-	if (cudaEventCreateWithFlags(&ctx->ev_counts, cudaEventDisableTiming) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
+	if (cudaEventCreateWithFlags(&ctx->ev_counts, cudaEventDisableTiming | (cfg->blocking_wait == 1 ? cudaEventBlockingSync : 0)) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
+	if (cfg->blocking_wait == 1 && cudaEventCreateWithFlags(&ctx->ev_done, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
 	if (cudaEventCreate(&ctx->ev_epoch) != cudaSuccess || cudaEventRecord(ctx->ev_epoch, ctx->stream) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
 	if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
 	if (cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) return fail(CRISPGPU_ERR_CUDA);
@@ -980,6 +983,7 @@ void crispgpu_destroy(crispgpu_ctx* ctx)
 	for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
 	if (ctx->ev_counts) cudaEventDestroy(ctx->ev_counts);
 	if (ctx->ev_epoch) cudaEventDestroy(ctx->ev_epoch);
+	if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
 	if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
 	if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
 	if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
@@ -1029,7 +1033,7 @@ int crispgpu_wait(crispgpu_ctx* ctx, int64_t ticket, crispgpu_results* out)
 	int rc = ctx->advanced ? 0 : run_stage2(ctx, true);
 	ctx->advanced = false;
 	if (rc) return rc;
-	CK(cudaEventSynchronize(ctx->ev[EV_D2H]));
+	CK(cudaEventSynchronize(ctx->ev_done ? ctx->ev_done : ctx->ev[EV_D2H]));
 	rc = finish_timing(ctx);
 	if (rc) return rc;
 	fill_results(ctx, out);

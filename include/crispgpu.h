@@ -79,6 +79,9 @@ typedef struct crispgpu_config {
 	                              columns < 2001 reads get compute_pvalue_exact (FET/contables_exact.c:62-117) on the
 	                              unstranded table instead of the Monte-Carlo estimate; reported with perm_k = 0, perm_hits = -1 */
 	int32_t use_qv;            /* USE_QV (--weighted), readmultiplebams.c:24: how remove_ambiguous_bases adjusts Qhighcounts */
+	int32_t blocking_wait;     /* 1: crispgpu_wait sleeps on the result event instead of spinning a core — for front ends
+	                              that keep more contexts waiting than the host has idle cores (adds wake-up latency) */
+	int32_t reserved3;
 } crispgpu_config;
 
 /* One packed read of the per-site pileup snapshot: what calculate_pooled_likelihoods_snp

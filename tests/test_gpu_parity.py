@@ -327,6 +327,10 @@ def test_submit_wait_equals_resident_path():
     t = eng.timing()
     assert t["launches"] >= 3 and t["n_tasks_em"] > 0 and t["em_ms"] > 0
     eng.close()
+    # blocking_wait only changes how the host thread waits
+    sleepy = Engine(_cfg(10, 20, dict(blocking_wait=1)))
+    compare_results(sleepy.run(pin_batch(batch)), a, tol=0.0, label="blocking-wait")
+    sleepy.close()
 
 
 @pytest.mark.parametrize("opts,kw", [
