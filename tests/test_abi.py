@@ -80,3 +80,35 @@ def test_batch_validation():
               indcounts=b.indcounts[:-1], read_off=b.read_off, reads=b.reads)
     with pytest.raises(KeyError):
         EngineConfig(ploidy=np.full(6, 20), options=dict(nonsense=1))
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/crispgpu.h is the boundary a C front end compiles against: it must be valid C99 on its own, and a C
+    program linked against libcrispgpu.so must get the reference's defaults without touching a GPU."""
+    import subprocess
+
+    from crisp_b200 import build as cbuild
+
+    src = tmp_path / "front_end.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "crispgpu.h"
+int main(void)
+{
+	crispgpu_config c;
+	crispgpu_batch b = {0};
+	crispgpu_bin bin = CRISPGPU_BIN(CRISPGPU_READ('I', 2, 1, 0), 7);
+	crispgpu_count cnt = CRISPGPU_COUNT(9, 33);
+	crispgpu_config_defaults(&c);
+	printf("%d %d %d %d %.1f %u %u %u %d\n", crispgpu_abi_version(), c.em_flag, c.max_iter, c.min_reads, c.thresh1,
+	       (unsigned)(bin >> 16), (unsigned)(bin & 0xffff), (unsigned)(cnt >> 27), (int)(b.bins == NULL));
+	return 0;
+}
+''')
+    exe = tmp_path / "front_end"
+    libdir = os.path.dirname(cbuild.LIB)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-L", libdir, "-lcrispgpu", "-Wl,-rpath," + libdir, "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out[:5] == ["2", "1", "20000", "4", "-3.5"]
+    assert out[5:] == ["7", str(ord("I") | (2 << 8) | (1 << 10)), "9", "1"]
