@@ -249,6 +249,19 @@ int occupancy_grid(crispgpu_ctx* ctx, K kernel, int threads, size_t smem, int* g
 	return 0;
 }
 
+// Threads and shared memory of a permutation tail kernel whose per-thread occupancy columns take `occ_bytes` per pool
+// (+ the touched-pool bitmaps of the low-coverage test): the largest power-of-two block that fits.
+void perm_tail_geometry(const crispgpu_ctx* ctx, int occ_bytes, bool bitmaps, int* threads, size_t* smem)
+{
+	const int P = ctx->P;
+	const size_t pfixed = ctx->pm_smem - (size_t)P * ctx->pm_threads * 4;
+	const size_t per_thread = (size_t)P * occ_bytes + (bitmaps ? (size_t)((P + 31) / 32) * 4 : 0);
+	int T = 256;
+	while (T > 32 && pfixed + per_thread * T > ctx->smem_optin - 1024) T >>= 1;
+	*threads = T;
+	*smem = pfixed + per_thread * T;
+}
+
 int launch_evaluate(crispgpu_ctx* ctx, const EngineParams& prm)
 {
 	const int n = ctx->n_sites;
@@ -494,9 +507,6 @@ int run_stage1(crispgpu_ctx* ctx)
 		if (ctx->ploidy[0] > 2) {
 			if (!ctx->pm_grid) {
 				rc = occupancy_grid(ctx, k_permute_stranded, ctx->pm_threads, ctx->pm_smem, &ctx->pm_grid); if (rc) return rc;
-				int g2 = 0;
-				rc = occupancy_grid(ctx, k_permute_stranded_tail, ctx->pm_threads, ctx->pm_smem, &g2); if (rc) return rc;
-				if (g2 < ctx->pm_grid) ctx->pm_grid = g2;
 			}
 			// head: first 1024 permutations of every task; tasks still undecided go to the chunked tail
 			PermTail tail{};
@@ -524,17 +534,26 @@ int run_stage1(crispgpu_ctx* ctx)
 				// the number of tail tasks sizes the chunk records (the one extra host wait of the permutation mode)
 				int32_t* hc2 = static_cast<int32_t*>(ctx->h_counters.p) + 12;
 				CK(cudaMemcpyAsync(hc2, ctx->d_tail_counters.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+				CK(cudaMemcpyAsync(hc2 + 1, static_cast<int32_t*>(ctx->d_counters.p) + 11, 4, cudaMemcpyDeviceToHost, ctx->stream));
 				CK(cudaStreamSynchronize(ctx->stream));
 				const int n_tail = hc2[0];
 				if (n_tail > 0) {
-					const int T = ctx->pm_threads, rem = g.max_iter - kPermHead;
+					// no pool deeper than 255 reads per strand: 16-bit occupancy words, twice the permutations in flight
+					const bool narrow = hc2[1] <= 255;
+					int T = 0, grid = 0;
+					size_t smem = 0;
+					perm_tail_geometry(ctx, narrow ? 2 : 4, false, &T, &smem);
+					rc = narrow ? occupancy_grid(ctx, k_permute_stranded_tail<uint16_t>, T, smem, &grid) : occupancy_grid(ctx, k_permute_stranded_tail<uint32_t>, T, smem, &grid);
+					if (rc) return rc;
+					const int rem = g.max_iter - kPermHead;
 					int chunk = ((rem + 255) / 256 + T - 1) / T * T;
 					if (chunk < 4 * T) chunk = 4 * T;
 					tail.chunk = chunk;
 					tail.nchunks = (rem + chunk - 1) / chunk;
 					rc = ensure_dev(ctx, ctx->d_tail_rec, (size_t)n_tail * tail.nchunks * kPermRec * 4); if (rc) return rc;
 					tail.rec = static_cast<int32_t*>(ctx->d_tail_rec.p);
-					k_permute_stranded_tail<<<ctx->pm_grid, ctx->pm_threads, ctx->pm_smem, ctx->stream>>>(prm, ctx->pm_l10cap, tail);
+					if (narrow) k_permute_stranded_tail<uint16_t><<<grid, T, smem, ctx->stream>>>(prm, ctx->pm_l10cap, tail);
+					else k_permute_stranded_tail<uint32_t><<<grid, T, smem, ctx->stream>>>(prm, ctx->pm_l10cap, tail);
 					CK(launch_check());
 					k_permute_stranded_resolve<<<(n_tail + 127) / 128, 128, 0, ctx->stream>>>(prm, tail);
 					launches += 2;
@@ -548,9 +567,6 @@ int run_stage1(crispgpu_ctx* ctx)
 			}
 			if (!ctx->pm_grid) {
 				rc = occupancy_grid(ctx, k_permute_lowcov, ctx->pm_threads, low_smem, &ctx->pm_grid); if (rc) return rc;
-				int g2 = 0;
-				rc = occupancy_grid(ctx, k_permute_lowcov_tail, ctx->pm_threads, low_smem, &g2); if (rc) return rc;
-				if (g2 < ctx->pm_grid) ctx->pm_grid = g2;
 			}
 			PermTail tail{};
 			rc = ensure_dev(ctx, ctx->d_tail_task, (size_t)n * 5 * 4); if (rc) return rc;
@@ -567,17 +583,26 @@ int run_stage1(crispgpu_ctx* ctx)
 			if (g.max_iter > kPermHead) {
 				int32_t* hc2 = static_cast<int32_t*>(ctx->h_counters.p) + 12;
 				CK(cudaMemcpyAsync(hc2, ctx->d_tail_counters.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+				CK(cudaMemcpyAsync(hc2 + 1, static_cast<int32_t*>(ctx->d_counters.p) + 11, 4, cudaMemcpyDeviceToHost, ctx->stream));
 				CK(cudaStreamSynchronize(ctx->stream));
 				const int n_tail = hc2[0];
 				if (n_tail > 0) {
-					const int T = ctx->pm_threads, rem = g.max_iter - kPermHead;
+					// no pool deeper than 31 reads per stratum: three 5-bit counters in 16-bit words
+					const bool narrow = hc2[1] <= 31;
+					int T = 0, grid = 0;
+					size_t smem = 0;
+					perm_tail_geometry(ctx, narrow ? 2 : 4, true, &T, &smem);
+					rc = narrow ? occupancy_grid(ctx, k_permute_lowcov_tail<uint16_t>, T, smem, &grid) : occupancy_grid(ctx, k_permute_lowcov_tail<uint32_t>, T, smem, &grid);
+					if (rc) return rc;
+					const int rem = g.max_iter - kPermHead;
 					int chunk = ((rem + 255) / 256 + T - 1) / T * T;
 					if (chunk < 4 * T) chunk = 4 * T;
 					tail.chunk = chunk;
 					tail.nchunks = (rem + chunk - 1) / chunk;
 					rc = ensure_dev(ctx, ctx->d_tail_rec, (size_t)n_tail * tail.nchunks * kLowRec * 4); if (rc) return rc;
 					tail.rec = static_cast<int32_t*>(ctx->d_tail_rec.p);
-					k_permute_lowcov_tail<<<ctx->pm_grid, ctx->pm_threads, low_smem, ctx->stream>>>(prm, tail);
+					if (narrow) k_permute_lowcov_tail<uint16_t><<<grid, T, smem, ctx->stream>>>(prm, tail);
+					else k_permute_lowcov_tail<uint32_t><<<grid, T, smem, ctx->stream>>>(prm, tail);
 					CK(launch_check());
 					k_permute_lowcov_resolve<<<(n_tail + 127) / 128, 128, 0, ctx->stream>>>(prm, tail);
 					launches += 2;

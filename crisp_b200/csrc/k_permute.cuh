@@ -78,7 +78,8 @@ struct StrandedView {
 	int32_t* Ntot;
 	int32_t* alt;
 	double* L10;
-	uint32_t* occ;  // [P][T]: low 16 bits forward balls, high 16 reverse balls
+	unsigned char* occ;  // [P][T] of OccT: low half forward balls, high half reverse balls (32-bit words, or 16-bit when no pool
+	                     // holds more than 255 reads per strand: twice the permutations in flight for the same shared memory)
 	int l10cap;
 };
 
@@ -93,7 +94,7 @@ __device__ __forceinline__ StrandedView stranded_view(unsigned char* smem_raw, i
 	v.alt = reinterpret_cast<int32_t*>(smem_raw + off); off += sizeof(int32_t) * 2 * P;
 	off = (off + 15) & ~size_t(15);
 	v.L10 = reinterpret_cast<double*>(smem_raw + off); off += sizeof(double) * l10cap;
-	v.occ = reinterpret_cast<uint32_t*>(smem_raw + off);
+	v.occ = smem_raw + off;
 	v.l10cap = l10cap;
 	return v;
 }
@@ -129,9 +130,11 @@ __device__ inline void stranded_setup(const EngineParams& prm, const StrandedVie
 	if (tid == 0) {
 		uint32_t cf = 0, cr = 0;
 		int of = 0, orr = 0, mx = 0;
+		uint32_t deepest = 0;  // most reads of one strand in one pool: decides the counter width of the tail kernel
 		double clra = 0.0;
 		v.cumf[0] = v.cumr[0] = 0;
 		for (int i = 0; i < P; i++) {
+			deepest = max(deepest, max(v.cumf[i + 1], v.cumr[i + 1]));
 			cf += v.cumf[i + 1]; v.cumf[i + 1] = cf;
 			cr += v.cumr[i + 1]; v.cumr[i + 1] = cr;
 			of += v.alt[i]; orr += v.alt[P + i];
@@ -142,6 +145,7 @@ __device__ inline void stranded_setup(const EngineParams& prm, const StrandedVie
 		v.sh->ones[0] = of; v.sh->ones[1] = orr;
 		v.sh->maxN = mx;
 		v.sh->clra = clra;
+		atomicMax(prm.q.counters + 11, (int)deepest);
 	}
 	__syncthreads();
 	const int maxN = v.sh->maxN;
@@ -151,10 +155,13 @@ __device__ inline void stranded_setup(const EngineParams& prm, const StrandedVie
 
 // One permutation (thread-local): place the forward and reverse balls, accumulate the statistic incrementally
 // (contables.c:312-323) and compare with the observed one.
+template <typename OccT>
 __device__ __forceinline__ int stranded_hit(const EngineParams& prm, const StrandedView& v, int s, int slot, uint32_t k)
 {
+	constexpr int HB = sizeof(OccT) * 4;            // bits per strand counter
+	constexpr uint32_t HM = (1u << HB) - 1u;
 	const int P = prm.c.P, T = blockDim.x;
-	uint32_t* myocc = v.occ + threadIdx.x;
+	OccT* myocc = reinterpret_cast<OccT*>(v.occ) + threadIdx.x;
 	const bool l10_smem = v.sh->maxN + 2 <= v.l10cap;
 	const double* L10 = v.L10;
 	const int32_t* Ntot = v.Ntot;
@@ -163,23 +170,23 @@ __device__ __forceinline__ int stranded_hit(const EngineParams& prm, const Stran
 	Philox rng;
 	rng.init(prm.c.rng_seed, prm.b.tid[s], prm.b.pos[s], slot, k, 0);
 	place_balls(rng, v.cumf, P, (uint32_t)v.sh->tot[0], v.sh->ones[0],
-		[&](int i) { return myocc[(size_t)i * T] & 0xffffu; },
+		[&](int i) { return (uint32_t)myocc[(size_t)i * T] & HM; },
 		[&](int i) {
 			const uint32_t w = myocc[(size_t)i * T];
-			const int cb = (int)(w & 0xffffu) + (int)(w >> 16);
+			const int cb = (int)(w & HM) + (int)(w >> HB);
 			const int N = Ntot[i];
 			stat += l10_smem ? L10[N - cb] - L10[cb + 1] : log10((double)(N - cb)) - log10((double)(cb + 1));
-			myocc[(size_t)i * T] = w + 1u;
+			myocc[(size_t)i * T] = (OccT)(w + 1u);
 		});
 	rng.init(prm.c.rng_seed, prm.b.tid[s], prm.b.pos[s], slot, k, 1);
 	place_balls(rng, v.cumr, P, (uint32_t)v.sh->tot[1], v.sh->ones[1],
-		[&](int i) { return myocc[(size_t)i * T] >> 16; },
+		[&](int i) { return (uint32_t)myocc[(size_t)i * T] >> HB; },
 		[&](int i) {
 			const uint32_t w = myocc[(size_t)i * T];
-			const int cb = (int)(w & 0xffffu) + (int)(w >> 16);
+			const int cb = (int)(w & HM) + (int)(w >> HB);
 			const int N = Ntot[i];
 			stat += l10_smem ? L10[N - cb] - L10[cb + 1] : log10((double)(N - cb)) - log10((double)(cb + 1));
-			myocc[(size_t)i * T] = w + 0x10000u;
+			myocc[(size_t)i * T] = (OccT)(w + (1u << HB));
 		});
 	return stat <= v.sh->clra + kCtEps ? 1 : 0;
 }
@@ -229,7 +236,7 @@ __global__ void __launch_bounds__(256, 4) k_permute_stranded(EngineParams prm, i
 		int stop_k = 0, stop_hits = 0, hits_before = 0;
 		for (int base = 0; base < head; base += T) {
 			const int k = base + tid + 1;
-			const int hit = k <= head ? stranded_hit(prm, v, s, slot, (uint32_t)k) : 0;
+			const int hit = k <= head ? stranded_hit<uint32_t>(prm, v, s, slot, (uint32_t)k) : 0;
 			int total;
 			const int H = hits_before + block_prefix(hit, sh->warp_hits, total);
 			const bool stop = k <= head && (H >= 10 || (k <= 1000 && H >= 5));
@@ -264,6 +271,7 @@ __global__ void __launch_bounds__(256, 4) k_permute_stranded(EngineParams prm, i
 // Tail: work items = (chunk, task), chunk-major so that every earlier chunk of a task has started before a later one.
 // A chunk records its hit count and the indices of its first ten hits; it is skipped when ten hits are already known
 // (they all lie in earlier chunks, so the reference's loop would have broken before this chunk).
+template <typename OccT>
 __global__ void __launch_bounds__(256, 4) k_permute_stranded_tail(EngineParams prm, int l10cap, PermTail tail)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -301,7 +309,7 @@ __global__ void __launch_bounds__(256, 4) k_permute_stranded_tail(EngineParams p
 		int found = 0;
 		for (int base = kbeg; base < kend; base += T) {
 			const int k = base + tid + 1;
-			const int hit = k <= kend ? stranded_hit(prm, v, s, slot, (uint32_t)k) : 0;
+			const int hit = k <= kend ? stranded_hit<OccT>(prm, v, s, slot, (uint32_t)k) : 0;
 			int total;
 			const int idx = found + block_prefix(hit, sh->warp_hits, total);  // 1-based rank of this hit within the chunk
 			if (hit && idx <= 10) firsts[idx - 1] = k;
@@ -356,7 +364,8 @@ struct LowcovView {
 	int32_t* alt;     // [3][P]
 	double* terms;    // [P]
 	uint32_t* touched;  // [ceil(P/32)][T] bitmap of pools holding balls in the current permutation
-	uint32_t* occ;      // [P][T]: 3 x 10-bit ball counts (f, r, b); all zero between permutations
+	unsigned char* occ; // [P][T] of OccT: three ball counts (f, r, b), 10 bits each in 32-bit words or 5 bits each in 16-bit words
+	                    // (when no pool holds more than 31 reads per stratum); all zero between permutations
 	int words;
 };
 
@@ -372,12 +381,12 @@ __device__ __forceinline__ LowcovView lowcov_view(unsigned char* smem_raw, int P
 	v.terms = reinterpret_cast<double*>(smem_raw + off); off += sizeof(double) * P;
 	v.words = (P + 31) >> 5;
 	v.touched = reinterpret_cast<uint32_t*>(smem_raw + off); off += sizeof(uint32_t) * v.words * T;
-	v.occ = reinterpret_cast<uint32_t*>(smem_raw + off);
+	v.occ = smem_raw + off;
 	return v;
 }
 
 // Block-wide set-up; returns false (after writing the result) when the table has fewer than two alt reads (:42).
-__device__ inline bool lowcov_setup(const EngineParams& prm, const LowcovView& v, int o)
+__device__ inline bool lowcov_setup(const EngineParams& prm, const LowcovView& v, int o, int occ_bytes)
 {
 	const DevBatch& b = prm.b;
 	const DevCfg& c = prm.c;
@@ -401,19 +410,21 @@ __device__ inline bool lowcov_setup(const EngineParams& prm, const LowcovView& v
 		const int R = v.alt[i] + v.alt[P + i] + v.alt[2 * P + i];
 		v.terms[i] = R > 0 ? ncr_lookup(c.ncr_tab, n0 + n1 + n2, R) : 0.0;
 	}
-	for (int k = tid; k < P * T; k += T) v.occ[k] = 0;
+	for (int k = tid; k < (int)((size_t)P * T * occ_bytes / 4); k += T) reinterpret_cast<uint32_t*>(v.occ)[k] = 0;
 	for (int k = tid; k < v.words * T; k += T) v.touched[k] = 0;
 	__syncthreads();
 	if (tid == 0) {
 		double clra = 0.0;
+		uint32_t deepest = 0;  // most reads of one stratum in one pool: decides the counter width of the tail kernel
 		for (int k = 0; k < 3; k++) {
 			uint32_t cc = 0; int on = 0;
 			v.cum[k * (P + 1)] = 0;
-			for (int i = 0; i < P; i++) { cc += v.cum[k * (P + 1) + i + 1]; v.cum[k * (P + 1) + i + 1] = cc; on += v.alt[k * P + i]; }
+			for (int i = 0; i < P; i++) { deepest = max(deepest, v.cum[k * (P + 1) + i + 1]); cc += v.cum[k * (P + 1) + i + 1]; v.cum[k * (P + 1) + i + 1] = cc; on += v.alt[k * P + i]; }
 			v.sh->tot[k] = (int)cc; v.sh->ones[k] = on;
 		}
 		for (int i = 0; i < P; i++) if (v.alt[i] + v.alt[P + i] + v.alt[2 * P + i] > 0) clra += v.terms[i];
 		v.sh->clra = clra;
+		atomicMax(prm.q.counters + 11, (int)deepest);
 	}
 	__syncthreads();
 	if (v.sh->ones[0] + v.sh->ones[1] + v.sh->ones[2] < 2) {
@@ -425,19 +436,22 @@ __device__ inline bool lowcov_setup(const EngineParams& prm, const LowcovView& v
 
 // One permutation: bit 0 = statistic <= observed, bit 1 = statistic >= observed.  Work is proportional to the number of
 // balls: pools that received balls are tracked in a bitmap, walked in ascending pool order and cleared on the way.
+template <typename OccT>
 __device__ __forceinline__ int lowcov_hit(const EngineParams& prm, const LowcovView& v, int s, int slot, uint32_t k)
 {
+	constexpr int FB = sizeof(OccT) == 4 ? 10 : 5;  // bits per stratum counter
+	constexpr uint32_t FM = (1u << FB) - 1u;
 	const int P = prm.c.P, T = blockDim.x;
-	uint32_t* myocc = v.occ + threadIdx.x;
+	OccT* myocc = reinterpret_cast<OccT*>(v.occ) + threadIdx.x;
 	uint32_t* mybits = v.touched + threadIdx.x;
 	for (int st = 0; st < 3; st++) {
 		Philox rng;
 		rng.init(prm.c.rng_seed, prm.b.tid[s], prm.b.pos[s], slot, k, (uint32_t)st);
-		const int sft = 10 * st;
+		const int sft = FB * st;
 		place_balls(rng, v.cum + st * (P + 1), P, (uint32_t)v.sh->tot[st], v.sh->ones[st],
-			[&](int i) { return (myocc[(size_t)i * T] >> sft) & 0x3ffu; },
+			[&](int i) { return ((uint32_t)myocc[(size_t)i * T] >> sft) & FM; },
 			[&](int i) {
-				myocc[(size_t)i * T] += 1u << sft;
+				myocc[(size_t)i * T] = (OccT)(myocc[(size_t)i * T] + (1u << sft));
 				mybits[(size_t)(i >> 5) * T] |= 1u << (i & 31);
 			});
 	}
@@ -451,7 +465,7 @@ __device__ __forceinline__ int lowcov_hit(const EngineParams& prm, const LowcovV
 			bits &= bits - 1;
 			const uint32_t x = myocc[(size_t)i * T];
 			myocc[(size_t)i * T] = 0;
-			const int r = (int)(x & 0x3ffu) + (int)((x >> 10) & 0x3ffu) + (int)((x >> 20) & 0x3ffu);
+			const int r = (int)(x & FM) + (int)((x >> FB) & FM) + (int)((x >> (2 * FB)) & FM);
 			stat += ncr_lookup(prm.c.ncr_tab, v.Ntot[i], r);
 		}
 	}
@@ -484,13 +498,13 @@ __global__ void k_permute_lowcov(EngineParams prm, PermTail tail)
 		const int task = sh->task;
 		if (task >= prm.q.counters[0]) break;
 		const int o = prm.q.perm_tasks[task], s = o / kSlots, slot = o - s * kSlots;
-		if (!lowcov_setup(prm, v, o)) continue;
+		if (!lowcov_setup(prm, v, o, 4)) continue;
 		const int maxiter = c.max_iter;
 		const int head = maxiter < kPermHead ? maxiter : kPermHead;
 		int lo_before = 0, hi_before = 0, stop_k = 0, stop_lo = 0, stop_hi = 0;
 		for (int base = 0; base < head; base += T) {
 			const int k = base + tid + 1;
-			const int f = k <= head ? lowcov_hit(prm, v, s, slot, (uint32_t)k) : 0;
+			const int f = k <= head ? lowcov_hit<uint32_t>(prm, v, s, slot, (uint32_t)k) : 0;
 			int tl, th;
 			const int Hlo = lo_before + block_prefix(f & 1, sh->warp_hits, tl);
 			const int Hhi = hi_before + block_prefix((f >> 1) & 1, sh->warp_hits2, th);
@@ -526,6 +540,7 @@ __global__ void k_permute_lowcov(EngineParams prm, PermTail tail)
 }
 
 // Tail: (chunk, task) items chunk-major; a chunk is skipped once both counters are known to have reached ten.
+template <typename OccT>
 __global__ void k_permute_lowcov_tail(EngineParams prm, PermTail tail)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -559,11 +574,11 @@ __global__ void k_permute_lowcov_tail(EngineParams prm, PermTail tail)
 			continue;
 		}
 		const int o = tail.task[h], s = o / kSlots, slot = o - s * kSlots;
-		lowcov_setup(prm, v, o);  // cannot fail: the head already accepted the table
+		lowcov_setup(prm, v, o, (int)sizeof(OccT));  // cannot fail: the head already accepted the table
 		int flo = 0, fhi = 0;
 		for (int base = kbeg; base < kend; base += T) {
 			const int k = base + tid + 1;
-			const int f = k <= kend ? lowcov_hit(prm, v, s, slot, (uint32_t)k) : 0;
+			const int f = k <= kend ? lowcov_hit<OccT>(prm, v, s, slot, (uint32_t)k) : 0;
 			int tl, th;
 			const int ilo = flo + block_prefix(f & 1, sh->warp_hits, tl);
 			const int ihi = fhi + block_prefix((f >> 1) & 1, sh->warp_hits2, th);

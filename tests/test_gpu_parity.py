@@ -42,6 +42,8 @@ SCENARIOS = [
     ("perm_c1", 150, 10, 20, 100, dict(chisq_permutation=1, max_iter=20000), dict(variant_frac=0.4, bidir_frac=0.05, with_qhigh=True)),
     ("perm_rare_c4", 60, 50, 48, 200, dict(chisq_permutation=1, max_iter=30000), dict(variant_frac=0.7, rare=True)),
     ("perm_c5", 40, 500, 10, 10, dict(chisq_permutation=1, max_iter=2000), dict(variant_frac=0.5)),
+    ("perm_deep_wide", 60, 6, 20, 700, dict(chisq_permutation=1, max_iter=3000), dict(variant_frac=0.5)),          # > 255 reads per strand: 32-bit occupancy words in the tail
+    ("lowcov_deep_wide", 100, 20, 2, 90, dict(chisq_permutation=1, max_iter=3000), dict(variant_frac=0.5, bidir_frac=0.1)),  # > 31 reads per stratum
     ("lowcovFET", 300, 40, 2, 10, dict(chisq_permutation=1, max_iter=2000), dict(variant_frac=0.5, bidir_frac=0.1)),
     ("diploid", 300, 40, 2, 10, {}, dict(variant_frac=0.5)),
     ("em0", 300, 10, 20, 100, dict(em_flag=0), dict(variant_frac=0.4, indel_frac=0.2, with_stats=True, with_qhigh=True)),
