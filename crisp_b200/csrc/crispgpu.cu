@@ -65,8 +65,10 @@ struct crispgpu_ctx {
 	size_t n_bins = 0;
 	bool resident = false;
 	// device results + pinned mirrors
-	DevBuf d_o[32], d_ac, d_qv;
+	DevBuf d_o[32], d_ac, d_qv;     // d_o / h_o: views into the two result arenas (one device-to-host copy per batch)
 	DevBuf h_o[32], h_ac, h_qv;
+	DevBuf d_out_arena, h_out_arena;
+	size_t out_bytes = 0;
 	DevOut dout{};
 	// queues
 	DevBuf d_perm_tasks, d_call_tasks, d_call_tasks2, d_counters, h_counters, d_gws;
@@ -390,14 +392,21 @@ int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b, bool lazy)
 
 int ensure_outputs(crispgpu_ctx* ctx, int n)
 {
+	// all per-site / per-slot result arrays live back to back (256-byte aligned) in one device arena mirrored by one pinned
+	// host arena, so that a batch's results come home in a single copy
+	size_t off[kNumOut + 1];
+	off[0] = 0;
+	for (int f = 0; f < kNumOut; f++) off[f + 1] = off[f] + (((size_t)n * kOutFields[f].width * kOutFields[f].elem + 255) & ~size_t(255));
+	int rc = ensure_dev(ctx, ctx->d_out_arena, off[kNumOut]);
+	if (rc) return rc;
+	rc = ensure_host(ctx, ctx->h_out_arena, off[kNumOut]);
+	if (rc) return rc;
 	for (int f = 0; f < kNumOut; f++) {
-		size_t bytes = (size_t)n * kOutFields[f].width * kOutFields[f].elem;
-		int rc = ensure_dev(ctx, ctx->d_o[f], bytes);
-		if (rc) return rc;
-		rc = ensure_host(ctx, ctx->h_o[f], bytes);
-		if (rc) return rc;
+		ctx->d_o[f].p = static_cast<unsigned char*>(ctx->d_out_arena.p) + off[f];
+		ctx->h_o[f].p = static_cast<unsigned char*>(ctx->h_out_arena.p) + off[f];
 	}
-	int rc = ensure_dev(ctx, ctx->d_perm_tasks, (size_t)n * 5 * 4);
+	ctx->out_bytes = off[kNumOut];
+	rc = ensure_dev(ctx, ctx->d_perm_tasks, (size_t)n * 5 * 4);
 	if (rc) return rc;
 	rc = ensure_dev(ctx, ctx->d_call_tasks, (size_t)n * 5 * 4);
 	if (rc) return rc;
@@ -750,11 +759,9 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 	CK(cudaEventRecord(ctx->ev[EV_CALL], ctx->stream));
 	int64_t d2h = 0;
 	if (fetch) {
-		for (int f = 0; f < kNumOut; f++) {
-			size_t bytes = (size_t)n * kOutFields[f].width * kOutFields[f].elem;
-			if (!bytes) continue;
-			CK(cudaMemcpyAsync(ctx->h_o[f].p, ctx->d_o[f].p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-			d2h += (int64_t)bytes;
+		if (n > 0) {
+			CK(cudaMemcpyAsync(ctx->h_out_arena.p, ctx->d_out_arena.p, ctx->out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+			d2h += (int64_t)ctx->out_bytes;
 		}
 		if (rows > 0) {
 			rc = ensure_host(ctx, ctx->h_ac, (size_t)rows * ctx->P * 4); if (rc) return rc;
@@ -1000,8 +1007,7 @@ void crispgpu_destroy(crispgpu_ctx* ctx)
 	fd(ctx->d_exact_row); fd(ctx->d_exact_cl); fd(ctx->d_exact_done); fd(ctx->d_need_reads);
 	for (auto& b : ctx->d_scr) fd(b);
 	for (auto& b : ctx->d_b) fd(b);
-	for (auto& b : ctx->d_o) fd(b);
-	for (auto& b : ctx->h_o) fh(b);
+	fd(ctx->d_out_arena); fh(ctx->h_out_arena);
 	fd(ctx->d_ac); fd(ctx->d_qv); fh(ctx->h_ac); fh(ctx->h_qv);
 	fd(ctx->d_tail_task); fd(ctx->d_tail_head); fd(ctx->d_tail_total); fd(ctx->d_tail_rec); fd(ctx->d_tail_counters);
 	fd(ctx->d_perm_tasks); fd(ctx->d_call_tasks); fd(ctx->d_call_tasks2); fd(ctx->d_counters); fh(ctx->h_counters); fd(ctx->d_gws);
