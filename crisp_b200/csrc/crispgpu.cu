@@ -68,6 +68,8 @@ struct crispgpu_ctx {
 	DevBuf d_o[32], d_ac, d_qv;     // d_o / h_o: views into the two result arenas (one device-to-host copy per batch)
 	DevBuf h_o[32], h_ac, h_qv;
 	DevBuf d_out_arena, h_out_arena;
+	DevBuf d_rows, h_rows;          // AC/QV rows of the batch: qv[rows][P] doubles followed by ac[rows][P] ints
+	bool timing_pending = false;    // the stage durations of the last batch have not been read from the events yet
 	size_t out_bytes = 0;
 	DevOut dout{};
 	// queues
@@ -268,10 +270,11 @@ int launch_evaluate(crispgpu_ctx* ctx, const EngineParams& prm)
 {
 	const int n = ctx->n_sites;
 	auto go = [&](auto kernel, int warps) -> int {
-		int grid = 0;
-		int rc = occupancy_grid(ctx, kernel, warps * 32, ctx->ev_smem, &grid);
-		if (rc) return rc;
-		grid *= 4;  // several waves of short CTAs: sites differ in the number of tested slots
+		if (!ctx->ev_grid) {  // one instantiation per context (the mode is part of the configuration): query once
+			int rc = occupancy_grid(ctx, kernel, warps * 32, ctx->ev_smem, &ctx->ev_grid);
+			if (rc) return rc;
+		}
+		int grid = ctx->ev_grid * 4;  // several waves of short CTAs: sites differ in the number of tested slots
 		int need = (n + warps - 1) / warps;
 		if (grid > need) grid = need;
 		if (grid < 1) grid = 1;
@@ -692,8 +695,9 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 	}
 	const int rows = g.em_flag >= 1 ? ctx->n_call : 0;
 	if (rows > 0) {
-		rc = ensure_dev(ctx, ctx->d_ac, (size_t)rows * ctx->P * 4); if (rc) return rc;
-		rc = ensure_dev(ctx, ctx->d_qv, (size_t)rows * ctx->P * 8); if (rc) return rc;
+		rc = ensure_dev(ctx, ctx->d_rows, (size_t)rows * ctx->P * 12); if (rc) return rc;
+		ctx->d_qv.p = ctx->d_rows.p;
+		ctx->d_ac.p = static_cast<unsigned char*>(ctx->d_rows.p) + (size_t)rows * ctx->P * 8;
 		prm = make_params(ctx);
 	}
 	if (ctx->n_call > 0) {
@@ -764,10 +768,10 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 			d2h += (int64_t)ctx->out_bytes;
 		}
 		if (rows > 0) {
-			rc = ensure_host(ctx, ctx->h_ac, (size_t)rows * ctx->P * 4); if (rc) return rc;
-			rc = ensure_host(ctx, ctx->h_qv, (size_t)rows * ctx->P * 8); if (rc) return rc;
-			CK(cudaMemcpyAsync(ctx->h_ac.p, ctx->d_ac.p, (size_t)rows * ctx->P * 4, cudaMemcpyDeviceToHost, ctx->stream));
-			CK(cudaMemcpyAsync(ctx->h_qv.p, ctx->d_qv.p, (size_t)rows * ctx->P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+			rc = ensure_host(ctx, ctx->h_rows, (size_t)rows * ctx->P * 12); if (rc) return rc;
+			ctx->h_qv.p = ctx->h_rows.p;
+			ctx->h_ac.p = static_cast<unsigned char*>(ctx->h_rows.p) + (size_t)rows * ctx->P * 8;
+			CK(cudaMemcpyAsync(ctx->h_rows.p, ctx->d_rows.p, (size_t)rows * ctx->P * 12, cudaMemcpyDeviceToHost, ctx->stream));
 			d2h += (int64_t)rows * ctx->P * 12;
 		}
 	}
@@ -1008,7 +1012,7 @@ void crispgpu_destroy(crispgpu_ctx* ctx)
 	for (auto& b : ctx->d_scr) fd(b);
 	for (auto& b : ctx->d_b) fd(b);
 	fd(ctx->d_out_arena); fh(ctx->h_out_arena);
-	fd(ctx->d_ac); fd(ctx->d_qv); fh(ctx->h_ac); fh(ctx->h_qv);
+	fd(ctx->d_rows); fh(ctx->h_rows);
 	fd(ctx->d_tail_task); fd(ctx->d_tail_head); fd(ctx->d_tail_total); fd(ctx->d_tail_rec); fd(ctx->d_tail_counters);
 	fd(ctx->d_perm_tasks); fd(ctx->d_call_tasks); fd(ctx->d_call_tasks2); fd(ctx->d_counters); fh(ctx->h_counters); fd(ctx->d_gws);
 	for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -1030,6 +1034,7 @@ int crispgpu_submit(crispgpu_ctx* ctx, const crispgpu_batch* batch, int64_t* tic
 		return CRISPGPU_ERR_TICKET;
 	}
 	CK(cudaSetDevice(ctx->device));
+	ctx->timing_pending = false;  // the stage events are about to be reused: read crispgpu_get_timing between wait and the next submit
 	CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
 	int rc = copy_batch(ctx, batch, true);
 	if (rc) return rc;
@@ -1065,8 +1070,7 @@ int crispgpu_wait(crispgpu_ctx* ctx, int64_t ticket, crispgpu_results* out)
 	ctx->advanced = false;
 	if (rc) return rc;
 	CK(cudaEventSynchronize(ctx->ev_done ? ctx->ev_done : ctx->ev[EV_D2H]));
-	rc = finish_timing(ctx);
-	if (rc) return rc;
+	ctx->timing_pending = true;
 	fill_results(ctx, out);
 	return CRISPGPU_OK;
 }
@@ -1131,8 +1135,7 @@ int crispgpu_run_resident(crispgpu_ctx* ctx, int fetch_results, crispgpu_results
 	rc = run_stage2(ctx, fetch_results != 0);
 	if (rc) return rc;
 	CK(cudaEventSynchronize(ctx->ev[EV_D2H]));
-	rc = finish_timing(ctx);
-	if (rc) return rc;
+	ctx->timing_pending = true;
 	if (fetch_results) fill_results(ctx, out);
 	return CRISPGPU_OK;
 }
@@ -1150,6 +1153,12 @@ extern "C" int crispgpu_debug_timeline(crispgpu_ctx* ctx, crispgpu_ctx* epoch, f
 int crispgpu_get_timing(crispgpu_ctx* ctx, crispgpu_timing* out)
 {
 	if (!ctx || !out) return CRISPGPU_ERR_ARG;
+	if (ctx->timing_pending) {  // the event queries are kept off the submit/wait path
+		CK(cudaSetDevice(ctx->device));
+		int rc = finish_timing(ctx);
+		if (rc) return rc;
+		ctx->timing_pending = false;
+	}
 	*out = ctx->timing;
 	return CRISPGPU_OK;
 }

@@ -222,7 +222,8 @@ typedef struct crispgpu_results {
 	const double* qv;           /* crispvar[].QV[i] */
 } crispgpu_results;
 
-/* Device timings of the last completed batch, CUDA events on the engine's stream (ms). */
+/* Device timings of the last completed batch, CUDA events on the engine's stream (ms).  The events are read when
+ * crispgpu_get_timing is called: call it after crispgpu_wait / crispgpu_run_resident and before the next submit. */
 typedef struct crispgpu_timing {
 	float h2d_ms;
 	float evaluate_ms;   /* evaluate_variant + contingency-table p-values (asymptotic) */
