@@ -165,6 +165,7 @@ def main():
     ap.add_argument("--sites", type=int, default=8192, help="candidate sites per GPU per step")
     ap.add_argument("--cpu-sites-per-core", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-arena", action="store_true", help="end-to-end leg: one pinned allocation per array instead of one arena for the batch")
     ap.add_argument("--contexts", type=int, default=0,
                     help="engine contexts per GPU in the end-to-end leg, one host thread each (batches in flight); 0 = 6, fewer when the ranks of a box would oversubscribe its cores")
     ap.add_argument("--format", "--e2e-format", dest="e2e_format", default="bins", choices=["bins", "reads"],
@@ -224,7 +225,7 @@ def main():
     # region shard of this rank: its own contiguous run of candidate sites (tid = rank)
     batch = make_batch(wl, args.sites, seed=1 + rank, tid=rank)
     shipped = batch.compact() if args.e2e_format == "bins" else batch   # the form both legs consume
-    pinned = pin_batch(shipped)
+    pinned = pin_batch(shipped, arena=not args.no_arena)
     stream = torch.cuda.Stream(device=local)
     eng = Engine(cfg, device=local, stream=stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}") if "flushed" in config["l2_policy"] else None

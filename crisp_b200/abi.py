@@ -90,6 +90,8 @@ class CBatch(C.Structure):
         ("bins", C.c_void_p),
         ("ic_off", C.c_void_p),
         ("ic_sparse", C.c_void_p),
+        ("arena_base", C.c_void_p),
+        ("arena_bytes", C.c_uint64),
     ]
 
 
@@ -324,6 +326,7 @@ class Batch:
             return self
         out = Batch.__new__(Batch)
         out.__dict__.update(self.__dict__)
+        out.__dict__.pop("_arena", None)   # the new arrays live outside a pinned arena the original may declare
         out.bin_off, out.bins = bins_from_reads(self.read_off, self.reads)
         out.reads = None
         out.read_off = None   # indexes the read stream only
@@ -337,6 +340,7 @@ class Batch:
             out = Batch.__new__(Batch)
             out.__dict__.update(self.__dict__)
         if out.ic_off is None:
+            out.__dict__.pop("_arena", None)
             out.ic_off, out.ic_sparse = sparse_counts_from_dense(self.indcounts)
             out.indcounts = None
         return out
@@ -355,6 +359,9 @@ class Batch:
         for name, _, _ in _BATCH_ARRAYS:
             a = getattr(self, name)
             setattr(b, name, a.ctypes.data if a is not None else None)
+        arena = getattr(self, "_arena", None)   # (address, bytes) of the one pinned allocation holding every array (pin_batch)
+        if arena is not None:
+            b.arena_base, b.arena_bytes = arena
         b._keep = self
         return b
 

@@ -68,6 +68,7 @@ struct crispgpu_ctx {
 	DevBuf d_o[32], d_ac, d_qv;     // d_o / h_o: views into the two result arenas (one device-to-host copy per batch)
 	DevBuf h_o[32], h_ac, h_qv;
 	DevBuf d_out_arena, h_out_arena;
+	DevBuf d_arena;                 // device image of a batch the front end packed into one pinned arena
 	DevBuf d_rows, h_rows;          // AC/QV rows of the batch: qv[rows][P] doubles followed by ac[rows][P] ints
 	bool timing_pending = false;    // the stage durations of the last batch have not been read from the events yet
 	size_t out_bytes = 0;
@@ -348,7 +349,29 @@ int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b, bool lazy)
 	ctx->binned = a[19].host != nullptr;
 	ctx->device_sort = false;
 	ctx->sparse_ic = a[21].host != nullptr;
+	// one-copy path: every array lies in the arena the batch declares
+	const unsigned char* abase = static_cast<const unsigned char*>(b->arena_base);
+	const bool arena = abase != nullptr && b->arena_bytes > 0;
+	if (arena) {
+		if (reinterpret_cast<uintptr_t>(abase) & 255) { snprintf(ctx->err, sizeof ctx->err, "batch arena is not 256-byte aligned"); return CRISPGPU_ERR_ARG; }
+		for (int i = 0; i < k; i++) {
+			if (a[i].bytes == 0 || a[i].host == nullptr) continue;
+			const unsigned char* p0 = static_cast<const unsigned char*>(a[i].host);
+			if (p0 < abase || p0 + a[i].bytes > abase + b->arena_bytes || (reinterpret_cast<uintptr_t>(p0) & 15)) {
+				snprintf(ctx->err, sizeof ctx->err, "batch array %d lies outside the declared arena (or is not 16-byte aligned)", i);
+				return CRISPGPU_ERR_ARG;
+			}
+		}
+		int rc = ensure_dev(ctx, ctx->d_arena, b->arena_bytes);
+		if (rc) return rc;
+		CK(cudaMemcpyAsync(ctx->d_arena.p, abase, b->arena_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		bytes += (int64_t)b->arena_bytes;
+	}
 	for (int i = 0; i < k; i++) {
+		if (arena && a[i].bytes && a[i].host != nullptr) {
+			dptr[i] = static_cast<unsigned char*>(ctx->d_arena.p) + (static_cast<const unsigned char*>(a[i].host) - abase);
+			continue;
+		}
 		if ((i == 3 || i == 4) && a[i].host == nullptr && a[i].bytes) {  // no maxvec from the host: k_candidates sorts the alleles
 			int rc = ensure_dev(ctx, ctx->d_b[i], a[i].bytes);
 			if (rc) return rc;
@@ -1012,7 +1035,7 @@ void crispgpu_destroy(crispgpu_ctx* ctx)
 	for (auto& b : ctx->d_scr) fd(b);
 	for (auto& b : ctx->d_b) fd(b);
 	fd(ctx->d_out_arena); fh(ctx->h_out_arena);
-	fd(ctx->d_rows); fh(ctx->h_rows);
+	fd(ctx->d_rows); fh(ctx->h_rows); fd(ctx->d_arena);
 	fd(ctx->d_tail_task); fd(ctx->d_tail_head); fd(ctx->d_tail_total); fd(ctx->d_tail_rec); fd(ctx->d_tail_counters);
 	fd(ctx->d_perm_tasks); fd(ctx->d_call_tasks); fd(ctx->d_call_tasks2); fd(ctx->d_counters); fh(ctx->h_counters); fd(ctx->d_gws);
 	for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);

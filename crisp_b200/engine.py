@@ -92,23 +92,33 @@ def pinned_like(a: np.ndarray):
     return out, block
 
 
-def pin_batch(batch: Batch) -> Batch:
-    """A copy of the batch whose arrays live in pinned memory, so crispgpu_submit's copies are asynchronous."""
+def pin_batch(batch: Batch, arena: bool = True) -> Batch:
+    """A copy of the batch in pinned memory, so that crispgpu_submit's copies are asynchronous.  With `arena` (default) all
+    arrays are packed 256-byte aligned into ONE pinned allocation that the batch declares (`arena_base`/`arena_bytes`):
+    the engine then moves the batch with a single copy."""
     from .abi import _BATCH_ARRAYS
 
     out = Batch.__new__(Batch)
-    out.n_pools = batch.n_pools
+    out.__dict__.update({k: v for k, v in batch.__dict__.items() if not k.startswith("_")})
     out._pinned_blocks = []
-    for name, _, _ in _BATCH_ARRAYS:
-        a = getattr(batch, name)
-        if a is None:
-            setattr(out, name, None)
-            continue
-        arr, block = pinned_like(a)
+    present = [(name, getattr(batch, name)) for name, _, _ in _BATCH_ARRAYS if getattr(batch, name) is not None]
+    if arena:
+        offs, total = [], 0
+        for _, a in present:
+            offs.append(total)
+            total += (a.nbytes + 255) & ~255
+        block = _PinnedBlock(total)
         out._pinned_blocks.append(block)
-        setattr(out, name, arr)
-    out.n_sites = batch.n_sites
-    out.n_amb = batch.n_amb
+        for (name, a), off in zip(present, offs):
+            view = np.frombuffer(block.buf, dtype=a.dtype, count=a.size, offset=off).reshape(a.shape)
+            view[...] = a
+            setattr(out, name, view)
+        out._arena = (block.ptr, total)
+    else:
+        for name, a in present:
+            arr, block = pinned_like(a)
+            out._pinned_blocks.append(block)
+            setattr(out, name, arr)
     return out
 
 

@@ -81,6 +81,56 @@ void crisp_shim_batch_view(const crisp_shim_batch* sb, crispgpu_batch* b)
 	b->tstats = sb->want_stats ? sb->tstats : NULL;
 }
 
+/* the arrays of a view in declaration order: address of the pointer field and its size in bytes */
+typedef struct { const void** field; size_t bytes; } shim_span;
+
+static int shim_spans(const crisp_shim_batch* sb, crispgpu_batch* v, shim_span* sp)
+{
+	const size_t n = (size_t)sb->n_sites, P = (size_t)sb->n_pools;
+	int k = 0;
+#define SPAN(name, nbytes) do { sp[k].field = (const void**)&v->name; sp[k].bytes = v->name ? (size_t)(nbytes) : 0; k++; } while (0)
+	SPAN(tid, n * 4); SPAN(pos, n * 4); SPAN(refbase, n); SPAN(maxvec_al, n * 8); SPAN(maxvec_ct, n * 32); SPAN(counts, n * 96);
+	SPAN(indcounts, n * P * 96); SPAN(indel_len, n * 16); SPAN(hplen, n * 16);
+	SPAN(read_off, (n * P + 1) * 4); SPAN(reads, sb->n_reads * sizeof(crispgpu_read));
+	SPAN(alt_off, (n * 5 + 1) * 4); SPAN(alt_reads, sb->n_alt * sizeof(crispgpu_altread));
+	SPAN(amb_idx, n * 20); SPAN(amb_dec, (size_t)sb->n_amb * P * 16); SPAN(amb_ep, (size_t)sb->n_amb * P * 16);
+	SPAN(qhigh, n * P * 128); SPAN(stats, n * P * 128); SPAN(tstats, n * 128);
+	SPAN(bin_off, (n * P + 1) * 4); SPAN(bins, sb->n_bins * sizeof(crispgpu_bin));
+	SPAN(ic_off, (n * P + 1) * 4); SPAN(ic_sparse, sb->n_ic * sizeof(crispgpu_count));
+#undef SPAN
+	return k;
+}
+
+size_t crisp_shim_batch_packed_bytes(const crisp_shim_batch* sb)
+{
+	crispgpu_batch v;
+	shim_span sp[32];
+	crisp_shim_batch_view(sb, &v);
+	const int k = shim_spans(sb, &v, sp);
+	size_t total = 0;
+	for (int i = 0; i < k; i++) total += (sp[i].bytes + 255) & ~(size_t)255;
+	return total;
+}
+
+int crisp_shim_batch_pack(const crisp_shim_batch* sb, void* arena, size_t arena_cap, crispgpu_batch* out)
+{
+	shim_span sp[32];
+	crisp_shim_batch_view(sb, out);
+	const int k = shim_spans(sb, out, sp);
+	size_t off = 0;
+	for (int i = 0; i < k; i++) {
+		if (sp[i].bytes == 0) { *sp[i].field = NULL; continue; }  /* absent or empty */
+		const size_t need = (sp[i].bytes + 255) & ~(size_t)255;
+		if (off + need > arena_cap) return -1;
+		memcpy((char*)arena + off, *sp[i].field, sp[i].bytes);
+		*sp[i].field = (char*)arena + off;
+		off += need;
+	}
+	out->arena_base = arena;
+	out->arena_bytes = off;
+	return 0;
+}
+
 static void reserve_site(crisp_shim_batch* sb)
 {
 	const size_t n = (size_t)sb->n_sites + 1, P = sb->n_pools;

@@ -47,6 +47,13 @@ void crisp_shim_batch_clear(crisp_shim_batch* sb);
 void crisp_shim_batch_free(crisp_shim_batch* sb);
 /* view of the accumulated sites as the ABI batch (pointers into sb; valid until the next append/clear) */
 void crisp_shim_batch_view(const crisp_shim_batch* sb, crispgpu_batch* out);
+/* Bytes crisp_shim_batch_pack needs for the accumulated sites (every array rounded up to 256 bytes). */
+size_t crisp_shim_batch_packed_bytes(const crisp_shim_batch* sb);
+/* Copy the accumulated arrays back to back (256-byte aligned) into `arena` — pinned memory from crispgpu_host_alloc, at
+ * least crisp_shim_batch_packed_bytes(sb) bytes, 256-byte aligned — and describe them in *out with arena_base /
+ * arena_bytes set: the engine then moves the batch with one asynchronous copy, and sb can be cleared and refilled while
+ * the batch is in flight.  Returns 0, or -1 if the arena is too small. */
+int crisp_shim_batch_pack(const crisp_shim_batch* sb, void* arena, size_t arena_cap, crispgpu_batch* out);
 
 #ifdef CRISP_SHIM_WITH_REFERENCE_TYPES
 /* Append the site currently held in `variant` (after calculate_allelecounts + sort_allelecounts and the candidate

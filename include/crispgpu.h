@@ -169,6 +169,13 @@ typedef struct crispgpu_batch {
 	 * entries into a zeroed dense table on the device (k_expand_counts). */
 	const uint32_t* ic_off;          /* [n*P+1] or NULL */
 	const crispgpu_count* ic_sparse; /* [ic_off[n*P]] or NULL */
+	/* Optional: the front end packed every array above into ONE host allocation (pinned, from crispgpu_host_alloc):
+	 * [arena_base, arena_base + arena_bytes), arena_base 256-byte aligned, every array 16-byte aligned inside it.  The
+	 * engine then moves the batch with a single copy and addresses the arrays by their offsets (a dozen copies
+	 * otherwise — what matters once several front-end threads share the device's driver lock).  Every non-NULL array
+	 * must lie inside the arena (CRISPGPU_ERR_ARG otherwise).  NULL / 0: arrays are copied one by one. */
+	const void* arena_base;
+	uint64_t arena_bytes;
 } crispgpu_batch;
 
 /* Per tested allele slot (al = slot+1 of maxvec), state of the reference's per-allele loop

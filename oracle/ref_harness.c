@@ -774,8 +774,15 @@ int crisp_ref_shim_roundtrip(void* h, const crispgpu_batch* b, char* msg, size_t
 		for (int k = 0; k < 8; k++) { maxvec[k].al = b->maxvec_al[s * 8 + k]; maxvec[k].ct = b->maxvec_ct[s * 8 + k]; }
 		crisp_shim_append_site(sb, &c->reflist, -1, &c->rq, c->bd, v, maxvec, b->tid[s]);
 	}
+	/* compare the PACKED batch (crisp_shim_batch_pack: every array copied into one arena), which also covers the view */
 	crispgpu_batch g;
-	crisp_shim_batch_view(sb, &g);
+	const size_t arena_cap = crisp_shim_batch_packed_bytes(sb);
+	void* arena = aligned_alloc(256, arena_cap ? arena_cap : 256);
+	if (crisp_shim_batch_pack(sb, arena, arena_cap, &g) != 0 || g.arena_base != arena || g.arena_bytes != arena_cap) {
+		if (msg) snprintf(msg, msgcap, "crisp_shim_batch_pack failed");
+		free(arena); crisp_shim_batch_free(sb);
+		return -2;
+	}
 #define CMP(name, bytes)                                                                                         \
 	do {                                                                                                         \
 		if ((bytes) && (b->name) && memcmp(g.name, b->name, (bytes)) != 0) {                                     \
@@ -816,6 +823,7 @@ int crisp_ref_shim_roundtrip(void* h, const crispgpu_batch* b, char* msg, size_t
 	}
 	CMP(qhigh, (size_t)n * P * 128); CMP(stats, (size_t)n * P * 128); CMP(tstats, (size_t)n * 128);
 #undef CMP
+	free(arena);
 	crisp_shim_batch_free(sb);
 	return bad;
 }

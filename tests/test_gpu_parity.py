@@ -298,6 +298,19 @@ def test_contexts_of_different_shapes_share_the_process():
     el.close()
 
 
+def test_arena_must_contain_every_array():
+    cfg = _cfg(10, 20, {})
+    batch = pin_batch(synth_batch(50, 10, cfg.ploidy, 100, seed=2, variant_frac=0.4).compact())
+    eng = Engine(cfg)
+    good = eng.run(batch)
+    outside = pin_batch(batch, arena=False)
+    outside._arena = batch._arena            # declares an arena its arrays do not live in
+    with pytest.raises(EngineError, match="outside the declared arena"):
+        eng.run(outside)
+    compare_results(eng.run(batch), good, tol=0.0, label="after-error")
+    eng.close()
+
+
 def test_advance_between_submit_and_wait():
     """crispgpu_advance queues stage 2 early; results and error behaviour are those of a plain submit/wait."""
     cfg = _cfg(10, 20, {})
@@ -351,7 +364,7 @@ def test_on_demand_read_fetch_equals_full_copy(opts, kw):
     eng = Engine(cfg)
     full = eng.run(batch)
     t_full = eng.timing()
-    lazy = eng.run(pin_batch(batch))
+    lazy = eng.run(pin_batch(batch, arena=False))   # separate pinned arrays: the read array may stay on the host
     t_lazy = eng.timing()
     again = eng.run(batch)   # the device read buffer now holds a mix of stale and fresh sites: results must not care
     eng.close()
@@ -397,14 +410,20 @@ def test_compact_read_format_matches_oracle(name, n, P, ploidy, depth, opts, kw)
     # ... and with the per-pool allele counts as their non-zero entries only (k_expand_counts)
     full = batch.compact()
     assert full.indcounts is None and full.ic_sparse.nbytes <= batch.indcounts.nbytes // 3   # at most 8 of 24 entries in use without indels
-    sparse = eng.run(pin_batch(full))
+    sparse = eng.run(pin_batch(full, arena=False))
     t = eng.timing()
+    # ... and packed into one pinned arena, moved with a single copy
+    packed = pin_batch(full)
+    one_copy = eng.run(packed)
+    t_arena = eng.timing()
     eng.close()
     skip = ("assoc_p", "assoc_p1") if opts.get("association") else ()
     compare_results(got, want, label=name, fp_skip=skip)
     compare_results(pinned, got, tol=0.0, label=name + "-pinned")
     compare_results(resident, got, tol=0.0, label=name + "-resident")
     compare_results(sparse, got, tol=0.0, label=name + "-sparse-counts")
+    compare_results(one_copy, got, tol=0.0, label=name + "-arena")
+    assert t_arena["h2d_bytes"] == packed._arena[1] and full.nbytes() <= packed._arena[1] < full.nbytes() + 256 * 32
     used = full.nbytes() - (0 if opts.get("em_flag", 1) >= 1 and opts.get("use_base_qvs", 1) == 1 else full.bins.nbytes + full.bin_off.nbytes)
     assert t["h2d_bytes"] == used
 
