@@ -190,6 +190,27 @@ def test_empty_and_degenerate_batches():
     eng.close()
 
 
+@pytest.mark.parametrize("P,ploidy,depth,n", [(1, 20, 200, 50), (2, 20, 100, 50), (2048, 4, 6, 6)], ids=["one_pool", "two_pools", "max_pools_2048"])
+def test_extreme_pool_counts(P, ploidy, depth, n):
+    """One pool, two pools, and the largest supported pool count (64 rounds of 32 lanes) against the oracle; one pool
+    more than that is refused at context creation, not mis-computed."""
+    cfg = _cfg(P, ploidy, {})
+    batch = synth_batch(n, P, cfg.ploidy, depth, seed=5, variant_frac=1.0)
+    want = OracleEngine(cfg).run(batch, mode=RNG_PHILOX)
+    eng = Engine(cfg)
+    got = eng.run(batch)
+    packed = eng.run(pin_batch(batch.compact()))
+    eng.close()
+    assert (want.status >= 3).sum() > 0
+    # P <= 2: the chi-square has <= 0 degrees of freedom; kf_gammaq's value there is rounding noise in the reference itself
+    skip = ("chi2pval", "ctpval") if P <= 2 else ()
+    compare_results(got, want, label=f"P={P}", fp_skip=skip)
+    compare_results(packed, got, tol=1e-12, label=f"P={P}-compact", fp_skip=skip)
+    if P == 2048:
+        with pytest.raises(EngineError):
+            Engine(_cfg(P + 1, ploidy, {}))
+
+
 def test_results_independent_of_batching_and_sharding():
     """Region shards (as at N GPUs) and arbitrary batch splits give bit-identical results, including the
     permutation test (streams are keyed by site)."""
