@@ -273,10 +273,18 @@ class Batch:
 
     def __init__(self, n_pools: int, **arrays):
         self.n_pools = int(n_pools)
+        # the compact forms stand in for the dense arrays they replace
+        optional = set()
+        if arrays.get("bins") is not None or arrays.get("bin_off") is not None:
+            optional |= {"reads", "read_off"}
+        if arrays.get("ic_off") is not None:
+            optional |= {"indcounts"}
+        if arrays.get("maxvec_al") is None and arrays.get("maxvec_ct") is None:
+            optional |= {"maxvec_al", "maxvec_ct"}   # sorted on the device (k_candidates)
         for name, dt, req in _BATCH_ARRAYS:
             a = arrays.pop(name, None)
             if a is None:
-                if req:
+                if req and name not in optional:
                     raise ValueError(f"batch array {name!r} is required")
                 setattr(self, name, None)
                 continue
@@ -377,13 +385,19 @@ class Batch:
             a = getattr(self, name)
             if a is not None:
                 out[name] = a.reshape(self.n_sites, w)[idx].reshape(-1)
-        # ragged: reads
-        ro = self.read_off.astype(np.int64)
-        lo, hi = ro[idx * P], ro[idx * P + P]
-        seg = [self.reads[a:b] for a, b in zip(lo, hi)]
-        out["reads"] = np.concatenate(seg) if seg else np.zeros(0, np.uint16)
-        per = (ro.reshape(-1)[1:] - ro.reshape(-1)[:-1]).reshape(self.n_sites, P)[idx].reshape(-1)
-        out["read_off"] = np.concatenate([[0], np.cumsum(per)]).astype(np.uint32)
+        # ragged arrays indexed per (site, pool) cell: reads, or their compact bins; sparse per-pool counts
+        def ragged(off, data, empty_dtype):
+            o = off.astype(np.int64)
+            seg = [data[a:b] for a, b in zip(o[idx * P], o[idx * P + P])] if data is not None else []
+            per = (o[1:] - o[:-1]).reshape(self.n_sites, P)[idx].reshape(-1)
+            return (np.concatenate(seg) if seg else np.zeros(0, empty_dtype)), np.concatenate([[0], np.cumsum(per)]).astype(np.uint32)
+
+        if self.reads is not None:
+            out["reads"], out["read_off"] = ragged(self.read_off, self.reads, np.uint16)
+        if self.bin_off is not None:
+            out["bins"], out["bin_off"] = ragged(self.bin_off, self.bins, np.uint32)
+        if self.ic_off is not None:
+            out["ic_sparse"], out["ic_off"] = ragged(self.ic_off, self.ic_sparse, np.uint32)
         if self.alt_off is not None:
             ao = self.alt_off.astype(np.int64)
             seg = [self.alt_reads[ao[s * 5]:ao[s * 5 + 5]] for s in idx]

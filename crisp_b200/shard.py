@@ -47,9 +47,19 @@ def shard_batch(batch: Batch, world: int, rank: int, by_reads: bool = True):
     """(sub-batch of rank, its site indices in the parent batch)."""
     weight = None
     if by_reads:
-        ro = batch.read_off.astype(np.int64)
         P = batch.n_pools
-        weight = ro[P::P] - ro[:-1:P] + 24 * P  # reads + counts, the bytes a site costs
+        # the bytes a site costs: its reads (2 B each) or bins (4 B each), plus its per-pool counts
+        if batch.read_off is not None:
+            ro = batch.read_off.astype(np.int64)
+            weight = 2 * (ro[P::P] - ro[:-1:P])
+        else:
+            bo = batch.bin_off.astype(np.int64)
+            weight = 4 * (bo[P::P] - bo[:-1:P])
+        if batch.ic_off is not None:
+            io = batch.ic_off.astype(np.int64)
+            weight = weight + 4 * (io[P::P] - io[:-1:P])
+        else:
+            weight = weight + 96 * P
     parts = partition_sites(batch.tid, batch.pos, world, weight)
     idx = parts[rank]
     return batch.select(idx), idx

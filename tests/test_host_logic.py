@@ -136,3 +136,19 @@ def test_compact_formats_round_trip():
     ro1 = np.array([0, 140000], np.uint32)
     bo1, b1 = bins_from_reads(ro1, np.full(140000, 0x1A1E, np.uint16))
     assert b1.tolist() == [(65535 << 16) | 0x1A1E, (65535 << 16) | 0x1A1E, (8930 << 16) | 0x1A1E] and bo1.tolist() == [0, 3]
+
+
+def test_sharding_a_compact_batch():
+    """Region shards of a compact batch are the compact forms of the dense batch's shards, and cover every site once."""
+    from crisp_b200.shard import shard_batch
+    batch = synth_batch(90, 6, np.full(6, 20), 80, seed=8, variant_frac=0.4, indel_frac=0.3)
+    compact = batch.compact()
+    seen = []
+    for r in range(3):
+        sub, idx = shard_batch(compact, 3, r)
+        seen.append(idx)
+        ref = batch.select(idx).compact()
+        assert sub.reads is None and sub.indcounts is None
+        for name in ("tid", "pos", "counts", "bin_off", "bins", "ic_off", "ic_sparse", "alt_off"):
+            assert np.array_equal(getattr(sub, name), getattr(ref, name)), name
+    assert np.array_equal(np.sort(np.concatenate(seen)), np.arange(batch.n_sites))
