@@ -261,8 +261,9 @@ void crispgpu_destroy(crispgpu_ctx* ctx);
 /* crispgpu_submit is asynchronous: it enqueues the host-to-device copies and the screening kernels and returns.
  * crispgpu_wait enqueues the caller kernels (they are sized by the number of surviving (site, slot) tasks, which has
  * arrived by then) and the device-to-host copies, and blocks until the results are in pinned host memory.
- * One batch may be in flight per context; keep a second context busy with the next batch to overlap its H2D with
- * this batch's compute (bench.py measures `e2e` that way).  A second submit before wait returns
+ * One batch may be in flight per context; keep several contexts busy (one front-end thread each; a context is not
+ * thread-safe, different contexts are independent) so that the copies and kernels of consecutive batches overlap
+ * (bench.py measures `e2e` that way, with six).  A second submit before wait returns
  * CRISPGPU_ERR_TICKET; so does a wait with a stale or unknown ticket. */
 int crispgpu_submit(crispgpu_ctx* ctx, const crispgpu_batch* batch, int64_t* ticket);
 int crispgpu_wait(crispgpu_ctx* ctx, int64_t ticket, crispgpu_results* out);

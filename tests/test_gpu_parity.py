@@ -415,7 +415,7 @@ BINNED = ["default_c1", "exome_c2", "varpool", "manyquals", "very_deep_sparse", 
 
 @pytest.mark.parametrize("name,n,P,ploidy,depth,opts,kw", [s for s in SCENARIOS if s[0] in BINNED], ids=BINNED)
 def test_compact_read_format_matches_oracle(name, n, P, ploidy, depth, opts, kw):
-    """The same scenarios shipped as (value, count) bins instead of one element per read (k_expand_bins)."""
+    """The same scenarios shipped as (value, count) bins instead of one element per read (consumed as they are by k_em)."""
     cfg = _cfg(P, ploidy, opts)
     batch = synth_batch(n, P, cfg.ploidy, depth, seed=11, **kw)
     want = OracleEngine(cfg).run(batch, mode=RNG_PHILOX)

@@ -113,7 +113,7 @@ def test_bench_reference_arm_prints_one_json_line():
 
 
 def test_compact_formats_round_trip():
-    """bins_from_reads / sparse_counts_from_dense are exact re-encodings (what k_expand_bins / k_expand_counts undo)."""
+    """bins_from_reads / sparse_counts_from_dense are exact re-encodings (what k_em reads directly and k_expand_counts undoes)."""
     from crisp_b200.abi import bins_from_reads, reads_from_bins, sparse_counts_from_dense
     batch = synth_batch(60, 6, np.full(6, 20), 80, seed=5, variant_frac=0.4, bidir_frac=0.1, indel_frac=0.3)
     bo, bins = bins_from_reads(batch.read_off, batch.reads)
