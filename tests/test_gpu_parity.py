@@ -211,6 +211,43 @@ def test_extreme_pool_counts(P, ploidy, depth, n):
             Engine(_cfg(P + 1, ploidy, {}))
 
 
+def _random_cases():
+    rng = np.random.default_rng(2024)
+    cases = []
+    for k in range(16):
+        P = int(rng.choice([3, 7, 31, 32, 33, 64, 65]))
+        ploidy = int(rng.choice([2, 5, 20, 31, 32, 63, 64, 127, 128, 130]))   # genotype counts around the 32/64/128 lane boundaries
+        depth = int(rng.choice([5, 40, 300]))
+        opts = [{}, dict(chisq_permutation=1, max_iter=1500), dict(em_flag=0), dict(use_base_qvs=0), dict(pivot_sample=max(1, P // 2)),
+                dict(agilent_ref_bias=0.52), dict(fast_filter=0)][int(rng.integers(0, 7))]
+        kw = dict(variant_frac=float(rng.choice([0.3, 0.7])), indel_frac=float(rng.choice([0.0, 0.3])), bidir_frac=float(rng.choice([0.0, 0.1])))
+        if rng.random() < 0.3:
+            kw["quals"] = range(12, 12 + int(rng.integers(17, 30)))           # more than 16 qualities: sparse likelihood path
+        if opts.get("em_flag") == 0:
+            kw.update(with_stats=True, with_qhigh=True)
+        if opts.get("chisq_permutation"):
+            kw.update(with_qhigh=True)
+        cases.append((f"r{k}_P{P}_n{ploidy}_d{depth}_" + "_".join(sorted(opts)) or "default", P, ploidy, depth, opts, kw))
+    return cases
+
+
+@pytest.mark.parametrize("name,P,ploidy,depth,opts,kw", _random_cases(), ids=[c[0] for c in _random_cases()])
+def test_random_shapes_match_oracle(name, P, ploidy, depth, opts, kw):
+    """Pool counts and pool sizes around the warp and chunk boundaries, random options, dense and compact batches."""
+    cfg = _cfg(P, ploidy, opts)
+    batch = synth_batch(60, P, cfg.ploidy, depth, seed=77, **kw)
+    want = OracleEngine(cfg).run(batch, mode=RNG_PHILOX)
+    eng = Engine(cfg)
+    got = eng.run(batch)
+    packed = eng.run(pin_batch(batch.compact()))
+    eng.close()
+    compare_results(got, want, label=name)
+    compare_results(packed, want, label=name + "-compact")
+    if opts.get("chisq_permutation"):
+        for r in (got, packed):
+            assert np.array_equal(r.perm_k, want.perm_k) and np.array_equal(r.perm_hits, want.perm_hits)
+
+
 def test_results_independent_of_batching_and_sharding():
     """Region shards (as at N GPUs) and arbitrary batch splits give bit-identical results, including the
     permutation test (streams are keyed by site)."""
