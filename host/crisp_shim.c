@@ -18,17 +18,22 @@ extern int maxalleles, MINQ, QVoffset, USE_QV;
 extern unsigned int BTI[];
 int calculate_indel_ambiguity(struct VARIANT* variant, REFLIST* reflist, int current, int allele);
 
-#define GROW(ptr, cap, need, type)                                    \
-	do {                                                              \
-		if ((size_t)(need) > (size_t)(cap)) {                         \
-			(cap) = (size_t)(need) * 2 + 64;                          \
-			(ptr) = (type*)realloc((ptr), (size_t)(cap) * sizeof(type)); \
-		}                                                             \
+/* grow an array geometrically; a failed allocation keeps the old block and makes the enclosing function return -1 */
+#define GROW(ptr, cap, need, type)                                            \
+	do {                                                                      \
+		if ((size_t)(need) > (size_t)(cap)) {                                 \
+			const size_t newcap_ = (size_t)(need) * 2 + 64;                   \
+			type* np_ = (type*)realloc((ptr), newcap_ * sizeof(type));        \
+			if (!np_) return -1;                                              \
+			(ptr) = np_;                                                      \
+			(cap) = newcap_;                                                  \
+		}                                                                     \
 	} while (0)
 
 crisp_shim_batch* crisp_shim_batch_new(int n_pools, int want_qhigh, int want_stats)
 {
 	crisp_shim_batch* sb = (crisp_shim_batch*)calloc(1, sizeof(*sb));
+	if (!sb) return NULL;
 	sb->n_pools = n_pools;
 	sb->want_qhigh = want_qhigh;
 	sb->want_stats = want_stats;
@@ -38,6 +43,10 @@ crisp_shim_batch* crisp_shim_batch_new(int n_pools, int want_qhigh, int want_sta
 	sb->ic_off = (uint32_t*)calloc(1, sizeof(uint32_t));
 	sb->bin_count = (uint32_t*)calloc(4096, sizeof(uint32_t));
 	sb->bin_touched = (uint16_t*)calloc(4096, sizeof(uint16_t));
+	if (!sb->read_off || !sb->alt_off || !sb->bin_off || !sb->ic_off || !sb->bin_count || !sb->bin_touched) {
+		crisp_shim_batch_free(sb);
+		return NULL;
+	}
 	return sb;
 }
 
@@ -131,31 +140,47 @@ int crisp_shim_batch_pack(const crisp_shim_batch* sb, void* arena, size_t arena_
 	return 0;
 }
 
-static void reserve_site(crisp_shim_batch* sb)
+/* room for one more site in every per-site array; -1 when an allocation fails (the batch stays valid) */
+static int reserve_site(crisp_shim_batch* sb)
 {
 	const size_t n = (size_t)sb->n_sites + 1, P = sb->n_pools;
-	if ((int)n > sb->cap_sites) {
-		const size_t c = n * 2 + 64;
-		sb->tid = (int32_t*)realloc(sb->tid, c * 4); sb->pos = (int32_t*)realloc(sb->pos, c * 4);
-		sb->refbase = (uint8_t*)realloc(sb->refbase, c); sb->maxvec_al = (uint8_t*)realloc(sb->maxvec_al, c * 8);
-		sb->maxvec_ct = (int32_t*)realloc(sb->maxvec_ct, c * 32); sb->counts = (int32_t*)realloc(sb->counts, c * 96);
-		sb->indcounts = (int32_t*)realloc(sb->indcounts, c * P * 96);
-		sb->indel_len = (int16_t*)realloc(sb->indel_len, c * 16); sb->hplen = (int16_t*)realloc(sb->hplen, c * 16);
-		sb->bin_off = (uint32_t*)realloc(sb->bin_off, (c * P + 1) * 4);
-		sb->ic_off = (uint32_t*)realloc(sb->ic_off, (c * P + 1) * 4);
-		sb->read_off = (uint32_t*)realloc(sb->read_off, (c * P + 1) * 4); sb->alt_off = (uint32_t*)realloc(sb->alt_off, (c * 5 + 1) * 4);
-		sb->amb_idx = (int32_t*)realloc(sb->amb_idx, c * 20);
-		sb->qhigh = (double*)realloc(sb->qhigh, c * P * 128); sb->stats = (double*)realloc(sb->stats, c * P * 128);
-		sb->tstats = (double*)realloc(sb->tstats, c * 128);
-		sb->cap_sites = (int)c;
-	}
+	if ((int)n <= sb->cap_sites) return 0;
+	const size_t c = n * 2 + 64;
+#define RESIZE(field, bytes) do { void* np_ = realloc(sb->field, (bytes)); if (!np_) return -1; sb->field = np_; } while (0)
+	RESIZE(tid, c * 4); RESIZE(pos, c * 4); RESIZE(refbase, c); RESIZE(maxvec_al, c * 8); RESIZE(maxvec_ct, c * 32);
+	RESIZE(counts, c * 96); RESIZE(indcounts, c * P * 96); RESIZE(indel_len, c * 16); RESIZE(hplen, c * 16);
+	RESIZE(bin_off, (c * P + 1) * 4); RESIZE(ic_off, (c * P + 1) * 4); RESIZE(read_off, (c * P + 1) * 4);
+	RESIZE(alt_off, (c * 5 + 1) * 4); RESIZE(amb_idx, c * 20);
+	if (sb->want_qhigh) RESIZE(qhigh, c * P * 128);
+	if (sb->want_stats) { RESIZE(stats, c * P * 128); RESIZE(tstats, c * 128); }
+#undef RESIZE
+	sb->cap_sites = (int)c;
+	return 0;
 }
+
+static int append_site(crisp_shim_batch* sb, REFLIST* reflist, int current, READQUEUE* bq, struct BAMFILE_data* bd,
+                       struct VARIANT* variant, ALLELE* maxvec, int tid);
 
 int crisp_shim_append_site(crisp_shim_batch* sb, REFLIST* reflist, int current, READQUEUE* bq, struct BAMFILE_data* bd,
                            struct VARIANT* variant, ALLELE* maxvec, int tid)
 {
+	const size_t n_reads = sb->n_reads, n_alt = sb->n_alt, n_bins = sb->n_bins, n_ic = sb->n_ic;
+	const int n_amb = sb->n_amb;
+	const int rc = append_site(sb, reflist, current, bq, bd, variant, maxvec, tid);
+	if (rc != 0) {  /* drop whatever the failed site had already appended */
+		sb->n_reads = n_reads; sb->n_alt = n_alt; sb->n_bins = n_bins; sb->n_ic = n_ic; sb->n_amb = n_amb;
+		memset(sb->bin_count, 0, 4096 * sizeof(uint32_t));
+	}
+	return rc;
+}
+
+static int append_site(crisp_shim_batch* sb, REFLIST* reflist, int current, READQUEUE* bq, struct BAMFILE_data* bd,
+                       struct VARIANT* variant, ALLELE* maxvec, int tid)
+{
 	const int P = sb->n_pools, s = sb->n_sites;
-	reserve_site(sb);
+	/* the offset arrays are 32-bit: refuse a site that could push a total past them (flush the batch first) */
+	if (sb->n_reads > 0xf0000000u || sb->n_alt > 0xf0000000u || sb->n_bins > 0xf0000000u || sb->n_ic > 0xf0000000u) return -2;
+	if (reserve_site(sb) != 0) return -1;
 	sb->tid[s] = tid;
 	sb->pos[s] = variant->position;
 	sb->refbase[s] = (uint8_t)variant->refbase;
@@ -173,10 +198,10 @@ int crisp_shim_append_site(crisp_shim_batch* sb, REFLIST* reflist, int current, 
 		}
 	for (int i = 0; i < P; i++)
 		for (int q = 0; q < 16; q++) {
-			sb->qhigh[((size_t)s * P + i) * 16 + q] = variant->Qhighcounts[i][q];
-			sb->stats[((size_t)s * P + i) * 16 + q] = variant->stats[i][q];
+			if (sb->want_qhigh) sb->qhigh[((size_t)s * P + i) * 16 + q] = variant->Qhighcounts[i][q];
+			if (sb->want_stats) sb->stats[((size_t)s * P + i) * 16 + q] = variant->stats[i][q];
 		}
-	for (int q = 0; q < 16; q++) sb->tstats[(size_t)s * 16 + q] = variant->tstats[q];
+	if (sb->want_stats) for (int q = 0; q < 16; q++) sb->tstats[(size_t)s * 16 + q] = variant->tstats[q];
 	/* homopolymer ambiguity of the tested indel alleles, newcrispcaller.c:191-198 */
 	for (int al = 1; al <= 5; al++) {
 		if (maxvec[al].ct < 3) continue;
@@ -189,6 +214,7 @@ int crisp_shim_append_site(crisp_shim_batch* sb, REFLIST* reflist, int current, 
 	for (int a = 0; a < 8; a++) {
 		int len = 0;
 		if (a >= 4 && (variant->itb[a][0] == '+' || variant->itb[a][0] == '-')) len = (int)strlen(variant->itb[a]) - 1;
+		if (len > 32767 || variant->HPlength[a] > 32767 || variant->HPlength[a] < -32768) return -2;
 		sb->indel_len[s * 8 + a] = (int16_t)(a >= 4 && variant->itb[a][0] == '-' ? -len : len);
 		sb->hplen[s * 8 + a] = (int16_t)variant->HPlength[a];
 	}
@@ -252,6 +278,7 @@ int crisp_shim_append_site(crisp_shim_batch* sb, REFLIST* reflist, int current, 
 					if (!hit) continue;
 					GROW(sb->alt_reads, sb->cap_alt, sb->n_alt + 1, crispgpu_altread);
 					crispgpu_altread* e = &sb->alt_reads[sb->n_alt++];
+					if (r->l1 + r->delta > 65535 || r->l1 + r->delta < 0 || r->alignedbases > 65535 || r->alignedbases < 0 || i > 65535) return -2;
 					e->pool = (uint16_t)i; e->offset = (uint16_t)(r->l1 + r->delta); e->aligned = (uint16_t)r->alignedbases; e->strand = r->strand; e->pad = 0;
 					taken++;
 				}
@@ -267,9 +294,14 @@ int crisp_shim_append_site(crisp_shim_batch* sb, REFLIST* reflist, int current, 
 		if (!((a2 >= 4 && variant->HPlength[a2] > 0) || (a3 >= 4 && variant->HPlength[a3] >= 100))) continue;
 		const int hp = variant->HPlength[a2];
 		if (sb->n_amb + 1 > sb->cap_amb) {
-			sb->cap_amb = (sb->n_amb + 1) * 2 + 16;
-			sb->amb_dec = (int32_t*)realloc(sb->amb_dec, (size_t)sb->cap_amb * P * 16);
-			sb->amb_ep = (double*)realloc(sb->amb_ep, (size_t)sb->cap_amb * P * 16);
+			const int c = (sb->n_amb + 1) * 2 + 16;
+			int32_t* nd = (int32_t*)realloc(sb->amb_dec, (size_t)c * P * 16);
+			if (!nd) return -1;
+			sb->amb_dec = nd;
+			double* ne = (double*)realloc(sb->amb_ep, (size_t)c * P * 16);
+			if (!ne) return -1;
+			sb->amb_ep = ne;
+			sb->cap_amb = c;
 		}
 		int32_t* dec = sb->amb_dec + (size_t)sb->n_amb * P * 4;
 		double* ep = sb->amb_ep + (size_t)sb->n_amb * P * 2;

@@ -38,6 +38,8 @@ typedef struct crisp_shim_batch {
 	uint16_t* bin_touched;  /* [4096] scratch: values seen in the current cell */
 } crisp_shim_batch;
 
+/* NULL when out of memory.  want_qhigh / want_stats: also snapshot Qhighcounts (read in permutation mode) / stats, tstats
+ * (read with --EM 0). */
 crisp_shim_batch* crisp_shim_batch_new(int n_pools, int want_qhigh, int want_stats);
 /* compact = 1: emit `bins`/`bin_off` instead of one element per read and `ic_sparse`/`ic_off` instead of the dense
  * indcounts table (about a fifth of the bytes on binned-quality data; the engine rebuilds both on the device).
@@ -58,7 +60,10 @@ int crisp_shim_batch_pack(const crisp_shim_batch* sb, void* arena, size_t arena_
 #ifdef CRISP_SHIM_WITH_REFERENCE_TYPES
 /* Append the site currently held in `variant` (after calculate_allelecounts + sort_allelecounts and the candidate
  * test of variantcalls.c:76-92).  reflist/current are used for calculate_indel_ambiguity exactly as
- * newcrispcaller.c:191-198 does; pass current < 0 to keep variant->HPlength as it is. */
+ * newcrispcaller.c:191-198 does; pass current < 0 to keep variant->HPlength as it is.
+ * Returns 0; -1 when an allocation fails; -2 when a value does not fit the batch format (read offset / aligned length
+ * above 65535, indel or homopolymer length above 32767, more than 2^32 - 2^28 elements in one batch: flush first).  On
+ * failure the site is not part of the batch and the sites appended before stay valid. */
 int crisp_shim_append_site(crisp_shim_batch* sb, REFLIST* reflist, int current, READQUEUE* bq, struct BAMFILE_data* bd,
                            struct VARIANT* variant, ALLELE* maxvec, int tid);
 /* Copy the results of site s into struct VARIANT (fields read by print_pooledvariant, newcrispprint.c:357-473). */

@@ -1,0 +1,247 @@
+"""BAM -> VCF through the reference's own front end (SURVEY.md §8c level 1).
+
+Synthetic pools are written as real BAM files (crisp_b200/bamsynth.py) and run through
+  * oracle/_ref/CRISP.binary — the unmodified reference program, and
+  * oracle/_ref/CRISP.gpu    — the same objects with the call at variantcalls.c:115 bound to host/crisp_frontend.c.
+CPU tests (no GPU): the batches CRISP.gpu packs at that call site, fed to the unmodified reference engine (the harness)
+and to the oracle restatement, reproduce CRISP.binary's VCF records; compact == dense; `--regions` shards concatenate
+to the unsharded VCF.  GPU tests: CRISP.gpu's VCF body equals CRISP.binary's — byte for byte in the asymptotic modes;
+in permutation mode everything but the Monte-Carlo CT= field, which is checked against its binomial error.
+"""
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from crisp_b200 import frontend as fe
+from crisp_b200.abi import bins_from_reads, sparse_counts_from_dense
+from crisp_b200.bamsynth import make_dataset
+from frontend_io import read_dump
+from oracle.loader import OracleEngine, RefEngine
+from util import compare_results
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFBIN = os.path.join(ROOT, "oracle", "_ref", "CRISP.binary")
+GPUBIN = os.path.join(ROOT, "oracle", "_ref", "CRISP.gpu")
+BAMTOOL = os.path.join(ROOT, "oracle", "_ref", "bamtool")
+
+# name, dataset kwargs, poolsize, extra reference flags
+CASES = {
+    "pooled": (dict(pools=6, poolsize=20, length=20000, depth=60, seed=7, indel_frac=0.2, pe_frac=0.3), 20, []),
+    "em0": (dict(pools=6, poolsize=20, length=16000, depth=60, seed=8, indel_frac=0.2, pe_frac=0.2), 20, ["--EM", "0"]),
+    "diploid": (dict(pools=24, poolsize=2, length=12000, depth=14, seed=9, pe_frac=0.2), 2, []),
+    "perm": (dict(pools=8, poolsize=16, length=16000, depth=50, seed=10, pe_frac=0.2), 16, ["--chisquare", "0", "--perms", "3000"]),
+    "manyquals": (dict(pools=5, poolsize=24, length=12000, depth=80, seed=11, indel_frac=0.1, qual_values=list(range(14, 42)),
+                       qual_probs=[1 / 28] * 28), 24, []),
+}
+
+
+def _programs():
+    """Looked up when a test runs (the session fixture has built oracle/_ref by then), not at collection."""
+    missing = [p for p in (REFBIN, GPUBIN, BAMTOOL) if not os.path.exists(p)]
+    if missing:
+        pytest.skip("oracle/_ref programs not built (need /root/reference): " + ", ".join(os.path.basename(m) for m in missing))
+
+
+@pytest.fixture(scope="module")
+def datasets(tmp_path_factory):
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            kw, poolsize, extra = CASES[name]
+            d = tmp_path_factory.mktemp(name)
+            ds = make_dataset(str(d), **kw)
+            ds["dir"] = str(d)
+            ref_vcf = os.path.join(str(d), "ref.vcf")
+            fe.run_program(REFBIN, ds, ref_vcf, poolsize, extra)
+            ds["ref_vcf"] = ref_vcf
+            cache[name] = ds
+        return cache[name]
+
+    return get
+
+
+def _strip_flank(info):
+    return re.sub(r"FLANKSEQ=[^;\t]*", "FLANKSEQ=", info)
+
+
+def test_bam_files_are_wellformed(tmp_path):
+    import gzip
+    import struct
+
+    ds = make_dataset(str(tmp_path), pools=2, poolsize=4, length=4000, depth=10, seed=3, indel_frac=0.3, pe_frac=0.4)
+    for path in ds["bams"]:
+        raw = gzip.open(path).read()
+        assert raw[:4] == b"BAM\x01"
+        (lt,) = struct.unpack_from("<i", raw, 4)
+        o = 8 + lt
+        (nref,) = struct.unpack_from("<i", raw, o)
+        assert nref == 1
+        (ln,) = struct.unpack_from("<i", raw, o + 4)
+        o += 8 + ln + 4
+        last, n = -1, 0
+        while o < len(raw):
+            (bs,) = struct.unpack_from("<i", raw, o)
+            tid, pos = struct.unpack_from("<ii", raw, o + 4)
+            assert tid == 0 and pos >= last
+            last = pos
+            o += 4 + bs
+            n += 1
+        assert o == len(raw) and n == 400
+    assert open(ds["fasta"] + ".fai").read().split("\t")[1] == "4000"
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_frontend_batches_reproduce_reference_vcf(name, datasets, tmp_path):
+    """What CRISP.gpu packs at variantcalls.c:115 is what the reference engine needs: the unmodified engine run on the
+    dumped batches prints CRISP.binary's records, and the oracle restatement agrees with it on every field."""
+    _programs()
+    ds = datasets(name)
+    kw, poolsize, extra = CASES[name]
+    dump = str(tmp_path / "dump.bin")
+    fe.run_program(GPUBIN, ds, str(tmp_path / "unused.vcf"), poolsize, extra,
+                   env=dict(CRISPGPU_DUMP=dump, CRISPGPU_DUMP_ONLY=1, CRISPGPU_BATCH=10))
+    recs = read_dump(dump)
+    assert len(recs) >= 2, "expected several batches"
+    want = fe.read_vcf(ds["ref_vcf"])
+    assert len(want) >= 8, "dataset too quiet to be a test"
+    got = []
+    perm = "--chisquare" in extra
+    for cfg, batch, ex in recs:
+        assert np.all(np.diff(batch.pos) > 0), "sites must arrive in coordinate order"
+        ref = RefEngine(cfg).run(batch, want_vcf=True, seed=11)
+        for line in ref.vcf.strip().split("\n"):
+            if line:
+                cols = line.split("\t")
+                s = int(cols[0])
+                P = batch.n_pools
+                got.append((int(batch.pos[s]), cols[1:], ex["readdepths"].reshape(-1, P)[s], ex["mqcounts"].reshape(-1, 4)[s]))
+        orc = OracleEngine(cfg).run(batch, seed=11)
+        compare_results(orc, ref, label=f"{name}: oracle vs reference engine on front-end batches")
+    # the harness rebuilds readdepths / MQcounts from the counts (it has no mapping qualities or filtered reads): those two
+    # printed fields are checked against what the front end recorded for the printer instead
+    extra_of = {(p0 + 1 if "VT=SNV;" in g[7] else p0): (dp, mq) for p0, g, dp, mq in got}
+    gmap = {(p0 + 1 if "VT=SNV;" in g[7] else p0): g for p0, g, dp, mq in got}
+    wmap = {int(w[1]): w for w in want}
+    if perm:   # Monte-Carlo p-values at the FAST_FILTER thresholds may flip a record in either run
+        assert len(set(gmap) ^ set(wmap)) <= 3, sorted(set(gmap) ^ set(wmap))
+    else:
+        assert sorted(gmap) == sorted(wmap), f"{len(got)} records from the packed batches, CRISP.binary printed {len(want)}"
+    for pos1 in sorted(set(gmap) & set(wmap)):
+        g, w = gmap[pos1], wmap[pos1]
+        if "VT=SNV;" in w[7]:
+            assert g[3:5] == w[3:5]
+        dp, mq = extra_of[pos1]
+        assert re.search(r"MQS=([^;]*)", w[7]).group(1) == ",".join(str(int(x)) for x in mq)
+        dpcol = 2   # AC:GQ:DP:..., GT:GQ:DP:... and (--EM 0) GT:AF:DP:... all carry the depth third
+        assert [c.split(":")[dpcol] for c in w[9:]] == [str(int(x)) for x in dp]
+        drop_dp = lambda cols: [":".join(f for k, f in enumerate(c.split(":")) if k != dpcol) for c in cols]
+        gi, wi = _strip_flank(g[7]), _strip_flank(w[7])
+        gi, wi = re.sub(r"MQS=[^;]*", "MQS=", gi), re.sub(r"MQS=[^;]*", "MQS=", wi)
+        if perm:   # the reference seeds drand48 with the time of day: CT= is a Monte-Carlo value
+            gi, wi = re.sub(r"CT=[^;]*", "CT=", gi), re.sub(r"CT=[^;]*", "CT=", wi)
+        # FILTER: the harness cannot reproduce a LowMQ flag (no mapping qualities); synthetic reads are all MAPQ 60
+        assert g[5:7] == w[5:7] and gi == wi and g[8] == w[8] and drop_dp(g[9:]) == drop_dp(w[9:]), f"record at {w[0]}:{w[1]} differs:\n{g}\n{w}"
+
+
+def test_frontend_compact_batches_equal_dense(datasets, tmp_path):
+    _programs()
+    ds = datasets("pooled")
+    kw, poolsize, extra = CASES["pooled"]
+    dumps = {}
+    for compact in (0, 1):
+        dump = str(tmp_path / f"dump{compact}.bin")
+        fe.run_program(GPUBIN, ds, str(tmp_path / "unused.vcf"), poolsize, extra,
+                       env=dict(CRISPGPU_DUMP=dump, CRISPGPU_DUMP_ONLY=1, CRISPGPU_BATCH=1000, CRISPGPU_COMPACT=compact))
+        dumps[compact] = read_dump(dump)
+    (_, dense, _), (_, comp, ex) = dumps[0][0], dumps[1][0]
+    assert ex["compact"] and comp.bins is not None and dense.reads is not None
+    bin_off, bins = bins_from_reads(dense.read_off, dense.reads)
+    assert np.array_equal(bin_off, comp.bin_off) and np.array_equal(bins, comp.bins)
+    ic_off, ic = sparse_counts_from_dense(dense.indcounts)
+    assert np.array_equal(ic_off, ex["ic_off"]) and np.array_equal(ic, ex["ic_sparse"])
+    for name in ("pos", "counts", "indcounts", "maxvec_al", "maxvec_ct", "alt_off", "hplen", "indel_len"):
+        assert np.array_equal(getattr(dense, name), getattr(comp, name)), name
+
+
+def test_region_shards_concatenate_to_the_unsharded_vcf(datasets, tmp_path):
+    """The reference's parallelism (README.md:51): `--regions` shards over indexed BAMs."""
+    _programs()
+    ds = datasets("pooled")
+    kw, poolsize, extra = CASES["pooled"]
+    fe.index_bams(BAMTOOL, ds)
+    out = str(tmp_path / "sharded.vcf")
+    info = fe.run_sharded(REFBIN, ds, out, poolsize, 3, extra)
+    assert info["nproc"] == 3
+    cmp = fe.compare_vcf(fe.read_vcf(out), fe.read_vcf(ds["ref_vcf"]))
+    # a shard starts with an empty read window, so a record within one read length of a cut may differ in depth
+    edges = [int(r.split(":")[1].split("-")[0]) for r in fe.regions(ds, 3)[1:]]
+    near = lambda k: any(abs(k[1] - e) <= 260 for e in edges)
+    bad = [d for d in cmp["differ"] if not near(d[0])] + [k for k in cmp["only_got"] + cmp["only_want"] if not near(k)]
+    assert not bad and cmp["same"] >= 0.8 * len(fe.read_vcf(ds["ref_vcf"])), (bad, cmp["same"])
+
+
+# ------------------------------------------------------------------------------------------------------------------ GPU
+def _ct_ok(a, b, perms):
+    """Two permutation p-values (log10, printed with one decimal) of the same table, from different random streams."""
+    if a == b:
+        return True
+    pa, pb = 10 ** float(a), 10 ** float(b)
+    p = max(pa, pb, 1.0 / (perms + 2))
+    k = max(10.0 / p, 1.0) if p > 10.0 / perms else perms   # the stop rule ends a test after ~10 hits
+    sd = math.sqrt(p * (1 - min(p, 0.999)) / min(k, perms))
+    return abs(pa - pb) <= 6 * sd + 0.12 * p   # + the one-decimal print rounding (10^0.05 = 1.12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,compact", [("pooled", 0), ("pooled", 1), ("em0", 0), ("diploid", 0), ("diploid", 1), ("manyquals", 0),
+                                          ("manyquals", 1), ("perm", 0)])
+def test_bam_to_vcf_on_gpu_equals_reference(name, compact, datasets, tmp_path):
+    """variantcalls.c / newcrispprint.c unchanged, engine on the B200: identical VCF."""
+    _programs()
+    ds = datasets(name)
+    kw, poolsize, extra = CASES[name]
+    out = str(tmp_path / "gpu.vcf")
+    stats = str(tmp_path / "stats.json")
+    fe.run_program(GPUBIN, ds, out, poolsize, extra, env=dict(CRISPGPU_BATCH=10, CRISPGPU_COMPACT=compact, CRISPGPU_STATS=stats))
+    st = fe.read_stats(stats)
+    assert st["batches"] >= 2 and st["sites"] > 0
+    perm = "--chisquare" in extra
+    got, want = fe.read_vcf(out), fe.read_vcf(ds["ref_vcf"])
+    cmp = fe.compare_vcf(got, want, monte_carlo=perm)
+    if not perm:
+        assert not cmp["differ"] and not cmp["only_got"] and not cmp["only_want"], cmp
+        assert cmp["same"] == len(want) == st["records"]
+        return
+    perms = int(extra[extra.index("--perms") + 1])
+    # a record may appear/disappear only if its CT sits at a FAST_FILTER threshold (-3 / -2, newcrispcaller.c:122-127)
+    flips = cmp["only_got"] + cmp["only_want"]
+    assert len(flips) <= max(1, len(want) // 10), flips
+    assert not cmp["differ"], cmp["differ"]
+    bad = [c for c in cmp["ct"] if not all(_ct_ok(x, y, perms) for x, y in zip(c[1].split(","), c[2].split(",")))]
+    assert not bad, bad
+
+
+@pytest.mark.gpu
+def test_config1_bam_to_vcf(tmp_path):
+    """BASELINE configs[0]: 10 pools x 20, 100 kb at 100x, --EM 1 — default and `--chisquare 0 --perms 20000`."""
+    _programs()
+    ds = make_dataset(str(tmp_path / "c1"), pools=10, poolsize=20, length=100000, depth=100, seed=1)
+    for extra in ([], ["--chisquare", "0", "--perms", "20000"]):
+        tag = "perm" if extra else "default"
+        ref_vcf, out = str(tmp_path / f"ref_{tag}.vcf"), str(tmp_path / f"gpu_{tag}.vcf")
+        fe.run_program(REFBIN, ds, ref_vcf, 20, extra)
+        fe.run_program(GPUBIN, ds, out, 20, extra, env=dict(CRISPGPU_COMPACT=1))
+        got, want = fe.read_vcf(out), fe.read_vcf(ref_vcf)
+        assert len(want) > 100
+        cmp = fe.compare_vcf(got, want, monte_carlo=bool(extra))
+        assert not cmp["differ"], cmp["differ"][:3]
+        if not extra:
+            assert not cmp["only_got"] and not cmp["only_want"] and cmp["same"] == len(want)
+        else:
+            assert len(cmp["only_got"]) + len(cmp["only_want"]) <= 4, (cmp["only_got"], cmp["only_want"])
+            bad = [c for c in cmp["ct"] if not all(_ct_ok(x, y, 20000) for x, y in zip(c[1].split(","), c[2].split(",")))]
+            assert not bad, bad
