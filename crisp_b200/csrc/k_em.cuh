@@ -12,6 +12,8 @@
 // the per-pool log-sum-exp needs no cross-lane traffic and terms more than 20 decades below the pool's maximum are
 // skipped warp-uniformly (they cannot change a double-precision sum).
 #pragma once
+#include <type_traits>
+
 #include "dmath.cuh"
 #include "engine_types.cuh"
 #include "k_evaluate.cuh"
@@ -32,7 +34,7 @@ struct EmShared {
 	int part_w[kEmMaxWarps];
 	int exitflag;
 	int iter;
-	int task;
+	int next_task;
 	double delta, deltaf, hwe;
 };
 
@@ -98,13 +100,16 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 		}
 	}
 
+	// the work counter is read one task ahead: the round trip of the atomic overlaps the task instead of starting it
+	if (tid == 0) sh->next_task = atomicAdd(head, 1);
 	for (;;) {
 		__syncthreads();
-		if (tid == 0) sh->task = atomicAdd(head, 1);
+		const int cur_task = sh->next_task;
 		__syncthreads();
-		if (sh->task >= n_tasks) break;
-		const int o = tasks[sh->task], s = o / kSlots, slot = o - s * kSlots;
-		const int task = row0 + sh->task;  // AC/QV row
+		if (cur_task >= n_tasks) break;
+		if (tid == 0) sh->next_task = atomicAdd(head, 1);
+		const int o = tasks[cur_task], s = o / kSlots, slot = o - s * kSlots;
+		const int task = row0 + cur_task;  // AC/QV row
 		const uint8_t* mal = b.maxvec_al + s * 8;
 		int a1, a2, a3;
 		slot_alleles(mal, slot, a1, a2, a3);
@@ -136,7 +141,8 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 		}
 		// site totals for the initial indel error rates (crispEM.c:366-374)
 		if (tid == 0) {
-			double E[3];
+			double E[3] = {0.001, 0.001, 0.001};
+			if constexpr (COUNTLIK)
 			for (int k = 0; k < 3; k++) {
 				int t1 = b.counts[s * kNC + a1 + 8 * k], t2 = b.counts[s * kNC + a2 + 8 * k];
 				if (row >= 0) {
@@ -151,7 +157,7 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 				}
 				E[k] = (double)(t2 + 1.0) / (t1 + t2 + 1.0);
 			}
-			if (E[0] >= 0.005 || E[1] >= 0.005) E[0] = E[1] = E[2] = 0.005;
+			if (COUNTLIK && (E[0] >= 0.005 || E[1] >= 0.005)) E[0] = E[1] = E[2] = 0.005;
 			for (int k = 0; k < 3; k++) { sh->E01[k] = E[k]; sh->E10[k] = E[k]; }
 			// starting allele frequency: p[0]/K with the clamp of crispEM.c:360
 			double p0 = prm.o.paf[o] / c.K;
@@ -160,6 +166,14 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 			sh->LL[0] = sh->LL[1] = sh->LL[2] = 0.0;
 			sh->exitflag = 0;
 			sh->iter = 0;
+		}
+		// dense path on a compact batch: the offsets of the site's P cells (the bins are then walked as one flat range)
+		// and the zeroed histogram are staged under the same barrier.  boff aliases the log-sum-exp shifts, which are
+		// first written in EM iteration 0.
+		uint32_t* boff = reinterpret_cast<uint32_t*>(mprev);
+		if (!COUNTLIK && dense) {
+			for (int k = tid; k < 2 * nq * 3 * P; k += blockDim.x) dh[k] = 0;
+			if (b.bins) for (int i = tid; i <= P; i += blockDim.x) boff[i] = b.bin_off[(size_t)s * P + i];
 		}
 		__syncthreads();
 
@@ -208,20 +222,20 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 			// calculate_pooled_likelihoods_snp, dense form (few distinct qualities, one pool size).
 			// (1) per pool (one warp) bin the packed reads into dh[allele][quality][class][pool];
 			// (2) contract with the staged table rows on the FP64 tensor cores (see below).
-			for (int k = tid; k < 2 * nq * 3 * P; k += blockDim.x) dh[k] = 0;
-			__syncthreads();
 			if (b.bins) {
-				// compact input: the cell's (value, count) bins are the histogram already — one shared-memory add per bin
-				for (int i = warp; i < P; i += nwarps) {
-					const uint32_t b0 = b.bin_off[(size_t)s * P + i], b1 = b.bin_off[(size_t)s * P + i + 1];
-					for (uint32_t bb = b0 + lane; bb < b1; bb += 32) {
-						const uint32_t e = __ldg(b.bins + bb);
-						const int base = (e >> 8) & 3;
-						const int which = base == a1 ? 0 : (base == a2 ? 1 : -1);
-						if (which < 0) continue;
-						const int cls = (e >> 11) & 1 ? 2 : ((e >> 10) & 1);
-						atomicAdd(dh + ((which * nq + qd[e & 0x7f]) * 3 + cls) * P + i, e >> 16);
-					}
+				// compact input: the (value, count) bins are the histogram already — one shared-memory add per bin.  The bins of
+				// a site are contiguous: every thread takes bins of the flat range (all loads independent, one memory latency
+				// for the site) and finds the pool of a bin in the staged offsets.
+				const uint32_t b0 = boff[0], b1 = boff[P];
+				for (uint32_t bb = b0 + tid; bb < b1; bb += blockDim.x) {
+					const uint32_t e = __ldg(b.bins + bb);
+					const int base = (e >> 8) & 3;
+					const int which = base == a1 ? 0 : (base == a2 ? 1 : -1);
+					if (which < 0) continue;
+					int lo = 0, hi = P;  // boff[lo] <= bb < boff[hi]: the last cell starting at or before bb
+					while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (boff[mid] <= bb) lo = mid; else hi = mid; }
+					const int cls = (e >> 11) & 1 ? 2 : ((e >> 10) & 1);
+					atomicAdd(dh + ((which * nq + qd[e & 0x7f]) * 3 + cls) * P + lo, e >> 16);
 				}
 			} else
 			for (int i = warp; i < P; i += nwarps) {
@@ -469,7 +483,12 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 		double my_p = sh->p[0], my_LL = 0.0, LLnull0 = 0.0;
 		int it = 0;
 		for (;;) {
-			const double my_l0 = log10(my_p), my_l1 = log10(1.0 - my_p);
+			// log10 p and log10(1-p) of the three planes in ONE call per warp: lane 2*pl holds p, lane 2*pl+1 holds 1-p
+			double my_lg;
+			{
+				const double pp = __shfl_sync(0xffffffffu, my_p, (lane >> 1) < 3 ? (lane >> 1) : 0);
+				my_lg = log10((lane & 1) ? 1.0 - pp : pp);
+			}
 			double* part = part_base + (it & 1) * 19 * rounds;
 			const int nunits = rounds * 3;
 			for (int u = warp; u < nunits; u += nwarps) {
@@ -477,44 +496,53 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 				const int i = rd * 32 + lane;
 				const bool act = i < P;
 				const int ii = act ? i : P - 1;
-				const int n = c.ploidy[ii];
+				const int n = NOBIDIR ? nmax : c.ploidy[ii];   // NOBIDIR: one pool size
 				// plane pl as a column of H; with NOBIDIR plane 0 is formed as forward + reverse - NC on the fly
 				const bool sum2 = NOBIDIR && pl == 0;
 				const double* Hp = (NOBIDIR ? (pl == 2 ? Gr : Gf) : G + (size_t)pl * plane) + ii;
 				const double* Hq = Gr + ii;
-				const double l0 = __shfl_sync(0xffffffffu, my_l0, pl), l1 = __shfl_sync(0xffffffffu, my_l1, pl);
+				const double l0 = __shfl_sync(0xffffffffu, my_lg, 2 * pl), l1 = __shfl_sync(0xffffffffu, my_lg, 2 * pl + 1);
 				const double dl = l0 - l1, base = (double)n * l1;
+				// value of genotype j: H[j] + j*dl  (tag: compile-time "plane 0 of the two-plane layout")
+				auto term = [&](auto tag, const double* hp, const double* hq, int j, double jd) -> double {
+					if constexpr (decltype(tag)::value) return fma(jd, dl, (*hp + *hq) - NCs[j]);
+					else return fma(jd, dl, *hp);
+				};
 				// Shift of the log-sum-exp: the exact maximum on the first iteration, afterwards the maximum seen in the
 				// previous iteration (any shift within a few decades of the maximum gives the same sum; the fallback below
 				// repeats the unit when the assumed shift turns out more than 3 decades too high).
 				double m;
-				if (it == 0 || countlik) {  // count-based planes are rebuilt every iteration: always take the exact maximum
+				auto exact_max = [&](auto tag) {
 					m = -1e300;
 					const double* hp = Hp;
 					const double* hq = Hq;
 					double jd = 0.0, vprev = -1e300;
 					for (int j = 0; j <= nmax; j++, hp += P, hq += P, jd += 1.0) {
-						const bool in = j <= n;
-						const double v = in ? fma(jd, dl, sum2 ? (*hp + *hq) - NCs[j] : *hp) : -1e300;
-						m = fmax(m, v);
+						const bool in = NOBIDIR || j <= n;
+						const double v = in ? term(tag, hp, hq, j, jd) : -1e300;
+						m = v > m ? v : m;
 						// H[j] + j*dl is concave in j (unimodal): past the mode nothing larger follows
 						if (unimodal && __all_sync(0xffffffffu, !in || v < vprev)) break;
 						vprev = v;
 					}
+				};
+				if (it == 0 || countlik) {  // count-based planes are rebuilt every iteration: always take the exact maximum
+					if (sum2) exact_max(std::true_type{}); else exact_max(std::false_type{});
 				} else m = mprev[pl * P + ii];
 				double S = 0.0, Wj = 0.0, newmax = -1e300;
 				double T00[3] = {0, 0, 0}, T01[3] = {0, 0, 0}, T10[3] = {0, 0, 0}, T11[3] = {0, 0, 0};
-				for (int attempt = 0; attempt < 2; attempt++) {
+				auto sum_loop = [&](auto tag) {
+					const Exp10K ek = exp10_constants();
 					const double* hp = Hp;
 					const double* hq = Hq;
 					double jd = 0.0, vprev = -1e300;
 					for (int j = 0; j <= nmax; j++, hp += P, hq += P, jd += 1.0) {
-						const bool in = j <= n;
-						const double v = in ? fma(jd, dl, sum2 ? (*hp + *hq) - NCs[j] : *hp) : -1e300;
+						const bool in = NOBIDIR || j <= n;
+						const double v = in ? term(tag, hp, hq, j, jd) : -1e300;
 						const double d = v - m;
-						newmax = fmax(newmax, v);
+						newmax = v > newmax ? v : newmax;
 						if (d > -kExpCut2) {
-							const double e = exp10_lse(d);
+							const double e = exp10_lse(d, ek);
 							S += e;
 							Wj = fma(jd, e, Wj);
 							if (countlik && pl == 0) {
@@ -533,6 +561,9 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 						if (unimodal && __all_sync(0xffffffffu, !in || (v < vprev && d <= -kExpCut2))) break;
 						vprev = v;
 					}
+				};
+				for (int attempt = 0; attempt < 2; attempt++) {
+					if (sum2) sum_loop(std::true_type{}); else sum_loop(std::false_type{});
 					if (__all_sync(0xffffffffu, fabs(m - newmax) <= 3.0)) break;
 					// the stored shift was off by more than 3 decades for some pool: redo the unit with the maxima just found
 					m = newmax; S = 0.0; Wj = 0.0;
@@ -636,38 +667,58 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 				const double dl = l0 - l1, base = (double)n * l1;
 				double best = -100000, second = -100000;
 				int bg = 0;
+				// The posterior terms t[j] are concave in j (see `unimodal`): once every lane of the warp is past its mode
+				// nothing larger follows, and once it is also below the cut-off nothing that counts follows — the three
+				// passes stop there instead of walking all n+1 genotypes (the argmax, the runner-up and every term of the
+				// sums that is kept are the ones a full walk finds).
 				{
 					const double* hp = Hp;
 					const double* hq = Hq;
-					double jd = 0.0;
-					for (int j = 0; j <= n; j++, hp += P, hq += P, jd += 1.0) {
-						const double t = fma(jd, dl, NOBIDIR ? (*hp + *hq) - NCs[j] : *hp) + base;
-						if (t > best) { second = best; bg = j; best = t; }
-						else if (t > second) second = t;
+					double jd = 0.0, tprev = -1e300;
+					for (int j = 0; j <= nmax; j++, hp += P, hq += P, jd += 1.0) {
+						const bool in = j <= n;
+						const double t = in ? fma(jd, dl, NOBIDIR ? (*hp + *hq) - NCs[j] : *hp) + base : -1e300;
+						if (in) {
+							if (t > best) { second = best; bg = j; best = t; }
+							else if (t > second) second = t;
+						}
+						if (unimodal && __all_sync(0xffffffffu, !in || t < tprev)) break;
+						tprev = t;
 					}
 				}
 				// the running log-sum-exp of :168-169 equals max + log10(sum 10^(t-max)) up to rounding
 				double S = 0.0;
 				{
+					const Exp10K ek = exp10_constants();
 					const double* hp = Hp;
 					const double* hq = Hq;
-					double jd = 0.0;
-					for (int j = 0; j <= n; j++, hp += P, hq += P, jd += 1.0) {
-						const double d = fma(jd, dl, NOBIDIR ? (*hp + *hq) - NCs[j] : *hp) + base - best;
-						if (d > -kExpCut) S += exp10_lse(d);
+					double jd = 0.0, tprev = -1e300;
+					for (int j = 0; j <= nmax; j++, hp += P, hq += P, jd += 1.0) {
+						const bool in = j <= n;
+						const double t = in ? fma(jd, dl, NOBIDIR ? (*hp + *hq) - NCs[j] : *hp) + base : -1e300;
+						const double d = t - best;
+						if (in && d > -kExpCut) S += exp10_lse(d, ek);
+						if (unimodal && __all_sync(0xffffffffu, !in || (t < tprev && d <= -kExpCut))) break;
+						tprev = t;
 					}
 				}
 				const double Lb = best + log10(S);
 				{
+					const Exp10K ek = exp10_constants();
 					const double* hp = Hp;
 					const double* hq = Hq;
-					double jd = 0.0;
+					double jd = 0.0, tprev = -1e300;
+					bool tail = false;  // every lane is past its mode and below the cut-off: the rest of the column is zero
 					for (int j = 0; j <= nmax; j++, hp += P, hq += P, jd += 1.0) {
 						double v = 0.0;
-						if (act && j <= n) {
+						if (!tail) {
+							const bool in = j <= n;
 							// (NOBIDIR: the forward value is read here before this lane overwrites it with the posterior)
-							const double d = fma(jd, dl, NOBIDIR ? (*hp + *hq) - NCs[j] : *hp) + base - Lb;
-							if (d > -kExpCut - 3) v = exp10_lse(d);
+							const double t = in ? fma(jd, dl, NOBIDIR ? (*hp + *hq) - NCs[j] : *hp) + base : -1e300;
+							const double d = t - Lb;
+							if (act && in && d > -kExpCut - 3) v = exp10_lse(d, ek);
+							if (unimodal && __all_sync(0xffffffffu, !in || (t < tprev && d <= -kExpCut - 3))) tail = true;
+							tprev = t;
 						}
 						if (act) post[(size_t)j * P + ii] = v;
 					}
@@ -683,11 +734,18 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 			if (c.varpoolsize == 0) {
 				// HWE chi-square over genotype classes with expected count >= 2 (crispEM.c:187-199)
 				const int n0 = c.ploidy[0];
-				for (int j = tid; j <= n0; j += blockDim.x) {
-					double gc = 0.0;
-					for (int i = 0; i < P; i++) gc += post[(size_t)j * P + i];
-					const double ec = exp10(c.NC[j] + j * l0 + (n0 - j) * l1 + log10((double)P));
-					gcnt[j] = ec >= 2 ? (gc - ec) * (gc - ec) / ec : -1.0;
+				// expected class counts, one thread per class; then one warp per class sums the posterior over pools
+				for (int j = tid; j <= n0; j += blockDim.x) gcnt[j] = exp10(c.NC[j] + j * l0 + (n0 - j) * l1 + log10((double)P));
+				__syncthreads();
+				for (int j = warp; j <= n0; j += nwarps) {
+					const double ec = gcnt[j];
+					if (ec >= 2) {
+						double gc = 0.0;
+						for (int i = lane; i < P; i += 32) gc += post[(size_t)j * P + i];
+						gc = warp_sum(gc);
+						__syncwarp();
+						if (lane == 0) gcnt[j] = (gc - ec) * (gc - ec) / ec;
+					} else if (lane == 0) gcnt[j] = -1.0;
 				}
 				__syncthreads();
 				if (tid == 0) {
@@ -765,16 +823,23 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 			const uint32_t alo = b.alt_off ? b.alt_off[s * kSlots + slot] : 0, ahi = b.alt_off ? b.alt_off[s * kSlots + slot + 1] : 0;
 			const int MR = c.min_reads;
 			int vpl = 0;
+			// first entry of every pool in the (pool-sorted) alt-read list of this slot, built by one pass over the list;
+			// the array aliases the log-sum-exp shifts, which the EM no longer needs
+			int32_t* astart = reinterpret_cast<int32_t*>(mprev);
+			if (ahi > alo) {
+				__syncthreads();
+				for (uint32_t e = alo + tid; e < ahi; e += blockDim.x) {
+					const int pe = b.alt_reads[e].pool, pp = e > alo ? (int)b.alt_reads[e - 1].pool : -1;
+					for (int q = pp + 1; q <= pe; q++) astart[q] = (int32_t)e;
+					if (e == ahi - 1) for (int q = pe + 1; q <= P; q++) astart[q] = (int32_t)ahi;
+				}
+				__syncthreads();
+			}
 			for (int i = warp; i < P; i += nwarps) {
 				const int f = cnt6[3 * P + i], r = cnt6[4 * P + i], bd = cnt6[5 * P + i];
 				if (f + r + bd < 2) continue;
-				// entries of this pool (list is sorted by pool): lower bounds by binary search
-				uint32_t lo = alo, hi = ahi;
-				while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (b.alt_reads[mid].pool < i) lo = mid + 1; else hi = mid; }
-				uint32_t e0 = lo;
-				hi = ahi;
-				while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (b.alt_reads[mid].pool <= i) lo = mid + 1; else hi = mid; }
-				int m = (int)(lo - e0);
+				const uint32_t e0 = ahi > alo ? (uint32_t)astart[i] : alo;
+				int m = ahi > alo ? astart[i + 1] - astart[i] : 0;
 				if (m > f + r + bd) m = f + r + bd;  // `i < reads` cap, allelecounts.c:53
 				int uq = 0, mid = 0;
 				for (int e = lane; e < m; e += 32) {
