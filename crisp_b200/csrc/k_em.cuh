@@ -279,7 +279,7 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 					const double bf = (kin && jcol < J) ? Ts[wd * J + jcol] : 0.0;
 #pragma unroll
 					for (int cls = 0; cls < NCLS; cls++) {
-						const double af = (kin && prow < P) ? (double)dh[(wd * 3 + cls) * P + prow] : 0.0;
+						const double af = (kin && prow < P) ? u32_to_double(dh[(wd * 3 + cls) * P + prow]) : 0.0;
 						asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
 						             : "+d"(acc[cls][0]), "+d"(acc[cls][1]) : "d"(af), "d"(bf));
 					}
@@ -328,7 +328,7 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 							const int which = base == a1 ? 0 : (base == a2 ? 1 : -1);
 							if (which < 0) continue;
 							const int cls = (e >> 11) & 1 ? 2 : ((e >> 10) & 1);
-							const double cntv = (double)(e >> 16);
+							const double cntv = u32_to_double(e >> 16);
 							const double* Tr = Tp + ((size_t)which * kNQ + (e & 0x7f)) * J + lane;
 							double t[4];
 #pragma unroll
@@ -358,7 +358,7 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 								const int which = base == a1 ? 0 : (base == a2 ? 1 : -1);
 								if (which < 0 || j > n) continue;
 								const int cls = (e >> 11) & 1 ? 2 : ((e >> 10) & 1);
-								const double t = (double)(e >> 16) * __ldg(Tp + ((size_t)which * kNQ + (e & 0x7f)) * J + j);
+								const double t = u32_to_double(e >> 16) * __ldg(Tp + ((size_t)which * kNQ + (e & 0x7f)) * J + j);
 								a3[0] += cls == 0 ? t : 0.0;
 								a3[1] += cls == 1 ? t : 0.0;
 								a3[2] += cls == 2 ? t : 0.0;
@@ -424,7 +424,7 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 								while (m) {
 									const int bq = __ffs(m) - 1;
 									m &= m - 1;
-									const double cntv = (double)__shfl_sync(0xffffffffu, hv, bq);
+									const double cntv = u32_to_double(__shfl_sync(0xffffffffu, hv, bq));
 									const double* Tr = Tw + (size_t)(qc + bq) * J;
 #pragma unroll
 									for (int jc = 0; jc < 4; jc++)
@@ -628,35 +628,34 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 			}
 			if ((it >= 2 && d0 <= 0.0001 && d1 <= 0.01 && d2 <= 0.01) || it >= 1000) break;
 		}
-		if (warp == 0) {
-			if (lane < 3) { sh->LL[lane] = my_LL; sh->p[lane] = my_p; }
-			if (lane == 0) { sh->LLnull0 = LLnull0; sh->iter = it; }
-		}
-		__syncthreads();
-
 		// =====================================================================================================
-		// statistics of the fit (crispEM.c:321-349)
+		// statistics of the fit (crispEM.c:321-349) — every warp holds the same iteration state (lane pl = plane pl), so every
+		// thread evaluates them: no hand-over through shared memory, no barrier.  (The planes were last read before the
+		// barrier that closed the final iteration, so the genotype phase below may overwrite them.)
 		// =====================================================================================================
-		if (tid == 0) {
-			const double LLt = sh->LL[0], LLf = sh->LL[1], LLr = sh->LL[2];
-			const double deltaf = (LLf > LLr) ? LLf - LLt - log10(2.0) : LLr - LLt - log10(2.0);
+		double delta, deltaf, pfin;
+		{
+			const double LLt = __shfl_sync(0xffffffffu, my_LL, 0), LLf = __shfl_sync(0xffffffffu, my_LL, 1), LLr = __shfl_sync(0xffffffffu, my_LL, 2);
+			pfin = __shfl_sync(0xffffffffu, my_p, 0);
+			deltaf = (LLf > LLr) ? LLf - LLt - log10(2.0) : LLr - LLt - log10(2.0);
 			const double ALPHA = c.alpha_prior;
-			const double LLrefadd = sh->LLnull0 + log10(1.0 - ALPHA);
+			const double LLrefadd = LLnull0 + log10(1.0 - ALPHA);
 			double LL = LLt + log10(ALPHA);
 			if (LLrefadd < LL) LL += log10(1.0 + exp10(LLrefadd - LL));
 			else LL = LLrefadd + log10(1.0 + exp10(LL - LLrefadd));
-			sh->delta = LL - LLrefadd;
-			sh->deltaf = deltaf;
-			sh->hwe = 0.0;
+			delta = LL - LLrefadd;
+			if (tid == 0) sh->hwe = 0.0;
 		}
-		__syncthreads();
-		const double delta = sh->delta, pfin = sh->p[0];
 		const bool called = delta >= 2;
 		int varpools = 0;
 		if (called) {
 			// ---- calculate_genotypes: argmax / runner-up per pool, posterior genotype counts, HWE ----
 			const double l0 = log10(pfin), l1 = log10(1.0 - pfin);
 			double* post = Gf;  // forward plane is no longer needed: reuse as posterior[j][pool]
+			// with more warps than rounds of pools the genotype pass occupies `rounds` warps; the others run the pool statistics
+			// (which read the counts and the alt-read list only) at the same time instead of waiting at the barrier
+			const int gw = rounds < nwarps ? rounds : 0;
+			if (gw == 0 || warp < gw)
 			for (int rd = warp; rd < rounds; rd += nwarps) {
 				const int i = rd * 32 + lane;
 				const bool act = i < P;
@@ -729,6 +728,54 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 				}
 				const int vp = warp_sum(act && bg > 0 ? 1 : 0), acs = warp_sum(act ? bg : 0);
 				if (lane == 0) { part_i[rd] = vp; part_i[rounds + rd] = acs; }
+			}
+			if (gw == 0) __syncthreads();
+			// ---- calculate_pool_statistics: read-evidence filter per pool ----
+			const uint32_t alo = b.alt_off ? b.alt_off[s * kSlots + slot] : 0, ahi = b.alt_off ? b.alt_off[s * kSlots + slot + 1] : 0;
+			const int MR = c.min_reads;
+			int vpl = 0;
+			if (gw == 0 || warp >= gw) {
+			const int w0 = gw, nw = nwarps - gw, gt = tid - gw * 32, gn = nw * 32;  // the warps of this phase, as a group
+			auto group_sync = [&]() {
+				if (gw == 0) __syncthreads();
+				else asm volatile("bar.sync 1, %0;" ::"r"(gn) : "memory");
+			};
+			// first entry of every pool in the (pool-sorted) alt-read list of this slot, built by one pass over the list;
+			// the array aliases the log-sum-exp shifts, which the EM no longer needs
+			int32_t* astart = reinterpret_cast<int32_t*>(mprev);
+			if (ahi > alo) {
+				for (uint32_t e = alo + gt; e < ahi; e += gn) {
+					const int pe = b.alt_reads[e].pool, pp = e > alo ? (int)b.alt_reads[e - 1].pool : -1;
+					for (int q = pp + 1; q <= pe; q++) astart[q] = (int32_t)e;
+					if (e == ahi - 1) for (int q = pe + 1; q <= P; q++) astart[q] = (int32_t)ahi;
+				}
+				group_sync();
+			}
+			for (int i = warp - w0; i < P; i += nw) {
+				const int f = cnt6[3 * P + i], r = cnt6[4 * P + i], bd = cnt6[5 * P + i];
+				if (f + r + bd < 2) continue;
+				const uint32_t e0 = ahi > alo ? (uint32_t)astart[i] : alo;
+				int m = ahi > alo ? astart[i + 1] - astart[i] : 0;
+				if (m > f + r + bd) m = f + r + bd;  // `i < reads` cap, allelecounts.c:53
+				int uq = 0, mid = 0;
+				for (int e = lane; e < m; e += 32) {
+					const crispgpu_altread x = b.alt_reads[e0 + e];
+					bool first = true;
+					for (int e2 = 0; e2 < e; e2++) {
+						const crispgpu_altread y = b.alt_reads[e0 + e2];
+						if (y.strand == x.strand && y.offset == x.offset) { first = false; break; }
+					}
+					uq += first ? 1 : 0;
+					if (x.offset >= 5 && (int)x.aligned - (int)x.offset >= 5) mid++;
+				}
+				uq = warp_sum(uq);
+				mid = warp_sum(mid);
+				if (m == 0) uq = 1;  // *unique starts at 1 (allelecounts.c:45)
+				int varpool = 0;
+				if (f + r + bd >= MR && mid > 0 && uq >= MR - 1) varpool = 1;
+				else if (f + r + bd >= MR - 1 && f + bd > 0 && r + bd > 0 && mid > 0 && uq >= MR - 1) varpool = 1;
+				vpl += varpool;
+			}
 			}
 			__syncthreads();
 			if (c.varpoolsize == 0) {
@@ -819,47 +866,6 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 				}
 				__syncthreads();
 			}
-			// ---- calculate_pool_statistics: read-evidence filter per pool ----
-			const uint32_t alo = b.alt_off ? b.alt_off[s * kSlots + slot] : 0, ahi = b.alt_off ? b.alt_off[s * kSlots + slot + 1] : 0;
-			const int MR = c.min_reads;
-			int vpl = 0;
-			// first entry of every pool in the (pool-sorted) alt-read list of this slot, built by one pass over the list;
-			// the array aliases the log-sum-exp shifts, which the EM no longer needs
-			int32_t* astart = reinterpret_cast<int32_t*>(mprev);
-			if (ahi > alo) {
-				__syncthreads();
-				for (uint32_t e = alo + tid; e < ahi; e += blockDim.x) {
-					const int pe = b.alt_reads[e].pool, pp = e > alo ? (int)b.alt_reads[e - 1].pool : -1;
-					for (int q = pp + 1; q <= pe; q++) astart[q] = (int32_t)e;
-					if (e == ahi - 1) for (int q = pe + 1; q <= P; q++) astart[q] = (int32_t)ahi;
-				}
-				__syncthreads();
-			}
-			for (int i = warp; i < P; i += nwarps) {
-				const int f = cnt6[3 * P + i], r = cnt6[4 * P + i], bd = cnt6[5 * P + i];
-				if (f + r + bd < 2) continue;
-				const uint32_t e0 = ahi > alo ? (uint32_t)astart[i] : alo;
-				int m = ahi > alo ? astart[i + 1] - astart[i] : 0;
-				if (m > f + r + bd) m = f + r + bd;  // `i < reads` cap, allelecounts.c:53
-				int uq = 0, mid = 0;
-				for (int e = lane; e < m; e += 32) {
-					const crispgpu_altread x = b.alt_reads[e0 + e];
-					bool first = true;
-					for (int e2 = 0; e2 < e; e2++) {
-						const crispgpu_altread y = b.alt_reads[e0 + e2];
-						if (y.strand == x.strand && y.offset == x.offset) { first = false; break; }
-					}
-					uq += first ? 1 : 0;
-					if (x.offset >= 5 && (int)x.aligned - (int)x.offset >= 5) mid++;
-				}
-				uq = warp_sum(uq);
-				mid = warp_sum(mid);
-				if (m == 0) uq = 1;  // *unique starts at 1 (allelecounts.c:45)
-				int varpool = 0;
-				if (f + r + bd >= MR && mid > 0 && uq >= MR - 1) varpool = 1;
-				else if (f + r + bd >= MR - 1 && f + bd > 0 && r + bd > 0 && mid > 0 && uq >= MR - 1) varpool = 1;
-				vpl += varpool;
-			}
 			// combine per-warp pool counts
 			__syncthreads();
 			if (lane == 0) sh->part_w[warp] = vpl;
@@ -870,9 +876,9 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 		if (tid == 0) {
 			prm.o.af_ml[o] = pfin;
 			prm.o.delta[o] = delta;
-			prm.o.deltaf[o] = sh->deltaf;
+			prm.o.deltaf[o] = deltaf;
 			prm.o.hwe[o] = sh->hwe;
-			prm.o.em_iters[o] = sh->iter;
+			prm.o.em_iters[o] = it;
 			prm.o.call_row[o] = called ? task : -1;
 			if (called) {
 				int vp = 0, acs = 0;
