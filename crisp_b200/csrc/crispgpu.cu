@@ -700,7 +700,7 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 		const bool scanned = g.em_flag >= 1 && g.use_base_qvs == 1 && (ctx->n_reads > 0 || (ctx->binned && ctx->n_bins > 0));
 		const bool nobidir = scanned && hc[10] == 0 && ctx->class_ploidy.size() == 1 && !(g.association == 1 && ctx->d_pheno.p);
 		ctx->nobidir = nobidir ? 1 : 0;
-		const int key = (dense ? nq : 0) + (nobidir ? 64 : 0);
+		const int key = (dense ? nq : 0) + (nobidir ? 64 : 0) + (ctx->bins_direct ? 128 : 0);
 		if (key != ctx->em_key) {
 			ctx->em_key = key;
 			ctx->em_grid = 0;
@@ -752,6 +752,10 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 			const bool g3 = ctx->em_smem_g, g2 = ctx->em_smem_g2;
 			// quality-value likelihood tasks (two-plane kernel when the batch allows it) ...
 			if (ctx->nobidir) {
+				static const size_t pad = getenv("CRISPGPU_EM_PAD_SMEM") ? (size_t)atoi(getenv("CRISPGPU_EM_PAD_SMEM")) : 0;  // occupancy experiment
+				static const bool generic = getenv("CRISPGPU_EM_GENERIC") != nullptr;  // measurement switch
+				if (g2 && ctx->dense_lik && ctx->bins_direct && !generic) rc = launch_em(k_em<true, false, false, true, 1>, l1, ctx->n_call1, cnt + 3, 0, sm2 + pad, true, &ctx->em_grid2);
+				else
 				rc = g2 ? launch_em(k_em<true, false, false, true>, l1, ctx->n_call1, cnt + 3, 0, sm2, true, &ctx->em_grid2)
 				        : launch_em(k_em<false, false, false, true>, l1, ctx->n_call1, cnt + 3, 0, sm2, false, &ctx->em_grid2);
 			} else if (g3) {

@@ -46,7 +46,10 @@ struct EmShared {
 // tasks[0..n_tasks): the (site, slot) list of this launch; head: its work counter; row0: first AC/QV row of the list
 // NOBIDIR: the batch has no bidirectional (overlapping-mate) reads and one pool size: the all-reads plane is not stored
 // (it equals forward + reverse - NC), two planes instead of three -> one more CTA per SM (or planes that fit at all)
-template <bool SMEM_G, bool ASSOC, bool COUNTLIK, bool NOBIDIR>
+// LIK: 0 = the likelihood path (dense / sparse, bins / reads) is chosen at run time; 1 = compiled for the dense path on a
+// compact batch alone (binned-quality data in the (value, count) format: the benchmark's case) — a third of the code,
+// fewer registers
+template <bool SMEM_G, bool ASSOC, bool COUNTLIK, bool NOBIDIR, int LIK = 0>
 __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int32_t* __restrict__ tasks, int n_tasks, int32_t* head, int row0)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -65,7 +68,8 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 	int32_t* cnt6 = reinterpret_cast<int32_t*>(smem_raw + off); off += sizeof(int32_t) * 6 * P;   // [6][P]: a1 f,r,b ; a2 f,r,b
 	off = (off + 15) & ~size_t(15);
 	const int nq = c.nq;
-	const bool dense = c.dense_lik != 0;
+	const bool dense = LIK == 1 || c.dense_lik != 0;
+	const bool has_bins = LIK == 1 || b.bins != nullptr;
 	// sparse path: one 16-bit histogram [6][128] per warp; dense path: one 32-bit histogram [allele][quality][class][pool]
 	uint16_t* hist = reinterpret_cast<uint16_t*>(smem_raw + off);
 	uint32_t* dh = reinterpret_cast<uint32_t*>(smem_raw + off);
@@ -173,7 +177,7 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 		uint32_t* boff = reinterpret_cast<uint32_t*>(mprev);
 		if (!COUNTLIK && dense) {
 			for (int k = tid; k < 2 * nq * 3 * P; k += blockDim.x) dh[k] = 0;
-			if (b.bins) for (int i = tid; i <= P; i += blockDim.x) boff[i] = b.bin_off[(size_t)s * P + i];
+			if (has_bins) for (int i = tid; i <= P; i += blockDim.x) boff[i] = b.bin_off[(size_t)s * P + i];
 		}
 		__syncthreads();
 
@@ -222,7 +226,7 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 			// calculate_pooled_likelihoods_snp, dense form (few distinct qualities, one pool size).
 			// (1) per pool (one warp) bin the packed reads into dh[allele][quality][class][pool];
 			// (2) contract with the staged table rows on the FP64 tensor cores (see below).
-			if (b.bins) {
+			if (has_bins) {
 				// compact input: the (value, count) bins are the histogram already — one shared-memory add per bin.  The bins of
 				// a site are contiguous: every thread takes bins of the flat range (all loads independent, one memory latency
 				// for the site) and finds the pool of a bin in the staged offsets.
@@ -269,28 +273,38 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 			// D[row = lane/4][col = 2 (lane%4) + {0,1}].
 			const int ptiles = (P + 7) >> 3, jtiles = (J + 7) >> 3, ksteps = (2 * nq + 3) >> 2;
 			constexpr int NCLS = NOBIDIR ? 2 : 3;  // no bidirectional reads: that class is empty
+			// Rows / columns beyond the table are clamped (their results are not stored) and a bin index beyond 2 nq gets a
+			// zero B element, so the inner loop carries no bounds predicates; (pt, jt) advance without a division.
+			const int kk = lane & 3, g8 = lane >> 2;
+			int pt = warp / jtiles, jt = warp - pt * jtiles;
 			for (int item = warp; item < ptiles * jtiles; item += nwarps) {
-				const int pt = item / jtiles, jt = item - pt * jtiles;
-				const int prow = pt * 8 + (lane >> 2), jcol = jt * 8 + (lane >> 2), kk = lane & 3;
+				const int prow = pt * 8 + g8, jcol = jt * 8 + g8;
+				const uint32_t* dhp = dh + (prow < P ? prow : P - 1);
+				const double* tsp = Ts + (jcol < J ? jcol : J - 1);
 				double acc[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
 				for (int ks = 0; ks < ksteps; ks++) {
 					const int wd = ks * 4 + kk;
 					const bool kin = wd < 2 * nq;
-					const double bf = (kin && jcol < J) ? Ts[wd * J + jcol] : 0.0;
+					const int wdc = kin ? wd : 0;
+					const double tv = tsp[wdc * J];
+					const double bf = kin ? tv : 0.0;
 #pragma unroll
 					for (int cls = 0; cls < NCLS; cls++) {
-						const double af = (kin && prow < P) ? u32_to_double(dh[(wd * 3 + cls) * P + prow]) : 0.0;
+						const double af = u32_to_double(dhp[(wdc * 3 + cls) * P]);
 						asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
 						             : "+d"(acc[cls][0]), "+d"(acc[cls][1]) : "d"(af), "d"(bf));
 					}
 				}
+				const int jt_store = jt;
+				jt += nwarps;
+				while (jt >= jtiles) { jt -= jtiles; pt++; }
 				const int i = prow;
 				if (i < P) {
 #pragma unroll
 					for (int t = 0; t < 2; t++) {
-						const int j = jt * 8 + kk * 2 + t;
+						const int j = jt_store * 8 + kk * 2 + t;
 						if (j < J) {
-							const double nc = c.NC[j];
+							const double nc = NOBIDIR ? NCs[j] : c.NC[j];
 							const size_t idx = (size_t)j * P + i;
 							Gf[idx] = acc[0][t] + nc;
 							Gr[idx] = acc[1][t] + nc;
@@ -315,7 +329,7 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 				for (int cls = 0; cls < 3; cls++)
 #pragma unroll
 					for (int jc = 0; jc < 4; jc++) acc[cls][jc] = 0.0;
-				if (b.bins) {
+				if (has_bins) {
 					// compact input: every (value, count) bin of the cell is one term count * T[allele][quality][j] — no histogram,
 					// no folding; the bin is broadcast and each lane updates its genotypes
 					const uint32_t b0 = b.bin_off[(size_t)s * P + i], b1 = b.bin_off[(size_t)s * P + i + 1];
@@ -483,12 +497,10 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 		double my_p = sh->p[0], my_LL = 0.0, LLnull0 = 0.0;
 		int it = 0;
 		for (;;) {
-			// log10 p and log10(1-p) of the three planes in ONE call per warp: lane 2*pl holds p, lane 2*pl+1 holds 1-p
-			double my_lg;
-			{
-				const double pp = __shfl_sync(0xffffffffu, my_p, (lane >> 1) < 3 ? (lane >> 1) : 0);
-				my_lg = log10((lane & 1) ? 1.0 - pp : pp);
-			}
+			// log10 p / log10(1-p) per plane: published in shared memory by the warp that closed the previous iteration; for the
+			// first iteration every warp takes them from the starting frequency (lane 0: p, lane 1: 1-p; the planes start equal)
+			double first_lg = 0.0;
+			if (it == 0) first_lg = log10((lane & 1) ? 1.0 - my_p : my_p);
 			double* part = part_base + (it & 1) * 19 * rounds;
 			const int nunits = rounds * 3;
 			for (int u = warp; u < nunits; u += nwarps) {
@@ -501,7 +513,8 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 				const bool sum2 = NOBIDIR && pl == 0;
 				const double* Hp = (NOBIDIR ? (pl == 2 ? Gr : Gf) : G + (size_t)pl * plane) + ii;
 				const double* Hq = Gr + ii;
-				const double l0 = __shfl_sync(0xffffffffu, my_lg, 2 * pl), l1 = __shfl_sync(0xffffffffu, my_lg, 2 * pl + 1);
+				const double l0 = it == 0 ? __shfl_sync(0xffffffffu, first_lg, 0) : sh->lp[pl][0];
+				const double l1 = it == 0 ? __shfl_sync(0xffffffffu, first_lg, 1) : sh->lp[pl][1];
 				const double dl = l0 - l1, base = (double)n * l1;
 				// value of genotype j: H[j] + j*dl  (tag: compile-time "plane 0 of the two-plane layout")
 				auto term = [&](auto tag, const double* hp, const double* hq, int j, double jd) -> double {
@@ -529,7 +542,7 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 				if (it == 0 || countlik) {  // count-based planes are rebuilt every iteration: always take the exact maximum
 					if (sum2) exact_max(std::true_type{}); else exact_max(std::false_type{});
 				} else m = mprev[pl * P + ii];
-				double S = 0.0, Wj = 0.0, newmax = -1e300;
+				double S = 0.0, Wj = 0.0;
 				double T00[3] = {0, 0, 0}, T01[3] = {0, 0, 0}, T10[3] = {0, 0, 0}, T11[3] = {0, 0, 0};
 				auto sum_loop = [&](auto tag) {
 					const Exp10K ek = exp10_constants();
@@ -540,7 +553,6 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 						const bool in = NOBIDIR || j <= n;
 						const double v = in ? term(tag, hp, hq, j, jd) : -1e300;
 						const double d = v - m;
-						newmax = v > newmax ? v : newmax;
 						if (d > -kExpCut2) {
 							const double e = exp10_lse(d, ek);
 							S += e;
@@ -562,17 +574,24 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 						vprev = v;
 					}
 				};
-				for (int attempt = 0; attempt < 2; attempt++) {
+				// The shift kept for the next iteration is this iteration's log-sum-exp itself (within log10(n+1) decades above
+				// the maximum).  A stored shift is good while the sum it produces stays within three decades of 1; otherwise (the
+				// frequency moved a lot, or the sum underflowed to zero) the unit is redone with the corrected shift.
+				double lS = 0.0;
+				for (int attempt = 0; attempt < 3; attempt++) {
 					if (sum2) sum_loop(std::true_type{}); else sum_loop(std::false_type{});
-					if (__all_sync(0xffffffffu, fabs(m - newmax) <= 3.0)) break;
-					// the stored shift was off by more than 3 decades for some pool: redo the unit with the maxima just found
-					m = newmax; S = 0.0; Wj = 0.0;
+					lS = log10(S);
+					if (__all_sync(0xffffffffu, fabs(lS) <= 3.0)) break;   // false for S = 0 (-inf) and NaN as well
+					if (__any_sync(0xffffffffu, !(S > 0.0) || !(fabs(lS) < 1e300))) {
+						if (sum2) exact_max(std::true_type{}); else exact_max(std::false_type{});
+					} else m += lS;
+					S = 0.0; Wj = 0.0;
 #pragma unroll
 					for (int k = 0; k < 3; k++) { T00[k] = T01[k] = T10[k] = T11[k] = 0.0; }
 				}
-				if (act) mprev[pl * P + ii] = newmax;
+				if (act) mprev[pl * P + ii] = m + lS;
 				m += base;
-				double L = m + log10(S);
+				double L = m + lS;
 				double llc = 0.0, pn = 0.0, nul = 0.0;
 				if (act) {
 					llc = L;
@@ -599,53 +618,64 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 				}
 			}
 			__syncthreads();
-			// ---- finish the iteration (every warp, identically): lane pl handles plane pl ----
-			double LLn = 0.0, pn = 0.0;
-			if (lane < 3) {
-				for (int r = 0; r < rounds; r++) { LLn += part[lane * rounds + r]; pn += part[(3 + lane) * rounds + r]; }
-				pn /= c.K;
-				if (pn < kMinP) pn = kMinP;
-				if (1.0 - pn <= kMinP) pn = 1.0 - kMinP;
-			}
-			// convergence: fabsf() of the double differences against double thresholds (crispEM.c:304)
-			const double dconv = (double)fabsf((float)(LLn - my_LL));
-			const double d0 = __shfl_sync(0xffffffffu, dconv, 0), d1 = __shfl_sync(0xffffffffu, dconv, 1), d2 = __shfl_sync(0xffffffffu, dconv, 2);
-			my_LL = LLn;
-			my_p = lane < 3 ? pn : 0.5;
-			it++;
-			LLnull0 = 0.0;
-			for (int r = 0; r < rounds; r++) LLnull0 += part[6 * rounds + r];
-			if (countlik) {
-				for (int k = 0; k < 3; k++) {
+			// ---- finish the iteration: ONE warp (lane pl handles plane pl) reduces the partial sums, applies the clamps and the
+			// convergence test and publishes log10 p / log10(1-p) for the next iteration — or, on the last one, the statistics of
+			// the fit — through shared memory.  The other warps wait at the barrier below instead of repeating ~300 instructions
+			// each per iteration (a third of the EM's issue slots in the replicated version).
+			if (warp == 0) {
+				double LLn = 0.0, pn = 0.0;
+				if (lane < 3) {
+					for (int r = 0; r < rounds; r++) { LLn += part[lane * rounds + r]; pn += part[(3 + lane) * rounds + r]; }
+					pn /= c.K;
+					if (pn < kMinP) pn = kMinP;
+					if (1.0 - pn <= kMinP) pn = 1.0 - kMinP;
+				}
+				// convergence: fabsf() of the double differences against double thresholds (crispEM.c:304)
+				const double dconv = (double)fabsf((float)(LLn - my_LL));
+				const double d0 = __shfl_sync(0xffffffffu, dconv, 0), d1 = __shfl_sync(0xffffffffu, dconv, 1), d2 = __shfl_sync(0xffffffffu, dconv, 2);
+				my_LL = LLn;
+				my_p = lane < 3 ? pn : 0.5;
+				LLnull0 = 0.0;
+				for (int r = 0; r < rounds; r++) LLnull0 += part[6 * rounds + r];
+				if (countlik && lane < 3) {
+					const int k = lane;
 					double t00 = 0, t01 = 0, t10 = 0, t11 = 0;
 					for (int r = 0; r < rounds; r++) { t00 += part[(7 + k) * rounds + r]; t01 += part[(10 + k) * rounds + r]; t10 += part[(13 + k) * rounds + r]; t11 += part[(16 + k) * rounds + r]; }
 					double e01 = (t01 + 1.5 - 1) / (t01 + t00 + 1.5 + 50 - 1), e10 = (t10 + 1.5 - 1) / (t10 + t11 + 50 + 1.5 - 1);
 					if (e10 > 0.05) e10 = 0.05;
-					E01[k] = e01;
-					E10[k] = e10;
+					sh->E01[k] = e01;
+					sh->E10[k] = e10;
 				}
+				const bool stop = (it + 1 >= 2 && d0 <= 0.0001 && d1 <= 0.01 && d2 <= 0.01) || it + 1 >= 1000;
+				if (!stop) {
+					const double pp = __shfl_sync(0xffffffffu, my_p, (lane >> 1) < 3 ? (lane >> 1) : 0);
+					const double lg = log10((lane & 1) ? 1.0 - pp : pp);   // lane 2 pl: log10 p, lane 2 pl + 1: log10(1-p)
+					if (lane < 6) sh->lp[lane >> 1][lane & 1] = lg;
+				} else {
+					// statistics of the fit (crispEM.c:321-349)
+					const double LLt = __shfl_sync(0xffffffffu, my_LL, 0), LLf = __shfl_sync(0xffffffffu, my_LL, 1), LLr = __shfl_sync(0xffffffffu, my_LL, 2);
+					const double pf = __shfl_sync(0xffffffffu, my_p, 0);
+					const double df = (LLf > LLr) ? LLf - LLt - log10(2.0) : LLr - LLt - log10(2.0);
+					const double ALPHA = c.alpha_prior;
+					const double LLrefadd = LLnull0 + log10(1.0 - ALPHA);
+					double LL = LLt + log10(ALPHA);
+					if (LLrefadd < LL) LL += log10(1.0 + exp10(LLrefadd - LL));
+					else LL = LLrefadd + log10(1.0 + exp10(LL - LLrefadd));
+					if (lane == 0) { sh->delta = LL - LLrefadd; sh->deltaf = df; sh->p[0] = pf; sh->hwe = 0.0; sh->iter = it + 1; }
+				}
+				if (lane == 0) sh->exitflag = stop ? 1 : 0;
+			}
+			__syncthreads();
+			it++;
+			if (countlik) {
+				for (int k = 0; k < 3; k++) { E01[k] = sh->E01[k]; E10[k] = sh->E10[k]; }
 				count_likelihood();  // crispEM.c:298, also on the exit iteration
 			}
-			if ((it >= 2 && d0 <= 0.0001 && d1 <= 0.01 && d2 <= 0.01) || it >= 1000) break;
+			if (sh->exitflag) break;
 		}
-		// =====================================================================================================
-		// statistics of the fit (crispEM.c:321-349) — every warp holds the same iteration state (lane pl = plane pl), so every
-		// thread evaluates them: no hand-over through shared memory, no barrier.  (The planes were last read before the
-		// barrier that closed the final iteration, so the genotype phase below may overwrite them.)
-		// =====================================================================================================
-		double delta, deltaf, pfin;
-		{
-			const double LLt = __shfl_sync(0xffffffffu, my_LL, 0), LLf = __shfl_sync(0xffffffffu, my_LL, 1), LLr = __shfl_sync(0xffffffffu, my_LL, 2);
-			pfin = __shfl_sync(0xffffffffu, my_p, 0);
-			deltaf = (LLf > LLr) ? LLf - LLt - log10(2.0) : LLr - LLt - log10(2.0);
-			const double ALPHA = c.alpha_prior;
-			const double LLrefadd = LLnull0 + log10(1.0 - ALPHA);
-			double LL = LLt + log10(ALPHA);
-			if (LLrefadd < LL) LL += log10(1.0 + exp10(LLrefadd - LL));
-			else LL = LLrefadd + log10(1.0 + exp10(LL - LLrefadd));
-			delta = LL - LLrefadd;
-			if (tid == 0) sh->hwe = 0.0;
-		}
+		// (the planes were last read before the barriers that closed the final iteration: the genotype phase may overwrite them)
+		const double delta = sh->delta, deltaf = sh->deltaf, pfin = sh->p[0];
+		it = sh->iter;
 		const bool called = delta >= 2;
 		int varpools = 0;
 		if (called) {

@@ -34,9 +34,10 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise EngineError(f"{LIB_PATH} is missing: build it with `python -m crisp_b200.build` (there is no CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    path = os.environ.get("CRISPGPU_LIB", LIB_PATH)   # the same override host/crisp_frontend.c honours (A/B measurements)
+    if not os.path.exists(path):
+        raise EngineError(f"{path} is missing: build it with `python -m crisp_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(path)
     lib.crispgpu_config_defaults.argtypes = [C.POINTER(Config)]
     lib.crispgpu_config_defaults.restype = None
     lib.crispgpu_create.argtypes = [C.POINTER(Config), C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
