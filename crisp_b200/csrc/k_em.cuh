@@ -21,7 +21,10 @@
 namespace crisp {
 
 constexpr int kEmMaxWarps = 8;
-constexpr double kExpCut2 = 24.0;  // cut-off used with an approximate log-sum-exp shift (leaves >= 20 decades of margin)
+// cut-off of the EM sums: a stored shift is accepted while it lies within 3 decades of the current log-sum-exp, so every
+// term above 10^-18 of the sum is kept — dropped terms total less than a fiftieth of an ulp of the sum
+constexpr double kExpCut2 = 21.0;
+constexpr uint32_t kCutHi = 0xC0350000u;  // high word of -21.0
 constexpr int kMaxRounds = 64;  // pools <= 2048
 
 struct EmShared {
@@ -553,7 +556,10 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 						const bool in = NOBIDIR || j <= n;
 						const double v = in ? term(tag, hp, hq, j, jd) : -1e300;
 						const double d = v - m;
-						if (d > -kExpCut2) {
+						// d > -cut on the integer pipe: the high word of a double, as unsigned, orders like -value for negatives and
+						// sits below 0x80000000 for positives (the low word decides nothing that matters for a cut-off)
+						const bool live = (uint32_t)__double2hiint(d) < kCutHi;
+						if (live) {
 							const double e = exp10_lse(d, ek);
 							S += e;
 							Wj = fma(jd, e, Wj);
@@ -570,7 +576,7 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 							}
 						}
 						// descending and below the cut-off for every lane: the remaining terms are smaller still
-						if (unimodal && __all_sync(0xffffffffu, !in || (v < vprev && d <= -kExpCut2))) break;
+						if (unimodal && __all_sync(0xffffffffu, !in || (v < vprev && !live))) break;
 						vprev = v;
 					}
 				};
