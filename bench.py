@@ -38,7 +38,19 @@ WORKLOADS = {
     # config 5 with the permutation test on: pool size 10 dispatches to the stranded test, pool size 2 to lowcovFET
     "c5_500x10_perm": dict(P=500, ploidy=10, depth=10, options=dict(chisq_permutation=1, max_iter=20000), synth=dict(variant_frac=0.3)),
     "c5p_500x2_lowcov": dict(P=500, ploidy=2, depth=10, options=dict(chisq_permutation=1, max_iter=20000), synth=dict(variant_frac=0.5)),
+    # config 4 exactly as BASELINE.json words it: --perms 1,000,000 with --ctpval -6; --ctpval is consumed only by the
+    # --EM 0 caller (crisp/oldcrispmethod.c:170), so this is that path: em_flag=0, thresh1=-6
+    "c4_perm_stress_em0": dict(P=50, ploidy=48, depth=200, options=dict(chisq_permutation=1, max_iter=1000000, em_flag=0, thresh1=-6.0),
+                               synth=dict(variant_frac=0.8, rare=True, with_stats=True, with_qhigh=True)),
+    # config 2 with a 40-valued quality spectrum (older instruments): the likelihood takes the sparse path, bins barely compress
+    "exome50x48_q40": dict(P=50, ploidy=48, depth=200, options={}, synth=dict(variant_frac=0.15, quals=range(2, 42))),
 }
+
+# the other BASELINE configs, measured at reduced size inside the default run: (workload, sites, reference sites per core)
+SIDE_CONFIGS = [
+    ("c1_10x20_perm", 1024, 24), ("c3_100x96", 1024, 16), ("c4_perm_stress", 1024, 1), ("c4_perm_stress_em0", 1024, 1),
+    ("c5_500x10", 1024, 16), ("c5_500x10_perm", 512, 2), ("c5p_500x2_lowcov", 512, 2), ("exome50x48_q40", 2048, 64),
+]
 
 
 def make_batch(wl: dict, n_sites: int, seed: int, tid: int = 0):
@@ -150,100 +162,74 @@ def emit(line: dict) -> None:
 _REAL_STDOUT = 1
 
 
-def main():
-    global _REAL_STDOUT
-    # keep stdout clean for the single JSON line: libraries that print to fd 1 are routed to stderr
-    sys.stdout.flush()
-    _REAL_STDOUT = os.dup(1)
-    os.dup2(2, 1)
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="exome50x48", choices=sorted(WORKLOADS))
-    ap.add_argument("--sites", type=int, default=8192, help="candidate sites per GPU per step")
-    ap.add_argument("--cpu-sites-per-core", type=int, default=512)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-arena", action="store_true", help="end-to-end leg: one pinned allocation per array instead of one arena for the batch")
-    ap.add_argument("--contexts", type=int, default=0,
-                    help="engine contexts per GPU in the end-to-end leg, one host thread each (batches in flight); 0 = 6, fewer when the ranks of a box would oversubscribe its cores")
-    ap.add_argument("--format", "--e2e-format", dest="e2e_format", default="bins", choices=["bins", "reads"],
-                    help="batch format of both legs: compact (read bins + sparse allele counts), or dense arrays with one element per read")
-    args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": f"{args.workload}: {wl['P']} pools x poolsize {wl['ploidy']}, {wl['depth']}x per pool, options {wl['options'] or 'defaults (--EM 1, asymptotic CT)'}",
-              "sites_per_gpu_per_step": args.sites, "sharding": "genomic region per rank, no collective",
-              "l2_policy": ("inputs larger than L2 (batch > 126 MB)" if args.e2e_format == "reads" and args.sites * (2 * wl['P'] * wl['depth'] + 96 * wl['P']) > 126e6
-                            else "L2 flushed between steps (256 MB fill, outside the per-step CUDA events)"),
-              "synthetic": wl["synth"]}
+def perm_placements(batch, results, lowcov: bool) -> float:
+    """Ball placements the permutation kernels performed: sum over tested (site, slot) of executed permutations x the
+    alternate reads of the slot's allele (forward + reverse; + bidirectional in the low-coverage test) — SURVEY.md §8d K3."""
+    k = results.perm_k.astype(np.int64)
+    s_idx, slot = np.nonzero(k > 0)
+    if s_idx.size == 0:
+        return 0.0
+    P = batch.n_pools
+    ic = batch.indcounts.reshape(batch.n_sites, P, 24).sum(axis=1)
+    al = results.allele[s_idx, slot].astype(np.int64)
+    ones = ic[s_idx, al] + ic[s_idx, al + 8] + (ic[s_idx, al + 16] if lowcov else 0)
+    return float((k[s_idx, slot] * ones).sum())
 
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        from oracle.loader import build
-        build()
-        cores = host_cores()
-        batch = make_batch(wl, cores * args.cpu_sites_per_core, seed=1)
-        for _ in range(max(0, min(args.warmup, 1))):
-            run_reference_sample(wl, batch, cores, max(1, args.cpu_sites_per_core // 8))
-        vals, t_total = [], 0.0
-        for _ in range(args.steps):
-            v, sites, busy, wall, kind = run_reference_sample(wl, batch, cores, args.cpu_sites_per_core)
-            vals.append(v)
-            t_total += busy
-        value = float(np.mean(vals))
-        line = {"impl": "reference", "metric": "candidate sites/sec", "value": value, "unit": "sites/s", "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": value, "unit": "sites/s", "cores": cores, "kind": kind,
-                                 "sample": f"{cores} processes x {args.cpu_sites_per_core} sites of the workload, one contiguous region each (the reference's --regions parallelism); sites/s = sites / slowest process"},
-                "e2e": {"value": value, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        emit(line)
-        return 0
 
+def rooflines(name, wl, batch, shipped, results, kt, steps, n_em, fmt, hbm_peak, hbm_src, fp64_peak, int32_peak, traffic=None, ncu_static=None):
+    """Roofline objects of the three kernel groups of one workload; `dominant` names the largest share of the step."""
+    traffic, ncu_static = traffic or {}, ncu_static or {}
+    P, J = wl["P"], wl["ploidy"] + 1
+    em_ms, ev_ms, pm_ms = kt["em_ms"] / steps, kt["evaluate_ms"] / steps, kt["permute_ms"] / steps
+    iters = results.em_iters[results.em_iters > 0]
+    # algorithmic work of the EM kernel (SURVEY.md §8d): per iteration 3 planes x sum_i (n_i+1) genotype evaluations at
+    # 35 flop + 3 P logs at 30 flop
+    ge_flops = float(iters.sum()) * (35.0 * 3 * P * J + 30.0 * 3 * P)
+    em_sites = np.unique(np.nonzero(results.em_iters > 0)[0])
+    if fmt == "bins" and shipped.bin_off is not None:   # the likelihood reads the sites' (value,count) bins, 4 B each
+        bo = shipped.bin_off.astype(np.int64)
+        em_bytes = float(sum(4 * (bo[(s + 1) * P] - bo[s * P]) for s in em_sites)) + n_em * (96.0 * P + 12.0 * P + 128.0)
+    else:
+        ro = batch.read_off.astype(np.int64)
+        em_bytes = float(sum(2 * (ro[(s + 1) * P] - ro[s * P]) for s in em_sites)) + n_em * (96.0 * P + 12.0 * P + 128.0)
+    ev_bytes = batch.n_sites * (96.0 * P + 40.0 + 5 * 110.0)
+    out = {}
+    out["k_em"] = {"kernel": "k_em", "bound": "fp64", "achieved": ge_flops / (em_ms * 1e-3) / 1e12 if em_ms > 0 else None, "peak": fp64_peak,
+                   "unit": "TFLOP/s", "frac": (ge_flops / (em_ms * 1e-3) / 1e12 / fp64_peak) if em_ms > 0 and fp64_peak > 0 else None,
+                   "traffic": traffic.get("k_em"), "algorithmic_bytes": em_bytes, "peak_source": "DFMA loop measured live (crispgpu_measure_fp64_tflops)",
+                   "ms_per_launch": em_ms, "tasks_per_launch": n_em, "mean_em_iterations": float(iters.mean()) if iters.size else 0.0,
+                   "algorithmic_hbm_GBps": em_bytes / (em_ms * 1e-3) / 1e9 if em_ms > 0 else None,
+                   "ncu_committed_capture": ncu_static.get("k_em") or None}
+    out["k_evaluate"] = {"kernel": "k_evaluate", "bound": "hbm", "achieved": ev_bytes / (ev_ms * 1e-3) / 1e9 if ev_ms > 0 else None, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": (ev_bytes / (ev_ms * 1e-3) / 1e9 / hbm_peak) if ev_ms > 0 else None, "traffic": traffic.get("k_evaluate"), "algorithmic_bytes": ev_bytes,
+                         "peak_source": hbm_src, "ms_per_launch": ev_ms, "sites_per_launch": batch.n_sites, "ncu_committed_capture": ncu_static.get("k_evaluate") or None}
+    if wl["options"].get("chisq_permutation") and pm_ms > 0:
+        lowcov = wl["ploidy"] <= 2
+        placements = perm_placements(batch, results, lowcov)
+        # algorithmic INT32 work per ball placement (SURVEY.md §8d K3): one Philox4x32-10 draw amortised over its four words
+        # (10 rounds x 4 multiplies / 4 = 10) + the bounded-integer reduction (2) + the search of the pool among P cumulative
+        # capacities (ceil log2 P) + the occupancy test and update (4)
+        ops = 16 + int(np.ceil(np.log2(max(P, 2))))
+        ach = placements * ops / (pm_ms * 1e-3) / 1e12
+        out["k_permute"] = {"kernel": "k_permute_lowcov(+tail)" if lowcov else "k_permute_stranded(+tail)", "bound": "int32", "achieved": ach, "peak": int32_peak,
+                            "unit": "TIOP/s", "frac": ach / int32_peak if int32_peak > 0 else None, "traffic": None,
+                            "peak_source": "IMAD loop measured live (crispgpu_measure_int32_tops)", "ms_per_launch": pm_ms,
+                            "placements_per_launch": placements, "int32_ops_per_placement": ops,
+                            "placements_per_s": placements / (pm_ms * 1e-3), "permutations_per_launch": float(results.perm_k[results.perm_k > 0].sum()),
+                            "ncu_committed_capture": ncu_static.get("k_permute") or None}
+    share = {"k_em": em_ms, "k_evaluate": ev_ms, "k_permute": pm_ms if "k_permute" in out else 0.0}
+    dominant = max(share, key=share.get)
+    return out, dominant
+
+
+def time_resident(eng, shipped, steps, warmup, stream, flush, barrier):
+    """K resident steps, CUDA events per step on the engine's stream (L2 flushed in between, outside the events)."""
     import torch
-    import torch.distributed as dist
-    from crisp_b200.abi import EngineConfig
-    from crisp_b200.engine import Engine, measure_fp64_tflops, pin_batch
-    from crisp_b200 import build as cbuild
-
-    cbuild.build()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    want_ctx = args.contexts if args.contexts > 0 else max(2, min(6, (os.cpu_count() or 8) // max(1, world)))
-    # spinning waits are faster, but only while every waiting thread has a core of its own
-    oversubscribed = world * (want_ctx + 1) > (os.cpu_count() or 8) // 2
-    cfg = EngineConfig(ploidy=np.full(wl["P"], wl["ploidy"]), options=wl["options"])
-    cfg_e2e = EngineConfig(ploidy=np.full(wl["P"], wl["ploidy"]), options=dict(wl["options"], blocking_wait=1 if oversubscribed else 0))
-    # region shard of this rank: its own contiguous run of candidate sites (tid = rank)
-    batch = make_batch(wl, args.sites, seed=1 + rank, tid=rank)
-    shipped = batch.compact() if args.e2e_format == "bins" else batch   # the form both legs consume
-    pinned = pin_batch(shipped, arena=not args.no_arena)
-    stream = torch.cuda.Stream(device=local)
-    eng = Engine(cfg, device=local, stream=stream.cuda_stream)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}") if "flushed" in config["l2_policy"] else None
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---------------- device-resident throughput ----------------
     eng.upload(shipped)
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         eng.run_resident(fetch=False)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     barrier()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     kt = {"evaluate_ms": 0.0, "em_ms": 0.0, "permute_ms": 0.0, "filter_ms": 0.0, "legacy_ms": 0.0}
     launches = 0
     with torch.cuda.stream(stream):
@@ -258,24 +244,22 @@ def main():
                 kt[k] += t[k]
             launches += t["launches"]
     barrier()
-    # the K steps, device time: sum of the per-step event pairs (equals one bracket around all of them when nothing sits between steps)
     ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
-    t_last = eng.timing()
-    # ---------------- end to end through the C ABI from pinned host memory ----------------
-    # The call sequence a front end makes: crispgpu_submit (asynchronous: H2D + screening kernels) on one context while
-    # the previous batch finishes on the other (crispgpu_wait: caller kernels + D2H).  Every step copies its inputs
-    # from pinned host memory and reads its results back to the host.
-    # One host thread per engine context, each looping crispgpu_submit / crispgpu_wait on its own stream; ctypes drops the
-    # GIL inside the calls, so the copies and kernels of the batches in flight overlap the way a multi-threaded front end
-    # would drive them.  The K timed steps (batches) are dealt round-robin to the threads.
-    import threading
-    nctx = max(1, min(want_ctx, args.steps))
-    e2e_streams = [torch.cuda.Stream(device=local) for _ in range(nctx)]
-    engs = [Engine(cfg_e2e, device=local, stream=st.cuda_stream) for st in e2e_streams]
+    return ms, kt, launches, eng.timing()
+
+
+def time_e2e(cfg_e2e, pinned, steps, warmup, nctx, local, barrier):
+    """K batches through crispgpu_submit / crispgpu_wait from pinned host memory: one host thread per engine context, steps
+    dealt round-robin; wall clock between two barriers.  Returns (seconds, timing of one context's last batch)."""
+    import torch
+    from crisp_b200.engine import Engine
+    nctx = max(1, min(nctx, steps))
+    streams = [torch.cuda.Stream(device=local) for _ in range(nctx)]
+    engs = [Engine(cfg_e2e, device=local, stream=st.cuda_stream) for st in streams]
     for e in engs:
-        for _ in range(max(1, args.warmup // 2)):
+        for _ in range(max(1, warmup // 2)):
             e.run(pinned)
-    share = [args.steps // nctx + (1 if k < args.steps % nctx else 0) for k in range(nctx)]
+    share = [steps // nctx + (1 if k < steps % nctx else 0) for k in range(nctx)]
     gate = threading.Barrier(nctx + 1)
     errors = []
 
@@ -297,26 +281,226 @@ def main():
     for w in workers:
         w.join()
     barrier()
-    e2e_s = time.perf_counter() - w0
+    secs = time.perf_counter() - w0
     if errors:
         raise errors[0]
-    t_e2e = engs[0].timing()
+    t = engs[0].timing()
     for e in engs:
         e.close()
+    return secs, t, nctx
+
+
+def side_config(name, sites, ref_per_core, local, peaks3, cores, want_cpu):
+    """One of the other BASELINE configs at reduced size: resident and end-to-end rate, roofline of the kernel that dominates
+    its step, and the reference on the host cores over a bounded sample."""
+    import torch
+    from crisp_b200.abi import EngineConfig
+    from crisp_b200.engine import Engine, pin_batch
+    wl = WORKLOADS[name]
+    hbm_peak, hbm_src, fp64_peak, int32_peak = peaks3
+    steps, warmup = 3, 3
+    t0 = time.perf_counter()
+    batch = make_batch(wl, sites, seed=11)
+    cfg = EngineConfig(ploidy=np.full(wl["P"], wl["ploidy"]), options=wl["options"])
+    shipped = batch.compact()
+    pinned = pin_batch(shipped)
+    stream = torch.cuda.Stream(device=local)
+    eng = Engine(cfg, device=local, stream=stream.cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+    ms, kt, launches, t_last = time_resident(eng, shipped, steps, warmup, stream, flush, torch.cuda.synchronize)
+    results = eng.run(batch)
+    eng.close()
+    secs, t_e2e, nctx = time_e2e(cfg, pinned, steps, warmup, 2, local, torch.cuda.synchronize)
+    roofs, dominant = rooflines(name, wl, batch, shipped, results, kt, steps, t_last["n_tasks_em"], "bins", hbm_peak, hbm_src, fp64_peak, int32_peak)
+    out = {"workload": f"{name}: {wl['P']} pools x poolsize {wl['ploidy']}, {wl['depth']}x per pool, options {wl['options'] or 'defaults'}",
+           "sites": batch.n_sites, "steps": steps, "value": batch.n_sites * steps / (ms * 1e-3), "unit": "sites/s", "ms_per_step": ms / steps,
+           "e2e": {"value": batch.n_sites * steps / secs, "unit": "sites/s", "h2d_bytes_per_step": int(t_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(t_e2e["d2h_bytes"]),
+                   "contexts": nctx},
+           "kernel_ms_per_step": {k: v / steps for k, v in kt.items()},
+           "tasks": {"em_tasks": t_last["n_tasks_em"], "perm_tasks": t_last["n_tasks_perm"], "called_alleles": int((results.status == 4).sum())},
+           "roofline": roofs[dominant]}
+    if want_cpu:
+        v, nsites, busy, wall, kind = run_reference_sample(wl, batch, cores, ref_per_core)
+        out["cpu_baseline"] = {"value": v, "unit": "sites/s", "cores": cores, "kind": kind,
+                               "sample": f"{nsites} sites of the same batch, {cores} processes x {ref_per_core} sites, {busy:.1f} s busy"}
+    out["wall_s"] = round(time.perf_counter() - t0, 1)
+    del flush
+    torch.cuda.empty_cache()
+    return out
+
+
+def bam_end_to_end(cores: int):
+    """BASELINE configs[0] as real files: 10 pools x poolsize 20, 100 kb at 100x, written as BAMs; the reference's own program
+    (CRISP.binary: one process, and one process per core over --regions shards — its only parallelism, README.md:51) beside
+    the same front end bound to the engine (CRISP.gpu, host/crisp_frontend.c).  Candidate sites = sites that reach
+    variantcalls.c:115.  The programs are the prebuilt oracle/_ref binaries (compiled from /root/reference)."""
+    import tempfile
+    from crisp_b200 import frontend as fe
+    from crisp_b200.bamsynth import make_dataset
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    refbin, gpubin, bamtool = (os.path.join(ref, x) for x in ("CRISP.binary", "CRISP.gpu", "bamtool"))
+    if not all(os.path.exists(x) for x in (refbin, gpubin, bamtool)):
+        return {"unavailable": "oracle/_ref programs not built (they need /root/reference at build time)"}
+    out = {"workload": "c1 as BAM files: 10 pools x poolsize 20, 100 kb at 100x per pool, --EM 1 (default flags)"}
+    with tempfile.TemporaryDirectory() as d:
+        ds = make_dataset(d, pools=10, poolsize=20, length=100000, depth=100, seed=1)
+        fe.index_bams(bamtool, ds)
+        stats = os.path.join(d, "stats.json")
+        t_gpu = fe.run_program(gpubin, ds, os.path.join(d, "gpu.vcf"), 20, env=dict(CRISPGPU_COMPACT=1, CRISPGPU_STATS=stats))
+        st = fe.read_stats(stats)
+        sites = st["sites"]
+        t_one = fe.run_program(refbin, ds, os.path.join(d, "ref.vcf"), 20)
+        sh = fe.run_sharded(refbin, ds, os.path.join(d, "ref_sharded.vcf"), 20, cores)
+        cmp = fe.compare_vcf(fe.read_vcf(os.path.join(d, "gpu.vcf")), fe.read_vcf(os.path.join(d, "ref.vcf")))
+        out.update({"candidate_sites": sites, "vcf_records": st["records"],
+                    "vcf_identical_to_reference": not cmp["differ"] and not cmp["only_got"] and not cmp["only_want"],
+                    "reference_1_process": {"wall_s": round(t_one, 3), "sites_per_s": sites / t_one},
+                    "reference_regions": {"processes": cores, "wall_s": round(sh["wall_s"], 3), "sites_per_s": sites / sh["wall_s"]},
+                    "frontend_plus_engine": {"wall_s": round(t_gpu, 3), "sites_per_s": sites / t_gpu, "processes": 1,
+                                             "pack_s": st["pack_s"], "engine_s": st["engine_s"], "device_s": st["device_s"], "print_s": st["print_s"],
+                                             "batches": st["batches"], "h2d_bytes": st["h2d_bytes"], "d2h_bytes": st["d2h_bytes"]},
+                    "note": "the front end (BAM decode + pileup, unchanged reference C, one process) is what remains of the wall time once the engine runs on the GPU"})
+    return out
+
+
+def main():
+    global _REAL_STDOUT
+    # keep stdout clean for the single JSON line: libraries that print to fd 1 are routed to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="exome50x48", choices=sorted(WORKLOADS))
+    ap.add_argument("--sites", type=int, default=8192, help="candidate sites per GPU per step")
+    ap.add_argument("--cpu-sites-per-core", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the reduced-size runs of the other BASELINE configs")
+    ap.add_argument("--no-bam", action="store_true", help="skip the BAM -> VCF run of config 1 through the reference's front end")
+    ap.add_argument("--no-arena", action="store_true", help="end-to-end leg: one pinned allocation per array instead of one arena for the batch")
+    ap.add_argument("--contexts", type=int, default=0,
+                    help="engine contexts per GPU in the end-to-end leg, one host thread each (batches in flight); 0 = 6, fewer when the ranks of a box would oversubscribe its cores")
+    ap.add_argument("--format", "--e2e-format", dest="e2e_format", default="bins", choices=["bins", "reads"],
+                    help="batch format of both legs: compact (read bins + sparse allele counts), or dense arrays with one element per read")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": f"{args.workload}: {wl['P']} pools x poolsize {wl['ploidy']}, {wl['depth']}x per pool, options {wl['options'] or 'defaults (--EM 1, asymptotic CT)'}",
+              "sites_per_gpu_per_step": args.sites, "sharding": "genomic region per rank, no collective; rank 0 merges the per-rank results in coordinate order (timed: `merge`)",
+              "l2_policy": ("inputs larger than L2 (batch > 126 MB)" if args.e2e_format == "reads" and args.sites * (2 * wl['P'] * wl['depth'] + 96 * wl['P']) > 126e6
+                            else "L2 flushed between steps (256 MB fill, outside the per-step CUDA events)"),
+              "synthetic": {k: (list(v) if isinstance(v, range) else v) for k, v in wl["synth"].items()}}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from oracle.loader import build
+        build()
+        cores = host_cores()
+        batch = make_batch(wl, cores * args.cpu_sites_per_core, seed=1)
+        for _ in range(max(0, min(args.warmup, 1))):
+            run_reference_sample(wl, batch, cores, max(1, args.cpu_sites_per_core // 8))
+        vals, t_total = [], 0.0
+        for _ in range(args.steps):
+            v, sites, busy, wall, kind = run_reference_sample(wl, batch, cores, args.cpu_sites_per_core)
+            vals.append(v)
+            t_total += busy
+        value = float(np.mean(vals))
+        line = {"impl": "reference", "metric": "candidate sites/sec", "value": value, "unit": "sites/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": "sites/s", "cores": cores, "kind": kind,
+                                 "sample": f"{cores} processes x {args.cpu_sites_per_core} sites of the workload, one contiguous region each (the reference's --regions parallelism); sites/s = sites / slowest process; mean of {args.steps} steps"},
+                "e2e": {"value": value, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        emit(line)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from crisp_b200.abi import EngineConfig
+    from crisp_b200.engine import Engine, measure_fp64_tflops, measure_int32_tops, pin_batch
+    from crisp_b200 import build as cbuild
+
+    if "CRISPGPU_LIB" not in os.environ:
+        cbuild.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    want_ctx = args.contexts if args.contexts > 0 else max(2, min(6, (os.cpu_count() or 8) // max(1, world)))
+    # spinning waits are faster, but only while every waiting thread has a core of its own
+    oversubscribed = world * (want_ctx + 1) > (os.cpu_count() or 8) // 2
+    cfg = EngineConfig(ploidy=np.full(wl["P"], wl["ploidy"]), options=wl["options"])
+    cfg_e2e = EngineConfig(ploidy=np.full(wl["P"], wl["ploidy"]), options=dict(wl["options"], blocking_wait=1 if oversubscribed else 0))
+    # region shard of this rank: its own contiguous run of candidate sites (tid = rank)
+    batch = make_batch(wl, args.sites, seed=1 + rank, tid=rank)
+    compact_batch = batch.compact()
+    shipped = compact_batch if args.e2e_format == "bins" else batch   # the form both legs consume
+    pinned = pin_batch(shipped, arena=not args.no_arena)
+    stream = torch.cuda.Stream(device=local)
+    eng = Engine(cfg, device=local, stream=stream.cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}") if "flushed" in config["l2_policy"] else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---------------- device-resident throughput ----------------
+    ms, kt, launches, t_last = time_resident(eng, shipped, args.steps, args.warmup, stream, flush, barrier)
+    # ---------------- end to end through the C ABI from pinned host memory ----------------
+    # The call sequence a front end makes: crispgpu_submit (asynchronous: H2D + screening kernels) on one context while
+    # the previous batch finishes on another (crispgpu_wait: caller kernels + D2H).  Every step copies its inputs from
+    # pinned host memory and reads its results back to the host.
+    e2e_s, t_e2e, nctx = time_e2e(cfg_e2e, pinned, args.steps, args.warmup, want_ctx, local, barrier)
     clocks = sampler.stop() if rank == 0 else None
+    # the same leg in the other batch format (fewer steps: the per-read arrays are 7x the bytes)
+    other_fmt = "reads" if args.e2e_format == "bins" else "bins"
+    other_steps = max(4, args.steps // 4)
+    pinned_other = pin_batch(batch if other_fmt == "reads" else compact_batch, arena=not args.no_arena)
+    e2e_other_s, t_e2e_other, _ = time_e2e(cfg_e2e, pinned_other, other_steps, args.warmup, want_ctx, local, barrier)
+    del pinned_other
     results = eng.run(batch)
 
-    times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local}")
+    # ---------------- coordinate-order merge of the per-rank results on rank 0 (SURVEY.md §8e) ----------------
+    merge = None
+    if world > 1:
+        from crisp_b200.shard import merge_results
+        barrier()
+        g0 = time.perf_counter()
+        payload = (results, np.arange(batch.n_sites) + rank * batch.n_sites)
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(payload, gathered, dst=0)
+        g1 = time.perf_counter()
+        if rank == 0:
+            merged = merge_results([g[0] for g in gathered], [g[1] for g in gathered], batch.n_sites * world, wl["P"])
+            g2 = time.perf_counter()
+            # the merged order is (tid, pos): every rank owns one contiguous region, regions ordered by rank
+            assert merged.n_calls == sum(g[0].n_calls for g in gathered)
+            merge = {"gather_ms_per_batch": (g1 - g0) * 1e3, "merge_ms_per_batch": (g2 - g1) * 1e3, "sites": batch.n_sites * world,
+                     "note": "host side, once per batch of all ranks; torch.distributed object gather (control plane) + crisp_b200.shard.merge_results"}
+
+    times = torch.tensor([ms, e2e_s * 1e3, e2e_other_s * 1e3], dtype=torch.float64, device=f"cuda:{local}")
     per_rank = [[float(times[0]) / args.steps, float(times[1]) / args.steps]]
     if world > 1:
-        gathered = [torch.zeros_like(times) for _ in range(world)]
-        dist.all_gather(gathered, times)
-        per_rank = [[float(g[0]) / args.steps, float(g[1]) / args.steps] for g in gathered]
+        gathered_t = [torch.zeros_like(times) for _ in range(world)]
+        dist.all_gather(gathered_t, times)
+        per_rank = [[float(g[0]) / args.steps, float(g[1]) / args.steps] for g in gathered_t]
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = float(times[0]), float(times[1])
+    ms_max, e2e_ms_max, e2e_other_ms_max = float(times[0]), float(times[1]), float(times[2])
     total_sites = batch.n_sites * world
     value = total_sites * args.steps / (ms_max * 1e-3)
     e2e_value = total_sites * args.steps / (e2e_ms_max * 1e-3)
+    e2e_other_value = total_sites * other_steps / (e2e_other_ms_max * 1e-3)
 
     if rank == 0:
         peaks = {}
@@ -327,66 +511,76 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         fp64_peak = measure_fp64_tflops(local)
-        P, J = wl["P"], wl["ploidy"] + 1
-        n_em = t_last["n_tasks_em"]
-        iters = results.em_iters[results.em_iters > 0]
-        # algorithmic work of the EM kernel: per iteration 3 planes x sum_i (n_i+1) genotype evaluations at
-        # 35 flop + 3 P logs at 30 flop; plus the likelihood contraction, 2 flop per (histogram bin, j, plane)
-        ge_flops = float(iters.sum()) * (35.0 * 3 * P * J + 30.0 * 3 * P)
-        em_ms = kt["em_ms"] / args.steps
-        ev_ms = kt["evaluate_ms"] / args.steps
-        ro = batch.read_off.astype(np.int64)
-        em_sites = np.unique(np.nonzero(results.em_iters > 0)[0])
-        if args.e2e_format == "bins":   # the likelihood reads the sites' (value,count) bins, 4 B each, instead of 2 B per read
-            bo = pinned.bin_off.astype(np.int64)
-            em_bytes = float(sum(4 * (bo[(s + 1) * P] - bo[s * P]) for s in em_sites)) + n_em * (96.0 * P + 12.0 * P + 128.0)
-        else:
-            em_bytes = float(sum(2 * (ro[(s + 1) * P] - ro[s * P]) for s in em_sites)) + n_em * (96.0 * P + 12.0 * P + 128.0)
-        ev_bytes = batch.n_sites * (96.0 * P + 40.0 + 5 * 110.0)
-        dominant = "k_em" if em_ms >= ev_ms else "k_evaluate"
+        int32_peak = measure_int32_tops(local)
         # DRAM traffic per launch from the committed ncu --set full capture of this very configuration (null otherwise)
         traffic, ncu_static = {}, {}
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1", "traffic.json"))).get(args.workload + (":bins" if args.e2e_format == "bins" else ""), {})
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2", "traffic.json"))).get(args.workload + (":bins" if args.e2e_format == "bins" else ""), {})
             if tj.get("sites") == batch.n_sites:
                 traffic = {k: v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in tj.items() if isinstance(v, dict)}
                 ncu_static = {k: {m: v[m] for m in ("issue_active_pct", "fp64_pipe_pct", "warp_instructions", "registers") if m in v} for k, v in tj.items() if isinstance(v, dict)}
         except Exception:
             pass
-        roof_em = {"kernel": "k_em", "bound": "fp64", "achieved": ge_flops / (em_ms * 1e-3) / 1e12 if em_ms > 0 else None, "peak": fp64_peak,
-                   "unit": "TFLOP/s", "frac": (ge_flops / (em_ms * 1e-3) / 1e12 / fp64_peak) if em_ms > 0 and fp64_peak > 0 else None,
-                   "traffic": traffic.get("k_em"), "algorithmic_bytes": em_bytes, "peak_source": "DFMA loop measured live (crispgpu_measure_fp64_tflops)",
-                   "ms_per_launch": em_ms, "tasks_per_launch": n_em, "mean_em_iterations": float(iters.mean()) if iters.size else 0.0,
-                   "algorithmic_hbm_GBps": em_bytes / (em_ms * 1e-3) / 1e9 if em_ms > 0 else None,
-                   "ncu_committed_capture": ncu_static.get("k_em") or None}
-        roof_ev = {"kernel": "k_evaluate", "bound": "hbm", "achieved": ev_bytes / (ev_ms * 1e-3) / 1e9 if ev_ms > 0 else None, "peak": hbm_peak, "unit": "GB/s",
-                   "frac": (ev_bytes / (ev_ms * 1e-3) / 1e9 / hbm_peak) if ev_ms > 0 else None, "traffic": traffic.get("k_evaluate"), "algorithmic_bytes": ev_bytes, "peak_source": hbm_src,
-                   "ms_per_launch": ev_ms, "sites_per_launch": batch.n_sites, "ncu_committed_capture": ncu_static.get("k_evaluate") or None}
+        roofs, dominant = rooflines(args.workload, wl, batch, shipped, results, kt, args.steps, t_last["n_tasks_em"], args.e2e_format,
+                                    hbm_peak, hbm_src, fp64_peak, int32_peak, traffic, ncu_static)
+        second = max((k for k in roofs if k != dominant), key=lambda k: roofs[k]["ms_per_launch"])
+        fmt_label = {"bins": "compact (pre-binned by the host packer): reads as (value,count) bins per site x pool (consumed as they are by k_em), per-pool allele counts as non-zero entries (k_expand_counts)",
+                     "reads": "one 16-bit element per read (the format the reference arm consumes); sites that reach the likelihood fetched on demand (k_fetch_reads)"}
         line = {"metric": "candidate sites/sec", "value": value, "unit": "sites/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config, "clocks": clocks,
+                "value_definition": "kernels only, inputs resident in HBM (CUDA events around every step); `e2e` is H2D + kernels + D2H through the C ABI",
                 "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": int(t_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(t_e2e["d2h_bytes"]),
                         "ms_per_step": e2e_ms_max / args.steps, "h2d_ms": t_e2e["h2d_ms"], "d2h_ms": t_e2e["d2h_ms"],
-                        "fetched_bytes_per_step": int(t_e2e["fetched_bytes"]),
-                        "input_format": ("compact: reads as (value,count) bins per site x pool (consumed as they are by k_em), per-pool allele counts as non-zero entries (k_expand_counts)" if args.e2e_format == "bins"
-                                         else "one 16-bit element per read; sites that reach the likelihood fetched on demand (k_fetch_reads)"),
+                        "fetched_bytes_per_step": int(t_e2e["fetched_bytes"]), "input_format": fmt_label[args.e2e_format],
+                        "single_context_device_ms": round(float(t_e2e["total_ms"]), 4),
                         "stage_ms_last_batch": {k: round(float(t_e2e[k]), 4) for k in ("h2d_ms", "evaluate_ms", "permute_ms", "filter_ms", "em_ms", "d2h_ms", "total_ms")},
                         "mode": f"{nctx} engine contexts per GPU, one host thread each looping crispgpu_submit/crispgpu_wait on pinned buffers; steps dealt round-robin; " + ("blocking waits (more waiting threads than spare cores)" if oversubscribed else "spinning waits")},
+                "e2e_" + other_fmt: {"value": e2e_other_value, "unit": "sites/s", "steps": other_steps, "h2d_bytes_per_step": int(t_e2e_other["h2d_bytes"]),
+                                     "d2h_bytes_per_step": int(t_e2e_other["d2h_bytes"]), "fetched_bytes_per_step": int(t_e2e_other["fetched_bytes"]),
+                                     "ms_per_step": e2e_other_ms_max / other_steps, "input_format": fmt_label[other_fmt]},
                 "gpu_launches": int(launches),
                 "per_rank_ms_per_step": {"resident": [round(x[0], 4) for x in per_rank], "e2e": [round(x[1], 4) for x in per_rank]},
-                "roofline": roof_em if dominant == "k_em" else roof_ev,
-                "roofline_secondary": roof_ev if dominant == "k_em" else roof_em,
+                "roofline": roofs[dominant], "roofline_secondary": roofs[second],
                 "kernel_ms_per_step": {k: v / args.steps for k, v in kt.items()},
-                "tasks": {"sites": batch.n_sites, "em_tasks": n_em, "called_alleles": int((results.status == 4).sum()), "perm_tasks": t_last["n_tasks_perm"]}}
+                "tasks": {"sites": batch.n_sites, "em_tasks": t_last["n_tasks_em"], "called_alleles": int((results.status == 4).sum()), "perm_tasks": t_last["n_tasks_perm"]}}
+        if merge:
+            line["merge"] = merge
+        eng.close()
+        del flush
+        torch.cuda.empty_cache()
         if world == 1 and not args.no_cpu_baseline:
-            from oracle.loader import build
+            from oracle.loader import RefEngine, build, have_ref
             build()
             cores = host_cores()
             v, sites, busy, wall, kind = run_reference_sample(wl, batch, cores, args.cpu_sites_per_core)
             line["cpu_baseline"] = {"value": v, "unit": "sites/s", "cores": cores, "kind": kind,
                                     "sample": f"{sites} sites of the same batch, {cores} processes x {args.cpu_sites_per_core} sites (contiguous regions), {busy:.1f} s busy"}
+            if have_ref():
+                # what packing a site costs the host in either batch format: the production packer (host/crisp_shim.c) on the
+                # reference's own read lists, one core
+                sub = batch.select(np.arange(min(256, batch.n_sites)))
+                r = RefEngine(cfg)
+                line["host_pack"] = {"reads_us_per_site": 1e6 * r.shim_pack_seconds(sub, False) / sub.n_sites,
+                                     "compact_us_per_site": 1e6 * r.shim_pack_seconds(sub, True) / sub.n_sites, "cores": 1, "sites": sub.n_sites,
+                                     "what": "crisp_shim_append_site alone (walks of the reference's read lists + packing), per candidate site of this workload; not inside `e2e`, whose batches are packed before the timed region"}
+            if not args.no_configs:
+                line["configs"] = {}
+                for name, nsites, per_core in SIDE_CONFIGS:
+                    if name == args.workload:
+                        continue
+                    try:
+                        line["configs"][name] = side_config(name, nsites, per_core, local, (hbm_peak, hbm_src, fp64_peak, int32_peak), cores, True)
+                    except Exception as exc:  # noqa: BLE001 — a side run must not take the headline down
+                        line["configs"][name] = {"error": repr(exc)[:300]}
+            if not args.no_bam:
+                try:
+                    line["bam_e2e"] = bam_end_to_end(cores)
+                except Exception as exc:  # noqa: BLE001
+                    line["bam_e2e"] = {"error": repr(exc)[:300]}
         emit(line)
-    eng.close()
+    else:
+        eng.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

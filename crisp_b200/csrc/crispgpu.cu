@@ -850,9 +850,51 @@ __global__ void k_dfma_peak(double* out, int iters)
 	if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) out[0] = a0;
 }
 
+// 32-bit integer multiply-add chains (IMAD, the instruction the permutation kernels' Philox rounds and index arithmetic are
+// made of): eight independent chains per thread, register-resident
+__global__ void k_imad_peak(uint32_t* out, int iters)
+{
+	uint32_t a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+	const uint32_t m = 0xD2511F53u + blockIdx.x, c = 0x9E3779B9u;
+	for (int i = 0; i < iters; i++) {
+		a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+		a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+	}
+	if ((a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7) == 0x12345678u) out[0] = a0;
+}
+
 }  // namespace
 
 extern "C" {
+
+int crispgpu_measure_int32_tops(int device_id, double* tops)
+{
+	if (!tops) return CRISPGPU_ERR_ARG;
+	cudaDeviceProp prop;
+	if (cudaSetDevice(device_id) != cudaSuccess || cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) return CRISPGPU_ERR_NO_DEVICE;
+	uint32_t* d = nullptr;
+	cudaEvent_t e0, e1;
+	if (cudaMalloc(&d, 8) != cudaSuccess) return CRISPGPU_ERR_CUDA;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+	double best = 0.0;
+	for (int rep = 0; rep < 4; rep++) {
+		cudaEventRecord(e0);
+		k_imad_peak<<<blocks, threads>>>(d, iters);
+		cudaEventRecord(e1);
+		if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return CRISPGPU_ERR_CUDA; }
+		float ms = 0;
+		cudaEventElapsedTime(&ms, e0, e1);
+		double t = 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;   // integer multiply-add instructions per lane
+		if (rep > 0 && t > best) best = t;
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(d);
+	*tops = best;
+	return CRISPGPU_OK;
+}
 
 int crispgpu_measure_fp64_tflops(int device_id, double* tflops)
 {

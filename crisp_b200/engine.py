@@ -19,7 +19,7 @@ EXPORTS = [
     "crispgpu_config_defaults", "crispgpu_create", "crispgpu_destroy", "crispgpu_submit", "crispgpu_wait", "crispgpu_advance", "crispgpu_screen_positions",
     "crispgpu_upload", "crispgpu_run_resident", "crispgpu_get_timing", "crispgpu_last_error",
     "crispgpu_host_alloc", "crispgpu_host_free", "crispgpu_abi_version", "crispgpu_device_count",
-    "crispgpu_measure_fp64_tflops",
+    "crispgpu_measure_fp64_tflops", "crispgpu_measure_int32_tops",
 ]
 
 _lib = None
@@ -207,6 +207,18 @@ def measure_fp64_tflops(device: int = 0) -> float:
     rc = load_library().crispgpu_measure_fp64_tflops(device, C.byref(v))
     if rc != 0:
         raise EngineError(f"crispgpu_measure_fp64_tflops failed: status {rc}")
+    return v.value
+
+
+def measure_int32_tops(device: int = 0) -> float:
+    """INT32 multiply-add throughput of the device (10^12 lane-instructions per second), measured with an IMAD loop."""
+    v = C.c_double(0.0)
+    lib = load_library()
+    lib.crispgpu_measure_int32_tops.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    lib.crispgpu_measure_int32_tops.restype = C.c_int
+    rc = lib.crispgpu_measure_int32_tops(device, C.byref(v))
+    if rc != 0:
+        raise EngineError(f"crispgpu_measure_int32_tops failed: status {rc}")
     return v.value
 
 

@@ -301,6 +301,9 @@ int crispgpu_device_count(void);
 /* Measured FP64 FMA throughput of the device (TFLOP/s, 2 flop per DFMA) from a register-resident DFMA loop:
  * the roofline denominator of the EM kernel (MEASURED_PEAKS.json carries no FP64 figure). */
 int crispgpu_measure_fp64_tflops(int device_id, double* tflops);
+/* Measured 32-bit integer multiply-add throughput (10^12 IMAD lane-instructions per second): the roofline denominator of
+ * the Monte-Carlo permutation kernels (counter-based RNG rounds and index arithmetic on the INT32 pipe). */
+int crispgpu_measure_int32_tops(int device_id, double* tops);
 
 #ifdef __cplusplus
 }

@@ -140,6 +140,17 @@ class RefEngine(_CpuEngine):
         rc = fn(self.h, C.byref(cb), msg, 256)
         return rc, msg.value.decode()
 
+    def shim_pack_seconds(self, batch: Batch, compact: bool) -> float:
+        """Seconds the production packer (crisp_shim_append_site, one host core) spends on the sites of `batch`."""
+        fn = self.lib.crisp_ref_shim_pack_seconds
+        fn.restype = C.c_double
+        fn.argtypes = [C.c_void_p, C.POINTER(CBatch), C.c_int]
+        cb = batch.as_c()
+        t = fn(self.h, C.byref(cb), 1 if compact else 0)
+        if t < 0:
+            raise RuntimeError("shim pack timing failed")
+        return t
+
     def sort_allelecounts(self, batch: Batch):
         """The reference's own sort_allelecounts (parsebam/allelecounts.c:134-183) on every site of the batch."""
         n = batch.n_sites

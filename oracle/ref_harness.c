@@ -829,6 +829,39 @@ int crisp_ref_shim_roundtrip(void* h, const crispgpu_batch* b, char* msg, size_t
 }
 
 
+/*
+ * Host cost of the production packer: rebuild the reference's structures for every site of `b` and time ONLY the
+ * crisp_shim_append_site calls (one host core), in the per-read format (compact = 0) or the binned one (compact = 1).
+ * Returns seconds spent in the packer for the batch's n_sites, or a negative value on failure.
+ */
+#include <time.h>
+double crisp_ref_shim_pack_seconds(void* h, const crispgpu_batch* b, int compact)
+{
+	ref_ctx* c = (ref_ctx*)h;
+	struct VARIANT* v = &c->variant;
+	const int P = c->P, n = b->n_sites;
+	apply_config(c);
+	crisp_shim_batch* sb = crisp_shim_batch_new(P, b->qhigh != NULL, b->stats != NULL);
+	if (!sb) return -1.0;
+	crisp_shim_batch_set_compact(sb, compact);
+	ALLELE maxvec[8];
+	double total = 0.0;
+	for (int s = 0; s < n; s++) {
+		fill_site(c, b, s);
+		v->position = b->pos[s];
+		if (build_reads(c, b, s) != 0) { crisp_shim_batch_free(sb); return -1.0; }
+		for (int k = 0; k < 8; k++) { maxvec[k].al = b->maxvec_al[s * 8 + k]; maxvec[k].ct = b->maxvec_ct[s * 8 + k]; }
+		struct timespec t0, t1;
+		clock_gettime(CLOCK_MONOTONIC, &t0);
+		const int rc = crisp_shim_append_site(sb, &c->reflist, -1, &c->rq, c->bd, v, maxvec, b->tid[s]);
+		clock_gettime(CLOCK_MONOTONIC, &t1);
+		if (rc != 0) { crisp_shim_batch_free(sb); return -2.0; }
+		total += (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+	}
+	crisp_shim_batch_free(sb);
+	return total;
+}
+
 /* ---- exact small-table mode: FET/contables_exact.c (dead in CRISP.binary, the specification of the GPU exact mode) ---- */
 double compute_pvalue_exact(int** ctable, int size, int offset, int R, int A, double prob, double** NCRtable, int st);
 void compute_NCRtable(double** NCRtable);
