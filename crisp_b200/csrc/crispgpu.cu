@@ -330,6 +330,43 @@ int collect_arrays(crispgpu_ctx* ctx, const crispgpu_batch* b, BatchArray* a)
 	return k;
 }
 
+// CRISPGPU_VALIDATE=1: host-side consistency checks of the offset arrays before anything is copied (the kernels trust them;
+// a non-monotone offset or an out-of-range row index would be an out-of-bounds device read).  O(n P) on the host, so off
+// by default; a front end under development switches it on.
+int validate_batch(crispgpu_ctx* ctx, const crispgpu_batch* b)
+{
+	static const bool on = getenv("CRISPGPU_VALIDATE") != nullptr;
+	if (!on) return 0;
+	const size_t n = b->n_sites, P = ctx->P;
+	auto monotone = [&](const uint32_t* off, size_t cells, const char* name) -> int {
+		if (!off) return 0;
+		if (off[0] != 0) { snprintf(ctx->err, sizeof ctx->err, "%s[0] is %u, not 0", name, off[0]); return CRISPGPU_ERR_ARG; }
+		for (size_t k = 0; k < cells; k++)
+			if (off[k + 1] < off[k]) { snprintf(ctx->err, sizeof ctx->err, "%s decreases at cell %zu (%u -> %u)", name, k, off[k], off[k + 1]); return CRISPGPU_ERR_ARG; }
+		return 0;
+	};
+	int rc;
+	if ((rc = monotone(b->read_off, n * P, "read_off"))) return rc;
+	if ((rc = monotone(b->bin_off, n * P, "bin_off"))) return rc;
+	if ((rc = monotone(b->ic_off, n * P, "ic_off"))) return rc;
+	if ((rc = monotone(b->alt_off, n * 5, "alt_off"))) return rc;
+	if (b->amb_idx)
+		for (size_t k = 0; k < n * 5; k++)
+			if (b->amb_idx[k] >= b->n_amb || b->amb_idx[k] < -1) { snprintf(ctx->err, sizeof ctx->err, "amb_idx[%zu] = %d outside [-1, %d)", k, b->amb_idx[k], b->n_amb); return CRISPGPU_ERR_ARG; }
+	if (b->alt_off && b->alt_reads)
+		for (size_t k = 0; k < b->alt_off[n * 5]; k++)
+			if (b->alt_reads[k].pool >= P) { snprintf(ctx->err, sizeof ctx->err, "alt_reads[%zu].pool = %u with %zu pools", k, b->alt_reads[k].pool, P); return CRISPGPU_ERR_ARG; }
+	if (b->maxvec_al)
+		for (size_t k = 0; k < n * 8; k++)
+			if (b->maxvec_al[k] >= 8) { snprintf(ctx->err, sizeof ctx->err, "maxvec_al[%zu] = %u is not an allele index", k, b->maxvec_al[k]); return CRISPGPU_ERR_ARG; }
+	for (size_t k = 0; k < n; k++)
+		if (b->refbase[k] >= 8) { snprintf(ctx->err, sizeof ctx->err, "refbase[%zu] = %u", k, b->refbase[k]); return CRISPGPU_ERR_ARG; }
+	if (b->ic_off && b->ic_sparse)
+		for (size_t k = 0; k < b->ic_off[n * P]; k++)
+			if ((b->ic_sparse[k] >> 27) >= 24) { snprintf(ctx->err, sizeof ctx->err, "ic_sparse[%zu] has index %u (>= 24)", k, b->ic_sparse[k] >> 27); return CRISPGPU_ERR_ARG; }
+	return 0;
+}
+
 // lazy: the caller's arrays outlive the call (submit/wait), so the packed reads — 80 % of a batch, needed only by the
 // sites that reach the quality-value likelihood — may stay in pinned host memory and be fetched on demand.
 int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b, bool lazy)
@@ -340,6 +377,7 @@ int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b, bool lazy)
 		snprintf(ctx->err, sizeof ctx->err, "batch is missing a required array");
 		return k;
 	}
+	{ const int vr = validate_batch(ctx, b); if (vr) return vr; }
 	const void** dptr = reinterpret_cast<const void**>(&ctx->db.tid);
 	int64_t bytes = 0;
 	constexpr int kReadsArray = 10;
@@ -386,6 +424,12 @@ int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b, bool lazy)
 			continue;
 		}
 		if (i == kReadsArray && ctx->binned) { dptr[i] = nullptr; continue; }  // k_em consumes the bins; no read stream on the device
+		if (i == 20 && ctx->binned && a[i].bytes == 0) {  // a compact batch without a single bin still takes the bins path (all cells empty)
+			int rc = ensure_dev(ctx, ctx->d_b[i], 16);
+			if (rc) return rc;
+			dptr[i] = ctx->d_b[i].p;
+			continue;
+		}
 		if (a[i].bytes == 0 || a[i].host == nullptr) { dptr[i] = nullptr; continue; }
 		int rc = ensure_dev(ctx, ctx->d_b[i], a[i].bytes);
 		if (rc) return rc;
@@ -495,7 +539,7 @@ int run_stage1(crispgpu_ctx* ctx)
 	int64_t launches = 0;
 	CK(cudaMemsetAsync(ctx->d_counters.p, 0, 16 * sizeof(int32_t), ctx->stream));
 	const bool lazy = ctx->lazy_reads != nullptr && n > 0;
-	const bool use_bins = ctx->binned && n > 0 && ctx->n_bins > 0 && g.em_flag >= 1 && g.use_base_qvs == 1;
+	const bool use_bins = ctx->binned && n > 0 && g.em_flag >= 1 && g.use_base_qvs == 1;
 	if (!use_bins) ctx->binned = false;
 	if (lazy) {
 		rc = ensure_dev(ctx, ctx->d_need_reads, (size_t)n); if (rc) return rc;
@@ -515,7 +559,7 @@ int run_stage1(crispgpu_ctx* ctx)
 		CK(launch_check());
 	}
 	CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
-	const bool scan = n > 0 && g.em_flag >= 1 && g.use_base_qvs == 1 && !lazy && (use_bins || (ctx->n_reads > 0 && ctx->db.reads != nullptr));
+	const bool scan = n > 0 && g.em_flag >= 1 && g.use_base_qvs == 1 && !lazy && ((use_bins && ctx->n_bins > 0) || (!use_bins && ctx->n_reads > 0 && ctx->db.reads != nullptr));
 	if (scan) {
 		// fork: the scan of the read stream (or of its compact bins) is independent of the count-based screening
 		CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
@@ -677,6 +721,16 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 	EngineParams prm = make_params(ctx);
 	CK(cudaEventSynchronize(ctx->ev_counts));
 	const int32_t* hc = static_cast<const int32_t*>(ctx->h_counters.p);
+	if (g.chisq_permutation == 1 && n > 0) {
+		// the occupancy counters of the permutation kernels are packed fields: 16 bits per strand (pool size > 2), 10 bits per
+		// stratum (low-coverage test).  A pool that could receive more balls than a field holds would corrupt its neighbour.
+		const int cap = ctx->ploidy[0] > 2 ? 65535 : 1023;
+		if (hc[13] > cap) {
+			snprintf(ctx->err, sizeof ctx->err, "permutation test: a pool can receive %d alternate reads of one %s in a permutation, more than the %d the packed occupancy "
+			         "counters hold (deeper data needs a wider counter layout)", hc[13], ctx->ploidy[0] > 2 ? "strand" : "stratum", cap);
+			return CRISPGPU_ERR_UNSUPPORTED;
+		}
+	}
 	ctx->n_perm = hc[0];
 	ctx->n_call1 = hc[1];
 	ctx->n_call2 = hc[8];

@@ -33,6 +33,7 @@ struct PermShared {
 	int warp_first[32];
 	int tot[3], ones[3];
 	int maxN;
+	int maxball;   // most balls one pool can receive on one strand / stratum in a permutation of this table
 	double clra;
 };
 
@@ -117,11 +118,14 @@ __device__ inline void stranded_setup(const EngineParams& prm, const StrandedVie
 		if (row >= 0) { const int32_t* d = b.amb_dec + ((size_t)row * P + i) * 4; dd[0] = d[0]; dd[1] = d[1]; }
 		const int nref = (a1 == refbase) + (a2 == refbase) + (a3 == refbase);
 		const int nf = r[a1] + r[a2] + r[a3] - nref * dd[0], nr = r[a1 + 8] + r[a2 + 8] + r[a3 + 8] - nref * dd[1];
-		v.cumf[i + 1] = nf;
-		v.cumr[i + 1] = nr;
-		v.Ntot[i] = nf + nr;
-		v.alt[i] = r[altal] - (altal == refbase ? dd[0] : 0);
-		v.alt[P + i] = r[altal + 8] - (altal == refbase ? dd[1] : 0);
+		// an inconsistent batch (ambiguity decrements above the counts) must not wrap the unsigned capacities or ask for more
+		// balls than slots — the sampler would never finish; for a valid batch the clamps change nothing
+		const int nfc = nf < 0 ? 0 : nf, nrc = nr < 0 ? 0 : nr;
+		v.cumf[i + 1] = nfc;
+		v.cumr[i + 1] = nrc;
+		v.Ntot[i] = nfc + nrc;
+		v.alt[i] = min(max(r[altal] - (altal == refbase ? dd[0] : 0), 0), nfc);
+		v.alt[P + i] = min(max(r[altal + 8] - (altal == refbase ? dd[1] : 0), 0), nrc);
 	}
 	__syncthreads();
 	double* terms = v.L10;  // borrowed before the log table is built
@@ -146,6 +150,9 @@ __device__ inline void stranded_setup(const EngineParams& prm, const StrandedVie
 		v.sh->maxN = mx;
 		v.sh->clra = clra;
 		atomicMax(prm.q.counters + 11, (int)deepest);
+		// most balls one pool can receive on one strand: must fit the 16-bit occupancy fields of the head kernel
+		v.sh->maxball = (int)min(deepest, (uint32_t)max(of, orr));
+		atomicMax(prm.q.counters + 13, v.sh->maxball);
 	}
 	__syncthreads();
 	const int maxN = v.sh->maxN;
@@ -231,6 +238,10 @@ __global__ void __launch_bounds__(256, 4) k_permute_stranded(EngineParams prm, i
 		if (exact_done && exact_done[task]) continue;  // small table: the exact test already wrote the p-value
 		const int o = prm.q.perm_tasks[task], s = o / kSlots, slot = o - s * kSlots;
 		stranded_setup(prm, v, o);
+		if (v.sh->maxball > 65535) {  // does not fit the 16-bit occupancy fields: the host reports CRISPGPU_ERR_UNSUPPORTED (counters[13])
+			if (tid == 0) { prm.o.ctpval[o] = 0.0; prm.o.perm_k[o] = 0; prm.o.perm_hits[o] = 0; }
+			continue;
+		}
 		const int maxiter = c.max_iter;
 		const int head = maxiter < kPermHead ? maxiter : kPermHead;
 		int stop_k = 0, stop_hits = 0, hits_before = 0;
@@ -404,11 +415,12 @@ __device__ inline bool lowcov_setup(const EngineParams& prm, const LowcovView& v
 		const int nref3 = (a1 == refbase) + (a2 == refbase) + (a3 == refbase), nref2 = (a1 == refbase) + (a2 == refbase);
 		const int n0 = r[a1] + r[a2] + r[a3] - nref3 * dd[0], n1 = r[a1 + 8] + r[a2 + 8] + r[a3 + 8] - nref3 * dd[1];
 		const int n2 = r[a1 + 16] + r[a2 + 16] - nref2 * dd[2];  // bidirectional column excludes allele3 (allelecounts.c:228)
-		v.cum[0 * (P + 1) + i + 1] = n0; v.cum[1 * (P + 1) + i + 1] = n1; v.cum[2 * (P + 1) + i + 1] = n2;
-		v.Ntot[i] = n0 + n1 + n2;
-		for (int k = 0; k < 3; k++) v.alt[k * P + i] = r[altal + 8 * k] - (altal == refbase ? dd[k] : 0);
+		const int nc[3] = {n0 < 0 ? 0 : n0, n1 < 0 ? 0 : n1, n2 < 0 ? 0 : n2};  // see stranded_setup: no-ops on a valid batch
+		v.cum[0 * (P + 1) + i + 1] = nc[0]; v.cum[1 * (P + 1) + i + 1] = nc[1]; v.cum[2 * (P + 1) + i + 1] = nc[2];
+		v.Ntot[i] = nc[0] + nc[1] + nc[2];
+		for (int k = 0; k < 3; k++) v.alt[k * P + i] = min(max(r[altal + 8 * k] - (altal == refbase ? dd[k] : 0), 0), nc[k]);
 		const int R = v.alt[i] + v.alt[P + i] + v.alt[2 * P + i];
-		v.terms[i] = R > 0 ? ncr_lookup(c.ncr_tab, n0 + n1 + n2, R) : 0.0;
+		v.terms[i] = R > 0 ? ncr_lookup(c.ncr_tab, nc[0] + nc[1] + nc[2], R) : 0.0;
 	}
 	for (int k = tid; k < (int)((size_t)P * T * occ_bytes / 4); k += T) reinterpret_cast<uint32_t*>(v.occ)[k] = 0;
 	for (int k = tid; k < v.words * T; k += T) v.touched[k] = 0;
@@ -416,18 +428,25 @@ __device__ inline bool lowcov_setup(const EngineParams& prm, const LowcovView& v
 	if (tid == 0) {
 		double clra = 0.0;
 		uint32_t deepest = 0;  // most reads of one stratum in one pool: decides the counter width of the tail kernel
+		uint32_t maxball = 0;  // most balls one pool can receive in one stratum: must fit the 10-bit fields of the head kernel
 		for (int k = 0; k < 3; k++) {
-			uint32_t cc = 0; int on = 0;
+			uint32_t cc = 0, dk = 0; int on = 0;
 			v.cum[k * (P + 1)] = 0;
-			for (int i = 0; i < P; i++) { deepest = max(deepest, v.cum[k * (P + 1) + i + 1]); cc += v.cum[k * (P + 1) + i + 1]; v.cum[k * (P + 1) + i + 1] = cc; on += v.alt[k * P + i]; }
+			for (int i = 0; i < P; i++) { dk = max(dk, v.cum[k * (P + 1) + i + 1]); cc += v.cum[k * (P + 1) + i + 1]; v.cum[k * (P + 1) + i + 1] = cc; on += v.alt[k * P + i]; }
 			v.sh->tot[k] = (int)cc; v.sh->ones[k] = on;
+			deepest = max(deepest, dk);
+			maxball = max(maxball, min(dk, (uint32_t)on));
 		}
+		v.sh->maxball = (int)maxball;
+		atomicMax(prm.q.counters + 13, (int)maxball);
 		for (int i = 0; i < P; i++) if (v.alt[i] + v.alt[P + i] + v.alt[2 * P + i] > 0) clra += v.terms[i];
 		v.sh->clra = clra;
 		atomicMax(prm.q.counters + 11, (int)deepest);
 	}
 	__syncthreads();
-	if (v.sh->ones[0] + v.sh->ones[1] + v.sh->ones[2] < 2) {
+	// fewer than two alt reads (:42) — or a table whose ball counts do not fit the 10-bit fields of the head kernel: the host
+	// reports CRISPGPU_ERR_UNSUPPORTED for the batch (crispgpu.cu, counters[13]); nothing is sampled from a corrupt layout
+	if (v.sh->ones[0] + v.sh->ones[1] + v.sh->ones[2] < 2 || v.sh->maxball > 1023) {
 		if (tid == 0) { prm.o.ctpval[o] = 0.0; prm.o.perm_k[o] = 0; prm.o.perm_hits[o] = 0; }
 		return false;
 	}

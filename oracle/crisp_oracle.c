@@ -5,7 +5,7 @@
  *
  * It is the checker for the CUDA engine (tests/, __graft_entry__.smoke(), bench.py's cpu_baseline leg) and is
  * never imported, linked or executed by the product path (crisp_b200/).  Parity is PINNED: the reference has no
- * tests or golden vectors of its own, so tests/test_oracle_vs_reference.py checks every function
+ * tests or golden vectors of its own, so tests/test_oracle.py checks every function
  * here against the unmodified reference compiled from /root/reference (oracle/_ref, see oracle/Makefile) and
  * against the committed fixtures in tests/golden/ that were generated from it.
  *
