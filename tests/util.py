@@ -75,3 +75,27 @@ def compare_results(got, want, fp_skip=(), int_skip=(), tol=REL_TOL, allow_flips
             break
     assert not msgs, "\n".join(msgs)
     return int(flips.size)
+
+
+def batch_from_counts(ic, refbase, quality=30):
+    """A consistent batch for hand-made per-pool allele counts ic[n][P][24] (forward / reverse entries only): one read of the
+    given quality per counted base, alleles sorted as the reference does."""
+    from crisp_b200.abi import Batch
+    from crisp_b200.synth import sort_alleles
+    ic = np.asarray(ic, dtype=np.int32)
+    n, P, _ = ic.shape
+    assert ic[:, :, 16:].sum() == 0
+    refbase = np.asarray(refbase, dtype=np.uint8)
+    counts = ic.sum(axis=1)
+    al, ct = sort_alleles(counts.reshape(n, 3, 8).sum(axis=1), refbase)
+    reads, per = [], np.zeros(n * P, np.int64)
+    for s in range(n):
+        for i in range(P):
+            for idx in np.nonzero(ic[s, i, :16])[0]:
+                base, rev = int(idx) % 8, int(idx) // 8
+                w = ((quality + 33) & 0xFF) | ((base & 3) << 8) | (rev << 10)
+                reads.extend([w] * int(ic[s, i, idx]))
+                per[s * P + i] += int(ic[s, i, idx])
+    return Batch(P, tid=np.zeros(n, np.int32), pos=1000 + 100 * np.arange(n, dtype=np.int32), refbase=refbase, maxvec_al=al.reshape(-1),
+                 maxvec_ct=ct.reshape(-1), counts=counts.reshape(-1), indcounts=ic.reshape(-1), reads=np.asarray(reads, np.uint16),
+                 read_off=np.concatenate([[0], np.cumsum(per)]).astype(np.uint32))
