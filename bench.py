@@ -437,7 +437,7 @@ def main():
     # spinning waits are faster, but only while every waiting thread has a core of its own
     oversubscribed = world * (want_ctx + 1) > (os.cpu_count() or 8) // 2
     cfg = EngineConfig(ploidy=np.full(wl["P"], wl["ploidy"]), options=wl["options"])
-    cfg_e2e = EngineConfig(ploidy=np.full(wl["P"], wl["ploidy"]), options=dict(wl["options"], blocking_wait=1 if oversubscribed else 0))
+    cfg_e2e = EngineConfig(ploidy=np.full(wl["P"], wl["ploidy"]), options=dict(wl["options"], blocking_wait=1 if oversubscribed else 0, minimal_results=1))   # as host/crisp_frontend.c asks for them
     # region shard of this rank: its own contiguous run of candidate sites (tid = rank)
     batch = make_batch(wl, args.sites, seed=1 + rank, tid=rank)
     compact_batch = batch.compact()

@@ -57,7 +57,7 @@ class Config(C.Structure):
         ("exact_mode", C.c_int32),
         ("use_qv", C.c_int32),
         ("blocking_wait", C.c_int32),
-        ("reserved3", C.c_int32),
+        ("minimal_results", C.c_int32),
     ]
 
 
@@ -160,7 +160,7 @@ def default_config_dict() -> dict:
         varpoolsize=0, em_flag=1, max_iter=20000, chisq_permutation=0, fast_filter=1, use_base_qvs=1,
         min_reads=4, qv_offset=33, min_q=13, pivot_sample=0, association=0, thresh1=-3.5, min_qpv=-5.0,
         thresh3=-2.0, ser=-1.0, relax=0.75, qmin=23.0, agilent_ref_bias=0.5, theta=0.001, rng_seed=1,
-        exact_mode=0, use_qv=0, blocking_wait=0,
+        exact_mode=0, use_qv=0, blocking_wait=0, minimal_results=0,
     )
 
 

@@ -106,6 +106,8 @@ struct crispgpu_ctx {
 	int n_call = 0, n_call1 = 0, n_call2 = 0, n_perm = 0;
 	int64_t stage1_launches = 0;
 	bool fetch_pending = false;
+	bool rows_on_host = false;     // k_em wrote the AC/QV rows of the batch into pinned host memory
+	std::vector<unsigned char> zeros;  // host view of result fields this configuration never produces
 	char err[512] = {0};
 };
 
@@ -154,13 +156,16 @@ int ensure_host(crispgpu_ctx* ctx, DevBuf& b, size_t bytes)
 }
 
 // result arrays in the order of DevOut / crispgpu_results; width = elements per site
-struct OutField { size_t elem; int width; };
+// need: which configurations read the field on the host — 0 always (what print_pooledvariant consumes), 1 only with --EM 0,
+// 2 diagnostics (dropped with config.minimal_results), 3 only in permutation mode, 4 only with --phenotypes.  A context lays
+// its result arena out with the fields it needs first and copies only that prefix device-to-host; the others stay zero.
+struct OutField { size_t elem; int width; int need; };
 const OutField kOutFields[] = {
-	{4, 1}, {4, 1},                 // varalleles, strandpass
-	{1, 5}, {1, 5}, {1, 5}, {4, 5}, // status, allele, call_rank, call_row
-	{8, 5}, {8, 5}, {8, 5}, {8, 5}, {8, 5}, {8, 5}, {8, 5}, {8, 5}, {8, 5},  // paf ctpval chi2pval af_ml delta deltaf hwe qvpf qvpr
-	{4, 5}, {4, 5}, {4, 5}, {4, 5}, {4, 5}, {4, 5},  // varpools allelecount variantpools em_iters perm_k perm_hits
-	{8, 5}, {8, 5}, {8, 5}, {8, 5}, {8, 5}, {8, 5},  // assoc_p assoc_llr assoc_or assoc_p1 assoc_llr1 assoc_or1
+	{4, 1, 0}, {4, 1, 1},                 // varalleles, strandpass
+	{1, 5, 0}, {1, 5, 0}, {1, 5, 0}, {4, 5, 0}, // status, allele, call_rank, call_row
+	{8, 5, 2}, {8, 5, 0}, {8, 5, 2}, {8, 5, 0}, {8, 5, 0}, {8, 5, 0}, {8, 5, 0}, {8, 5, 1}, {8, 5, 1},  // paf ctpval chi2pval af_ml delta deltaf hwe qvpf qvpr
+	{4, 5, 0}, {4, 5, 0}, {4, 5, 0}, {4, 5, 2}, {4, 5, 3}, {4, 5, 3},  // varpools allelecount variantpools em_iters perm_k perm_hits
+	{8, 5, 4}, {8, 5, 4}, {8, 5, 4}, {8, 5, 4}, {8, 5, 4}, {8, 5, 4},  // assoc_p assoc_llr assoc_or assoc_p1 assoc_llr1 assoc_or1
 };
 constexpr int kNumOut = sizeof(kOutFields) / sizeof(kOutFields[0]);
 // DevOut, crispgpu_results and DevBatch are walked as arrays of pointers in the order of kOutFields / collect_arrays
@@ -464,18 +469,30 @@ int ensure_outputs(crispgpu_ctx* ctx, int n)
 {
 	// all per-site / per-slot result arrays live back to back (256-byte aligned) in one device arena mirrored by one pinned
 	// host arena, so that a batch's results come home in a single copy
-	size_t off[kNumOut + 1];
-	off[0] = 0;
-	for (int f = 0; f < kNumOut; f++) off[f + 1] = off[f] + (((size_t)n * kOutFields[f].width * kOutFields[f].elem + 255) & ~size_t(255));
-	int rc = ensure_dev(ctx, ctx->d_out_arena, off[kNumOut]);
+	const crispgpu_config& g = ctx->cfg;
+	auto needed = [&](int need) {
+		return need == 0 || (need == 1 && g.em_flag == 0) || (need == 2 && !g.minimal_results) || (need == 3 && g.chisq_permutation == 1) ||
+		       (need == 4 && g.association == 1);
+	};
+	size_t off[kNumOut], total = 0, copy_bytes = 0;
+	for (int pass = 0; pass < 2; pass++) {  // needed fields first, then the rest (device-only scratch the kernels still write)
+		for (int f = 0; f < kNumOut; f++) {
+			if (needed(kOutFields[f].need) != (pass == 0)) continue;
+			off[f] = total;
+			total += ((size_t)n * kOutFields[f].width * kOutFields[f].elem + 255) & ~size_t(255);
+		}
+		if (pass == 0) copy_bytes = total;
+	}
+	int rc = ensure_dev(ctx, ctx->d_out_arena, total);
 	if (rc) return rc;
-	rc = ensure_host(ctx, ctx->h_out_arena, off[kNumOut]);
+	rc = ensure_host(ctx, ctx->h_out_arena, copy_bytes);
 	if (rc) return rc;
+	if (ctx->zeros.size() < (size_t)n * 40) ctx->zeros.assign((size_t)n * 40 + 4096, 0);  // what the fields that are never copied read as
 	for (int f = 0; f < kNumOut; f++) {
 		ctx->d_o[f].p = static_cast<unsigned char*>(ctx->d_out_arena.p) + off[f];
-		ctx->h_o[f].p = static_cast<unsigned char*>(ctx->h_out_arena.p) + off[f];
+		ctx->h_o[f].p = needed(kOutFields[f].need) ? static_cast<void*>(static_cast<unsigned char*>(ctx->h_out_arena.p) + off[f]) : static_cast<void*>(ctx->zeros.data());
 	}
-	ctx->out_bytes = off[kNumOut];
+	ctx->out_bytes = copy_bytes;
 	rc = ensure_dev(ctx, ctx->d_perm_tasks, (size_t)n * 5 * 4);
 	if (rc) return rc;
 	rc = ensure_dev(ctx, ctx->d_call_tasks, (size_t)n * 5 * 4);
@@ -772,9 +789,21 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 	}
 	const int rows = g.em_flag >= 1 ? ctx->n_call : 0;
 	if (rows > 0) {
-		rc = ensure_dev(ctx, ctx->d_rows, (size_t)rows * ctx->P * 12); if (rc) return rc;
-		ctx->d_qv.p = ctx->d_rows.p;
-		ctx->d_ac.p = static_cast<unsigned char*>(ctx->d_rows.p) + (size_t)rows * ctx->P * 8;
+		// The per-pool rows (allele counts, genotype qualities) are indexed by EM task, but only called alleles have one:
+		// when the results go to the host k_em writes them straight into the pinned host buffer (mapped, same address under
+		// unified addressing), so only the rows of called alleles cross the link — a third of the tasks at the benchmark
+		// shape — and no copy is enqueued for them.  Device-resident runs keep them in device memory.
+		if (fetch) {
+			rc = ensure_host(ctx, ctx->h_rows, (size_t)rows * ctx->P * 12); if (rc) return rc;
+			ctx->h_qv.p = ctx->h_rows.p;
+			ctx->h_ac.p = static_cast<unsigned char*>(ctx->h_rows.p) + (size_t)rows * ctx->P * 8;
+			ctx->d_qv.p = ctx->h_qv.p;
+			ctx->d_ac.p = ctx->h_ac.p;
+		} else {
+			rc = ensure_dev(ctx, ctx->d_rows, (size_t)rows * ctx->P * 12); if (rc) return rc;
+			ctx->d_qv.p = ctx->d_rows.p;
+			ctx->d_ac.p = static_cast<unsigned char*>(ctx->d_rows.p) + (size_t)rows * ctx->P * 8;
+		}
 		prm = make_params(ctx);
 	}
 	if (ctx->n_call > 0) {
@@ -848,13 +877,7 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 			CK(cudaMemcpyAsync(ctx->h_out_arena.p, ctx->d_out_arena.p, ctx->out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
 			d2h += (int64_t)ctx->out_bytes;
 		}
-		if (rows > 0) {
-			rc = ensure_host(ctx, ctx->h_rows, (size_t)rows * ctx->P * 12); if (rc) return rc;
-			ctx->h_qv.p = ctx->h_rows.p;
-			ctx->h_ac.p = static_cast<unsigned char*>(ctx->h_rows.p) + (size_t)rows * ctx->P * 8;
-			CK(cudaMemcpyAsync(ctx->h_rows.p, ctx->d_rows.p, (size_t)rows * ctx->P * 12, cudaMemcpyDeviceToHost, ctx->stream));
-			d2h += (int64_t)rows * ctx->P * 12;
-		}
+		ctx->rows_on_host = rows > 0;  // their bytes are counted once the number of called alleles is known (crispgpu_wait)
 	}
 	CK(cudaEventRecord(ctx->ev[EV_D2H], ctx->stream));
 	if (ctx->ev_done) CK(cudaEventRecord(ctx->ev_done, ctx->stream));
@@ -1195,6 +1218,14 @@ int crispgpu_wait(crispgpu_ctx* ctx, int64_t ticket, crispgpu_results* out)
 	CK(cudaEventSynchronize(ctx->ev_done ? ctx->ev_done : ctx->ev[EV_D2H]));
 	ctx->timing_pending = true;
 	fill_results(ctx, out);
+	if (ctx->rows_on_host) {
+		// the rows k_em wrote across the link: one per called allele
+		int64_t called = 0;
+		const int32_t* va = ctx->res.varalleles;
+		for (int s2 = 0; s2 < ctx->n_sites; s2++) called += va[s2];
+		ctx->timing.d2h_bytes += called * ctx->P * 12;
+		ctx->rows_on_host = false;
+	}
 	return CRISPGPU_OK;
 }
 

@@ -168,6 +168,7 @@ static void fill_config(struct VARIANT* variant)
 	c->agilent_ref_bias = AGILENT_REF_BIAS;
 	c->theta = THETA;
 	c->use_qv = USE_QV;
+	c->minimal_results = 1;  /* the printer reads no diagnostic field */
 	c->rng_seed = getenv("CRISPGPU_SEED") ? strtoull(getenv("CRISPGPU_SEED"), NULL, 10) : 1;
 	c->exact_mode = getenv("CRISPGPU_EXACT") ? atoi(getenv("CRISPGPU_EXACT")) : 0;
 }

@@ -81,7 +81,10 @@ typedef struct crispgpu_config {
 	int32_t use_qv;            /* USE_QV (--weighted), readmultiplebams.c:24: how remove_ambiguous_bases adjusts Qhighcounts */
 	int32_t blocking_wait;     /* 1: crispgpu_wait sleeps on the result event instead of spinning a core — for front ends
 	                              that keep more contexts waiting than the host has idle cores (adds wake-up latency) */
-	int32_t reserved3;
+	int32_t minimal_results;   /* 1: crispgpu_results carries only what print_pooledvariant reads; the diagnostic fields (paf, chi2pval,
+	                              em_iters) are not copied back and read as 0.  Fields no configuration of this context can
+	                              produce (assoc_* without --phenotypes, qvpf/qvpr/strandpass with --EM 1, perm_k/perm_hits
+	                              without --chisquare 0) are never copied and always read as 0. */
 } crispgpu_config;
 
 /* One packed read of the per-site pileup snapshot: what calculate_pooled_likelihoods_snp
