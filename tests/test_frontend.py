@@ -217,9 +217,13 @@ def test_bam_to_vcf_on_gpu_equals_reference(name, compact, datasets, tmp_path):
         assert cmp["same"] == len(want) == st["records"]
         return
     perms = int(extra[extra.index("--perms") + 1])
-    # a record may appear/disappear only if its CT sits at a FAST_FILTER threshold (-3 / -2, newcrispcaller.c:122-127)
-    flips = cmp["only_got"] + cmp["only_want"]
-    assert len(flips) <= max(1, len(want) // 10), flips
+    # a record may appear/disappear only if its Monte-Carlo CT sits at a FAST_FILTER threshold (-3 / -2, newcrispcaller.c:
+    # 122-127; the reference seeds drand48 with the time of day, so its own records flip from run to run there)
+    by_key = {(r[0], int(r[1]), r[3]): r for r in got + want}
+    for k in cmp["only_got"] + cmp["only_want"]:
+        cts = [float(x) for x in re.search(r"CT=([^;]*)", by_key[k][7]).group(1).split(",")]
+        assert any(-3.7 <= c <= -1.5 for c in cts), (k, cts)
+    assert len(cmp["only_got"]) + len(cmp["only_want"]) <= max(2, len(want) // 4)
     assert not cmp["differ"], cmp["differ"]
     bad = [c for c in cmp["ct"] if not all(_ct_ok(x, y, perms) for x, y in zip(c[1].split(","), c[2].split(",")))]
     assert not bad, bad
@@ -242,6 +246,10 @@ def test_config1_bam_to_vcf(tmp_path):
         if not extra:
             assert not cmp["only_got"] and not cmp["only_want"] and cmp["same"] == len(want)
         else:
-            assert len(cmp["only_got"]) + len(cmp["only_want"]) <= 4, (cmp["only_got"], cmp["only_want"])
+            by_key = {(r[0], int(r[1]), r[3]): r for r in got + want}
+            for k in cmp["only_got"] + cmp["only_want"]:
+                cts = [float(x) for x in re.search(r"CT=([^;]*)", by_key[k][7]).group(1).split(",")]
+                assert any(-3.7 <= c <= -1.5 for c in cts), (k, cts)
+            assert len(cmp["only_got"]) + len(cmp["only_want"]) <= 8, (cmp["only_got"], cmp["only_want"])
             bad = [c for c in cmp["ct"] if not all(_ct_ok(x, y, 20000) for x, y in zip(c[1].split(","), c[2].split(",")))]
             assert not bad, bad
