@@ -360,7 +360,67 @@ def bam_end_to_end(cores: int):
                                              "pack_s": st["pack_s"], "engine_s": st["engine_s"], "device_s": st["device_s"], "print_s": st["print_s"],
                                              "batches": st["batches"], "h2d_bytes": st["h2d_bytes"], "d2h_bytes": st["d2h_bytes"]},
                     "note": "the front end (BAM decode + pileup, unchanged reference C, one process) is what remains of the wall time once the engine runs on the GPU"})
+        try:
+            out["device_pileup"] = device_pileup_leg(ds, cores, sites, t_one, sh["wall_s"])
+        except Exception as exc:  # noqa: BLE001
+            out["device_pileup"] = {"error": repr(exc)[:300]}
     return out
+
+
+def device_pileup_leg(ds, cores, frontend_sites, ref_wall_1, ref_wall_regions, local=0, steps=10):
+    """SURVEY.md section 8f items 1-3 on the same BAM files: host/bam_decode.c (host threads) -> crispgpu_pileup_run (allele counting,
+    candidate screen and site packing on the device, then the engine) — no reference code in the loop.  Reports the decoder's
+    rate, the pileup's resident and end-to-end rates (positions/s, candidate sites/s) and the HBM roofline of k_pile_tile."""
+    import json as _json
+    from crisp_b200.abi import EngineConfig
+    from crisp_b200.engine import Engine
+    from crisp_b200.pileup import decode_bams, make_window, read_fasta
+    P, L = ds["pools"], ds["length"]
+    t0 = time.perf_counter()
+    aln = decode_bams(ds["bams"], threads=cores)
+    t_dec = time.perf_counter() - t0
+    ref = read_fasta(ds["fasta"])
+    eng = Engine(EngineConfig(ploidy=np.full(P, ds["poolsize"]), options=dict(minimal_results=1)), device=local)
+    win = make_window(0, 0, L, ref)
+    for _ in range(3):
+        n_sites, res = eng.pileup_run(aln, win, want_sites=False)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        n_sites, res = eng.pileup_run(aln, win, want_sites=False)
+    e2e = (time.perf_counter() - t0) / steps
+    t_e2e = eng.timing()
+    eng.pileup_upload(aln, win)
+    for _ in range(3):
+        eng.pileup_run_resident(False)
+    acc = {"pileup_ms": 0.0, "pile_tile_ms": 0.0, "total_ms": 0.0}
+    for _ in range(steps):
+        eng.pileup_run_resident(False)
+        t = eng.timing()
+        for k in acc:
+            acc[k] += t[k] / steps
+    eng.close()
+    peaks = {}
+    try:
+        peaks = _json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    gbs = t["pile_bytes"] / (acc["pile_tile_ms"] * 1e-3) / 1e9
+    called = int((res.varalleles >= 1).sum())
+    return {"what": "BAM files -> host/bam_decode.c -> crispgpu_pileup_run (pileup, screen, packing, engine on the device); same files as above",
+            "alignments": aln.n_reads, "bases": aln.n_bases, "positions": L, "candidate_sites": int(n_sites), "candidate_sites_reference_frontend": frontend_sites,
+            "called_sites": called,
+            "decode": {"wall_s": round(t_dec, 4), "threads": cores, "compressed_MBps": aln.stats["compressed_bytes"] / t_dec / 1e6, "alignments_per_s": aln.n_reads / t_dec,
+                       "inflate_s": round(aln.stats["inflate_s"], 4), "parse_s": round(aln.stats["parse_s"], 4), "read_s": round(aln.stats["read_s"], 4)},
+            "e2e": {"ms_per_window": e2e * 1e3, "positions_per_s": L / e2e, "candidate_sites_per_s": n_sites / e2e, "h2d_bytes": int(t_e2e["h2d_bytes"]), "d2h_bytes": int(t_e2e["d2h_bytes"]),
+                    "what": "crispgpu_pileup_run from pinned host memory: H2D of the alignments + pileup + engine + D2H of the results, one context, synchronous"},
+            "resident": {"pileup_ms": acc["pileup_ms"], "pile_tile_ms": acc["pile_tile_ms"], "total_ms": acc["total_ms"], "positions_per_s": L / (acc["total_ms"] * 1e-3),
+                         "candidate_sites_per_s": n_sites / (acc["total_ms"] * 1e-3)},
+            "roofline": {"kernel": "k_pile_tile", "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": None,
+                         "algorithmic_bytes": int(t["pile_bytes"]), "ms_per_launch": acc["pile_tile_ms"],
+                         "bytes_definition": "16 per alignment + 1.5 per base (4-bit base + quality byte) + 32 per (position, pool) cell of the count table written"},
+            "bam_to_calls": {"wall_s": round(t_dec + e2e, 4), "vs_reference_1_process": ref_wall_1 / (t_dec + e2e), "vs_reference_regions": ref_wall_regions / (t_dec + e2e),
+                             "what": "decode (host threads) + one crispgpu_pileup_run, against CRISP.binary's wall time on the same files (VCF text not written here)"}}
 
 
 def main():

@@ -13,7 +13,7 @@ from typing import Optional
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAXALLELES = 8
 NCOUNT = 24
 MAXSLOTS = 5
@@ -151,6 +151,11 @@ class Timing(C.Structure):
         ("h2d_bytes", C.c_int64),
         ("d2h_bytes", C.c_int64),
         ("fetched_bytes", C.c_int64),
+        ("pileup_ms", C.c_float),
+        ("pile_tile_ms", C.c_float),
+        ("n_positions", C.c_int32),
+        ("n_alignments", C.c_int32),
+        ("pile_bytes", C.c_int64),
     ]
 
 

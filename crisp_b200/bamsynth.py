@@ -26,7 +26,7 @@ READLEN = 100
 QUALS = np.array([20, 25, 30, 35, 40], dtype=np.uint8)
 QPROB = np.array([0.05, 0.10, 0.25, 0.35, 0.25])
 BASES = np.frombuffer(b"ACGT", dtype=np.uint8)
-NT16 = np.array([1, 2, 4, 8], dtype=np.uint8)  # A C G T in BAM's 4-bit code
+NT16 = np.array([1, 2, 4, 8, 15], dtype=np.uint8)  # A C G T N in BAM's 4-bit code
 
 _BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
 
@@ -84,7 +84,7 @@ def _pack_records(tid, pos, flag, mapq, cigars, seq, qual, names, mpos, isize):
         rec["tid"] = tid
         rec["pos"] = pos[m]
         rec["l_name"] = L
-        rec["mapq"] = mapq
+        rec["mapq"] = mapq[m] if isinstance(mapq, np.ndarray) else mapq
         rec["bin"] = bins[m]
         rec["ncig"] = nc
         rec["flag"] = flag[m]
@@ -115,8 +115,13 @@ def write_reference(path: str, name: str, seq: np.ndarray, width: int = 60) -> N
 
 
 def make_dataset(outdir: str, pools: int, poolsize: int, length: int, depth: float, seed: int = 1, spacing: int = 500,
-                 indel_frac: float = 0.0, pe_frac: float = 0.0, chrom: str = "chr1", qual_values=None, qual_probs=None) -> dict:
-    """Write ref.fa(.fai), pool_XX.bam and bams.list under outdir; return the planted truth."""
+                 indel_frac: float = 0.0, pe_frac: float = 0.0, chrom: str = "chr1", qual_values=None, qual_probs=None,
+                 lowmapq_frac: float = 0.0, noisy_frac: float = 0.0, clip_frac: float = 0.0, n_frac: float = 0.0) -> dict:
+    """Write ref.fa(.fai), pool_XX.bam and bams.list under outdir; return the planted truth.
+
+    What the read filters of calculate_allelecounts (parsebam/variant.c:286-302) look at can be switched on: `lowmapq_frac` of
+    the reads get a mapping quality from {0, 5, 15, 25, 37}, `noisy_frac` carry 3-8 extra mismatches (the MAX_MM filter),
+    `clip_frac` of the gap-free single-end reads are soft-clipped at one or both ends, `n_frac` of the bases read 'N'."""
     os.makedirs(outdir, exist_ok=True)
     rng = np.random.default_rng(seed)
     qv = QUALS if qual_values is None else np.asarray(qual_values, dtype=np.uint8)
@@ -207,14 +212,37 @@ def make_dataset(outdir: str, pools: int, poolsize: int, length: int, depth: flo
         qual = qv[rng.choice(qv.shape[0], size=(n, READLEN), p=qp)]
         err = rng.random((n, READLEN)) < 10.0 ** (-qual.astype(np.float64) / 10.0)
         seq = np.where(err, (seq + rng.integers(1, 4, size=(n, READLEN))) % 4, seq).astype(np.uint8)
-        order = np.argsort(start, kind="stable")
+        mapq = np.full(n, 60, dtype=np.int64)
+        pos = start.copy()
+        if lowmapq_frac > 0:
+            m = rng.random(n) < lowmapq_frac
+            mapq[m] = rng.choice([0, 5, 15, 25, 37], size=int(m.sum()))
+        if noisy_frac > 0:
+            for r in np.nonzero(rng.random(n) < noisy_frac)[0]:
+                at = rng.choice(READLEN, size=int(rng.integers(3, 9)), replace=False)
+                seq[r, at] = (seq[r, at] + rng.integers(1, 4, size=at.shape[0])) % 4
+        if clip_frac > 0:
+            plain = (cig[:, 1] == 0) & (mpos < 0)
+            for r in np.nonzero(plain & (rng.random(n) < clip_frac))[0]:
+                lead = int(rng.integers(0, 11)) if rng.random() < 0.7 else 0
+                trail = int(rng.integers(1, 11)) if (lead == 0 or rng.random() < 0.5) else 0
+                ops = ([(lead << 4) | 4] if lead else []) + [((READLEN - lead - trail) << 4) | 0] + ([(trail << 4) | 4] if trail else [])
+                cig[r, :] = 0
+                cig[r, :len(ops)] = ops
+                pos[r] = start[r] + lead
+                seq[r, :lead] = rng.integers(0, 4, size=lead)
+                if trail:
+                    seq[r, READLEN - trail:] = rng.integers(0, 4, size=trail)
+        if n_frac > 0:
+            seq = np.where(rng.random((n, READLEN)) < n_frac, 4, seq).astype(np.uint8)
+        order = np.argsort(pos, kind="stable")
         names = np.zeros((n, 10), dtype=np.uint8)
         digits = fragment.copy()
         for c in range(8, -1, -1):
             names[:, c] = 48 + digits % 10
             digits //= 10
         names[:, 0] = ord("r")
-        recs = _pack_records(0, start[order].astype(np.int32), flag[order], 60, cig[order], seq[order], qual[order], names[order],
+        recs = _pack_records(0, pos[order].astype(np.int32), flag[order], mapq[order], cig[order], seq[order], qual[order], names[order],
                              mpos[order], isize[order])
         path = os.path.join(outdir, f"pool_{p:03d}.bam")
         with open(path, "wb") as f:

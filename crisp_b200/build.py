@@ -9,12 +9,29 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libcrispgpu.so")
 SOURCES = ["crispgpu.cu"]
-HEADERS = ["dmath.cuh", "engine_types.cuh", "k_evaluate.cuh", "k_em.cuh", "k_permute.cuh", "k_legacy.cuh",
+HEADERS = ["dmath.cuh", "engine_types.cuh", "k_evaluate.cuh", "k_em.cuh", "k_permute.cuh", "k_legacy.cuh", "k_pileup.cuh",
            os.path.join("..", "..", "include", "crispgpu.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared", "--fmad=true", "-Xptxas", "-v",
 ]
+
+
+BAMLIB = os.path.join(CSRC, "libcrispbam.so")
+HOST = os.path.join(HERE, "..", "host")
+
+
+def build_bam_decoder(force: bool = False) -> str:
+    """host/bam_decode.c (parallel BGZF inflate + BAM record split, plain C with zlib and pthreads) -> csrc/libcrispbam.so."""
+    src = [os.path.join(HOST, "bam_decode.c"), os.path.join(HOST, "bam_decode.h"), os.path.join(HERE, "..", "include", "crispgpu.h")]
+    if not force and os.path.exists(BAMLIB) and all(os.path.getmtime(f) <= os.path.getmtime(BAMLIB) for f in src):
+        return BAMLIB
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-std=gnu99", "-Wall", "-fPIC", "-shared", "-o", BAMLIB, src[0], "-lz", "-lpthread"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("gcc failed building libcrispbam.so")
+    return BAMLIB
 
 
 def needs_build() -> bool:
@@ -25,6 +42,7 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    build_bam_decoder(force)
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -21,6 +21,7 @@
 #include "k_evaluate.cuh"
 #include "k_legacy.cuh"
 #include "k_permute.cuh"
+#include "k_pileup.cuh"
 
 using namespace crisp;
 
@@ -108,6 +109,15 @@ struct crispgpu_ctx {
 	bool fetch_pending = false;
 	bool rows_on_host = false;     // k_em wrote the AC/QV rows of the batch into pinned host memory
 	std::vector<unsigned char> zeros;  // host view of result fields this configuration never produces
+	// pileup on the device (crispgpu_pileup_run)
+	DevBuf p_pool_off, p_rec, p_mate, p_isize, p_seq4, p_qual, p_ref, p_flags, p_state, p_win, p_flag, p_cand;
+	DevBuf p_sites, p_work, p_reads, p_alt;   // site arrays (mirrored on the host), scan scratch, read stream, alt-read lists
+	DevBuf ph_state, ph_sites, ph_reads, ph_alt;
+	PileReads prd{};
+	PileWindow pwin{};
+	bool pile_resident = false, pile_timing = false, pile_streams = false;
+	int64_t pile_h2d = 0;
+	cudaEvent_t ev_pile[4]{};       // pileup start, k_pile_tile start / end, pileup end
 	char err[512] = {0};
 };
 
@@ -903,7 +913,14 @@ void fill_results(crispgpu_ctx* ctx, crispgpu_results* out)
 int finish_timing(crispgpu_ctx* ctx)
 {
 	crispgpu_timing& t = ctx->timing;
-	CK(cudaEventElapsedTime(&t.h2d_ms, ctx->ev[EV_START], ctx->ev[EV_H2D]));
+	if (ctx->pile_timing) {
+		CK(cudaEventElapsedTime(&t.h2d_ms, ctx->ev[EV_START], ctx->ev_pile[0]));
+		CK(cudaEventElapsedTime(&t.pileup_ms, ctx->ev_pile[0], ctx->ev_pile[3]));
+		CK(cudaEventElapsedTime(&t.pile_tile_ms, ctx->ev_pile[1], ctx->ev_pile[2]));
+	} else {
+		CK(cudaEventElapsedTime(&t.h2d_ms, ctx->ev[EV_START], ctx->ev[EV_H2D]));
+		t.pileup_ms = t.pile_tile_ms = 0.f;
+	}
 	CK(cudaEventElapsedTime(&t.evaluate_ms, ctx->ev[EV_H2D], ctx->ev[EV_EVAL]));
 	CK(cudaEventElapsedTime(&t.permute_ms, ctx->ev[EV_EVAL], ctx->ev[EV_PERM]));
 	CK(cudaEventElapsedTime(&t.filter_ms, ctx->ev[EV_PERM], ctx->ev[EV_FILTER]));
@@ -1161,6 +1178,10 @@ void crispgpu_destroy(crispgpu_ctx* ctx)
 	fd(ctx->d_rows); fh(ctx->h_rows); fd(ctx->d_arena);
 	fd(ctx->d_tail_task); fd(ctx->d_tail_head); fd(ctx->d_tail_total); fd(ctx->d_tail_rec); fd(ctx->d_tail_counters);
 	fd(ctx->d_perm_tasks); fd(ctx->d_call_tasks); fd(ctx->d_call_tasks2); fd(ctx->d_counters); fh(ctx->h_counters); fd(ctx->d_gws);
+	fd(ctx->p_pool_off); fd(ctx->p_rec); fd(ctx->p_mate); fd(ctx->p_isize); fd(ctx->p_seq4); fd(ctx->p_qual); fd(ctx->p_ref); fd(ctx->p_flags);
+	fd(ctx->p_state); fd(ctx->p_win); fd(ctx->p_flag); fd(ctx->p_cand); fd(ctx->p_sites); fd(ctx->p_work); fd(ctx->p_reads); fd(ctx->p_alt);
+	fh(ctx->ph_state); fh(ctx->ph_sites); fh(ctx->ph_reads); fh(ctx->ph_alt);
+	for (auto& e : ctx->ev_pile) if (e) cudaEventDestroy(e);
 	for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
 	if (ctx->ev_counts) cudaEventDestroy(ctx->ev_counts);
 	if (ctx->ev_epoch) cudaEventDestroy(ctx->ev_epoch);
@@ -1181,6 +1202,7 @@ int crispgpu_submit(crispgpu_ctx* ctx, const crispgpu_batch* batch, int64_t* tic
 	}
 	CK(cudaSetDevice(ctx->device));
 	ctx->timing_pending = false;  // the stage events are about to be reused: read crispgpu_get_timing between wait and the next submit
+	ctx->pile_timing = false;
 	CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
 	int rc = copy_batch(ctx, batch, true);
 	if (rc) return rc;
@@ -1263,6 +1285,251 @@ int crispgpu_screen_positions(crispgpu_ctx* ctx, int32_t n, const uint8_t* refba
 	return CRISPGPU_OK;
 }
 
+
+namespace {
+
+struct SiteLayout {   // the candidate-site arrays of a window in one arena (device) mirrored by one pinned arena (host)
+	size_t tid, pos, refbase, maxvec_al, maxvec_ct, counts, indcounts, readdepths, mqcounts, filtered, read_off, alt_off, copy_bytes;
+	size_t cell_reads, alt_len, alt_cell_off, total;
+};
+
+SiteLayout site_layout(size_t n, size_t P)
+{
+	SiteLayout L{};
+	size_t o = 0;
+	auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 255) & ~size_t(255); return at; };
+	L.tid = take(n * 4); L.pos = take(n * 4); L.refbase = take(n); L.maxvec_al = take(n * 8); L.maxvec_ct = take(n * 32);
+	L.counts = take(n * kNC * 4); L.indcounts = take(n * P * kNC * 4); L.readdepths = take(n * P * 4); L.mqcounts = take(n * 16);
+	L.filtered = take(n * 8); L.read_off = take((n * P + 1) * 4); L.alt_off = take((n * 5 + 1) * 4);
+	L.copy_bytes = o;
+	L.cell_reads = take(n * P * 4); L.alt_len = take(n * 5 * P * 4); L.alt_cell_off = take((n * 5 * P + 1) * 4);
+	L.total = o;
+	return L;
+}
+
+int pile_upload(crispgpu_ctx* ctx, const crispgpu_alignments* aln, const crispgpu_window* win)
+{
+	if (!aln || !win || aln->n_pools != ctx->P || !aln->pool_off || !win->refseq || win->end < win->start || win->ref_len < 0) {
+		snprintf(ctx->err, sizeof ctx->err, "pileup: missing array, pool count different from the context's, or an inverted window");
+		return CRISPGPU_ERR_ARG;
+	}
+	if (ctx->cfg.em_flag == 0) {
+		snprintf(ctx->err, sizeof ctx->err, "pileup: the legacy caller (--EM 0) reads the per-pool error sums (variant->stats), which the device pileup does not accumulate");
+		return CRISPGPU_ERR_UNSUPPORTED;
+	}
+	const size_t P = ctx->P, R = aln->pool_off[P];
+	if (R && (!aln->rec || !aln->seq4 || !aln->qual)) return CRISPGPU_ERR_ARG;
+	if ((aln->n_bases & 7) || aln->n_bases >= (1ull << 32)) { snprintf(ctx->err, sizeof ctx->err, "pileup: n_bases must be a multiple of 8 below 2^32"); return CRISPGPU_ERR_ARG; }
+	int rc;
+	int64_t bytes = 0;
+	auto up = [&](DevBuf& b, const void* src, size_t n) -> int {
+		int r2 = ensure_dev(ctx, b, n ? n : 16);
+		if (r2) return r2;
+		if (n) CK(cudaMemcpyAsync(b.p, src, n, cudaMemcpyHostToDevice, ctx->stream));
+		bytes += (int64_t)n;
+		return 0;
+	};
+	if ((rc = up(ctx->p_pool_off, aln->pool_off, (P + 1) * 4)) || (rc = up(ctx->p_rec, aln->rec, R * sizeof(crispgpu_alnrec))) ||
+	    (rc = up(ctx->p_seq4, aln->seq4, aln->n_bases / 2)) || (rc = up(ctx->p_qual, aln->qual, aln->n_bases)) ||
+	    (rc = up(ctx->p_ref, win->refseq, (size_t)win->ref_len))) return rc;
+	if (aln->mate_pos && (rc = up(ctx->p_mate, aln->mate_pos, R * 4))) return rc;
+	if (aln->mate_pos && aln->isize && (rc = up(ctx->p_isize, aln->isize, R * 4))) return rc;
+	if ((rc = ensure_dev(ctx, ctx->p_flags, R ? R : 16)) || (rc = ensure_dev(ctx, ctx->p_state, 64)) || (rc = ensure_host(ctx, ctx->ph_state, 64))) return rc;
+	PileReads& rd = ctx->prd;
+	rd.P = (int)P; rd.n_reads = (uint32_t)R; rd.n_bases = aln->n_bases;
+	rd.pool_off = static_cast<const uint32_t*>(ctx->p_pool_off.p);
+	rd.rec = static_cast<const crispgpu_alnrec*>(ctx->p_rec.p);
+	rd.mate_pos = aln->mate_pos ? static_cast<const int32_t*>(ctx->p_mate.p) : nullptr;
+	rd.isize = (aln->mate_pos && aln->isize) ? static_cast<const int32_t*>(ctx->p_isize.p) : nullptr;
+	rd.seq4 = static_cast<const uint8_t*>(ctx->p_seq4.p);
+	rd.qual = static_cast<const uint8_t*>(ctx->p_qual.p);
+	rd.flags = static_cast<uint8_t*>(ctx->p_flags.p);
+	rd.state = static_cast<int32_t*>(ctx->p_state.p);
+	PileWindow& w = ctx->pwin;
+	w.tid = win->tid; w.w0 = win->start; w.W = win->end - win->start; w.ref0 = win->ref_start; w.reflen = win->ref_len;
+	w.refseq = static_cast<const uint8_t*>(ctx->p_ref.p);
+	w.min_q = ctx->cfg.min_q; w.min_m = win->min_mapq;
+	ctx->pile_streams = win->want_streams != 0;
+	ctx->pile_h2d = bytes;
+	return 0;
+}
+
+// alignments resident in device memory -> candidate sites packed as the engine's batch -> the engine's two stages
+int pile_run(crispgpu_ctx* ctx, bool fetch, crispgpu_pileup_sites* sites, crispgpu_results* results)
+{
+	const PileReads& rd = ctx->prd;
+	const PileWindow& w = ctx->pwin;
+	const size_t P = ctx->P, W = (size_t)w.W;
+	int rc;
+	for (auto& e : ctx->ev_pile) if (!e) CK(cudaEventCreate(&e));
+	CK(cudaEventRecord(ctx->ev_pile[0], ctx->stream));
+	CK(cudaMemsetAsync(ctx->p_state.p, 0, 64, ctx->stream));
+	int64_t launches = 0;
+	if (rd.n_reads) {
+		const int need = (int)((rd.n_reads + 255) / 256);
+		k_pile_check<<<need < ctx->num_sms * 8 ? need : ctx->num_sms * 8, 256, 0, ctx->stream>>>(rd);
+		CK(launch_check());
+		launches++;
+	}
+	if ((rc = ensure_dev(ctx, ctx->p_win, W * P * kPileCell * 4 + 16)) || (rc = ensure_dev(ctx, ctx->p_flag, W + 16)) || (rc = ensure_dev(ctx, ctx->p_cand, W * 4 + 16))) return rc;
+	uint32_t* d_win = static_cast<uint32_t*>(ctx->p_win.p);
+	CK(cudaEventRecord(ctx->ev_pile[1], ctx->stream));
+	if (W) {
+		const dim3 grid((unsigned)((W + kPileTile - 1) / kPileTile), (unsigned)P);
+		k_pile_tile<<<grid, 256, 0, ctx->stream>>>(rd, w, d_win);
+		CK(launch_check());
+		launches++;
+	}
+	CK(cudaEventRecord(ctx->ev_pile[2], ctx->stream));
+	int32_t* hs = static_cast<int32_t*>(ctx->ph_state.p);
+	if (W) {
+		const int need = (int)((W + 7) / 8);
+		k_pile_screen<<<need < ctx->num_sms * 16 ? need : ctx->num_sms * 16, 256, 0, ctx->stream>>>(d_win, w, (int)P, static_cast<const int32_t*>(ctx->d_ploidy.p), static_cast<uint8_t*>(ctx->p_flag.p));
+		CK(launch_check());
+		k_pile_select<<<1, 1024, 0, ctx->stream>>>(static_cast<const uint8_t*>(ctx->p_flag.p), (int)W, static_cast<int32_t*>(ctx->p_cand.p), rd.state + 2);
+		CK(launch_check());
+		launches += 2;
+	}
+	CK(cudaMemcpyAsync(hs, ctx->p_state.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	if (hs[0]) {
+		snprintf(ctx->err, sizeof ctx->err, "pileup: alignments outside the interface%s%s%s%s%s", (hs[0] & kPileErrAlign) ? "; base_off not a multiple of 8" : "",
+		         (hs[0] & kPileErrBounds) ? "; a read reaches past n_bases (or has an empty match block)" : "", (hs[0] & kPileErrOrder) ? "; a pool's alignments are not in coordinate order" : "",
+		         (hs[0] & kPileErrMate) ? "; overlapping mates (the reference's mate merge is not piled up on the device)" : "", (hs[0] & kPileErrPool) ? "; pool_off is not a partition of the alignments" : "");
+		return (hs[0] & kPileErrMate) ? CRISPGPU_ERR_UNSUPPORTED : CRISPGPU_ERR_ARG;
+	}
+	const size_t n = (size_t)hs[2];
+	const SiteLayout L = site_layout(n ? n : 1, P);
+	if ((rc = ensure_dev(ctx, ctx->p_sites, L.total)) || (rc = ensure_host(ctx, ctx->ph_sites, L.copy_bytes))) return rc;
+	unsigned char* ds = static_cast<unsigned char*>(ctx->p_sites.p);
+	PileSites ps{};
+	ps.n = (int)n;
+	ps.cand = static_cast<const int32_t*>(ctx->p_cand.p);
+	ps.tid = reinterpret_cast<int32_t*>(ds + L.tid); ps.pos = reinterpret_cast<int32_t*>(ds + L.pos); ps.refbase = ds + L.refbase;
+	ps.maxvec_al = ds + L.maxvec_al; ps.maxvec_ct = reinterpret_cast<int32_t*>(ds + L.maxvec_ct); ps.counts = reinterpret_cast<int32_t*>(ds + L.counts);
+	ps.indcounts = reinterpret_cast<int32_t*>(ds + L.indcounts); ps.readdepths = reinterpret_cast<int32_t*>(ds + L.readdepths);
+	ps.mqcounts = reinterpret_cast<int32_t*>(ds + L.mqcounts); ps.filtered = reinterpret_cast<int32_t*>(ds + L.filtered);
+	ps.read_off = reinterpret_cast<uint32_t*>(ds + L.read_off); ps.alt_off = reinterpret_cast<uint32_t*>(ds + L.alt_off);
+	ps.cell_reads = reinterpret_cast<uint32_t*>(ds + L.cell_reads); ps.alt_len = reinterpret_cast<uint32_t*>(ds + L.alt_len);
+	ps.alt_cell_off = reinterpret_cast<uint32_t*>(ds + L.alt_cell_off);
+	size_t n_reads = 0, n_alt = 0;
+	if (n) {
+		const size_t cells = n * P;
+		const int wgrid = (int)((cells + 7) / 8 < (size_t)ctx->num_sms * 16 ? (cells + 7) / 8 : (size_t)ctx->num_sms * 16);
+		k_pile_gather_counts<<<(int)(n < (size_t)ctx->num_sms * 8 ? n : (size_t)ctx->num_sms * 8), 128, 0, ctx->stream>>>(ps, w, (int)P, d_win);
+		CK(launch_check());
+		k_pile_scan<<<1, 1024, 0, ctx->stream>>>(ps.cell_reads, ps.read_off, cells);
+		k_pile_gather_reads<0><<<wgrid, 256, 0, ctx->stream>>>(rd, w, ps);
+		CK(launch_check());
+		k_pile_scan<<<1, 1024, 0, ctx->stream>>>(ps.alt_len, ps.alt_cell_off, cells * 5);
+		CK(launch_check());
+		CK(cudaMemcpyAsync(hs + 4, ps.read_off + cells, 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaMemcpyAsync(hs + 5, ps.alt_cell_off + cells * 5, 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		n_reads = static_cast<uint32_t>(hs[4]);
+		n_alt = static_cast<uint32_t>(hs[5]);
+		if ((rc = ensure_dev(ctx, ctx->p_reads, n_reads * 2 + 16)) || (rc = ensure_dev(ctx, ctx->p_alt, n_alt * sizeof(crispgpu_altread) + 16))) return rc;
+		ps.reads = static_cast<uint16_t*>(ctx->p_reads.p);
+		ps.alt_reads = static_cast<crispgpu_altread*>(ctx->p_alt.p);
+		k_pile_gather_reads<1><<<wgrid, 256, 0, ctx->stream>>>(rd, w, ps);
+		CK(launch_check());
+		k_pile_alt_off<<<(int)((n * 5 + 256) / 256), 256, 0, ctx->stream>>>(ps, (int)P);
+		CK(launch_check());
+		launches += 6;
+	}
+	CK(cudaEventRecord(ctx->ev_pile[3], ctx->stream));
+	// the packed sites are the engine's batch
+	DevBatch& b = ctx->db;
+	b = DevBatch{};
+	b.n_sites = (int)n; b.P = (int)P;
+	b.tid = ps.tid; b.pos = ps.pos; b.refbase = ps.refbase; b.maxvec_al = ps.maxvec_al; b.maxvec_ct = ps.maxvec_ct; b.counts = ps.counts;
+	b.indcounts = ps.indcounts; b.read_off = ps.read_off; b.reads = ps.reads; b.alt_off = ps.alt_off; b.alt_reads = ps.alt_reads;
+	ctx->n_sites = (int)n; ctx->n_reads = n_reads; ctx->n_bins = 0;
+	ctx->binned = false; ctx->sparse_ic = false; ctx->device_sort = false; ctx->lazy_reads = nullptr; ctx->resident = false;
+	ctx->copied_bytes = ctx->pile_h2d;
+	ctx->timing.h2d_bytes = ctx->pile_h2d;
+	if ((rc = run_stage1(ctx)) || (rc = run_stage2(ctx, fetch))) return rc;
+	ctx->timing.launches += launches;
+	ctx->timing.n_positions = (int32_t)W;
+	ctx->timing.n_alignments = (int32_t)rd.n_reads;
+	ctx->timing.pile_bytes = (int64_t)rd.n_reads * 16 + (int64_t)(rd.n_bases + rd.n_bases / 2) + (int64_t)(W * P * kPileCell * 4);
+	if (fetch && n) {
+		CK(cudaMemcpyAsync(ctx->ph_sites.p, ds, L.copy_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+		ctx->timing.d2h_bytes += (int64_t)L.copy_bytes;
+		if (ctx->pile_streams) {
+			if ((rc = ensure_host(ctx, ctx->ph_reads, n_reads * 2 + 16)) || (rc = ensure_host(ctx, ctx->ph_alt, n_alt * sizeof(crispgpu_altread) + 16))) return rc;
+			if (n_reads) CK(cudaMemcpyAsync(ctx->ph_reads.p, ps.reads, n_reads * 2, cudaMemcpyDeviceToHost, ctx->stream));
+			if (n_alt) CK(cudaMemcpyAsync(ctx->ph_alt.p, ps.alt_reads, n_alt * sizeof(crispgpu_altread), cudaMemcpyDeviceToHost, ctx->stream));
+		}
+	}
+	CK(cudaStreamSynchronize(ctx->stream));
+	ctx->pile_timing = true;
+	ctx->timing_pending = true;
+	if (fetch) {
+		fill_results(ctx, results);
+		if (ctx->rows_on_host) {
+			int64_t called = 0;
+			for (size_t s2 = 0; s2 < n; s2++) called += ctx->res.varalleles[s2];
+			ctx->timing.d2h_bytes += called * (int64_t)P * 12;
+			ctx->rows_on_host = false;
+		}
+	}
+	if (sites) {
+		const unsigned char* hsb = static_cast<const unsigned char*>(ctx->ph_sites.p);
+		*sites = crispgpu_pileup_sites{};
+		sites->n_sites = (int32_t)n;
+		sites->n_positions = (int32_t)W;
+		if (fetch && n) {
+			sites->pos = reinterpret_cast<const int32_t*>(hsb + L.pos); sites->refbase = hsb + L.refbase; sites->maxvec_al = hsb + L.maxvec_al;
+			sites->maxvec_ct = reinterpret_cast<const int32_t*>(hsb + L.maxvec_ct); sites->counts = reinterpret_cast<const int32_t*>(hsb + L.counts);
+			sites->indcounts = reinterpret_cast<const int32_t*>(hsb + L.indcounts); sites->readdepths = reinterpret_cast<const int32_t*>(hsb + L.readdepths);
+			sites->mqcounts = reinterpret_cast<const int32_t*>(hsb + L.mqcounts); sites->filtered = reinterpret_cast<const int32_t*>(hsb + L.filtered);
+			if (ctx->pile_streams) {
+				sites->read_off = reinterpret_cast<const uint32_t*>(hsb + L.read_off); sites->alt_off = reinterpret_cast<const uint32_t*>(hsb + L.alt_off);
+				sites->reads = static_cast<const crispgpu_read*>(ctx->ph_reads.p); sites->alt_reads = static_cast<const crispgpu_altread*>(ctx->ph_alt.p);
+			}
+		}
+	}
+	return CRISPGPU_OK;
+}
+
+}  // namespace
+
+int crispgpu_pileup_run(crispgpu_ctx* ctx, const crispgpu_alignments* aln, const crispgpu_window* win, crispgpu_pileup_sites* sites, crispgpu_results* results)
+{
+	if (!ctx) return CRISPGPU_ERR_ARG;
+	if (ctx->inflight) return CRISPGPU_ERR_TICKET;
+	CK(cudaSetDevice(ctx->device));
+	ctx->timing_pending = false;
+	CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
+	int rc = pile_upload(ctx, aln, win);
+	if (rc) return rc;
+	ctx->pile_resident = false;
+	return pile_run(ctx, true, sites, results);
+}
+
+int crispgpu_pileup_upload(crispgpu_ctx* ctx, const crispgpu_alignments* aln, const crispgpu_window* win)
+{
+	if (!ctx) return CRISPGPU_ERR_ARG;
+	if (ctx->inflight) return CRISPGPU_ERR_TICKET;
+	CK(cudaSetDevice(ctx->device));
+	int rc = pile_upload(ctx, aln, win);
+	if (rc) return rc;
+	CK(cudaStreamSynchronize(ctx->stream));
+	ctx->pile_resident = true;
+	return CRISPGPU_OK;
+}
+
+int crispgpu_pileup_run_resident(crispgpu_ctx* ctx, int fetch_results, crispgpu_pileup_sites* sites, crispgpu_results* results)
+{
+	if (!ctx) return CRISPGPU_ERR_ARG;
+	if (!ctx->pile_resident) { snprintf(ctx->err, sizeof ctx->err, "no resident alignments: call crispgpu_pileup_upload first"); return CRISPGPU_ERR_ARG; }
+	CK(cudaSetDevice(ctx->device));
+	ctx->timing_pending = false;
+	CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
+	return pile_run(ctx, fetch_results != 0, sites, results);
+}
+
 int crispgpu_upload(crispgpu_ctx* ctx, const crispgpu_batch* batch)
 {
 	if (!ctx || !batch || batch->n_sites < 0) return CRISPGPU_ERR_ARG;
@@ -1283,6 +1550,7 @@ int crispgpu_run_resident(crispgpu_ctx* ctx, int fetch_results, crispgpu_results
 		return CRISPGPU_ERR_ARG;
 	}
 	CK(cudaSetDevice(ctx->device));
+	ctx->pile_timing = false;
 	CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
 	int rc = run_stage1(ctx);
 	if (rc) return rc;

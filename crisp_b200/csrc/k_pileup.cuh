@@ -1,0 +1,442 @@
+// k_pileup.cuh — the pileup of the reference's front end on the device: per-position, per-pool,
+// per-strand allele counts from BAM alignments, the candidate screen, and the packing of the candidate sites into the
+// engine's batch arrays — everything calculate_allelecounts (parsebam/variant.c:225-342) + advance_read (:56-131) + the
+// mismatch count of parse_cigar (parsebam/bamread.c:10-76) + sort_allelecounts / the potential-variant test
+// (variantcalls.c:62-92) + the three read-list walks of host/crisp_shim.c produce for a window of reference positions, so
+// that the alignments (in the BAM's own encoding) are the only thing that crosses PCIe.
+//
+// Scope of this version (checked on the device by k_pile_check, never assumed): substitutions only — alignments whose CIGAR
+// is one match block between clips, no overlapping mate pairs (the reference's OVERLAPPING_PE_READS merge, variant.c:137-220,
+// and its indel allele discovery stay on the host).
+//
+// What the reference does per (position p, pool j, read) and what is reproduced here bit for bit:
+//   a read is visible at p when read.position <= p < read.lastpos            (variant.c:251-257: lastpos is one past the
+//                                                                              last aligned base; advance_read fails at it)
+//   readdepths[j]++ and MQcounts[class of the mapping quality]++ for every visible read          (:280-283)
+//   MAX_MM = alignedbases/40 + 2; mismatches = bases of the match block that differ from the reference (either case) and
+//   are not 'N'                                                                (:286, bamread.c:31-41)
+//   filteredreads[0]++ when mismatches > MAX_MM and mquality >= MIN_M, else [1]++ when quality < MINQ and mquality >= MIN_M (:288-289)
+//   the base is counted when quality >= MINQ and mquality >= MIN_M and mismatches <= MAX_MM and
+//   (base != refb or mismatches <= MAX_MM - 1): indcounts[j][BTI[base] + 8*strand]++             (:299-312)
+//   counted reads are the likelihood stream (filter '0', type 0) and, per tested allele, the alt-read list in read order.
+#pragma once
+#include "dmath.cuh"
+#include "engine_types.cuh"
+
+namespace crisp {
+
+struct PileReads {   // alignments of all pools, pool-major, every pool in BAM (coordinate) order
+	int P;
+	uint32_t n_reads;
+	unsigned long long n_bases;
+	const uint32_t* pool_off;      // [P+1]
+	const crispgpu_alnrec* rec;    // [R]
+	const int32_t* mate_pos;       // [R] or null
+	const int32_t* isize;          // [R] or null
+	const uint8_t* seq4;           // 4-bit bases, read r at seq4 + base_off/2
+	const uint8_t* qual;           // phred scores, read r at qual + base_off
+	uint8_t* flags;                // [R] written by k_pile_tile: bit 0 passes the read filters, bit 1 also when the base equals the reference
+	int32_t* state;                // [0] error bits of k_pile_check, [1] longest match block, [2] candidates
+};
+
+enum { kPileErrAlign = 1, kPileErrBounds = 2, kPileErrOrder = 4, kPileErrMate = 8, kPileErrPool = 16 };
+
+struct PileWindow {
+	int tid, w0, W;            // reference positions [w0, w0 + W)
+	int ref0;                  // reference position of refseq[0]
+	int reflen;
+	const uint8_t* refseq;     // reference characters (either case) covering the window and the reads that overlap it
+	int min_q, min_m;          // MINQ, MIN_M
+};
+
+// BAM's 4-bit base code -> the character bam_nt16_rev_table gives the reference's reader (bamread.c:122) and BTI of it
+// (variant.c:17-26): "=ACMGRSVTWYHKDBN" -> 0 0 1 0 2 0 1 0 3 0 1 0 2 0 1 0
+__device__ __forceinline__ int nt16_char(int c) { return (int)(((c & 8) ? 0x4e42444b48595754ull : 0x565352474d43413dull) >> (8 * (c & 7))) & 255; }
+__device__ __forceinline__ int nt16_bti(int c) { return (int)(0x0102010301020100ull >> (4 * c)) & 3; }
+__device__ __forceinline__ int upper(int ch) { return (ch >= 'a' && ch <= 'z') ? ch - 32 : ch; }
+__device__ __forceinline__ int ref_code(int up) { return up == 'A' ? 0 : up == 'C' ? 1 : up == 'G' ? 2 : up == 'T' ? 3 : 255; }
+
+__device__ __forceinline__ int ref_at(const PileWindow& w, int p)
+{
+	const int k = p - w.ref0;
+	return (k >= 0 && k < w.reflen) ? upper(__ldg(w.refseq + k)) : 'N';
+}
+
+__device__ __forceinline__ uint32_t lower_bound_pos(const crispgpu_alnrec* rec, uint32_t lo, uint32_t hi, int key)
+{
+	while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (rec[mid].pos < key) lo = mid + 1; else hi = mid; }
+	return lo;
+}
+
+// every alignment against the scope and the layout rules of the interface; the longest match block of the set
+__global__ void k_pile_check(PileReads rd)
+{
+	int err = 0, span = 0;
+	for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < rd.n_reads; r += gridDim.x * blockDim.x) {
+		const crispgpu_alnrec a = rd.rec[r];
+		if (a.base_off & 7u) err |= kPileErrAlign;
+		if ((unsigned long long)a.base_off + (((unsigned)a.clip + a.mlen + 7u) & ~7u) > rd.n_bases || a.mlen == 0) err |= kPileErrBounds;
+		if (r > 0 && rd.rec[r - 1].pos > a.pos) {
+			// allowed only across a pool boundary
+			bool boundary = false;
+			uint32_t lo = 0, hi = rd.P;
+			while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (rd.pool_off[mid] < r) lo = mid + 1; else hi = mid; }
+			boundary = lo <= (uint32_t)rd.P && rd.pool_off[lo] == r;
+			if (!boundary) err |= kPileErrOrder;
+		}
+		if (rd.mate_pos) {
+			const int mp = rd.mate_pos[r], is = rd.isize ? rd.isize[r] : 0;
+			// the mate starts inside this read's match block: the reference would merge the pair (variant.c:274)
+			if (mp > a.pos && mp < a.pos + (int)a.mlen - 1) err |= kPileErrMate;
+			// the reference's "2nd read ends before 1st read" filter could fire (variant.c:271)
+			if (is < 0 && a.pos < mp) err |= kPileErrMate;
+		}
+		span = max(span, (int)a.mlen);
+	}
+	if (threadIdx.x == 0 && blockIdx.x == 0) {
+		if (rd.pool_off[0] != 0 || rd.pool_off[rd.P] != rd.n_reads) err |= kPileErrPool;
+		for (int j = 0; j < rd.P; j++) if (rd.pool_off[j] > rd.pool_off[j + 1]) err |= kPileErrPool;
+	}
+	err = __reduce_or_sync(0xffffffffu, err);
+	span = __reduce_max_sync(0xffffffffu, span);
+	if ((threadIdx.x & 31) == 0) {
+		if (err) atomicOr(rd.state, err);
+		atomicMax(rd.state + 1, span);
+	}
+}
+
+constexpr int kPileTile = 1024;   // reference positions per CTA tile
+constexpr int kPileCell = 8;      // counters per (position, pool) cell of the window table: base 0..3 + 4 * strand
+
+// Four consecutive bases of a read held by one lane: read-base indices i0 .. i0+3 (i0 a multiple of 4)
+struct Quad { uint32_t q; uint32_t s; };   // four quality bytes; four 4-bit base codes in the low 16 bits (first base in bits 12..15)
+__device__ __forceinline__ Quad load_quad(const PileReads& rd, uint32_t base_off, int i0)
+{
+	Quad v;
+	v.q = __ldg(reinterpret_cast<const uint32_t*>(rd.qual + base_off + i0));
+	const uint16_t h = __ldg(reinterpret_cast<const uint16_t*>(rd.seq4 + (base_off >> 1) + (i0 >> 1)));
+	v.s = ((uint32_t)(h & 0xff) << 8) | (h >> 8);   // bytes are little-endian, nibbles high-first
+	return v;
+}
+__device__ __forceinline__ int quad_base(const Quad& v, int b) { return (v.s >> (12 - 4 * b)) & 15; }
+__device__ __forceinline__ int quad_qual(const Quad& v, int b) { return (v.q >> (8 * b)) & 255; }
+
+// One CTA per (tile of kPileTile positions, pool): the alignments overlapping the tile are walked once, one warp per
+// alignment, each lane holding four consecutive bases (one 4-byte quality load, one 2-byte base load per lane).  The warp
+// first counts the read's mismatches against the reference (the read filter needs them before any base is counted), then
+// adds its bases into a shared-memory table [position][base + 4 strand]; the table leaves as full 32-byte cells of the
+// window table win[position][pool][8].  An alignment is loaded by at most two tiles.
+__global__ void __launch_bounds__(256) k_pile_tile(PileReads rd, PileWindow w, uint32_t* __restrict__ win)
+{
+	__shared__ uint32_t hist[kPileTile * kPileCell];
+	if (rd.state[0]) return;
+	const int max_span = rd.state[1];
+	const int pool = blockIdx.y, t0 = w.w0 + blockIdx.x * kPileTile, t1 = min(t0 + kPileTile, w.w0 + w.W);
+	for (int k = threadIdx.x; k < kPileTile * kPileCell; k += blockDim.x) hist[k] = 0;
+	__syncthreads();
+	const uint32_t r0 = rd.pool_off[pool], r1 = rd.pool_off[pool + 1];
+	const uint32_t lo = lower_bound_pos(rd.rec, r0, r1, t0 - max_span + 1), hi = lower_bound_pos(rd.rec, r0, r1, t1);
+	const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+	for (uint32_t r = lo + (threadIdx.x >> 5); r < hi; r += nw) {
+		const crispgpu_alnrec a = rd.rec[r];
+		const int ml = a.mlen, clip = a.clip, end = clip + ml;
+		if (a.pos + ml <= t0) continue;
+		// pass 1: mismatches of the match block
+		int mm = 0;
+		Quad first{0, 0};
+		for (int c = 0; c < end; c += 128) {
+			const int i0 = c + 4 * lane;
+			if (i0 >= end || i0 + 4 <= clip) continue;
+			const Quad v = load_quad(rd, a.base_off, i0);
+			if (c == 0) first = v;
+#pragma unroll
+			for (int b = 0; b < 4; b++) {
+				const int k = i0 + b - clip;
+				if (k < 0 || k >= ml) continue;
+				const int code = quad_base(v, b);
+				mm += (code != 15 && nt16_char(code) != ref_at(w, a.pos + k)) ? 1 : 0;
+			}
+		}
+		mm = __reduce_add_sync(0xffffffffu, mm);
+		const int maxmm = ml / 40 + 2;   // MAX_MM = alignedbases/40 + 2 (no gaps in this version)
+		const bool mq = a.mapq >= w.min_m;
+		const int fl = (mq && mm <= maxmm ? 1 : 0) | (mq && mm <= maxmm - 1 ? 2 : 0);
+		if (lane == 0) rd.flags[r] = (uint8_t)fl;   // tiles that share the read write the same value
+		if (!(fl & 1)) continue;
+		// pass 2: count
+		const int st = a.strand ? 4 : 0;
+		for (int c = 0; c < end; c += 128) {
+			const int i0 = c + 4 * lane;
+			if (i0 >= end || i0 + 4 <= clip) continue;
+			const Quad v = c == 0 ? first : load_quad(rd, a.base_off, i0);
+#pragma unroll
+			for (int b = 0; b < 4; b++) {
+				const int k = i0 + b - clip;
+				if (k < 0 || k >= ml) continue;
+				const int p = a.pos + k;
+				if (p < t0 || p >= t1) continue;
+				if (quad_qual(v, b) < w.min_q) continue;
+				const int code = quad_base(v, b);
+				if (nt16_char(code) == ref_at(w, p) && !(fl & 2)) continue;
+				atomicAdd(&hist[(p - t0) * kPileCell + nt16_bti(code) + st], 1u);
+			}
+		}
+	}
+	__syncthreads();
+	// 32-byte cells: two 16-byte stores per cell, consecutive positions 32 * P bytes apart
+	for (int k = threadIdx.x; k < (t1 - t0) * 2; k += blockDim.x) {
+		const int x = k >> 1, h = k & 1;
+		const uint4 v = *reinterpret_cast<const uint4*>(&hist[x * kPileCell + 4 * h]);
+		*reinterpret_cast<uint4*>(win + ((size_t)(t0 - w.w0 + x) * rd.P + pool) * kPileCell + 4 * h) = v;
+	}
+}
+
+// sort_allelecounts (allelecounts.c:134-183, IUPAC off) on the eight per-allele read totals: reference allele swapped to
+// the front, then the exchange sort `if (ct[i] < ct[j]) swap` over i = 1..6, j = i+1..7 — the same comparisons in the
+// same order, so ties fall the same way
+__device__ __forceinline__ void sort_alleles(int ref, int (&ct)[8], int (&al)[8])
+{
+	if (ref >= 1 && ref < 8) {
+#pragma unroll
+		for (int a = 1; a < 8; a++)
+			if (a == ref) { const int tc = ct[0]; ct[0] = ct[a]; ct[a] = tc; const int ta = al[0]; al[0] = al[a]; al[a] = ta; }
+	}
+#pragma unroll
+	for (int i = 1; i < 7; i++)
+#pragma unroll
+		for (int j = i + 1; j < 8; j++)
+			if (ct[i] < ct[j]) { const int tc = ct[i]; ct[i] = ct[j]; ct[j] = tc; const int ta = al[i]; al[i] = al[j]; al[j] = ta; }
+}
+
+// Candidate test of every window position (variantcalls.c:47,76-92): one warp per position, lanes over pools; the
+// potential-variant score adds 2 per (non-reference allele, pool) with >= 3 reads, and the read count for diploid pools
+// with >= 1.  flag[x] = 1 when the score reaches 2 on an A/C/G/T reference base.
+__global__ void k_pile_screen(const uint32_t* __restrict__ win, PileWindow w, int P, const int32_t* __restrict__ ploidy, uint8_t* __restrict__ flag)
+{
+	const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+	for (int x = blockIdx.x * wpb + (threadIdx.x >> 5); x < w.W; x += gridDim.x * wpb) {
+		const int ref = ref_code(ref_at(w, w.w0 + x));
+		int pot = 0;
+		for (int i = lane; i < P; i += 32) {
+			const uint4* c = reinterpret_cast<const uint4*>(win + ((size_t)x * P + i) * kPileCell);
+			const uint4 f = __ldg(c), r = __ldg(c + 1);
+			const int t[4] = {(int)(f.x + r.x), (int)(f.y + r.y), (int)(f.z + r.z), (int)(f.w + r.w)};
+			const bool diploid = ploidy[i] == 2;
+#pragma unroll
+			for (int a = 0; a < 4; a++) {
+				if (a == ref) continue;
+				if (t[a] >= 3) pot += 2;
+				else if (t[a] >= 1 && diploid) pot += t[a];
+			}
+		}
+		pot = __reduce_add_sync(0xffffffffu, pot);
+		if (lane == 0) flag[x] = (pot >= 2 && ref < 4) ? 1 : 0;
+	}
+}
+
+// candidate positions in coordinate order: one CTA, every thread owns a contiguous chunk of the window
+__global__ void k_pile_select(const uint8_t* __restrict__ flag, int W, int32_t* __restrict__ cand, int32_t* n_cand)
+{
+	__shared__ int sums[1024];
+	const int T = blockDim.x, tid = threadIdx.x, chunk = (W + T - 1) / T, a = min(W, tid * chunk), b = min(W, a + chunk);
+	int c = 0;
+	for (int x = a; x < b; x++) c += flag[x];
+	sums[tid] = c;
+	__syncthreads();
+	for (int d = 1; d < T; d <<= 1) {
+		const int v = tid >= d ? sums[tid - d] : 0;
+		__syncthreads();
+		sums[tid] += v;
+		__syncthreads();
+	}
+	int o = sums[tid] - c;
+	for (int x = a; x < b; x++) if (flag[x]) cand[o++] = x;
+	if (tid == T - 1) *n_cand = sums[tid];
+}
+
+// exclusive prefix sum of n 32-bit counts into off[0..n] by one CTA (the arrays scanned here hold a few 10^5 cells)
+__global__ void k_pile_scan(const uint32_t* __restrict__ cnt, uint32_t* __restrict__ off, size_t n)
+{
+	__shared__ unsigned long long sums[1024];
+	const int T = blockDim.x, tid = threadIdx.x;
+	const size_t chunk = (n + T - 1) / T, a = min(n, (size_t)tid * chunk), b = min(n, a + chunk);
+	unsigned long long c = 0;
+	for (size_t x = a; x < b; x++) c += cnt[x];
+	sums[tid] = c;
+	__syncthreads();
+	for (int d = 1; d < T; d <<= 1) {
+		const unsigned long long v = tid >= d ? sums[tid - d] : 0;
+		__syncthreads();
+		sums[tid] += v;
+		__syncthreads();
+	}
+	unsigned long long o = sums[tid] - c;
+	for (size_t x = a; x < b; x++) { off[x] = (uint32_t)o; o += cnt[x]; }
+	if (tid == T - 1) off[n] = (uint32_t)sums[tid];
+}
+
+struct PileSites {   // the candidate sites of the window as the engine's batch arrays (device memory)
+	int n;
+	const int32_t* cand;     // [n] window offset of each candidate
+	int32_t* tid; int32_t* pos; uint8_t* refbase; uint8_t* maxvec_al; int32_t* maxvec_ct; int32_t* counts; int32_t* indcounts;
+	uint32_t* cell_reads;    // [n P] counted reads per (site, pool) -> read_off by k_pile_scan
+	uint32_t* read_off; uint16_t* reads;
+	uint32_t* alt_len;       // [n 5 P] alt-read list lengths per (site, slot, pool) -> alt_cell_off
+	uint32_t* alt_cell_off; uint32_t* alt_off; crispgpu_altread* alt_reads;
+	int32_t* readdepths;     // [n P]
+	int32_t* mqcounts;       // [n 4]
+	int32_t* filtered;       // [n 2]
+};
+
+// One CTA per candidate: its cells of the window table become the dense per-pool rows of the batch (indel and
+// bidirectional entries zero), the site totals, the sorted allele vector and the per-cell read counts.
+__global__ void __launch_bounds__(128) k_pile_gather_counts(PileSites ps, PileWindow w, int P, const uint32_t* __restrict__ win)
+{
+	__shared__ int tot[kPileCell];
+	for (int c = blockIdx.x; c < ps.n; c += gridDim.x) {
+		const int x = ps.cand[c];
+		if (threadIdx.x < kPileCell) tot[threadIdx.x] = 0;
+		__syncthreads();
+		int mine[kPileCell] = {0, 0, 0, 0, 0, 0, 0, 0};
+		for (int j = threadIdx.x; j < P; j += blockDim.x) {
+			const uint4* cell = reinterpret_cast<const uint4*>(win + ((size_t)x * P + j) * kPileCell);
+			const uint4 f = cell[0], r = cell[1];
+			const int v[kPileCell] = {(int)f.x, (int)f.y, (int)f.z, (int)f.w, (int)r.x, (int)r.y, (int)r.z, (int)r.w};
+			int4* row = reinterpret_cast<int4*>(ps.indcounts + ((size_t)c * P + j) * kNC);
+			row[0] = make_int4(v[0], v[1], v[2], v[3]);
+			row[1] = make_int4(0, 0, 0, 0);
+			row[2] = make_int4(v[4], v[5], v[6], v[7]);
+			row[3] = make_int4(0, 0, 0, 0);
+			row[4] = make_int4(0, 0, 0, 0);
+			row[5] = make_int4(0, 0, 0, 0);
+			int t = 0;
+#pragma unroll
+			for (int e = 0; e < kPileCell; e++) { mine[e] += v[e]; t += v[e]; }
+			ps.cell_reads[(size_t)c * P + j] = (uint32_t)t;
+		}
+#pragma unroll
+		for (int e = 0; e < kPileCell; e++) {
+			const int s = __reduce_add_sync(0xffffffffu, mine[e]);
+			if ((threadIdx.x & 31) == 0 && s) atomicAdd(&tot[e], s);
+		}
+		__syncthreads();
+		if (threadIdx.x < kNC) {
+			const int e = threadIdx.x;
+			ps.counts[c * kNC + e] = (e < 4) ? tot[e] : (e >= 8 && e < 12) ? tot[e - 4] : 0;
+		}
+		if (threadIdx.x == 0) {
+			const int ref = ref_code(ref_at(w, w.w0 + x));
+			int ct[8], al[8];
+#pragma unroll
+			for (int a = 0; a < 8; a++) { ct[a] = a < 4 ? tot[a] + tot[a + 4] : 0; al[a] = a; }
+			sort_alleles(ref, ct, al);
+#pragma unroll
+			for (int a = 0; a < 8; a++) { ps.maxvec_al[c * 8 + a] = (uint8_t)al[a]; ps.maxvec_ct[c * 8 + a] = ct[a]; }
+			ps.tid[c] = w.tid; ps.pos[c] = w.w0 + x; ps.refbase[c] = (uint8_t)ref;
+		}
+		if (threadIdx.x < 4) ps.mqcounts[c * 4 + threadIdx.x] = 0;
+		if (threadIdx.x < 2) ps.filtered[c * 2 + threadIdx.x] = 0;
+		__syncthreads();
+	}
+}
+
+// One warp per (candidate, pool): the reads of the pool that cover the position, in BAM order.  PASS 0 measures the
+// alt-read lists; PASS 1 writes the likelihood stream, the alt-read lists, the read depth, the mapping-quality classes
+// and the two filtered-read counters.
+template <int PASS>
+__global__ void k_pile_gather_reads(PileReads rd, PileWindow w, PileSites ps)
+{
+	const int lane = threadIdx.x & 31, P = rd.P;
+	const int max_span = rd.state[1];
+	const size_t cells = (size_t)ps.n * P;
+	for (size_t cell = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5); cell < cells; cell += (size_t)gridDim.x * (blockDim.x >> 5)) {
+		const int c = (int)(cell / P), j = (int)(cell - (size_t)c * P);
+		const int p = ps.pos[c];
+		const int refc = ref_at(w, p);
+		const uint32_t r0 = rd.pool_off[j], r1 = rd.pool_off[j + 1];
+		const uint32_t lo = lower_bound_pos(rd.rec, r0, r1, p - max_span + 1), hi = lower_bound_pos(rd.rec, r0, r1, p + 1);
+		int slot_al[5];
+#pragma unroll
+		for (int k = 0; k < 5; k++) slot_al[k] = ps.maxvec_ct[c * 8 + k + 1] >= 3 ? ps.maxvec_al[c * 8 + k + 1] : -1;
+		uint32_t nread = 0, nalt[5] = {0, 0, 0, 0, 0};
+		int depth = 0, mq[4] = {0, 0, 0, 0}, filt[2] = {0, 0};
+		const uint32_t rbase = PASS ? ps.read_off[cell] : 0;
+		for (uint32_t rb = lo; rb < hi; rb += 32) {
+			const uint32_t r = rb + lane;
+			int b = -1, q = 0;
+			bool covers = false, letter = false;   // letter: the base is the allele's own character (an 'N' counts as allele 0 but is
+			                                       // no alt read of it: calculate_uniquereads compares characters, allelecounts.c:55)
+			crispgpu_alnrec a{};
+			if (r < hi) {
+				a = rd.rec[r];
+				const int k = p - a.pos;
+				covers = k >= 0 && k < (int)a.mlen;
+				if (covers) {
+					const uint32_t i = a.base_off + a.clip + k;
+					q = rd.qual[i];
+					const int code = (rd.seq4[i >> 1] >> ((i & 1) ? 0 : 4)) & 15;
+					const int fl = rd.flags[r];
+					const bool mqok = a.mapq >= w.min_m;
+					if (PASS) {
+						// variant.c:288-289: MAX_MM test first, then the base quality
+						if (mqok && !(fl & 1)) filt[0]++;
+						else if (q < w.min_q && mqok) filt[1]++;
+					}
+					if (q >= w.min_q && (fl & 1) && !(nt16_char(code) == refc && !(fl & 2))) { b = nt16_bti(code); letter = code == (1 << b); }
+				}
+			}
+			if (PASS) {
+				const unsigned cm = __ballot_sync(0xffffffffu, covers);
+				depth += __popc(cm);
+				if (covers) { const int m = a.mapq; mq[m < 10 ? 0 : (m >= 40 ? 3 : m / 20 + 1)]++; }
+				const unsigned bm = __ballot_sync(0xffffffffu, b >= 0);
+				if (b >= 0) ps.reads[rbase + nread + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)(((q + 33) & 0xff) | ((b & 3) << 8) | ((a.strand ? 1 : 0) << 10));
+				nread += __popc(bm);
+			}
+#pragma unroll
+			for (int k = 0; k < 5; k++) {
+				if (slot_al[k] < 0) continue;   // warp-uniform
+				const unsigned am = __ballot_sync(0xffffffffu, letter && b == slot_al[k]);
+				if (PASS && letter && b == slot_al[k]) {
+					crispgpu_altread e;
+					e.pool = (uint16_t)j;
+					e.offset = (uint16_t)(a.clip + (p - a.pos));   // l1 + delta: index of the base in the read
+					e.aligned = a.mlen;
+					e.strand = a.strand ? 1 : 0;
+					e.pad = 0;
+					ps.alt_reads[ps.alt_cell_off[((size_t)c * 5 + k) * P + j] + nalt[k] + __popc(am & ((1u << lane) - 1u))] = e;
+				}
+				nalt[k] += __popc(am);
+			}
+		}
+		if (!PASS) {
+			if (lane < 5) {
+				uint32_t v = 0;
+#pragma unroll
+				for (int k = 0; k < 5; k++) if (lane == k) v = nalt[k];
+				ps.alt_len[((size_t)c * 5 + lane) * P + j] = v;
+			}
+		} else {
+			if (lane == 0) ps.readdepths[cell] = depth;
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				const int t = __reduce_add_sync(0xffffffffu, mq[k]);
+				if (lane == 0 && t) atomicAdd(&ps.mqcounts[c * 4 + k], t);
+			}
+#pragma unroll
+			for (int k = 0; k < 2; k++) {
+				const int t = __reduce_add_sync(0xffffffffu, filt[k]);
+				if (lane == 0 && t) atomicAdd(&ps.filtered[c * 2 + k], t);
+			}
+		}
+	}
+}
+
+// alt_off[site * 5 + slot] = start of the slot's list (its pools follow one another)
+__global__ void k_pile_alt_off(PileSites ps, int P)
+{
+	const int n5 = ps.n * 5;
+	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= n5; k += gridDim.x * blockDim.x) ps.alt_off[k] = ps.alt_cell_off[(size_t)k * P];
+}
+
+}  // namespace crisp

@@ -20,6 +20,7 @@ EXPORTS = [
     "crispgpu_upload", "crispgpu_run_resident", "crispgpu_get_timing", "crispgpu_last_error",
     "crispgpu_host_alloc", "crispgpu_host_free", "crispgpu_abi_version", "crispgpu_device_count",
     "crispgpu_measure_fp64_tflops", "crispgpu_measure_int32_tops",
+    "crispgpu_pileup_run", "crispgpu_pileup_upload", "crispgpu_pileup_run_resident",
 ]
 
 _lib = None
@@ -194,6 +195,43 @@ class Engine:
         cres = CResults()
         self._check(self.lib.crispgpu_run_resident(self.h, 1 if fetch else 0, C.byref(cres)), "crispgpu_run_resident")
         return Results.from_c(cres, self.cfg.n_pools) if fetch else None
+
+    # ---- pileup on the device: alignments in, candidate sites + their results out ----
+    def pileup_run(self, aln, window, want_sites: bool = True):
+        """crispgpu_pileup_run: (PileupSites, Results) for the candidate sites of `window` (a crisp_b200.pileup.make_window
+        pair) piled up from `aln` (crisp_b200.pileup.Alignments)."""
+        from .pileup import CPileupSites, sites_from_c
+
+        cw, keep = window
+        ca = aln.as_c()
+        cs, cres = CPileupSites(), CResults()
+        fn = self.lib.crispgpu_pileup_run
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        fn.restype = C.c_int
+        self._check(fn(self.h, C.byref(ca), C.byref(cw), C.byref(cs), C.byref(cres)), "crispgpu_pileup_run")
+        del keep
+        return (sites_from_c(cs, self.cfg.n_pools) if want_sites else cs.n_sites), Results.from_c(cres, self.cfg.n_pools)
+
+    def pileup_upload(self, aln, window) -> None:
+        cw, keep = window
+        ca = aln.as_c()
+        fn = self.lib.crispgpu_pileup_upload
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        fn.restype = C.c_int
+        self._check(fn(self.h, C.byref(ca), C.byref(cw)), "crispgpu_pileup_upload")
+        del keep
+
+    def pileup_run_resident(self, fetch: bool = False):
+        from .pileup import CPileupSites, sites_from_c
+
+        cs, cres = CPileupSites(), CResults()
+        fn = self.lib.crispgpu_pileup_run_resident
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        fn.restype = C.c_int
+        self._check(fn(self.h, 1 if fetch else 0, C.byref(cs), C.byref(cres)), "crispgpu_pileup_run_resident")
+        if not fetch:
+            return cs.n_sites
+        return sites_from_c(cs, self.cfg.n_pools), Results.from_c(cres, self.cfg.n_pools)
 
     def timing(self) -> dict:
         t = Timing()

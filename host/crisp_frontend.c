@@ -65,6 +65,7 @@ typedef struct {
 	char refb;
 	short iupac;
 	int mq[4];         /* MQcounts */
+	int filt[2];       /* filteredreads[0..1] (variant.c:288-289; the log prints them, the device pileup reproduces them) */
 	size_t itb_off[4]; /* indel allele strings of alleles 4..7 in `text` */
 	size_t win_off;    /* reference window in `text` */
 	int win_start, win_len;
@@ -255,13 +256,15 @@ static void dump_batch(const crispgpu_batch* b)
 	put_bytes(f, b->bins, b->bins ? (size_t)b->bin_off[n * P] * 4 : 0);
 	put_bytes(f, b->ic_off, b->ic_sparse ? (n * P + 1) * 4 : 0);
 	put_bytes(f, b->ic_sparse, b->ic_sparse ? (size_t)b->ic_off[n * P] * 4 : 0);
-	/* printer state, so that a test can replay the records: readdepths, MQcounts, refb */
+	/* printer state, so that a test can replay the records: readdepths, MQcounts, refb; filteredreads[0..1] */
 	put_bytes(f, F.depths, n * P * 4);
 	int32_t* mq = (int32_t*)malloc(n * 16 + 16);
 	char* rb = (char*)malloc(n + 1);
 	for (size_t s = 0; s < n; s++) { memcpy(mq + s * 4, F.st[s].mq, 16); rb[s] = F.st[s].refb; }
 	put_bytes(f, mq, n * 16);
 	put_bytes(f, rb, n);
+	for (size_t s = 0; s < n; s++) { mq[s * 2] = F.st[s].filt[0]; mq[s * 2 + 1] = F.st[s].filt[1]; }
+	put_bytes(f, mq, n * 8);
 	free(mq);
 	free(rb);
 	fflush(f);
@@ -400,6 +403,7 @@ int __wrap_newCRISPcaller(REFLIST* reflist, int current, int position, READQUEUE
 	st->refb = variant->refb;
 	st->iupac = variant->IUPAC;
 	for (int k = 0; k < 4; k++) st->mq[k] = variant->MQcounts[k];
+	st->filt[0] = variant->filteredreads[0]; st->filt[1] = variant->filteredreads[1];
 	for (int i = 0; i < P; i++) F.depths[(size_t)s * P + i] = variant->readdepths[i];
 	int reach = 12;
 	for (int a = 4; a < 8; a++) {

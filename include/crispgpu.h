@@ -28,7 +28,8 @@
 extern "C" {
 #endif
 
-#define CRISPGPU_ABI_VERSION 2  /* 2: compact batch arrays (bins, sparse counts), crispgpu_advance, fetched_bytes */
+#define CRISPGPU_ABI_VERSION 3  /* 2: compact batch arrays (bins, sparse counts), crispgpu_advance, fetched_bytes
+                                   3: crispgpu_pileup_run, config.minimal_results, timing.pileup_ms, crispgpu_measure_int32_tops */
 
 #define CRISPGPU_MAXALLELES 8  /* `maxalleles`, readmultiplebams.c:27: A,C,G,T + indel slots 4..6 */
 #define CRISPGPU_NCOUNT 24     /* 3 strand classes x 8 alleles: index = allele + s*8, s=0 fwd,1 rev,2 bidirectional
@@ -249,6 +250,11 @@ typedef struct crispgpu_timing {
 	int64_t h2d_bytes;   /* bytes moved host -> device for the batch, on-demand fetches included */
 	int64_t d2h_bytes;
 	int64_t fetched_bytes; /* the part of h2d_bytes pulled on demand from pinned host memory (k_fetch_reads; inside filter_ms) */
+	float pileup_ms;       /* crispgpu_pileup_run: alignments -> counts -> candidate screen -> packed sites (after h2d_ms, before evaluate_ms) */
+	float pile_tile_ms;    /* the part of pileup_ms spent in k_pile_tile (the kernel that streams the alignments) */
+	int32_t n_positions;   /* crispgpu_pileup_run: reference positions piled up */
+	int32_t n_alignments;  /* crispgpu_pileup_run: alignments handed over */
+	int64_t pile_bytes;    /* algorithmic bytes of k_pile_tile: 16 per alignment + 1.5 per base + 32 per (position, pool) cell written */
 } crispgpu_timing;
 
 typedef struct crispgpu_ctx crispgpu_ctx;
@@ -281,6 +287,83 @@ int crispgpu_wait(crispgpu_ctx* ctx, int64_t ticket, crispgpu_results* out);
 int crispgpu_screen_positions(crispgpu_ctx* ctx, int32_t n_sites, const uint8_t* refbase, const int32_t* counts,
                               const int32_t* indcounts, const uint32_t* ic_off, const crispgpu_count* ic_sparse,
                               uint8_t* maxvec_al, int32_t* maxvec_ct, int32_t* potential);
+
+/* ---- pileup on the device -----------------------------------------------------------------
+ * Replaces, for a window of reference positions, what the reference's front end does between reading the alignments and
+ * the call into the engine: calculate_allelecounts + advance_read (parsebam/variant.c:225-342, 56-131), the mismatch
+ * count of parse_cigar (parsebam/bamread.c:10-76), sort_allelecounts and the potential-variant test
+ * (variantcalls.c:62-92), and the three read-list walks of host/crisp_shim.c.  The host inflates BGZF and splits the BAM
+ * records (host/bam_decode.c); the alignments are the only input that crosses PCIe, in the BAM's own encoding (4-bit
+ * bases, one quality byte per base): the candidate sites are found and packed in device memory and go straight
+ * through the engine.
+ *
+ * This version piles up substitutions only: every alignment has the CIGAR [S|H] M [S|H] (one match block) and mates
+ * must not overlap (the reference's overlapping-mate merge, variant.c:137-220, and its indel allele discovery stay on
+ * the host).  An alignment outside that scope makes the call fail with CRISPGPU_ERR_UNSUPPORTED — it is never silently
+ * mis-piled.  The front end filters on the BAM flag (BAM_FILTER_MASK, readmultiplebams.c:121) before handing reads over. */
+typedef struct crispgpu_alnrec {  /* one alignment, 16 bytes */
+	int32_t pos;        /* bam1_core_t.pos: 0-based reference position of the first base of the match block */
+	uint32_t base_off;  /* index of the read's first base (soft clip included) in `qual`; a multiple of 8.  Its 4-bit
+	                       bases start at seq4 + base_off/2 */
+	uint16_t clip;      /* leading soft clip: bases before the match block */
+	uint16_t mlen;      /* length of the match block */
+	uint8_t mapq;       /* bam1_core_t.qual */
+	uint8_t strand;     /* (flag & 16) != 0 */
+	uint16_t reserved;
+} crispgpu_alnrec;
+
+typedef struct crispgpu_alignments {
+	int32_t n_pools;
+	int32_t reserved;
+	const uint32_t* pool_off;      /* [n_pools+1] first alignment of each pool; a pool's alignments are in BAM (coordinate) order */
+	const crispgpu_alnrec* rec;    /* [R], R = pool_off[n_pools] */
+	const int32_t* mate_pos;       /* [R] bam1_core_t.mpos, or NULL for single-end data: used only to refuse overlapping mates */
+	const int32_t* isize;          /* [R] bam1_core_t.isize, or NULL (with mate_pos) */
+	const uint8_t* seq4;           /* [n_bases/2] bases as BAM stores them: two per byte, high nibble first, codes "=ACMGRSVTWYHKDBN" */
+	const uint8_t* qual;           /* [n_bases] phred scores as BAM stores them (no +33) */
+	uint64_t n_bases;              /* size of `qual`; every read occupies a multiple of 8 bases (padding is never read as data) */
+} crispgpu_alignments;
+
+typedef struct crispgpu_window {
+	int32_t tid;               /* reference id (pass-through: results and RNG key) */
+	int32_t start, end;        /* reference positions [start, end) to call */
+	int32_t ref_start;         /* position of refseq[0]; the sequence must cover every alignment that overlaps the window */
+	int32_t ref_len;
+	int32_t want_streams;      /* 1: also return the packed read stream and alt-read lists of the candidate sites (tests) */
+	int32_t min_mapq;          /* MIN_M (--mmq, default 20), readmultiplebams.c:26; the base quality threshold is config.min_q */
+	int32_t reserved;
+	const char* refseq;        /* reference bases (either case) */
+} crispgpu_window;
+
+/* The candidate sites of the window in coordinate order: what variantcalls.c:76-92 lets through, with the struct VARIANT
+ * fields the printer needs.  Context-owned pinned memory, valid until the next call on the context. */
+typedef struct crispgpu_pileup_sites {
+	int32_t n_sites;
+	int32_t n_positions;
+	const int32_t* pos;        /* [n] */
+	const uint8_t* refbase;    /* [n] */
+	const uint8_t* maxvec_al;  /* [n][8] */
+	const int32_t* maxvec_ct;  /* [n][8] */
+	const int32_t* counts;     /* [n][24] */
+	const int32_t* indcounts;  /* [n][P][24] */
+	const int32_t* readdepths; /* [n][P]  variant->readdepths */
+	const int32_t* mqcounts;   /* [n][4]  variant->MQcounts */
+	const int32_t* filtered;   /* [n][2]  variant->filteredreads[0..1] */
+	const uint32_t* read_off;  /* want_streams: [n*P+1] */
+	const crispgpu_read* reads;
+	const uint32_t* alt_off;   /* want_streams: [n*5+1] */
+	const crispgpu_altread* alt_reads;
+} crispgpu_pileup_sites;
+
+/* Synchronous: pile up the window, screen and pack its candidate sites on the device, run the engine on them.
+ * `results` is what crispgpu_wait would return for the same sites.  `aln` arrays in pinned memory (crispgpu_host_alloc)
+ * make the copies DMA transfers. */
+int crispgpu_pileup_run(crispgpu_ctx* ctx, const crispgpu_alignments* aln, const crispgpu_window* win, crispgpu_pileup_sites* sites,
+                        crispgpu_results* results);
+/* Device-resident variant used to time the pileup kernels alone: crispgpu_pileup_upload copies the alignments and the
+ * reference window once, crispgpu_pileup_run_resident piles them up again (fetch_results = 0: nothing is copied back). */
+int crispgpu_pileup_upload(crispgpu_ctx* ctx, const crispgpu_alignments* aln, const crispgpu_window* win);
+int crispgpu_pileup_run_resident(crispgpu_ctx* ctx, int fetch_results, crispgpu_pileup_sites* sites, crispgpu_results* results);
 
 /* Optional, between submit and wait: waits only for the screening counters of the batch and enqueues its caller
  * kernels and device-to-host copies without waiting for them.  A front end juggling two contexts calls it on the other

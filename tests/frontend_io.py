@@ -17,7 +17,7 @@ _ARRAYS = [("ploidy", np.int32), ("tid", np.int32), ("pos", np.int32), ("refbase
            ("read_off", np.uint32), ("reads", np.uint16), ("alt_off", np.uint32), ("alt_reads", ALTREAD_DTYPE),
            ("amb_idx", np.int32), ("amb_dec", np.int32), ("amb_ep", np.float64), ("qhigh", np.float64), ("stats", np.float64),
            ("tstats", np.float64), ("bin_off", np.uint32), ("bins", np.uint32), ("ic_off", np.uint32), ("ic_sparse", np.uint32),
-           ("readdepths", np.int32), ("mqcounts", np.int32), ("refb", np.uint8)]
+           ("readdepths", np.int32), ("mqcounts", np.int32), ("refb", np.uint8), ("filtered", np.int32)]
 
 
 def read_dump(path: str):
@@ -46,7 +46,7 @@ def read_dump(path: str):
                                      "qv_offset", "min_q", "pivot_sample", "varpoolsize", "use_qv", "association")}
         opts.update(dhead)
         cfg = EngineConfig(ploidy=arr.pop("ploidy"), options=opts)
-        extras = {k: arr.pop(k) for k in ("readdepths", "mqcounts", "refb")}
+        extras = {k: arr.pop(k) for k in ("readdepths", "mqcounts", "refb", "filtered")}
         n = head["n_sites"]
         if arr["alt_reads"] is None:
             arr["alt_reads"] = np.zeros(0, ALTREAD_DTYPE)

@@ -29,7 +29,7 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_abi_version_and_defaults(lib):
-    assert lib.crispgpu_abi_version() == 2
+    assert lib.crispgpu_abi_version() == 3
     cfg = Config()
     lib.crispgpu_config_defaults(C.byref(cfg))
     # reference defaults: newcrispcaller.c:20-32, readmultiplebams.c:25-26, crispEM.c:14,26
@@ -44,7 +44,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(Config) == 4 * 2 + 8 + 4 * 12 + 8 + 8 * 8 + 8 + 4 * 4
     assert C.sizeof(CBatch) == 8 + 8 * 16 + 8 + 8 * 9
     assert C.sizeof(CResults) == 8 + 8 * 29
-    assert C.sizeof(Timing) == 4 * 8 + 4 * 2 + 8 * 4
+    assert C.sizeof(Timing) == 4 * 8 + 4 * 2 + 8 * 4 + 4 * 4 + 8
 
 
 def test_argument_errors(lib):
@@ -102,6 +102,8 @@ int main(void)
 	crispgpu_config_defaults(&c);
 	printf("%d %d %d %d %.1f %u %u %u %d\n", crispgpu_abi_version(), c.em_flag, c.max_iter, c.min_reads, c.thresh1,
 	       (unsigned)(bin >> 16), (unsigned)(bin & 0xffff), (unsigned)(cnt >> 27), (int)(b.bins == NULL));
+	printf("%u %u %u %u %u\n", (unsigned)sizeof(crispgpu_alnrec), (unsigned)sizeof(crispgpu_alignments), (unsigned)sizeof(crispgpu_window),
+	       (unsigned)sizeof(crispgpu_pileup_sites), (unsigned)sizeof(crispgpu_timing));
 	return 0;
 }
 ''')
@@ -110,5 +112,7 @@ int main(void)
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
                     "-L", libdir, "-lcrispgpu", "-Wl,-rpath," + libdir, "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
-    assert out[:5] == ["2", "1", "20000", "4", "-3.5"]
-    assert out[5:] == ["7", str(ord("I") | (2 << 8) | (1 << 10)), "9", "1"]
+    assert out[:5] == ["3", "1", "20000", "4", "-3.5"]
+    assert out[5:9] == ["7", str(ord("I") | (2 << 8) | (1 << 10)), "9", "1"]
+    from crisp_b200.pileup import ALNREC_DTYPE, CAlignments, CPileupSites, CWindow
+    assert [int(x) for x in out[9:]] == [ALNREC_DTYPE.itemsize, C.sizeof(CAlignments), C.sizeof(CWindow), C.sizeof(CPileupSites), C.sizeof(Timing)]
