@@ -107,86 +107,212 @@ __global__ void k_pile_check(PileReads rd)
 
 constexpr int kPileTile = 1024;   // reference positions per CTA tile
 constexpr int kPileCell = 8;      // counters per (position, pool) cell of the window table: base 0..3 + 4 * strand
+constexpr int kPileSpan = 512;    // longest match block whose reference stretch is staged in shared memory (longer reads: global loads)
+constexpr int kPileRefWords = (kPileTile + 2 * kPileSpan + 16) / 4;
 
-// Four consecutive bases of a read held by one lane: read-base indices i0 .. i0+3 (i0 a multiple of 4)
-struct Quad { uint32_t q; uint32_t s; };   // four quality bytes; four 4-bit base codes in the low 16 bits (first base in bits 12..15)
-__device__ __forceinline__ Quad load_quad(const PileReads& rd, uint32_t base_off, int i0)
+// the 4-bit code whose character (bam_nt16_rev_table) is the upper-cased reference character, 0xFF when there is none:
+// read and reference characters are equal exactly when the codes are
+__device__ __forceinline__ int ref_nt16(int up)
 {
-	Quad v;
-	v.q = __ldg(reinterpret_cast<const uint32_t*>(rd.qual + base_off + i0));
-	const uint16_t h = __ldg(reinterpret_cast<const uint16_t*>(rd.seq4 + (base_off >> 1) + (i0 >> 1)));
-	v.s = ((uint32_t)(h & 0xff) << 8) | (h >> 8);   // bytes are little-endian, nibbles high-first
-	return v;
+	switch (up) {
+	case 'A': return 1; case 'C': return 2; case 'G': return 4; case 'T': return 8; case 'N': return 15; case '=': return 0;
+	case 'M': return 3; case 'R': return 5; case 'S': return 6; case 'V': return 7; case 'W': return 9; case 'Y': return 10;
+	case 'H': return 11; case 'K': return 12; case 'D': return 13; case 'B': return 14;
+	default: return 0xFF;
+	}
 }
-__device__ __forceinline__ int quad_base(const Quad& v, int b) { return (v.s >> (12 - 4 * b)) & 15; }
-__device__ __forceinline__ int quad_qual(const Quad& v, int b) { return (v.q >> (8 * b)) & 255; }
 
-// One CTA per (tile of kPileTile positions, pool): the alignments overlapping the tile are walked once, one warp per
-// alignment, each lane holding four consecutive bases (one 4-byte quality load, one 2-byte base load per lane).  The warp
-// first counts the read's mismatches against the reference (the read filter needs them before any base is counted), then
-// adds its bases into a shared-memory table [position][base + 4 strand]; the table leaves as full 32-byte cells of the
-// window table win[position][pool][8].  An alignment is loaded by at most two tiles.
+// 0x01 in every byte b of a word with lo <= b < hi (any integers)
+__device__ __forceinline__ uint32_t byte_range01(int lo, int hi)
+{
+	lo = max(lo, 0); hi = min(hi, 4);
+	if (lo >= hi) return 0u;
+	const uint32_t upto_hi = hi >= 4 ? 0x01010101u : (0x01010101u >> (8 * (4 - hi)));
+	return upto_hi & (0x01010101u << (8 * lo));
+}
+
+// hist index of counter e at tile offset x.  Counter-major; inside every block of 128 positions the column is transposed
+// ([x & 3][x >> 2]) so that the 32 lanes of a warp — which hold four consecutive bases each — hit 32 different banks.
+__device__ __forceinline__ int pile_slot(int e, int x) { return e * kPileTile + (x & ~127) + ((x & 3) << 5) + ((x >> 2) & 31); }
+// BTI of a 4-bit base code: the table "0 0 1 0 2 0 1 0 3 0 1 0 2 0 1 0" is the index of the lowest set bit (0 for code 0)
+__device__ __forceinline__ int nt16_bti_ffs(int c) { return max(__ffs(c) - 1, 0); }
+// eight 4-bit bases of a 32-bit word of BAM sequence in linear order (base k in bits 4k .. 4k+3): BAM keeps the first base
+// of a byte in the high nibble
+__device__ __forceinline__ uint32_t linear_nibbles(uint32_t v) { return ((v & 0x0F0F0F0Fu) << 4) | ((v >> 4) & 0x0F0F0F0Fu); }
+
+// One CTA per (tile of kPileTile positions, pool): the alignments overlapping the tile are walked once, 32 at a time per warp.
+//
+// Phase A, one LANE per alignment: the read's mismatches against the reference (the read filter needs them before any base
+// is counted), eight bases per step — the read's 4-bit codes XOR the reference stretch of the tile, which is staged in shared
+// memory as a stream of 4-bit codes; "differs" and "is N" are nibble masks, the count is a popc.
+// Phase B, one WARP per alignment that passed, each lane holding four consecutive bases as the bytes of a word (one 4-byte
+// quality load, one 2-byte base load per lane, the loads of the next alignments in flight).  A read that may count reference
+// bases adds +1 / -1 to a per-strand coverage difference array at its first / past-last position inside the tile; only its
+// EXCEPTIONS touch the counters: a base that differs from the reference (counted under its own allele when its quality
+// passes) or a reference base below MINQ takes one off the reference allele's counter.  After the walk a prefix sum of the
+// difference arrays gives, per position and strand, the reads that cover it, which are added to the reference allele's
+// counter — so the common case (base equals the reference, quality passes) costs no atomic at all.
+// The table of 8 counters per position (base + 4 strand) leaves as full 32-byte cells of the window table
+// win[position][pool][8].  An alignment is loaded by at most two tiles.
 __global__ void __launch_bounds__(256) k_pile_tile(PileReads rd, PileWindow w, uint32_t* __restrict__ win)
 {
 	__shared__ uint32_t hist[kPileTile * kPileCell];
+	__shared__ int cov[2][kPileTile + 8];
+	__shared__ uint32_t sref[kPileRefWords];        // reference codes, one per byte (0xFF: a character no read base can equal)
+	__shared__ uint32_t sref4[kPileRefWords / 2 + 2];  // the same as a stream of 4-bit codes
 	if (rd.state[0]) return;
 	const int max_span = rd.state[1];
+	const bool staged = max_span <= kPileSpan;
 	const int pool = blockIdx.y, t0 = w.w0 + blockIdx.x * kPileTile, t1 = min(t0 + kPileTile, w.w0 + w.W);
+	const int s0 = t0 - kPileSpan - 4;   // reference position of the first staged code
 	for (int k = threadIdx.x; k < kPileTile * kPileCell; k += blockDim.x) hist[k] = 0;
-	__syncthreads();
+	for (int k = threadIdx.x; k < 2 * (kPileTile + 8); k += blockDim.x) (&cov[0][0])[k] = 0;
+	int odd = 0;
+	if (staged)
+		for (int k = threadIdx.x; k < kPileRefWords; k += blockDim.x) {
+			uint32_t v = 0;
+#pragma unroll
+			for (int b = 0; b < 4; b++) {
+				const int code = ref_nt16(ref_at(w, s0 + 4 * k + b));
+				odd |= code == 0xFF;
+				v |= (uint32_t)code << (8 * b);
+			}
+			sref[k] = v;
+		}
+	const bool fast = staged && !__syncthreads_or(odd);   // (also the barrier after the zero fill and the staging)
+	if (!staged) __syncthreads();
+	if (fast) {
+		for (int k = threadIdx.x; k < kPileRefWords / 2; k += blockDim.x) {
+			const uint32_t a = sref[2 * k], b = sref[2 * k + 1];
+			sref4[k] = (a & 0xFu) | ((a >> 4) & 0xF0u) | ((a >> 8) & 0xF00u) | ((a >> 12) & 0xF000u) |
+			           ((b & 0xFu) << 16) | ((b << 12) & 0xF00000u) | ((b << 8) & 0xF000000u) | ((b << 4) & 0xF0000000u);
+		}
+		if (threadIdx.x < 2) sref4[kPileRefWords / 2 + threadIdx.x] = 0;
+		__syncthreads();
+	}
+	// reference code at position p / codes of p0 .. p0+3, one per byte
+	auto ref_code1 = [&](int p) -> int { return staged ? (int)((sref[(p - s0) >> 2] >> (8 * ((p - s0) & 3))) & 255u) : ref_nt16(ref_at(w, p)); };
+	auto ref_quad = [&](int p0) -> uint32_t {
+		if (staged) {
+			const int j = p0 - s0;
+			return __funnelshift_r(sref[j >> 2], sref[(j >> 2) + 1], 8 * (j & 3));
+		}
+		uint32_t v = 0;
+#pragma unroll
+		for (int b = 0; b < 4; b++) v |= (uint32_t)ref_nt16(ref_at(w, p0 + b)) << (8 * b);
+		return v;
+	};
+	const uint32_t minq4 = (uint32_t)(w.min_q < 0 ? 0 : (w.min_q > 127 ? 127 : w.min_q)) * 0x01010101u;
 	const uint32_t r0 = rd.pool_off[pool], r1 = rd.pool_off[pool + 1];
 	const uint32_t lo = lower_bound_pos(rd.rec, r0, r1, t0 - max_span + 1), hi = lower_bound_pos(rd.rec, r0, r1, t1);
 	const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-	for (uint32_t r = lo + (threadIdx.x >> 5); r < hi; r += nw) {
-		const crispgpu_alnrec a = rd.rec[r];
-		const int ml = a.mlen, clip = a.clip, end = clip + ml;
-		if (a.pos + ml <= t0) continue;
-		// pass 1: mismatches of the match block
-		int mm = 0;
-		Quad first{0, 0};
-		for (int c = 0; c < end; c += 128) {
-			const int i0 = c + 4 * lane;
-			if (i0 >= end || i0 + 4 <= clip) continue;
-			const Quad v = load_quad(rd, a.base_off, i0);
-			if (c == 0) first = v;
-#pragma unroll
-			for (int b = 0; b < 4; b++) {
-				const int k = i0 + b - clip;
-				if (k < 0 || k >= ml) continue;
-				const int code = quad_base(v, b);
-				mm += (code != 15 && nt16_char(code) != ref_at(w, a.pos + k)) ? 1 : 0;
+	for (uint32_t g = lo + 32u * (threadIdx.x >> 5); g < hi; g += 32u * nw) {
+		// ---- phase A: lane = alignment g + lane ----
+		const uint32_t mine = g + lane;
+		crispgpu_alnrec a{};
+		int fl = 0;
+		if (mine < hi) {
+			a = rd.rec[mine];
+			const int ml = a.mlen, clip = a.clip;
+			int mm = 0;
+			if (fast) {
+				const uint32_t* sw = reinterpret_cast<const uint32_t*>(rd.seq4 + (a.base_off >> 1)) + (clip >> 3);
+				const int sh = 4 * (clip & 7), lastw = ((clip + ml - 1) >> 3) - (clip >> 3);
+				uint32_t cur = linear_nibbles(__ldg(sw));
+				int jn = a.pos - s0;
+				for (int t = 0; 8 * t < ml; t++, jn += 8) {
+					const uint32_t nxt = (sh && t + 1 <= lastw) ? linear_nibbles(__ldg(sw + t + 1)) : 0u;
+					const uint32_t s8 = __funnelshift_r(cur, nxt, sh);
+					cur = sh ? nxt : ((8 * (t + 1) < ml) ? linear_nibbles(__ldg(sw + t + 1)) : 0u);
+					const uint32_t r8 = __funnelshift_r(sref4[jn >> 3], sref4[(jn >> 3) + 1], 4 * (jn & 7));
+					uint32_t x = s8 ^ r8;
+					x |= x >> 1; x |= x >> 2;
+					const uint32_t isn = s8 & (s8 >> 1) & (s8 >> 2) & (s8 >> 3);
+					uint32_t m = x & ~isn & 0x11111111u;
+					const int left = ml - 8 * t;
+					if (left < 8) m &= (1u << (4 * left)) - 1u;
+					mm += __popc(m);
+				}
+			} else {
+				for (int k = 0; k < ml; k++) {
+					const uint32_t i = a.base_off + clip + k;
+					const int code = (rd.seq4[i >> 1] >> ((i & 1) ? 0 : 4)) & 15;
+					mm += (code != 15 && code != ref_code1(a.pos + k)) ? 1 : 0;
+				}
+			}
+			const int maxmm = ml / 40 + 2;   // MAX_MM = alignedbases/40 + 2 (no gaps in this version)
+			const bool mq = a.mapq >= w.min_m;
+			fl = (mq && mm <= maxmm ? 1 : 0) | (mq && mm <= maxmm - 1 ? 2 : 0);
+			rd.flags[mine] = (uint8_t)fl;   // tiles that share the read write the same value
+			if (a.pos + ml <= t0) fl = 0;   // nothing of it inside this tile
+		}
+		// ---- phase B: the warp takes the alignments that passed one after the other ----
+		unsigned todo = __ballot_sync(0xffffffffu, fl & 1);
+		const uint32_t w0 = (uint32_t)a.pos, w1 = a.base_off, w2 = (uint32_t)a.clip | ((uint32_t)a.mlen << 16), w3 = (uint32_t)fl | (a.strand ? 4u : 0u);
+		while (todo) {
+			const int j = __ffs(todo) - 1;
+			todo &= todo - 1;
+			const int pos = (int)__shfl_sync(0xffffffffu, w0, j);
+			const uint32_t boff = __shfl_sync(0xffffffffu, w1, j);
+			const uint32_t cm = __shfl_sync(0xffffffffu, w2, j), fs = __shfl_sync(0xffffffffu, w3, j);
+			const int clip = (int)(cm & 0xffffu), ml = (int)(cm >> 16), end = clip + ml, st = (int)(fs & 4u);
+			const bool refs = (fs & 2u) != 0;   // reference bases of this read count
+			if (refs && lane == 0) {
+				atomicAdd(&cov[st >> 2][max(pos, t0) - t0], 1);
+				atomicAdd(&cov[st >> 2][min(pos + ml, t1) - t0], -1);
+			}
+			for (int c = 0; c < end; c += 128) {
+				const int i0 = c + 4 * lane;
+				if (i0 >= end || i0 + 4 <= clip) continue;
+				const uint32_t q = __ldg(reinterpret_cast<const uint32_t*>(rd.qual + boff + i0));
+				const uint32_t h = __ldg(reinterpret_cast<const uint16_t*>(rd.seq4 + (boff >> 1) + (i0 >> 1)));
+				// memory byte 0 = (base 0 high nibble, base 1 low nibble), byte 1 = (base 2, base 3): one code per byte
+				const uint32_t sq = ((h >> 4) & 0xFu) | ((h & 0xFu) << 8) | ((h & 0xF000u) << 4) | ((h & 0x0F00u) << 16);
+				const int p0 = pos + i0 - clip;
+				const uint32_t rq = ref_quad(p0);
+				const uint32_t x = sq ^ rq;
+				const uint32_t y = (x | (x >> 4)) & 0x0F0F0F0Fu;
+				const uint32_t neq = ((y + 0x0F0F0F0Fu) >> 4) & 0x01010101u;                        // differs from the reference
+				const uint32_t qok = ((((q | 0x80808080u) - minq4) | q) >> 7) & 0x01010101u;       // quality >= MINQ (MINQ <= 127)
+				const uint32_t valid = byte_range01(clip - i0, end - i0) & byte_range01(t0 - p0, t1 - p0);
+				// exceptions: with `refs` everything but (equal, quality ok); without, only the countable non-reference bases
+				uint32_t exc = valid & (refs ? (neq | (qok ^ 0x01010101u)) : (neq & qok));
+				while (exc) {
+					const int bit = __ffs(exc) - 1;
+					exc &= exc - 1;
+					const int x0 = p0 + (bit >> 3) - t0;
+					const int rc = (rq >> bit) & 255;
+					if (refs && rc != 0xFF) atomicSub(&hist[pile_slot(nt16_bti_ffs(rc) + st, x0)], 1u);
+					if ((neq >> bit) & (qok >> bit) & 1u) atomicAdd(&hist[pile_slot(nt16_bti_ffs((sq >> bit) & 15) + st, x0)], 1u);
+				}
 			}
 		}
-		mm = __reduce_add_sync(0xffffffffu, mm);
-		const int maxmm = ml / 40 + 2;   // MAX_MM = alignedbases/40 + 2 (no gaps in this version)
-		const bool mq = a.mapq >= w.min_m;
-		const int fl = (mq && mm <= maxmm ? 1 : 0) | (mq && mm <= maxmm - 1 ? 2 : 0);
-		if (lane == 0) rd.flags[r] = (uint8_t)fl;   // tiles that share the read write the same value
-		if (!(fl & 1)) continue;
-		// pass 2: count
-		const int st = a.strand ? 4 : 0;
-		for (int c = 0; c < end; c += 128) {
-			const int i0 = c + 4 * lane;
-			if (i0 >= end || i0 + 4 <= clip) continue;
-			const Quad v = c == 0 ? first : load_quad(rd, a.base_off, i0);
+	}
+	__syncthreads();
+	// coverage: prefix sums of the two difference arrays (one warp each), added to the reference allele's counters
+	if (threadIdx.x < 64) {
+		const int s = threadIdx.x >> 5;
+		int run = 0;
+		for (int x = lane; x < kPileTile; x += 32) {
+			int v = cov[s][x];
 #pragma unroll
-			for (int b = 0; b < 4; b++) {
-				const int k = i0 + b - clip;
-				if (k < 0 || k >= ml) continue;
-				const int p = a.pos + k;
-				if (p < t0 || p >= t1) continue;
-				if (quad_qual(v, b) < w.min_q) continue;
-				const int code = quad_base(v, b);
-				if (nt16_char(code) == ref_at(w, p) && !(fl & 2)) continue;
-				atomicAdd(&hist[(p - t0) * kPileCell + nt16_bti(code) + st], 1u);
-			}
+			for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += u; }
+			v += run;
+			run = __shfl_sync(0xffffffffu, v, 31);
+			cov[s][x] = v;
 		}
+	}
+	__syncthreads();
+	for (int k = threadIdx.x; k < 2 * (t1 - t0); k += blockDim.x) {
+		const int s = k & 1, x = k >> 1;
+		const int rc = ref_code1(t0 + x);
+		if (rc != 0xFF && cov[s][x]) hist[pile_slot(nt16_bti_ffs(rc) + 4 * s, x)] += (uint32_t)cov[s][x];
 	}
 	__syncthreads();
 	// 32-byte cells: two 16-byte stores per cell, consecutive positions 32 * P bytes apart
 	for (int k = threadIdx.x; k < (t1 - t0) * 2; k += blockDim.x) {
 		const int x = k >> 1, h = k & 1;
-		const uint4 v = *reinterpret_cast<const uint4*>(&hist[x * kPileCell + 4 * h]);
+		const uint4 v = make_uint4(hist[pile_slot(4 * h, x)], hist[pile_slot(4 * h + 1, x)], hist[pile_slot(4 * h + 2, x)], hist[pile_slot(4 * h + 3, x)]);
 		*reinterpret_cast<uint4*>(win + ((size_t)(t0 - w.w0 + x) * rd.P + pool) * kPileCell + 4 * h) = v;
 	}
 }

@@ -108,7 +108,21 @@ class RefEngine(_CpuEngine):
     lib_path = REF_LIB
     prefix = "crisp_ref"
 
-    def replay_vcf(self, batch: Batch, res: Results) -> str:
+    def replay_vcf(self, batch: Batch, res: Results, readdepths=None, mqcounts=None) -> str:
+        """VCF records of `res` printed by the reference's print_pooledvariant.  readdepths [n][P] / mqcounts [n][4]: the front
+        end's own counters for the DP and MQS fields (default: rebuilt from the allele counts)."""
+        st = self.lib.crisp_ref_set_printer_state
+        st.restype = None
+        st.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        rd = None if readdepths is None else np.ascontiguousarray(readdepths, np.int32)
+        mq = None if mqcounts is None else np.ascontiguousarray(mqcounts, np.int32)
+        st(self.h, None if rd is None else rd.ctypes.data, None if mq is None else mq.ctypes.data)
+        try:
+            return self._replay_vcf(batch, res)
+        finally:
+            st(self.h, None, None)
+
+    def _replay_vcf(self, batch: Batch, res: Results) -> str:
         fn = self.lib.crisp_ref_replay_vcf
         fn.restype = C.c_int
         fn.argtypes = [C.c_void_p, C.POINTER(CBatch), C.POINTER(HostResults), C.c_char_p, C.c_size_t,

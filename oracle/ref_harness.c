@@ -98,6 +98,9 @@ typedef struct ref_ctx {
 	unsigned char* refseq;
 	int reflen;
 	char err[256];
+	/* optional printer state of the batch being replayed (crisp_ref_set_printer_state): what the front end recorded */
+	const int32_t* pr_depths;   /* [n][P] variant->readdepths */
+	const int32_t* pr_mq;       /* [n][4] variant->MQcounts */
 } ref_ctx;
 
 static const char BASES[4] = {'A', 'C', 'G', 'T'};
@@ -678,6 +681,15 @@ int crisp_ref_run(void* h, const crispgpu_batch* b, crisp_host_results* out, int
  * reference's print_pooledvariant write the VCF record.  Used to prove "GPU results -> unchanged printer"
  * gives the same text as the reference end to end.
  */
+/* Read depths and mapping-quality classes the next crisp_ref_replay_vcf prints (NULL: rebuilt from the counts, as before).
+ * The front end owns these counters (parsebam/variant.c:280-283); the batch does not carry them. */
+void crisp_ref_set_printer_state(void* h, const int32_t* readdepths, const int32_t* mqcounts)
+{
+	ref_ctx* c = (ref_ctx*)h;
+	c->pr_depths = readdepths;
+	c->pr_mq = mqcounts;
+}
+
 int crisp_ref_replay_vcf(void* h, const crispgpu_batch* b, const crisp_host_results* res, char* vcf, size_t vcf_cap, size_t* vcf_len)
 {
 	ref_ctx* c = (ref_ctx*)h;
@@ -698,6 +710,8 @@ int crisp_ref_replay_vcf(void* h, const crispgpu_batch* b, const crisp_host_resu
 	for (int s = 0; s < b->n_sites; s++) {
 		if (res->varalleles[s] < 1) continue;
 		fill_site(c, b, s);
+		if (c->pr_depths) for (int i = 0; i < c->P; i++) v->readdepths[i] = c->pr_depths[(size_t)s * c->P + i];
+		if (c->pr_mq) for (int k = 0; k < 4; k++) v->MQcounts[k] = c->pr_mq[s * 4 + k];
 		for (int k = 0; k < 8; k++) {
 			maxvec[k].al = b->maxvec_al[s * 8 + k];
 			maxvec[k].ct = b->maxvec_ct[s * 8 + k];

@@ -244,7 +244,7 @@ def _random_alignments(rng, P, L, depth, ploidy, readlen=(30, 150), long_frac=0.
     (2, 3, 2500, 40, 8, dict(long_frac=0.1)),          # reads longer than one 128-base warp pass, tiles of 1024 positions crossed
     (3, 40, 300, 8, 2, {}),                            # diploid pools: the potential-variant score counts single reads
     (4, 1, 1500, 60, 30, {}),
-    (5, 70, 200, 10, 4, dict(readlen=(10, 40))),       # more than two lanes-rounds of pools, short reads
+    (5, 70, 200, 40, 4, dict(readlen=(10, 40))),       # more than two lanes-rounds of pools, short reads
 ], ids=["pooled", "long_reads", "diploid", "one_pool", "many_pools"])
 def test_device_pileup_matches_restatement(seed, P, L, depth, ploidy, kw):
     rng = np.random.default_rng(seed)
@@ -317,8 +317,7 @@ def test_device_pileup_refuses_what_it_cannot_pile():
 
 
 def _strip(info, perm):
-    info = re.sub(r"FLANKSEQ=[^;\t]*", "FLANKSEQ=", info)
-    info = re.sub(r"MQS=[^;]*", "MQS=", info)
+    info = re.sub(r"FLANKSEQ=[^;\t]*", "FLANKSEQ=", info)   # the harness has no reference sequence around the site
     return re.sub(r"CT=[^;]*", "CT=", info) if perm else info
 
 
@@ -350,21 +349,17 @@ def test_bam_to_vcf_through_the_device_pileup(tmp_path, poolsize, extra, opts, k
     cfg = eng.cfg
     eng.close()
     got = {}
-    for line in RefEngine(cfg).replay_vcf(sites.as_batch(P), res).splitlines():
+    # depth and mapping-quality classes are printed from the front end's own counters: the device pileup's go to the printer
+    for line in RefEngine(cfg).replay_vcf(sites.as_batch(P), res, readdepths=sites.readdepths, mqcounts=sites.mqcounts).splitlines():
         cols = line.split("\t")
-        got[int(sites.pos[int(cols[0])]) + 1] = (int(cols[0]), cols[1:])
+        got[int(sites.pos[int(cols[0])]) + 1] = cols[1:]
     if perm:   # Monte-Carlo p-values at the FAST_FILTER thresholds may flip a record in either run
         assert len(set(got) ^ set(want)) <= 3, sorted(set(got) ^ set(want))
     else:
         assert sorted(got) == sorted(want), f"only device {sorted(set(got) - set(want))[:5]}, only CRISP.binary {sorted(set(want) - set(got))[:5]}"
     for pos1 in sorted(set(got) & set(want)):
-        (s, g), w = got[pos1], want[pos1]
-        # depth and mapping-quality classes are printed from the front end's own counters: the device pileup's must be the reference's
-        assert re.search(r"MQS=([^;]*)", w[7]).group(1) == ",".join(str(int(x)) for x in sites.mqcounts[s])
-        assert [c.split(":")[2] for c in w[9:]] == [str(int(x)) for x in sites.readdepths[s]]
-        drop_dp = lambda cols: [":".join(f for k, f in enumerate(c.split(":")) if k != 2) for c in cols]  # noqa: E731
-        assert g[3:7] == w[3:7] and _strip(g[7], perm) == _strip(w[7], perm) and g[8] == w[8] and drop_dp(g[9:]) == drop_dp(w[9:]), \
-            f"record at {w[0]}:{w[1]} differs:\n{g}\n{w}"
+        g, w = got[pos1], want[pos1]
+        assert g[3:7] == w[3:7] and _strip(g[7], perm) == _strip(w[7], perm) and g[8:] == w[8:], f"record at {w[0]}:{w[1]} differs:\n{g}\n{w}"
 
 
 @pytest.mark.gpu
