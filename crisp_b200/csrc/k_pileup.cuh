@@ -140,13 +140,56 @@ __device__ __forceinline__ int nt16_bti_ffs(int c) { return max(__ffs(c) - 1, 0)
 // of a byte in the high nibble
 __device__ __forceinline__ uint32_t linear_nibbles(uint32_t v) { return ((v & 0x0F0F0F0Fu) << 4) | ((v >> 4) & 0x0F0F0F0Fu); }
 
+// first alignment of [lo, hi) whose position is >= key, by the whole warp: 32 probes per round instead of one
+__device__ __forceinline__ uint32_t lower_bound_warp(const crispgpu_alnrec* rec, uint32_t lo, uint32_t hi, int key, int lane)
+{
+	while (hi - lo > 32u) {
+		const uint32_t step = (hi - lo + 31u) >> 5;
+		const uint32_t at = lo + (uint32_t)lane * step;
+		const bool below = at < hi && rec[at].pos < key;       // monotone in the lane: a prefix of the lanes says yes
+		const int nb = __popc(__ballot_sync(0xffffffffu, below));
+		if (nb == 0) return lo;
+		const uint32_t nlo = lo + (uint32_t)(nb - 1) * step + 1u, nhi = lo + (uint32_t)nb * step;   // rec[nlo-1] < key <= rec[nhi] (if any)
+		lo = nlo;
+		hi = nhi < hi ? nhi : hi;
+	}
+	const bool below = lo + lane < hi && rec[lo + lane].pos < key;
+	return lo + (uint32_t)__popc(__ballot_sync(0xffffffffu, below));
+}
+
+// One alignment of phase B: the lane's four bases (one code per byte in `sq`, qualities in `q`) against the tile.
+template <bool STAGED, class RefQuad>
+__device__ __forceinline__ void pile_count_quad(uint32_t q, uint32_t h, int p0, int i0, int lo_i, int hi_i, bool refs, int st, int t0, uint32_t minq4,
+                                                uint32_t* hist, RefQuad&& ref_quad)
+{
+	// memory byte 0 = (base 0 high nibble, base 1 low nibble), byte 1 = (base 2, base 3): one code per byte
+	const uint32_t sq = __byte_perm((h & 0xF0F0u) >> 4, h & 0x0F0Fu, 0x5140);
+	const uint32_t rq = ref_quad(p0);
+	const uint32_t x = sq ^ rq;
+	const uint32_t y = (x | (x >> 4)) & 0x0F0F0F0Fu;
+	const uint32_t neq = ((y + 0x0F0F0F0Fu) >> 4) & 0x01010101u;                        // differs from the reference
+	const uint32_t qok = ((((q | 0x80808080u) - minq4) | q) >> 7) & 0x01010101u;       // quality >= MINQ (MINQ <= 127)
+	const uint32_t valid = (i0 >= lo_i && i0 + 4 <= hi_i) ? 0x01010101u : byte_range01(lo_i - i0, hi_i - i0);
+	// exceptions: with `refs` everything but (equal, quality ok); without, only the countable non-reference bases
+	uint32_t exc = valid & (refs ? (neq | (qok ^ 0x01010101u)) : (neq & qok));
+	while (exc) {
+		const int bit = __ffs(exc) - 1;
+		exc &= exc - 1;
+		const int x0 = p0 + (bit >> 3) - t0;
+		const int rc = (rq >> bit) & 255;
+		if (refs && rc != 0xFF) atomicSub(&hist[pile_slot(nt16_bti_ffs(rc) + st, x0)], 1u);
+		if ((neq >> bit) & (qok >> bit) & 1u) atomicAdd(&hist[pile_slot(nt16_bti_ffs((sq >> bit) & 15) + st, x0)], 1u);
+	}
+}
+
 // One CTA per (tile of kPileTile positions, pool): the alignments overlapping the tile are walked once, 32 at a time per warp.
 //
 // Phase A, one LANE per alignment: the read's mismatches against the reference (the read filter needs them before any base
 // is counted), eight bases per step — the read's 4-bit codes XOR the reference stretch of the tile, which is staged in shared
-// memory as a stream of 4-bit codes; "differs" and "is N" are nibble masks, the count is a popc.
+// memory as a stream of 4-bit codes; "differs" and "is N" are nibble masks, the count is a popc.  The lane leaves the record
+// and the filter outcome in the warp's slot of shared memory.
 // Phase B, one WARP per alignment that passed, each lane holding four consecutive bases as the bytes of a word (one 4-byte
-// quality load, one 2-byte base load per lane, the loads of the next alignments in flight).  A read that may count reference
+// quality load, one 2-byte base load per lane, the loads of the next alignment in flight).  A read that may count reference
 // bases adds +1 / -1 to a per-strand coverage difference array at its first / past-last position inside the tile; only its
 // EXCEPTIONS touch the counters: a base that differs from the reference (counted under its own allele when its quality
 // passes) or a reference base below MINQ takes one off the reference allele's counter.  After the walk a prefix sum of the
@@ -154,46 +197,16 @@ __device__ __forceinline__ uint32_t linear_nibbles(uint32_t v) { return ((v & 0x
 // counter — so the common case (base equals the reference, quality passes) costs no atomic at all.
 // The table of 8 counters per position (base + 4 strand) leaves as full 32-byte cells of the window table
 // win[position][pool][8].  An alignment is loaded by at most two tiles.
-__global__ void __launch_bounds__(256) k_pile_tile(PileReads rd, PileWindow w, uint32_t* __restrict__ win)
+template <bool STAGED>
+__device__ __forceinline__ void pile_tile_body(const PileReads& rd, const PileWindow& w, uint32_t* __restrict__ win, uint32_t* hist, int (*cov)[kPileTile + 8],
+                                               uint32_t* sref, uint32_t* sref4, uint4* srec, int* stot, int max_span, bool fast)
 {
-	__shared__ uint32_t hist[kPileTile * kPileCell];
-	__shared__ int cov[2][kPileTile + 8];
-	__shared__ uint32_t sref[kPileRefWords];        // reference codes, one per byte (0xFF: a character no read base can equal)
-	__shared__ uint32_t sref4[kPileRefWords / 2 + 2];  // the same as a stream of 4-bit codes
-	if (rd.state[0]) return;
-	const int max_span = rd.state[1];
-	const bool staged = max_span <= kPileSpan;
 	const int pool = blockIdx.y, t0 = w.w0 + blockIdx.x * kPileTile, t1 = min(t0 + kPileTile, w.w0 + w.W);
 	const int s0 = t0 - kPileSpan - 4;   // reference position of the first staged code
-	for (int k = threadIdx.x; k < kPileTile * kPileCell; k += blockDim.x) hist[k] = 0;
-	for (int k = threadIdx.x; k < 2 * (kPileTile + 8); k += blockDim.x) (&cov[0][0])[k] = 0;
-	int odd = 0;
-	if (staged)
-		for (int k = threadIdx.x; k < kPileRefWords; k += blockDim.x) {
-			uint32_t v = 0;
-#pragma unroll
-			for (int b = 0; b < 4; b++) {
-				const int code = ref_nt16(ref_at(w, s0 + 4 * k + b));
-				odd |= code == 0xFF;
-				v |= (uint32_t)code << (8 * b);
-			}
-			sref[k] = v;
-		}
-	const bool fast = staged && !__syncthreads_or(odd);   // (also the barrier after the zero fill and the staging)
-	if (!staged) __syncthreads();
-	if (fast) {
-		for (int k = threadIdx.x; k < kPileRefWords / 2; k += blockDim.x) {
-			const uint32_t a = sref[2 * k], b = sref[2 * k + 1];
-			sref4[k] = (a & 0xFu) | ((a >> 4) & 0xF0u) | ((a >> 8) & 0xF00u) | ((a >> 12) & 0xF000u) |
-			           ((b & 0xFu) << 16) | ((b << 12) & 0xF00000u) | ((b << 8) & 0xF000000u) | ((b << 4) & 0xF0000000u);
-		}
-		if (threadIdx.x < 2) sref4[kPileRefWords / 2 + threadIdx.x] = 0;
-		__syncthreads();
-	}
 	// reference code at position p / codes of p0 .. p0+3, one per byte
-	auto ref_code1 = [&](int p) -> int { return staged ? (int)((sref[(p - s0) >> 2] >> (8 * ((p - s0) & 3))) & 255u) : ref_nt16(ref_at(w, p)); };
+	auto ref_code1 = [&](int p) -> int { return STAGED ? (int)((sref[(p - s0) >> 2] >> (8 * ((p - s0) & 3))) & 255u) : ref_nt16(ref_at(w, p)); };
 	auto ref_quad = [&](int p0) -> uint32_t {
-		if (staged) {
+		if (STAGED) {
 			const int j = p0 - s0;
 			return __funnelshift_r(sref[j >> 2], sref[(j >> 2) + 1], 8 * (j & 3));
 		}
@@ -203,19 +216,19 @@ __global__ void __launch_bounds__(256) k_pile_tile(PileReads rd, PileWindow w, u
 		return v;
 	};
 	const uint32_t minq4 = (uint32_t)(w.min_q < 0 ? 0 : (w.min_q > 127 ? 127 : w.min_q)) * 0x01010101u;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 	const uint32_t r0 = rd.pool_off[pool], r1 = rd.pool_off[pool + 1];
-	const uint32_t lo = lower_bound_pos(rd.rec, r0, r1, t0 - max_span + 1), hi = lower_bound_pos(rd.rec, r0, r1, t1);
-	const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-	for (uint32_t g = lo + 32u * (threadIdx.x >> 5); g < hi; g += 32u * nw) {
+	const uint32_t lo = lower_bound_warp(rd.rec, r0, r1, t0 - max_span + 1, lane), hi = lower_bound_warp(rd.rec, r0, r1, t1, lane);
+	uint4* myrec = srec + 32 * warp;
+	for (uint32_t g = lo + 32u * warp; g < hi; g += 32u * nw) {
 		// ---- phase A: lane = alignment g + lane ----
 		const uint32_t mine = g + lane;
-		crispgpu_alnrec a{};
-		int fl = 0;
+		uint4 packed = make_uint4(0u, 0u, 0u, 0u);
 		if (mine < hi) {
-			a = rd.rec[mine];
+			const crispgpu_alnrec a = rd.rec[mine];
 			const int ml = a.mlen, clip = a.clip;
 			int mm = 0;
-			if (fast) {
+			if (STAGED && fast) {
 				const uint32_t* sw = reinterpret_cast<const uint32_t*>(rd.seq4 + (a.base_off >> 1)) + (clip >> 3);
 				const int sh = 4 * (clip & 7), lastw = ((clip + ml - 1) >> 3) - (clip >> 3);
 				uint32_t cur = linear_nibbles(__ldg(sw));
@@ -242,58 +255,61 @@ __global__ void __launch_bounds__(256) k_pile_tile(PileReads rd, PileWindow w, u
 			}
 			const int maxmm = ml / 40 + 2;   // MAX_MM = alignedbases/40 + 2 (no gaps in this version)
 			const bool mq = a.mapq >= w.min_m;
-			fl = (mq && mm <= maxmm ? 1 : 0) | (mq && mm <= maxmm - 1 ? 2 : 0);
+			int fl = (mq && mm <= maxmm ? 1 : 0) | (mq && mm <= maxmm - 1 ? 2 : 0);
 			rd.flags[mine] = (uint8_t)fl;   // tiles that share the read write the same value
 			if (a.pos + ml <= t0) fl = 0;   // nothing of it inside this tile
+			packed = make_uint4((uint32_t)a.pos, a.base_off, (uint32_t)a.clip | ((uint32_t)a.mlen << 16), (uint32_t)fl | (a.strand ? 4u : 0u));
 		}
+		__syncwarp();
+		myrec[lane] = packed;
+		__syncwarp();
 		// ---- phase B: the warp takes the alignments that passed one after the other ----
-		unsigned todo = __ballot_sync(0xffffffffu, fl & 1);
-		const uint32_t w0 = (uint32_t)a.pos, w1 = a.base_off, w2 = (uint32_t)a.clip | ((uint32_t)a.mlen << 16), w3 = (uint32_t)fl | (a.strand ? 4u : 0u);
+		unsigned todo = __ballot_sync(0xffffffffu, packed.w & 1u);
+		uint32_t q_n = 0, h_n = 0;
+		auto issue = [&](int j) {   // the first 128 bases of alignment j: loads in flight while the previous one is counted
+			const uint4 rj = myrec[j];
+			const int i0 = 4 * lane;
+			if (i0 < (int)((rj.z & 0xffffu) + (rj.z >> 16))) {
+				q_n = __ldg(reinterpret_cast<const uint32_t*>(rd.qual + rj.y + i0));
+				h_n = __ldg(reinterpret_cast<const uint16_t*>(rd.seq4 + (rj.y >> 1) + (i0 >> 1)));
+			}
+		};
+		if (todo) issue(__ffs(todo) - 1);
 		while (todo) {
 			const int j = __ffs(todo) - 1;
 			todo &= todo - 1;
-			const int pos = (int)__shfl_sync(0xffffffffu, w0, j);
-			const uint32_t boff = __shfl_sync(0xffffffffu, w1, j);
-			const uint32_t cm = __shfl_sync(0xffffffffu, w2, j), fs = __shfl_sync(0xffffffffu, w3, j);
-			const int clip = (int)(cm & 0xffffu), ml = (int)(cm >> 16), end = clip + ml, st = (int)(fs & 4u);
-			const bool refs = (fs & 2u) != 0;   // reference bases of this read count
+			const uint4 rj = myrec[j];
+			const uint32_t q0 = q_n, h0 = h_n;
+			if (todo) issue(__ffs(todo) - 1);
+			const int pos = (int)rj.x, clip = (int)(rj.z & 0xffffu), ml = (int)(rj.z >> 16), end = clip + ml, st = (int)(rj.w & 4u);
+			const bool refs = (rj.w & 2u) != 0;   // reference bases of this read count
+			// base indices of the read that lie inside the match block and inside the tile
+			const int lo_i = clip + max(t0 - pos, 0), hi_i = min(end, clip + t1 - pos);
 			if (refs && lane == 0) {
-				atomicAdd(&cov[st >> 2][max(pos, t0) - t0], 1);
-				atomicAdd(&cov[st >> 2][min(pos + ml, t1) - t0], -1);
+				int* cs = cov[st >> 2];
+				atomicAdd(cs + (pos + lo_i - clip - t0), 1);
+				atomicAdd(cs + (pos + hi_i - clip - t0), -1);
 			}
-			for (int c = 0; c < end; c += 128) {
+			{
+				const int i0 = 4 * lane;
+				if (i0 < hi_i && i0 + 4 > lo_i) pile_count_quad<STAGED>(q0, h0, pos + i0 - clip, i0, lo_i, hi_i, refs, st, t0, minq4, hist, ref_quad);
+			}
+			for (int c = 128; c < hi_i; c += 128) {   // reads longer than one pass of the warp
 				const int i0 = c + 4 * lane;
-				if (i0 >= end || i0 + 4 <= clip) continue;
-				const uint32_t q = __ldg(reinterpret_cast<const uint32_t*>(rd.qual + boff + i0));
-				const uint32_t h = __ldg(reinterpret_cast<const uint16_t*>(rd.seq4 + (boff >> 1) + (i0 >> 1)));
-				// memory byte 0 = (base 0 high nibble, base 1 low nibble), byte 1 = (base 2, base 3): one code per byte
-				const uint32_t sq = ((h >> 4) & 0xFu) | ((h & 0xFu) << 8) | ((h & 0xF000u) << 4) | ((h & 0x0F00u) << 16);
-				const int p0 = pos + i0 - clip;
-				const uint32_t rq = ref_quad(p0);
-				const uint32_t x = sq ^ rq;
-				const uint32_t y = (x | (x >> 4)) & 0x0F0F0F0Fu;
-				const uint32_t neq = ((y + 0x0F0F0F0Fu) >> 4) & 0x01010101u;                        // differs from the reference
-				const uint32_t qok = ((((q | 0x80808080u) - minq4) | q) >> 7) & 0x01010101u;       // quality >= MINQ (MINQ <= 127)
-				const uint32_t valid = byte_range01(clip - i0, end - i0) & byte_range01(t0 - p0, t1 - p0);
-				// exceptions: with `refs` everything but (equal, quality ok); without, only the countable non-reference bases
-				uint32_t exc = valid & (refs ? (neq | (qok ^ 0x01010101u)) : (neq & qok));
-				while (exc) {
-					const int bit = __ffs(exc) - 1;
-					exc &= exc - 1;
-					const int x0 = p0 + (bit >> 3) - t0;
-					const int rc = (rq >> bit) & 255;
-					if (refs && rc != 0xFF) atomicSub(&hist[pile_slot(nt16_bti_ffs(rc) + st, x0)], 1u);
-					if ((neq >> bit) & (qok >> bit) & 1u) atomicAdd(&hist[pile_slot(nt16_bti_ffs((sq >> bit) & 15) + st, x0)], 1u);
-				}
+				if (i0 >= hi_i || i0 + 4 <= lo_i) continue;
+				const uint32_t q = __ldg(reinterpret_cast<const uint32_t*>(rd.qual + rj.y + i0));
+				const uint32_t h = __ldg(reinterpret_cast<const uint16_t*>(rd.seq4 + (rj.y >> 1) + (i0 >> 1)));
+				pile_count_quad<STAGED>(q, h, pos + i0 - clip, i0, lo_i, hi_i, refs, st, t0, minq4, hist, ref_quad);
 			}
 		}
 	}
 	__syncthreads();
-	// coverage: prefix sums of the two difference arrays (one warp each), added to the reference allele's counters
-	if (threadIdx.x < 64) {
-		const int s = threadIdx.x >> 5;
+	// coverage: prefix sums of the two difference arrays — warp k scans a quarter of one strand, the quarters' totals are added
+	// when the sums go to the reference allele's counters
+	{
+		const int s = warp & 1, qd = warp >> 1, x0 = qd * (kPileTile / 4);
 		int run = 0;
-		for (int x = lane; x < kPileTile; x += 32) {
+		for (int x = x0 + lane; x < x0 + kPileTile / 4; x += 32) {
 			int v = cov[s][x];
 #pragma unroll
 			for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += u; }
@@ -301,12 +317,15 @@ __global__ void __launch_bounds__(256) k_pile_tile(PileReads rd, PileWindow w, u
 			run = __shfl_sync(0xffffffffu, v, 31);
 			cov[s][x] = v;
 		}
+		if (lane == 0) stot[s * 4 + qd] = run;
 	}
 	__syncthreads();
 	for (int k = threadIdx.x; k < 2 * (t1 - t0); k += blockDim.x) {
-		const int s = k & 1, x = k >> 1;
+		const int s = k & 1, x = k >> 1, qd = x / (kPileTile / 4);
+		int v = cov[s][x];
+		for (int d = 0; d < qd; d++) v += stot[s * 4 + d];
 		const int rc = ref_code1(t0 + x);
-		if (rc != 0xFF && cov[s][x]) hist[pile_slot(nt16_bti_ffs(rc) + 4 * s, x)] += (uint32_t)cov[s][x];
+		if (rc != 0xFF && v) hist[pile_slot(nt16_bti_ffs(rc) + 4 * s, x)] += (uint32_t)v;
 	}
 	__syncthreads();
 	// 32-byte cells: two 16-byte stores per cell, consecutive positions 32 * P bytes apart
@@ -315,6 +334,48 @@ __global__ void __launch_bounds__(256) k_pile_tile(PileReads rd, PileWindow w, u
 		const uint4 v = make_uint4(hist[pile_slot(4 * h, x)], hist[pile_slot(4 * h + 1, x)], hist[pile_slot(4 * h + 2, x)], hist[pile_slot(4 * h + 3, x)]);
 		*reinterpret_cast<uint4*>(win + ((size_t)(t0 - w.w0 + x) * rd.P + pool) * kPileCell + 4 * h) = v;
 	}
+}
+
+__global__ void __launch_bounds__(256) k_pile_tile(PileReads rd, PileWindow w, uint32_t* __restrict__ win)
+{
+	__shared__ uint32_t hist[kPileTile * kPileCell];
+	__shared__ int cov[2][kPileTile + 8];
+	__shared__ uint32_t sref[kPileRefWords];        // reference codes, one per byte (0xFF: a character no read base can equal)
+	__shared__ uint32_t sref4[kPileRefWords / 2 + 2];  // the same as a stream of 4-bit codes
+	__shared__ uint4 srec[256];                     // per warp: the 32 alignments of its group (position, base offset, clip | length, flags)
+	__shared__ int stot[8];
+	if (rd.state[0]) return;
+	const int max_span = rd.state[1];
+	const bool staged = max_span <= kPileSpan;
+	const int t0 = w.w0 + blockIdx.x * kPileTile;
+	const int s0 = t0 - kPileSpan - 4;
+	for (int k = threadIdx.x; k < kPileTile * kPileCell; k += blockDim.x) hist[k] = 0;
+	for (int k = threadIdx.x; k < 2 * (kPileTile + 8); k += blockDim.x) (&cov[0][0])[k] = 0;
+	int odd = 0;
+	if (staged)
+		for (int k = threadIdx.x; k < kPileRefWords; k += blockDim.x) {
+			uint32_t v = 0;
+#pragma unroll
+			for (int b = 0; b < 4; b++) {
+				const int code = ref_nt16(ref_at(w, s0 + 4 * k + b));
+				odd |= code == 0xFF;
+				v |= (uint32_t)code << (8 * b);
+			}
+			sref[k] = v;
+		}
+	const bool fast = staged && !__syncthreads_or(odd);   // (also the barrier after the zero fill and the staging)
+	if (!staged) __syncthreads();
+	if (fast) {
+		for (int k = threadIdx.x; k < kPileRefWords / 2; k += blockDim.x) {
+			const uint32_t a = sref[2 * k], b = sref[2 * k + 1];
+			sref4[k] = (a & 0xFu) | ((a >> 4) & 0xF0u) | ((a >> 8) & 0xF00u) | ((a >> 12) & 0xF000u) |
+			           ((b & 0xFu) << 16) | ((b << 12) & 0xF00000u) | ((b << 8) & 0xF000000u) | ((b << 4) & 0xF0000000u);
+		}
+		if (threadIdx.x < 2) sref4[kPileRefWords / 2 + threadIdx.x] = 0;
+		__syncthreads();
+	}
+	if (staged) pile_tile_body<true>(rd, w, win, hist, cov, sref, sref4, srec, stot, max_span, fast);
+	else pile_tile_body<false>(rd, w, win, hist, cov, sref, sref4, srec, stot, max_span, fast);
 }
 
 // sort_allelecounts (allelecounts.c:134-183, IUPAC off) on the eight per-allele read totals: reference allele swapped to
