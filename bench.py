@@ -361,13 +361,13 @@ def bam_end_to_end(cores: int):
                                              "batches": st["batches"], "h2d_bytes": st["h2d_bytes"], "d2h_bytes": st["d2h_bytes"]},
                     "note": "the front end (BAM decode + pileup, unchanged reference C, one process) is what remains of the wall time once the engine runs on the GPU"})
         try:
-            out["device_pileup"] = device_pileup_leg(ds, cores, sites, t_one, sh["wall_s"])
+            out["device_pileup"] = device_pileup_leg(ds, cores, sites, t_one, sh["wall_s"], ref_vcf=os.path.join(d, "ref.vcf"))
         except Exception as exc:  # noqa: BLE001
             out["device_pileup"] = {"error": repr(exc)[:300]}
     return out
 
 
-def device_pileup_leg(ds, cores, frontend_sites, ref_wall_1, ref_wall_regions, local=0, steps=10):
+def device_pileup_leg(ds, cores, frontend_sites, ref_wall_1, ref_wall_regions, local=0, steps=10, ref_vcf=None):
     """SURVEY.md section 8f items 1-3 on the same BAM files: host/bam_decode.c (host threads) -> crispgpu_pileup_run (allele counting,
     candidate screen and site packing on the device, then the engine) — no reference code in the loop.  Reports the decoder's
     rate, the pileup's resident and end-to-end rates (positions/s, candidate sites/s) and the HBM roofline of k_pile_tile."""
@@ -419,8 +419,25 @@ def device_pileup_leg(ds, cores, frontend_sites, ref_wall_1, ref_wall_regions, l
             "roofline": {"kernel": "k_pile_tile", "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": None,
                          "algorithmic_bytes": int(t["pile_bytes"]), "ms_per_launch": acc["pile_tile_ms"],
                          "bytes_definition": "16 per alignment + 1.5 per base (4-bit base + quality byte) + 32 per (position, pool) cell of the count table written"},
-            "bam_to_calls": {"wall_s": round(t_dec + e2e, 4), "vs_reference_1_process": ref_wall_1 / (t_dec + e2e), "vs_reference_regions": ref_wall_regions / (t_dec + e2e),
-                             "what": "decode (host threads) + one crispgpu_pileup_run, against CRISP.binary's wall time on the same files (VCF text not written here)"}}
+            "bam_to_vcf": bam_to_vcf_leg(ds, cores, ref_wall_1, ref_wall_regions, ref_vcf)}
+
+
+def bam_to_vcf_leg(ds, cores, ref_wall_1, ref_wall_regions, ref_vcf):
+    """The whole program without the reference: crisp_b200.caller.call_bams (decode on host threads, pileup + engine on the device,
+    VCF text by host/vcf_writer.c, file written) against CRISP.binary's wall time on the same files; records compared."""
+    import tempfile
+    from crisp_b200.caller import call_bams
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "b200.vcf")
+        call_bams(ds["bams"], ds["fasta"], ds["poolsize"], out_vcf=path, threads=cores)   # warm: library loads, pinned pools
+        r = call_bams(ds["bams"], ds["fasta"], ds["poolsize"], out_vcf=path, threads=cores)
+        body = lambda p: [x for x in open(p, "rb").read().split(b"\n") if x and not x.startswith(b"#")]  # noqa: E731
+        same = None if not ref_vcf else body(path) == body(ref_vcf)
+    return {"wall_s": round(r["wall_s"], 4), "decode_s": round(r["decode_s"], 4), "device_s": round(r["device_s"], 4), "format_s": round(r["format_s"], 4),
+            "records": r["records"], "records_identical_to_CRISP.binary": same,
+            "vs_reference_1_process": ref_wall_1 / r["wall_s"], "vs_reference_regions": ref_wall_regions / r["wall_s"],
+            "what": "BAM files to VCF file with no reference code in the loop (decode threads = host cores; one device window), against CRISP.binary on the same files: "
+                    "one process, and one process per core over --regions shards"}
 
 
 def main():

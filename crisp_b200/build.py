@@ -34,6 +34,22 @@ def build_bam_decoder(force: bool = False) -> str:
     return BAMLIB
 
 
+VCFLIB = os.path.join(CSRC, "libcrispvcf.so")
+
+
+def build_vcf_writer(force: bool = False) -> str:
+    """host/vcf_writer.c (batch VCF record formatter, plain C with pthreads) -> csrc/libcrispvcf.so."""
+    src = [os.path.join(HOST, "vcf_writer.c"), os.path.join(HOST, "vcf_writer.h"), os.path.join(HERE, "..", "include", "crispgpu.h")]
+    if not force and os.path.exists(VCFLIB) and all(os.path.getmtime(f) <= os.path.getmtime(VCFLIB) for f in src):
+        return VCFLIB
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-std=gnu99", "-Wall", "-fPIC", "-shared", "-o", VCFLIB, src[0], "-lpthread"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("gcc failed building libcrispvcf.so")
+    return VCFLIB
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
@@ -43,6 +59,7 @@ def needs_build() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     build_bam_decoder(force)
+    build_vcf_writer(force)
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
