@@ -460,8 +460,8 @@ def main():
     ap.add_argument("--no-arena", action="store_true", help="end-to-end leg: one pinned allocation per array instead of one arena for the batch")
     ap.add_argument("--contexts", type=int, default=0,
                     help="engine contexts per GPU in the end-to-end leg, one host thread each (batches in flight); 0 = 6, fewer when the ranks of a box would oversubscribe its cores")
-    ap.add_argument("--format", "--e2e-format", dest="e2e_format", default="bins", choices=["bins", "reads"],
-                    help="batch format of both legs: compact (read bins + sparse allele counts), or dense arrays with one element per read")
+    ap.add_argument("--format", "--e2e-format", dest="e2e_format", default="narrow", choices=["narrow", "bins", "reads"],
+                    help="batch format of both legs: compact in its narrow transport form (16-bit bins and counts), compact (32-bit read bins + sparse allele counts), or dense arrays with one element per read")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -500,7 +500,7 @@ def main():
     import torch
     import torch.distributed as dist
     from crisp_b200.abi import EngineConfig
-    from crisp_b200.engine import Engine, measure_fp64_tflops, measure_int32_tops, pin_batch
+    from crisp_b200.engine import Engine, NarrowBatch, measure_fp64_tflops, measure_int32_tops, pin_batch
     from crisp_b200 import build as cbuild
 
     if "CRISPGPU_LIB" not in os.environ:
@@ -518,8 +518,12 @@ def main():
     # region shard of this rank: its own contiguous run of candidate sites (tid = rank)
     batch = make_batch(wl, args.sites, seed=1 + rank, tid=rank)
     compact_batch = batch.compact()
-    shipped = compact_batch if args.e2e_format == "bins" else batch   # the form both legs consume
-    pinned = pin_batch(shipped, arena=not args.no_arena)
+    # the form both legs consume
+    if args.e2e_format == "narrow":
+        shipped = pinned = NarrowBatch(batch)
+    else:
+        shipped = compact_batch if args.e2e_format == "bins" else batch
+        pinned = pin_batch(shipped, arena=not args.no_arena)
     stream = torch.cuda.Stream(device=local)
     eng = Engine(cfg, device=local, stream=stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}") if "flushed" in config["l2_policy"] else None
@@ -541,11 +545,17 @@ def main():
     e2e_s, t_e2e, nctx = time_e2e(cfg_e2e, pinned, args.steps, args.warmup, want_ctx, local, barrier)
     clocks = sampler.stop() if rank == 0 else None
     # the same leg in the other batch format (fewer steps: the per-read arrays are 7x the bytes)
-    other_fmt = "reads" if args.e2e_format == "bins" else "bins"
+    other_fmt = "reads" if args.e2e_format != "reads" else "bins"
     other_steps = max(4, args.steps // 4)
     pinned_other = pin_batch(batch if other_fmt == "reads" else compact_batch, arena=not args.no_arena)
     e2e_other_s, t_e2e_other, _ = time_e2e(cfg_e2e, pinned_other, other_steps, args.warmup, want_ctx, local, barrier)
     del pinned_other
+    e2e_wide = None
+    if args.e2e_format == "narrow":   # the 32-bit compact form, for comparison
+        pinned_wide = pin_batch(compact_batch, arena=not args.no_arena)
+        ws, wt, _ = time_e2e(cfg_e2e, pinned_wide, args.steps, args.warmup, want_ctx, local, barrier)
+        e2e_wide = (ws, wt)
+        del pinned_wide
     results = eng.run(batch)
 
     # ---------------- coordinate-order merge of the per-rank results on rank 0 ----------------
@@ -566,14 +576,14 @@ def main():
             merge = {"gather_ms_per_batch": (g1 - g0) * 1e3, "merge_ms_per_batch": (g2 - g1) * 1e3, "sites": batch.n_sites * world,
                      "note": "host side, once per batch of all ranks; torch.distributed object gather (control plane) + crisp_b200.shard.merge_results"}
 
-    times = torch.tensor([ms, e2e_s * 1e3, e2e_other_s * 1e3], dtype=torch.float64, device=f"cuda:{local}")
+    times = torch.tensor([ms, e2e_s * 1e3, e2e_other_s * 1e3, (e2e_wide[0] if e2e_wide else 0.0) * 1e3], dtype=torch.float64, device=f"cuda:{local}")
     per_rank = [[float(times[0]) / args.steps, float(times[1]) / args.steps]]
     if world > 1:
         gathered_t = [torch.zeros_like(times) for _ in range(world)]
         dist.all_gather(gathered_t, times)
         per_rank = [[float(g[0]) / args.steps, float(g[1]) / args.steps] for g in gathered_t]
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max, e2e_other_ms_max = float(times[0]), float(times[1]), float(times[2])
+    ms_max, e2e_ms_max, e2e_other_ms_max, e2e_wide_ms_max = float(times[0]), float(times[1]), float(times[2]), float(times[3])
     total_sites = batch.n_sites * world
     value = total_sites * args.steps / (ms_max * 1e-3)
     e2e_value = total_sites * args.steps / (e2e_ms_max * 1e-3)
@@ -592,16 +602,18 @@ def main():
         # DRAM traffic per launch from the committed ncu --set full capture of this very configuration (null otherwise)
         traffic, ncu_static = {}, {}
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r2", "traffic.json"))).get(args.workload + (":bins" if args.e2e_format == "bins" else ""), {})
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2", "traffic.json"))).get(args.workload + (":bins" if args.e2e_format != "reads" else ""), {})
             if tj.get("sites") == batch.n_sites:
                 traffic = {k: v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in tj.items() if isinstance(v, dict)}
                 ncu_static = {k: {m: v[m] for m in ("issue_active_pct", "fp64_pipe_pct", "warp_instructions", "registers") if m in v} for k, v in tj.items() if isinstance(v, dict)}
         except Exception:
             pass
-        roofs, dominant = rooflines(args.workload, wl, batch, shipped, results, kt, args.steps, t_last["n_tasks_em"], args.e2e_format,
+        roofs, dominant = rooflines(args.workload, wl, batch, compact_batch if args.e2e_format == "narrow" else shipped, results, kt, args.steps, t_last["n_tasks_em"],
+                                    "bins" if args.e2e_format == "narrow" else args.e2e_format,
                                     hbm_peak, hbm_src, fp64_peak, int32_peak, traffic, ncu_static)
         second = max((k for k in roofs if k != dominant), key=lambda k: roofs[k]["ms_per_launch"])
-        fmt_label = {"bins": "compact (pre-binned by the host packer): reads as (value,count) bins per site x pool (consumed as they are by k_em), per-pool allele counts as non-zero entries (k_expand_counts)",
+        fmt_label = {"narrow": "compact, narrow transport form (crispgpu_batch_pack_narrow): reads pre-binned by the host packer as 16-bit (value, count) entries with one length byte per site x pool cell, per-pool allele counts as 16-bit non-zero entries; widened on the device (k_unpack_bins16, k_narrow_offsets, k_expand_counts16) into the compact arrays k_em consumes",
+                     "bins": "compact (pre-binned by the host packer): reads as (value,count) bins per site x pool (consumed as they are by k_em), per-pool allele counts as non-zero entries (k_expand_counts)",
                      "reads": "one 16-bit element per read (the format the reference arm consumes); sites that reach the likelihood fetched on demand (k_fetch_reads)"}
         line = {"metric": "candidate sites/sec", "value": value, "unit": "sites/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -616,6 +628,8 @@ def main():
                 "e2e_" + other_fmt: {"value": e2e_other_value, "unit": "sites/s", "steps": other_steps, "h2d_bytes_per_step": int(t_e2e_other["h2d_bytes"]),
                                      "d2h_bytes_per_step": int(t_e2e_other["d2h_bytes"]), "fetched_bytes_per_step": int(t_e2e_other["fetched_bytes"]),
                                      "ms_per_step": e2e_other_ms_max / other_steps, "input_format": fmt_label[other_fmt]},
+                **({"e2e_bins": {"value": total_sites * args.steps / (e2e_wide_ms_max * 1e-3), "unit": "sites/s", "steps": args.steps, "h2d_bytes_per_step": int(e2e_wide[1]["h2d_bytes"]),
+                                 "d2h_bytes_per_step": int(e2e_wide[1]["d2h_bytes"]), "ms_per_step": e2e_wide_ms_max / args.steps, "input_format": fmt_label["bins"]}} if e2e_wide else {}),
                 "gpu_launches": int(launches),
                 "per_rank_ms_per_step": {"resident": [round(x[0], 4) for x in per_rank], "e2e": [round(x[1], 4) for x in per_rank]},
                 "roofline": roofs[dominant], "roofline_secondary": roofs[second],

@@ -92,6 +92,12 @@ class CBatch(C.Structure):
         ("ic_sparse", C.c_void_p),
         ("arena_base", C.c_void_p),
         ("arena_bytes", C.c_uint64),
+        ("bins16", C.c_void_p),
+        ("bin_len", C.c_void_p),
+        ("bin_site", C.c_void_p),
+        ("ic16", C.c_void_p),
+        ("ic_len", C.c_void_p),
+        ("ic_site", C.c_void_p),
     ]
 
 
@@ -247,6 +253,34 @@ def sparse_counts_from_dense(indcounts: np.ndarray):
     ic = ((idx.astype(np.uint64) << 27) | val.astype(np.uint64)).astype(np.uint32)
     off = np.concatenate([[0], np.cumsum(np.bincount(cell, minlength=rows.shape[0]))]).astype(np.uint32)
     return off, ic
+
+
+def narrow_arrays(batch: "Batch") -> dict:
+    """numpy statement of the narrow transport form of a compact batch (crispgpu_batch.bins16 ... ic_site): what
+    crispgpu_batch_pack_narrow writes.  Test aid; the engine's path goes through the C packer."""
+    n, P = batch.n_sites, batch.n_pools
+
+    def split(words, cap, cnt_of, make):
+        cnt = cnt_of(words).astype(np.int64)
+        pieces = (cnt + cap - 1) // cap
+        idx = np.repeat(np.arange(words.shape[0]), pieces)
+        k = np.arange(idx.shape[0]) - np.repeat(np.cumsum(pieces) - pieces, pieces)
+        part = np.minimum(cnt[idx] - k * cap, cap)
+        return make(words[idx], part).astype(np.uint16), pieces
+
+    b16, bp = split(batch.bins, 32, lambda w: w >> 16,
+                    lambda w, c: (w & 0x7F) | (((w >> 8) & 0xF) << 7) | ((c - 1).astype(np.uint32) << 11))
+    i16, ip = split(batch.ic_sparse, 2047, lambda w: w & 0x7FFFFFF, lambda w, c: ((w >> 27) << 11) | c.astype(np.uint32))
+
+    def lens(off, pieces):
+        cum = np.concatenate([[0], np.cumsum(pieces)])
+        per = cum[off[1:].astype(np.int64)] - cum[off[:-1].astype(np.int64)]
+        site = np.concatenate([[0], np.cumsum(per.reshape(n, P).sum(axis=1))]).astype(np.uint32)
+        return per.astype(np.uint8), site
+
+    bl, bs = lens(batch.bin_off, bp)
+    il, isite = lens(batch.ic_off, ip)
+    return dict(bins16=b16, bin_len=bl, bin_site=bs, ic16=i16, ic_len=il, ic_site=isite)
 
 
 def bins_from_reads(read_off: np.ndarray, reads: np.ndarray):

@@ -57,6 +57,9 @@ struct crispgpu_ctx {
 	bool device_sort = false;      // maxvec_al/maxvec_ct are produced on the device (k_candidates)
 	bool sparse_ic = false;        // the batch came with sparse per-pool allele counts
 	bool binned = false;           // the batch came in the compact (value, count) read format
+	bool narrow = false;           // ... in its narrow transport form (bins16 / ic16): widened on the device
+	const void* nar[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // device addresses of bins16, bin_len, bin_site, ic16, ic_len, ic_site
+	DevBuf d_nar[6];
 	DevBuf d_exact_row, d_exact_cl, d_exact_done;  // exact_mode: term tables of the exact 2 x k test, per-task decided flags
 	// device batch
 	DevBuf d_b[24];
@@ -298,8 +301,14 @@ int launch_evaluate(crispgpu_ctx* ctx, const EngineParams& prm)
 		return 0;
 	};
 	const bool perm = ctx->cfg.chisq_permutation == 1, pivot = ctx->cfg.pivot_sample > 0;
-	if (perm) return pivot ? go(k_evaluate<4, true, true>, 4) : go(k_evaluate<4, true, false>, 4);
-	return pivot ? go(k_evaluate<4, false, true>, 4) : go(k_evaluate<4, false, false>, 4);
+	int rc = perm ? (pivot ? go(k_evaluate<4, true, true>, 4) : go(k_evaluate<4, true, false>, 4))
+	              : (pivot ? go(k_evaluate<4, false, true>, 4) : go(k_evaluate<4, false, false>, 4));
+	if (rc) return rc;
+	// p-values, filters, queues and the result zero fill: one thread per (site, slot)
+	const int fgrid = (n * kSlots + 255) / 256;
+	if (perm) { if (pivot) k_eval_finish<true, true><<<fgrid, 256, 0, ctx->stream>>>(prm); else k_eval_finish<true, false><<<fgrid, 256, 0, ctx->stream>>>(prm); }
+	else { if (pivot) k_eval_finish<false, true><<<fgrid, 256, 0, ctx->stream>>>(prm); else k_eval_finish<false, false><<<fgrid, 256, 0, ctx->stream>>>(prm); }
+	return 0;
 }
 
 struct BatchArray { const void* host; size_t bytes; };
@@ -307,10 +316,12 @@ struct BatchArray { const void* host; size_t bytes; };
 int collect_arrays(crispgpu_ctx* ctx, const crispgpu_batch* b, BatchArray* a)
 {
 	const size_t n = b->n_sites, P = ctx->P;
-	const bool sparse_ic = b->ic_off != nullptr && (b->ic_sparse != nullptr || (n && b->ic_off[n * P] == 0));
-	const bool binned = b->bins != nullptr || (b->bin_off != nullptr && n && b->bin_off[n * P] == 0);
-	if (!b->tid || !b->pos || !b->refbase || (!b->maxvec_al != !b->maxvec_ct) || !b->counts || (!b->indcounts && !sparse_ic) || (!b->read_off && !binned)) return CRISPGPU_ERR_ARG;
-	const size_t nreads = (n && !binned) ? b->read_off[n * P] : 0;
+	const bool narrow = b->bin_site != nullptr && b->ic_site != nullptr && b->bin_len != nullptr && b->ic_len != nullptr;
+	if (narrow && ((b->bin_site[n] && !b->bins16) || (b->ic_site[n] && !b->ic16))) return CRISPGPU_ERR_ARG;
+	const bool sparse_ic = !narrow && b->ic_off != nullptr && (b->ic_sparse != nullptr || (n && b->ic_off[n * P] == 0));
+	const bool binned = !narrow && (b->bins != nullptr || (b->bin_off != nullptr && n && b->bin_off[n * P] == 0));
+	if (!b->tid || !b->pos || !b->refbase || (!b->maxvec_al != !b->maxvec_ct) || !b->counts || (!b->indcounts && !sparse_ic && !narrow) || (!b->read_off && !binned && !narrow)) return CRISPGPU_ERR_ARG;
+	const size_t nreads = (n && !binned && !narrow) ? b->read_off[n * P] : 0;
 	const size_t nalt = (b->alt_off && n) ? b->alt_off[n * 5] : 0;
 	if (nreads && !b->reads) return CRISPGPU_ERR_ARG;
 	if (binned && !b->bin_off) return CRISPGPU_ERR_ARG;
@@ -323,11 +334,11 @@ int collect_arrays(crispgpu_ctx* ctx, const crispgpu_batch* b, BatchArray* a)
 	a[k++] = {b->maxvec_al, n * 8};
 	a[k++] = {b->maxvec_ct, n * 32};
 	a[k++] = {b->counts, n * 96};
-	a[k++] = {b->indcounts, n * P * 96};
+	a[k++] = {narrow ? nullptr : b->indcounts, n * P * 96};
 	a[k++] = {b->indel_len, b->indel_len ? n * 16 : 0};
 	a[k++] = {b->hplen, b->hplen ? n * 16 : 0};
-	a[k++] = {binned ? nullptr : b->read_off, (n * P + 1) * 4};  // a compact batch has no read stream to index
-	a[k++] = {b->reads, nreads * 2};
+	a[k++] = {(binned || narrow) ? nullptr : b->read_off, (n * P + 1) * 4};  // a compact batch has no read stream to index
+	a[k++] = {narrow ? nullptr : b->reads, nreads * 2};
 	a[k++] = {b->alt_off, b->alt_off ? (n * 5 + 1) * 4 : 0};
 	a[k++] = {b->alt_reads, nalt * sizeof(crispgpu_altread)};
 	a[k++] = {b->amb_idx, b->amb_idx ? n * 20 : 0};
@@ -342,6 +353,13 @@ int collect_arrays(crispgpu_ctx* ctx, const crispgpu_batch* b, BatchArray* a)
 	a[k++] = {sparse_ic ? b->ic_off : nullptr, sparse_ic ? (n * P + 1) * 4 : 0};
 	a[k++] = {sparse_ic ? b->ic_sparse : nullptr, sparse_ic && n ? (size_t)b->ic_off[n * P] * 4 : 0};
 	if (sparse_ic) a[6].host = nullptr;  // the dense table is rebuilt on the device
+	// narrow transport arrays (widened on the device into a[19], a[20] and the dense a[6])
+	a[k++] = {narrow ? b->bins16 : nullptr, narrow ? (size_t)b->bin_site[n] * 2 : 0};
+	a[k++] = {narrow ? b->bin_len : nullptr, narrow ? n * P : 0};
+	a[k++] = {narrow ? b->bin_site : nullptr, narrow ? (n + 1) * 4 : 0};
+	a[k++] = {narrow ? b->ic16 : nullptr, narrow ? (size_t)b->ic_site[n] * 2 : 0};
+	a[k++] = {narrow ? b->ic_len : nullptr, narrow ? n * P : 0};
+	a[k++] = {narrow ? b->ic_site : nullptr, narrow ? (n + 1) * 4 : 0};
 	return k;
 }
 
@@ -365,6 +383,17 @@ int validate_batch(crispgpu_ctx* ctx, const crispgpu_batch* b)
 	if ((rc = monotone(b->bin_off, n * P, "bin_off"))) return rc;
 	if ((rc = monotone(b->ic_off, n * P, "ic_off"))) return rc;
 	if ((rc = monotone(b->alt_off, n * 5, "alt_off"))) return rc;
+	if (b->bin_site && b->bin_len && b->ic_site && b->ic_len) {
+		if ((rc = monotone(b->bin_site, n, "bin_site")) || (rc = monotone(b->ic_site, n, "ic_site"))) return rc;
+		for (size_t s2 = 0; s2 < n; s2++) {
+			size_t nb = 0, ni = 0;
+			for (size_t i = 0; i < P; i++) { nb += b->bin_len[s2 * P + i]; ni += b->ic_len[s2 * P + i]; }
+			if (nb != b->bin_site[s2 + 1] - b->bin_site[s2] || ni != b->ic_site[s2 + 1] - b->ic_site[s2]) {
+				snprintf(ctx->err, sizeof ctx->err, "narrow batch: the cell lengths of site %zu do not add up to its run of entries", s2);
+				return CRISPGPU_ERR_ARG;
+			}
+		}
+	}
 	if (b->amb_idx)
 		for (size_t k = 0; k < n * 5; k++)
 			if (b->amb_idx[k] >= b->n_amb || b->amb_idx[k] < -1) { snprintf(ctx->err, sizeof ctx->err, "amb_idx[%zu] = %d outside [-1, %d)", k, b->amb_idx[k], b->n_amb); return CRISPGPU_ERR_ARG; }
@@ -386,7 +415,7 @@ int validate_batch(crispgpu_ctx* ctx, const crispgpu_batch* b)
 // sites that reach the quality-value likelihood — may stay in pinned host memory and be fetched on demand.
 int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b, bool lazy)
 {
-	BatchArray a[24];
+	BatchArray a[32];
 	const int k = collect_arrays(ctx, b, a);
 	if (k < 0) {
 		snprintf(ctx->err, sizeof ctx->err, "batch is missing a required array");
@@ -399,7 +428,8 @@ int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b, bool lazy)
 	constexpr size_t kLazyMinBytes = 1 << 20;
 	const bool reads_used = ctx->cfg.em_flag >= 1 && ctx->cfg.use_base_qvs == 1;
 	ctx->lazy_reads = nullptr;
-	ctx->binned = a[19].host != nullptr;
+	ctx->narrow = a[25].host != nullptr;   // bin_site present
+	ctx->binned = a[19].host != nullptr || ctx->narrow;
 	ctx->device_sort = false;
 	ctx->sparse_ic = a[21].host != nullptr;
 	// one-copy path: every array lies in the arena the batch declares
@@ -421,6 +451,27 @@ int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b, bool lazy)
 		bytes += (int64_t)b->arena_bytes;
 	}
 	for (int i = 0; i < k; i++) {
+		if (i >= 23) {   // narrow transport arrays: not part of the device batch, their widened forms are
+			const void*& dst = ctx->nar[i - 23];
+			dst = nullptr;
+			if (!a[i].bytes || !a[i].host) continue;
+			if (arena) { dst = static_cast<unsigned char*>(ctx->d_arena.p) + (static_cast<const unsigned char*>(a[i].host) - abase); continue; }
+			int rc = ensure_dev(ctx, ctx->d_nar[i - 23], a[i].bytes);
+			if (rc) return rc;
+			CK(cudaMemcpyAsync(ctx->d_nar[i - 23].p, a[i].host, a[i].bytes, cudaMemcpyHostToDevice, ctx->stream));
+			bytes += (int64_t)a[i].bytes;
+			dst = ctx->d_nar[i - 23].p;
+			continue;
+		}
+		if (ctx->narrow && (i == 6 || i == 19 || i == 20)) {   // widened on the device (k_expand_counts16, k_narrow_offsets, k_unpack_bins16)
+			const size_t nb16 = a[23].bytes / 2;
+			const size_t need = i == 6 ? a[6].bytes : (i == 19 ? ((size_t)b->n_sites * ctx->P + 1) * 4 : nb16 * 4);
+			int rc = ensure_dev(ctx, ctx->d_b[i], need ? need : 16);
+			if (rc) return rc;
+			dptr[i] = ctx->d_b[i].p;
+			if ((i == 19 || i == 20) && !reads_used) dptr[i] = nullptr;
+			continue;
+		}
 		if (arena && a[i].bytes && a[i].host != nullptr) {
 			dptr[i] = static_cast<unsigned char*>(ctx->d_arena.p) + (static_cast<const unsigned char*>(a[i].host) - abase);
 			continue;
@@ -469,7 +520,7 @@ int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b, bool lazy)
 	ctx->db.P = ctx->P;
 	ctx->n_sites = b->n_sites;
 	ctx->n_reads = (b->n_sites && !ctx->binned) ? b->read_off[(size_t)b->n_sites * ctx->P] : 0;
-	ctx->n_bins = (ctx->binned && b->n_sites) ? b->bin_off[(size_t)b->n_sites * ctx->P] : 0;
+	ctx->n_bins = !(ctx->binned && b->n_sites) ? 0 : (ctx->narrow ? b->bin_site[b->n_sites] : b->bin_off[(size_t)b->n_sites * ctx->P]);
 	ctx->timing.h2d_bytes = bytes;
 	ctx->copied_bytes = bytes;
 	return 0;
@@ -573,6 +624,13 @@ int run_stage1(crispgpu_ctx* ctx)
 		CK(cudaMemsetAsync(ctx->d_need_reads.p, 0, (size_t)n, ctx->stream));
 	} else ctx->lazy_reads = nullptr;
 	EngineParams prm = make_params(ctx);
+	if (ctx->narrow && n > 0) {
+		const int need = (n + 7) / 8;
+		k_expand_counts16<<<need < ctx->num_sms * 8 ? need : ctx->num_sms * 8, 256, 0, ctx->stream>>>(static_cast<const uint8_t*>(ctx->nar[4]), static_cast<const uint32_t*>(ctx->nar[5]),
+		                                                                                 static_cast<const uint16_t*>(ctx->nar[3]), static_cast<int32_t*>(ctx->d_b[6].p), n, ctx->P);
+		launches++;
+		CK(launch_check());
+	}
 	if (ctx->sparse_ic && n > 0) {
 		const size_t cells = (size_t)n * ctx->P;
 		k_expand_counts<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->db.ic_off, ctx->db.ic_sparse, static_cast<int32_t*>(ctx->d_b[6].p), cells);
@@ -586,12 +644,18 @@ int run_stage1(crispgpu_ctx* ctx)
 		CK(launch_check());
 	}
 	CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
-	const bool scan = n > 0 && g.em_flag >= 1 && g.use_base_qvs == 1 && !lazy && ((use_bins && ctx->n_bins > 0) || (!use_bins && ctx->n_reads > 0 && ctx->db.reads != nullptr));
+	const bool scan = n > 0 && g.em_flag >= 1 && g.use_base_qvs == 1 && !lazy && ((use_bins && (ctx->n_bins > 0 || ctx->narrow)) || (!use_bins && ctx->n_reads > 0 && ctx->db.reads != nullptr));
 	if (scan) {
 		// fork: the scan of the read stream (or of its compact bins) is independent of the count-based screening
 		CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
 		CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-		if (use_bins) k_scan_bins<<<ctx->num_sms * 2, 256, 0, ctx->side>>>(ctx->db.bins, ctx->n_bins, static_cast<int32_t*>(ctx->d_counters.p));
+		if (use_bins && ctx->narrow) {
+			const int need = (n + 7) / 8;
+			k_narrow_offsets<<<need < ctx->num_sms * 8 ? need : ctx->num_sms * 8, 256, 0, ctx->side>>>(static_cast<const uint8_t*>(ctx->nar[1]), static_cast<const uint32_t*>(ctx->nar[2]),
+			                                                                                static_cast<uint32_t*>(ctx->d_b[19].p), n, ctx->P);
+			if (ctx->n_bins > 0) k_unpack_bins16<<<ctx->num_sms * 4, 256, 0, ctx->side>>>(static_cast<const uint16_t*>(ctx->nar[0]), static_cast<uint32_t*>(ctx->d_b[20].p), ctx->n_bins, static_cast<int32_t*>(ctx->d_counters.p));
+			launches++;
+		} else if (use_bins) k_scan_bins<<<ctx->num_sms * 2, 256, 0, ctx->side>>>(ctx->db.bins, ctx->n_bins, static_cast<int32_t*>(ctx->d_counters.p));
 		else k_qualmap<<<ctx->num_sms * 2, 256, 0, ctx->side>>>(ctx->db.reads, ctx->n_reads, static_cast<int32_t*>(ctx->d_counters.p));
 		launches++;
 		CK(launch_check());
@@ -600,7 +664,7 @@ int run_stage1(crispgpu_ctx* ctx)
 	if (n > 0) {
 		rc = launch_evaluate(ctx, prm);
 		if (rc) return rc;
-		launches++;
+		launches += 2;
 	}
 	CK(launch_check());
 	if (scan) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
@@ -1176,6 +1240,7 @@ void crispgpu_destroy(crispgpu_ctx* ctx)
 	for (auto& b : ctx->d_b) fd(b);
 	fd(ctx->d_out_arena); fh(ctx->h_out_arena);
 	fd(ctx->d_rows); fh(ctx->h_rows); fd(ctx->d_arena);
+	for (auto& b : ctx->d_nar) fd(b);
 	fd(ctx->d_tail_task); fd(ctx->d_tail_head); fd(ctx->d_tail_total); fd(ctx->d_tail_rec); fd(ctx->d_tail_counters);
 	fd(ctx->d_perm_tasks); fd(ctx->d_call_tasks); fd(ctx->d_call_tasks2); fd(ctx->d_counters); fh(ctx->h_counters); fd(ctx->d_gws);
 	fd(ctx->p_pool_off); fd(ctx->p_rec); fd(ctx->p_mate); fd(ctx->p_isize); fd(ctx->p_seq4); fd(ctx->p_qual); fd(ctx->p_ref); fd(ctx->p_flags);
@@ -1528,6 +1593,127 @@ int crispgpu_pileup_run_resident(crispgpu_ctx* ctx, int fetch_results, crispgpu_
 	ctx->timing_pending = false;
 	CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
 	return pile_run(ctx, fetch_results != 0, sites, results);
+}
+
+
+namespace {
+
+struct NarrowPlan { size_t nb16, nic16; bool ok; };
+
+NarrowPlan narrow_plan(const crispgpu_batch* b, size_t P)
+{
+	NarrowPlan pl{0, 0, false};
+	const size_t n = (size_t)b->n_sites;
+	if (!b->bin_off || !b->ic_off || (n && b->bin_off[n * P] && !b->bins) || (n && b->ic_off[n * P] && !b->ic_sparse)) return pl;
+	for (size_t c = 0; c < n * P; c++) {
+		size_t e = 0;
+		for (uint32_t k = b->bin_off[c]; k < b->bin_off[c + 1]; k++) e += ((b->bins[k] >> 16) + 31) / 32;
+		if (e > 255) return pl;
+		pl.nb16 += e;
+		e = 0;
+		for (uint32_t k = b->ic_off[c]; k < b->ic_off[c + 1]; k++) e += ((b->ic_sparse[k] & 0x7ffffffu) + 2046) / 2047;
+		if (e > 255) return pl;
+		pl.nic16 += e;
+	}
+	pl.ok = true;
+	return pl;
+}
+
+// the arrays of a batch that travel unchanged in a narrow arena (everything but the read stream and the four compact arrays)
+struct Span { const void** field; size_t bytes; };
+int narrow_spans(crispgpu_batch* v, size_t P, Span* sp)
+{
+	const size_t n = (size_t)v->n_sites;
+	int k = 0;
+	auto add = [&](const void** f, size_t bytes) { sp[k].field = f; sp[k].bytes = *f ? bytes : 0; k++; };
+	add((const void**)&v->tid, n * 4); add((const void**)&v->pos, n * 4); add((const void**)&v->refbase, n);
+	add((const void**)&v->maxvec_al, n * 8); add((const void**)&v->maxvec_ct, n * 32); add((const void**)&v->counts, n * 96);
+	add((const void**)&v->indel_len, n * 16); add((const void**)&v->hplen, n * 16);
+	add((const void**)&v->alt_off, (n * 5 + 1) * 4); add((const void**)&v->alt_reads, (v->alt_off && n) ? (size_t)v->alt_off[n * 5] * sizeof(crispgpu_altread) : 0);
+	add((const void**)&v->amb_idx, n * 20); add((const void**)&v->amb_dec, (size_t)v->n_amb * P * 16); add((const void**)&v->amb_ep, (size_t)v->n_amb * P * 16);
+	add((const void**)&v->qhigh, n * P * 128); add((const void**)&v->stats, n * P * 128); add((const void**)&v->tstats, n * 128);
+	return k;
+}
+
+size_t pad256(size_t x) { return (x + 255) & ~size_t(255); }
+
+}  // namespace
+
+size_t crispgpu_batch_narrow_bytes(const crispgpu_batch* compact, int32_t n_pools)
+{
+	if (!compact || n_pools <= 0 || compact->n_sites < 0) return 0;
+	const size_t P = (size_t)n_pools, n = (size_t)compact->n_sites;
+	const NarrowPlan pl = narrow_plan(compact, P);
+	if (!pl.ok) return 0;
+	crispgpu_batch v = *compact;
+	Span sp[20];
+	const int k = narrow_spans(&v, P, sp);
+	size_t total = 0;
+	for (int i = 0; i < k; i++) total += pad256(sp[i].bytes);
+	total += pad256(pl.nb16 * 2) + pad256(n * P) + pad256((n + 1) * 4) + pad256(pl.nic16 * 2) + pad256(n * P) + pad256((n + 1) * 4);
+	return total + 256;
+}
+
+int crispgpu_batch_pack_narrow(const crispgpu_batch* compact, int32_t n_pools, void* arena, size_t arena_cap, crispgpu_batch* out)
+{
+	if (!compact || !arena || !out || n_pools <= 0 || (reinterpret_cast<uintptr_t>(arena) & 255)) return CRISPGPU_ERR_ARG;
+	const size_t need = crispgpu_batch_narrow_bytes(compact, n_pools);
+	if (need == 0 || need > arena_cap) return CRISPGPU_ERR_ARG;
+	const size_t P = (size_t)n_pools, n = (size_t)compact->n_sites;
+	const NarrowPlan pl = narrow_plan(compact, P);
+	*out = *compact;
+	Span sp[20];
+	const int k = narrow_spans(out, P, sp);
+	unsigned char* base = static_cast<unsigned char*>(arena);
+	size_t off = 0;
+	for (int i = 0; i < k; i++) {
+		if (*sp[i].field == nullptr) continue;                          // absent
+		if (sp[i].bytes == 0) { *sp[i].field = base + off; continue; }   // present but empty (a batch without sites)
+		memcpy(base + off, *sp[i].field, sp[i].bytes);
+		*sp[i].field = base + off;
+		off += pad256(sp[i].bytes);
+	}
+	auto take = [&](size_t bytes) { unsigned char* p = base + off; off += pad256(bytes); return p; };
+	uint16_t* b16 = reinterpret_cast<uint16_t*>(take(pl.nb16 * 2));
+	uint8_t* blen = take(n * P);
+	uint32_t* bsite = reinterpret_cast<uint32_t*>(take((n + 1) * 4));
+	uint16_t* i16 = reinterpret_cast<uint16_t*>(take(pl.nic16 * 2));
+	uint8_t* ilen = take(n * P);
+	uint32_t* isite = reinterpret_cast<uint32_t*>(take((n + 1) * 4));
+	size_t kb = 0, ki = 0;
+	for (size_t s = 0; s < n; s++) {
+		bsite[s] = (uint32_t)kb;
+		isite[s] = (uint32_t)ki;
+		for (size_t i = 0; i < P; i++) {
+			const size_t c = s * P + i, kb0 = kb, ki0 = ki;
+			for (uint32_t e = compact->bin_off[c]; e < compact->bin_off[c + 1]; e++) {
+				const uint32_t w = compact->bins[e];
+				for (uint32_t left = w >> 16; left > 0;) {
+					const uint32_t take_n = left > 32 ? 32 : left;
+					b16[kb++] = CRISPGPU_BIN16(w & 0xffffu, take_n);
+					left -= take_n;
+				}
+			}
+			for (uint32_t e = compact->ic_off[c]; e < compact->ic_off[c + 1]; e++) {
+				const uint32_t w = compact->ic_sparse[e];
+				for (uint32_t left = w & 0x7ffffffu; left > 0;) {
+					const uint32_t take_n = left > 2047 ? 2047 : left;
+					i16[ki++] = CRISPGPU_COUNT16(w >> 27, take_n);
+					left -= take_n;
+				}
+			}
+			blen[c] = (uint8_t)(kb - kb0);
+			ilen[c] = (uint8_t)(ki - ki0);
+		}
+	}
+	bsite[n] = (uint32_t)kb;
+	isite[n] = (uint32_t)ki;
+	out->indcounts = nullptr; out->read_off = nullptr; out->reads = nullptr;
+	out->bin_off = nullptr; out->bins = nullptr; out->ic_off = nullptr; out->ic_sparse = nullptr;
+	out->bins16 = b16; out->bin_len = blen; out->bin_site = bsite; out->ic16 = i16; out->ic_len = ilen; out->ic_site = isite;
+	out->arena_base = arena;
+	out->arena_bytes = off;
+	return CRISPGPU_OK;
 }
 
 int crispgpu_upload(crispgpu_ctx* ctx, const crispgpu_batch* batch)

@@ -258,28 +258,69 @@ __global__ void __launch_bounds__(WARPS * 32, (PIVOT ? 512 : kEvalThreadsPerSM) 
 				my_tested = af_ok ? 2 : 1;
 			}
 		}
-		// ---- lanes 0..4 finish their slot: p-value, filters, outputs ----
+		// ---- lanes 0..4 leave their slot's statistics for k_eval_finish (p-value, filters, outputs: one thread per slot there) ----
 		if (lane < kSlots) {
-			const int slot = lane, o = s * kSlots + slot;
-			int a1, a2, a3;
-			slot_alleles(mal, slot, a1, a2, a3);
+			const int o = s * kSlots + lane;
+			prm.o.status[o] = (uint8_t)my_tested;   // 0 untested, 1 rejected by the allele-frequency guess, 2 statistics follow
+			prm.o.paf[o] = my_p0;
+			prm.o.ctpval[o] = my_sj0;
+			prm.o.chi2pval[o] = my_sj1;
+		}
+	}
+}
+
+// appends v to a device queue for the lanes with pred set: one atomic per warp (all lanes of the warp must call it)
+__device__ __forceinline__ void queue_push_warp(int32_t* list, int32_t* counter, int32_t v, bool pred)
+{
+	const unsigned m = __ballot_sync(0xffffffffu, pred);
+	if (!m) return;
+	const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+	int base = 0;
+	if (lane == leader) base = atomicAdd(counter, __popc(m));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	if (pred) list[base + __popc(m & ((1u << lane) - 1u))] = v;
+}
+
+// Second half of the screening: one thread per (site, slot).  The incomplete-gamma tail (a series or a continued fraction of
+// up to 100 dependent steps, FET/kfunc.c:73-116) is the long pole of the screening; here 32 slots run it side by side in a
+// warp instead of five lanes of a warp per site.  Also the FAST_FILTER rejects, the task queues and the zero fill of every
+// per-slot result field.
+template <bool PERM, bool PIVOT>
+__global__ void __launch_bounds__(256) k_eval_finish(EngineParams prm)
+{
+	const DevBatch& b = prm.b;
+	const DevCfg& c = prm.c;
+	const int P = c.P, pivot = PIVOT ? c.pivot_sample : 0;
+	const int total = b.n_sites * kSlots, padded = (total + 31) & ~31;
+	for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < padded; o += gridDim.x * blockDim.x) {
+		const bool live = o < total;
+		bool to_perm = false, to_call = false, to_call2 = false;
+		if (live) {
+			const int s = o / kSlots, slot = o - s * kSlots;
+			const uint8_t* mal = b.maxvec_al + s * 8;
+			const int a2 = mal[slot + 1];
+			const int tested = prm.o.status[o];
+			const double p0 = prm.o.paf[o], sj0 = prm.o.ctpval[o], sj1 = prm.o.chi2pval[o];
 			uint8_t status = CRISPGPU_SLOT_UNTESTED;
 			double ctp = 0, chi = 0;
-			if (my_tested == 1) status = CRISPGPU_SLOT_REJECT_AF;
-			else if (my_tested == 2) {
-				if (!permmode) {
-					ctp = chi = chi2_from_groups(P, pivot, my_sj0, my_sj1, true);
-					status = pass_fast_filter(c, b, s, a2, my_p0, ctp, ctp, 0.0) ? CRISPGPU_SLOT_NOCALL : CRISPGPU_SLOT_REJECT_CT;
-					if (status == CRISPGPU_SLOT_NOCALL) push_call_task(prm, o, a2);
+			if (tested == 1) status = CRISPGPU_SLOT_REJECT_AF;
+			else if (tested == 2) {
+				if (!PERM) {
+					ctp = chi = chi2_from_groups(P, pivot, sj0, sj1, true);
+					status = pass_fast_filter(c, b, s, a2, p0, ctp, ctp, 0.0) ? CRISPGPU_SLOT_NOCALL : CRISPGPU_SLOT_REJECT_CT;
+					if (status == CRISPGPU_SLOT_NOCALL) {
+						if (c.em_flag >= 1 && (a2 >= 4 || c.use_base_qvs == 0)) to_call2 = true;
+						else { to_call = true; if (prm.q.need_reads) prm.q.need_reads[s] = 1; }
+					}
 				} else {
-					if (c.ploidy0 > 2) chi = chi2_from_groups(P, pivot, my_sj0, my_sj1, false);
+					if (c.ploidy0 > 2) chi = chi2_from_groups(P, pivot, sj0, sj1, false);
 					status = CRISPGPU_SLOT_REJECT_CT;  // provisional: k_filter decides once the permutation p-value exists
-					queue_push(prm.q.perm_tasks, prm.q.counters + 0, o);
+					to_perm = true;
 				}
 			}
 			prm.o.status[o] = status;
-			prm.o.allele[o] = mal[slot + 1];
-			prm.o.paf[o] = my_tested ? my_p0 : 0.0;
+			prm.o.allele[o] = (uint8_t)a2;
+			prm.o.paf[o] = tested ? p0 : 0.0;
 			prm.o.ctpval[o] = ctp;
 			prm.o.chi2pval[o] = chi;
 			prm.o.call_rank[o] = -1;
@@ -288,8 +329,13 @@ __global__ void __launch_bounds__(WARPS * 32, (PIVOT ? 512 : kEvalThreadsPerSM) 
 			prm.o.varpools[o] = 0; prm.o.allelecount[o] = 0; prm.o.variantpools[o] = 0;
 			prm.o.em_iters[o] = 0; prm.o.perm_k[o] = 0; prm.o.perm_hits[o] = 0;
 			prm.o.assoc_p[o] = 0; prm.o.assoc_llr[o] = 0; prm.o.assoc_or[o] = 0; prm.o.assoc_p1[o] = 0; prm.o.assoc_llr1[o] = 0; prm.o.assoc_or1[o] = 0;
+			if (slot == 0) { prm.o.varalleles[s] = 0; prm.o.strandpass[s] = 0; }
 		}
-		if (lane == 0) { prm.o.varalleles[s] = 0; prm.o.strandpass[s] = 0; }
+		if (PERM) queue_push_warp(prm.q.perm_tasks, prm.q.counters + 0, o, to_perm);
+		else {
+			queue_push_warp(prm.q.call_tasks, prm.q.counters + 1, o, to_call);
+			queue_push_warp(prm.q.call_tasks2, prm.q.counters + 8, o, to_call2);
+		}
 	}
 }
 
@@ -393,6 +439,86 @@ __global__ void k_expand_counts(const uint32_t* __restrict__ ic_off, const uint3
 			const uint32_t x = __ldg(ic_sparse + e);
 			const uint32_t idx = x >> 27;
 			if (idx < (uint32_t)kNC) row[idx] = (int32_t)(x & 0x7ffffffu);
+		}
+	}
+}
+
+// ---- narrow transport form (crispgpu_batch.bins16 / ic16): widened on the device into the compact arrays ----
+
+// One warp per site: the cells' entry counts (one byte each) become 32-bit offsets into the site's run of entries.
+__global__ void k_narrow_offsets(const uint8_t* __restrict__ len, const uint32_t* __restrict__ site, uint32_t* __restrict__ off, int n_sites, int P)
+{
+	const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+	for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < n_sites; s += gridDim.x * wpb) {
+		uint32_t run = site[s];
+		for (int i0 = 0; i0 < P; i0 += 32) {
+			const int i = i0 + lane;
+			const uint32_t v = i < P ? len[(size_t)s * P + i] : 0u;
+			uint32_t inc = v;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+			if (i < P) off[(size_t)s * P + i] = run + inc - v;
+			run += __shfl_sync(0xffffffffu, inc, 31);
+		}
+		if (s == n_sites - 1 && lane == 0) off[(size_t)n_sites * P] = run;
+	}
+}
+
+// 16-bit bins -> the (value, count) words k_em reads, eight per thread and trip (one 16-byte load, two 16-byte stores); the
+// quality-presence bitmap and the bidirectional flag (k_scan_bins' outputs) are taken on the way.
+__global__ void k_unpack_bins16(const uint16_t* __restrict__ bins16, uint32_t* __restrict__ bins, size_t n_bins, int32_t* counters)
+{
+	__shared__ unsigned char seen[kNQ];
+	int bidir = 0;
+	for (int q = threadIdx.x; q < kNQ; q += blockDim.x) seen[q] = 0;
+	__syncthreads();
+	auto widen = [&](uint32_t e) -> uint32_t {
+		seen[e & 0x7f] = 1;
+		if (e & 0x400u) bidir = 1;
+		return (e & 0x7fu) | (((e >> 7) & 0xfu) << 8) | ((((e >> 11) & 0x1fu) + 1u) << 16);
+	};
+	const size_t nvec = n_bins / 8;
+	const uint4* v = reinterpret_cast<const uint4*>(bins16);
+	uint4* o = reinterpret_cast<uint4*>(bins);
+	for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nvec; k += (size_t)gridDim.x * blockDim.x) {
+		const uint4 x = __ldg(v + k);
+		o[2 * k] = make_uint4(widen(x.x & 0xffffu), widen(x.x >> 16), widen(x.y & 0xffffu), widen(x.y >> 16));
+		o[2 * k + 1] = make_uint4(widen(x.z & 0xffffu), widen(x.z >> 16), widen(x.w & 0xffffu), widen(x.w >> 16));
+	}
+	if (blockIdx.x == 0 && threadIdx.x < (int)(n_bins - nvec * 8)) bins[nvec * 8 + threadIdx.x] = widen(bins16[nvec * 8 + threadIdx.x]);
+	if (__any_sync(0xffffffffu, bidir) && (threadIdx.x & 31) == 0) atomicOr(reinterpret_cast<unsigned int*>(counters) + 10, 1u);
+	__syncthreads();
+	for (int q = threadIdx.x; q < kNQ; q += blockDim.x)
+		if (seen[q]) atomicOr(reinterpret_cast<unsigned int*>(counters) + 4 + (q >> 5), 1u << (q & 31));
+}
+
+// Narrow sparse per-pool allele counts -> the dense [n][P][24] table: one warp per site finds its cells' entries from the
+// length bytes, every lane zeroes the 96-byte rows of its cells and adds their entries (entries of one index add up).
+__global__ void k_expand_counts16(const uint8_t* __restrict__ len, const uint32_t* __restrict__ site, const uint16_t* __restrict__ ic16,
+                                  int32_t* __restrict__ indcounts, int n_sites, int P)
+{
+	const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+	for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < n_sites; s += gridDim.x * wpb) {
+		uint32_t run = site[s];
+		for (int i0 = 0; i0 < P; i0 += 32) {
+			const int i = i0 + lane;
+			const uint32_t v = i < P ? len[(size_t)s * P + i] : 0u;
+			uint32_t inc = v;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+			if (i < P) {
+				int32_t* row = indcounts + ((size_t)s * P + i) * kNC;
+				int4* row4 = reinterpret_cast<int4*>(row);
+#pragma unroll
+				for (int k = 0; k < kNC / 4; k++) row4[k] = make_int4(0, 0, 0, 0);
+				const uint32_t e0 = run + inc - v;
+				for (uint32_t e = e0; e < e0 + v; e++) {
+					const uint32_t x = __ldg(ic16 + e);
+					const uint32_t idx = x >> 11;
+					if (idx < (uint32_t)kNC) row[idx] += (int32_t)(x & 0x7ffu);
+				}
+			}
+			run += __shfl_sync(0xffffffffu, inc, 31);
 		}
 	}
 }

@@ -21,6 +21,7 @@ EXPORTS = [
     "crispgpu_host_alloc", "crispgpu_host_free", "crispgpu_abi_version", "crispgpu_device_count",
     "crispgpu_measure_fp64_tflops", "crispgpu_measure_int32_tops",
     "crispgpu_pileup_run", "crispgpu_pileup_upload", "crispgpu_pileup_run_resident",
+    "crispgpu_batch_narrow_bytes", "crispgpu_batch_pack_narrow",
 ]
 
 _lib = None
@@ -122,6 +123,47 @@ def pin_batch(batch: Batch, arena: bool = True) -> Batch:
             out._pinned_blocks.append(block)
             setattr(out, name, arr)
     return out
+
+
+class NarrowBatch:
+    """A compact batch packed into one pinned arena in the narrow transport form (16-bit bins and counts, one length byte per
+    cell: crispgpu_batch_pack_narrow) — what a front end ships when the host link is the bound.  Takes the place of a `Batch`
+    in Engine.submit / upload."""
+
+    def __init__(self, batch: Batch, pinned: bool = True):
+        lib = load_library()
+        lib.crispgpu_batch_narrow_bytes.argtypes = [C.POINTER(CBatch), C.c_int32]
+        lib.crispgpu_batch_narrow_bytes.restype = C.c_size_t
+        lib.crispgpu_batch_pack_narrow.argtypes = [C.POINTER(CBatch), C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(CBatch)]
+        lib.crispgpu_batch_pack_narrow.restype = C.c_int
+        src = batch.compact()
+        csrc = src.as_c()
+        csrc.arena_base, csrc.arena_bytes = None, 0
+        need = lib.crispgpu_batch_narrow_bytes(C.byref(csrc), src.n_pools)
+        if need == 0:
+            raise EngineError("batch cannot be packed in the narrow form (a cell with more than 255 bins or count entries)")
+        if pinned:
+            self._block = _PinnedBlock(need)
+            ptr = self._block.ptr
+        else:   # pageable memory (CPU-side tests of the packer)
+            self._block = np.empty(need + 256, np.uint8)
+            ptr = (self._block.ctypes.data + 255) & ~255
+        self._c = CBatch()
+        rc = lib.crispgpu_batch_pack_narrow(C.byref(csrc), src.n_pools, ptr, need, C.byref(self._c))
+        if rc != 0:
+            raise EngineError(f"crispgpu_batch_pack_narrow failed: status {rc}")
+        self.n_sites, self.n_pools = batch.n_sites, batch.n_pools
+
+    def nbytes(self) -> int:
+        return int(self._c.arena_bytes)
+
+    def array(self, name: str, dtype, count: int) -> np.ndarray:
+        """View of one arena array (tests)."""
+        ptr = getattr(self._c, name)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(count * np.dtype(dtype).itemsize,)).view(dtype) if ptr and count else np.zeros(0, dtype)
+
+    def as_c(self) -> CBatch:
+        return self._c
 
 
 class Engine:

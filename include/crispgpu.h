@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define CRISPGPU_ABI_VERSION 3  /* 2: compact batch arrays (bins, sparse counts), crispgpu_advance, fetched_bytes
-                                   3: crispgpu_pileup_run, config.minimal_results, timing.pileup_ms, crispgpu_measure_int32_tops */
+                                   3: crispgpu_pileup_run, config.minimal_results, timing.pileup_ms, crispgpu_measure_int32_tops, narrow transport arrays */
 
 #define CRISPGPU_MAXALLELES 8  /* `maxalleles`, readmultiplebams.c:27: A,C,G,T + indel slots 4..6 */
 #define CRISPGPU_NCOUNT 24     /* 3 strand classes x 8 alleles: index = allele + s*8, s=0 fwd,1 rev,2 bidirectional
@@ -180,7 +180,27 @@ typedef struct crispgpu_batch {
 	 * must lie inside the arena (CRISPGPU_ERR_ARG otherwise).  NULL / 0: arrays are copied one by one. */
 	const void* arena_base;
 	uint64_t arena_bytes;
+	/* Narrow transport form of the two compact arrays (what crosses PCIe when the host link is the bound — eight ranks of
+	 * a box share it): 16-bit entries and one length byte per cell instead of 32-bit entries and 32-bit offsets.  Built
+	 * from a compact batch by crispgpu_batch_pack_narrow; when `bins16` / `ic16` are non-NULL the corresponding wide
+	 * arrays above are ignored and may be NULL.  The engine widens them on the device (k_unpack_bins16,
+	 * k_expand_counts16) into exactly the arrays the compact batch would have produced, so results are identical.
+	 *   bins16[k]  bits 0-6 quality char, 7-8 base, 9 strand, 10 bidirectional (crispgpu_read without its unused bit 7),
+	 *              bits 11-15 count - 1 (a bin of more than 32 reads takes several entries)
+	 *   bin_len[c] entries of cell c = s*P+i (a cell with more than 255 entries cannot be packed: pack_narrow refuses)
+	 *   bin_site[s] first entry of site s, bin_site[n] = total
+	 *   ic16[k]    bits 11-15 index (allele + 8*strand class), bits 0-10 count (entries of one index add up)
+	 *   ic_len[c], ic_site[s] as above */
+	const uint16_t* bins16;
+	const uint8_t* bin_len;      /* [n*P] */
+	const uint32_t* bin_site;    /* [n+1] */
+	const uint16_t* ic16;
+	const uint8_t* ic_len;       /* [n*P] */
+	const uint32_t* ic_site;     /* [n+1] */
 } crispgpu_batch;
+
+#define CRISPGPU_BIN16(read_value, count) ((uint16_t)(((read_value) & 0x7f) | ((((read_value) >> 8) & 0xf) << 7) | ((((count) - 1) & 0x1f) << 11)))
+#define CRISPGPU_COUNT16(index, count) ((uint16_t)((((index) & 0x1f) << 11) | ((count) & 0x7ff)))
 
 /* Per tested allele slot (al = slot+1 of maxvec), state of the reference's per-allele loop
  * (newcrispcaller.c:205-246). */
@@ -376,6 +396,14 @@ int crispgpu_run_resident(crispgpu_ctx* ctx, int fetch_results, crispgpu_results
 
 int crispgpu_get_timing(crispgpu_ctx* ctx, crispgpu_timing* out);
 const char* crispgpu_last_error(crispgpu_ctx* ctx);
+
+/* Narrow transport: bytes crispgpu_batch_pack_narrow needs for `compact` (a batch with bins/bin_off and ic_sparse/ic_off), or 0
+ * when the batch cannot be packed (not compact, or a cell with more than 255 entries). */
+size_t crispgpu_batch_narrow_bytes(const crispgpu_batch* compact, int32_t n_pools);
+/* Packs every array of `compact` into `arena` (256-byte aligned, from crispgpu_host_alloc) with the two compact arrays in their narrow
+ * form; *out views the arena (arena_base / arena_bytes set: one host-to-device copy).  Host code only.  Returns 0, or
+ * CRISPGPU_ERR_ARG when the batch cannot be packed or the arena is too small. */
+int crispgpu_batch_pack_narrow(const crispgpu_batch* compact, int32_t n_pools, void* arena, size_t arena_cap, crispgpu_batch* out);
 
 /* Pinned host memory for batch arrays. */
 void* crispgpu_host_alloc(size_t bytes);
