@@ -18,6 +18,7 @@
  *   CRISPGPU_DEVICE     CUDA device (default 0)
  *   CRISPGPU_BATCH      candidate sites per batch (default 4096)
  *   CRISPGPU_COMPACT    1: ship (value,count) bins and sparse counts instead of one element per read
+ *                       2: ... in their narrow transport form (crispgpu_batch_pack_narrow: 16-bit entries, one pinned arena)
  *   CRISPGPU_SEED       key of the engine's counter-based RNG (permutation tests); default 1
  *   CRISPGPU_EXACT      1: exact p-value for small tables (config.exact_mode)
  *   CRISPGPU_DUMP       file: every flushed batch is appended to it in the layout tests/frontend_io.py reads
@@ -57,6 +58,10 @@ typedef struct {
 	int (*wait)(crispgpu_ctx*, int64_t, crispgpu_results*);
 	const char* (*last_error)(crispgpu_ctx*);
 	int (*get_timing)(crispgpu_ctx*, crispgpu_timing*);
+	size_t (*narrow_bytes)(const crispgpu_batch*, int32_t);
+	int (*pack_narrow)(const crispgpu_batch*, int32_t, void*, size_t, crispgpu_batch*);
+	void* (*host_alloc)(size_t);
+	void (*host_free)(void*);
 } engine_api;
 
 /* what print_pooledvariant reads from struct VARIANT / REFLIST beyond the batch arrays (newcrispprint.c:347-476) */
@@ -72,7 +77,9 @@ typedef struct {
 } site_state;
 
 static struct {
-	int ready, dump_only, batch_sites, finished;
+	int ready, dump_only, batch_sites, finished, narrow;
+	void* arena;          /* pinned arena of the narrow transport form */
+	size_t arena_cap;
 	engine_api api;
 	crispgpu_ctx* ctx;
 	crispgpu_config cfg;
@@ -131,6 +138,10 @@ static void load_engine(void)
 	SYM(wait, "crispgpu_wait");
 	SYM(last_error, "crispgpu_last_error");
 	SYM(get_timing, "crispgpu_get_timing");
+	SYM(narrow_bytes, "crispgpu_batch_narrow_bytes");
+	SYM(pack_narrow, "crispgpu_batch_pack_narrow");
+	SYM(host_alloc, "crispgpu_host_alloc");
+	SYM(host_free, "crispgpu_host_free");
 #undef SYM
 }
 
@@ -197,6 +208,7 @@ static void frontend_init(struct VARIANT* variant, REFLIST* reflist, FILE* vfile
 	F.sb = crisp_shim_batch_new(P, CHISQ_PERMUTATION != 0, EMflag == 0);
 	if (!F.sb) die("out of memory", NULL);
 	crisp_shim_batch_set_compact(F.sb, getenv("CRISPGPU_COMPACT") && atoi(getenv("CRISPGPU_COMPACT")));
+	F.narrow = getenv("CRISPGPU_COMPACT") && atoi(getenv("CRISPGPU_COMPACT")) == 2;
 	memset(&F.pv, 0, sizeof F.pv);
 	F.pv.ploidy = (int*)calloc(P, sizeof(int));
 	for (int i = 0; i < P; i++) F.pv.ploidy[i] = variant->ploidy[i];
@@ -330,7 +342,21 @@ static void frontend_flush(void)
 		crispgpu_results r;
 		int64_t ticket = 0;
 		double t0 = now_s();
-		int rc = F.api.submit(F.ctx, &b, &ticket);
+		/* narrow transport: the compact arrays as 16-bit entries in one pinned arena (falls back to the compact batch when a cell
+		 * is too full for a length byte) */
+		crispgpu_batch nb;
+		const crispgpu_batch* ship = &b;
+		if (F.narrow) {
+			const size_t need = F.api.narrow_bytes(&b, F.cfg.n_pools);
+			if (need > F.arena_cap) {
+				if (F.arena) F.api.host_free(F.arena);
+				F.arena_cap = need + need / 2;
+				F.arena = F.api.host_alloc(F.arena_cap);
+				if (!F.arena) die("pinned allocation failed", NULL);
+			}
+			if (need && F.api.pack_narrow(&b, F.cfg.n_pools, F.arena, F.arena_cap, &nb) == 0) ship = &nb;
+		}
+		int rc = F.api.submit(F.ctx, ship, &ticket);
 		if (rc == 0) rc = F.api.wait(F.ctx, ticket, &r);
 		if (rc != 0) die("engine call failed", F.api.last_error(F.ctx));
 		crispgpu_timing tm;

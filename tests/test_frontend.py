@@ -197,8 +197,8 @@ def _ct_ok(a, b, perms):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,compact", [("pooled", 0), ("pooled", 1), ("em0", 0), ("diploid", 0), ("diploid", 1), ("manyquals", 0),
-                                          ("manyquals", 1), ("perm", 0)])
+@pytest.mark.parametrize("name,compact", [("pooled", 0), ("pooled", 1), ("pooled", 2), ("em0", 0), ("em0", 2), ("diploid", 0), ("diploid", 1), ("diploid", 2),
+                                          ("manyquals", 0), ("manyquals", 1), ("manyquals", 2), ("perm", 0), ("perm", 2)])
 def test_bam_to_vcf_on_gpu_equals_reference(name, compact, datasets, tmp_path):
     """variantcalls.c / newcrispprint.c unchanged, engine on the B200: identical VCF."""
     _programs()
