@@ -43,7 +43,7 @@ WORKLOADS = {
     "c4_perm_stress_em0": dict(P=50, ploidy=48, depth=200, options=dict(chisq_permutation=1, max_iter=1000000, em_flag=0, thresh1=-6.0),
                                synth=dict(variant_frac=0.8, rare=True, with_stats=True, with_qhigh=True)),
     # config 2 with a 40-valued quality spectrum (older instruments): the likelihood takes the sparse path, bins barely compress
-    "exome50x48_q40": dict(P=50, ploidy=48, depth=200, options={}, synth=dict(variant_frac=0.15, quals=range(2, 42))),
+    "exome50x48_q40": dict(P=50, ploidy=48, depth=200, options={}, synth=dict(variant_frac=0.15, quals=range(13, 53))),
 }
 
 # the other BASELINE configs, measured at reduced size inside the default run: (workload, sites, reference sites per core)

@@ -42,7 +42,7 @@ def test_abi_version_and_defaults(lib):
 def test_struct_sizes_match_header():
     # LP64 layout of include/crispgpu.h
     assert C.sizeof(Config) == 4 * 2 + 8 + 4 * 12 + 8 + 8 * 8 + 8 + 4 * 4
-    assert C.sizeof(CBatch) == 8 + 8 * 16 + 8 + 8 * 9
+    assert C.sizeof(CBatch) == 8 + 8 * 16 + 8 + 8 * 9 + 8 * 6
     assert C.sizeof(CResults) == 8 + 8 * 29
     assert C.sizeof(Timing) == 4 * 8 + 4 * 2 + 8 * 4 + 4 * 4 + 8
 
@@ -102,8 +102,8 @@ int main(void)
 	crispgpu_config_defaults(&c);
 	printf("%d %d %d %d %.1f %u %u %u %d\n", crispgpu_abi_version(), c.em_flag, c.max_iter, c.min_reads, c.thresh1,
 	       (unsigned)(bin >> 16), (unsigned)(bin & 0xffff), (unsigned)(cnt >> 27), (int)(b.bins == NULL));
-	printf("%u %u %u %u %u\n", (unsigned)sizeof(crispgpu_alnrec), (unsigned)sizeof(crispgpu_alignments), (unsigned)sizeof(crispgpu_window),
-	       (unsigned)sizeof(crispgpu_pileup_sites), (unsigned)sizeof(crispgpu_timing));
+	printf("%u %u %u %u %u %u\n", (unsigned)sizeof(crispgpu_alnrec), (unsigned)sizeof(crispgpu_alignments), (unsigned)sizeof(crispgpu_window),
+	       (unsigned)sizeof(crispgpu_pileup_sites), (unsigned)sizeof(crispgpu_timing), (unsigned)sizeof(crispgpu_batch));
 	return 0;
 }
 ''')
@@ -115,4 +115,5 @@ int main(void)
     assert out[:5] == ["3", "1", "20000", "4", "-3.5"]
     assert out[5:9] == ["7", str(ord("I") | (2 << 8) | (1 << 10)), "9", "1"]
     from crisp_b200.pileup import ALNREC_DTYPE, CAlignments, CPileupSites, CWindow
-    assert [int(x) for x in out[9:]] == [ALNREC_DTYPE.itemsize, C.sizeof(CAlignments), C.sizeof(CWindow), C.sizeof(CPileupSites), C.sizeof(Timing)]
+    from crisp_b200.abi import CBatch
+    assert [int(x) for x in out[9:]] == [ALNREC_DTYPE.itemsize, C.sizeof(CAlignments), C.sizeof(CWindow), C.sizeof(CPileupSites), C.sizeof(Timing), C.sizeof(CBatch)]
