@@ -94,6 +94,10 @@ struct crispgpu_ctx {
 	bool em_smem_g = true;
 	int pm_threads = 256, pm_grid = 0, pm_l10cap = 2048;
 	size_t pm_smem = 0;
+	int ps_l10cap = 2048;
+	bool ps_many = false;              // many-pool geometry of the stranded kernels (hash tables / narrow columns over a fixed area)
+	int ps_threads = 0, ps_area = 0;   // stranded permutation kernels: block size and bytes of the occupancy area (hash tables at many pools)
+	size_t ps_smem = 0;
 	int lg_grid = 0;
 	size_t lg_smem = 0;
 	// bookkeeping
@@ -241,6 +245,20 @@ int setup_geometry(crispgpu_ctx* ctx)
 	while (ctx->pm_threads > 32 && pfixed + (size_t)P * ctx->pm_threads * 4 > budget - 1024) ctx->pm_threads >>= 1;
 	ctx->pm_smem = pfixed + (size_t)P * ctx->pm_threads * 4;
 	if (ctx->pm_smem > budget) ctx->pm_smem = 0;  // permutation modes unsupported for this many pools
+	// stranded test: below kPermHashPools pools the occupancy area is the [P][T] columns; from there on full blocks over a fixed
+	// area, in which a permutation keeps a hash table sized by the balls of its table (or a column, when the balls are many)
+	ctx->ps_threads = ctx->pm_threads;
+	ctx->ps_area = (int)((size_t)P * ctx->pm_threads * 4);
+	ctx->ps_smem = ctx->pm_smem;
+	ctx->ps_l10cap = ctx->pm_l10cap;
+	if (P >= kPermHashPools && ctx->pm_smem) {
+		// many pools are shallow pools: a short log table (deeper tables compute the logarithms), three CTAs per SM
+		const int l10 = P > 512 ? P : 512;
+		const size_t sfixed = pfixed - sizeof(double) * (ctx->pm_l10cap > P ? ctx->pm_l10cap : P) + sizeof(double) * l10;
+		size_t area = (budget - 1024) / 3 > sfixed + 2048 ? ((budget - 1024) / 3 - sfixed - 1024) & ~size_t(255) : 0;
+		if (area < (size_t)P * 4 * 32) area = (size_t)P * 4 * 32;   // at least one warp of 32-bit columns
+		if (sfixed + area <= budget - 1024) { ctx->ps_threads = 256; ctx->ps_area = (int)area; ctx->ps_smem = sfixed + area; ctx->ps_l10cap = l10; ctx->ps_many = true; }
+	}
 	ctx->lg_smem = (size_t)4 * P * sizeof(double);
 	return 0;
 }
@@ -675,8 +693,11 @@ int run_stage1(crispgpu_ctx* ctx)
 			return CRISPGPU_ERR_UNSUPPORTED;
 		}
 		if (ctx->ploidy[0] > 2) {
+			const bool many = ctx->ps_many;
 			if (!ctx->pm_grid) {
-				rc = occupancy_grid(ctx, k_permute_stranded, ctx->pm_threads, ctx->pm_smem, &ctx->pm_grid); if (rc) return rc;
+				rc = many ? occupancy_grid(ctx, k_permute_stranded<true>, ctx->ps_threads, ctx->ps_smem, &ctx->pm_grid)
+				          : occupancy_grid(ctx, k_permute_stranded<false>, ctx->ps_threads, ctx->ps_smem, &ctx->pm_grid);
+				if (rc) return rc;
 			}
 			// head: first 1024 permutations of every task; tasks still undecided go to the chunked tail
 			PermTail tail{};
@@ -698,7 +719,8 @@ int run_stage1(crispgpu_ctx* ctx)
 				launches++;
 				exact_done = static_cast<const int32_t*>(ctx->d_exact_done.p);
 			}
-			k_permute_stranded<<<ctx->pm_grid, ctx->pm_threads, ctx->pm_smem, ctx->stream>>>(prm, ctx->pm_l10cap, tail, exact_done);
+			if (many) k_permute_stranded<true><<<ctx->pm_grid, ctx->ps_threads, ctx->ps_smem, ctx->stream>>>(prm, ctx->ps_l10cap, ctx->ps_area, tail, exact_done);
+			else k_permute_stranded<false><<<ctx->pm_grid, ctx->ps_threads, ctx->ps_smem, ctx->stream>>>(prm, ctx->ps_l10cap, ctx->ps_area, tail, exact_done);
 			CK(launch_check());
 			if (g.max_iter > kPermHead) {
 				// the number of tail tasks sizes the chunk records (the one extra host wait of the permutation mode)
@@ -713,7 +735,10 @@ int run_stage1(crispgpu_ctx* ctx)
 					int T = 0, grid = 0;
 					size_t smem = 0;
 					perm_tail_geometry(ctx, narrow ? 2 : 4, false, &T, &smem);
-					rc = narrow ? occupancy_grid(ctx, k_permute_stranded_tail<uint16_t>, T, smem, &grid) : occupancy_grid(ctx, k_permute_stranded_tail<uint32_t>, T, smem, &grid);
+					int area = (int)((size_t)ctx->P * T * (narrow ? 2 : 4));
+					if (many) { T = 256; area = ctx->ps_area; smem = ctx->ps_smem; }
+					rc = many ? occupancy_grid(ctx, k_permute_stranded_tail<uint32_t, true>, T, smem, &grid)
+					   : narrow ? occupancy_grid(ctx, k_permute_stranded_tail<uint16_t, false>, T, smem, &grid) : occupancy_grid(ctx, k_permute_stranded_tail<uint32_t, false>, T, smem, &grid);
 					if (rc) return rc;
 					const int rem = g.max_iter - kPermHead;
 					int chunk = ((rem + 255) / 256 + T - 1) / T * T;
@@ -722,8 +747,9 @@ int run_stage1(crispgpu_ctx* ctx)
 					tail.nchunks = (rem + chunk - 1) / chunk;
 					rc = ensure_dev(ctx, ctx->d_tail_rec, (size_t)n_tail * tail.nchunks * kPermRec * 4); if (rc) return rc;
 					tail.rec = static_cast<int32_t*>(ctx->d_tail_rec.p);
-					if (narrow) k_permute_stranded_tail<uint16_t><<<grid, T, smem, ctx->stream>>>(prm, ctx->pm_l10cap, tail);
-					else k_permute_stranded_tail<uint32_t><<<grid, T, smem, ctx->stream>>>(prm, ctx->pm_l10cap, tail);
+					if (many) k_permute_stranded_tail<uint32_t, true><<<grid, T, smem, ctx->stream>>>(prm, ctx->ps_l10cap, area, tail);
+					else if (narrow) k_permute_stranded_tail<uint16_t, false><<<grid, T, smem, ctx->stream>>>(prm, ctx->pm_l10cap, area, tail);
+					else k_permute_stranded_tail<uint32_t, false><<<grid, T, smem, ctx->stream>>>(prm, ctx->pm_l10cap, area, tail);
 					CK(launch_check());
 					k_permute_stranded_resolve<<<(n_tail + 127) / 128, 128, 0, ctx->stream>>>(prm, tail);
 					launches += 2;

@@ -34,8 +34,13 @@ struct PermShared {
 	int tot[3], ones[3];
 	int maxN;
 	int maxball;   // most balls one pool can receive on one strand / stratum in a permutation of this table
+	int occ_bytes; // stranded test: width of this table's occupancy words (1, 2 or 4 bytes: two 4-, 8- or 16-bit ball counters)
+	int hash_log;  // stranded test: > 0 = the permutation's occupancy is a per-thread hash table of 2^hash_log entries
+	int active;    // threads of the block that run permutations (the occupancy area holds that many tables / columns)
 	double clra;
 };
+
+constexpr int kPermHashPools = 128;   // from this many pools on the stranded kernels may keep a permutation's occupancy in a hash table
 
 // inclusive prefix sum of a 0/1 flag over the block in thread order; returns this thread's inclusive count and the block total
 __device__ __forceinline__ int block_prefix(int flag, int* warp_tot, int& total)
@@ -79,12 +84,16 @@ struct StrandedView {
 	int32_t* Ntot;
 	int32_t* alt;
 	double* L10;
-	unsigned char* occ;  // [P][T] of OccT: low half forward balls, high half reverse balls (32-bit words, or 16-bit when no pool
-	                     // holds more than 255 reads per strand: twice the permutations in flight for the same shared memory)
+	unsigned char* occ;  // column mode: [P][active] of OccT, low half forward balls, high half reverse balls (32-bit words, or 16-bit
+	                     // when no pool holds more than 255 reads per strand: twice the permutations in flight for the same shared
+	                     // memory).  Hash mode (many pools, few balls): [2^hash_log][active] 32-bit entries
+	                     // (pool + 1) << 20 | reverse balls << 10 | forward balls, open addressing — shared memory and the per-
+	                     // permutation zero fill then scale with the balls of the table, not with its pools.
 	int l10cap;
+	int area;            // bytes of the occupancy area
 };
 
-__device__ __forceinline__ StrandedView stranded_view(unsigned char* smem_raw, int P, int l10cap)
+__device__ __forceinline__ StrandedView stranded_view(unsigned char* smem_raw, int P, int l10cap, int area)
 {
 	StrandedView v;
 	v.sh = reinterpret_cast<PermShared*>(smem_raw);
@@ -97,6 +106,7 @@ __device__ __forceinline__ StrandedView stranded_view(unsigned char* smem_raw, i
 	v.L10 = reinterpret_cast<double*>(smem_raw + off); off += sizeof(double) * l10cap;
 	v.occ = smem_raw + off;
 	v.l10cap = l10cap;
+	v.area = area;
 	return v;
 }
 
@@ -153,6 +163,20 @@ __device__ inline void stranded_setup(const EngineParams& prm, const StrandedVie
 		// most balls one pool can receive on one strand: must fit the 16-bit occupancy fields of the head kernel
 		v.sh->maxball = (int)min(deepest, (uint32_t)max(of, orr));
 		atomicMax(prm.q.counters + 13, v.sh->maxball);
+		// how a permutation keeps its occupancy: a column of P words per thread, or — when the table has many pools and few
+		// balls — a hash table of at least twice as many entries as balls; whichever lets more threads run
+		// the narrowest words whose two fields hold the most balls a pool can receive on one strand: the narrower the column,
+		// the more permutations fit the occupancy area
+		const int occ_bytes = v.sh->maxball <= 15 ? 1 : (v.sh->maxball <= 255 ? 2 : 4);
+		v.sh->occ_bytes = occ_bytes;
+		int logc = 4;
+		while ((1 << logc) < 2 * (of + orr) && logc < 20) logc++;
+		const int act_hash = v.area / (4 << logc), act_col = v.area / (P * occ_bytes);
+		const bool hash = P >= kPermHashPools && v.sh->maxball <= 1023 && act_hash > act_col;
+		int act = min(T, hash ? act_hash : act_col);
+		if (act >= 32) act &= ~31;
+		v.sh->hash_log = hash ? logc : 0;
+		v.sh->active = max(act, 1);
 	}
 	__syncthreads();
 	const int maxN = v.sh->maxN;
@@ -162,27 +186,64 @@ __device__ inline void stranded_setup(const EngineParams& prm, const StrandedVie
 
 // One permutation (thread-local): place the forward and reverse balls, accumulate the statistic incrementally
 // (contables.c:312-323) and compare with the observed one.
-template <typename OccT>
+// MANY: the many-pool geometry (hash tables, a per-table number of active threads); otherwise every thread of the block runs
+// a permutation on a column of OccT words
+template <typename OccT, bool MANY>
 __device__ __forceinline__ int stranded_hit(const EngineParams& prm, const StrandedView& v, int s, int slot, uint32_t k)
 {
 	constexpr int HB = sizeof(OccT) * 4;            // bits per strand counter
 	constexpr uint32_t HM = (1u << HB) - 1u;
-	const int P = prm.c.P, T = blockDim.x;
-	OccT* myocc = reinterpret_cast<OccT*>(v.occ) + threadIdx.x;
+	const int P = prm.c.P, T = MANY ? v.sh->active : (int)blockDim.x;
 	const bool l10_smem = v.sh->maxN + 2 <= v.l10cap;
 	const double* L10 = v.L10;
 	const int32_t* Ntot = v.Ntot;
-	for (int i = 0; i < P; i++) myocc[(size_t)i * T] = 0;
 	double stat = 0.0;
 	Philox rng;
+	auto step = [&](int i, int cb) {   // the statistic's increment when pool i, holding cb balls, receives one more (contables.c:316,322)
+		const int N = Ntot[i];
+		stat += l10_smem ? L10[N - cb] - L10[cb + 1] : log10((double)(N - cb)) - log10((double)(cb + 1));
+	};
+	if (MANY && v.sh->hash_log) {
+		const int logc = v.sh->hash_log;
+		const uint32_t mask = (1u << logc) - 1u;
+		uint32_t* tab = reinterpret_cast<uint32_t*>(v.occ) + threadIdx.x;
+		for (uint32_t e = 0; e <= mask; e++) tab[(size_t)e * T] = 0;
+		// slot of pool i: its entry, or the empty slot where it would go
+		auto find = [&](int i, uint32_t& at) -> uint32_t {
+			uint32_t h = ((uint32_t)(i + 1) * 0x9E3779B1u) >> (32 - logc);
+			for (;;) {
+				const uint32_t e = tab[(size_t)h * T];
+				if (e == 0 || (e >> 20) == (uint32_t)(i + 1)) { at = h; return e; }
+				h = (h + 1) & mask;
+			}
+		};
+		uint32_t at;
+		rng.init(prm.c.rng_seed, prm.b.tid[s], prm.b.pos[s], slot, k, 0);
+		place_balls(rng, v.cumf, P, (uint32_t)v.sh->tot[0], v.sh->ones[0],
+			[&](int i) { return find(i, at) & 1023u; },
+			[&](int i) {
+				const uint32_t e = find(i, at);
+				step(i, (int)(e & 1023u) + (int)((e >> 10) & 1023u));
+				tab[(size_t)at * T] = (e ? e : ((uint32_t)(i + 1) << 20)) + 1u;
+			});
+		rng.init(prm.c.rng_seed, prm.b.tid[s], prm.b.pos[s], slot, k, 1);
+		place_balls(rng, v.cumr, P, (uint32_t)v.sh->tot[1], v.sh->ones[1],
+			[&](int i) { return (find(i, at) >> 10) & 1023u; },
+			[&](int i) {
+				const uint32_t e = find(i, at);
+				step(i, (int)(e & 1023u) + (int)((e >> 10) & 1023u));
+				tab[(size_t)at * T] = (e ? e : ((uint32_t)(i + 1) << 20)) + (1u << 10);
+			});
+		return stat <= v.sh->clra + kCtEps ? 1 : 0;
+	}
+	OccT* myocc = reinterpret_cast<OccT*>(v.occ) + threadIdx.x;
+	for (int i = 0; i < P; i++) myocc[(size_t)i * T] = 0;
 	rng.init(prm.c.rng_seed, prm.b.tid[s], prm.b.pos[s], slot, k, 0);
 	place_balls(rng, v.cumf, P, (uint32_t)v.sh->tot[0], v.sh->ones[0],
 		[&](int i) { return (uint32_t)myocc[(size_t)i * T] & HM; },
 		[&](int i) {
 			const uint32_t w = myocc[(size_t)i * T];
-			const int cb = (int)(w & HM) + (int)(w >> HB);
-			const int N = Ntot[i];
-			stat += l10_smem ? L10[N - cb] - L10[cb + 1] : log10((double)(N - cb)) - log10((double)(cb + 1));
+			step(i, (int)(w & HM) + (int)(w >> HB));
 			myocc[(size_t)i * T] = (OccT)(w + 1u);
 		});
 	rng.init(prm.c.rng_seed, prm.b.tid[s], prm.b.pos[s], slot, k, 1);
@@ -190,9 +251,7 @@ __device__ __forceinline__ int stranded_hit(const EngineParams& prm, const Stran
 		[&](int i) { return (uint32_t)myocc[(size_t)i * T] >> HB; },
 		[&](int i) {
 			const uint32_t w = myocc[(size_t)i * T];
-			const int cb = (int)(w & HM) + (int)(w >> HB);
-			const int N = Ntot[i];
-			stat += l10_smem ? L10[N - cb] - L10[cb + 1] : log10((double)(N - cb)) - log10((double)(cb + 1));
+			step(i, (int)(w & HM) + (int)(w >> HB));
 			myocc[(size_t)i * T] = (OccT)(w + (1u << HB));
 		});
 	return stat <= v.sh->clra + kCtEps ? 1 : 0;
@@ -222,12 +281,13 @@ struct PermTail {
 // Head: one CTA per task, the first kPermHead permutations with the reference's sequential stop rule
 // (contables.c:327-328) evaluated on prefix sums in permutation order.  Tasks that neither stopped nor exhausted
 // their permutations go to the tail queue.
-__global__ void __launch_bounds__(256, 4) k_permute_stranded(EngineParams prm, int l10cap, PermTail tail, const int32_t* __restrict__ exact_done)
+template <bool MANY>
+__global__ void __launch_bounds__(256, MANY ? 3 : 4) k_permute_stranded(EngineParams prm, int l10cap, int occ_area, PermTail tail, const int32_t* __restrict__ exact_done)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const DevCfg& c = prm.c;
 	const int T = blockDim.x, tid = threadIdx.x;
-	const StrandedView v = stranded_view(smem_raw, c.P, l10cap);
+	const StrandedView v = stranded_view(smem_raw, c.P, l10cap, occ_area);
 	PermShared* sh = v.sh;
 	for (;;) {
 		__syncthreads();
@@ -245,12 +305,19 @@ __global__ void __launch_bounds__(256, 4) k_permute_stranded(EngineParams prm, i
 		const int maxiter = c.max_iter;
 		const int head = maxiter < kPermHead ? maxiter : kPermHead;
 		int stop_k = 0, stop_hits = 0, hits_before = 0;
-		for (int base = 0; base < head; base += T) {
+		const int act = MANY ? sh->active : T;   // threads that run permutations
+		for (int base = 0; base < head; base += act) {
 			const int k = base + tid + 1;
-			const int hit = k <= head ? stranded_hit<uint32_t>(prm, v, s, slot, (uint32_t)k) : 0;
+			const bool mine = tid < act && k <= head;
+			int hit = 0;
+			if (mine) {
+				if (!MANY) hit = stranded_hit<uint32_t, false>(prm, v, s, slot, (uint32_t)k);
+				else hit = sh->occ_bytes == 1 ? stranded_hit<uint8_t, true>(prm, v, s, slot, (uint32_t)k)
+				         : sh->occ_bytes == 2 ? stranded_hit<uint16_t, true>(prm, v, s, slot, (uint32_t)k) : stranded_hit<uint32_t, true>(prm, v, s, slot, (uint32_t)k);
+			}
 			int total;
 			const int H = hits_before + block_prefix(hit, sh->warp_hits, total);
-			const bool stop = k <= head && (H >= 10 || (k <= 1000 && H >= 5));
+			const bool stop = mine && (H >= 10 || (k <= 1000 && H >= 5));
 			const unsigned sb = __ballot_sync(0xffffffffu, stop);
 			if ((tid & 31) == 0) sh->warp_first[tid >> 5] = sb ? (__ffs(sb) - 1) : -1;
 			__syncthreads();
@@ -282,13 +349,13 @@ __global__ void __launch_bounds__(256, 4) k_permute_stranded(EngineParams prm, i
 // Tail: work items = (chunk, task), chunk-major so that every earlier chunk of a task has started before a later one.
 // A chunk records its hit count and the indices of its first ten hits; it is skipped when ten hits are already known
 // (they all lie in earlier chunks, so the reference's loop would have broken before this chunk).
-template <typename OccT>
-__global__ void __launch_bounds__(256, 4) k_permute_stranded_tail(EngineParams prm, int l10cap, PermTail tail)
+template <typename OccT, bool MANY>   // MANY: the width of the occupancy words is chosen per table at run time
+__global__ void __launch_bounds__(256, MANY ? 3 : 4) k_permute_stranded_tail(EngineParams prm, int l10cap, int occ_area, PermTail tail)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const DevCfg& c = prm.c;
-	const int T = blockDim.x, tid = threadIdx.x;
-	const StrandedView v = stranded_view(smem_raw, c.P, l10cap);
+	const int tid = threadIdx.x;
+	const StrandedView v = stranded_view(smem_raw, c.P, l10cap, occ_area);
 	PermShared* sh = v.sh;
 	const int ntask = tail.counters[0];
 	const long long nitems = (long long)ntask * tail.nchunks;
@@ -318,9 +385,15 @@ __global__ void __launch_bounds__(256, 4) k_permute_stranded_tail(EngineParams p
 		const int o = tail.task[h], s = o / kSlots, slot = o - s * kSlots;
 		stranded_setup(prm, v, o);
 		int found = 0;
-		for (int base = kbeg; base < kend; base += T) {
+		const int act = MANY ? sh->active : (int)blockDim.x;
+		for (int base = kbeg; base < kend; base += act) {
 			const int k = base + tid + 1;
-			const int hit = k <= kend ? stranded_hit<OccT>(prm, v, s, slot, (uint32_t)k) : 0;
+			int hit = 0;
+			if (tid < act && k <= kend) {
+				if (!MANY) hit = stranded_hit<OccT, false>(prm, v, s, slot, (uint32_t)k);
+				else hit = sh->occ_bytes == 1 ? stranded_hit<uint8_t, true>(prm, v, s, slot, (uint32_t)k)
+				         : sh->occ_bytes == 2 ? stranded_hit<uint16_t, true>(prm, v, s, slot, (uint32_t)k) : stranded_hit<uint32_t, true>(prm, v, s, slot, (uint32_t)k);
+			}
 			int total;
 			const int idx = found + block_prefix(hit, sh->warp_hits, total);  // 1-based rank of this hit within the chunk
 			if (hit && idx <= 10) firsts[idx - 1] = k;
