@@ -188,8 +188,10 @@ __device__ __forceinline__ void pile_count_quad(uint32_t q, uint32_t h, int p0, 
 // is counted), eight bases per step — the read's 4-bit codes XOR the reference stretch of the tile, which is staged in shared
 // memory as a stream of 4-bit codes; "differs" and "is N" are nibble masks, the count is a popc.  The lane leaves the record
 // and the filter outcome in the warp's slot of shared memory.
-// Phase B, one WARP per alignment that passed, each lane holding four consecutive bases as the bytes of a word (one 4-byte
-// quality load, one 2-byte base load per lane, the loads of the next alignment in flight).  A read that may count reference
+// Phase B: an alignment that passed is counted by its own lane as well, eight bases per step (the 4-bit codes again, the eight
+// quality bytes as two words, "differs", "quality >= MINQ" and "inside the tile" as eight-bit masks) — or, when the tile's
+// reference stretch holds a character outside BAM's alphabet or a read is longer than the staged stretch, by the whole warp,
+// each lane holding four consecutive bases as the bytes of a word.  A read that may count reference
 // bases adds +1 / -1 to a per-strand coverage difference array at its first / past-last position inside the tile; only its
 // EXCEPTIONS touch the counters: a base that differs from the reference (counted under its own allele when its quality
 // passes) or a reference base below MINQ takes one off the reference allele's counter.  After the walk a prefix sum of the
@@ -258,6 +260,54 @@ __device__ __forceinline__ void pile_tile_body(const PileReads& rd, const PileWi
 			int fl = (mq && mm <= maxmm ? 1 : 0) | (mq && mm <= maxmm - 1 ? 2 : 0);
 			rd.flags[mine] = (uint8_t)fl;   // tiles that share the read write the same value
 			if (a.pos + ml <= t0) fl = 0;   // nothing of it inside this tile
+			if (STAGED && fast) {
+				// ---- phase B, fast form: the lane counts its own alignment, eight bases per step ----
+				if (fl & 1) {
+					const bool refs = (fl & 2) != 0;   // reference bases of this read count
+					const int st = a.strand ? 4 : 0;
+					// indices of the match block that lie inside the tile
+					const int k_lo = max(t0 - a.pos, 0), k_hi = min(ml, t1 - a.pos);
+					if (refs) {
+						int* cs = cov[st >> 2];
+						atomicAdd(cs + (a.pos + k_lo - t0), 1);
+						atomicAdd(cs + (a.pos + k_hi - t0), -1);
+					}
+					const uint32_t* sw = reinterpret_cast<const uint32_t*>(rd.seq4 + (a.base_off >> 1)) + (clip >> 3);
+					const int sh = 4 * (clip & 7), lastw = ((clip + ml - 1) >> 3) - (clip >> 3);
+					const uint32_t* qw = reinterpret_cast<const uint32_t*>(rd.qual + a.base_off) + (clip >> 2);
+					const int qsh = 8 * (clip & 3), lastq = ((clip + ml - 1) >> 2) - (clip >> 2);
+					const int t_first = k_lo >> 3, t_end = (k_hi + 7) >> 3;   // steps that touch the tile
+					uint32_t cur = linear_nibbles(__ldg(sw + t_first));
+					uint32_t q0 = __ldg(qw + 2 * t_first);
+					for (int t = t_first; t < t_end; t++) {
+						const uint32_t nxt = (t + 1 <= lastw) ? linear_nibbles(__ldg(sw + t + 1)) : 0u;
+						const uint32_t s8 = __funnelshift_r(cur, nxt, sh);
+						cur = nxt;
+						const uint32_t q1 = (2 * t + 1 <= lastq) ? __ldg(qw + 2 * t + 1) : 0u, q2 = (2 * t + 2 <= lastq) ? __ldg(qw + 2 * t + 2) : 0u;
+						const uint32_t qa = __funnelshift_r(q0, q1, qsh), qb = __funnelshift_r(q1, q2, qsh);
+						q0 = q2;
+						const int jn = a.pos + 8 * t - s0;
+						const uint32_t r8 = __funnelshift_r(sref4[jn >> 3], sref4[(jn >> 3) + 1], 4 * (jn & 7));
+						uint32_t x = s8 ^ r8;
+						x |= x >> 1; x |= x >> 2;
+						x &= 0x11111111u;                                        // nibble k: base k differs from the reference
+						x = (x | (x >> 3)) & 0x03030303u; x = (x | (x >> 6)) & 0x000F000Fu; x = (x | (x >> 12)) & 0xFFu;   // one bit per base
+						const uint32_t ma = ((((qa | 0x80808080u) - minq4) | qa) >> 7) & 0x01010101u, mb = ((((qb | 0x80808080u) - minq4) | qb) >> 7) & 0x01010101u;
+						const uint32_t qok = ((ma * 0x01020408u) >> 24) | (((mb * 0x01020408u) >> 24) << 4);   // bit k: quality of base k >= MINQ
+						const int lo = max(k_lo - 8 * t, 0), hi = min(k_hi - 8 * t, 8);
+						const uint32_t valid = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+						uint32_t exc = valid & (refs ? (x | (qok ^ 0xFFu)) : (x & qok));
+						while (exc) {
+							const int b = __ffs(exc) - 1;
+							exc &= exc - 1;
+							const int x0 = a.pos + 8 * t + b - t0;
+							if (refs) atomicSub(&hist[pile_slot(nt16_bti_ffs((r8 >> (4 * b)) & 15) + st, x0)], 1u);
+							if ((x >> b) & (qok >> b) & 1u) atomicAdd(&hist[pile_slot(nt16_bti_ffs((s8 >> (4 * b)) & 15) + st, x0)], 1u);
+						}
+					}
+				}
+				fl = 0;   // done: nothing left for the warp-per-alignment form below
+			}
 			packed = make_uint4((uint32_t)a.pos, a.base_off, (uint32_t)a.clip | ((uint32_t)a.mlen << 16), (uint32_t)fl | (a.strand ? 4u : 0u));
 		}
 		__syncwarp();
