@@ -233,20 +233,26 @@ __device__ __forceinline__ void pile_tile_body(const PileReads& rd, const PileWi
 			if (STAGED && fast) {
 				const uint32_t* sw = reinterpret_cast<const uint32_t*>(rd.seq4 + (a.base_off >> 1)) + (clip >> 3);
 				const int sh = 4 * (clip & 7), lastw = ((clip + ml - 1) >> 3) - (clip >> 3);
-				uint32_t cur = linear_nibbles(__ldg(sw));
-				int jn = a.pos - s0;
-				for (int t = 0; 8 * t < ml; t++, jn += 8) {
-					const uint32_t nxt = (sh && t + 1 <= lastw) ? linear_nibbles(__ldg(sw + t + 1)) : 0u;
-					const uint32_t s8 = __funnelshift_r(cur, nxt, sh);
-					cur = sh ? nxt : ((8 * (t + 1) < ml) ? linear_nibbles(__ldg(sw + t + 1)) : 0u);
-					const uint32_t r8 = __funnelshift_r(sref4[jn >> 3], sref4[(jn >> 3) + 1], 4 * (jn & 7));
-					uint32_t x = s8 ^ r8;
-					x |= x >> 1; x |= x >> 2;
-					const uint32_t isn = s8 & (s8 >> 1) & (s8 >> 2) & (s8 >> 3);
-					uint32_t m = x & ~isn & 0x11111111u;
-					const int left = ml - 8 * t;
-					if (left < 8) m &= (1u << (4 * left)) - 1u;
-					mm += __popc(m);
+				// four steps per trip: their five sequence words are loaded together (five loads in flight per lane)
+				for (int tb = 0; 8 * tb < ml; tb += 4) {
+					uint32_t wv[5];
+#pragma unroll
+					for (int j = 0; j < 5; j++) wv[j] = (tb + j <= lastw) ? __ldg(sw + tb + j) : 0u;
+#pragma unroll
+					for (int j = 0; j < 4; j++) {
+						const int t = tb + j;
+						if (8 * t >= ml) break;
+						const uint32_t s8 = __funnelshift_r(linear_nibbles(wv[j]), linear_nibbles(wv[j + 1]), sh);
+						const int jn = a.pos + 8 * t - s0;
+						const uint32_t r8 = __funnelshift_r(sref4[jn >> 3], sref4[(jn >> 3) + 1], 4 * (jn & 7));
+						uint32_t x = s8 ^ r8;
+						x |= x >> 1; x |= x >> 2;
+						const uint32_t isn = s8 & (s8 >> 1) & (s8 >> 2) & (s8 >> 3);
+						uint32_t m = x & ~isn & 0x11111111u;
+						const int left = ml - 8 * t;
+						if (left < 8) m &= (1u << (4 * left)) - 1u;
+						mm += __popc(m);
+					}
 				}
 			} else {
 				for (int k = 0; k < ml; k++) {
@@ -277,32 +283,37 @@ __device__ __forceinline__ void pile_tile_body(const PileReads& rd, const PileWi
 					const uint32_t* qw = reinterpret_cast<const uint32_t*>(rd.qual + a.base_off) + (clip >> 2);
 					const int qsh = 8 * (clip & 3), lastq = ((clip + ml - 1) >> 2) - (clip >> 2);
 					const int t_first = k_lo >> 3, t_end = (k_hi + 7) >> 3;   // steps that touch the tile
-					uint32_t cur = linear_nibbles(__ldg(sw + t_first));
-					uint32_t q0 = __ldg(qw + 2 * t_first);
-					for (int t = t_first; t < t_end; t++) {
-						const uint32_t nxt = (t + 1 <= lastw) ? linear_nibbles(__ldg(sw + t + 1)) : 0u;
-						const uint32_t s8 = __funnelshift_r(cur, nxt, sh);
-						cur = nxt;
-						const uint32_t q1 = (2 * t + 1 <= lastq) ? __ldg(qw + 2 * t + 1) : 0u, q2 = (2 * t + 2 <= lastq) ? __ldg(qw + 2 * t + 2) : 0u;
-						const uint32_t qa = __funnelshift_r(q0, q1, qsh), qb = __funnelshift_r(q1, q2, qsh);
-						q0 = q2;
-						const int jn = a.pos + 8 * t - s0;
-						const uint32_t r8 = __funnelshift_r(sref4[jn >> 3], sref4[(jn >> 3) + 1], 4 * (jn & 7));
-						uint32_t x = s8 ^ r8;
-						x |= x >> 1; x |= x >> 2;
-						x &= 0x11111111u;                                        // nibble k: base k differs from the reference
-						x = (x | (x >> 3)) & 0x03030303u; x = (x | (x >> 6)) & 0x000F000Fu; x = (x | (x >> 12)) & 0xFFu;   // one bit per base
-						const uint32_t ma = ((((qa | 0x80808080u) - minq4) | qa) >> 7) & 0x01010101u, mb = ((((qb | 0x80808080u) - minq4) | qb) >> 7) & 0x01010101u;
-						const uint32_t qok = ((ma * 0x01020408u) >> 24) | (((mb * 0x01020408u) >> 24) << 4);   // bit k: quality of base k >= MINQ
-						const int lo = max(k_lo - 8 * t, 0), hi = min(k_hi - 8 * t, 8);
-						const uint32_t valid = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
-						uint32_t exc = valid & (refs ? (x | (qok ^ 0xFFu)) : (x & qok));
-						while (exc) {
-							const int b = __ffs(exc) - 1;
-							exc &= exc - 1;
-							const int x0 = a.pos + 8 * t + b - t0;
-							if (refs) atomicSub(&hist[pile_slot(nt16_bti_ffs((r8 >> (4 * b)) & 15) + st, x0)], 1u);
-							if ((x >> b) & (qok >> b) & 1u) atomicAdd(&hist[pile_slot(nt16_bti_ffs((s8 >> (4 * b)) & 15) + st, x0)], 1u);
+					for (int tb = t_first; tb < t_end; tb += 4) {
+						// four steps per trip: five sequence words and nine quality words loaded together
+						uint32_t wv[5], qv[9];
+#pragma unroll
+						for (int j = 0; j < 5; j++) wv[j] = (tb + j <= lastw) ? __ldg(sw + tb + j) : 0u;
+#pragma unroll
+						for (int j = 0; j < 9; j++) qv[j] = (2 * tb + j <= lastq) ? __ldg(qw + 2 * tb + j) : 0u;
+#pragma unroll
+						for (int j = 0; j < 4; j++) {
+							const int t = tb + j;
+							if (t >= t_end) break;
+							const uint32_t s8 = __funnelshift_r(linear_nibbles(wv[j]), linear_nibbles(wv[j + 1]), sh);
+							const uint32_t qa = __funnelshift_r(qv[2 * j], qv[2 * j + 1], qsh), qb = __funnelshift_r(qv[2 * j + 1], qv[2 * j + 2], qsh);
+							const int jn = a.pos + 8 * t - s0;
+							const uint32_t r8 = __funnelshift_r(sref4[jn >> 3], sref4[(jn >> 3) + 1], 4 * (jn & 7));
+							uint32_t x = s8 ^ r8;
+							x |= x >> 1; x |= x >> 2;
+							x &= 0x11111111u;                                        // nibble k: base k differs from the reference
+							x = (x | (x >> 3)) & 0x03030303u; x = (x | (x >> 6)) & 0x000F000Fu; x = (x | (x >> 12)) & 0xFFu;   // one bit per base
+							const uint32_t ma = ((((qa | 0x80808080u) - minq4) | qa) >> 7) & 0x01010101u, mb = ((((qb | 0x80808080u) - minq4) | qb) >> 7) & 0x01010101u;
+							const uint32_t qok = ((ma * 0x01020408u) >> 24) | (((mb * 0x01020408u) >> 24) << 4);   // bit k: quality of base k >= MINQ
+							const int lo = max(k_lo - 8 * t, 0), hi8 = min(k_hi - 8 * t, 8);
+							const uint32_t valid = ((1u << hi8) - 1u) & ~((1u << lo) - 1u);
+							uint32_t exc = valid & (refs ? (x | (qok ^ 0xFFu)) : (x & qok));
+							while (exc) {
+								const int b = __ffs(exc) - 1;
+								exc &= exc - 1;
+								const int x0 = a.pos + 8 * t + b - t0;
+								if (refs) atomicSub(&hist[pile_slot(nt16_bti_ffs((r8 >> (4 * b)) & 15) + st, x0)], 1u);
+								if ((x >> b) & (qok >> b) & 1u) atomicAdd(&hist[pile_slot(nt16_bti_ffs((s8 >> (4 * b)) & 15) + st, x0)], 1u);
+							}
 						}
 					}
 				}
