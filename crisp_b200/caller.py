@@ -54,6 +54,9 @@ def vcf_header(bams, fasta: str, poolsize: int, options: dict) -> bytes:
     return ("\n".join(lines) + "\n").encode()
 
 
+_ARENA = {}   # the last call's pinned alignment arrays, taken over by the next call (pinning costs more than decoding)
+
+
 def call_bams(bams, fasta: str, poolsize: int, out_vcf: str | None = None, options: dict | None = None, window: int = 1 << 20, threads: int | None = None,
               device: int = 0, min_mapq: int = 20, tid: int = 0) -> dict:
     """Call the first reference sequence of `fasta` from one BAM per pool.  Returns timings, counts and (when out_vcf is None)
@@ -61,7 +64,7 @@ def call_bams(bams, fasta: str, poolsize: int, out_vcf: str | None = None, optio
     options = dict(options or {})
     threads = threads or os.cpu_count() or 1
     t0 = time.perf_counter()
-    aln = decode_bams(bams, tid=tid, threads=threads)
+    aln = decode_bams(bams, tid=tid, threads=threads, reuse=_ARENA.pop("aln", None))
     t1 = time.perf_counter()
     ref = read_fasta(fasta)
     L = ref.shape[0]
@@ -86,6 +89,7 @@ def call_bams(bams, fasta: str, poolsize: int, out_vcf: str | None = None, optio
             t_fmt += tc - tb
     finally:
         eng.close()
+        _ARENA["aln"] = aln
     out = dict(decode_s=t1 - t0, device_s=t_dev, format_s=t_fmt, candidate_sites=n_sites, records=n_records, alignments=aln.n_reads, positions=L,
                decode_stats=aln.stats)
     if out_vcf:

@@ -43,14 +43,14 @@ class CPileupSites(C.Structure):
 
 class CBamOptions(C.Structure):
     _fields_ = [("tid", C.c_int32), ("start", C.c_int32), ("end", C.c_int32), ("filter_mask", C.c_uint32), ("threads", C.c_int32),
-                ("paired", C.c_int32), ("reserved", C.c_int32), ("alloc", C.c_void_p), ("release", C.c_void_p)]
+                ("paired", C.c_int32), ("reuse", C.c_int32), ("alloc", C.c_void_p), ("release", C.c_void_p)]
 
 
 class CBamReads(C.Structure):
     _fields_ = [("aln", CAlignments), ("n_records", C.c_int64), ("n_flag_filtered", C.c_int64), ("n_outside", C.c_int64),
                 ("n_complex", C.c_int64), ("compressed_bytes", C.c_int64), ("inflated_bytes", C.c_int64), ("read_s", C.c_double),
                 ("inflate_s", C.c_double), ("parse_s", C.c_double), ("n_refs", C.c_int32), ("first_ref_len", C.c_int32),
-                ("first_ref_name", C.c_char * 64)]
+                ("first_ref_name", C.c_char * 64), ("cap_reads", C.c_uint64), ("cap_bases", C.c_uint64), ("cap_pools", C.c_int32), ("cap_paired", C.c_int32)]
 
 
 _bamlib = None
@@ -112,10 +112,12 @@ class _DecodedOwner:
 
 
 def decode_bams(paths, tid: int = 0, start: int = 0, end: int = 2**31 - 1, threads: int | None = None, paired: bool = False,
-                pinned: bool = True, filter_mask: int = BAM_FILTER_MASK, allow_complex: bool = False) -> Alignments:
+                pinned: bool = True, filter_mask: int = BAM_FILTER_MASK, allow_complex: bool = False, reuse: Alignments | None = None) -> Alignments:
     """Decode one coordinate-sorted BAM per pool into an `Alignments` set (alignments overlapping [start, end) of reference
     `tid`).  Raises when the files hold alignments outside the device pileup's scope (CIGARs with gaps) unless
-    `allow_complex` (they are then dropped and counted in stats['n_complex'])."""
+    `allow_complex` (they are then dropped and counted in stats['n_complex']).  `reuse`: an earlier result of this function
+    (same `pinned`) whose arrays are taken over when large enough — pinning memory costs more than decoding into it; that
+    earlier object must not be used afterwards."""
     lib = load_bam_library()
     alloc = release = None
     if pinned:
@@ -123,9 +125,14 @@ def decode_bams(paths, tid: int = 0, start: int = 0, end: int = 2**31 - 1, threa
         g = load_library()
         alloc = C.cast(g.crispgpu_host_alloc, C.c_void_p).value
         release = C.cast(g.crispgpu_host_free, C.c_void_p).value
-    opt = CBamOptions(tid, start, end, filter_mask, threads or (os.cpu_count() or 1), 1 if paired else 0, 0, alloc, release)
-    arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
     out = CBamReads()
+    taking = reuse is not None and isinstance(reuse._owner, _DecodedOwner) and reuse._owner.release == release
+    if taking:
+        C.memmove(C.byref(out), C.byref(reuse._owner.reads), C.sizeof(CBamReads))
+        reuse._owner.reads = CBamReads()   # ownership moves to this call
+        reuse.rec = reuse.seq4 = reuse.qual = reuse.pool_off = None
+    opt = CBamOptions(tid, start, end, filter_mask, threads or (os.cpu_count() or 1), 1 if paired else 0, 1 if taking else 0, alloc, release)
+    arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
     rc = lib.crisp_bam_decode(arr, len(paths), C.byref(opt), C.byref(out))
     if rc != 0:
         raise RuntimeError(f"crisp_bam_decode failed: status {rc}")

@@ -328,6 +328,9 @@ void crisp_bam_release(crisp_bam_reads* r, void (*release)(void*))
 int crisp_bam_decode(const char* const* paths, int32_t n_pools, const crisp_bam_options* opt, crisp_bam_reads* out)
 {
 	if (!paths || n_pools <= 0 || !opt || !out) return -1;
+	crisp_bam_reads old;
+	memset(&old, 0, sizeof old);
+	if (opt->reuse) old = *out;   /* arrays of an earlier call */
 	memset(out, 0, sizeof *out);
 	void* (*alloc)(size_t) = opt->alloc ? opt->alloc : malloc;
 	void (*release)(void*) = opt->release ? opt->release : free;
@@ -374,13 +377,24 @@ int crisp_bam_decode(const char* const* paths, int32_t n_pools, const crisp_bam_
 	{
 		const uint64_t R = jb.pool_read0[n_pools], B = jb.pool_base0[n_pools];
 		if (R >= (1ull << 32) || B >= (1ull << 32)) { rc = -1; goto done; }   /* the window is too large for 32-bit offsets: decode it in slices */
-		uint32_t* pool_off = (uint32_t*)alloc(sizeof(uint32_t) * ((size_t)n_pools + 1));
-		jb.rec = (crispgpu_alnrec*)alloc(sizeof(crispgpu_alnrec) * (R ? R : 1));
-		jb.seq4 = (uint8_t*)alloc(B / 2 + 16);
-		jb.qual = (uint8_t*)alloc(B + 16);
-		if (opt->paired) {
-			jb.mate_pos = (int32_t*)alloc(sizeof(int32_t) * (R ? R : 1));
-			jb.isize = (int32_t*)alloc(sizeof(int32_t) * (R ? R : 1));
+		uint32_t* pool_off;
+		if (old.aln.rec && old.cap_reads >= R && old.cap_bases >= B && old.cap_pools >= n_pools && (!opt->paired || old.cap_paired)) {
+			pool_off = (uint32_t*)old.aln.pool_off; jb.rec = (crispgpu_alnrec*)old.aln.rec; jb.seq4 = (uint8_t*)old.aln.seq4; jb.qual = (uint8_t*)old.aln.qual;
+			if (opt->paired) { jb.mate_pos = (int32_t*)old.aln.mate_pos; jb.isize = (int32_t*)old.aln.isize; }
+			else { if (old.aln.mate_pos) release((void*)old.aln.mate_pos); if (old.aln.isize) release((void*)old.aln.isize); }
+			out->cap_reads = old.cap_reads; out->cap_bases = old.cap_bases; out->cap_pools = old.cap_pools; out->cap_paired = opt->paired ? old.cap_paired : 0;
+			memset(&old, 0, sizeof old);
+		} else {
+			const uint64_t cr = R + R / 8 + 1, cb = (B + B / 8 + 64) & ~(uint64_t)7;   /* some slack for the next window */
+			pool_off = (uint32_t*)alloc(sizeof(uint32_t) * ((size_t)n_pools + 1));
+			jb.rec = (crispgpu_alnrec*)alloc(sizeof(crispgpu_alnrec) * cr);
+			jb.seq4 = (uint8_t*)alloc(cb / 2 + 16);
+			jb.qual = (uint8_t*)alloc(cb + 16);
+			if (opt->paired) {
+				jb.mate_pos = (int32_t*)alloc(sizeof(int32_t) * cr);
+				jb.isize = (int32_t*)alloc(sizeof(int32_t) * cr);
+			}
+			out->cap_reads = cr; out->cap_bases = cb; out->cap_pools = n_pools; out->cap_paired = opt->paired;
 		}
 		out->aln.n_pools = n_pools;
 		out->aln.pool_off = pool_off;
@@ -407,6 +421,7 @@ done:
 	free(jb.item_pool);
 	free(jb.item_block);
 	pthread_mutex_destroy(&jb.mu);
+	crisp_bam_release(&old, release);   /* arrays of the earlier call that were not taken over */
 	if (rc) crisp_bam_release(out, release);
 	return rc;
 }

@@ -27,7 +27,8 @@ typedef struct crisp_bam_options {
 	uint32_t filter_mask;   /* BAM_FILTER_MASK: reads with (flag & mask) != 0 are dropped (0x704 = unmapped|secondary|qcfail|dup) */
 	int32_t threads;        /* host threads (<= 0: one) */
 	int32_t paired;         /* 1: also fill mate_pos / isize */
-	int32_t reserved;
+	int32_t reuse;          /* 1: `out` holds the arrays of an earlier call (same allocator): they are used again when large
+	                           enough — pinning memory costs more than decoding into it — and whatever viewed them is overwritten */
 	void* (*alloc)(size_t);     /* allocator of the output arrays (NULL: malloc) */
 	void (*release)(void*);     /* its counterpart (NULL: free) */
 } crisp_bam_options;
@@ -44,6 +45,8 @@ typedef struct crisp_bam_reads {
 	int32_t n_refs;
 	int32_t first_ref_len;
 	char first_ref_name[64];
+	uint64_t cap_reads, cap_bases;  /* capacity of the arrays (alignments, bases): what a later call with opt->reuse can take over */
+	int32_t cap_pools, cap_paired;
 } crisp_bam_reads;
 
 /* Decode n_pools coordinate-sorted BAM files (one per pool) into one alignment set.  Returns 0, or a negative number:
