@@ -1381,10 +1381,10 @@ namespace {
 
 struct SiteLayout {   // the candidate-site arrays of a window in one arena (device) mirrored by one pinned arena (host)
 	size_t tid, pos, refbase, maxvec_al, maxvec_ct, counts, indcounts, readdepths, mqcounts, filtered, read_off, alt_off, copy_bytes;
-	size_t cell_reads, alt_len, alt_cell_off, total;
+	size_t cell_reads, alt_len, alt_cell_off, stats, tstats, total;
 };
 
-SiteLayout site_layout(size_t n, size_t P)
+SiteLayout site_layout(size_t n, size_t P, bool with_stats)
 {
 	SiteLayout L{};
 	size_t o = 0;
@@ -1394,6 +1394,7 @@ SiteLayout site_layout(size_t n, size_t P)
 	L.filtered = take(n * 8); L.read_off = take((n * P + 1) * 4); L.alt_off = take((n * 5 + 1) * 4);
 	L.copy_bytes = o;
 	L.cell_reads = take(n * P * 4); L.alt_len = take(n * 5 * P * 4); L.alt_cell_off = take((n * 5 * P + 1) * 4);
+	L.stats = take(with_stats ? n * P * 128 : 0); L.tstats = take(with_stats ? n * 128 : 0);
 	L.total = o;
 	return L;
 }
@@ -1404,8 +1405,8 @@ int pile_upload(crispgpu_ctx* ctx, const crispgpu_alignments* aln, const crispgp
 		snprintf(ctx->err, sizeof ctx->err, "pileup: missing array, pool count different from the context's, or an inverted window");
 		return CRISPGPU_ERR_ARG;
 	}
-	if (ctx->cfg.em_flag == 0) {
-		snprintf(ctx->err, sizeof ctx->err, "pileup: the legacy caller (--EM 0) reads the per-pool error sums (variant->stats), which the device pileup does not accumulate");
+	if (ctx->cfg.use_qv == 1) {
+		snprintf(ctx->err, sizeof ctx->err, "pileup: --weighted counts (Qhighcounts of 1 - error probability per read) are not accumulated by the device pileup");
 		return CRISPGPU_ERR_UNSUPPORTED;
 	}
 	const size_t P = ctx->P, R = aln->pool_off[P];
@@ -1490,7 +1491,8 @@ int pile_run(crispgpu_ctx* ctx, bool fetch, crispgpu_pileup_sites* sites, crispg
 		return (hs[0] & kPileErrMate) ? CRISPGPU_ERR_UNSUPPORTED : CRISPGPU_ERR_ARG;
 	}
 	const size_t n = (size_t)hs[2];
-	const SiteLayout L = site_layout(n ? n : 1, P);
+	const bool with_stats = ctx->cfg.em_flag == 0;   // the legacy caller reads the per-pool error-probability sums (chernoff_bound)
+	const SiteLayout L = site_layout(n ? n : 1, P, with_stats);
 	if ((rc = ensure_dev(ctx, ctx->p_sites, L.total)) || (rc = ensure_host(ctx, ctx->ph_sites, L.copy_bytes))) return rc;
 	unsigned char* ds = static_cast<unsigned char*>(ctx->p_sites.p);
 	PileSites ps{};
@@ -1503,6 +1505,8 @@ int pile_run(crispgpu_ctx* ctx, bool fetch, crispgpu_pileup_sites* sites, crispg
 	ps.read_off = reinterpret_cast<uint32_t*>(ds + L.read_off); ps.alt_off = reinterpret_cast<uint32_t*>(ds + L.alt_off);
 	ps.cell_reads = reinterpret_cast<uint32_t*>(ds + L.cell_reads); ps.alt_len = reinterpret_cast<uint32_t*>(ds + L.alt_len);
 	ps.alt_cell_off = reinterpret_cast<uint32_t*>(ds + L.alt_cell_off);
+	ps.stats = with_stats ? reinterpret_cast<double*>(ds + L.stats) : nullptr;
+	ps.tstats = with_stats ? reinterpret_cast<double*>(ds + L.tstats) : nullptr;
 	size_t n_reads = 0, n_alt = 0;
 	if (n) {
 		const size_t cells = n * P;
@@ -1526,6 +1530,11 @@ int pile_run(crispgpu_ctx* ctx, bool fetch, crispgpu_pileup_sites* sites, crispg
 		CK(launch_check());
 		k_pile_alt_off<<<(int)((n * 5 + 256) / 256), 256, 0, ctx->stream>>>(ps, (int)P);
 		CK(launch_check());
+		if (with_stats) {
+			k_pile_tstats<<<(int)((n * 16 + 255) / 256), 256, 0, ctx->stream>>>(ps, (int)P);
+			CK(launch_check());
+			launches++;
+		}
 		launches += 6;
 	}
 	CK(cudaEventRecord(ctx->ev_pile[3], ctx->stream));
@@ -1535,6 +1544,7 @@ int pile_run(crispgpu_ctx* ctx, bool fetch, crispgpu_pileup_sites* sites, crispg
 	b.n_sites = (int)n; b.P = (int)P;
 	b.tid = ps.tid; b.pos = ps.pos; b.refbase = ps.refbase; b.maxvec_al = ps.maxvec_al; b.maxvec_ct = ps.maxvec_ct; b.counts = ps.counts;
 	b.indcounts = ps.indcounts; b.read_off = ps.read_off; b.reads = ps.reads; b.alt_off = ps.alt_off; b.alt_reads = ps.alt_reads;
+	b.stats = ps.stats; b.tstats = ps.tstats;
 	ctx->n_sites = (int)n; ctx->n_reads = n_reads; ctx->n_bins = 0;
 	ctx->binned = false; ctx->sparse_ic = false; ctx->device_sort = false; ctx->lazy_reads = nullptr; ctx->resident = false;
 	ctx->copied_bytes = ctx->pile_h2d;

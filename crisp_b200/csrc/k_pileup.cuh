@@ -534,6 +534,8 @@ struct PileSites {   // the candidate sites of the window as the engine's batch 
 	int32_t* readdepths;     // [n P]
 	int32_t* mqcounts;       // [n 4]
 	int32_t* filtered;       // [n 2]
+	double* stats;           // [n P 16] or null: sum of 10^(-q/10) over the counted reads per allele + 8 strand (variant->stats; --EM 0)
+	double* tstats;          // [n 16]
 };
 
 // One CTA per candidate: its cells of the window table become the dense per-pool rows of the batch (indel and
@@ -608,6 +610,7 @@ __global__ void k_pile_gather_reads(PileReads rd, PileWindow w, PileSites ps)
 		for (int k = 0; k < 5; k++) slot_al[k] = ps.maxvec_ct[c * 8 + k + 1] >= 3 ? ps.maxvec_al[c * 8 + k + 1] : -1;
 		uint32_t nread = 0, nalt[5] = {0, 0, 0, 0, 0};
 		int depth = 0, mq[4] = {0, 0, 0, 0}, filt[2] = {0, 0};
+		double ep_sum = 0.0;   // lane e < 16: error-probability sum of the reads counted under allele (e & 7), strand (e >> 3), in read order
 		const uint32_t rbase = PASS ? ps.read_off[cell] : 0;
 		for (uint32_t rb = lo; rb < hi; rb += 32) {
 			const uint32_t r = rb + lane;
@@ -640,6 +643,17 @@ __global__ void k_pile_gather_reads(PileReads rd, PileWindow w, PileSites ps)
 				const unsigned bm = __ballot_sync(0xffffffffu, b >= 0);
 				if (b >= 0) ps.reads[rbase + nread + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)(((q + 33) & 0xff) | ((b & 3) << 8) | ((a.strand ? 1 : 0) << 10));
 				nread += __popc(bm);
+				if (ps.stats) {
+					// ep = 0.1^(quality/10) added in read order (variant.c:318-319): lane l's read goes to the lane that owns its class
+					const double ep = b >= 0 ? pow(0.1, (double)q / 10) : 0.0;
+					const int cls = b >= 0 ? b + (a.strand ? 8 : 0) : -1;
+					for (unsigned left = bm; left;) {
+						const int l = __ffs(left) - 1;
+						left &= left - 1;
+						const double e = __shfl_sync(0xffffffffu, ep, l);
+						if (__shfl_sync(0xffffffffu, cls, l) == lane) ep_sum += e;
+					}
+				}
 			}
 #pragma unroll
 			for (int k = 0; k < 5; k++) {
@@ -666,6 +680,7 @@ __global__ void k_pile_gather_reads(PileReads rd, PileWindow w, PileSites ps)
 			}
 		} else {
 			if (lane == 0) ps.readdepths[cell] = depth;
+			if (ps.stats && lane < 16) ps.stats[cell * 16 + lane] = ep_sum;
 #pragma unroll
 			for (int k = 0; k < 4; k++) {
 				const int t = __reduce_add_sync(0xffffffffu, mq[k]);
@@ -677,6 +692,17 @@ __global__ void k_pile_gather_reads(PileReads rd, PileWindow w, PileSites ps)
 				if (lane == 0 && t) atomicAdd(&ps.filtered[c * 2 + k], t);
 			}
 		}
+	}
+}
+
+// variant->tstats: the error-probability sums over all pools, added in pool order
+__global__ void k_pile_tstats(PileSites ps, int P)
+{
+	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < ps.n * 16; k += gridDim.x * blockDim.x) {
+		const int c = k >> 4, e = k & 15;
+		double t = 0.0;
+		for (int j = 0; j < P; j++) t += ps.stats[((size_t)c * P + j) * 16 + e];
+		ps.tstats[k] = t;
 	}
 }
 

@@ -324,7 +324,8 @@ NOMAPQ = HARD   # (kept name: every filter the front end applies is on)
     (20, [], {}, dict(pools=6, length=12000, depth=60, seed=41, **HARD)),
     (2, [], {}, dict(pools=12, length=8000, depth=12, seed=42, **HARD)),
     (16, ["--chisquare", "0", "--perms", "3000"], dict(chisq_permutation=1, max_iter=3000), dict(pools=8, length=9000, depth=50, seed=43, **HARD)),
-], ids=["pooled", "diploid", "perm"])
+    (20, ["--EM", "0"], dict(em_flag=0), dict(pools=6, length=16000, depth=60, seed=44, clip_frac=0.2, lowmapq_frac=0.1, n_frac=0.005)),
+], ids=["pooled", "diploid", "perm", "em0"])
 def test_bam_to_vcf_without_the_reference(tmp_path, poolsize, extra, opts, kw):
     """BAM files -> host/bam_decode.c -> crispgpu_pileup_run -> host/vcf_writer.c == CRISP.binary on the same files (the
     reference's whole program: its own BAM reader, pileup, engine and printer), record for record, byte for byte; several
@@ -345,7 +346,7 @@ def test_bam_to_vcf_without_the_reference(tmp_path, poolsize, extra, opts, kw):
     # same column header (pool names derived from the BAM paths as the reference does)
     assert [x for x in got_lines if x.startswith(b"#CHROM")] == [x for x in want_lines if x.startswith(b"#CHROM")]
     assert sample_id("/a/b/pool_003.sorted.bam") == "pool_003"
-    if not opts:
+    if not opts.get("chisq_permutation"):
         assert got == want, next((f"first difference:\n{g.decode()}\n{w.decode()}" for g, w in zip(got, want) if g != w), f"{len(got)} records vs {len(want)}")
         return
     key = lambda line: int(line.split(b"\t")[1])  # noqa: E731
@@ -357,11 +358,11 @@ def test_bam_to_vcf_without_the_reference(tmp_path, poolsize, extra, opts, kw):
 
 
 @pytest.mark.gpu
-def test_device_pileup_refuses_the_legacy_caller():
-    """--EM 0 reads the per-pool error sums (variant->stats/tstats), which the device pileup does not accumulate."""
+def test_device_pileup_refuses_weighted_counts():
+    """--weighted sums 1 - error probability per read into Qhighcounts, which the device pileup does not accumulate."""
     from crisp_b200.engine import EngineError
     aln, ref, length, poolsize, _ = golden()
-    eng = _engine(aln.n_pools, poolsize, em_flag=0)
-    with pytest.raises(EngineError, match="--EM 0"):
+    eng = _engine(aln.n_pools, poolsize, use_qv=1)
+    with pytest.raises(EngineError, match="--weighted"):
         eng.pileup_run(aln, make_window(0, 0, length, ref))
     eng.close()
