@@ -83,15 +83,57 @@ def merge_results(parts: list[Results], indices: list[np.ndarray], n_sites: int,
     return out
 
 
+def pack_results(res: Results, idx: np.ndarray) -> np.ndarray:
+    """One flat byte buffer holding a rank's results and the parent indices of its sites (what travels to rank 0)."""
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    head = np.array([res.n_sites, res.n_calls, res.n_pools, idx.size], dtype=np.int64)
+    parts = [head.view(np.uint8), idx.view(np.uint8)]
+    for name, dt, _ in _RESULT_FIELDS:
+        parts.append(np.ascontiguousarray(getattr(res, name), dtype=dt).reshape(-1).view(np.uint8))
+    parts.append(np.ascontiguousarray(res.ac[: res.n_calls], dtype=np.int32).reshape(-1).view(np.uint8))
+    parts.append(np.ascontiguousarray(res.qv[: res.n_calls], dtype=np.float64).reshape(-1).view(np.uint8))
+    return np.concatenate(parts)
+
+
+def unpack_results(buf: np.ndarray):
+    """Inverse of pack_results: (Results, idx)."""
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    n, n_calls, P, n_idx = (int(x) for x in buf[:32].view(np.int64))
+    o = 32
+    idx = buf[o:o + 8 * n_idx].view(np.int64).copy()
+    o += 8 * n_idx
+    res = Results(n, P, max_calls=n_calls)
+    res.n_calls = n_calls
+    for name, dt, w in _RESULT_FIELDS:
+        nb = n * w * np.dtype(dt).itemsize
+        getattr(res, name)[...] = buf[o:o + nb].view(dt).reshape(getattr(res, name).shape)
+        o += nb
+    nb = n_calls * P * 4
+    res.ac[...] = buf[o:o + nb].view(np.int32).reshape(n_calls, P)
+    o += nb
+    res.qv[...] = buf[o:o + n_calls * P * 8].view(np.float64).reshape(n_calls, P)
+    return res, idx
+
+
 def gather_results(local: Results, idx: np.ndarray, n_sites: int, n_pools: int, group=None):
-    """Collect every rank's results on rank 0 (torch.distributed object gather; control plane only — the
-    data path has no collective).  Returns the merged Results on rank 0 and None elsewhere."""
+    """Collect every rank's results on rank 0 and merge them in coordinate order (control plane only — the data path has no
+    collective).  Each rank's results travel as ONE flat byte tensor (two small collectives: the sizes, then the padded
+    buffers), not as pickled Python objects.  Returns the merged Results on rank 0 and None elsewhere."""
+    import torch
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    payload = (local, np.asarray(idx))
-    gathered = [None] * world if rank == 0 else None
-    dist.gather_object(payload, gathered, dst=0, group=group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    mine = pack_results(local, idx)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([mine.size], dtype=torch.int64, device=dev), group=group)
+    sizes = [int(x.item()) for x in sizes]
+    cap = max(sizes)
+    send = torch.zeros(cap, dtype=torch.uint8, device=dev)
+    send[: mine.size] = torch.from_numpy(mine).to(dev)
+    recv = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+    dist.gather(send, recv, dst=0, group=group)
     if rank != 0:
         return None
-    return merge_results([g[0] for g in gathered], [g[1] for g in gathered], n_sites, n_pools)
+    parts = [unpack_results(recv[r][: sizes[r]].cpu().numpy()) for r in range(world)]
+    return merge_results([p[0] for p in parts], [p[1] for p in parts], n_sites, n_pools)
