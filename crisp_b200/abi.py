@@ -98,6 +98,7 @@ class CBatch(C.Structure):
         ("ic16", C.c_void_p),
         ("ic_len", C.c_void_p),
         ("ic_site", C.c_void_p),
+        ("alt32", C.c_void_p),
     ]
 
 

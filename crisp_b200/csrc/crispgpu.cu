@@ -58,8 +58,10 @@ struct crispgpu_ctx {
 	bool sparse_ic = false;        // the batch came with sparse per-pool allele counts
 	bool binned = false;           // the batch came in the compact (value, count) read format
 	bool narrow = false;           // ... in its narrow transport form (bins16 / ic16): widened on the device
-	const void* nar[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // device addresses of bins16, bin_len, bin_site, ic16, ic_len, ic_site
-	DevBuf d_nar[6];
+	const void* nar[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // device addresses of bins16, bin_len, bin_site, ic16, ic_len, ic_site, alt32
+	DevBuf d_nar[7];
+	bool narrow_counts = false;    // the narrow batch came without site totals: k_expand_counts16 writes them
+	size_t n_alt32 = 0;            // alt-read records that came as 4-byte words (k_unpack_alt32)
 	DevBuf d_exact_row, d_exact_cl, d_exact_done;  // exact_mode: term tables of the exact 2 x k test, per-task decided flags
 	// device batch
 	DevBuf d_b[24];
@@ -338,12 +340,13 @@ int collect_arrays(crispgpu_ctx* ctx, const crispgpu_batch* b, BatchArray* a)
 	if (narrow && ((b->bin_site[n] && !b->bins16) || (b->ic_site[n] && !b->ic16))) return CRISPGPU_ERR_ARG;
 	const bool sparse_ic = !narrow && b->ic_off != nullptr && (b->ic_sparse != nullptr || (n && b->ic_off[n * P] == 0));
 	const bool binned = !narrow && (b->bins != nullptr || (b->bin_off != nullptr && n && b->bin_off[n * P] == 0));
-	if (!b->tid || !b->pos || !b->refbase || (!b->maxvec_al != !b->maxvec_ct) || !b->counts || (!b->indcounts && !sparse_ic && !narrow) || (!b->read_off && !binned && !narrow)) return CRISPGPU_ERR_ARG;
+	if (!b->tid || !b->pos || !b->refbase || (!b->maxvec_al != !b->maxvec_ct) || (!b->counts && !narrow) || (!b->indcounts && !sparse_ic && !narrow) || (!b->read_off && !binned && !narrow)) return CRISPGPU_ERR_ARG;
 	const size_t nreads = (n && !binned && !narrow) ? b->read_off[n * P] : 0;
 	const size_t nalt = (b->alt_off && n) ? b->alt_off[n * 5] : 0;
 	if (nreads && !b->reads) return CRISPGPU_ERR_ARG;
 	if (binned && !b->bin_off) return CRISPGPU_ERR_ARG;
-	if (nalt && !b->alt_reads) return CRISPGPU_ERR_ARG;
+	const bool alt_narrow = narrow && b->alt32 != nullptr;
+	if (nalt && !b->alt_reads && !alt_narrow) return CRISPGPU_ERR_ARG;
 	if (b->amb_idx && b->n_amb > 0 && !b->amb_dec) return CRISPGPU_ERR_ARG;
 	int k = 0;
 	a[k++] = {b->tid, n * 4};
@@ -358,7 +361,7 @@ int collect_arrays(crispgpu_ctx* ctx, const crispgpu_batch* b, BatchArray* a)
 	a[k++] = {(binned || narrow) ? nullptr : b->read_off, (n * P + 1) * 4};  // a compact batch has no read stream to index
 	a[k++] = {narrow ? nullptr : b->reads, nreads * 2};
 	a[k++] = {b->alt_off, b->alt_off ? (n * 5 + 1) * 4 : 0};
-	a[k++] = {b->alt_reads, nalt * sizeof(crispgpu_altread)};
+	a[k++] = {alt_narrow ? nullptr : b->alt_reads, nalt * sizeof(crispgpu_altread)};
 	a[k++] = {b->amb_idx, b->amb_idx ? n * 20 : 0};
 	a[k++] = {b->amb_dec, (b->amb_idx && b->amb_dec) ? (size_t)b->n_amb * P * 16 : 0};
 	a[k++] = {b->amb_ep, (b->amb_idx && b->amb_ep) ? (size_t)b->n_amb * P * 16 : 0};
@@ -378,6 +381,7 @@ int collect_arrays(crispgpu_ctx* ctx, const crispgpu_batch* b, BatchArray* a)
 	a[k++] = {narrow ? b->ic16 : nullptr, narrow ? (size_t)b->ic_site[n] * 2 : 0};
 	a[k++] = {narrow ? b->ic_len : nullptr, narrow ? n * P : 0};
 	a[k++] = {narrow ? b->ic_site : nullptr, narrow ? (n + 1) * 4 : 0};
+	a[k++] = {alt_narrow ? b->alt32 : nullptr, alt_narrow ? nalt * 4 : 0};
 	return k;
 }
 
@@ -447,6 +451,8 @@ int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b, bool lazy)
 	const bool reads_used = ctx->cfg.em_flag >= 1 && ctx->cfg.use_base_qvs == 1;
 	ctx->lazy_reads = nullptr;
 	ctx->narrow = a[25].host != nullptr;   // bin_site present
+	ctx->narrow_counts = false;
+	ctx->n_alt32 = 0;
 	ctx->binned = a[19].host != nullptr || ctx->narrow;
 	ctx->device_sort = false;
 	ctx->sparse_ic = a[21].host != nullptr;
@@ -479,6 +485,20 @@ int copy_batch(crispgpu_ctx* ctx, const crispgpu_batch* b, bool lazy)
 			CK(cudaMemcpyAsync(ctx->d_nar[i - 23].p, a[i].host, a[i].bytes, cudaMemcpyHostToDevice, ctx->stream));
 			bytes += (int64_t)a[i].bytes;
 			dst = ctx->d_nar[i - 23].p;
+			continue;
+		}
+		if (ctx->narrow && i == 5 && a[5].host == nullptr) {   // site totals summed on the device
+			int rc = ensure_dev(ctx, ctx->d_b[5], a[5].bytes ? a[5].bytes : 16);
+			if (rc) return rc;
+			dptr[5] = ctx->d_b[5].p;
+			ctx->narrow_counts = true;
+			continue;
+		}
+		if (ctx->narrow && i == 12 && a[29].host != nullptr) {   // 4-byte alt-read records widened on the device
+			int rc = ensure_dev(ctx, ctx->d_b[12], a[12].bytes ? a[12].bytes : 16);
+			if (rc) return rc;
+			dptr[12] = ctx->d_b[12].p;
+			ctx->n_alt32 = a[29].bytes / 4;
 			continue;
 		}
 		if (ctx->narrow && (i == 6 || i == 19 || i == 20)) {   // widened on the device (k_expand_counts16, k_narrow_offsets, k_unpack_bins16)
@@ -645,9 +665,15 @@ int run_stage1(crispgpu_ctx* ctx)
 	if (ctx->narrow && n > 0) {
 		const int need = (n + 7) / 8;
 		k_expand_counts16<<<need < ctx->num_sms * 8 ? need : ctx->num_sms * 8, 256, 0, ctx->stream>>>(static_cast<const uint8_t*>(ctx->nar[4]), static_cast<const uint32_t*>(ctx->nar[5]),
-		                                                                                 static_cast<const uint16_t*>(ctx->nar[3]), static_cast<int32_t*>(ctx->d_b[6].p), n, ctx->P);
+		                                                                                 static_cast<const uint16_t*>(ctx->nar[3]), static_cast<int32_t*>(ctx->d_b[6].p),
+		                                                                                 ctx->narrow_counts ? static_cast<int32_t*>(ctx->d_b[5].p) : nullptr, n, ctx->P);
 		launches++;
 		CK(launch_check());
+		if (ctx->n_alt32) {
+			k_unpack_alt32<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(static_cast<const uint32_t*>(ctx->nar[6]), static_cast<crispgpu_altread*>(ctx->d_b[12].p), ctx->n_alt32);
+			launches++;
+			CK(launch_check());
+		}
 	}
 	if (ctx->sparse_ic && n > 0) {
 		const size_t cells = (size_t)n * ctx->P;
@@ -1634,12 +1660,16 @@ int crispgpu_pileup_run_resident(crispgpu_ctx* ctx, int fetch_results, crispgpu_
 
 namespace {
 
-struct NarrowPlan { size_t nb16, nic16; bool ok; };
+struct NarrowPlan { size_t nb16, nic16; bool ok; bool alt32; size_t nalt; };
 
 NarrowPlan narrow_plan(const crispgpu_batch* b, size_t P)
 {
-	NarrowPlan pl{0, 0, false};
+	NarrowPlan pl{0, 0, false, false, 0};
 	const size_t n = (size_t)b->n_sites;
+	pl.nalt = (b->alt_off && n) ? b->alt_off[n * 5] : 0;
+	pl.alt32 = b->alt_off != nullptr && (pl.nalt == 0 || b->alt_reads != nullptr);
+	for (size_t k = 0; k < pl.nalt && pl.alt32; k++)
+		if (b->alt_reads[k].pool > 0x7ff || b->alt_reads[k].offset > 0x3ff || b->alt_reads[k].aligned > 0x3ff || b->alt_reads[k].strand > 1) pl.alt32 = false;
 	if (!b->bin_off || !b->ic_off || (n && b->bin_off[n * P] && !b->bins) || (n && b->ic_off[n * P] && !b->ic_sparse)) return pl;
 	for (size_t c = 0; c < n * P; c++) {
 		size_t e = 0;
@@ -1657,15 +1687,20 @@ NarrowPlan narrow_plan(const crispgpu_batch* b, size_t P)
 
 // the arrays of a batch that travel unchanged in a narrow arena (everything but the read stream and the four compact arrays)
 struct Span { const void** field; size_t bytes; };
-int narrow_spans(crispgpu_batch* v, size_t P, Span* sp)
+int narrow_spans(crispgpu_batch* v, size_t P, Span* sp, bool alt32)
 {
 	const size_t n = (size_t)v->n_sites;
 	int k = 0;
 	auto add = [&](const void** f, size_t bytes) { sp[k].field = f; sp[k].bytes = *f ? bytes : 0; k++; };
 	add((const void**)&v->tid, n * 4); add((const void**)&v->pos, n * 4); add((const void**)&v->refbase, n);
-	add((const void**)&v->maxvec_al, n * 8); add((const void**)&v->maxvec_ct, n * 32); add((const void**)&v->counts, n * 96);
+	// the site totals are recomputed on the device from the per-pool counts (k_expand_counts16): they do not travel.  The allele
+	// order does (40 B per site): sorting every site again on the device costs the single-GPU step more than the bytes cost
+	v->counts = nullptr;
+	add((const void**)&v->maxvec_al, n * 8); add((const void**)&v->maxvec_ct, n * 32);
 	add((const void**)&v->indel_len, n * 16); add((const void**)&v->hplen, n * 16);
-	add((const void**)&v->alt_off, (n * 5 + 1) * 4); add((const void**)&v->alt_reads, (v->alt_off && n) ? (size_t)v->alt_off[n * 5] * sizeof(crispgpu_altread) : 0);
+	add((const void**)&v->alt_off, (n * 5 + 1) * 4);
+	if (alt32) v->alt_reads = nullptr;
+	add((const void**)&v->alt_reads, (v->alt_off && n) ? (size_t)v->alt_off[n * 5] * sizeof(crispgpu_altread) : 0);
 	add((const void**)&v->amb_idx, n * 20); add((const void**)&v->amb_dec, (size_t)v->n_amb * P * 16); add((const void**)&v->amb_ep, (size_t)v->n_amb * P * 16);
 	add((const void**)&v->qhigh, n * P * 128); add((const void**)&v->stats, n * P * 128); add((const void**)&v->tstats, n * 128);
 	return k;
@@ -1683,8 +1718,8 @@ size_t crispgpu_batch_narrow_bytes(const crispgpu_batch* compact, int32_t n_pool
 	if (!pl.ok) return 0;
 	crispgpu_batch v = *compact;
 	Span sp[20];
-	const int k = narrow_spans(&v, P, sp);
-	size_t total = 0;
+	const int k = narrow_spans(&v, P, sp, pl.alt32);
+	size_t total = pl.alt32 ? pad256(pl.nalt * 4) : 0;
 	for (int i = 0; i < k; i++) total += pad256(sp[i].bytes);
 	total += pad256(pl.nb16 * 2) + pad256(n * P) + pad256((n + 1) * 4) + pad256(pl.nic16 * 2) + pad256(n * P) + pad256((n + 1) * 4);
 	return total + 256;
@@ -1699,7 +1734,7 @@ int crispgpu_batch_pack_narrow(const crispgpu_batch* compact, int32_t n_pools, v
 	const NarrowPlan pl = narrow_plan(compact, P);
 	*out = *compact;
 	Span sp[20];
-	const int k = narrow_spans(out, P, sp);
+	const int k = narrow_spans(out, P, sp, pl.alt32);
 	unsigned char* base = static_cast<unsigned char*>(arena);
 	size_t off = 0;
 	for (int i = 0; i < k; i++) {
@@ -1744,6 +1779,12 @@ int crispgpu_batch_pack_narrow(const crispgpu_batch* compact, int32_t n_pools, v
 	}
 	bsite[n] = (uint32_t)kb;
 	isite[n] = (uint32_t)ki;
+	out->alt32 = nullptr;
+	if (pl.alt32) {
+		uint32_t* a32 = reinterpret_cast<uint32_t*>(take(pl.nalt * 4));
+		for (size_t q = 0; q < pl.nalt; q++) a32[q] = CRISPGPU_ALT32(compact->alt_reads[q].pool, compact->alt_reads[q].offset, compact->alt_reads[q].aligned, compact->alt_reads[q].strand);
+		out->alt32 = a32;
+	}
 	out->indcounts = nullptr; out->read_off = nullptr; out->reads = nullptr;
 	out->bin_off = nullptr; out->bins = nullptr; out->ic_off = nullptr; out->ic_sparse = nullptr;
 	out->bins16 = b16; out->bin_len = blen; out->bin_site = bsite; out->ic16 = i16; out->ic_len = ilen; out->ic_site = isite;

@@ -494,11 +494,15 @@ __global__ void k_unpack_bins16(const uint16_t* __restrict__ bins16, uint32_t* _
 
 // Narrow sparse per-pool allele counts -> the dense [n][P][24] table: one warp per site finds its cells' entries from the
 // length bytes, every lane zeroes the 96-byte rows of its cells and adds their entries (entries of one index add up).
+// counts != null: the site totals (variant->counts = the column sums of the per-pool rows) are written as well.
 __global__ void k_expand_counts16(const uint8_t* __restrict__ len, const uint32_t* __restrict__ site, const uint16_t* __restrict__ ic16,
-                                  int32_t* __restrict__ indcounts, int n_sites, int P)
+                                  int32_t* __restrict__ indcounts, int32_t* __restrict__ counts, int n_sites, int P)
 {
-	const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+	__shared__ int tot[8][kNC];
+	const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
 	for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < n_sites; s += gridDim.x * wpb) {
+		if (counts && lane < kNC) tot[wib][lane] = 0;
+		__syncwarp();
 		uint32_t run = site[s];
 		for (int i0 = 0; i0 < P; i0 += 32) {
 			const int i = i0 + lane;
@@ -515,11 +519,28 @@ __global__ void k_expand_counts16(const uint8_t* __restrict__ len, const uint32_
 				for (uint32_t e = e0; e < e0 + v; e++) {
 					const uint32_t x = __ldg(ic16 + e);
 					const uint32_t idx = x >> 11;
-					if (idx < (uint32_t)kNC) row[idx] += (int32_t)(x & 0x7ffu);
+					if (idx < (uint32_t)kNC) {
+						row[idx] += (int32_t)(x & 0x7ffu);
+						if (counts) atomicAdd(&tot[wib][idx], (int)(x & 0x7ffu));
+					}
 				}
 			}
 			run += __shfl_sync(0xffffffffu, inc, 31);
 		}
+		__syncwarp();
+		if (counts && lane < kNC) counts[(size_t)s * kNC + lane] = tot[wib][lane];
+		__syncwarp();
+	}
+}
+
+// 4-byte alt-read records (crispgpu_batch.alt32) -> the 8-byte records the pool statistics read
+__global__ void k_unpack_alt32(const uint32_t* __restrict__ alt32, crispgpu_altread* __restrict__ out, size_t n)
+{
+	for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+		const uint32_t x = __ldg(alt32 + k);
+		crispgpu_altread e;
+		e.pool = (uint16_t)(x & 0x7ffu); e.offset = (uint16_t)((x >> 11) & 0x3ffu); e.aligned = (uint16_t)((x >> 21) & 0x3ffu); e.strand = (uint8_t)(x >> 31); e.pad = 0;
+		out[k] = e;
 	}
 }
 

@@ -197,10 +197,17 @@ typedef struct crispgpu_batch {
 	const uint16_t* ic16;
 	const uint8_t* ic_len;       /* [n*P] */
 	const uint32_t* ic_site;     /* [n+1] */
+	/* In a narrow batch `counts` may be NULL (crispgpu_batch_pack_narrow leaves it out): the site totals are the column sums
+	 * of the per-pool counts (k_expand_counts16); `maxvec_al`/`maxvec_ct` may be NULL as in any batch.  `alt32`, when non-NULL,
+	 * replaces `alt_reads` (same alt_off): pool in bits 0-10, read offset in bits 11-20, aligned bases in bits 21-30, strand
+	 * in bit 31 — packed by crispgpu_batch_pack_narrow when every record fits (reads shorter than 1024 bases). */
+	const uint32_t* alt32;
 } crispgpu_batch;
 
 #define CRISPGPU_BIN16(read_value, count) ((uint16_t)(((read_value) & 0x7f) | ((((read_value) >> 8) & 0xf) << 7) | ((((count) - 1) & 0x1f) << 11)))
 #define CRISPGPU_COUNT16(index, count) ((uint16_t)((((index) & 0x1f) << 11) | ((count) & 0x7ff)))
+#define CRISPGPU_ALT32(pool, offset, aligned, strand) \
+	((uint32_t)(((pool) & 0x7ffu) | (((offset) & 0x3ffu) << 11) | (((aligned) & 0x3ffu) << 21) | (((strand) ? 1u : 0u) << 31)))
 
 /* Per tested allele slot (al = slot+1 of maxvec), state of the reference's per-allele loop
  * (newcrispcaller.c:205-246). */

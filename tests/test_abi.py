@@ -42,7 +42,7 @@ def test_abi_version_and_defaults(lib):
 def test_struct_sizes_match_header():
     # LP64 layout of include/crispgpu.h
     assert C.sizeof(Config) == 4 * 2 + 8 + 4 * 12 + 8 + 8 * 8 + 8 + 4 * 4
-    assert C.sizeof(CBatch) == 8 + 8 * 16 + 8 + 8 * 9 + 8 * 6
+    assert C.sizeof(CBatch) == 8 + 8 * 16 + 8 + 8 * 9 + 8 * 7
     assert C.sizeof(CResults) == 8 + 8 * 29
     assert C.sizeof(Timing) == 4 * 8 + 4 * 2 + 8 * 4 + 4 * 4 + 8
 

@@ -17,6 +17,14 @@ def check_pack(batch):
     for name, dt in FIELDS:
         got = nb.array(name, dt, want[name].size)
         assert np.array_equal(got, want[name]), name
+    # the site totals do not travel (recomputed on the device); alt-read records as 4-byte words
+    c = nb.as_c()
+    assert not c.counts and c.maxvec_al and c.maxvec_ct
+    ar = batch.alt_reads
+    if ar is not None and ar.size and int(ar["offset"].max()) < 1024 and int(ar["aligned"].max()) < 1024:
+        a32 = nb.array("alt32", np.uint32, ar.size)
+        assert not c.alt_reads
+        assert np.array_equal(a32, ar["pool"].astype(np.uint32) | (ar["offset"].astype(np.uint32) << 11) | (ar["aligned"].astype(np.uint32) << 21) | (ar["strand"].astype(np.uint32) << 31))
     return nb, want
 
 
