@@ -1489,7 +1489,8 @@ int pile_run(crispgpu_ctx* ctx, bool fetch, crispgpu_pileup_sites* sites, crispg
 		CK(launch_check());
 		launches++;
 	}
-	if ((rc = ensure_dev(ctx, ctx->p_win, W * P * kPileCell * 4 + 16)) || (rc = ensure_dev(ctx, ctx->p_flag, W + 16)) || (rc = ensure_dev(ctx, ctx->p_cand, W * 4 + 16))) return rc;
+	const size_t screen_ctas = (W + kPileScreenTile - 1) / kPileScreenTile;
+	if ((rc = ensure_dev(ctx, ctx->p_win, W * P * kPileCell * 4 + 16)) || (rc = ensure_dev(ctx, ctx->p_flag, (W / 32 + 1 + screen_ctas) * 4 + 16)) || (rc = ensure_dev(ctx, ctx->p_cand, W * 4 + 16))) return rc;
 	uint32_t* d_win = static_cast<uint32_t*>(ctx->p_win.p);
 	CK(cudaEventRecord(ctx->ev_pile[1], ctx->stream));
 	if (W) {
@@ -1501,10 +1502,11 @@ int pile_run(crispgpu_ctx* ctx, bool fetch, crispgpu_pileup_sites* sites, crispg
 	CK(cudaEventRecord(ctx->ev_pile[2], ctx->stream));
 	int32_t* hs = static_cast<int32_t*>(ctx->ph_state.p);
 	if (W) {
-		const int need = (int)((W + 7) / 8);
-		k_pile_screen<<<need < ctx->num_sms * 16 ? need : ctx->num_sms * 16, 256, 0, ctx->stream>>>(d_win, w, (int)P, static_cast<const int32_t*>(ctx->d_ploidy.p), static_cast<uint8_t*>(ctx->p_flag.p));
+		uint32_t* bits = static_cast<uint32_t*>(ctx->p_flag.p);
+		int32_t* cta_count = reinterpret_cast<int32_t*>(bits + W / 32 + 1);
+		k_pile_screen<<<(unsigned)screen_ctas, 64, 0, ctx->stream>>>(d_win, w, (int)P, static_cast<const int32_t*>(ctx->d_ploidy.p), bits, cta_count);
 		CK(launch_check());
-		k_pile_select<<<1, 1024, 0, ctx->stream>>>(static_cast<const uint8_t*>(ctx->p_flag.p), (int)W, static_cast<int32_t*>(ctx->p_cand.p), rd.state + 2);
+		k_pile_select<<<(unsigned)screen_ctas, 64, 0, ctx->stream>>>(bits, cta_count, (int)W, static_cast<int32_t*>(ctx->p_cand.p), rd.state + 2);
 		CK(launch_check());
 		launches += 2;
 	}

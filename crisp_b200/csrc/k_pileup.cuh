@@ -456,13 +456,21 @@ __device__ __forceinline__ void sort_alleles(int ref, int (&ct)[8], int (&al)[8]
 			if (ct[i] < ct[j]) { const int tc = ct[i]; ct[i] = ct[j]; ct[j] = tc; const int ta = al[i]; al[i] = al[j]; al[j] = ta; }
 }
 
-// Candidate test of every window position (variantcalls.c:47,76-92): one warp per position, lanes over pools; the
-// potential-variant score adds 2 per (non-reference allele, pool) with >= 3 reads, and the read count for diploid pools
-// with >= 1.  flag[x] = 1 when the score reaches 2 on an A/C/G/T reference base.
-__global__ void k_pile_screen(const uint32_t* __restrict__ win, PileWindow w, int P, const int32_t* __restrict__ ploidy, uint8_t* __restrict__ flag)
+// Candidate test of every window position (variantcalls.c:47,76-92): one CTA per 64 consecutive positions, a warp per 32 of
+// them, lanes over pools; the potential-variant score adds 2 per (non-reference allele, pool) with >= 3 reads, and the read
+// count for diploid pools with >= 1.  A position is a candidate when the score reaches 2 on an A/C/G/T reference base: one
+// bit per position (bits[x / 32]) and the number of candidates per CTA.
+constexpr int kPileScreenTile = 64;   // two warps: many small CTAs, so that short windows still fill the device
+__global__ void __launch_bounds__(64) k_pile_screen(const uint32_t* __restrict__ win, PileWindow w, int P, const int32_t* __restrict__ ploidy, uint32_t* __restrict__ bits,
+                                                     int32_t* __restrict__ cta_count)
 {
-	const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-	for (int x = blockIdx.x * wpb + (threadIdx.x >> 5); x < w.W; x += gridDim.x * wpb) {
+	__shared__ int cnt[2];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int x0 = blockIdx.x * kPileScreenTile + warp * 32;
+	uint32_t mask = 0;
+	for (int k = 0; k < 32; k++) {
+		const int x = x0 + k;
+		if (x >= w.W) break;   // warp-uniform
 		const int ref = ref_code(ref_at(w, w.w0 + x));
 		int pot = 0;
 		for (int i = lane; i < P; i += 32) {
@@ -478,28 +486,38 @@ __global__ void k_pile_screen(const uint32_t* __restrict__ win, PileWindow w, in
 			}
 		}
 		pot = __reduce_add_sync(0xffffffffu, pot);
-		if (lane == 0) flag[x] = (pot >= 2 && ref < 4) ? 1 : 0;
+		if (pot >= 2 && ref < 4) mask |= 1u << k;
 	}
+	if (lane == 0) {
+		if (x0 < w.W) bits[x0 >> 5] = mask;
+		cnt[warp] = __popc(mask);
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) cta_count[blockIdx.x] = cnt[0] + cnt[1];
 }
 
-// candidate positions in coordinate order: one CTA, every thread owns a contiguous chunk of the window
-__global__ void k_pile_select(const uint8_t* __restrict__ flag, int W, int32_t* __restrict__ cand, int32_t* n_cand)
+// candidate positions in coordinate order: CTA b writes the candidates of its 64 positions behind those of the CTAs before it
+__global__ void __launch_bounds__(64) k_pile_select(const uint32_t* __restrict__ bits, const int32_t* __restrict__ cta_count, int W, int32_t* __restrict__ cand, int32_t* n_cand)
 {
-	__shared__ int sums[1024];
-	const int T = blockDim.x, tid = threadIdx.x, chunk = (W + T - 1) / T, a = min(W, tid * chunk), b = min(W, a + chunk);
-	int c = 0;
-	for (int x = a; x < b; x++) c += flag[x];
-	sums[tid] = c;
+	__shared__ int part[2];
+	__shared__ int base;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int before = 0;
+	for (int k = threadIdx.x; k < (int)blockIdx.x; k += blockDim.x) before += cta_count[k];
+	before = __reduce_add_sync(0xffffffffu, before);
+	if (lane == 0) part[warp] = before;
 	__syncthreads();
-	for (int d = 1; d < T; d <<= 1) {
-		const int v = tid >= d ? sums[tid - d] : 0;
-		__syncthreads();
-		sums[tid] += v;
-		__syncthreads();
+	if (threadIdx.x == 0) base = part[0] + part[1];
+	__syncthreads();
+	if (threadIdx.x < 2) {
+		const int x0 = blockIdx.x * kPileScreenTile + threadIdx.x * 32;
+		const int xa = blockIdx.x * kPileScreenTile;
+		const uint32_t m0 = xa < W ? bits[xa >> 5] : 0u, m1 = xa + 32 < W ? bits[(xa + 32) >> 5] : 0u;
+		int o = base + (threadIdx.x ? __popc(m0) : 0);
+		uint32_t mine = threadIdx.x ? m1 : m0;
+		while (mine) { const int bit = __ffs(mine) - 1; mine &= mine - 1; cand[o++] = x0 + bit; }
+		if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 1) *n_cand = o;
 	}
-	int o = sums[tid] - c;
-	for (int x = a; x < b; x++) if (flag[x]) cand[o++] = x;
-	if (tid == T - 1) *n_cand = sums[tid];
 }
 
 // exclusive prefix sum of n 32-bit counts into off[0..n] by one CTA (the arrays scanned here hold a few 10^5 cells)
@@ -604,7 +622,7 @@ __global__ void k_pile_gather_reads(PileReads rd, PileWindow w, PileSites ps)
 		const int p = ps.pos[c];
 		const int refc = ref_at(w, p);
 		const uint32_t r0 = rd.pool_off[j], r1 = rd.pool_off[j + 1];
-		const uint32_t lo = lower_bound_pos(rd.rec, r0, r1, p - max_span + 1), hi = lower_bound_pos(rd.rec, r0, r1, p + 1);
+		const uint32_t lo = lower_bound_warp(rd.rec, r0, r1, p - max_span + 1, lane), hi = lower_bound_warp(rd.rec, r0, r1, p + 1, lane);
 		int slot_al[5];
 #pragma unroll
 		for (int k = 0; k < 5; k++) slot_al[k] = ps.maxvec_ct[c * 8 + k + 1] >= 3 ? ps.maxvec_al[c * 8 + k + 1] : -1;
