@@ -1489,8 +1489,8 @@ int pile_run(crispgpu_ctx* ctx, bool fetch, crispgpu_pileup_sites* sites, crispg
 		CK(launch_check());
 		launches++;
 	}
-	const size_t screen_ctas = (W + kPileScreenTile - 1) / kPileScreenTile;
-	if ((rc = ensure_dev(ctx, ctx->p_win, W * P * kPileCell * 4 + 16)) || (rc = ensure_dev(ctx, ctx->p_flag, (W / 32 + 1 + screen_ctas) * 4 + 16)) || (rc = ensure_dev(ctx, ctx->p_cand, W * 4 + 16))) return rc;
+	const size_t n_words = (W + 31) / 32;
+	if ((rc = ensure_dev(ctx, ctx->p_win, W * P * kPileCell * 4 + 16)) || (rc = ensure_dev(ctx, ctx->p_flag, n_words * 4 + 16)) || (rc = ensure_dev(ctx, ctx->p_cand, W * 4 + 16))) return rc;
 	uint32_t* d_win = static_cast<uint32_t*>(ctx->p_win.p);
 	CK(cudaEventRecord(ctx->ev_pile[1], ctx->stream));
 	if (W) {
@@ -1503,10 +1503,9 @@ int pile_run(crispgpu_ctx* ctx, bool fetch, crispgpu_pileup_sites* sites, crispg
 	int32_t* hs = static_cast<int32_t*>(ctx->ph_state.p);
 	if (W) {
 		uint32_t* bits = static_cast<uint32_t*>(ctx->p_flag.p);
-		int32_t* cta_count = reinterpret_cast<int32_t*>(bits + W / 32 + 1);
-		k_pile_screen<<<(unsigned)screen_ctas, 64, 0, ctx->stream>>>(d_win, w, (int)P, static_cast<const int32_t*>(ctx->d_ploidy.p), bits, cta_count);
+		k_pile_screen<<<(unsigned)n_words, 256, 0, ctx->stream>>>(d_win, w, (int)P, static_cast<const int32_t*>(ctx->d_ploidy.p), bits);
 		CK(launch_check());
-		k_pile_select<<<(unsigned)screen_ctas, 64, 0, ctx->stream>>>(bits, cta_count, (int)W, static_cast<int32_t*>(ctx->p_cand.p), rd.state + 2);
+		k_pile_select<<<(unsigned)((n_words + kPileSelectWords - 1) / kPileSelectWords), kPileSelectWords, 0, ctx->stream>>>(bits, (int)n_words, static_cast<int32_t*>(ctx->p_cand.p), rd.state + 2);
 		CK(launch_check());
 		launches += 2;
 	}

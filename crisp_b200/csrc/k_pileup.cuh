@@ -456,20 +456,20 @@ __device__ __forceinline__ void sort_alleles(int ref, int (&ct)[8], int (&al)[8]
 			if (ct[i] < ct[j]) { const int tc = ct[i]; ct[i] = ct[j]; ct[j] = tc; const int ta = al[i]; al[i] = al[j]; al[j] = ta; }
 }
 
-// Candidate test of every window position (variantcalls.c:47,76-92): one CTA per 64 consecutive positions, a warp per 32 of
-// them, lanes over pools; the potential-variant score adds 2 per (non-reference allele, pool) with >= 3 reads, and the read
-// count for diploid pools with >= 1.  A position is a candidate when the score reaches 2 on an A/C/G/T reference base: one
-// bit per position (bits[x / 32]) and the number of candidates per CTA.
-constexpr int kPileScreenTile = 64;   // two warps: many small CTAs, so that short windows still fill the device
-__global__ void __launch_bounds__(64) k_pile_screen(const uint32_t* __restrict__ win, PileWindow w, int P, const int32_t* __restrict__ ploidy, uint32_t* __restrict__ bits,
-                                                     int32_t* __restrict__ cta_count)
+// Candidate test of every window position (variantcalls.c:47,76-92): one CTA per 32 consecutive positions, four per warp,
+// lanes over pools; the potential-variant score adds 2 per (non-reference allele, pool) with >= 3 reads, and the read count
+// for diploid pools with >= 1.  A position is a candidate when the score reaches 2 on an A/C/G/T reference base: one bit per
+// position, bits[x / 32].
+__global__ void __launch_bounds__(256) k_pile_screen(const uint32_t* __restrict__ win, PileWindow w, int P, const int32_t* __restrict__ ploidy, uint32_t* __restrict__ bits)
 {
-	__shared__ int cnt[2];
+	__shared__ uint32_t word;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int x0 = blockIdx.x * kPileScreenTile + warp * 32;
+	if (threadIdx.x == 0) word = 0;
+	__syncthreads();
 	uint32_t mask = 0;
-	for (int k = 0; k < 32; k++) {
-		const int x = x0 + k;
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const int x = blockIdx.x * 32 + warp * 4 + k;
 		if (x >= w.W) break;   // warp-uniform
 		const int ref = ref_code(ref_at(w, w.w0 + x));
 		int pot = 0;
@@ -486,38 +486,37 @@ __global__ void __launch_bounds__(64) k_pile_screen(const uint32_t* __restrict__
 			}
 		}
 		pot = __reduce_add_sync(0xffffffffu, pot);
-		if (pot >= 2 && ref < 4) mask |= 1u << k;
+		if (pot >= 2 && ref < 4) mask |= 1u << (warp * 4 + k);
 	}
-	if (lane == 0) {
-		if (x0 < w.W) bits[x0 >> 5] = mask;
-		cnt[warp] = __popc(mask);
-	}
+	if (lane == 0 && mask) atomicOr(&word, mask);
 	__syncthreads();
-	if (threadIdx.x == 0) cta_count[blockIdx.x] = cnt[0] + cnt[1];
+	if (threadIdx.x == 0) bits[blockIdx.x] = word;
 }
 
-// candidate positions in coordinate order: CTA b writes the candidates of its 64 positions behind those of the CTAs before it
-__global__ void __launch_bounds__(64) k_pile_select(const uint32_t* __restrict__ bits, const int32_t* __restrict__ cta_count, int W, int32_t* __restrict__ cand, int32_t* n_cand)
+// candidate positions in coordinate order: CTA b owns 64 words of the bit map (2048 positions); it counts the candidates
+// before them, then every thread writes the candidates of its word
+constexpr int kPileSelectWords = 64;
+__global__ void __launch_bounds__(kPileSelectWords) k_pile_select(const uint32_t* __restrict__ bits, int n_words, int32_t* __restrict__ cand, int32_t* n_cand)
 {
 	__shared__ int part[2];
-	__shared__ int base;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int w0 = blockIdx.x * kPileSelectWords;
 	int before = 0;
-	for (int k = threadIdx.x; k < (int)blockIdx.x; k += blockDim.x) before += cta_count[k];
+	for (int k = threadIdx.x; k < w0; k += blockDim.x) before += __popc(__ldg(bits + k));
 	before = __reduce_add_sync(0xffffffffu, before);
-	if (lane == 0) part[warp] = before;
+	const int wi = w0 + threadIdx.x;
+	uint32_t mine = wi < n_words ? bits[wi] : 0u;
+	int inc = __popc(mine);
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+	if (lane == 31) part[warp] = inc;   // the warp's candidates
+	const int before_all = before;
+	__shared__ int bef[2];
+	if (lane == 0) bef[warp] = before_all;
 	__syncthreads();
-	if (threadIdx.x == 0) base = part[0] + part[1];
-	__syncthreads();
-	if (threadIdx.x < 2) {
-		const int x0 = blockIdx.x * kPileScreenTile + threadIdx.x * 32;
-		const int xa = blockIdx.x * kPileScreenTile;
-		const uint32_t m0 = xa < W ? bits[xa >> 5] : 0u, m1 = xa + 32 < W ? bits[(xa + 32) >> 5] : 0u;
-		int o = base + (threadIdx.x ? __popc(m0) : 0);
-		uint32_t mine = threadIdx.x ? m1 : m0;
-		while (mine) { const int bit = __ffs(mine) - 1; mine &= mine - 1; cand[o++] = x0 + bit; }
-		if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 1) *n_cand = o;
-	}
+	int o = bef[0] + bef[1] + (warp ? part[0] : 0) + inc - __popc(mine);
+	while (mine) { const int bit = __ffs(mine) - 1; mine &= mine - 1; cand[o++] = wi * 32 + bit; }
+	if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *n_cand = bef[0] + bef[1] + part[0] + part[1];
 }
 
 // exclusive prefix sum of n 32-bit counts into off[0..n] by one CTA (the arrays scanned here hold a few 10^5 cells)

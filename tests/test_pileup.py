@@ -193,13 +193,16 @@ def test_device_pileup_matches_reference_fixture():
     eng.close()
 
 
-def _random_alignments(rng, P, L, depth, ploidy, readlen=(30, 150), long_frac=0.0):
+def _random_alignments(rng, P, L, depth, ploidy, readlen=(30, 150), long_frac=0.0, long_len=(200, 420), odd_ref=False):
     ref_codes = rng.integers(0, 4, size=L)
     ref = np.frombuffer(b"ACGT", np.uint8)[ref_codes].copy()
     lower = rng.random(L) < 0.1
     ref[lower] += 32
     ref[rng.random(L) < 0.01] = ord("N")
     ref[rng.random(L) < 0.003] = ord("R")
+    if odd_ref:   # characters outside BAM's base alphabet: no read base equals them
+        ref[rng.random(L) < 0.004] = ord("X")
+        ref[rng.random(L) < 0.002] = ord("*")
     alphabet = "ACGT"
     pools = []
     for j in range(P):
@@ -210,7 +213,7 @@ def _random_alignments(rng, P, L, depth, ploidy, readlen=(30, 150), long_frac=0.
         starts = np.sort(rng.integers(-40, L - 10, size=n))
         reads = []
         for s in starts:
-            ln = int(rng.integers(readlen[0], readlen[1] + 1)) if rng.random() >= long_frac else int(rng.integers(200, 420))
+            ln = int(rng.integers(readlen[0], readlen[1] + 1)) if rng.random() >= long_frac else int(rng.integers(long_len[0], long_len[1]))
             lead = int(rng.integers(0, 9)) if rng.random() < 0.2 and ln > 20 else 0
             trail = int(rng.integers(0, 9)) if rng.random() < 0.2 and ln > 20 else 0
             ml = ln - lead - trail
@@ -245,7 +248,9 @@ def _random_alignments(rng, P, L, depth, ploidy, readlen=(30, 150), long_frac=0.
     (3, 40, 300, 8, 2, {}),                            # diploid pools: the potential-variant score counts single reads
     (4, 1, 1500, 60, 30, {}),
     (5, 70, 200, 40, 4, dict(readlen=(10, 40))),       # more than two lanes-rounds of pools, short reads
-], ids=["pooled", "long_reads", "diploid", "one_pool", "many_pools"])
+    (6, 4, 3000, 30, 12, dict(long_frac=0.05, long_len=(600, 1500))),   # match blocks beyond the staged reference stretch: the general kernel path
+    (7, 4, 2200, 30, 12, dict(odd_ref=True)),           # reference characters outside BAM's alphabet: staged, but not the 4-bit fast path
+], ids=["pooled", "long_reads", "diploid", "one_pool", "many_pools", "very_long_reads", "odd_reference"])
 def test_device_pileup_matches_restatement(seed, P, L, depth, ploidy, kw):
     rng = np.random.default_rng(seed)
     aln, ref = _random_alignments(rng, P, L, depth, ploidy, **kw)
