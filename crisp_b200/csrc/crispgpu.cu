@@ -669,11 +669,6 @@ int run_stage1(crispgpu_ctx* ctx)
 		                                                                                 ctx->narrow_counts ? static_cast<int32_t*>(ctx->d_b[5].p) : nullptr, n, ctx->P);
 		launches++;
 		CK(launch_check());
-		if (ctx->n_alt32) {
-			k_unpack_alt32<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(static_cast<const uint32_t*>(ctx->nar[6]), static_cast<crispgpu_altread*>(ctx->d_b[12].p), ctx->n_alt32);
-			launches++;
-			CK(launch_check());
-		}
 	}
 	if (ctx->sparse_ic && n > 0) {
 		const size_t cells = (size_t)n * ctx->P;
@@ -689,10 +684,21 @@ int run_stage1(crispgpu_ctx* ctx)
 	}
 	CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
 	const bool scan = n > 0 && g.em_flag >= 1 && g.use_base_qvs == 1 && !lazy && ((use_bins && (ctx->n_bins > 0 || ctx->narrow)) || (!use_bins && ctx->n_reads > 0 && ctx->db.reads != nullptr));
+	// 4-byte alt-read words -> records: only the caller kernels read them, so the side stream takes them when it is in use
+	const bool alt32 = ctx->narrow && n > 0 && ctx->n_alt32 > 0;
+	if (alt32 && !scan) {
+		k_unpack_alt32<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(static_cast<const uint32_t*>(ctx->nar[6]), static_cast<crispgpu_altread*>(ctx->d_b[12].p), ctx->n_alt32);
+		launches++;
+		CK(launch_check());
+	}
 	if (scan) {
 		// fork: the scan of the read stream (or of its compact bins) is independent of the count-based screening
 		CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
 		CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+		if (alt32) {
+			k_unpack_alt32<<<ctx->num_sms * 2, 256, 0, ctx->side>>>(static_cast<const uint32_t*>(ctx->nar[6]), static_cast<crispgpu_altread*>(ctx->d_b[12].p), ctx->n_alt32);
+			launches++;
+		}
 		if (use_bins && ctx->narrow) {
 			const int need = (n + 7) / 8;
 			k_narrow_offsets<<<need < ctx->num_sms * 8 ? need : ctx->num_sms * 8, 256, 0, ctx->side>>>(static_cast<const uint8_t*>(ctx->nar[1]), static_cast<const uint32_t*>(ctx->nar[2]),
