@@ -70,7 +70,9 @@ def call_bams(bams, fasta: str, poolsize: int, out_vcf: str | None = None, optio
     L = ref.shape[0]
     P = len(bams)
     cfg = EngineConfig(ploidy=np.full(P, poolsize), options=dict(options, minimal_results=1))
+    t2 = time.perf_counter()
     eng = Engine(cfg, device=device)
+    t3 = time.perf_counter()
     body, n_sites, n_records, t_dev, t_fmt = [], 0, 0, 0.0, 0.0
     chrom = aln.stats["first_ref_name"]
     try:
@@ -90,8 +92,8 @@ def call_bams(bams, fasta: str, poolsize: int, out_vcf: str | None = None, optio
     finally:
         eng.close()
         _ARENA["aln"] = aln
-    out = dict(decode_s=t1 - t0, device_s=t_dev, format_s=t_fmt, candidate_sites=n_sites, records=n_records, alignments=aln.n_reads, positions=L,
-               decode_stats=aln.stats)
+    out = dict(decode_s=t1 - t0, fasta_s=t2 - t1, engine_create_s=t3 - t2, device_s=t_dev, format_s=t_fmt, candidate_sites=n_sites, records=n_records,
+               alignments=aln.n_reads, positions=L, decode_stats=aln.stats)
     if out_vcf:
         with open(out_vcf, "wb") as f:
             f.write(vcf_header(bams, fasta, poolsize, cfg.options))
