@@ -75,6 +75,7 @@ def call_bams(bams, fasta: str, poolsize: int, out_vcf: str | None = None, optio
     t3 = time.perf_counter()
     body, n_sites, n_records, t_dev, t_fmt = [], 0, 0, 0.0, 0.0
     chrom = aln.stats["first_ref_name"]
+    out = {}
     try:
         for start in range(0, L, window):
             end = min(L, start + window)
@@ -89,17 +90,19 @@ def call_bams(bams, fasta: str, poolsize: int, out_vcf: str | None = None, optio
             n_records += text.count(b"\n")
             t_dev += tb - ta
             t_fmt += tc - tb
+        out = dict(decode_s=t1 - t0, fasta_s=t2 - t1, engine_create_s=t3 - t2, device_s=t_dev, format_s=t_fmt, candidate_sites=n_sites, records=n_records,
+                   alignments=aln.n_reads, positions=L, decode_stats=aln.stats)
+        if out_vcf:
+            with open(out_vcf, "wb") as f:
+                f.write(vcf_header(bams, fasta, poolsize, cfg.options))
+                for t in body:
+                    f.write(t)
+        else:
+            out["vcf_body"] = b"".join(body)
+        out["wall_s"] = time.perf_counter() - t0   # BAM files read to VCF file written
     finally:
+        t4 = time.perf_counter()
         eng.close()
         _ARENA["aln"] = aln
-    out = dict(decode_s=t1 - t0, fasta_s=t2 - t1, engine_create_s=t3 - t2, device_s=t_dev, format_s=t_fmt, candidate_sites=n_sites, records=n_records,
-               alignments=aln.n_reads, positions=L, decode_stats=aln.stats)
-    if out_vcf:
-        with open(out_vcf, "wb") as f:
-            f.write(vcf_header(bams, fasta, poolsize, cfg.options))
-            for t in body:
-                f.write(t)
-    else:
-        out["vcf_body"] = b"".join(body)
-    out["wall_s"] = time.perf_counter() - t0
+        out["teardown_s"] = time.perf_counter() - t4   # engine destruction (device buffers, pinned arenas): once per run
     return out
