@@ -48,7 +48,7 @@ WORKLOADS = {
 
 # the other BASELINE configs, measured at reduced size inside the default run: (workload, sites, reference sites per core)
 SIDE_CONFIGS = [
-    ("c1_10x20_perm", 1024, 24), ("c3_100x96", 1024, 16), ("c4_perm_stress", 1024, 1), ("c4_perm_stress_em0", 1024, 1),
+    ("c1_10x20_perm", 1024, 24), ("c3_100x96", 4096, 16), ("c4_perm_stress", 1024, 1), ("c4_perm_stress_em0", 1024, 1),
     ("c5_500x10", 1024, 16), ("c5_500x10_perm", 512, 2), ("c5p_500x2_lowcov", 512, 2), ("exome50x48_q40", 2048, 64),
 ]
 

@@ -515,15 +515,23 @@ __global__ void k_expand_counts16(const uint8_t* __restrict__ len, const uint32_
 				int4* row4 = reinterpret_cast<int4*>(row);
 #pragma unroll
 				for (int k = 0; k < kNC / 4; k++) row4[k] = make_int4(0, 0, 0, 0);
+				// entries of one index follow one another (a count above 2047 is split in place): their sum is kept in a register
+				// and stored once, so the freshly zeroed row is never read back
 				const uint32_t e0 = run + inc - v;
+				uint32_t prev = 0xffffffffu;
+				int acc = 0;
 				for (uint32_t e = e0; e < e0 + v; e++) {
 					const uint32_t x = __ldg(ic16 + e);
 					const uint32_t idx = x >> 11;
-					if (idx < (uint32_t)kNC) {
-						row[idx] += (int32_t)(x & 0x7ffu);
-						if (counts) atomicAdd(&tot[wib][idx], (int)(x & 0x7ffu));
+					if (idx >= (uint32_t)kNC) continue;
+					if (idx != prev) {
+						if (prev != 0xffffffffu) { row[prev] = acc; if (counts) atomicAdd(&tot[wib][prev], acc); }
+						prev = idx;
+						acc = 0;
 					}
+					acc += (int)(x & 0x7ffu);
 				}
+				if (prev != 0xffffffffu) { row[prev] = acc; if (counts) atomicAdd(&tot[wib][prev], acc); }
 			}
 			run += __shfl_sync(0xffffffffu, inc, 31);
 		}

@@ -189,7 +189,7 @@ typedef struct crispgpu_batch {
 	 *              bits 11-15 count - 1 (a bin of more than 32 reads takes several entries)
 	 *   bin_len[c] entries of cell c = s*P+i (a cell with more than 255 entries cannot be packed: pack_narrow refuses)
 	 *   bin_site[s] first entry of site s, bin_site[n] = total
-	 *   ic16[k]    bits 11-15 index (allele + 8*strand class), bits 0-10 count (entries of one index add up)
+	 *   ic16[k]    bits 11-15 index (allele + 8*strand class), bits 0-10 count (a count above 2047 takes several ADJACENT entries of one index, which add up)
 	 *   ic_len[c], ic_site[s] as above */
 	const uint16_t* bins16;
 	const uint8_t* bin_len;      /* [n*P] */

@@ -152,3 +152,32 @@ def test_sharding_a_compact_batch():
         for name in ("tid", "pos", "counts", "bin_off", "bins", "ic_off", "ic_sparse", "alt_off"):
             assert np.array_equal(getattr(sub, name), getattr(ref, name)), name
     assert np.array_equal(np.sort(np.concatenate(seen)), np.arange(batch.n_sites))
+
+
+def test_results_pack_unpack_round_trip():
+    """What a rank sends to rank 0 (shard.pack_results) comes back as the same results (flat byte buffer, no pickling)."""
+    from crisp_b200.abi import _RESULT_FIELDS, Results
+    from crisp_b200.shard import merge_results, pack_results, unpack_results
+    rng = np.random.default_rng(4)
+    n, P, calls = 37, 6, 11
+    r = Results(n, P, max_calls=calls)
+    r.n_calls = calls
+    for name, dt, w in _RESULT_FIELDS:
+        a = getattr(r, name)
+        a[...] = (rng.random(a.shape) * 50).astype(dt)
+    r.ac[...] = rng.integers(0, 20, size=r.ac.shape)
+    r.qv[...] = rng.random(r.qv.shape)
+    idx = rng.permutation(100)[:n]
+    buf = pack_results(r, idx)
+    assert buf.dtype == np.uint8
+    back, idx2 = unpack_results(buf)
+    assert np.array_equal(idx2, idx) and back.n_calls == calls and back.n_sites == n
+    for name, _, _ in _RESULT_FIELDS:
+        assert np.array_equal(getattr(back, name), getattr(r, name)), name
+    assert np.array_equal(back.ac, r.ac) and np.array_equal(back.qv, r.qv)
+    # an empty rank (no sites) packs and merges
+    e = Results(0, P, max_calls=0)
+    eb, ei = unpack_results(pack_results(e, np.zeros(0, np.int64)))
+    assert eb.n_sites == 0 and ei.size == 0
+    merged = merge_results([back, eb], [np.arange(n), ei], n, P)
+    assert np.array_equal(merged.delta, r.delta) and merged.n_calls == calls
