@@ -44,7 +44,8 @@ __device__ inline double d_gammaq(double s, double z)
 		double sum = 1., x = 1.;
 		for (int k = 1; k < 100; ++k) {
 			sum += (x *= z / (s + k));
-			if (x / sum < 1e-14) break;
+			if (x < 1e-14 * sum) break;   // the reference's x / sum < 1e-14 without the division (sum >= 1): the same term count but for
+			                              // quotients within an ulp of the threshold, where one more term of 1e-14 relative size is added
 		}
 		double lp = s * log(z) - z - d_lgamma(s + 1.) + log(sum);
 		return log(1.0 - exp(lp));
