@@ -329,6 +329,17 @@ def side_config(name, sites, ref_per_core, local, peaks3, cores, want_cpu):
     return out
 
 
+def narrow_pack_us(batch) -> float:
+    """Host cost of crispgpu_batch_pack_narrow per site (compact batch -> narrow arena), one core."""
+    from crisp_b200.engine import NarrowBatch
+    c = batch.compact()
+    NarrowBatch(c, pinned=False)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        NarrowBatch(c, pinned=False)
+    return 1e6 * (time.perf_counter() - t0) / 5 / batch.n_sites
+
+
 def bam_end_to_end(cores: int):
     """BASELINE configs[0] as real files: 10 pools x poolsize 20, 100 kb at 100x, written as BAMs; the reference's own program
     (CRISP.binary: one process, and one process per core over --regions shards — its only parallelism, README.md:51) beside
@@ -653,8 +664,9 @@ def main():
                 sub = batch.select(np.arange(min(256, batch.n_sites)))
                 r = RefEngine(cfg)
                 line["host_pack"] = {"reads_us_per_site": 1e6 * r.shim_pack_seconds(sub, False) / sub.n_sites,
-                                     "compact_us_per_site": 1e6 * r.shim_pack_seconds(sub, True) / sub.n_sites, "cores": 1, "sites": sub.n_sites,
-                                     "what": "crisp_shim_append_site alone (walks of the reference's read lists + packing), per candidate site of this workload; not inside `e2e`, whose batches are packed before the timed region"}
+                                     "compact_us_per_site": 1e6 * r.shim_pack_seconds(sub, True) / sub.n_sites,
+                                     "narrow_extra_us_per_site": narrow_pack_us(sub), "cores": 1, "sites": sub.n_sites,
+                                     "what": "crisp_shim_append_site alone (walks of the reference's read lists + packing), per candidate site of this workload, and what crispgpu_batch_pack_narrow adds on top of the compact form; not inside `e2e`, whose batches are packed before the timed region"}
             if not args.no_configs:
                 line["configs"] = {}
                 for name, nsites, per_core in SIDE_CONFIGS:

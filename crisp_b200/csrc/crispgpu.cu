@@ -1717,12 +1717,11 @@ size_t pad256(size_t x) { return (x + 255) & ~size_t(255); }
 
 }  // namespace
 
-size_t crispgpu_batch_narrow_bytes(const crispgpu_batch* compact, int32_t n_pools)
+namespace {
+
+size_t narrow_bytes_of(const crispgpu_batch* compact, size_t P, const NarrowPlan& pl)
 {
-	if (!compact || n_pools <= 0 || compact->n_sites < 0) return 0;
-	const size_t P = (size_t)n_pools, n = (size_t)compact->n_sites;
-	const NarrowPlan pl = narrow_plan(compact, P);
-	if (!pl.ok) return 0;
+	const size_t n = (size_t)compact->n_sites;
 	crispgpu_batch v = *compact;
 	Span sp[20];
 	const int k = narrow_spans(&v, P, sp, pl.alt32);
@@ -1732,13 +1731,21 @@ size_t crispgpu_batch_narrow_bytes(const crispgpu_batch* compact, int32_t n_pool
 	return total + 256;
 }
 
+}  // namespace
+
+size_t crispgpu_batch_narrow_bytes(const crispgpu_batch* compact, int32_t n_pools)
+{
+	if (!compact || n_pools <= 0 || compact->n_sites < 0) return 0;
+	const NarrowPlan pl = narrow_plan(compact, (size_t)n_pools);
+	return pl.ok ? narrow_bytes_of(compact, (size_t)n_pools, pl) : 0;
+}
+
 int crispgpu_batch_pack_narrow(const crispgpu_batch* compact, int32_t n_pools, void* arena, size_t arena_cap, crispgpu_batch* out)
 {
-	if (!compact || !arena || !out || n_pools <= 0 || (reinterpret_cast<uintptr_t>(arena) & 255)) return CRISPGPU_ERR_ARG;
-	const size_t need = crispgpu_batch_narrow_bytes(compact, n_pools);
-	if (need == 0 || need > arena_cap) return CRISPGPU_ERR_ARG;
+	if (!compact || !arena || !out || n_pools <= 0 || compact->n_sites < 0 || (reinterpret_cast<uintptr_t>(arena) & 255)) return CRISPGPU_ERR_ARG;
 	const size_t P = (size_t)n_pools, n = (size_t)compact->n_sites;
-	const NarrowPlan pl = narrow_plan(compact, P);
+	const NarrowPlan pl = narrow_plan(compact, P);   // one pass over the entries sizes the narrow arrays; the second pass writes them
+	if (!pl.ok || narrow_bytes_of(compact, P, pl) > arena_cap) return CRISPGPU_ERR_ARG;
 	*out = *compact;
 	Span sp[20];
 	const int k = narrow_spans(out, P, sp, pl.alt32);
