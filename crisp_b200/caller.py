@@ -77,10 +77,17 @@ def call_bams(bams, fasta: str, poolsize: int, out_vcf: str | None = None, optio
     chrom = aln.stats["first_ref_name"]
     out = {}
     try:
+        # the region's alignments and reference go to the device once; the windows are called on them where they lie
+        window = max(1, min(window, max(65536, (2 << 30) // (32 * P))))   # the window's count table: 32 B per position and pool
+        ta = time.perf_counter()
+        eng.pileup_upload(aln, make_window(tid, 0, min(L, window), ref, min_mapq=min_mapq))
+        t_dev += time.perf_counter() - ta
         for start in range(0, L, window):
             end = min(L, start + window)
             ta = time.perf_counter()
-            sites, res = eng.pileup_run(aln, make_window(tid, start, end, ref, min_mapq=min_mapq))
+            if start:
+                eng.pileup_set_window(make_window(tid, start, end, None, min_mapq=min_mapq))
+            sites, res = eng.pileup_run_resident(fetch=True)
             tb = time.perf_counter()
             text = format_records(sites, res, cfg.ploidy, chrom, ref, chrom_len=L, em_flag=cfg.options["em_flag"], varpoolsize=cfg.options["varpoolsize"],
                                   threads=min(threads, 16))

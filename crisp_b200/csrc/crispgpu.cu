@@ -1654,6 +1654,29 @@ int crispgpu_pileup_upload(crispgpu_ctx* ctx, const crispgpu_alignments* aln, co
 	return CRISPGPU_OK;
 }
 
+int crispgpu_pileup_set_window(crispgpu_ctx* ctx, const crispgpu_window* win)
+{
+	if (!ctx || !win) return CRISPGPU_ERR_ARG;
+	if (ctx->inflight) return CRISPGPU_ERR_TICKET;
+	if (!ctx->pile_resident) { snprintf(ctx->err, sizeof ctx->err, "no resident alignments: call crispgpu_pileup_upload first"); return CRISPGPU_ERR_ARG; }
+	if (win->end < win->start) return CRISPGPU_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	PileWindow& w = ctx->pwin;
+	if (win->refseq) {   // a new reference stretch; NULL keeps the one that is on the device
+		if (win->ref_len < 0) return CRISPGPU_ERR_ARG;
+		int rc = ensure_dev(ctx, ctx->p_ref, win->ref_len ? (size_t)win->ref_len : 16);
+		if (rc) return rc;
+		if (win->ref_len) CK(cudaMemcpyAsync(ctx->p_ref.p, win->refseq, (size_t)win->ref_len, cudaMemcpyHostToDevice, ctx->stream));
+		w.ref0 = win->ref_start; w.reflen = win->ref_len;
+		w.refseq = static_cast<const uint8_t*>(ctx->p_ref.p);
+	}
+	w.tid = win->tid; w.w0 = win->start; w.W = win->end - win->start;
+	w.min_m = win->min_mapq;
+	ctx->pile_streams = win->want_streams != 0;
+	ctx->pile_h2d = 0;   // nothing of the alignments moves for this window
+	return CRISPGPU_OK;
+}
+
 int crispgpu_pileup_run_resident(crispgpu_ctx* ctx, int fetch_results, crispgpu_pileup_sites* sites, crispgpu_results* results)
 {
 	if (!ctx) return CRISPGPU_ERR_ARG;

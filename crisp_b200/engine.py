@@ -20,7 +20,7 @@ EXPORTS = [
     "crispgpu_upload", "crispgpu_run_resident", "crispgpu_get_timing", "crispgpu_last_error",
     "crispgpu_host_alloc", "crispgpu_host_free", "crispgpu_abi_version", "crispgpu_device_count",
     "crispgpu_measure_fp64_tflops", "crispgpu_measure_int32_tops",
-    "crispgpu_pileup_run", "crispgpu_pileup_upload", "crispgpu_pileup_run_resident",
+    "crispgpu_pileup_run", "crispgpu_pileup_upload", "crispgpu_pileup_run_resident", "crispgpu_pileup_set_window",
     "crispgpu_batch_narrow_bytes", "crispgpu_batch_pack_narrow",
 ]
 
@@ -261,6 +261,16 @@ class Engine:
         fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         fn.restype = C.c_int
         self._check(fn(self.h, C.byref(ca), C.byref(cw)), "crispgpu_pileup_upload")
+        del keep
+
+    def pileup_set_window(self, window) -> None:
+        """Another window over the resident alignments (crispgpu_pileup_set_window); a window made with refseq=None keeps the
+        reference stretch that is on the device."""
+        cw, keep = window
+        fn = self.lib.crispgpu_pileup_set_window
+        fn.argtypes = [C.c_void_p, C.c_void_p]
+        fn.restype = C.c_int
+        self._check(fn(self.h, C.byref(cw)), "crispgpu_pileup_set_window")
         del keep
 
     def pileup_run_resident(self, fetch: bool = False):

@@ -228,8 +228,11 @@ def sites_from_c(cs: CPileupSites, P: int) -> PileupSites:
     return out
 
 
-def make_window(tid: int, start: int, end: int, refseq: np.ndarray, ref_start: int = 0, want_streams: bool = False, min_mapq: int = 20):
-    """(CWindow, keep-alive) for reference bytes `refseq` (uint8 array of characters) starting at position ref_start."""
+def make_window(tid: int, start: int, end: int, refseq, ref_start: int = 0, want_streams: bool = False, min_mapq: int = 20):
+    """(CWindow, keep-alive) for reference bytes `refseq` (uint8 array of characters) starting at position ref_start; refseq None:
+    a window over the reference stretch that is already on the device (Engine.pileup_set_window)."""
+    if refseq is None:
+        return CWindow(tid, start, end, ref_start, 0, 1 if want_streams else 0, min_mapq, 0, None), None
     ref = np.ascontiguousarray(refseq, dtype=np.uint8)
     return CWindow(tid, start, end, ref_start, ref.shape[0], 1 if want_streams else 0, min_mapq, 0, ref.ctypes.data), ref
 

@@ -388,8 +388,12 @@ typedef struct crispgpu_pileup_sites {
 int crispgpu_pileup_run(crispgpu_ctx* ctx, const crispgpu_alignments* aln, const crispgpu_window* win, crispgpu_pileup_sites* sites,
                         crispgpu_results* results);
 /* Device-resident variant used to time the pileup kernels alone: crispgpu_pileup_upload copies the alignments and the
- * reference window once, crispgpu_pileup_run_resident piles them up again (fetch_results = 0: nothing is copied back). */
+ * reference window once, crispgpu_pileup_run_resident piles them up (fetch_results = 0: nothing is copied back) — the way to
+ * time the kernels alone, and, with crispgpu_pileup_set_window, to call a decoded region window by window. */
 int crispgpu_pileup_upload(crispgpu_ctx* ctx, const crispgpu_alignments* aln, const crispgpu_window* win);
+/* Another window over the alignments that are resident: a region decoded once is called window by window without moving
+ * its alignments again.  win->refseq NULL keeps the reference stretch already on the device. */
+int crispgpu_pileup_set_window(crispgpu_ctx* ctx, const crispgpu_window* win);
 int crispgpu_pileup_run_resident(crispgpu_ctx* ctx, int fetch_results, crispgpu_pileup_sites* sites, crispgpu_results* results);
 
 /* Optional, between submit and wait: waits only for the screening counters of the batch and enqueues its caller

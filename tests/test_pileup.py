@@ -276,6 +276,15 @@ def test_device_pileup_windows_concatenate():
         pos.append(s.pos), ct.append(r.ctpval), delta.append(r.delta)
     assert np.array_equal(np.concatenate(pos), whole_sites.pos)
     assert np.array_equal(np.concatenate(ct), whole.ctpval) and np.array_equal(np.concatenate(delta), whole.delta)
+    # the same windows over alignments that went to the device once (crispgpu_pileup_upload + _set_window)
+    eng.pileup_upload(aln, make_window(0, 0, 1024, ref))
+    pos2, ct2 = [], []
+    for k, (a, b) in enumerate([(0, 1024), (1024, 1025), (1025, 3333), (3333, length)]):
+        if k:
+            eng.pileup_set_window(make_window(0, a, b, None))
+        s, r = eng.pileup_run_resident(fetch=True)
+        pos2.append(s.pos), ct2.append(r.ctpval)
+    assert np.array_equal(np.concatenate(pos2), whole_sites.pos) and np.array_equal(np.concatenate(ct2), whole.ctpval)
     # an empty window and a window without alignments
     s, r = eng.pileup_run(aln, make_window(0, 500, 500, ref))
     assert s.n_sites == 0 and r.n_sites == 0
