@@ -80,7 +80,7 @@ struct crispgpu_ctx {
 	size_t out_bytes = 0;
 	DevOut dout{};
 	// queues
-	DevBuf d_perm_tasks, d_call_tasks, d_call_tasks2, d_counters, h_counters, d_gws;
+	DevBuf d_perm_tasks, d_call_tasks, d_call_tasks2, d_order, d_counters, h_counters, d_gws, d_trace;
 	DevBuf d_tail_task, d_tail_head, d_tail_total, d_tail_rec, d_tail_counters;  // long permutation tasks (k_permute_stranded_tail)
 	size_t gws_stride = 0;
 	// launch geometry
@@ -598,6 +598,8 @@ int ensure_outputs(crispgpu_ctx* ctx, int n)
 	if (rc) return rc;
 	rc = ensure_dev(ctx, ctx->d_call_tasks2, (size_t)n * 5 * 4);
 	if (rc) return rc;
+	rc = ensure_dev(ctx, ctx->d_order, (size_t)n * 5 * 4);
+	if (rc) return rc;
 	return 0;
 }
 
@@ -942,6 +944,13 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 		if (g.em_flag >= 1) {
 			const bool assoc = g.association == 1 && ctx->d_pheno.p != nullptr;
 			int32_t* cnt = static_cast<int32_t*>(ctx->d_counters.p);
+			static const bool keep_order = getenv("CRISPGPU_EM_SITE_ORDER") != nullptr;  // measurement switch
+			static const char* trace_path = getenv("CRISPGPU_EM_TRACE");                 // measurement switch: task timeline of the last launch
+			if (trace_path) {
+				rc = ensure_dev(ctx, ctx->d_trace, (size_t)ctx->n_call * 8 * sizeof(long long)); if (rc) return rc;
+				CK(cudaMemsetAsync(ctx->d_trace.p, 0, (size_t)ctx->n_call * 8 * sizeof(long long), ctx->stream));
+				prm.em_trace = static_cast<long long*>(ctx->d_trace.p);
+			}
 			auto launch_em = [&](auto kernel, const int32_t* list, int ntasks, int32_t* head, int row0, size_t smem, bool smem_g, int* grid_cache) -> int {
 				if (ntasks <= 0) return 0;
 				if (!*grid_cache) {
@@ -952,6 +961,13 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 					if (r2) return r2;
 				}
 				int grid = *grid_cache < ntasks ? *grid_cache : ntasks;
+				if (ntasks > *grid_cache && !keep_order) {
+					// more tasks than resident CTAs: slow tasks first (k_order_tasks), so the launch does not end on one
+					int32_t* ordered = static_cast<int32_t*>(ctx->d_order.p) + row0;
+					k_order_tasks<<<1, 1024, 0, ctx->stream>>>(list, ntasks, prm.o.paf, ordered);
+					launches++;
+					list = ordered;
+				}
 				if (!smem_g) {
 					int r2 = ensure_dev(ctx, ctx->d_gws, (size_t)*grid_cache * ctx->gws_stride * sizeof(double));
 					if (r2) return r2;
@@ -996,6 +1012,12 @@ int run_stage2(crispgpu_ctx* ctx, bool fetch)
 		}
 		launches++;
 		CK(launch_check());
+	}
+	if (prm.em_trace) {
+		std::vector<long long> tr((size_t)ctx->n_call * 8);
+		CK(cudaStreamSynchronize(ctx->stream));
+		CK(cudaMemcpy(tr.data(), ctx->d_trace.p, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+		if (FILE* f = fopen(getenv("CRISPGPU_EM_TRACE"), "wb")) { fwrite(tr.data(), sizeof(long long), tr.size(), f); fclose(f); }
 	}
 	if (n > 0) {
 		k_finalize<<<(n + 255) / 256, 256, 0, ctx->stream>>>(prm);
@@ -1300,7 +1322,7 @@ void crispgpu_destroy(crispgpu_ctx* ctx)
 	fd(ctx->d_rows); fh(ctx->h_rows); fd(ctx->d_arena);
 	for (auto& b : ctx->d_nar) fd(b);
 	fd(ctx->d_tail_task); fd(ctx->d_tail_head); fd(ctx->d_tail_total); fd(ctx->d_tail_rec); fd(ctx->d_tail_counters);
-	fd(ctx->d_perm_tasks); fd(ctx->d_call_tasks); fd(ctx->d_call_tasks2); fd(ctx->d_counters); fh(ctx->h_counters); fd(ctx->d_gws);
+	fd(ctx->d_perm_tasks); fd(ctx->d_call_tasks); fd(ctx->d_call_tasks2); fd(ctx->d_order); fd(ctx->d_trace); fd(ctx->d_counters); fh(ctx->h_counters); fd(ctx->d_gws);
 	fd(ctx->p_pool_off); fd(ctx->p_rec); fd(ctx->p_mate); fd(ctx->p_isize); fd(ctx->p_seq4); fd(ctx->p_qual); fd(ctx->p_ref); fd(ctx->p_flags);
 	fd(ctx->p_state); fd(ctx->p_win); fd(ctx->p_flag); fd(ctx->p_cand); fd(ctx->p_sites); fd(ctx->p_work); fd(ctx->p_reads); fd(ctx->p_alt);
 	fh(ctx->ph_state); fh(ctx->ph_sites); fh(ctx->ph_reads); fh(ctx->ph_alt);

@@ -241,6 +241,166 @@ struct Philox {
 // instruction on the XU pipe
 __device__ __forceinline__ double u32_to_double(uint32_t v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
 
+// log10 for the EM's own logarithms (the log-sum-exp of every (plane, pool) unit, log10 p and log10(1-p) of every iteration):
+// they sit on the serial part of an iteration, where libdevice's log10 (~95 dependent instructions) was a tenth of the
+// iteration's latency.  x = 2^e * m; the top seven mantissa bits pick c ~ m from a table holding rc = fl(1/c) and
+// -log10(rc) (m >= 1.4140625 is halved first, so e = 0 and c = 1 around x = 1 and nothing cancels there); r = m*rc - 1
+// exactly (one FMA), |r| < 2^-7; log10(1+r) by its Taylor polynomial to degree 9 (Estrin, dependent depth 6);
+// e*log10(2) in two pieces, the high one exact.  Max error 2.3 ulp (3e-16 relative), 2e-18 absolute for |log10 x| < 0.01
+// (tests/test_dmath.py runs these operations on the CPU against the 80-bit log10l; scripts/make_log10_table.py made the
+// table).  Zero, negative, subnormal, infinite and NaN arguments take libdevice's log10.
+__device__ const double kLog10Tab[256] = {
+	1.0, 0.0,
+	0.9884169884169884, 0.005059798769402255,
+	0.9808429118773946, 0.008400542026431423,
+	0.973384030418251, 0.01171578317790831,
+	0.9660377358490566, 0.015005908624958285,
+	0.9588014981273408, 0.018271296052725657,
+	0.9516728624535316, 0.021512314690558438,
+	0.9446494464944649, 0.024729325562556182,
+	0.9377289377289377, 0.027922681728906475,
+	0.9309090909090909, 0.03109272851841309,
+	0.924187725631769, 0.034239803752598975,
+	0.9175627240143369, 0.037364237961747995,
+	0.9110320284697508, 0.04046635459323036,
+	0.9045936395759717, 0.04354647021244068,
+	0.8982456140350877, 0.04660489469666063,
+	0.89198606271777, 0.049641931422142765,
+	0.8858131487889274, 0.052657877444698284,
+	0.8797250859106529, 0.055653023674057736,
+	0.8737201365187713, 0.05862765504225989,
+	0.8677966101694915, 0.06158205066631345,
+	0.8619528619528619, 0.0645164840053628,
+	0.8561872909698997, 0.06743122301258009,
+	0.8504983388704319, 0.07032653028199379,
+	0.8448844884488449, 0.07320266319045544,
+	0.839344262295082, 0.07605987403493628,
+	0.8338762214983714, 0.0788984101653369,
+	0.8284789644012945, 0.08171851411298506,
+	0.8231511254019293, 0.08452042371498796,
+	0.8178913738019169, 0.08730437223459894,
+	0.8126984126984127, 0.09007058847775094,
+	0.807570977917981, 0.09281929690590195,
+	0.8025078369905956, 0.09555071774533158,
+	0.7975077881619937, 0.09826506709302253,
+	0.7925696594427245, 0.1009625570192533,
+	0.7876923076923077, 0.10364339566702482,
+	0.7828746177370031, 0.1063077873484365,
+	0.7781155015197568, 0.10895593263812474,
+	0.7734138972809668, 0.11158802846386917,
+	0.7687687687687688, 0.11420426819447031,
+	0.764179104477612, 0.11680484172499567,
+	0.7596439169139466, 0.11938993555948905,
+	0.7551622418879056, 0.1219597328912326,
+	0.750733137829912, 0.12451441368064815,
+	0.7463556851311953, 0.12705415473092094,
+	0.7420289855072464, 0.12957912976142455,
+	0.7377521613832853, 0.13208950947902418,
+	0.7335243553008596, 0.13458546164733035,
+	0.7293447293447294, 0.1370671511539745,
+	0.7252124645892352, 0.139534740075973,
+	0.7211267605633803, 0.14198838774324452,
+	0.7170868347338936, 0.14442825080034363,
+	0.713091922005571, 0.14685448326646958,
+	0.7091412742382271, 0.14926723659380836,
+	1.4104683195592287, -0.14936333593971826,
+	1.4027397260273973, -0.14697709651935606,
+	1.3950953678474114, -0.1446038967237414,
+	1.3875338753387534, -0.14224359481677037,
+	1.3800539083557952, -0.1398960513607849,
+	1.3726541554959786, -0.13756112916714316,
+	1.3653333333333333, -0.13523869324811189,
+	1.3580901856763925, -0.13292861077003787,
+	1.3509234828496042, -0.1306307510077584,
+	1.3438320209973753, -0.12834498530021146,
+	1.3368146214099217, -0.126071187007208,
+	1.3298701298701299, -0.12380923146733008,
+	1.322997416020672, -0.12155899595691938,
+	1.3161953727506426, -0.11932035965012298,
+	1.3094629156010231, -0.11709320357996399,
+	1.3027989821882953, -0.11487741060040409,
+	1.2962025316455696, -0.11267286534937053,
+	1.2896725440806045, -0.11047945421271568,
+	1.2832080200501252, -0.1082970652890825,
+	1.2768079800498753, -0.10612558835564843,
+	1.2704714640198511, -0.10396491483472131,
+	1.2641975308641975, -0.1018149377611622,
+	1.257985257985258, -0.09967555175061071,
+	1.2518337408312958, -0.09754665296848895,
+	1.245742092457421, -0.09542813909976157,
+	1.2397094430992737, -0.09331990931942975,
+	1.2337349397590363, -0.09122186426373809,
+	1.2278177458033572, -0.08913390600207322,
+	1.2219570405727924, -0.08705593800953547,
+	1.2161520190023754, -0.08498786514016247,
+	1.210401891252955, -0.0829295936007884,
+	1.204705882352941, -0.08088103092551918,
+	1.199063231850117, -0.0788420859508069,
+	1.1934731934731935, -0.07681266879110651,
+	1.1879350348027842, -0.07479269081509914,
+	1.1824480369515011, -0.07278206462246531,
+	1.1770114942528735, -0.07078070402119342,
+	1.17162471395881, -0.06878852400540891,
+	1.1662870159453302, -0.06680544073370936,
+	1.1609977324263039, -0.06483137150799223,
+	1.1557562076749435, -0.06286623475276117,
+	1.150561797752809, -0.0609099499948992,
+	1.145413870246085, -0.05896243784389427,
+	1.1403118040089086, -0.057023619972507565,
+	1.1352549889135255, -0.05509341909787022,
+	1.130242825607064, -0.05317175896299888,
+	1.1252747252747253, -0.05125856431871835,
+	1.1203501094091903, -0.049353760905980516,
+	1.1154684095860568, -0.047457275438569556,
+	1.1106290672451193, -0.045569035586182624,
+	1.1058315334773219, -0.043688969957877646,
+	1.1010752688172043, -0.041817008085876836,
+	1.0963597430406853, -0.039953080409718615,
+	1.091684434968017, -0.038097118260747485,
+	1.0870488322717622, -0.036249053846934574,
+	1.0824524312896406, -0.03440882023801921,
+	1.0778947368421052, -0.03257635135096418,
+	1.0733752620545074, -0.03075158193571686,
+	1.068893528183716, -0.028934447561267493,
+	1.0644490644490645, -0.027124884601999015,
+	1.060041407867495, -0.02532283022431864,
+	1.0556701030927835, -0.02352822237356711,
+	1.051334702258727, -0.02174099976119644,
+	1.047034764826176, -0.019961101852210554,
+	1.0427698574338085, -0.018188468852862242,
+	1.0385395537525355, -0.016423041698600736,
+	1.0343434343434343, -0.014664762042262037,
+	1.0301810865191148, -0.012913572242498677,
+	1.0260521042084167, -0.011169415352440806,
+	1.0219560878243512, -0.009432235108585003,
+	1.0178926441351888, -0.007701975919903315,
+	1.0138613861386139, -0.005978582857169383,
+	1.009861932938856, -0.004262001642494803,
+	1.005893909626719, -0.0025521786390719794,
+	1.0, 0.0,
+};
+__constant__ double kLog10K[11] = {0.4342944819032518, -0.2171472409516259, 0.14476482730108395, -0.10857362047581295, 0.08685889638065036, -0.07238241365054197, 0.06204206884332169, -0.05428681023790648, 0.048254942433694645, 0.30102999566383914, 1.42050232272661e-13};
+__device__ __forceinline__ double log10_fast(double x)
+{
+	const int hi = __double2hiint(x);
+	if ((uint32_t)(hi - 0x00100000) >= 0x7FE00000u) return log10(x);
+	const int i = (hi >> 13) & 0x7f;
+	const int up = i >= 53 ? 1 : 0;
+	const double m = __hiloint2double((hi & 0x000FFFFF) | (up ? 0x3FE00000 : 0x3FF00000), __double2loint(x));
+	const double2 tc = __ldg(reinterpret_cast<const double2*>(kLog10Tab) + i);
+	const double ed = u32_to_double((uint32_t)((hi >> 20) + up + 1)) - 1024.0;   // exponent - 1023 + up, without a conversion instruction
+	const double r = fma(m, tc.x, -1.0);
+	const double r2 = r * r;
+	const double A = fma(kLog10K[1], r, kLog10K[0]), B = fma(kLog10K[3], r, kLog10K[2]), C = fma(kLog10K[5], r, kLog10K[4]), D = fma(kLog10K[7], r, kLog10K[6]);
+	const double r4 = r2 * r2;
+	const double AB = fma(B, r2, A), CD = fma(D, r2, C);
+	const double in = fma(r4, kLog10K[8], CD);
+	const double P = fma(r4, in, AB);
+	const double t = fma(ed, kLog10K[9], tc.y);
+	const double s = fma(ed, kLog10K[10], r * P);
+	return t + s;
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll

@@ -111,6 +111,7 @@ struct EngineParams {
 	DevQueues q;
 	double* gws;          // global workspace for genotype likelihoods when they do not fit in shared memory
 	size_t gws_stride;    // doubles per CTA
+	long long* em_trace;  // measurement switch (CRISPGPU_EM_TRACE): per EM task eight words: ns at task start / counts staged / histogram built / planes built / first iteration done / EM done / task end, then SM | task << 16 | (2 iterations + called) << 48; null in normal runs
 };
 
 }  // namespace crisp

@@ -115,6 +115,15 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 		__syncthreads();
 		if (cur_task >= n_tasks) break;
 		if (tid == 0) sh->next_task = atomicAdd(head, 1);
+		// measurement switch: phase timestamps of the task (thread 0, straight to the trace buffer)
+		auto stamp = [&](int k) {
+			if (prm.em_trace && tid == 0) {
+				long long t;
+				asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+				prm.em_trace[(size_t)(row0 + cur_task) * 8 + k] = t;
+			}
+		};
+		stamp(0);
 		const int o = tasks[cur_task], s = o / kSlots, slot = o - s * kSlots;
 		const int task = row0 + cur_task;  // AC/QV row
 		const uint8_t* mal = b.maxvec_al + s * 8;
@@ -183,6 +192,7 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 			if (has_bins) for (int i = tid; i <= P; i += blockDim.x) boff[i] = b.bin_off[(size_t)s * P + i];
 		}
 		__syncthreads();
+		stamp(1);
 
 		// =====================================================================================================
 		// likelihood planes
@@ -269,6 +279,7 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 				}
 			}
 			__syncthreads();
+			stamp(2);
 			// (2) on the FP64 tensor cores: G[class][pool][j] = sum_bin dh[bin][class][pool] * Ts[bin][j] is a small GEMM
 			// (M = pools, N = genotypes, K = 2 nq bins).  One DMMA.8x8x4 does the work of eight DFMA warp instructions in one
 			// issue slot — the FP64 rate is the same, but this kernel is bound by issue slots, not by the FP64 pipe.
@@ -277,42 +288,48 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 			const int ptiles = (P + 7) >> 3, jtiles = (J + 7) >> 3, ksteps = (2 * nq + 3) >> 2;
 			constexpr int NCLS = NOBIDIR ? 2 : 3;  // no bidirectional reads: that class is empty
 			// Rows / columns beyond the table are clamped (their results are not stored) and a bin index beyond 2 nq gets a
-			// zero B element, so the inner loop carries no bounds predicates; (pt, jt) advance without a division.
+			// zero B element, so the inner loop carries no bounds predicates.  A warp takes eight pools and TWO genotype tiles
+			// per trip: the pool fragment (histogram load + conversion) serves both, and four accumulator chains (2 classes x
+			// 2 tiles) are in flight instead of two — the phase ran at the latency of the DMMA chain (6 us of a 38 us task).
 			const int kk = lane & 3, g8 = lane >> 2;
-			int pt = warp / jtiles, jt = warp - pt * jtiles;
-			for (int item = warp; item < ptiles * jtiles; item += nwarps) {
-				const int prow = pt * 8 + g8, jcol = jt * 8 + g8;
+			const int jpairs = (jtiles + 1) >> 1;
+			for (int item = warp; item < ptiles * jpairs; item += nwarps) {
+				const int pt = item / jpairs, jp = item - pt * jpairs;
+				const int prow = pt * 8 + g8, jcol0 = jp * 16 + g8, jcol1 = jcol0 + 8;
 				const uint32_t* dhp = dh + (prow < P ? prow : P - 1);
-				const double* tsp = Ts + (jcol < J ? jcol : J - 1);
-				double acc[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+				const double* tsp0 = Ts + (jcol0 < J ? jcol0 : J - 1);
+				const double* tsp1 = Ts + (jcol1 < J ? jcol1 : J - 1);
+				double acc[2][3][2] = {{{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}}};
 				for (int ks = 0; ks < ksteps; ks++) {
 					const int wd = ks * 4 + kk;
 					const bool kin = wd < 2 * nq;
 					const int wdc = kin ? wd : 0;
-					const double tv = tsp[wdc * J];
-					const double bf = kin ? tv : 0.0;
+					const double tv0 = tsp0[wdc * J], tv1 = tsp1[wdc * J];
+					const double bf0 = kin ? tv0 : 0.0, bf1 = kin ? tv1 : 0.0;
 #pragma unroll
 					for (int cls = 0; cls < NCLS; cls++) {
 						const double af = u32_to_double(dhp[(wdc * 3 + cls) * P]);
 						asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-						             : "+d"(acc[cls][0]), "+d"(acc[cls][1]) : "d"(af), "d"(bf));
+						             : "+d"(acc[0][cls][0]), "+d"(acc[0][cls][1]) : "d"(af), "d"(bf0));
+						asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+						             : "+d"(acc[1][cls][0]), "+d"(acc[1][cls][1]) : "d"(af), "d"(bf1));
 					}
 				}
-				const int jt_store = jt;
-				jt += nwarps;
-				while (jt >= jtiles) { jt -= jtiles; pt++; }
 				const int i = prow;
 				if (i < P) {
 #pragma unroll
-					for (int t = 0; t < 2; t++) {
-						const int j = jt_store * 8 + kk * 2 + t;
-						if (j < J) {
-							const double nc = NOBIDIR ? NCs[j] : c.NC[j];
-							const size_t idx = (size_t)j * P + i;
-							Gf[idx] = acc[0][t] + nc;
-							Gr[idx] = acc[1][t] + nc;
-							if (!NOBIDIR) Gt[idx] = (acc[0][t] + acc[1][t] + acc[2][t]) + nc;
-							if (j == 0) Gb0[i] = acc[2][t];
+					for (int h = 0; h < 2; h++) {
+#pragma unroll
+						for (int t = 0; t < 2; t++) {
+							const int j = jp * 16 + h * 8 + kk * 2 + t;
+							if (j < J) {
+								const double nc = NOBIDIR ? NCs[j] : c.NC[j];
+								const size_t idx = (size_t)j * P + i;
+								Gf[idx] = acc[h][0][t] + nc;
+								Gr[idx] = acc[h][1][t] + nc;
+								if (!NOBIDIR) Gt[idx] = (acc[h][0][t] + acc[h][1][t] + acc[h][2][t]) + nc;
+								if (j == 0) Gb0[i] = acc[h][2][t];
+							}
 						}
 					}
 				}
@@ -492,6 +509,7 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 			__syncthreads();
 		}
 
+		stamp(3);
 		// =====================================================================================================
 		// EM iterations (crispEM.c:233-314)
 		// =====================================================================================================
@@ -503,7 +521,7 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 			// log10 p / log10(1-p) per plane: published in shared memory by the warp that closed the previous iteration; for the
 			// first iteration every warp takes them from the starting frequency (lane 0: p, lane 1: 1-p; the planes start equal)
 			double first_lg = 0.0;
-			if (it == 0) first_lg = log10((lane & 1) ? 1.0 - my_p : my_p);
+			if (it == 0) first_lg = log10_fast((lane & 1) ? 1.0 - my_p : my_p);
 			double* part = part_base + (it & 1) * 19 * rounds;
 			const int nunits = rounds * 3;
 			for (int u = warp; u < nunits; u += nwarps) {
@@ -532,14 +550,16 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 					m = -1e300;
 					const double* hp = Hp;
 					const double* hq = Hq;
-					double jd = 0.0, vprev = -1e300;
-					for (int j = 0; j <= nmax; j++, hp += P, hq += P, jd += 1.0) {
-						const bool in = NOBIDIR || j <= n;
-						const double v = in ? term(tag, hp, hq, j, jd) : -1e300;
-						m = v > m ? v : m;
+					double jd = 0.0;
+					// two genotypes per trip (independent loads and FMAs; one vote per pair)
+					for (int j = 0; j <= nmax; j += 2, hp += 2 * P, hq += 2 * P, jd += 2.0) {
+						const bool in0 = NOBIDIR || j <= n, in1 = j < nmax && (NOBIDIR || j + 1 <= n);
+						const double v0 = in0 ? term(tag, hp, hq, j, jd) : -1e300;
+						const double v1 = in1 ? term(tag, hp + P, hq + P, j + 1, jd + 1.0) : -1e300;
+						m = v0 > m ? v0 : m;
+						m = v1 > m ? v1 : m;
 						// H[j] + j*dl is concave in j (unimodal): past the mode nothing larger follows
-						if (unimodal && __all_sync(0xffffffffu, !in || v < vprev)) break;
-						vprev = v;
+						if (unimodal && __all_sync(0xffffffffu, !in1 || v1 < v0)) break;
 					}
 				};
 				if (it == 0 || countlik) {  // count-based planes are rebuilt every iteration: always take the exact maximum
@@ -551,33 +571,40 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 					const Exp10K ek = exp10_constants();
 					const double* hp = Hp;
 					const double* hq = Hq;
-					double jd = 0.0, vprev = -1e300;
-					for (int j = 0; j <= nmax; j++, hp += P, hq += P, jd += 1.0) {
-						const bool in = NOBIDIR || j <= n;
-						const double v = in ? term(tag, hp, hq, j, jd) : -1e300;
-						const double d = v - m;
-						// d > -cut on the integer pipe: the high word of a double, as unsigned, orders like -value for negatives and
-						// sits below 0x80000000 for positives (the low word decides nothing that matters for a cut-off)
-						const bool live = (uint32_t)__double2hiint(d) < kCutHi;
-						if (live) {
-							const double e = exp10_lse(d, ek);
-							S += e;
-							Wj = fma(jd, e, Wj);
-							if (countlik && pl == 0) {
-								const double f = jd / n;
+					double jd = 0.0;
+					auto add_term = [&](double e, double jv) {
+						S += e;
+						Wj = fma(jv, e, Wj);
+						if (countlik && pl == 0) {
+							const double f = jv / n;
 #pragma unroll
-								for (int k = 0; k < 3; k++) {
-									const double den1 = (1.0 - f) * (1.0 - E01[k]) + f * E10[k], den2 = (1.0 - f) * E01[k] + f * (1.0 - E10[k]);
-									T00[k] += e * (1.0 - f) * (1.0 - E01[k]) / den1;
-									T10[k] += e * f * E10[k] / den1;
-									T11[k] += e * f * (1.0 - E10[k]) / den2;
-									T01[k] += e * (1.0 - f) * E01[k] / den2;
-								}
+							for (int k = 0; k < 3; k++) {
+								const double den1 = (1.0 - f) * (1.0 - E01[k]) + f * E10[k], den2 = (1.0 - f) * E01[k] + f * (1.0 - E10[k]);
+								T00[k] += e * (1.0 - f) * (1.0 - E01[k]) / den1;
+								T10[k] += e * f * E10[k] / den1;
+								T11[k] += e * f * (1.0 - E10[k]) / den2;
+								T01[k] += e * (1.0 - f) * E01[k] / den2;
 							}
 						}
-						// descending and below the cut-off for every lane: the remaining terms are smaller still
-						if (unimodal && __all_sync(0xffffffffu, !in || (v < vprev && !live))) break;
-						vprev = v;
+					};
+					// Two genotypes per trip: a warp walks its unit alone, one dependent chain of ~12 FP64 operations per 10^d, so
+					// the loop ran at the latency of that chain; the two chains of a pair are independent and interleave.  Terms are
+					// added in the order of j, a term below the cut-off adds an exact zero: the sums are those of the one-by-one walk.
+					for (int j = 0; j <= nmax; j += 2, hp += 2 * P, hq += 2 * P, jd += 2.0) {
+						const bool in0 = NOBIDIR || j <= n, in1 = j < nmax && (NOBIDIR || j + 1 <= n);
+						const double v0 = in0 ? term(tag, hp, hq, j, jd) : -1e300;
+						const double v1 = in1 ? term(tag, hp + P, hq + P, j + 1, jd + 1.0) : -1e300;
+						const double d0 = v0 - m, d1 = v1 - m;
+						// d > -cut on the integer pipe: the high word of a double, as unsigned, orders like -value for negatives and
+						// sits below 0x80000000 for positives (the low word decides nothing that matters for a cut-off)
+						const bool live0 = (uint32_t)__double2hiint(d0) < kCutHi, live1 = (uint32_t)__double2hiint(d1) < kCutHi;
+						if (live0 || live1) {
+							const double e0 = exp10_lse(live0 ? d0 : 0.0, ek), e1 = exp10_lse(live1 ? d1 : 0.0, ek);
+							add_term(live0 ? e0 : 0.0, jd);
+							add_term(live1 ? e1 : 0.0, jd + 1.0);
+						}
+						// descending and below the cut-off for every lane at the second of the pair (then also at whatever follows)
+						if (unimodal && __all_sync(0xffffffffu, !in1 || (v1 < v0 && !live1))) break;
 					}
 				};
 				// The shift kept for the next iteration is this iteration's log-sum-exp itself (within log10(n+1) decades above
@@ -586,7 +613,7 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 				double lS = 0.0;
 				for (int attempt = 0; attempt < 3; attempt++) {
 					if (sum2) sum_loop(std::true_type{}); else sum_loop(std::false_type{});
-					lS = log10(S);
+					lS = log10_fast(S);
 					if (__all_sync(0xffffffffu, fabs(lS) <= 3.0)) break;   // false for S = 0 (-inf) and NaN as well
 					if (__any_sync(0xffffffffu, !(S > 0.0) || !(fabs(lS) < 1e300))) {
 						if (sum2) exact_max(std::true_type{}); else exact_max(std::false_type{});
@@ -655,7 +682,7 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 				const bool stop = (it + 1 >= 2 && d0 <= 0.0001 && d1 <= 0.01 && d2 <= 0.01) || it + 1 >= 1000;
 				if (!stop) {
 					const double pp = __shfl_sync(0xffffffffu, my_p, (lane >> 1) < 3 ? (lane >> 1) : 0);
-					const double lg = log10((lane & 1) ? 1.0 - pp : pp);   // lane 2 pl: log10 p, lane 2 pl + 1: log10(1-p)
+					const double lg = log10_fast((lane & 1) ? 1.0 - pp : pp);   // lane 2 pl: log10 p, lane 2 pl + 1: log10(1-p)
 					if (lane < 6) sh->lp[lane >> 1][lane & 1] = lg;
 				} else {
 					// statistics of the fit (crispEM.c:321-349)
@@ -663,22 +690,24 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 					const double pf = __shfl_sync(0xffffffffu, my_p, 0);
 					const double df = (LLf > LLr) ? LLf - LLt - log10(2.0) : LLr - LLt - log10(2.0);
 					const double ALPHA = c.alpha_prior;
-					const double LLrefadd = LLnull0 + log10(1.0 - ALPHA);
-					double LL = LLt + log10(ALPHA);
-					if (LLrefadd < LL) LL += log10(1.0 + exp10(LLrefadd - LL));
-					else LL = LLrefadd + log10(1.0 + exp10(LL - LLrefadd));
+					const double LLrefadd = LLnull0 + log10_fast(1.0 - ALPHA);
+					double LL = LLt + log10_fast(ALPHA);
+					if (LLrefadd < LL) LL += log10_fast(1.0 + exp10(LLrefadd - LL));
+					else LL = LLrefadd + log10_fast(1.0 + exp10(LL - LLrefadd));
 					if (lane == 0) { sh->delta = LL - LLrefadd; sh->deltaf = df; sh->p[0] = pf; sh->hwe = 0.0; sh->iter = it + 1; }
 				}
 				if (lane == 0) sh->exitflag = stop ? 1 : 0;
 			}
 			__syncthreads();
 			it++;
+			if (it == 1) stamp(4);
 			if (countlik) {
 				for (int k = 0; k < 3; k++) { E01[k] = sh->E01[k]; E10[k] = sh->E10[k]; }
 				count_likelihood();  // crispEM.c:298, also on the exit iteration
 			}
 			if (sh->exitflag) break;
 		}
+		stamp(5);
 		// (the planes were last read before the barriers that closed the final iteration: the genotype phase may overwrite them)
 		const double delta = sh->delta, deltaf = sh->deltaf, pfin = sh->p[0];
 		it = sh->iter;
@@ -686,7 +715,7 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 		int varpools = 0;
 		if (called) {
 			// ---- calculate_genotypes: argmax / runner-up per pool, posterior genotype counts, HWE ----
-			const double l0 = log10(pfin), l1 = log10(1.0 - pfin);
+			const double l0 = log10_fast(pfin), l1 = log10_fast(1.0 - pfin);
 			double* post = Gf;  // forward plane is no longer needed: reuse as posterior[j][pool]
 			// with more warps than rounds of pools the genotype pass occupies `rounds` warps; the others run the pool statistics
 			// (which read the counts and the alt-read list only) at the same time instead of waiting at the barrier
@@ -737,7 +766,7 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 						tprev = t;
 					}
 				}
-				const double Lb = best + log10(S);
+				const double Lb = best + log10_fast(S);
 				{
 					const Exp10K ek = exp10_constants();
 					const double* hp = Hp;
@@ -793,16 +822,39 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 				const uint32_t e0 = ahi > alo ? (uint32_t)astart[i] : alo;
 				int m = ahi > alo ? astart[i + 1] - astart[i] : 0;
 				if (m > f + r + bd) m = f + r + bd;  // `i < reads` cap, allelecounts.c:53
+				// Reads with a (strand, start) pair not seen earlier in the pool's list (calculate_uniquereads).  The list was
+				// re-read from memory once per earlier read (m^2/2 loads per pool: the alleles at 10-20 % frequency made the
+				// slowest tasks of a launch, 110-190 us against 50); now 32 reads per trip: one __match_any finds the repeats
+				// inside the trip, the keys of the first four trips stay in registers and are compared through shuffles, and
+				// only a list beyond 128 reads goes back to memory for the part past them.
 				int uq = 0, mid = 0;
-				for (int e = lane; e < m; e += 32) {
-					const crispgpu_altread x = b.alt_reads[e0 + e];
-					bool first = true;
-					for (int e2 = 0; e2 < e; e2++) {
-						const crispgpu_altread y = b.alt_reads[e0 + e2];
-						if (y.strand == x.strand && y.offset == x.offset) { first = false; break; }
+				uint32_t kept[4] = {0, 0, 0, 0};
+				for (int c0 = 0, ch = 0; c0 < m; c0 += 32, ch++) {
+					const int e = c0 + lane;
+					const bool in = e < m;
+					crispgpu_altread x{};
+					if (in) x = b.alt_reads[e0 + e];
+					const uint32_t key = in ? ((uint32_t)x.strand << 16) | x.offset : 0x80000000u | (uint32_t)lane;
+					const unsigned peers = __match_any_sync(0xffffffffu, key);
+					bool first = in && __ffs(peers) - 1 == lane;
+#pragma unroll
+					for (int pc = 0; pc < 4; pc++) {
+						if (pc < ch) {
+							bool seen = false;
+							for (int j = 0; j < 32; j++) seen |= __shfl_sync(0xffffffffu, kept[pc], j) == key;
+							first = first && !seen;
+						}
 					}
+					if (ch >= 4) {
+						for (int e2 = 128; e2 < c0 && first; e2++) {
+							const crispgpu_altread y = b.alt_reads[e0 + e2];
+							if (y.strand == x.strand && y.offset == x.offset) first = false;
+						}
+					}
+#pragma unroll
+					for (int pc = 0; pc < 4; pc++) if (pc == ch) kept[pc] = key;
 					uq += first ? 1 : 0;
-					if (x.offset >= 5 && (int)x.aligned - (int)x.offset >= 5) mid++;
+					if (in && x.offset >= 5 && (int)x.aligned - (int)x.offset >= 5) mid++;
 				}
 				uq = warp_sum(uq);
 				mid = warp_sum(mid);
@@ -915,6 +967,12 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 			prm.o.deltaf[o] = deltaf;
 			prm.o.hwe[o] = sh->hwe;
 			prm.o.em_iters[o] = it;
+			if (prm.em_trace) {
+				unsigned sm;
+				asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+				stamp(6);
+				prm.em_trace[(size_t)task * 8 + 7] = (long long)sm | ((long long)o << 16) | ((long long)(it * 2 + (called ? 1 : 0)) << 48);
+			}
 			prm.o.call_row[o] = called ? task : -1;
 			if (called) {
 				int vp = 0, acs = 0;

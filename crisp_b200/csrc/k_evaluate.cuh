@@ -339,6 +339,54 @@ __global__ void __launch_bounds__(256) k_eval_finish(EngineParams prm)
 	}
 }
 
+// Order of the EM task list.  k_em's CTAs take tasks from a shared counter; a task runs for 15-100 us (14 + 3.8 per EM
+// iteration + 24 when the allele is called; CRISPGPU_EM_TRACE, scripts/em_trace.py) and the launch for a few hundred, so the
+// launch ends one task after the last one was taken: in site order the SMs idle for 15 % of it at the benchmark shape.
+// What can be known beforehand is the starting frequency paf (expected copies of the allele): below ~3 copies the allele is
+// rarely called and the few slow fits (up to 22 iterations) are among the lowest; above, it is called and the read-evidence
+// pass grows with the number of its reads.  The list is therefore put as: uncertain alleles in ascending paf, then the
+// clear ones in descending paf (a counting sort on exponent + 3 mantissa bits of paf, one CTA, keys kept in registers) —
+// the launch then ends on the lightest called alleles, which are all alike (simulated on the trace: 392 -> 364 us; 345 for
+// an order by the true durations).  The order within a bucket — like the order of the list before — depends on timing;
+// nothing downstream depends on it.
+__global__ void __launch_bounds__(1024) k_order_tasks(const int32_t* __restrict__ in, int n, const double* __restrict__ paf, int32_t* __restrict__ out)
+{
+	__shared__ int32_t cur[256];
+	constexpr int R = 8;             // tasks per thread held in registers (8192 per launch); the rest is read again
+	constexpr int kClear = 93;       // key of paf = 3: (10 + log2 3) * 8
+	const int tid = threadIdx.x, lane = tid & 31;
+	if (tid < 256) cur[tid] = 0;
+	__syncthreads();
+	auto key_of = [&](int o) {
+		int k = (__double2hiint(paf[o]) >> 17) - ((1023 - 10) << 3);   // 2^-10 .. 2^22, eight steps per octave
+		k = k < 0 ? 0 : (k > 255 ? 255 : k);
+		return k < kClear ? k : kClear + 255 - k;
+	};
+	int ov[R], kv[R];
+#pragma unroll
+	for (int r = 0; r < R; r++) { const int i = tid + r * 1024; ov[r] = i < n ? in[i] : -1; }
+#pragma unroll
+	for (int r = 0; r < R; r++) kv[r] = ov[r] >= 0 ? key_of(ov[r]) : -1;
+#pragma unroll
+	for (int r = 0; r < R; r++) if (kv[r] >= 0) atomicAdd(&cur[kv[r]], 1);
+	for (int i = tid + R * 1024; i < n; i += 1024) atomicAdd(&cur[key_of(in[i])], 1);
+	__syncthreads();
+	if (tid < 32) {
+		int v[8], sum = 0;
+#pragma unroll
+		for (int k = 0; k < 8; k++) { v[k] = cur[lane * 8 + k]; sum += v[k]; }
+		int incl = sum;
+		for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+		int run = incl - sum;
+#pragma unroll
+		for (int k = 0; k < 8; k++) { cur[lane * 8 + k] = run; run += v[k]; }
+	}
+	__syncthreads();
+#pragma unroll
+	for (int r = 0; r < R; r++) if (kv[r] >= 0) out[atomicAdd(&cur[kv[r]], 1)] = ov[r];
+	for (int i = tid + R * 1024; i < n; i += 1024) { const int o = in[i]; out[atomicAdd(&cur[key_of(o)], 1)] = o; }
+}
+
 // Which quality characters occur in the batch's packed read stream: a 128-bit presence bitmap (counters[4..7]).
 // HBM-streaming pass (2 B per read, 16-byte loads); lets k_em pick the dense likelihood path.
 __global__ void k_qualmap(const uint16_t* __restrict__ reads, size_t n_reads, int32_t* counters)
