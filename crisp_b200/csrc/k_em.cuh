@@ -244,15 +244,23 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 				// a site are contiguous: every thread takes bins of the flat range (all loads independent, one memory latency
 				// for the site) and finds the pool of a bin in the staged offsets.
 				const uint32_t b0 = boff[0], b1 = boff[P];
-				for (uint32_t bb = b0 + tid; bb < b1; bb += blockDim.x) {
-					const uint32_t e = __ldg(b.bins + bb);
-					const int base = (e >> 8) & 3;
-					const int which = base == a1 ? 0 : (base == a2 ? 1 : -1);
-					if (which < 0) continue;
-					int lo = 0, hi = P;  // boff[lo] <= bb < boff[hi]: the last cell starting at or before bb
-					while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (boff[mid] <= bb) lo = mid; else hi = mid; }
-					const int cls = (e >> 11) & 1 ? 2 : ((e >> 10) & 1);
-					atomicAdd(dh + ((which * nq + qd[e & 0x7f]) * 3 + cls) * P + lo, e >> 16);
+				// four bins per thread and trip, loaded before any is used: a site has ~3.6 bins per thread at the benchmark
+				// shape, and one at a time the loop paid a memory latency for each
+				for (uint32_t bq = b0 + tid; bq < b1; bq += 4 * blockDim.x) {
+					uint32_t ev[4];
+#pragma unroll
+					for (int u = 0; u < 4; u++) { const uint32_t bb = bq + u * blockDim.x; ev[u] = bb < b1 ? __ldg(b.bins + bb) : 0u; }
+#pragma unroll
+					for (int u = 0; u < 4; u++) {
+						const uint32_t bb = bq + u * blockDim.x, e = ev[u];
+						const int base = (e >> 8) & 3;
+						const int which = base == a1 ? 0 : (base == a2 ? 1 : -1);
+						if (bb >= b1 || which < 0) continue;
+						int lo = 0, hi = P;  // boff[lo] <= bb < boff[hi]: the last cell starting at or before bb
+						while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (boff[mid] <= bb) lo = mid; else hi = mid; }
+						const int cls = (e >> 11) & 1 ? 2 : ((e >> 10) & 1);
+						atomicAdd(dh + ((which * nq + qd[e & 0x7f]) * 3 + cls) * P + lo, e >> 16);
+					}
 				}
 			} else
 			for (int i = warp; i < P; i += nwarps) {
@@ -658,6 +666,11 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 			if (warp == 0) {
 				double LLn = 0.0, pn = 0.0;
 				if (lane < 3) {
+					// (up to 64 pools spelled out: the general loop, unrolled by the compiler for any `rounds`, was a sixth of the
+					// instructions of this serial stretch)
+					if (rounds == 2) { LLn = part[lane * 2] + part[lane * 2 + 1]; pn = part[(3 + lane) * 2] + part[(3 + lane) * 2 + 1]; }
+					else if (rounds == 1) { LLn = part[lane]; pn = part[3 + lane]; }
+					else
 					for (int r = 0; r < rounds; r++) { LLn += part[lane * rounds + r]; pn += part[(3 + lane) * rounds + r]; }
 					pn /= c.K;
 					if (pn < kMinP) pn = kMinP;
@@ -669,6 +682,9 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 				my_LL = LLn;
 				my_p = lane < 3 ? pn : 0.5;
 				LLnull0 = 0.0;
+				if (rounds == 2) LLnull0 = part[12] + part[13];
+				else if (rounds == 1) LLnull0 = part[6];
+				else
 				for (int r = 0; r < rounds; r++) LLnull0 += part[6 * rounds + r];
 				if (countlik && lane < 3) {
 					const int k = lane;
