@@ -521,15 +521,17 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 		// =====================================================================================================
 		// EM iterations (crispEM.c:233-314)
 		// =====================================================================================================
-		// Iteration state lives in registers, replicated in every warp (lane pl holds plane pl): one barrier per
-		// iteration, after which every warp reduces the per-round partial sums in the same fixed order.
-		double my_p = sh->p[0], my_LL = 0.0, LLnull0 = 0.0;
+		// Iteration state lives in registers, replicated in every warp (lane pl holds plane pl): ONE barrier per iteration,
+		// after which every warp reduces the per-round partial sums in the same fixed order and derives the next frequencies
+		// itself (~120 instructions).  A version that left this to one warp and published the result through shared memory
+		// saved those instructions in the other five, but the five then waited at a second barrier for a dependent chain
+		// that was 45 % of the iteration's duration (task timeline, scripts/em_trace.py).  The partial sums are double
+		// buffered, so a warp that runs ahead into the next iteration does not overwrite what a slower one still reads.
+		double my_p = sh->p[0], my_LL = 0.0;
+		// log10 p (even lanes) and log10(1-p) (odd lanes) of plane lane/2; the planes start from the same frequency
+		double cur_lg = log10_fast((lane & 1) ? 1.0 - my_p : my_p);
 		int it = 0;
 		for (;;) {
-			// log10 p / log10(1-p) per plane: published in shared memory by the warp that closed the previous iteration; for the
-			// first iteration every warp takes them from the starting frequency (lane 0: p, lane 1: 1-p; the planes start equal)
-			double first_lg = 0.0;
-			if (it == 0) first_lg = log10_fast((lane & 1) ? 1.0 - my_p : my_p);
 			double* part = part_base + (it & 1) * 19 * rounds;
 			const int nunits = rounds * 3;
 			for (int u = warp; u < nunits; u += nwarps) {
@@ -542,8 +544,7 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 				const bool sum2 = NOBIDIR && pl == 0;
 				const double* Hp = (NOBIDIR ? (pl == 2 ? Gr : Gf) : G + (size_t)pl * plane) + ii;
 				const double* Hq = Gr + ii;
-				const double l0 = it == 0 ? __shfl_sync(0xffffffffu, first_lg, 0) : sh->lp[pl][0];
-				const double l1 = it == 0 ? __shfl_sync(0xffffffffu, first_lg, 1) : sh->lp[pl][1];
+				const double l0 = __shfl_sync(0xffffffffu, cur_lg, 2 * pl), l1 = __shfl_sync(0xffffffffu, cur_lg, 2 * pl + 1);
 				const double dl = l0 - l1, base = (double)n * l1;
 				// value of genotype j: H[j] + j*dl  (tag: compile-time "plane 0 of the two-plane layout")
 				auto term = [&](auto tag, const double* hp, const double* hq, int j, double jd) -> double {
@@ -659,49 +660,44 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 				}
 			}
 			__syncthreads();
-			// ---- finish the iteration: ONE warp (lane pl handles plane pl) reduces the partial sums, applies the clamps and the
-			// convergence test and publishes log10 p / log10(1-p) for the next iteration — or, on the last one, the statistics of
-			// the fit — through shared memory.  The other warps wait at the barrier below instead of repeating ~300 instructions
-			// each per iteration (a third of the EM's issue slots in the replicated version).
-			if (warp == 0) {
-				double LLn = 0.0, pn = 0.0;
-				if (lane < 3) {
-					// (up to 64 pools spelled out: the general loop, unrolled by the compiler for any `rounds`, was a sixth of the
-					// instructions of this serial stretch)
-					if (rounds == 2) { LLn = part[lane * 2] + part[lane * 2 + 1]; pn = part[(3 + lane) * 2] + part[(3 + lane) * 2 + 1]; }
-					else if (rounds == 1) { LLn = part[lane]; pn = part[3 + lane]; }
-					else
-					for (int r = 0; r < rounds; r++) { LLn += part[lane * rounds + r]; pn += part[(3 + lane) * rounds + r]; }
-					pn /= c.K;
-					if (pn < kMinP) pn = kMinP;
-					if (1.0 - pn <= kMinP) pn = 1.0 - kMinP;
-				}
-				// convergence: fabsf() of the double differences against double thresholds (crispEM.c:304)
-				const double dconv = (double)fabsf((float)(LLn - my_LL));
-				const double d0 = __shfl_sync(0xffffffffu, dconv, 0), d1 = __shfl_sync(0xffffffffu, dconv, 1), d2 = __shfl_sync(0xffffffffu, dconv, 2);
-				my_LL = LLn;
-				my_p = lane < 3 ? pn : 0.5;
-				LLnull0 = 0.0;
-				if (rounds == 2) LLnull0 = part[12] + part[13];
-				else if (rounds == 1) LLnull0 = part[6];
+			// ---- finish the iteration (every warp, lane pl handles plane pl): partial sums, clamps, convergence test ----
+			double LLn = 0.0, pn = 0.0;
+			if (lane < 3) {
+				// (up to 64 pools spelled out: the general loop, unrolled by the compiler for any `rounds`, was a sixth of the
+				// instructions of this stretch)
+				if (rounds == 2) { LLn = part[lane * 2] + part[lane * 2 + 1]; pn = part[(3 + lane) * 2] + part[(3 + lane) * 2 + 1]; }
+				else if (rounds == 1) { LLn = part[lane]; pn = part[3 + lane]; }
 				else
-				for (int r = 0; r < rounds; r++) LLnull0 += part[6 * rounds + r];
-				if (countlik && lane < 3) {
+				for (int r = 0; r < rounds; r++) { LLn += part[lane * rounds + r]; pn += part[(3 + lane) * rounds + r]; }
+				pn /= c.K;
+				if (pn < kMinP) pn = kMinP;
+				if (1.0 - pn <= kMinP) pn = 1.0 - kMinP;
+			}
+			// convergence: fabsf() of the double differences against double thresholds (crispEM.c:304)
+			const double dconv = (double)fabsf((float)(LLn - my_LL));
+			const double d0 = __shfl_sync(0xffffffffu, dconv, 0), d1 = __shfl_sync(0xffffffffu, dconv, 1), d2 = __shfl_sync(0xffffffffu, dconv, 2);
+			my_LL = LLn;
+			my_p = lane < 3 ? pn : 0.5;
+			if (countlik) {
+				double e01 = 0.0, e10 = 0.0;
+				if (lane < 3) {
 					const int k = lane;
 					double t00 = 0, t01 = 0, t10 = 0, t11 = 0;
 					for (int r = 0; r < rounds; r++) { t00 += part[(7 + k) * rounds + r]; t01 += part[(10 + k) * rounds + r]; t10 += part[(13 + k) * rounds + r]; t11 += part[(16 + k) * rounds + r]; }
-					double e01 = (t01 + 1.5 - 1) / (t01 + t00 + 1.5 + 50 - 1), e10 = (t10 + 1.5 - 1) / (t10 + t11 + 50 + 1.5 - 1);
+					e01 = (t01 + 1.5 - 1) / (t01 + t00 + 1.5 + 50 - 1);
+					e10 = (t10 + 1.5 - 1) / (t10 + t11 + 50 + 1.5 - 1);
 					if (e10 > 0.05) e10 = 0.05;
-					sh->E01[k] = e01;
-					sh->E10[k] = e10;
 				}
-				const bool stop = (it + 1 >= 2 && d0 <= 0.0001 && d1 <= 0.01 && d2 <= 0.01) || it + 1 >= 1000;
-				if (!stop) {
-					const double pp = __shfl_sync(0xffffffffu, my_p, (lane >> 1) < 3 ? (lane >> 1) : 0);
-					const double lg = log10_fast((lane & 1) ? 1.0 - pp : pp);   // lane 2 pl: log10 p, lane 2 pl + 1: log10(1-p)
-					if (lane < 6) sh->lp[lane >> 1][lane & 1] = lg;
-				} else {
+				for (int k = 0; k < 3; k++) { E01[k] = __shfl_sync(0xffffffffu, e01, k); E10[k] = __shfl_sync(0xffffffffu, e10, k); }
+			}
+			const bool stop = (it + 1 >= 2 && d0 <= 0.0001 && d1 <= 0.01 && d2 <= 0.01) || it + 1 >= 1000;
+			it++;
+			if (it == 1) stamp(4);
+			if (stop) {
+				if (warp == 0) {
 					// statistics of the fit (crispEM.c:321-349)
+					double LLnull0 = 0.0;
+					for (int r = 0; r < rounds; r++) LLnull0 += part[6 * rounds + r];
 					const double LLt = __shfl_sync(0xffffffffu, my_LL, 0), LLf = __shfl_sync(0xffffffffu, my_LL, 1), LLr = __shfl_sync(0xffffffffu, my_LL, 2);
 					const double pf = __shfl_sync(0xffffffffu, my_p, 0);
 					const double df = (LLf > LLr) ? LLf - LLt - log10(2.0) : LLr - LLt - log10(2.0);
@@ -710,23 +706,21 @@ __global__ void __maxnreg__(NOBIDIR ? 80 : 96) k_em(EngineParams prm, const int3
 					double LL = LLt + log10_fast(ALPHA);
 					if (LLrefadd < LL) LL += log10_fast(1.0 + exp10(LLrefadd - LL));
 					else LL = LLrefadd + log10_fast(1.0 + exp10(LL - LLrefadd));
-					if (lane == 0) { sh->delta = LL - LLrefadd; sh->deltaf = df; sh->p[0] = pf; sh->hwe = 0.0; sh->iter = it + 1; }
+					if (lane == 0) { sh->delta = LL - LLrefadd; sh->deltaf = df; sh->p[0] = pf; sh->hwe = 0.0; }
 				}
-				if (lane == 0) sh->exitflag = stop ? 1 : 0;
+				if (countlik) count_likelihood();  // crispEM.c:298, also on the exit iteration
+				break;
 			}
-			__syncthreads();
-			it++;
-			if (it == 1) stamp(4);
-			if (countlik) {
-				for (int k = 0; k < 3; k++) { E01[k] = sh->E01[k]; E10[k] = sh->E10[k]; }
-				count_likelihood();  // crispEM.c:298, also on the exit iteration
+			{
+				const double pp = __shfl_sync(0xffffffffu, my_p, (lane >> 1) < 3 ? (lane >> 1) : 0);
+				cur_lg = log10_fast((lane & 1) ? 1.0 - pp : pp);   // lane 2 pl: log10 p, lane 2 pl + 1: log10(1-p)
 			}
-			if (sh->exitflag) break;
+			if (countlik) count_likelihood();  // crispEM.c:298 (ends on a barrier: the planes are rebuilt before the next units read them)
 		}
+		__syncthreads();  // the statistics of the fit, written by warp 0
 		stamp(5);
 		// (the planes were last read before the barriers that closed the final iteration: the genotype phase may overwrite them)
 		const double delta = sh->delta, deltaf = sh->deltaf, pfin = sh->p[0];
-		it = sh->iter;
 		const bool called = delta >= 2;
 		int varpools = 0;
 		if (called) {
