@@ -181,3 +181,14 @@ def test_results_pack_unpack_round_trip():
     assert eb.n_sites == 0 and ei.size == 0
     merged = merge_results([back, eb], [np.arange(n), ei], n, P)
     assert np.array_equal(merged.delta, r.delta) and merged.n_calls == calls
+
+
+def test_em_trace_report_reads_the_committed_timeline():
+    """scripts/em_trace.py on the task timeline committed under profiles/r2 (CRISPGPU_EM_TRACE of one k_em launch at the
+    benchmark shape): the parser, the phase table and the schedule simulation run, and the figures DESIGN.md quotes hold."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "em_trace.py"), os.path.join(root, "profiles", "r2", "em_trace_final.bin")],
+                         capture_output=True, text=True, check=True).stdout
+    assert "tasks 5271" in out and "planes (DMMA)" in out and "makespan" in out
+    busy = float(out.split("busy task-time / (span x concurrent) = ")[1].split(";")[0])
+    assert 0.85 < busy < 0.95
