@@ -38,11 +38,13 @@ VCFLIB = os.path.join(CSRC, "libcrispvcf.so")
 
 
 def build_vcf_writer(force: bool = False) -> str:
-    """host/vcf_writer.c (batch VCF record formatter, plain C with pthreads) -> csrc/libcrispvcf.so."""
-    src = [os.path.join(HOST, "vcf_writer.c"), os.path.join(HOST, "vcf_writer.h"), os.path.join(HERE, "..", "include", "crispgpu.h")]
+    """host/vcf_writer.c (batch VCF record formatter) + host/vcf_post.c (pooled-count -> genotype conversion, BGZF output), plain C
+    with pthreads and zlib -> csrc/libcrispvcf.so."""
+    src = [os.path.join(HOST, "vcf_writer.c"), os.path.join(HOST, "vcf_post.c"), os.path.join(HOST, "vcf_writer.h"), os.path.join(HOST, "vcf_post.h"),
+           os.path.join(HERE, "..", "include", "crispgpu.h")]
     if not force and os.path.exists(VCFLIB) and all(os.path.getmtime(f) <= os.path.getmtime(VCFLIB) for f in src):
         return VCFLIB
-    cmd = [os.environ.get("CC", "gcc"), "-O2", "-std=gnu99", "-Wall", "-fPIC", "-shared", "-o", VCFLIB, src[0], "-lpthread"]
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-std=gnu99", "-Wall", "-fPIC", "-shared", "-o", VCFLIB, src[0], src[1], "-lpthread", "-lz"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

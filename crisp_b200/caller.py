@@ -20,7 +20,7 @@ import numpy as np
 from .abi import EngineConfig
 from .engine import Engine
 from .pileup import decode_bams, make_window, read_fasta
-from .vcf import format_records
+from .vcf import bgzf_compress, expand_genotypes, format_records
 
 _INFO = [("NP", "1", "Integer", "pools with data"), ("DP", ".", "Integer", "filtered reads on the forward strand, reverse strand and from both mates, all pools"),
          ("CT", ".", "Float", "log10 contingency-table p-value per ALT allele"), ("AC", ".", "Integer", "estimated allele count over all pools per ALT allele"),
@@ -58,9 +58,10 @@ _ARENA = {}   # the last call's pinned alignment arrays, taken over by the next 
 
 
 def call_bams(bams, fasta: str, poolsize: int, out_vcf: str | None = None, options: dict | None = None, window: int = 1 << 20, threads: int | None = None,
-              device: int = 0, min_mapq: int = 20, tid: int = 0) -> dict:
+              device: int = 0, min_mapq: int = 20, tid: int = 0, expand_gt: bool = False) -> dict:
     """Call the first reference sequence of `fasta` from one BAM per pool.  Returns timings, counts and (when out_vcf is None)
-    the VCF body."""
+    the VCF body.  `out_vcf` ending in .gz is written as BGZF (what bgzip writes); `expand_gt` writes pooled genotypes as
+    pool-size allele lists ("0/0/0/1") the way scripts/convert_pooled_vcf.py converts them (host/vcf_post.c)."""
     options = dict(options or {})
     threads = threads or os.cpu_count() or 1
     t0 = time.perf_counter()
@@ -100,10 +101,11 @@ def call_bams(bams, fasta: str, poolsize: int, out_vcf: str | None = None, optio
         out = dict(decode_s=t1 - t0, fasta_s=t2 - t1, engine_create_s=t3 - t2, device_s=t_dev, format_s=t_fmt, candidate_sites=n_sites, records=n_records,
                    alignments=aln.n_reads, positions=L, decode_stats=aln.stats)
         if out_vcf:
+            text = vcf_header(bams, fasta, poolsize, cfg.options) + b"".join(body)
+            if expand_gt and poolsize != 2:   # genotypes of pool-size alleles instead of allele counts (scripts/convert_pooled_vcf.py);
+                text, out["expand_stats"] = expand_genotypes(text, poolsize=poolsize)   # diploid output carries GT already
             with open(out_vcf, "wb") as f:
-                f.write(vcf_header(bams, fasta, poolsize, cfg.options))
-                for t in body:
-                    f.write(t)
+                f.write(bgzf_compress(text, threads=threads) if out_vcf.endswith(".gz") else text)   # .gz: BGZF, as bgzip writes it
         else:
             out["vcf_body"] = b"".join(body)
         out["wall_s"] = time.perf_counter() - t0   # BAM files read to VCF file written

@@ -28,6 +28,11 @@ class CVcfOptions(C.Structure):
     _fields_ = [("ploidy", C.c_void_p), ("em_flag", C.c_int32), ("varpoolsize", C.c_int32), ("threads", C.c_int32), ("reserved", C.c_int32)]
 
 
+class CExpandStats(C.Structure):
+    _fields_ = [("n_header_lines", C.c_int64), ("n_records_in", C.c_int64), ("n_records_out", C.c_int64), ("n_multiallelic_indel", C.c_int64),
+                ("n_over_poolsize", C.c_int64)]
+
+
 _lib = None
 
 
@@ -42,6 +47,13 @@ def load_vcf_library() -> C.CDLL:
         lib.crisp_vcf_format.restype = C.c_int
         lib.crisp_vcf_free.argtypes = [C.c_void_p]
         lib.crisp_vcf_free.restype = None
+        lib.crisp_vcf_expand_genotypes.argtypes = [C.c_char_p, C.c_size_t, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                                   C.POINTER(CExpandStats)]
+        lib.crisp_vcf_expand_genotypes.restype = C.c_int
+        lib.crisp_bgzf_compress.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        lib.crisp_bgzf_compress.restype = C.c_int
+        lib.crisp_vcf_post_free.argtypes = [C.c_void_p]
+        lib.crisp_vcf_post_free.restype = None
         _lib = lib
     return _lib
 
@@ -84,3 +96,34 @@ def format_records(sites, res: Results, ploidy, chrom: str, refseq: np.ndarray, 
     finally:
         lib.crisp_vcf_free(out)
         del keep
+
+
+def expand_genotypes(vcf: bytes, poolsize: int | None = None, pool_sizes=None) -> tuple[bytes, dict]:
+    """A pooled CRISP VCF with the per-pool allele counts of its first FORMAT field written out as genotypes of pool-size
+    alleles ("0/0/0/1", key GT) — what scripts/convert_pooled_vcf.py does so that standard tools read the file; host/vcf_post.c.
+    One pool size for all (`poolsize`: the counts are those of the ALT alleles) or one per pool (`pool_sizes`: the counts
+    include the reference allele first).  Returns (text, counters of what was read, written and left out)."""
+    lib = load_vcf_library()
+    ps = None if pool_sizes is None else np.ascontiguousarray(pool_sizes, np.int32)
+    out, n, st = C.c_void_p(), C.c_size_t(0), CExpandStats()
+    rc = lib.crisp_vcf_expand_genotypes(vcf, len(vcf), int(poolsize) if poolsize else -1, None if ps is None else ps.ctypes.data, 0 if ps is None else ps.shape[0],
+                                        C.byref(out), C.byref(n), C.byref(st))
+    if rc != 0:
+        raise ValueError(f"crisp_vcf_expand_genotypes failed: status {rc}" + (" (no pool size given, a malformed record, or a count that is not a number)" if rc == -1 else ""))
+    try:
+        return C.string_at(out, n.value), {k: getattr(st, k) for k, _ in CExpandStats._fields_}
+    finally:
+        lib.crisp_vcf_post_free(out)
+
+
+def bgzf_compress(data: bytes, level: int = -1, threads: int | None = None) -> bytes:
+    """`data` as BGZF (what bgzip writes: tabix/bcftools read it, and so does gzip), blocks deflated on host threads."""
+    lib = load_vcf_library()
+    out, n = C.c_void_p(), C.c_size_t(0)
+    rc = lib.crisp_bgzf_compress(data, len(data), level, threads or min(16, os.cpu_count() or 1), C.byref(out), C.byref(n))
+    if rc != 0:
+        raise RuntimeError(f"crisp_bgzf_compress failed: status {rc}")
+    try:
+        return C.string_at(out, n.value)
+    finally:
+        lib.crisp_vcf_post_free(out)
