@@ -168,3 +168,42 @@ def test_bgzf_output_is_read_by_the_bam_decoder_indexer():
         a, b = decode_bams(ds["bams"], tid=0, threads=2, pinned=False), decode_bams(paths, tid=0, threads=2, pinned=False)
         assert a.n_reads == b.n_reads and a.n_reads > 0
         assert np.array_equal(a.rec, b.rec) and np.array_equal(a.seq4[:a.n_bases // 2], b.seq4[:b.n_bases // 2])
+
+
+def test_call_bams_output_forms_with_the_device_stubbed(tmp_path, monkeypatch):
+    """The file-writing end of crisp_b200.caller.call_bams (plain, BGZF, genotype lists) on the CPU: decode is the real one into
+    pageable memory, the engine and the record formatter are stand-ins (the real chain is tests/test_pileup.py, GPU)."""
+    import types
+    import crisp_b200.caller as caller
+    from crisp_b200 import pileup
+    from crisp_b200.bamsynth import make_dataset
+
+    class StubEngine:
+        def __init__(self, cfg, device=0): pass
+        def pileup_upload(self, aln, win): pass
+        def pileup_set_window(self, win): pass
+        def pileup_run_resident(self, fetch=True): return types.SimpleNamespace(n_sites=2), None
+        def close(self): pass
+
+    rec = b"chr1\t100\t.\tA\tG\t312\tPASS\tNP=2\tAC:GQ:DP\t1:33:60\t0:50:58\nchr1\t200\t.\tC\tT\t90\tPASS\tNP=2\tAC:GQ:DP\t4:20:60\t.:0:0\n"
+    real_decode = pileup.decode_bams
+    monkeypatch.setattr(caller, "decode_bams", lambda bams, tid=0, threads=None, reuse=None: real_decode(bams, tid=tid, threads=threads, pinned=False))
+    monkeypatch.setattr(caller, "Engine", StubEngine)
+    monkeypatch.setattr(caller, "format_records", lambda *a, **k: rec)
+    monkeypatch.setattr(caller, "_ARENA", {})
+    ds = make_dataset(str(tmp_path), pools=2, poolsize=4, length=3000, depth=8, seed=2)
+    texts = {}
+    for name, kw in (("a.vcf", {}), ("b.vcf.gz", {}), ("c.vcf.gz", dict(expand_gt=True)), ("d.vcf", dict(expand_gt=True))):
+        p = str(tmp_path / name)
+        r = caller.call_bams(ds["bams"], ds["fasta"], 4, out_vcf=p, threads=2, **kw)
+        raw = open(p, "rb").read()
+        if name.endswith(".gz"):
+            _bgzf_blocks(raw)
+            raw = gzip.decompress(raw)
+        texts[name] = raw
+        assert r["records"] == 2 and ("expand_stats" in r) == bool(kw)
+    assert texts["a.vcf"] == texts["b.vcf.gz"] and texts["c.vcf.gz"] == texts["d.vcf"]
+    assert texts["a.vcf"].endswith(rec) and texts["a.vcf"].startswith(b"##fileformat=VCF")
+    assert texts["d.vcf"] == expand_genotypes(texts["a.vcf"], poolsize=4)[0]
+    assert b"\tGT:GQ:DP\t0/0/0/1:33:60\t0/0/0/0:50:58\n" in texts["d.vcf"] and b"\t1/1/1/1:20:60\t./././.:0:0\n" in texts["d.vcf"]
+    assert caller.call_bams(ds["bams"], ds["fasta"], 4, threads=2)["vcf_body"] == rec
