@@ -58,14 +58,16 @@ _ARENA = {}   # the last call's pinned alignment arrays, taken over by the next 
 
 
 def call_bams(bams, fasta: str, poolsize: int, out_vcf: str | None = None, options: dict | None = None, window: int = 1 << 20, threads: int | None = None,
-              device: int = 0, min_mapq: int = 20, tid: int = 0, expand_gt: bool = False) -> dict:
+              device: int = 0, min_mapq: int = 20, tid: int = 0, expand_gt: bool = False, region: tuple[int, int] | None = None) -> dict:
     """Call the first reference sequence of `fasta` from one BAM per pool.  Returns timings, counts and (when out_vcf is None)
     the VCF body.  `out_vcf` ending in .gz is written as BGZF (what bgzip writes); `expand_gt` writes pooled genotypes as
-    pool-size allele lists ("0/0/0/1") the way scripts/convert_pooled_vcf.py converts them (host/vcf_post.c)."""
+    pool-size allele lists ("0/0/0/1") the way scripts/convert_pooled_vcf.py converts them (host/vcf_post.c).  `region` =
+    (start, end), 0-based half-open: only sites in it are called — the reference's --regions; the decoder reaches it through
+    the BAI index when the files have one, so shards of a chromosome can run as separate processes (one per GPU)."""
     options = dict(options or {})
     threads = threads or os.cpu_count() or 1
     t0 = time.perf_counter()
-    aln = decode_bams(bams, tid=tid, threads=threads, reuse=_ARENA.pop("aln", None))
+    aln = decode_bams(bams, tid=tid, threads=threads, reuse=_ARENA.pop("aln", None), **({} if region is None else dict(start=int(region[0]), end=int(region[1]))))
     t1 = time.perf_counter()
     ref = read_fasta(fasta)
     L = ref.shape[0]
@@ -81,12 +83,13 @@ def call_bams(bams, fasta: str, poolsize: int, out_vcf: str | None = None, optio
         # the region's alignments and reference go to the device once; the windows are called on them where they lie
         window = max(1, min(window, max(65536, (2 << 30) // (32 * P))))   # the window's count table: 32 B per position and pool
         ta = time.perf_counter()
-        eng.pileup_upload(aln, make_window(tid, 0, min(L, window), ref, min_mapq=min_mapq))
+        r0, r1 = (0, L) if region is None else (max(0, int(region[0])), min(L, int(region[1])))
+        eng.pileup_upload(aln, make_window(tid, r0, min(r1, r0 + window), ref, min_mapq=min_mapq))
         t_dev += time.perf_counter() - ta
-        for start in range(0, L, window):
-            end = min(L, start + window)
+        for start in range(r0, r1, window):
+            end = min(r1, start + window)
             ta = time.perf_counter()
-            if start:
+            if start != r0:
                 eng.pileup_set_window(make_window(tid, start, end, None, min_mapq=min_mapq))
             sites, res = eng.pileup_run_resident(fetch=True)
             tb = time.perf_counter()

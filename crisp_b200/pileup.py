@@ -43,7 +43,7 @@ class CPileupSites(C.Structure):
 
 class CBamOptions(C.Structure):
     _fields_ = [("tid", C.c_int32), ("start", C.c_int32), ("end", C.c_int32), ("filter_mask", C.c_uint32), ("threads", C.c_int32),
-                ("paired", C.c_int32), ("reuse", C.c_int32), ("alloc", C.c_void_p), ("release", C.c_void_p)]
+                ("paired", C.c_int32), ("reuse", C.c_int32), ("use_index", C.c_int32), ("reserved", C.c_int32), ("alloc", C.c_void_p), ("release", C.c_void_p)]
 
 
 class CBamReads(C.Structure):
@@ -112,12 +112,14 @@ class _DecodedOwner:
 
 
 def decode_bams(paths, tid: int = 0, start: int = 0, end: int = 2**31 - 1, threads: int | None = None, paired: bool = False,
-                pinned: bool = True, filter_mask: int = BAM_FILTER_MASK, allow_complex: bool = False, reuse: Alignments | None = None) -> Alignments:
+                pinned: bool = True, filter_mask: int = BAM_FILTER_MASK, allow_complex: bool = False, reuse: Alignments | None = None,
+                use_index: bool = True) -> Alignments:
     """Decode one coordinate-sorted BAM per pool into an `Alignments` set (alignments overlapping [start, end) of reference
     `tid`).  Raises when the files hold alignments outside the device pileup's scope (CIGARs with gaps) unless
     `allow_complex` (they are then dropped and counted in stats['n_complex']).  `reuse`: an earlier result of this function
     (same `pinned`) whose arrays are taken over when large enough — pinning memory costs more than decoding into it; that
-    earlier object must not be used afterwards."""
+    earlier object must not be used afterwards.  `use_index`: a region is reached through the BAI index next to each file
+    (x.bam.bai or x.bai) when there is one — only the blocks it names are inflated; the result is the same without."""
     lib = load_bam_library()
     alloc = release = None
     if pinned:
@@ -131,7 +133,7 @@ def decode_bams(paths, tid: int = 0, start: int = 0, end: int = 2**31 - 1, threa
         C.memmove(C.byref(out), C.byref(reuse._owner.reads), C.sizeof(CBamReads))
         reuse._owner.reads = CBamReads()   # ownership moves to this call
         reuse.rec = reuse.seq4 = reuse.qual = reuse.pool_off = None
-    opt = CBamOptions(tid, start, end, filter_mask, threads or (os.cpu_count() or 1), 1 if paired else 0, 1 if taking else 0, alloc, release)
+    opt = CBamOptions(tid, start, end, filter_mask, threads or (os.cpu_count() or 1), 1 if paired else 0, 1 if taking else 0, 1 if use_index else 0, 0, alloc, release)
     arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
     rc = lib.crisp_bam_decode(arr, len(paths), C.byref(opt), C.byref(out))
     if rc != 0:

@@ -29,6 +29,10 @@ typedef struct crisp_bam_options {
 	int32_t paired;         /* 1: also fill mate_pos / isize */
 	int32_t reuse;          /* 1: `out` holds the arrays of an earlier call (same allocator): they are used again when large
 	                           enough — pinning memory costs more than decoding into it — and whatever viewed them is overwritten */
+	int32_t use_index;      /* 1: with a region (tid >= 0 and start/end narrower than everything) and a BAI index next to a file
+	                           (x.bam.bai or x.bai), only the blocks the index names for the region are inflated; without an
+	                           index, or with one that does not fit the file, the whole file is decoded and filtered as before */
+	int32_t reserved;
 	void* (*alloc)(size_t);     /* allocator of the output arrays (NULL: malloc) */
 	void (*release)(void*);     /* its counterpart (NULL: free) */
 } crisp_bam_options;

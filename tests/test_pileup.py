@@ -125,6 +125,62 @@ def test_decoder_region_and_flag_filter(tmp_path):
     assert decode_bams(ds["bams"], pinned=False, tid=3).n_reads == 0
 
 
+def _same_alignments(a, b):
+    assert np.array_equal(a.pool_off, b.pool_off)
+    for k in ("pos", "clip", "mlen", "mapq", "strand"):
+        assert np.array_equal(a.rec[k], b.rec[k]), k
+    for j in range(a.n_reads):
+        oa, ob, n = int(a.rec["base_off"][j]), int(b.rec["base_off"][j]), int(a.rec["clip"][j]) + int(a.rec["mlen"][j])
+        assert np.array_equal(a.qual[oa:oa + n], b.qual[ob:ob + n]) and np.array_equal(a.seq4[oa // 2:(oa + n + 1) // 2], b.seq4[ob // 2:(ob + n + 1) // 2])
+
+
+def test_decoder_reaches_a_region_through_the_bai_index(tmp_path):
+    """With a BAI index next to the files (built by the reference's own samtools, oracle/_ref/bamtool) a region decode inflates
+    only the blocks the index names and returns exactly what the whole-file decode filtered to the region returns."""
+    from crisp_b200 import frontend as fe
+    bamtool = os.path.join(ROOT, "oracle", "_ref", "bamtool")
+    if not os.path.exists(bamtool):
+        pytest.skip("oracle/_ref/bamtool not built (needs /root/reference)")
+    ds = make_dataset(str(tmp_path), pools=3, poolsize=8, length=120000, depth=12, seed=16)
+    whole = decode_bams(ds["bams"], pinned=False, threads=2)
+    assert whole.stats["inflated_bytes"] > 40 * 65280      # dozens of BGZF blocks per pool
+    fe.index_bams(bamtool, ds)
+    assert all(os.path.exists(b + ".bai") for b in ds["bams"])
+    rng = np.random.default_rng(4)
+    regions = [(0, 500), (0, 120000), (119000, 2**31 - 1), (60000, 60001), (16383, 16385), (32768, 49152)] + \
+              [tuple(sorted(int(x) for x in rng.integers(0, 120000, 2))) for _ in range(12)]
+    for start, end in regions:
+        if end == start:
+            end += 1
+        plain = decode_bams(ds["bams"], pinned=False, threads=2, tid=0, start=start, end=end, use_index=False)
+        fast = decode_bams(ds["bams"], pinned=False, threads=2, tid=0, start=start, end=end)
+        _same_alignments(plain, fast)
+        assert fast.stats["inflated_bytes"] <= plain.stats["inflated_bytes"]
+        if end - start < 20000:
+            assert fast.stats["inflated_bytes"] < plain.stats["inflated_bytes"] // 2, (start, end, fast.stats["inflated_bytes"])
+        assert fast.stats["first_ref_name"] == plain.stats["first_ref_name"] and fast.stats["n_refs"] == plain.stats["n_refs"]
+    # a region on a reference the files do not have, and one past the end of the data
+    assert decode_bams(ds["bams"], pinned=False, tid=5, start=10, end=20).n_reads == 0
+    assert decode_bams(ds["bams"], pinned=False, tid=0, start=10**8, end=10**8 + 5).n_reads == 0
+    # the index of another file, a truncated one and garbage are ignored (whole-file decode), not trusted
+    other = make_dataset(str(tmp_path / "other"), pools=1, poolsize=8, length=30000, depth=30, seed=17)
+    fe.index_bams(bamtool, other)
+    want = decode_bams(ds["bams"], pinned=False, tid=0, start=70000, end=71000, use_index=False)
+    for bad in (open(other["bams"][0] + ".bai", "rb").read(), open(ds["bams"][0] + ".bai", "rb").read()[:40], b"BAI\x01" + bytes(range(200)), b"hello"):
+        for b in ds["bams"]:
+            open(b + ".bai", "wb").write(bad)
+        _same_alignments(want, decode_bams(ds["bams"], pinned=False, tid=0, start=70000, end=71000))
+    # x.bai beside x.bam is found as well
+    for b in ds["bams"]:
+        os.remove(b + ".bai")
+    fe.index_bams(bamtool, ds)
+    for b in ds["bams"]:
+        os.rename(b + ".bai", b[:-4] + ".bai")
+    got = decode_bams(ds["bams"], pinned=False, tid=0, start=70000, end=71000)
+    _same_alignments(want, got)
+    assert got.stats["inflated_bytes"] < want.stats["inflated_bytes"] // 2
+
+
 def test_decoder_rejects_corrupt_files(tmp_path):
     ds = make_dataset(str(tmp_path), pools=1, poolsize=4, length=3000, depth=5, seed=2)
     raw = bytearray(open(ds["bams"][0], "rb").read())

@@ -187,7 +187,13 @@ def test_call_bams_output_forms_with_the_device_stubbed(tmp_path, monkeypatch):
 
     rec = b"chr1\t100\t.\tA\tG\t312\tPASS\tNP=2\tAC:GQ:DP\t1:33:60\t0:50:58\nchr1\t200\t.\tC\tT\t90\tPASS\tNP=2\tAC:GQ:DP\t4:20:60\t.:0:0\n"
     real_decode = pileup.decode_bams
-    monkeypatch.setattr(caller, "decode_bams", lambda bams, tid=0, threads=None, reuse=None: real_decode(bams, tid=tid, threads=threads, pinned=False))
+    decoded = []
+
+    def decode(bams, tid=0, threads=None, reuse=None, **kw):
+        decoded.append(kw)
+        return real_decode(bams, tid=tid, threads=threads, pinned=False, **kw)
+
+    monkeypatch.setattr(caller, "decode_bams", decode)
     monkeypatch.setattr(caller, "Engine", StubEngine)
     monkeypatch.setattr(caller, "format_records", lambda *a, **k: rec)
     monkeypatch.setattr(caller, "_ARENA", {})
@@ -207,3 +213,12 @@ def test_call_bams_output_forms_with_the_device_stubbed(tmp_path, monkeypatch):
     assert texts["d.vcf"] == expand_genotypes(texts["a.vcf"], poolsize=4)[0]
     assert b"\tGT:GQ:DP\t0/0/0/1:33:60\t0/0/0/0:50:58\n" in texts["d.vcf"] and b"\t1/1/1/1:20:60\t./././.:0:0\n" in texts["d.vcf"]
     assert caller.call_bams(ds["bams"], ds["fasta"], 4, threads=2)["vcf_body"] == rec
+    # a region: the decoder is asked for it, and the windows cover it and nothing else
+    windows = []
+    monkeypatch.setattr(caller, "make_window", lambda tid, start, end, ref, **kw: windows.append((start, end)) or (start, end))
+    whole = caller.call_bams(ds["bams"], ds["fasta"], 4, threads=2, window=1000)
+    assert windows == [(0, 1000), (1000, 2000), (2000, 3000)] and decoded[-1] == {}
+    del windows[:]
+    part = caller.call_bams(ds["bams"], ds["fasta"], 4, threads=2, window=1000, region=(500, 2200))
+    assert windows == [(500, 1500), (1500, 2200)] and decoded[-1] == dict(start=500, end=2200)
+    assert 0 < part["alignments"] < whole["alignments"]
